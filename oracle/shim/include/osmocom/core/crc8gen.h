@@ -1,0 +1,1 @@
+#include <osmocom/core/crcgen.h>

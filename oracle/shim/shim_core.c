@@ -1,0 +1,372 @@
+/* oracle shim: libosmocore functions the reference's src/l1 and src/gmr1_rx.c call.
+ *
+ * TEST INFRASTRUCTURE ONLY - never linked into the product library.
+ *
+ * libosmocore is a third-party dependency that is NOT vendored under /root/reference
+ * (configure.ac:23 pins it only as ">= 0.4.1").  What follows restates its published
+ * generic algorithms; the reference has no tests or golden
+ * vectors for this boundary, so PARITY IS UNPINNED here and this file is normative for
+ * the repo.  Call sites in the reference: osmo_conv_decode at src/l1/bcch.c:94, ccch.c:98,
+ * facch3.c:160, facch9.c:134, tch3.c:174, tch9.c:170, rach.c:167, xch_dc12.c:97.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdint.h>
+
+#include <osmocom/core/bits.h>
+#include <osmocom/core/conv.h>
+#include <osmocom/core/crcgen.h>
+#include <osmocom/core/utils.h>
+#include <osmocom/core/msgb.h>
+#include <osmocom/core/gsmtap_util.h>
+
+/* ---------------------------------------------------------------- bits.h */
+
+static inline int bitnum(unsigned int pos, int lsb_mode)
+{
+	return lsb_mode ? (pos & 7) : (7 - (pos & 7));
+}
+
+int osmo_pbit2ubit_ext(ubit_t *out, unsigned int out_ofs, const pbit_t *in, unsigned int in_ofs,
+                       unsigned int num_bits, int lsb_mode)
+{
+	unsigned int i;
+	for (i = 0; i < num_bits; i++) {
+		unsigned int ip = in_ofs + i;
+		out[out_ofs + i] = (in[ip >> 3] >> bitnum(ip, lsb_mode)) & 1;
+	}
+	return out_ofs + num_bits;
+}
+
+int osmo_ubit2pbit_ext(pbit_t *out, unsigned int out_ofs, const ubit_t *in, unsigned int in_ofs,
+                       unsigned int num_bits, int lsb_mode)
+{
+	unsigned int i;
+	for (i = 0; i < num_bits; i++) {
+		unsigned int op = out_ofs + i;
+		uint8_t m = 1 << bitnum(op, lsb_mode);
+		if (in[in_ofs + i])
+			out[op >> 3] |= m;
+		else
+			out[op >> 3] &= ~m;
+	}
+	return ((out_ofs + num_bits - 1) >> 3) + 1;
+}
+
+int osmo_pbit2ubit(ubit_t *out, const pbit_t *in, unsigned int num_bits)
+{
+	return osmo_pbit2ubit_ext(out, 0, in, 0, num_bits, 0);
+}
+
+/* MSB first; whole output bytes are zero-filled before bits are set */
+int osmo_ubit2pbit(pbit_t *out, const ubit_t *in, unsigned int num_bits)
+{
+	unsigned int nbytes = (num_bits + 7) >> 3;
+	memset(out, 0x00, nbytes);
+	osmo_ubit2pbit_ext(out, 0, in, 0, num_bits, 0);
+	return nbytes;
+}
+
+/* ---------------------------------------------------------------- crcgen */
+
+#define CRCGEN_IMPL(NAME, T)                                                             \
+T NAME##_compute_bits(const struct NAME##_code *c, const ubit_t *in, int len)            \
+{                                                                                        \
+	const uint32_t mask = (1u << c->bits) - 1, top = 1u << (c->bits - 1);            \
+	uint32_t crc = c->init;                                                          \
+	int i;                                                                           \
+	for (i = 0; i < len; i++) {                                                      \
+		uint32_t bit = in[i] & 1;                                                \
+		crc ^= bit << (c->bits - 1);                                             \
+		if (crc & top) { crc <<= 1; crc ^= c->poly; }                            \
+		else           { crc <<= 1; }                                            \
+	}                                                                                \
+	crc &= mask;                                                                     \
+	return (T)crc;                                                                   \
+}                                                                                        \
+int NAME##_check_bits(const struct NAME##_code *c, const ubit_t *in, int len,            \
+                      const ubit_t *crc_bits)                                            \
+{                                                                                        \
+	uint32_t crc = NAME##_compute_bits(c, in, len);                                  \
+	int i;                                                                           \
+	for (i = 0; i < c->bits; i++)                                                    \
+		if (crc_bits[i] ^ (((crc ^ c->remainder) >> (c->bits - i - 1)) & 1))     \
+			return 1;                                                        \
+	return 0;                                                                        \
+}                                                                                        \
+void NAME##_set_bits(const struct NAME##_code *c, const ubit_t *in, int len,             \
+                     ubit_t *crc_bits)                                                   \
+{                                                                                        \
+	uint32_t crc = NAME##_compute_bits(c, in, len);                                  \
+	int i;                                                                           \
+	for (i = 0; i < c->bits; i++)                                                    \
+		crc_bits[i] = ((crc ^ c->remainder) >> (c->bits - i - 1)) & 1;           \
+}
+
+CRCGEN_IMPL(osmo_crc8gen, uint8_t)
+CRCGEN_IMPL(osmo_crc16gen, uint16_t)
+
+/* ---------------------------------------------------------------- conv.h */
+
+#define MAX_AE 0x00ffffff
+
+int osmo_conv_get_input_length(const struct osmo_conv_code *code, int len)
+{
+	return len <= 0 ? code->len : len;
+}
+
+int osmo_conv_get_output_length(const struct osmo_conv_code *code, int len)
+{
+	int pbits, out_len;
+
+	out_len = osmo_conv_get_input_length(code, len) * code->N;
+	if (code->term == CONV_TERM_FLUSH)
+		out_len += code->N * (code->K - 1);
+	if (code->puncture) {
+		for (pbits = 0; code->puncture[pbits] >= 0; pbits++);
+		out_len -= pbits;
+	}
+	return out_len;
+}
+
+/* -- encoder: state 0 (tail-biting: pre-loaded with the last K-1 input bits), output bits
+ *    emitted MSB (bit N-1) first, positions in the puncture list skipped, FLUSH appends K-1
+ *    zero inputs */
+int osmo_conv_encode(const struct osmo_conv_code *code, const ubit_t *input, ubit_t *output)
+{
+	int i, j, o_idx = 0, p_idx = 0, steps = code->len;
+	uint8_t state = 0;
+
+	if (code->term == CONV_TERM_TAIL_BITING)
+		for (i = 0; i < code->K - 1; i++)
+			state = (state << 1) | input[code->len - code->K + 1 + i];
+	if (code->term == CONV_TERM_FLUSH)
+		steps += code->K - 1;
+
+	for (i = 0; i < steps; i++) {
+		int flush = (i >= code->len);
+		uint8_t bit = flush ? 0 : input[i], ov;
+
+		if (flush && code->next_term_output) {
+			ov    = code->next_term_output[state];
+			state = code->next_term_state[state];
+		} else {
+			ov    = code->next_output[state][bit];
+			state = code->next_state[state][bit];
+		}
+
+		for (j = code->N - 1; j >= 0; j--) {
+			int idx = i * code->N + (code->N - 1 - j);
+			if (code->puncture && idx == code->puncture[p_idx]) {
+				p_idx++;
+				continue;
+			}
+			output[o_idx++] = (ov >> j) & 1;
+		}
+	}
+	return o_idx;
+}
+
+struct vdec {
+	const struct osmo_conv_code *code;
+	int n_states, o_idx, p_idx;
+	unsigned int *ae, *ae_next;
+	uint8_t *state_history;
+};
+
+/* one trellis step; `flush` restricts to the 0-input branch (or the next_term_* tables) */
+static int vdec_step(struct vdec *d, const sbit_t *input, int i_idx, int flush)
+{
+	const struct osmo_conv_code *code = d->code;
+	const int ns = d->n_states, N = code->N;
+	sbit_t in_sym[16];
+	int s, b, j;
+
+	for (s = 0; s < ns; s++)
+		d->ae_next[s] = MAX_AE;
+
+	for (j = 0; j < N; j++) {
+		int idx = d->o_idx * N + j;
+		if (code->puncture && idx == code->puncture[d->p_idx]) {
+			in_sym[j] = 0;
+			d->p_idx++;
+		} else {
+			in_sym[j] = input[i_idx++];
+		}
+	}
+
+	for (s = 0; s < ns; s++) {
+		for (b = 0; b < (flush ? 1 : 2); b++) {
+			int nae, ov, state;
+			uint8_t m;
+
+			if (flush && code->next_term_output) {
+				ov    = code->next_term_output[s];
+				state = code->next_term_state[s];
+			} else {
+				ov    = code->next_output[s][b];
+				state = code->next_state[s][b];
+			}
+
+			nae = d->ae[s];
+			m = 1 << (N - 1);
+			for (j = 0; j < N; j++) {
+				int is = (int)in_sym[j];
+				if (is) {
+					int ov_sym = (ov & m) ? -127 : 127;
+					nae += ((is - ov_sym) * (is - ov_sym)) >> 9;
+				}
+				m >>= 1;
+			}
+
+			if (d->ae_next[state] > (unsigned int)nae) {
+				d->ae_next[state] = nae;
+				d->state_history[ns * d->o_idx + state] = s;
+			}
+		}
+	}
+
+	memcpy(d->ae, d->ae_next, sizeof(unsigned int) * ns);
+	d->o_idx++;
+	return i_idx;
+}
+
+int osmo_conv_decode(const struct osmo_conv_code *code, const sbit_t *input, ubit_t *output)
+{
+	struct vdec d;
+	const int ns = 1 << (code->K - 1);
+	const int has_flush = (code->term == CONV_TERM_FLUSH);
+	int i, s, n, i_idx, min_ae;
+	uint8_t cur, prev;
+
+	d.code = code;
+	d.n_states = ns;
+	d.o_idx = d.p_idx = 0;
+	d.ae      = malloc(sizeof(unsigned int) * ns);
+	d.ae_next = malloc(sizeof(unsigned int) * ns);
+	d.state_history = calloc(ns * (code->len + code->K - 1), 1);
+
+	for (s = 0; s < ns; s++)
+		d.ae[s] = (s == 0) ? 0 : MAX_AE;
+
+	if (code->term == CONV_TERM_TAIL_BITING) {
+		unsigned int m = MAX_AE;
+		/* first pass only seeds the metrics; rewind: restart indices, normalise by the min */
+		for (i = 0, i_idx = 0; i < code->len; i++)
+			i_idx = vdec_step(&d, input, i_idx, 0);
+		d.o_idx = d.p_idx = 0;
+		for (s = 0; s < ns; s++)
+			if (d.ae[s] < m)
+				m = d.ae[s];
+		for (s = 0; s < ns; s++)
+			d.ae[s] -= m;
+	}
+
+	for (i = 0, i_idx = 0; i < code->len; i++)
+		i_idx = vdec_step(&d, input, i_idx, 0);
+	if (has_flush)
+		for (i = 0; i < code->K - 1; i++)
+			i_idx = vdec_step(&d, input, i_idx, 1);
+
+	/* end state: 0 after a flush, else the FIRST state with minimal accumulated error */
+	if (has_flush) {
+		cur = 0;
+		min_ae = d.ae[0];
+	} else {
+		min_ae = MAX_AE;
+		cur = 0xff;
+		for (s = 0; s < ns; s++)
+			if (d.ae[s] < (unsigned int)min_ae) {
+				min_ae = d.ae[s];
+				cur = s;
+			}
+		if (cur == 0xff) {
+			min_ae = -1;
+			goto done;
+		}
+	}
+
+	n = d.o_idx;
+	if (has_flush) {
+		for (i = 0; i < code->K - 1; i++, n--)
+			cur = d.state_history[ns * (n - 1) + cur];
+	}
+	for (i = n - 1; i >= 0; i--) {
+		prev = d.state_history[ns * i + cur];
+		output[i] = (code->next_state[prev][0] == cur) ? 0 : 1;
+		cur = prev;
+	}
+
+done:
+	free(d.state_history);
+	free(d.ae_next);
+	free(d.ae);
+	return min_ae;
+}
+
+/* ---------------------------------------------------------------- utils.h */
+
+int osmo_hexparse(const char *str, uint8_t *b, int max_len)
+{
+	int i, l = strlen(str), nib;
+	if (l & 1 || (l >> 1) > max_len)
+		return -1;
+	memset(b, 0x00, max_len);
+	for (i = 0; i < l; i++) {
+		char c = str[i];
+		if (c >= '0' && c <= '9')      nib = c - '0';
+		else if (c >= 'a' && c <= 'f') nib = 10 + c - 'a';
+		else if (c >= 'A' && c <= 'F') nib = 10 + c - 'A';
+		else return -1;
+		b[i >> 1] |= nib << ((i & 1) ? 0 : 4);
+	}
+	return l >> 1;
+}
+
+char *osmo_hexdump_nospc(const unsigned char *buf, int len)
+{
+	static char s[4096];
+	int i;
+	for (i = 0; i < len && i < 2047; i++)
+		sprintf(&s[2 * i], "%02x", buf[i]);
+	s[2 * i] = 0;
+	return s;
+}
+
+/* ---------------------------------------------------------------- msgb / gsmtap stubs
+ * GSMTAP wire output is out of scope; messages are built and dropped. */
+
+struct msgb *msgb_alloc(uint16_t size, const char *name)
+{
+	struct msgb *m = calloc(1, sizeof(*m) + size);
+	(void)name;
+	if (m)
+		m->alloc = size;
+	return m;
+}
+
+uint8_t *msgb_put(struct msgb *m, unsigned int len)
+{
+	uint8_t *p = &m->data[m->len];
+	m->len += len;
+	return p;
+}
+
+void msgb_free(struct msgb *m) { free(m); }
+
+struct gsmtap_inst { int dummy; };
+static struct gsmtap_inst g_gti;
+
+struct gsmtap_inst *gsmtap_source_init(const char *host, uint16_t port, int ofd_wq_mode)
+{
+	(void)host; (void)port; (void)ofd_wq_mode;
+	return &g_gti;
+}
+int gsmtap_source_add_sink(struct gsmtap_inst *gti) { (void)gti; return 0; }
+int gsmtap_sendmsg(struct gsmtap_inst *gti, struct msgb *msg)
+{
+	(void)gti;
+	msgb_free(msg);
+	return 0;
+}
