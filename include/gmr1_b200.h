@@ -1,0 +1,111 @@
+/* gmr1_b200.h - C ABI of the B200-native batched GMR-1 receiver PHY (libgmr1_b200.so).
+ *
+ * The library is a drop-in for the per-burst receive path of osmocom/osmo-gmr
+ * (libgmr1-sdr + libgmr1-l1, consumed by src/gmr1_rx.c).  It exports
+ *
+ *   (1) batched entry points  gmr1b200_*_batch : n independent units per call, one or a few
+ *       CUDA kernel launches, plain pointers + sizes.  Every pointer argument may be either
+ *       HOST memory (pageable or pinned) or DEVICE memory; the library detects which
+ *       (cudaPointerGetAttributes).  With only device pointers a call is asynchronous on
+ *       `stream`; as soon as one pointer is host memory the call stages that buffer through
+ *       device scratch on `stream` and returns after the results are back (the reference's
+ *       synchronous semantics).  `stream` is a cudaStream_t passed as void* (NULL = default).
+ *
+ *   (2) the reference's own symbols (gmr1_bcch_decode, gmr1_pi4cxpsk_demod, ...), same
+ *       signatures, as n = 1 wrappers over (1), declared in gmr1_b200_compat.h.
+ *
+ * Each declaration cites the reference interface it replaces (path:line under the reference
+ * root).  Array layouts are "unit-major": n consecutive copies of the reference's per-call
+ * array.  sbit_t = int8_t (+127 strong 0 ... -127 strong 1, 0 erased), ubit_t = uint8_t
+ * holding one bit, L2 bytes LSB-first exactly as the reference packs them.
+ *
+ * Error convention (reference: 0 ok, -errno hard error, >0 soft condition):
+ *   0 success, -EINVAL bad argument, -ENOMEM allocation failure, -EIO CUDA failure
+ *   (text from gmr1b200_last_error()), -ENODEV no usable GPU.  There is NO CPU fallback.
+ */
+#ifndef GMR1_B200_H
+#define GMR1_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int8_t  gmr1b200_sbit_t;
+typedef uint8_t gmr1b200_ubit_t;
+
+/* ---- library state --------------------------------------------------------------------- */
+
+/* Select the CUDA device for the calling thread and upload the constant tables.
+ * Optional: every entry point initialises the current device lazily. */
+int gmr1b200_init(int device);
+/* Text of the last CUDA / argument error on the calling thread ("" if none). */
+const char *gmr1b200_last_error(void);
+/* Library version string. */
+const char *gmr1b200_version(void);
+/* Number of CUDA kernels this library has launched in this process (all threads). */
+uint64_t gmr1b200_kernel_launches(void);
+
+/* ---- stage 3: channel decode (soft bits -> L2) -------------------------------------------
+ * crc[i]  = what the reference function returns for unit i (0 = CRC ok)
+ * conv_rv[i] = osmo_conv_decode() return value (Viterbi path metric); may be NULL
+ * All are bit-exact with the reference C path (integer arithmetic only). */
+
+/* replaces gmr1_bcch_decode, src/l1/bcch.c:84 (include/osmocom/gmr1/l1/bcch.h:38)
+ * l2 [n][24], bits_e [n][424] */
+int gmr1b200_bcch_decode_batch(uint8_t *l2, const gmr1b200_sbit_t *bits_e,
+                               int32_t *conv_rv, int32_t *crc, int n, void *stream);
+
+/* replaces gmr1_ccch_decode, src/l1/ccch.c:88 (l1/ccch.h:38).  l2 [n][24], bits_e [n][432] */
+int gmr1b200_ccch_decode_batch(uint8_t *l2, const gmr1b200_sbit_t *bits_e,
+                               int32_t *conv_rv, int32_t *crc, int n, void *stream);
+
+/* replaces gmr1_facch3_decode, src/l1/facch3.c:122 (l1/facch3.h:39-40)
+ * l2 [n][10], bits_s [n][32] (may be NULL), bits_e [n][416] (4 bursts x 104),
+ * ciph [n][384] ubit or NULL */
+int gmr1b200_facch3_decode_batch(uint8_t *l2, gmr1b200_ubit_t *bits_s,
+                                 const gmr1b200_sbit_t *bits_e, const gmr1b200_ubit_t *ciph,
+                                 int32_t *conv_rv, int32_t *crc, int n, void *stream);
+
+/* replaces gmr1_facch9_decode, src/l1/facch9.c:107 (l1/facch9.h:40-41)
+ * l2 [n][38], bits_sacch [n][10] sbit, bits_status [n][4] sbit (either may be NULL),
+ * bits_e [n][662], ciph [n][658] or NULL */
+int gmr1b200_facch9_decode_batch(uint8_t *l2, gmr1b200_sbit_t *bits_sacch, gmr1b200_sbit_t *bits_status,
+                                 const gmr1b200_sbit_t *bits_e, const gmr1b200_ubit_t *ciph,
+                                 int32_t *conv_rv, int32_t *crc, int n, void *stream);
+
+/* replaces gmr1_tch3_decode, src/l1/tch3.c:124 (l1/tch3.h:40-42)
+ * frame0/frame1 [n][10] (MSB first), bits_s [n][4] ubit or NULL, bits_e [n][212],
+ * ciph [n][208] or NULL, m = multiplexing mode, conv0_rv / conv1_rv [n] or NULL */
+int gmr1b200_tch3_decode_batch(uint8_t *frame0, uint8_t *frame1, gmr1b200_ubit_t *bits_s,
+                               const gmr1b200_sbit_t *bits_e, const gmr1b200_ubit_t *ciph, int m,
+                               int32_t *conv0_rv, int32_t *conv1_rv, int n, void *stream);
+
+/* replaces gmr1_tch9_decode + struct gmr1_interleaver, src/l1/tch9.c:140, interleave.c:168
+ * (l1/tch9.h:50-53).  mode: 0 = 2k4 (l2 [n][18]), 1 = 4k8 ([n][30]), 2 = 9k6 ([n][60])
+ * (enum gmr1_tch9_mode).  The stateful depth-3 inter-burst de-interleaver is expressed as a
+ * gather: prev1[i] / prev2[i] = index (within this batch) of the burst received one / two
+ * bursts before burst i on the same channel, or -1 when there is none (interleaver memory is
+ * zero, as after gmr1_interleaver_init).  prev1 / prev2 NULL = -1 everywhere. */
+int gmr1b200_tch9_decode_batch(uint8_t *l2, gmr1b200_sbit_t *bits_sacch, gmr1b200_sbit_t *bits_status,
+                               const gmr1b200_sbit_t *bits_e, int mode, const gmr1b200_ubit_t *ciph,
+                               const int32_t *prev1, const int32_t *prev2,
+                               int32_t *conv_rv, int n, void *stream);
+
+/* replaces gmr1_rach_decode, src/l1/rach.c:137 (l1/rach.h:38-39)
+ * rach [n][18], bits_e [n][494], sb_mask [n] or NULL (then sb_mask0 for every unit),
+ * crc_rv [n][2] or NULL, crc [n] = return value (crc_rv[0] || crc_rv[1]) */
+int gmr1b200_rach_decode_batch(uint8_t *rach, const gmr1b200_sbit_t *bits_e,
+                               const uint8_t *sb_mask, int sb_mask0,
+                               int32_t *conv_rv, int32_t *crc_rv, int32_t *crc, int n, void *stream);
+
+/* replaces gmr1_xch_dc12_decode, src/l1/xch_dc12.c:87 (l1/xch_dc12.h:38)
+ * l2 [n][24], bits_e [n][432] */
+int gmr1b200_xch_dc12_decode_batch(uint8_t *l2, const gmr1b200_sbit_t *bits_e,
+                                   int32_t *conv_rv, int32_t *crc, int n, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GMR1_B200_H */

@@ -1,0 +1,319 @@
+// decode_kernels.cu - stage 3 of the receive path on the GPU: batched channel decode.
+//
+//   decode_tpc_kernel<CH>  K5 / K7 codes, one thread per codeword, 128 codewords per CTA.
+//       phase 1  soft-bit rows of the CTA's 128 units -> shared memory
+//                (un-ciphered channels: one TMA bulk copy of the contiguous tile; ciphered /
+//                 TCH9: cooperative coalesced loop that applies the cipher sign / gathers the
+//                 three bursts the inter-burst deinterleaver spans)
+//       phase 2  per thread: gather program -> ACS in registers -> decisions to shared memory
+//                -> traceback -> CRC -> packed L2 (decode_unit.cuh)
+//   decode_dc12_kernel     K9 (256 states), one warp per codeword, path metrics and
+//                survivor bits in shared memory, 8 states per lane.
+//
+// Replaces gmr1_{bcch,ccch,facch3,facch9,tch3,tch9,rach,xch_dc12}_decode + osmo_conv_decode +
+// osmo_crc*gen_check_bits of the reference (see decode_unit.cuh for file:line).
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include "decode_unit.cuh"
+#include "tma.cuh"
+#include "launch.h"
+
+namespace gmr1 {
+
+static constexpr int TPC_T = 128;    // threads (= codewords) per CTA
+
+// ---- device tables --------------------------------------------------------------------------
+__constant__ uint16_t c_g[CH_COUNT][MAX_CODED];     // gather programs (uniform access)
+__constant__ uint16_t c_rach_g2[MAX_CODED];
+__device__ int16_t  d_cmap[CH_COUNT][MAX_EBITS];     // per-lane access -> global
+__device__ uint16_t d_t9_src[648];
+
+static bool g_tables_up[64] = {false};
+
+static cudaError_t upload_tables()
+{
+	int dev = 0;
+	cudaError_t e = cudaGetDevice(&dev);
+	if (e != cudaSuccess)
+		return e;
+	if (dev < 64 && g_tables_up[dev])
+		return cudaSuccess;
+	for (int ch = 0; ch < CH_COUNT; ch++) {
+		const ChanTab &t = chan_tab(ch);
+		if ((e = cudaMemcpyToSymbol(c_g, t.g, sizeof(t.g), sizeof(t.g) * ch)) != cudaSuccess) return e;
+		if ((e = cudaMemcpyToSymbol(d_cmap, t.cmap, sizeof(t.cmap), sizeof(t.cmap) * ch)) != cudaSuccess) return e;
+	}
+	if ((e = cudaMemcpyToSymbol(c_rach_g2, chan_tab(CH_RACH).g2, sizeof(c_rach_g2))) != cudaSuccess) return e;
+	if ((e = cudaMemcpyToSymbol(d_t9_src, chan_tab(CH_TCH9_9K6).t9_src, sizeof(d_t9_src))) != cudaSuccess) return e;
+	if (dev < 64)
+		g_tables_up[dev] = true;
+	return cudaSuccess;
+}
+
+// ---- compile-time geometry per channel ---------------------------------------------------------
+__host__ __device__ constexpr int chan_n_in(int ch)
+{
+	return ch == CH_BCCH ? 424 : ch == CH_CCCH ? 432 : ch == CH_FACCH3 ? 416 :
+	       ch == CH_RACH ? 494 : ch == CH_TCH3 ? 212 : ch == CH_DC12 ? 432 : 662;
+}
+__host__ __device__ constexpr bool chan_is_t9(int ch)
+{
+	return ch == CH_TCH9_2K4 || ch == CH_TCH9_4K8 || ch == CH_TCH9_9K6;
+}
+__host__ __device__ constexpr int chan_n_row(int ch) { return chan_is_t9(ch) ? 648 : chan_n_in(ch); }
+__host__ __device__ constexpr int chan_len(int ch)
+{
+	return ch == CH_BCCH || ch == CH_CCCH || ch == CH_DC12 ? 208 : ch == CH_FACCH3 ? 92 :
+	       ch == CH_FACCH9 ? 316 : ch == CH_TCH9_2K4 ? 144 : ch == CH_TCH9_4K8 ? 240 :
+	       ch == CH_TCH9_9K6 ? 480 : ch == CH_RACH ? 159 : 48;
+}
+__host__ __device__ constexpr int chan_n_ciph(int ch)
+{
+	return ch == CH_FACCH3 ? 384 : (ch == CH_FACCH9 || chan_is_t9(ch)) ? 658 : ch == CH_TCH3 ? 208 : 0;
+}
+__host__ __device__ constexpr int chan_n_steps(int ch)
+{
+	return chan_len(ch) + ((ch == CH_TCH3 || ch == CH_DC12) ? 0 : 4);
+}
+// decision bytes per thread
+__host__ __device__ constexpr int chan_dec_bytes(int ch)
+{
+	return ch == CH_TCH3 ? 48 * 8 : chan_n_steps(ch) * 2;
+}
+__host__ __device__ constexpr int tpc_rows_bytes(int ch) { return (TPC_T * chan_n_row(ch) + 15) & ~15; }
+__host__ __device__ constexpr int tpc_smem_bytes(int ch)
+{
+	return tpc_rows_bytes(ch) + TPC_T * chan_dec_bytes(ch) + 16;
+}
+
+// ---- thread-per-codeword kernel ------------------------------------------------------------------
+template <int CH>
+__global__ void __launch_bounds__(TPC_T) decode_tpc_kernel(const DecodeArgs a)
+{
+	extern __shared__ __align__(16) uint8_t smem[];
+	constexpr int NIN = chan_n_in(CH), NROW = chan_n_row(CH);
+	int8_t *rows = (int8_t *)smem;                                    // [TPC_T][NROW], unpadded
+	uint8_t *dec = smem + tpc_rows_bytes(CH);                          // [steps][words][TPC_T]
+	uint64_t *bar = (uint64_t *)(dec + TPC_T * chan_dec_bytes(CH));
+
+	TabRef tb;
+	tb.g = c_g[CH];
+	tb.g2 = (CH == CH_RACH) ? c_rach_g2 : nullptr;
+	tb.cmap = d_cmap[CH];
+	tb.t9_src = d_t9_src;
+	tb.n_in = NIN; tb.n_row = NROW; tb.n_ciph = chan_n_ciph(CH);
+	tb.n_steps = chan_n_steps(CH); tb.len = chan_len(CH);
+
+	const int tid = threadIdx.x;
+	const int base = blockIdx.x * TPC_T;
+	const int cnt = min(TPC_T, a.n - base);
+
+	// ---- phase 1: stage the tile
+	const bool plain = !chan_is_t9(CH) && (chan_n_ciph(CH) == 0 || a.ciph == nullptr);
+	const bool bulk = plain && cnt == TPC_T && ((((uintptr_t)a.ebits) & 15) == 0);
+	if (bulk) {
+		// the tile is one contiguous, 16-byte aligned span of TPC_T*NIN bytes: a single TMA
+		// bulk copy brings it in while no LSU instruction is spent on it
+		if (tid == 0) {
+			mbar_init(bar, 1);
+			mbar_fence_init();
+			mbar_arrive_expect_tx(bar, (uint32_t)(TPC_T * NIN));
+			tma_load_1d(rows, a.ebits + (size_t)base * NIN, (uint32_t)(TPC_T * NIN), bar);
+		}
+		__syncthreads();
+		mbar_wait(bar, 0);
+	} else {
+		for (int idx = tid; idx < TPC_T * NROW; idx += TPC_T) {
+			const int tt = idx / NROW, r = idx - tt * NROW;
+			rows[idx] = (tt < cnt) ? stage_elem<CH>(tb, a, base + tt, r) : (int8_t)0;
+		}
+		__syncthreads();
+	}
+
+	// ---- phase 2: one codeword per thread
+	if (tid < cnt) {
+		if constexpr (CH == CH_TCH3)
+			decode_unit_tch3(tb, a, base + tid, rows + tid * NROW, (uint32_t *)dec, TPC_T, tid);
+		else
+			decode_unit_k5<CH>(tb, a, base + tid, rows + tid * NROW, (uint16_t *)dec, TPC_T, tid);
+	}
+}
+
+template <int CH>
+static cudaError_t launch_tpc(const DecodeArgs &a, cudaStream_t st)
+{
+	static bool attr_done[64] = {false};
+	int dev = 0;
+	cudaGetDevice(&dev);
+	constexpr int smem = tpc_smem_bytes(CH);
+	if (dev >= 64 || !attr_done[dev]) {
+		cudaError_t e = cudaFuncSetAttribute(decode_tpc_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		if (e != cudaSuccess)
+			return e;
+		if (dev < 64)
+			attr_done[dev] = true;
+	}
+	const int grid = (a.n + TPC_T - 1) / TPC_T;
+	decode_tpc_kernel<CH><<<grid, TPC_T, smem, st>>>(a);
+	return cudaGetLastError();
+}
+
+// ---- DC12: K9 r1/3 tail-biting, one warp per codeword ------------------------------------------------
+// Lane L owns new states 8L..8L+7 = butterflies 4L..4L+3 (old states 4L+i and 128+4L+i).  For
+// these generator polynomials (constant and D^8 term in every g) the four branch outputs of a
+// butterfly are x, ~x, ~x, x, so one 3-bit x per butterfly is all a lane keeps.
+static constexpr int DC12_WARPS = 4;
+struct Dc12Smem {
+	uint32_t ae[2][256];
+	uint8_t  dec[208][32];
+	int8_t   row[432];
+	uint8_t  out[32];
+};
+
+__global__ void __launch_bounds__(DC12_WARPS * 32) decode_dc12_kernel(const DecodeArgs a)
+{
+	using C = CodeK9_13;
+	extern __shared__ __align__(16) uint8_t smem[];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int unit = blockIdx.x * DC12_WARPS + warp;
+	if (unit >= a.n)
+		return;
+	Dc12Smem &s = reinterpret_cast<Dc12Smem *>(smem)[warp];
+	const uint16_t *g = c_g[CH_DC12];
+
+	for (int r = lane; r < 432; r += 32)
+		s.row[r] = a.ebits[(size_t)unit * 432 + r];
+	for (int i = lane; i < 256; i += 32)
+		s.ae[0][i] = i ? MAX_AE : 0u;
+
+	unsigned x[4];
+#pragma unroll
+	for (int i = 0; i < 4; i++) {
+		unsigned p = 4 * lane + i, reg = p << 1, ov = 0;
+		for (int j = 0; j < 3; j++)
+			ov = (ov << 1) | (__popc(reg & C::poly(j)) & 1);
+		x[i] = ov;
+	}
+	__syncwarp();
+
+	int cur = 0;
+	for (int pass = 0; pass < 2; pass++) {
+		for (int i = 0; i < 208; i++) {
+			uint32_t m0[3], m1[3], tot = 0;
+#pragma unroll
+			for (int j = 0; j < 3; j++) {
+				const int is = gather_sbit(s.row, g[i * 3 + j]);
+				const int d0 = is - 127, d1 = is + 127;
+				m0[j] = is ? (uint32_t)((d0 * d0) >> 9) : 0u;
+				m1[j] = is ? (uint32_t)((d1 * d1) >> 9) : 0u;
+				tot += m0[j] + m1[j];
+			}
+			const uint4 lo = *reinterpret_cast<const uint4 *>(&s.ae[cur][4 * lane]);
+			const uint4 hi = *reinterpret_cast<const uint4 *>(&s.ae[cur][128 + 4 * lane]);
+			const uint32_t lov[4] = {lo.x, lo.y, lo.z, lo.w}, hiv[4] = {hi.x, hi.y, hi.z, hi.w};
+			uint32_t nv[8];
+			unsigned d = 0;
+#pragma unroll
+			for (int b = 0; b < 4; b++) {
+				const uint32_t A = ((x[b] & 4) ? m1[0] : m0[0]) + ((x[b] & 2) ? m1[1] : m0[1]) +
+				                   ((x[b] & 1) ? m1[2] : m0[2]);
+				const uint32_t B = tot - A;
+				const uint32_t a0 = lov[b] + A, b0 = hiv[b] + B;   // -> state 8L+2b
+				const uint32_t a1 = lov[b] + B, b1 = hiv[b] + A;   // -> state 8L+2b+1
+				const bool d0 = b0 < a0, d1 = b1 < a1;
+				nv[2 * b] = d0 ? b0 : a0;
+				nv[2 * b + 1] = d1 ? b1 : a1;
+				d |= (d0 ? 1u : 0u) << (2 * b);
+				d |= (d1 ? 1u : 0u) << (2 * b + 1);
+			}
+			uint4 *dst = reinterpret_cast<uint4 *>(&s.ae[cur ^ 1][8 * lane]);
+			dst[0] = make_uint4(nv[0], nv[1], nv[2], nv[3]);
+			dst[1] = make_uint4(nv[4], nv[5], nv[6], nv[7]);
+			if (pass)
+				s.dec[i][lane] = (uint8_t)d;
+			cur ^= 1;
+			__syncwarp();
+		}
+		if (pass == 0) {   // rewind: subtract the minimum (osmo_conv_decode_rewind)
+			uint32_t mn = MAX_AE;
+			for (int i = 0; i < 8; i++)
+				mn = min(mn, s.ae[cur][8 * lane + i]);
+			for (int o = 16; o; o >>= 1)
+				mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+			for (int i = 0; i < 8; i++)
+				s.ae[cur][8 * lane + i] -= mn;
+			__syncwarp();
+		}
+	}
+
+	// end state = first state with the minimal metric: min over (metric << 8 | state)
+	uint32_t key = 0xffffffffu;
+	for (int i = 0; i < 8; i++) {
+		const uint32_t v = s.ae[cur][8 * lane + i];
+		if (v < MAX_AE)
+			key = min(key, (v << 8) | (uint32_t)(8 * lane + i));
+	}
+	for (int o = 16; o; o >>= 1)
+		key = min(key, __shfl_xor_sync(0xffffffffu, key, o));
+
+	if (lane == 0) {
+		if (a.conv)
+			a.conv[unit] = key == 0xffffffffu ? -1 : (int32_t)(key >> 8);
+		for (int i = 0; i < 32; i++)
+			s.out[i] = 0;
+		unsigned st = key & 0xff;
+		if (key != 0xffffffffu)
+			for (int i = 207; i >= 0; i--) {
+				const unsigned bit = (s.dec[i][st >> 3] >> (st & 7)) & 1u;
+				s.out[i >> 3] |= (uint8_t)((st & 1u) << (i & 7));
+				st = (st >> 1) | (bit << 7);
+			}
+		if (a.crc)
+			a.crc[unit] = crc_check_packed(s.out, 0, 192, 0x1021, 16);
+		for (int i = 0; i < 24; i++)
+			a.l2[(size_t)unit * 24 + i] = s.out[i];
+	}
+}
+
+static cudaError_t launch_dc12(const DecodeArgs &a, cudaStream_t st)
+{
+	static bool attr_done[64] = {false};
+	int dev = 0;
+	cudaGetDevice(&dev);
+	const int smem = (int)sizeof(Dc12Smem) * DC12_WARPS;
+	if (dev >= 64 || !attr_done[dev]) {
+		cudaError_t e = cudaFuncSetAttribute(decode_dc12_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		if (e != cudaSuccess)
+			return e;
+		if (dev < 64)
+			attr_done[dev] = true;
+	}
+	decode_dc12_kernel<<<(a.n + DC12_WARPS - 1) / DC12_WARPS, DC12_WARPS * 32, smem, st>>>(a);
+	return cudaGetLastError();
+}
+
+// ---- dispatch ------------------------------------------------------------------------------------
+cudaError_t launch_decode(int ch, const DecodeArgs &a, cudaStream_t st)
+{
+	if (a.n <= 0)
+		return cudaSuccess;
+	cudaError_t e = upload_tables();
+	if (e != cudaSuccess)
+		return e;
+	switch (ch) {
+	case CH_BCCH:     return launch_tpc<CH_BCCH>(a, st);
+	case CH_CCCH:     return launch_tpc<CH_CCCH>(a, st);
+	case CH_FACCH3:   return launch_tpc<CH_FACCH3>(a, st);
+	case CH_FACCH9:   return launch_tpc<CH_FACCH9>(a, st);
+	case CH_TCH9_2K4: return launch_tpc<CH_TCH9_2K4>(a, st);
+	case CH_TCH9_4K8: return launch_tpc<CH_TCH9_4K8>(a, st);
+	case CH_TCH9_9K6: return launch_tpc<CH_TCH9_9K6>(a, st);
+	case CH_RACH:     return launch_tpc<CH_RACH>(a, st);
+	case CH_TCH3:     return launch_tpc<CH_TCH3>(a, st);
+	case CH_DC12:     return launch_dc12(a, st);
+	default:          return cudaErrorInvalidValue;
+	}
+}
+
+}  // namespace gmr1

@@ -1,0 +1,260 @@
+// decode_unit.cuh - per-channel decode of ONE unit (codeword / burst) by ONE thread:
+// staged soft-bit row -> Viterbi -> traceback -> CRC -> packed L2 + side outputs.
+// Mirrors the reference decode entry points (return value = CRC result, *conv_rv = Viterbi
+// metric): gmr1_bcch_decode (src/l1/bcch.c:84), gmr1_ccch_decode (ccch.c:88),
+// gmr1_facch3_decode (facch3.c:122), gmr1_facch9_decode (facch9.c:107), gmr1_tch9_decode
+// (tch9.c:140), gmr1_rach_decode (rach.c:137), gmr1_tch3_decode (tch3.c:124).
+#pragma once
+#include "viterbi_tpc.cuh"
+
+namespace gmr1 {
+
+// Batched decode arguments. All pointers are device pointers on the GPU path. Unused ones
+// are NULL. Layouts are unit-major, exactly n consecutive copies of the reference's arrays.
+struct DecodeArgs {
+	const int8_t  *ebits;     // [n][n_in]
+	const uint8_t *ciph;      // [n][n_ciph] ubit (one byte per bit) or NULL
+	int32_t        n;
+	uint8_t       *l2;        // [n][l2_bytes]   (tch3: frame0 [n][10])
+	uint8_t       *l2b;       // tch3: frame1 [n][10]
+	int32_t       *conv;      // [n] or NULL      (tch3: conv0)
+	int32_t       *conv1;     // tch3: conv1 [n] or NULL
+	int32_t       *crc;       // [n] (return value of the reference function) or NULL
+	int32_t       *crc2;      // rach: crc_rv [n][2] or NULL
+	uint8_t       *bits_s;    // facch3: [n][32] ubit, tch3: [n][4] ubit, or NULL
+	int8_t        *sacch;     // facch9/tch9: [n][10] sbit or NULL
+	int8_t        *status;    // facch9/tch9: [n][4] sbit or NULL
+	const int32_t *prev1;     // tch9: index of the previous burst of the same channel, -1 = none
+	const int32_t *prev2;     // tch9: index of the burst before that, -1 = none
+	const uint8_t *sb_mask;   // rach: [n] or NULL (then sb_mask0 for all)
+	int32_t        sb_mask0;
+	int32_t        tch3_m;    // tch3 multiplexing mode (0 / 1)
+};
+
+// device-resident (or host, in the emulation) tables one channel needs
+struct TabRef {
+	const uint16_t *g;        // gather program            (uniform access: __constant__)
+	const uint16_t *g2;       // RACH second source or NULL (uniform)
+	const int16_t  *cmap;     // ebit -> cipher index       (per-lane access: global)
+	const uint16_t *t9_src;   // TCH9 staging map           (per-lane access: global)
+	int32_t n_in, n_row, n_ciph, n_steps, len;
+};
+
+template <int CH> struct ChanCode { using type = CodeK5_12; };
+template <> struct ChanCode<CH_FACCH3>   { using type = CodeK5_14; };
+template <> struct ChanCode<CH_RACH>     { using type = CodeK5_14; };
+template <> struct ChanCode<CH_TCH9_2K4> { using type = CodeK5_15; };
+template <> struct ChanCode<CH_TCH9_4K8> { using type = CodeK5_13; };
+template <> struct ChanCode<CH_TCH3>     { using type = CodeK7_12; };
+template <> struct ChanCode<CH_DC12>     { using type = CodeK9_13; };
+
+// bytes of packed L2 each unit produces
+GMR1_HD constexpr int chan_l2_bytes(int ch)
+{
+	return ch == CH_BCCH || ch == CH_CCCH || ch == CH_DC12 ? 24 :
+	       ch == CH_FACCH3 ? 10 : ch == CH_FACCH9 ? 38 :
+	       ch == CH_TCH9_2K4 ? 18 : ch == CH_TCH9_4K8 ? 30 : ch == CH_TCH9_9K6 ? 60 :
+	       ch == CH_RACH ? 18 : 10;
+}
+
+// ---- staging: value of staged-row element r of `unit` ---------------------------------------
+// Default channels: the row is the ebits row with the cipher sign already applied
+// (reference: "if (ciph[i]) bits[i] *= -1", e.g. facch9.c:121-125).
+// TCH9: the row is the inter-burst-deinterleaved, descrambled vector (tch9.c:163-166).
+template <int CH>
+GMR1_HD int8_t stage_elem(const TabRef &tb, const DecodeArgs &a, int unit, int r)
+{
+	constexpr bool T9 = (CH == CH_TCH9_2K4 || CH == CH_TCH9_4K8 || CH == CH_TCH9_9K6);
+	if (T9) {
+		const uint16_t w = tb.t9_src[r];
+		const int age = (w >> 10) & 3, s = w & G_IDX;
+		int u = unit;
+		if (age == 1) u = a.prev1 ? a.prev1[unit] : -1;
+		if (age == 2) u = a.prev2 ? a.prev2[unit] : -1;
+		if (u < 0)
+			return 0;
+		int v = a.ebits[(size_t)u * tb.n_in + s];
+		if (a.ciph && a.ciph[(size_t)u * tb.n_ciph + tb.cmap[s]])
+			v = sbit_neg(v);
+		if (w & G_FLIP)
+			v = sbit_neg(v);
+		return (int8_t)v;
+	} else {
+		int v = a.ebits[(size_t)unit * tb.n_in + r];
+		if (a.ciph) {
+			const int c = tb.cmap[r];
+			if (c >= 0 && a.ciph[(size_t)unit * tb.n_ciph + c])
+				v = sbit_neg(v);
+		}
+		return (int8_t)v;
+	}
+}
+
+// ---- per-unit decode, flush-terminated K5 channels ------------------------------------------
+// row: staged soft bits of this unit (n_row bytes, overwritten with the packed output bits),
+// dec: decision storage [n_steps][T] words, t: this thread's slot
+template <int CH>
+GMR1_HD void decode_unit_k5(const TabRef &tb, const DecodeArgs &a, int unit,
+                            int8_t *row, uint16_t *dec, int T, int t)
+{
+	using C = typename ChanCode<CH>::type;
+	constexpr bool T9 = (CH == CH_TCH9_2K4 || CH == CH_TCH9_4K8 || CH == CH_TCH9_9K6);
+	constexpr bool F9 = (CH == CH_FACCH9);
+
+	// side outputs that are plain copies of (deciphered) soft bits
+	if (CH == CH_FACCH3 && a.bits_s) {
+		for (int b = 0; b < 4; b++)
+			for (int j = 0; j < 8; j++)     // facch3.c:141-142 (status bits are not ciphered)
+				a.bits_s[(size_t)unit * 32 + 8 * b + j] = a.ebits[(size_t)unit * 416 + 104 * b + 22 + j] < 0;
+	}
+	if (T9 || F9) {
+		const int8_t *e = a.ebits + (size_t)unit * 662;
+		if (a.status)
+			for (int i = 0; i < 4; i++)     // facch9.c:118
+				a.status[(size_t)unit * 4 + i] = e[52 + i];
+		if (a.sacch)
+			for (int i = 0; i < 10; i++) {  // facch9.c:121-128: my[52+i] after deciphering
+				int v = e[56 + i];
+				if (a.ciph && a.ciph[(size_t)unit * 658 + 52 + i])
+					v = sbit_neg(v);
+				a.sacch[(size_t)unit * 10 + i] = (int8_t)v;
+			}
+	}
+
+	uint32_t ae[C::NS];
+#pragma unroll
+	for (int s = 0; s < C::NS; s++)
+		ae[s] = s ? MAX_AE : 0u;
+
+	forward<C, false, true, CH == CH_RACH>(ae, row, tb.g, tb.g2, 0, tb.len, dec, T, t);
+	forward<C, true,  true, CH == CH_RACH>(ae, row, tb.g, tb.g2, tb.len, C::K - 1, dec, T, t);
+
+	if (a.conv)
+		a.conv[unit] = (int32_t)ae[0];
+
+	// traceback into LSB-first packed bytes, reusing the (now dead) staged row
+	uint8_t *out = (uint8_t *)row;
+	{
+		unsigned acc = 0;
+		auto emit = [&](int i, unsigned bit) {
+			acc |= bit << (i & 7);
+			if ((i & 7) == 0) {
+				out[i >> 3] = (uint8_t)acc;
+				acc = 0;
+			}
+		};
+		traceback<C>(dec, T, t, tb.n_steps, tb.len, 0u, emit);
+	}
+
+	constexpr int NB = chan_l2_bytes(CH);
+	uint8_t *l2 = a.l2 + (size_t)unit * NB;
+
+	if (CH == CH_RACH) {
+		// bits_u[0..134] = class 2 (123 data + CRC12), bits_u[135..158] = class 1 (16 data + CRC8)
+		int c0 = crc_check_packed(out, 135, 16, 0x9b, 8);
+		const int c1 = crc_check_packed(out, 0, 123, 0x80f, 12);
+		if (c0) {   // retry with the SB mask applied to the CRC8 bits (rach.c:178-182)
+			const unsigned mask = a.sb_mask ? a.sb_mask[unit] : (unsigned)a.sb_mask0;
+			for (int i = 0; i < 8; i++) {
+				const int q = 135 + 16 + i;
+				out[q >> 3] ^= (uint8_t)(((mask >> (7 - i)) & 1u) << (q & 7));
+			}
+			c0 = crc_check_packed(out, 135, 16, 0x9b, 8);
+		}
+		if (a.crc2) {
+			a.crc2[(size_t)unit * 2] = c0;
+			a.crc2[(size_t)unit * 2 + 1] = c1;
+		}
+		if (a.crc)
+			a.crc[unit] = (c0 || c1) ? 1 : 0;
+		// rach[0..15] = class-1 data, rach[16..138] = class-2 data, LSB first (rach.c:190-193)
+		for (int i = 0; i < 18; i++) {
+			unsigned byte = 0;
+			for (int b = 0; b < 8; b++) {
+				const int o = 8 * i + b;
+				int q = -1;
+				if (o < 16)       q = 135 + o;
+				else if (o < 139) q = o - 16;
+				if (q >= 0)
+					byte |= ((out[q >> 3] >> (q & 7)) & 1u) << b;
+			}
+			l2[i] = (uint8_t)byte;
+		}
+	} else {
+		constexpr int n_data = CH == CH_FACCH3 ? 76 : CH == CH_FACCH9 ? 300 :
+		                       CH == CH_TCH9_2K4 ? 144 : CH == CH_TCH9_4K8 ? 240 :
+		                       CH == CH_TCH9_9K6 ? 480 : 192;
+		if (!T9) {
+			const int c = crc_check_packed(out, 0, n_data, 0x1021, 16);
+			if (a.crc)
+				a.crc[unit] = c;
+		}
+		for (int i = 0; i < NB; i++) {
+			unsigned byte = out[i];
+			if (8 * i + 8 > n_data)         // last partial byte: upper bits stay 0
+				byte &= (1u << (n_data - 8 * i)) - 1u;
+			l2[i] = (uint8_t)byte;
+		}
+	}
+}
+
+// ---- per-unit decode, TCH3 (two tail-biting K7 frames + class-2 bits) --------------------------
+GMR1_HD void decode_unit_tch3(const TabRef &tb, const DecodeArgs &a, int unit,
+                              const int8_t *row, uint32_t *dec, int T, int t)
+{
+	using C = CodeK7_12;
+	if (a.bits_s)
+		for (int i = 0; i < 4; i++)         // tch3.c:134-135
+			a.bits_s[(size_t)unit * 4 + i] = a.ebits[(size_t)unit * 212 + 52 + i] < 0;
+
+	for (int f = 0; f < 2; f++) {
+		const uint16_t *g = tb.g + (2 * (a.tch3_m ? 1 : 0) + f) * 128;
+		uint32_t ae[C::NS];
+#pragma unroll
+		for (int s = 0; s < C::NS; s++)
+			ae[s] = s ? MAX_AE : 0u;
+		// seeding pass, no history kept
+		forward<C, false, false, false>(ae, row, g, nullptr, 0, 48, dec, T, t);
+		uint32_t mn = MAX_AE;
+#pragma unroll
+		for (int s = 0; s < C::NS; s++)
+			mn = ae[s] < mn ? ae[s] : mn;
+#pragma unroll
+		for (int s = 0; s < C::NS; s++)
+			ae[s] -= mn;
+		forward<C, false, true, false>(ae, row, g, nullptr, 0, 48, dec, T, t);
+		// end state: first state with the minimal metric
+		uint32_t best = MAX_AE;
+		unsigned end = 0xff;
+#pragma unroll
+		for (int s = 0; s < C::NS; s++)
+			if (ae[s] < best) {
+				best = ae[s];
+				end = (unsigned)s;
+			}
+		int32_t *cv = f ? a.conv1 : a.conv;
+		if (cv)
+			cv[unit] = end == 0xff ? -1 : (int32_t)best;
+
+		// frame bits 0..47 from the decoder, 48..79 = sign of c[72..103]; MSB-first packing
+		uint32_t w0 = 0, w1 = 0, w2 = 0;        // bits 0..31, 32..63, 64..79
+		if (end != 0xff) {
+			auto emit = [&](int i, unsigned bit) {
+				if (i < 32) w0 |= bit << (31 - i);
+				else        w1 |= bit << (63 - i);
+			};
+			traceback<C>(dec, T, t, 48, 48, end, emit);
+		}
+		for (int j = 48; j < 80; j++) {
+			const unsigned bit = gather_sbit(row, g[96 + (j - 48)]) < 0 ? 1u : 0u;
+			if (j < 64) w1 |= bit << (63 - j);
+			else        w2 |= bit << (95 - j);
+		}
+		uint8_t *fr = (f ? a.l2b : a.l2) + (size_t)unit * 10;
+		fr[0] = (uint8_t)(w0 >> 24); fr[1] = (uint8_t)(w0 >> 16); fr[2] = (uint8_t)(w0 >> 8); fr[3] = (uint8_t)w0;
+		fr[4] = (uint8_t)(w1 >> 24); fr[5] = (uint8_t)(w1 >> 16); fr[6] = (uint8_t)(w1 >> 8); fr[7] = (uint8_t)w1;
+		fr[8] = (uint8_t)(w2 >> 24); fr[9] = (uint8_t)(w2 >> 16);
+	}
+}
+
+}  // namespace gmr1

@@ -1,0 +1,199 @@
+// viterbi_tpc.cuh - thread-per-codeword soft Viterbi for the 16-state (K5) and 64-state (K7)
+// GMR-1 codes, fused with the gather program (demux/decipher/descramble/deinterleave/
+// depuncture), traceback, CRC and L2 packing.
+//
+// Semantics follow osmo_conv_decode as the reference calls it (src/l1/bcch.c:94 and the
+// other seven call sites; algorithm restated in SURVEY.md Appendix A.1):
+//   * branch metric per soft bit  ((is - (+-127))^2) >> 9, 0 for an erased (0) soft bit
+//   * path metrics 32-bit, start state 0, all others MAX_AE = 0xffffff, never renormalised
+//   * survivor: predecessor st>>1 is evaluated first and kept on ties (strict '<' replaces)
+//   * FLUSH: K-1 extra steps with the 0-input branch only, end state 0
+//   * TAIL_BITING: one seeding pass, subtract min, second pass, end state = first minimum
+//   * output bit i = LSB of the state after step i
+//
+// Why one thread per codeword (and not one warp): all path metrics live in registers, the
+// trellis is fully unrolled with compile-time branch-metric indices, and no shuffle/ballot
+// traffic is needed - ~6 integer ops per state update, 32 codewords per warp in lock-step.
+// The functions are __host__ __device__ so tests can run the identical code on the CPU
+// (tests/emu) - that build is a test harness, not a product path.
+#pragma once
+#include <stdint.h>
+#include "gmr1_tables.h"
+
+#ifdef __CUDACC__
+#define GMR1_HD __host__ __device__ __forceinline__
+#else
+#define GMR1_HD inline
+#endif
+
+namespace gmr1 {
+
+static constexpr uint32_t MAX_AE = 0x00ffffffu;
+
+// ---- compile-time trellis ---------------------------------------------------------------
+template <int N_, int K_, unsigned G0, unsigned G1 = 0, unsigned G2 = 0, unsigned G3 = 0, unsigned G4 = 0>
+struct Code {
+	static constexpr int N = N_, K = K_, NS = 1 << (K_ - 1);
+	static constexpr unsigned poly(int j) { return j == 0 ? G0 : j == 1 ? G1 : j == 2 ? G2 : j == 3 ? G3 : G4; }
+	static constexpr unsigned parity(unsigned x)
+	{
+		x ^= x >> 16; x ^= x >> 8; x ^= x >> 4; x ^= x >> 2; x ^= x >> 1;
+		return x & 1u;
+	}
+	// next_output[s][b], MSB = g0 (reference src/l1/conv.c tables)
+	static constexpr unsigned out(unsigned s, unsigned b)
+	{
+		unsigned reg = (s << 1) | b, ov = 0;
+		for (int j = 0; j < N_; j++)
+			ov = (ov << 1) | parity(reg & poly(j));
+		return ov;
+	}
+};
+
+using CodeK5_12 = Code<2, 5, 0x19, 0x17>;
+using CodeK5_13 = Code<3, 5, 0x15, 0x1b, 0x1f>;
+using CodeK5_14 = Code<4, 5, 0x19, 0x17, 0x15, 0x1f>;
+using CodeK5_15 = Code<5, 5, 0x15, 0x1b, 0x1f, 0x1d, 0x17>;
+using CodeK7_12 = Code<2, 7, 0x6d, 0x4f>;
+using CodeK9_13 = Code<3, 9, 0x1ed, 0x19b, 0x127>;
+
+// ---- soft-bit fetch through the gather program -------------------------------------------
+GMR1_HD int sbit_neg(int v) { return (int)(int8_t)(-v); }   // int8 negate, -128 stays -128
+
+GMR1_HD int gather_sbit(const int8_t *row, uint16_t w)
+{
+	if (w == G_ERASED)
+		return 0;
+	int v = row[w & G_IDX];
+	return (w & G_FLIP) ? sbit_neg(v) : v;
+}
+
+// ---- one trellis step --------------------------------------------------------------------
+// DW = number of 32-bit decision words per step (NS/32 rounded up)
+template <class C, bool FLUSH_STEP>
+GMR1_HD void acs_step(uint32_t (&ae)[C::NS], const int (&v)[C::N], uint32_t (&dec)[(C::NS + 31) / 32])
+{
+	constexpr int N = C::N, NS = C::NS, H = NS / 2;
+	uint32_t m0[N], m1[N];
+#pragma unroll
+	for (int j = 0; j < N; j++) {
+		int is = v[j];
+		int d0 = is - 127, d1 = is + 127;
+		m0[j] = is ? (uint32_t)((d0 * d0) >> 9) : 0u;
+		m1[j] = is ? (uint32_t)((d1 * d1) >> 9) : 0u;
+	}
+	// all 2^N branch sums, built by doubling (entries that no transition uses are dead code)
+	uint32_t bm[1 << N];
+	bm[0] = 0;
+#pragma unroll
+	for (int j = 0; j < N; j++) {
+#pragma unroll
+		for (int o = (1 << j) - 1; o >= 0; o--) {
+			uint32_t base = bm[o];
+			bm[2 * o + 1] = base + m1[j];
+			bm[2 * o]     = base + m0[j];
+		}
+	}
+	uint32_t nae[NS];
+#pragma unroll
+	for (int i = 0; i < (NS + 31) / 32; i++)
+		dec[i] = 0;
+#pragma unroll
+	for (int k = 0; k < H; k++) {
+		const uint32_t lo = ae[k], hi = ae[k + H];
+		{
+			const uint32_t a = lo + bm[C::out(k, 0)], b = hi + bm[C::out(k + H, 0)];
+			const bool d = b < a;
+			nae[2 * k] = d ? b : a;
+			dec[(2 * k) >> 5] |= d ? (1u << ((2 * k) & 31)) : 0u;
+		}
+		if (!FLUSH_STEP) {
+			const uint32_t a = lo + bm[C::out(k, 1)], b = hi + bm[C::out(k + H, 1)];
+			const bool d = b < a;
+			nae[2 * k + 1] = d ? b : a;
+			dec[(2 * k + 1) >> 5] |= d ? (1u << ((2 * k + 1) & 31)) : 0u;
+		} else {
+			nae[2 * k + 1] = MAX_AE;
+		}
+	}
+#pragma unroll
+	for (int s = 0; s < NS; s++)
+		ae[s] = nae[s];
+}
+
+// decision storage: word w of step i of thread t lives at dec[(i*DW + w)*T + t] (T = threads
+// per CTA) so a warp's accesses are consecutive.  16-state codes use 16-bit words.
+template <int NS> struct DecWord { using type = uint32_t; };
+template <> struct DecWord<16> { using type = uint16_t; };
+
+// ---- forward pass over n steps ------------------------------------------------------------
+// g: gather program (N words per step), g2: optional second source averaged in (RACH)
+template <class C, bool FLUSH_STEP, bool STORE, bool HAS_G2>
+GMR1_HD void forward(uint32_t (&ae)[C::NS], const int8_t *row, const uint16_t *g, const uint16_t *g2,
+                     int step0, int nsteps, typename DecWord<C::NS>::type *dec_base, int T, int t)
+{
+	constexpr int DW = (C::NS + 31) / 32;
+	for (int i = step0; i < step0 + nsteps; i++) {
+		int v[C::N];
+#pragma unroll
+		for (int j = 0; j < C::N; j++) {
+			const uint16_t w = g[i * C::N + j];
+			int s = gather_sbit(row, w);
+			if (HAS_G2) {
+				const uint16_t w2 = g2[i * C::N + j];
+				if (w2 != G_ERASED)
+					s = (s + gather_sbit(row, w2)) >> 1;    // rach.c:159-160
+			}
+			v[j] = s;
+		}
+		uint32_t dec[DW];
+		acs_step<C, FLUSH_STEP>(ae, v, dec);
+		if (STORE) {
+#pragma unroll
+			for (int w = 0; w < DW; w++)
+				dec_base[(size_t)(i * DW + w) * T + t] = (typename DecWord<C::NS>::type)dec[w];
+		}
+	}
+}
+
+// ---- traceback ------------------------------------------------------------------------------
+// Walks steps n_steps-1 .. 0 from end_state, emits bit i (< len) = LSB of the state after
+// step i through emit(i, bit).
+template <class C, class Emit>
+GMR1_HD void traceback(const typename DecWord<C::NS>::type *dec_base, int T, int t,
+                       int n_steps, int len, unsigned end_state, Emit emit)
+{
+	constexpr int DW = (C::NS + 31) / 32;
+	unsigned st = end_state;
+	for (int i = n_steps - 1; i >= 0; i--) {
+		const uint32_t d = dec_base[(size_t)(i * DW + (DW > 1 ? (st >> 5) : 0)) * T + t];
+		const unsigned bit = (d >> (st & 31)) & 1u;
+		if (i < len)
+			emit(i, st & 1u);
+		st = (st >> 1) | (bit << (C::K - 2));
+	}
+}
+
+// ---- bit-serial CRC over LSB-first packed bytes (osmo_crc{8,16}gen_*) --------
+// returns 0 when the `bits` CRC bits that follow the data match, 1 otherwise
+GMR1_HD int crc_check_packed(const uint8_t *p, int bit0, int n_data, unsigned poly, int bits)
+{
+	const unsigned top = 1u << (bits - 1), mask = (1u << bits) - 1u;
+	unsigned crc = 0;
+	for (int i = 0; i < n_data; i++) {
+		const int q = bit0 + i;
+		const unsigned b = (p[q >> 3] >> (q & 7)) & 1u;
+		crc ^= b << (bits - 1);
+		crc = (crc & top) ? ((crc << 1) ^ poly) : (crc << 1);
+	}
+	crc &= mask;
+	int bad = 0;
+	for (int i = 0; i < bits; i++) {
+		const int q = bit0 + n_data + i;
+		const unsigned b = (p[q >> 3] >> (q & 7)) & 1u;
+		bad |= (int)(b ^ ((crc >> (bits - 1 - i)) & 1u));
+	}
+	return bad;
+}
+
+}  // namespace gmr1

@@ -1,0 +1,104 @@
+"""ctypes binding of libgmr1_b200.so (see include/gmr1_b200.h for the contract)."""
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgmr1_b200.so")
+
+_P = ctypes.c_void_p
+_I = ctypes.c_int
+
+
+def build(verbose=False):
+    """Compile the CUDA extension in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-C", _HERE, "-j8"], capture_output=True, text=True)
+    if verbose or r.returncode:
+        print(r.stdout[-4000:])
+        print(r.stderr[-4000:])
+    if r.returncode:
+        raise RuntimeError("building libgmr1_b200.so failed")
+    return LIB_PATH
+
+
+def _ptr(x):
+    """numpy array / torch tensor / int / None -> address (host or device, the library detects)."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if hasattr(x, "data_ptr"):          # torch tensor
+        assert x.is_contiguous()
+        return x.data_ptr()
+    if hasattr(x, "ctypes"):            # numpy array
+        assert x.flags["C_CONTIGUOUS"]
+        return x.ctypes.data
+    raise TypeError(type(x))
+
+
+class Gmr1Error(RuntimeError):
+    pass
+
+
+class Lib:
+    """One loaded libgmr1_b200.so.  Methods mirror the C entry points one to one."""
+
+    # name -> argtypes (restype is int unless listed in _RESTYPE)
+    _SIG = {
+        "gmr1b200_init": [_I],
+        "gmr1b200_bcch_decode_batch": [_P, _P, _P, _P, _I, _P],
+        "gmr1b200_ccch_decode_batch": [_P, _P, _P, _P, _I, _P],
+        "gmr1b200_facch3_decode_batch": [_P, _P, _P, _P, _P, _P, _I, _P],
+        "gmr1b200_facch9_decode_batch": [_P, _P, _P, _P, _P, _P, _P, _I, _P],
+        "gmr1b200_tch3_decode_batch": [_P, _P, _P, _P, _P, _I, _P, _P, _I, _P],
+        "gmr1b200_tch9_decode_batch": [_P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _P],
+        "gmr1b200_rach_decode_batch": [_P, _P, _P, _I, _P, _P, _P, _I, _P],
+        "gmr1b200_xch_dc12_decode_batch": [_P, _P, _P, _P, _I, _P],
+    }
+
+    def __init__(self, path=LIB_PATH):
+        if not os.path.exists(path):
+            raise ImportError(
+                f"{path} not found: build it first (python -c 'import __graft_entry__ as g; g.build()'). "
+                "There is no CPU fallback.")
+        self.path = path
+        self.c = ctypes.CDLL(path)
+        for name, args in self._SIG.items():
+            fn = getattr(self.c, name)
+            fn.argtypes = args
+            fn.restype = _I
+        self.c.gmr1b200_last_error.restype = ctypes.c_char_p
+        self.c.gmr1b200_version.restype = ctypes.c_char_p
+        self.c.gmr1b200_kernel_launches.restype = ctypes.c_uint64
+
+    # -- helpers
+    def _chk(self, rc, what):
+        if rc < 0:
+            raise Gmr1Error(f"{what}: rc={rc} ({self.c.gmr1b200_last_error().decode()})")
+        return rc
+
+    def version(self):
+        return self.c.gmr1b200_version().decode()
+
+    def kernel_launches(self):
+        return int(self.c.gmr1b200_kernel_launches())
+
+    def init(self, device=0):
+        return self._chk(self.c.gmr1b200_init(device), "init")
+
+    def call(self, name, *args):
+        """Raw call by C name with pointer-like python objects converted."""
+        fn = getattr(self.c, name)
+        conv = [(_ptr(a) if t is _P else a) for a, t in zip(args, fn.argtypes)]
+        return self._chk(fn(*conv), name)
+
+
+_lib = None
+
+
+def lib():
+    """Process-wide library handle (loaded on first use)."""
+    global _lib
+    if _lib is None:
+        _lib = Lib()
+    return _lib

@@ -1,0 +1,51 @@
+// tests/emu/decode_emu.cpp - TEST HARNESS: runs the product's __host__ __device__ decode code
+// (osmo_gmr_b200/csrc/decode_unit.cuh, viterbi_tpc.cuh - the exact functions the CUDA kernels
+// inline) on the CPU, one "thread" at a time, so that the kernel logic can be checked against
+// the oracle without a GPU.  It is NOT part of the product library and nothing in the product
+// falls back to it; it only exists so `pytest -m "not gpu"` can catch logic errors early.
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "decode_unit.cuh"
+
+using namespace gmr1;
+
+template <int CH>
+static void run(const DecodeArgs &a)
+{
+	const ChanTab &t = chan_tab(CH);
+	TabRef tb;
+	tb.g = t.g; tb.g2 = (CH == CH_RACH) ? t.g2 : nullptr; tb.cmap = t.cmap; tb.t9_src = t.t9_src;
+	tb.n_in = t.n_in; tb.n_row = t.n_row; tb.n_ciph = t.n_ciph; tb.n_steps = t.n_steps; tb.len = t.len;
+	std::vector<int8_t> row(t.n_row + 16);
+	std::vector<uint32_t> dec(2 * 1024);
+	for (int u = 0; u < a.n; u++) {
+		for (int r = 0; r < t.n_row; r++)
+			row[r] = stage_elem<CH>(tb, a, u, r);
+		if constexpr (CH == CH_TCH3)
+			decode_unit_tch3(tb, a, u, row.data(), dec.data(), 1, 0);
+		else
+			decode_unit_k5<CH>(tb, a, u, row.data(), (uint16_t *)dec.data(), 1, 0);
+	}
+}
+
+extern "C" int gmr1_emu_decode(int ch, const DecodeArgs *a)
+{
+	switch (ch) {
+	case CH_BCCH:     run<CH_BCCH>(*a); break;
+	case CH_CCCH:     run<CH_CCCH>(*a); break;
+	case CH_FACCH3:   run<CH_FACCH3>(*a); break;
+	case CH_FACCH9:   run<CH_FACCH9>(*a); break;
+	case CH_TCH9_2K4: run<CH_TCH9_2K4>(*a); break;
+	case CH_TCH9_4K8: run<CH_TCH9_4K8>(*a); break;
+	case CH_TCH9_9K6: run<CH_TCH9_9K6>(*a); break;
+	case CH_RACH:     run<CH_RACH>(*a); break;
+	case CH_TCH3:     run<CH_TCH3>(*a); break;
+	default: return -1;
+	}
+	return 0;
+}
+
+extern "C" int gmr1_emu_keep_mask(int ch, uint8_t *mask, int max) { return chan_keep_mask(ch, mask, max); }
+extern "C" int gmr1_emu_code_output(int ch, int state, int bit) { return code_output(chan_code(ch), state, bit); }
+extern "C" int gmr1_emu_sizeof_args() { return (int)sizeof(DecodeArgs); }

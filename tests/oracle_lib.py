@@ -1,0 +1,126 @@
+"""ctypes wrapper around the CPU oracle.  TEST INFRASTRUCTURE ONLY.
+
+Preference order: oracle/_ref/libgmr1_ref.so (the reference's own C sources compiled against
+oracle/shim) and, when that is absent, oracle/liboracle.so (our plain-C restatement).  Both
+export the reference's function names, so the wrapper is the same.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P = ctypes.c_void_p
+
+
+def p(a):
+    return a.ctypes.data_as(P) if a is not None else None
+
+
+class IL(ctypes.Structure):
+    _fields_ = [("N", ctypes.c_int), ("K", ctypes.c_int), ("n", ctypes.c_int), ("bits", P)]
+
+
+class CxVec(ctypes.Structure):
+    _fields_ = [("len", ctypes.c_int), ("max_len", ctypes.c_int), ("flags", ctypes.c_int), ("data", P)]
+
+
+class Oracle:
+    def __init__(self, path, kind):
+        self.path, self.kind = path, kind
+        self.c = ctypes.CDLL(path)
+
+    # ---------------- L1 encoders (used as vector generators)
+    def encode(self, name, nbits, l2):
+        out = np.zeros(nbits, np.uint8)
+        getattr(self.c, f"gmr1_{name}_encode")(p(out), p(l2))
+        return out
+
+    def facch3_encode(self, l2, bits_s, ciph=None):
+        out = np.zeros(416, np.uint8)
+        self.c.gmr1_facch3_encode(p(out), p(l2), p(bits_s), p(ciph))
+        return out
+
+    def facch9_encode(self, l2, sacch, status, ciph=None):
+        out = np.zeros(662, np.uint8)
+        self.c.gmr1_facch9_encode(p(out), p(l2), p(sacch), p(status), p(ciph))
+        return out
+
+    def rach_encode(self, rach, sb_mask):
+        out = np.zeros(494, np.uint8)
+        self.c.gmr1_rach_encode(p(out), p(rach), ctypes.c_uint8(int(sb_mask)))
+        return out
+
+    def interleaver(self):
+        il = IL()
+        self.c.gmr1_interleaver_init(ctypes.byref(il), 3, 648)
+        return il
+
+    def tch9_encode(self, l2, mode, sacch, status, ciph, il):
+        out = np.zeros(662, np.uint8)
+        self.c.gmr1_tch9_encode(p(out), p(l2), mode, p(sacch), p(status), p(ciph), ctypes.byref(il))
+        return out
+
+    # ---------------- L1 decoders
+    def simple_decode(self, name, e, l2_bytes=24):
+        l2 = np.zeros(l2_bytes, np.uint8)
+        cv = ctypes.c_int()
+        crc = getattr(self.c, f"gmr1_{name}_decode")(p(l2), p(e), ctypes.byref(cv))
+        return l2, crc, cv.value
+
+    def facch3_decode(self, e, ciph=None):
+        l2 = np.zeros(10, np.uint8)
+        s = np.zeros(32, np.uint8)
+        cv = ctypes.c_int()
+        crc = self.c.gmr1_facch3_decode(p(l2), p(s), p(e), p(ciph), ctypes.byref(cv))
+        return l2, s, crc, cv.value
+
+    def facch9_decode(self, e, ciph=None):
+        l2 = np.zeros(38, np.uint8)
+        sa = np.zeros(10, np.int8)
+        st = np.zeros(4, np.int8)
+        cv = ctypes.c_int()
+        crc = self.c.gmr1_facch9_decode(p(l2), p(sa), p(st), p(e), p(ciph), ctypes.byref(cv))
+        return l2, sa, st, crc, cv.value
+
+    def tch9_decode(self, e, mode, ciph, il):
+        l2 = np.zeros((18, 30, 60)[mode], np.uint8)
+        sa = np.zeros(10, np.int8)
+        st = np.zeros(4, np.int8)
+        cv = ctypes.c_int()
+        self.c.gmr1_tch9_decode(p(l2), p(sa), p(st), p(e), mode, p(ciph), ctypes.byref(il), ctypes.byref(cv))
+        return l2, sa, st, cv.value
+
+    def tch3_decode(self, e, ciph, m):
+        f0 = np.zeros(10, np.uint8)
+        f1 = np.zeros(10, np.uint8)
+        s = np.zeros(4, np.uint8)
+        c0, c1 = ctypes.c_int(), ctypes.c_int()
+        self.c.gmr1_tch3_decode(p(f0), p(f1), p(s), p(e), p(ciph), m, ctypes.byref(c0), ctypes.byref(c1))
+        return f0, f1, s, c0.value, c1.value
+
+    def rach_decode(self, e, sb_mask):
+        r = np.zeros(18, np.uint8)
+        cv = ctypes.c_int()
+        c2 = (ctypes.c_int * 2)()
+        crc = self.c.gmr1_rach_decode(p(r), p(e), ctypes.c_uint8(int(sb_mask)), ctypes.byref(cv), c2)
+        return r, crc, cv.value, list(c2)
+
+    def a5(self, n, key, fn, nbits):
+        dl = np.zeros(nbits, np.uint8)
+        k = np.ascontiguousarray(key, np.uint8)
+        self.c.gmr1_a5(n, p(k), ctypes.c_uint32(fn), nbits, p(dl), None)
+        return dl
+
+
+def load():
+    ref = os.path.join(ROOT, "oracle", "_ref", "libgmr1_ref.so")
+    port = os.path.join(ROOT, "oracle", "liboracle.so")
+    if not os.path.exists(ref) and os.path.isdir("/root/reference/src"):
+        subprocess.call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"])
+    if os.path.exists(ref):
+        return Oracle(ref, "reference")
+    if not os.path.exists(port):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"])
+    return Oracle(port, "port")
