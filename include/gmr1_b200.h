@@ -105,6 +105,61 @@ int gmr1b200_rach_decode_batch(uint8_t *rach, const gmr1b200_sbit_t *bits_e,
 int gmr1b200_xch_dc12_decode_batch(uint8_t *l2, const gmr1b200_sbit_t *bits_e,
                                    int32_t *conv_rv, int32_t *crc, int n, void *stream);
 
+/* ---- stage 2: pi/4-CxPSK burst demodulation (IQ window -> soft bits) ------------------------
+ * Burst formats: the ten descriptors of the reference's src/sdr/nb.c (include/osmocom/gmr1/sdr/
+ * nb.h:37-46), selected by id.  A burst "window" is burst_len*sps + search_window complex
+ * float samples, exactly what gmr1_rx.c:burst_map() cuts (src/gmr1_rx.c:149-170); the extra
+ * samples are the TOA search range.  Windows are addressed inside one IQ buffer (a recording
+ * or a batch of recordings) by sample offset, so nothing is copied to form them. */
+enum gmr1b200_burst_type {
+	GMR1B200_BT_BCCH = 0,       /* gmr1_bcch_burst        nb.c:54  */
+	GMR1B200_BT_DC2,            /* gmr1_dc2_burst         nb.c:81  */
+	GMR1B200_BT_DC6,            /* gmr1_dc6_burst         nb.c:112 */
+	GMR1B200_BT_DC12,           /* gmr1_dc12_burst        nb.c:143 */
+	GMR1B200_BT_NT3_SPEECH,     /* gmr1_nt3_speech_burst  nb.c:170 */
+	GMR1B200_BT_NT3_FACCH,      /* gmr1_nt3_facch_burst   nb.c:202 */
+	GMR1B200_BT_NT6,            /* gmr1_nt6_burst         nb.c:240 */
+	GMR1B200_BT_NT9,            /* gmr1_nt9_burst         nb.c:281 */
+	GMR1B200_BT_RACH,           /* gmr1_rach_burst        nb.c:317 */
+	GMR1B200_BT_SDCCH,          /* gmr1_sdcch_burst       nb.c:369 */
+	GMR1B200_BT_COUNT
+};
+
+/* symbols (incl. guard) and soft bits of a burst type; -EINVAL for a bad id */
+int gmr1b200_burst_len(int burst_type);
+int gmr1b200_burst_ebits(int burst_type);
+
+/* replaces gmr1_pi4cxpsk_demod, src/sdr/pi4cxpsk.c:520 (sdr/pi4cxpsk.h:101-105), n bursts/call.
+ *   iq          interleaved (re, im) float32, iq_len complex samples in total
+ *   win_ofs     [n] first complex sample of each window, or NULL: window b starts at b*win_stride
+ *   win_len     complex samples per window (same for the whole batch) = burst_len*sps + search
+ *   sps         samples per symbol, 4..16 (the sps < 4 interpolating path of the reference,
+ *               pi4cxpsk.c:298-343, is not implemented: -EINVAL)
+ *   freq_shift  [n] rad/symbol pre-rotation (the reference's freq_shift argument) or NULL,
+ *               then freq_shift0 applies to every burst
+ *   ebits       [n][ebits_stride] soft bits out (ebits_stride >= burst ebits)
+ *   sync_id, toa (samples, fractional), freq_err (rad/symbol), pwr: [n] each, any may be NULL
+ * sync_id[i] = -1 marks a window in which no training sequence correlated (the reference
+ * returns an error there); its ebits are zeroed. */
+int gmr1b200_pi4cxpsk_demod_batch(int burst_type, const float *iq, int64_t iq_len,
+                                  const int64_t *win_ofs, int64_t win_stride, int win_len, int sps,
+                                  const float *freq_shift, float freq_shift0,
+                                  gmr1b200_sbit_t *ebits, int ebits_stride,
+                                  int32_t *sync_id, float *toa, float *freq_err, float *pwr,
+                                  int n, void *stream);
+
+/* replaces gmr1_pi4cxpsk_detect, src/sdr/pi4cxpsk.c:617 (sdr/pi4cxpsk.h:107-110).
+ * burst_types[n_types] must have equal length and modulation rotation (as the reference
+ * requires); e_toa [n] expected TOA or NULL (then e_toa0; negative = no weighting).
+ * Outputs bt_id (index into burst_types), sync_id, toa: [n] each, any may be NULL. */
+int gmr1b200_pi4cxpsk_detect_batch(const int *burst_types, int n_types,
+                                   const float *e_toa, float e_toa0,
+                                   const float *iq, int64_t iq_len,
+                                   const int64_t *win_ofs, int64_t win_stride, int win_len, int sps,
+                                   const float *freq_shift, float freq_shift0,
+                                   int32_t *bt_id, int32_t *sync_id, float *toa,
+                                   int n, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -237,7 +237,7 @@ int osmo_conv_decode(const struct osmo_conv_code *code, const sbit_t *input, ubi
 	struct vdec d;
 	const int ns = 1 << (code->K - 1);
 	const int has_flush = (code->term == CONV_TERM_FLUSH);
-	int i, s, n, i_idx, min_ae;
+	int i, s, n, i_idx, min_ae, found = 0;
 	uint8_t cur, prev;
 
 	d.code = code;
@@ -274,14 +274,19 @@ int osmo_conv_decode(const struct osmo_conv_code *code, const sbit_t *input, ubi
 		cur = 0;
 		min_ae = d.ae[0];
 	} else {
+		/* Frozen deviation: upstream marks "no state found" with min_state = 0xff in a
+		 * uint8_t, which for the 256-state K9 codes collides with the valid state 255
+		 * (it would return -1 and leave the output unwritten = undefined in the caller).
+		 * The oracle keeps a separate flag, so state 255 decodes like any other. */
 		min_ae = MAX_AE;
-		cur = 0xff;
+		cur = 0;
 		for (s = 0; s < ns; s++)
 			if (d.ae[s] < (unsigned int)min_ae) {
 				min_ae = d.ae[s];
 				cur = s;
+				found = 1;
 			}
-		if (cur == 0xff) {
+		if (!found) {
 			min_ae = -1;
 			goto done;
 		}

@@ -218,23 +218,23 @@ float osmo_cxvec_peak_energy_find(const struct osmo_cxvec *cv, int win_size,
 	if (win_size <= 0)
 		return 0.0f;
 
-	/* sliding energy sum over win_size samples; history ring primed with zeros; a new
-	 * maximum is taken only on a strictly greater sum */
-	{
-		float he[win_size];
-		memset(he, 0x00, sizeof(he));
+	/* Energy of the win_size samples ending at idx (samples before the start count as 0, i.e.
+	 * the window slides in from the left); a new maximum is taken only on a strictly greater
+	 * sum, so the first of equal windows wins.
+	 * Frozen choice: upstream keeps a running sum (subtract the oldest, add the newest); here
+	 * every window is summed afresh, oldest sample first.  The two are the same function up to
+	 * float rounding drift of the running sum; the fresh sum has no history, which is what lets
+	 * a GPU evaluate all windows in parallel and still agree bit for bit. */
+	max_val = 0.0f;
+	max_idx = 0;
+	for (idx = 0; idx < cv->len; idx++) {
 		val = 0.0f;
-		max_val = 0.0f;
-		max_idx = 0;
-		for (idx = 0; idx < cv->len; idx++) {
-			hi = idx % win_size;
-			val -= he[hi];
-			he[hi] = osmo_normsqf(cv->data[idx]);
-			val += he[hi];
-			if (val > max_val) {
-				max_val = val;
-				max_idx = idx - win_size + 1;
-			}
+		for (hi = idx - win_size + 1; hi <= idx; hi++)
+			if (hi >= 0)
+				val += osmo_normsqf(cv->data[hi]);
+		if (val > max_val) {
+			max_val = val;
+			max_idx = idx - win_size + 1;
 		}
 	}
 	if (max_idx < 0)	/* frozen edge case: best window hangs over the start */

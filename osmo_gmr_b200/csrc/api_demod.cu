@@ -1,0 +1,138 @@
+// api_demod.cu - C ABI: batched pi/4-CxPSK demodulation / burst-type detection (include/gmr1_b200.h)
+#include "../../include/gmr1_b200.h"
+#include "api_common.h"
+#include "launch.h"
+
+using namespace gmr1;
+
+// device copy of the ten standard burst descriptors, one per device
+static BurstTab *g_d_bursts[64] = {nullptr};
+
+static cudaError_t device_bursts(const BurstTab **out)
+{
+	int dev = 0;
+	cudaError_t e = cudaGetDevice(&dev);
+	if (e != cudaSuccess)
+		return e;
+	if (dev >= 64)
+		return cudaErrorInvalidDevice;
+	if (!g_d_bursts[dev]) {
+		BurstTab *d = nullptr;
+		if ((e = cudaMalloc(&d, sizeof(BurstTab) * BT_COUNT)) != cudaSuccess)
+			return e;
+		for (int i = 0; i < BT_COUNT; i++)
+			if ((e = cudaMemcpy(d + i, &burst_tab(i), sizeof(BurstTab), cudaMemcpyHostToDevice)) != cudaSuccess)
+				return e;
+		g_d_bursts[dev] = d;
+	}
+	*out = g_d_bursts[dev];
+	return cudaSuccess;
+}
+
+static int run_demod(const int *types, int n_types, int mode, DemodArgs a, int64_t iq_len, void *stream)
+{
+	if (a.n < 0 || !a.iq || n_types < 1 || n_types > 8 || a.win_len < 1)
+		return set_err(-EINVAL, "pi4cxpsk batch: bad argument");
+	for (int i = 0; i < n_types; i++)
+		if (types[i] < 0 || types[i] >= BT_COUNT)
+			return set_err(-EINVAL, "pi4cxpsk batch: unknown burst type");
+	if (a.sps < 4 || a.sps > 16)
+		return set_err(-EINVAL, "pi4cxpsk batch: sps must be 4..16");
+	const BurstTab &t0 = burst_tab(types[0]);
+	if (a.win_len < t0.len * a.sps)
+		return set_err(-EINVAL, "pi4cxpsk batch: window shorter than the burst");
+	if (mode == 0 && (!a.ebits || a.ebits_stride < t0.ebits))
+		return set_err(-EINVAL, "pi4cxpsk_demod_batch: ebits NULL or ebits_stride too small");
+	if (a.n == 0)
+		return 0;
+	if (!a.ofs && (a.stride < 0 || (int64_t)(a.n - 1) * a.stride + a.win_len > iq_len))
+		return set_err(-EINVAL, "pi4cxpsk batch: windows exceed iq_len");
+
+	const BurstTab *d_all = nullptr;
+	cudaError_t e = device_bursts(&d_all);
+	if (e != cudaSuccess)
+		return cuda_rc(e, "burst table upload");
+
+	const size_t n = (size_t)a.n;
+	Stage s(stream);
+	a.iq = (const float2 *)s.in((const float *)a.iq, (size_t)iq_len * 2);
+	a.ofs = s.in(a.ofs, n);
+	a.freq_shift = s.in(a.freq_shift, n);
+	a.e_toa = s.in(a.e_toa, n);
+	a.ebits = s.out(a.ebits, n * (size_t)a.ebits_stride);
+	a.sync_id = s.out(a.sync_id, n);
+	a.bt_id = s.out(a.bt_id, n);
+	a.toa = s.out(a.toa, n);
+	a.freq_err = s.out(a.freq_err, n);
+	a.pwr = s.out(a.pwr, n);
+
+	// the kernel takes a dense array of the selected descriptors
+	BurstTab h_sel[8];
+	for (int i = 0; i < n_types; i++)
+		h_sel[i] = burst_tab(types[i]);
+	const BurstTab *d_sel = nullptr;
+	if (n_types == 1) {
+		d_sel = d_all + types[0];
+	} else {
+		BurstTab *tmp = nullptr;
+		if (!s.failed()) {
+			cudaError_t e2 = cudaMallocAsync(&tmp, sizeof(BurstTab) * n_types, (cudaStream_t)stream);
+			if (e2 == cudaSuccess) {
+				for (int i = 0; i < n_types; i++)
+					cudaMemcpyAsync(tmp + i, d_all + types[i], sizeof(BurstTab), cudaMemcpyDeviceToDevice,
+					                (cudaStream_t)stream);
+				d_sel = tmp;
+			} else {
+				return s.finish(e2, "descriptor scratch");
+			}
+		}
+	}
+	if (!s.failed()) {
+		e = launch_demod(a, d_sel, h_sel, n_types, mode, (cudaStream_t)stream);
+		if (e == cudaSuccess)
+			g_launches.fetch_add(1);
+	}
+	if (n_types > 1 && d_sel)
+		cudaFreeAsync((void *)d_sel, (cudaStream_t)stream);
+	return s.finish(e, "pi4cxpsk kernel");
+}
+
+extern "C" {
+
+int gmr1b200_burst_len(int bt)
+{
+	return (bt < 0 || bt >= BT_COUNT) ? -EINVAL : burst_tab(bt).len;
+}
+
+int gmr1b200_burst_ebits(int bt)
+{
+	return (bt < 0 || bt >= BT_COUNT) ? -EINVAL : burst_tab(bt).ebits;
+}
+
+int gmr1b200_pi4cxpsk_demod_batch(int burst_type, const float *iq, int64_t iq_len, const int64_t *win_ofs,
+                                  int64_t win_stride, int win_len, int sps, const float *freq_shift, float freq_shift0,
+                                  int8_t *ebits, int ebits_stride, int32_t *sync_id, float *toa, float *freq_err,
+                                  float *pwr, int n, void *stream)
+{
+	DemodArgs a = {};
+	a.iq = (const float2 *)iq; a.ofs = win_ofs; a.stride = win_stride; a.n = n; a.win_len = win_len; a.sps = sps;
+	a.freq_shift = freq_shift; a.freq_shift0 = freq_shift0; a.e_toa0 = -1.0f;
+	a.ebits = ebits; a.ebits_stride = ebits_stride; a.sync_id = sync_id; a.toa = toa; a.freq_err = freq_err; a.pwr = pwr;
+	return run_demod(&burst_type, 1, 0, a, iq_len, stream);
+}
+
+int gmr1b200_pi4cxpsk_detect_batch(const int *burst_types, int n_types, const float *e_toa, float e_toa0,
+                                   const float *iq, int64_t iq_len, const int64_t *win_ofs, int64_t win_stride,
+                                   int win_len, int sps, const float *freq_shift, float freq_shift0,
+                                   int32_t *bt_id, int32_t *sync_id, float *toa, int n, void *stream)
+{
+	if (!burst_types)
+		return set_err(-EINVAL, "pi4cxpsk_detect_batch: burst_types NULL");
+	DemodArgs a = {};
+	a.iq = (const float2 *)iq; a.ofs = win_ofs; a.stride = win_stride; a.n = n; a.win_len = win_len; a.sps = sps;
+	a.freq_shift = freq_shift; a.freq_shift0 = freq_shift0; a.e_toa = e_toa; a.e_toa0 = e_toa0;
+	a.bt_id = bt_id; a.sync_id = sync_id; a.toa = toa;
+	return run_demod(burst_types, n_types, 1, a, iq_len, stream);
+}
+
+}  // extern "C"

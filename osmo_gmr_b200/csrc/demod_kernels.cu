@@ -1,0 +1,476 @@
+// demod_kernels.cu - stage 2 of the receive path on the GPU: batched pi/4-CxPSK burst demodulation.
+//
+// One warp per burst.  The burst window (len*sps + search-window complex float samples, 4-11 KB
+// at sps 4) is read from HBM exactly once into the warp's slice of shared memory; every later
+// pass (mean, variance, normalise + derotate, training-sequence correlation over all search
+// offsets, early/late peak search, symbol pick, frequency / phase estimation, soft bits) works
+// out of shared memory and registers, with warp-shuffle reductions.  Output per burst: ebits
+// (int8), sync id, fractional TOA, frequency error, sync power.
+//
+// Replaces, for a whole batch per launch, the reference's
+//   gmr1_pi4cxpsk_demod       src/sdr/pi4cxpsk.c:520-602
+//   _gmr1_pi4cxpsk_sync_find  :184-268   (incl. the never-reset accumulator quirk, :207/:232)
+//   _gmr1_pi4cxpsk_align      :280-348   (sps >= 4 path)
+//   _gmr1_pi4cxpsk_freq_err   :360-406
+//   _gmr1_pi4cxpsk_phase      :415-433
+//   _gmr1_pi4cxpsk_soft_symbols / _soft_bits  :442-503
+//   gmr1_pi4cxpsk_detect      :617-682
+// and the libosmo-dsp primitives they call (sig_normalize, correlate, peak_energy_find with
+// PEAK_EARLY_LATE, interpolate_point, rotate, scale) as restated in SURVEY.md Appendix A.2.
+//
+// Float contract: same operations in the same order wherever the order is observable at
+// reasonable cost (per-offset correlation sums, sinc-interpolation tap order, chunk sums);
+// the two whole-window reductions (mean, variance) are tree sums, so results agree with the
+// C path to float rounding, not bit for bit.  Built with -fmad=false, IEEE div/sqrt, and the
+// accurate sincosf/atan2f (no fast-math).
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "gmr1_tables.h"
+#include "launch.h"
+
+namespace gmr1 {
+
+static constexpr int DM_WARPS = 4;
+static constexpr float PI_F = 3.14159265358979323846264338327f;
+
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+	for (int o = 16; o; o >>= 1)
+		v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+
+__device__ __forceinline__ float sinc_f(float x)     // osmo_sinc
+{
+	return (x >= 0.01f || x <= -0.01f) ? sinf(x) / x : 1.0f;
+}
+
+// |re + j im| the way glibc's cabsf/hypotf evaluates it (double sqrt, then round to float)
+__device__ __forceinline__ float cabs_f(float re, float im)
+{
+	return (float)sqrt((double)re * (double)re + (double)im * (double)im);
+}
+
+// conj(ref) * g for ref in {1, j, -1, -j} (symbol index 0..3): exact component shuffles
+__device__ __forceinline__ float2 mul_conj_sym(int sym, float2 g)
+{
+	switch (sym & 3) {
+	case 0:  return make_float2(g.x, g.y);
+	case 1:  return make_float2(g.y, -g.x);
+	case 2:  return make_float2(-g.x, -g.y);
+	default: return make_float2(-g.y, g.x);
+	}
+}
+
+// Sinc interpolation of the real vector acc[0..len) at `early` and at `early + 2` (the late
+// gate), 10 taps either side, taps summed in index order by one lane each.  Both share the same
+// 21 sinc values because (i+2) - (early+2) == i - early exactly in fp32 for the values that occur.
+__device__ __forceinline__ void interp_early_late(const float *acc, int len, float early, float *terms,
+                                                  int lane, float &ev, float &lv)
+{
+	const int fe = (int)floorf(early);
+	if (lane < 21) {
+		const int k = fe - 10 + lane;
+		const float s = sinc_f(PI_F * ((float)k - early));
+		terms[lane]      = (k >= 0 && k < len) ? acc[k] * s : 0.0f;
+		terms[32 + lane] = (k + 2 >= 0 && k + 2 < len) ? acc[k + 2] * s : 0.0f;
+	}
+	__syncwarp();
+	float sum = 0.0f;
+	if (lane < 2) {
+		const float *t = terms + 32 * lane;
+#pragma unroll
+		for (int i = 0; i < 21; i++)
+			sum += t[i];
+	}
+	__syncwarp();
+	ev = __shfl_sync(0xffffffffu, sum, 0);
+	lv = __shfl_sync(0xffffffffu, sum, 1);
+}
+
+__device__ __forceinline__ float interp_point(const float *acc, int len, float pos, float *terms, int lane)
+{
+	const int fp = (int)floorf(pos);
+	if (lane < 21) {
+		const int k = fp - 10 + lane;
+		terms[lane] = (k >= 0 && k < len) ? acc[k] * sinc_f(PI_F * ((float)k - pos)) : 0.0f;
+	}
+	__syncwarp();
+	float sum = 0.0f;
+	if (lane == 0) {
+#pragma unroll
+		for (int i = 0; i < 21; i++)
+			sum += terms[i];
+	}
+	__syncwarp();
+	return __shfl_sync(0xffffffffu, sum, 0);
+}
+
+// osmo_cxvec_peak_energy_find(acc, 3, PEAK_EARLY_LATE, &peak) on a real vector; all lanes
+// return the same position / peak value
+__device__ float peak_early_late(const float *acc, int w, float *terms, int lane, float &peak_val)
+{
+	const int win = w < 3 ? w : 3;
+	float best = 0.0f;
+	int best_idx = 0x7fffffff;
+	for (int idx = lane; idx < w; idx += 32) {
+		float val = 0.0f;
+		for (int hi = idx - win + 1; hi <= idx; hi++)
+			if (hi >= 0) {
+				const float a = acc[hi];
+				val += a * a;
+			}
+		if (val > best) {
+			best = val;
+			best_idx = idx;
+		}
+	}
+#pragma unroll
+	for (int o = 16; o; o >>= 1) {
+		const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+		const int oi = __shfl_xor_sync(0xffffffffu, best_idx, o);
+		if (ov > best || (ov == best && oi < best_idx)) {
+			best = ov;
+			best_idx = oi;
+		}
+	}
+	int max_idx = (best > 0.0f) ? best_idx - win + 1 : 0;
+	if (max_idx < 0)
+		max_idx = 0;
+
+	int mwi = max_idx;
+	float mv = -1.0f;
+	for (int idx = max_idx; idx < max_idx + win; idx++) {
+		const float a = acc[idx], e = a * a;
+		if (e > mv) {
+			mv = e;
+			mwi = idx;
+		}
+	}
+
+	float early = (float)(mwi - 1), incr = 0.5f;
+	while (incr > (1.0f / 1024.0f)) {
+		float ev, lv;
+		interp_early_late(acc, w, early, terms, lane, ev, lv);
+		const float e2 = ev * ev, l2 = lv * lv;
+		if (e2 < l2)
+			early += incr;
+		else if (e2 > l2)
+			early -= incr;
+		else
+			break;
+		incr *= 0.5f;
+	}
+	const float pos = early + 1.0f;
+	peak_val = interp_point(acc, w, pos, terms, lane);
+	return pos;
+}
+
+// Search all sync sequences of one burst type in the normalised/derotated window `y`.
+// Returns the winning sequence index (all lanes), its TOA and power (pi4cxpsk.c:184-268).
+// accv is NOT cleared between sequences - the reference clears it once per call (:207) and
+// keeps adding (:232-233); tl restarts per sequence (:216).
+__device__ int sync_find(const BurstTab &bt, const float2 *y, int sps, int w, float *accv, float *terms,
+                         int lane, float &toa, float &pwr)
+{
+	for (int m = lane; m < w; m += 32)
+		accv[m] = 0.0f;
+	__syncwarp();
+	float p_toa = 0.0f, p_pwr = 0.0f;
+	int p_idx = -1;
+	for (int s = 0; s < bt.n_sync; s++) {
+		int tl = 0;
+		for (int c = 0; c < bt.n_chunk[s]; c++) {
+			const int b0 = bt.s_pos[s][c] * sps, cl = bt.s_len[s][c];
+			for (int m = lane; m < w; m += 32) {
+				float cr = 0.0f, ci = 0.0f;
+				for (int n = 0; n < cl; n++) {
+					const float2 p = mul_conj_sym(bt.s_sym[s][c][n], y[b0 + m + n * sps]);
+					cr += p.x;
+					ci += p.y;
+				}
+				accv[m] += cabs_f(cr, ci);
+			}
+			tl += cl;
+		}
+		__syncwarp();
+		float peak;
+		const float s_toa = peak_early_late(accv, w, terms, lane, peak);
+		peak /= (float)tl;
+		const float s_pwr = peak * peak;
+		if (s_pwr > p_pwr) {
+			p_pwr = s_pwr;
+			p_toa = s_toa;
+			p_idx = s;
+		}
+	}
+	toa = p_toa;
+	pwr = p_pwr;
+	return p_idx;
+}
+
+// per-warp shared-memory slice
+struct WarpSmem {
+	float2 *win;     // [L]   window, later normalised + derotated in place
+	float2 *z;       // [len] one sample per symbol
+	float  *accv;    // [w]
+	float  *terms;   // [64]
+};
+
+__device__ __forceinline__ WarpSmem carve(uint8_t *base, int L, int nsym, int w)
+{
+	WarpSmem s;
+	s.win = (float2 *)base;
+	base += (size_t)((L + 1) & ~1) * 8;
+	s.z = (float2 *)base;
+	base += (size_t)((nsym + 1) & ~1) * 8;
+	s.accv = (float *)base;
+	base += (size_t)((w + 3) & ~3) * 4;
+	s.terms = (float *)base;
+	return s;
+}
+
+static inline size_t warp_smem_bytes(int L, int nsym, int w)
+{
+	return (size_t)((L + 1) & ~1) * 8 + (size_t)((nsym + 1) & ~1) * 8 + (size_t)((w + 3) & ~3) * 4 + 64 * 4;
+}
+
+// load + osmo_cxvec_sig_normalize(in, 1, fs) into s.win; returns nothing, all lanes in step
+__device__ void load_normalize(const float2 *__restrict__ x, int L, float fs, float2 *win, int lane)
+{
+	float sr = 0.0f, si = 0.0f;
+	for (int i = lane; i < L; i += 32) {
+		const float2 v = __ldg(&x[i]);
+		win[i] = v;
+		sr += v.x;
+		si += v.y;
+	}
+	sr = warp_sum(sr);
+	si = warp_sum(si);
+	const float ar = sr / (float)L, ai = si / (float)L;
+	__syncwarp();
+	float acc = 0.0f;
+	for (int i = lane; i < L; i += 32) {
+		const float2 v = win[i];
+		const float dr = v.x - ar, di = v.y - ai;
+		acc += dr * dr + di * di;
+	}
+	acc = warp_sum(acc);
+	float sd = sqrtf(acc / (float)L);
+	if (sd == 0.0f)
+		sd = 1.0f;
+	for (int i = lane; i < L; i += 32) {
+		const float2 v = win[i];
+		float yr = (v.x - ar) / sd, yi = (v.y - ai) / sd;
+		if (fs != 0.0f) {
+			float sn, cs;
+			sincosf(fs * (float)i, &sn, &cs);
+			const float tr = yr * cs - yi * sn, ti = yr * sn + yi * cs;
+			yr = tr;
+			yi = ti;
+		}
+		win[i] = make_float2(yr, yi);
+	}
+	__syncwarp();
+}
+
+// ---- kernel ---------------------------------------------------------------------------------------
+// mode 0: demod (bt[0] only).  mode 1: detect among n_bt burst types (pi4cxpsk.c:617-682).
+__global__ void __launch_bounds__(DM_WARPS * 32)
+demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int mode, int warp_bytes)
+{
+	extern __shared__ __align__(16) uint8_t smem[];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int b = blockIdx.x * DM_WARPS + warp;
+	if (b >= a.n)
+		return;
+
+	const BurstTab &bt0 = bts[0];
+	const int sps = a.sps, L = a.win_len;
+	const int w = L - bt0.len * sps + 1;
+	WarpSmem s = carve(smem + (size_t)warp * warp_bytes, L, bt0.len, w);
+
+	const float2 *x = a.iq + (a.ofs ? a.ofs[b] : (int64_t)b * a.stride);
+	const float freq_shift = a.freq_shift ? a.freq_shift[b] : a.freq_shift0;
+	const float fs = (freq_shift - bt0.rotation) / (float)sps;
+
+	load_normalize(x, L, fs, s.win, lane);
+
+	if (mode == 1) {
+		const float e_toa = a.e_toa ? a.e_toa[b] : a.e_toa0;
+		int p_id = -1, p_sid = -1;
+		float p_toa = 0.0f, p_pwr = 0.0f;
+		for (int id = 0; id < n_bt; id++) {
+			float toa, pwr;
+			const int sid = sync_find(bts[id], s.win, sps, w, s.accv, s.terms, lane, toa, pwr);
+			if (e_toa >= 0.0f)     // the reference divides by fabs() in double (pi4cxpsk.c:658-659)
+				pwr = (float)((double)pwr / fabs((double)(e_toa - toa)));
+			if (pwr > p_pwr) {
+				p_id = id;
+				p_sid = sid;
+				p_pwr = pwr;
+				p_toa = toa;
+			}
+		}
+		if (lane == 0) {
+			if (a.bt_id) a.bt_id[b] = p_id;
+			if (a.sync_id) a.sync_id[b] = p_sid;
+			if (a.toa) a.toa[b] = p_toa;
+			if (a.pwr) a.pwr[b] = p_pwr;
+		}
+		return;
+	}
+
+	const BurstTab &bt = bt0;
+	float toa, pwr;
+	const int sync_id = sync_find(bt, s.win, sps, w, s.accv, s.terms, lane, toa, pwr);
+	if (lane == 0) {
+		if (a.sync_id) a.sync_id[b] = sync_id;
+		if (a.toa) a.toa[b] = toa;
+		if (a.pwr) a.pwr[b] = pwr;
+	}
+	if (sync_id < 0) {          // nothing correlated (all-zero input): the reference returns -errno
+		if (lane == 0 && a.freq_err) a.freq_err[b] = 0.0f;
+		for (int k = lane; k < bt.ebits; k += 32)
+			a.ebits[(size_t)b * a.ebits_stride + k] = 0;
+		return;
+	}
+
+	// align: one sample per symbol at the rounded TOA (sps >= 4 path, pi4cxpsk.c:286-297)
+	const int d = (int)roundf(toa);
+	for (int i = lane; i < bt.len; i += 32) {
+		int q = i * sps + d;       // d >= -1; index -1 would read before the window: clamp
+		q = q < 0 ? 0 : (q >= L ? L - 1 : q);
+		s.z[i] = s.win[q];
+	}
+	__syncwarp();
+
+	// fine frequency error from the chunk-to-chunk phase slope (pi4cxpsk.c:360-406)
+	const int nch = bt.n_chunk[sync_id];
+	float ferr = 0.0f;
+	if (nch > 1) {
+		float cr = 0.0f, ci = 0.0f, pos = 0.0f;
+		if (lane < nch) {
+			const int p0 = bt.s_pos[sync_id][lane], cl = bt.s_len[sync_id][lane];
+			pos = (float)p0 + (float)cl / 2.0f;
+			for (int j = 0; j < cl; j++) {
+				const float2 p = mul_conj_sym(bt.s_sym[sync_id][lane][j], s.z[p0 + j]);
+				cr += p.x;
+				ci += p.y;
+			}
+		}
+		float f = 0.0f;
+		for (int i = 1; i < nch; i++) {
+			const float ar = __shfl_sync(0xffffffffu, cr, i), ai = __shfl_sync(0xffffffffu, ci, i);
+			const float br = __shfl_sync(0xffffffffu, cr, i - 1), bi = __shfl_sync(0xffffffffu, ci, i - 1);
+			const float pa = __shfl_sync(0xffffffffu, pos, i), pb = __shfl_sync(0xffffffffu, pos, i - 1);
+			// corr[i] * conj(corr[i-1])
+			const float re = ar * br - ai * (-bi), im = ar * (-bi) + ai * br;
+			f += atan2f(im, re) / (pa - pb);
+		}
+		ferr = f / (float)(nch - 1);
+	}
+	if (lane == 0 && a.freq_err) a.freq_err[b] = ferr;
+
+	// compensate (osmo_cxvec_rotate by -ferr), pi4cxpsk.c:574-575
+	if (ferr != 0.0f) {
+		for (int i = lane; i < bt.len; i += 32) {
+			float sn, cs;
+			sincosf((-ferr) * (float)i, &sn, &cs);
+			const float2 v = s.z[i];
+			s.z[i] = make_float2(v.x * cs - v.y * sn, v.x * sn + v.y * cs);
+		}
+		__syncwarp();
+	}
+
+	// phase reference from all sync chunks, one accumulator in symbol order (pi4cxpsk.c:415-433)
+	float pr = 0.0f, pi = 0.0f;
+	if (lane == 0) {
+		for (int c = 0; c < nch; c++) {
+			const int p0 = bt.s_pos[sync_id][c], cl = bt.s_len[sync_id][c];
+			for (int j = 0; j < cl; j++) {
+				const float2 p = mul_conj_sym(bt.s_sym[sync_id][c][j], s.z[p0 + j]);
+				pr += p.x;
+				pi += p.y;
+			}
+		}
+		const float ab = cabs_f(pr, pi);
+		pr /= ab;
+		pi /= ab;
+	}
+	pr = __shfl_sync(0xffffffffu, pr, 0);
+	pi = __shfl_sync(0xffffffffu, pi, 0);
+
+	// scale by conj(phasor), soft symbols, soft bits (pi4cxpsk.c:581, 442-503)
+	const int nbits = bt.nbits, mask = (1 << nbits) - 1;
+	const float dd = (2.0f * PI_F) / (float)(1 << nbits);
+	const bool scale_real = (-pi == 0.0f);     // osmo_cxvec_scale takes the real path if imag == 0
+	int8_t *eb = a.ebits + (size_t)b * a.ebits_stride;
+	int kbase = 0;
+	for (int c = 0; c < bt.n_data; c++) {
+		const int p0 = bt.d_pos[c], cl = bt.d_len[c];
+		for (int j = lane; j < cl; j += 32) {
+			const float2 v = s.z[p0 + j];
+			float zr, zi;
+			if (scale_real) {
+				zr = v.x * pr;
+				zi = v.y * pr;
+			} else {
+				zr = v.x * pr - v.y * (-pi);
+				zi = v.x * (-pi) + v.y * pr;
+			}
+			const float sv = atan2f(zi, zr) / dd;
+			const float svr = roundf(sv);
+			const int sp = (int)svr & mask;
+			const int ss = (svr > sv ? (sp - 1) : (sp + 1)) & mask;
+			const int dq = (int)roundf((2.0f * fabsf(svr - sv)) * 64.0f);
+			// Gray map of the symbol index: {00, 01, 11, 10} (2 bits) / {0, 1} (1 bit), MSB first
+			const int gp = nbits == 2 ? (sp ^ (sp >> 1)) : sp;
+			const int gs = nbits == 2 ? (ss ^ (ss >> 1)) : ss;
+			for (int q = 0; q < nbits; q++) {
+				const int vp = (gp >> (nbits - 1 - q)) & 1, vs = (gs >> (nbits - 1 - q)) & 1;
+				const int val = 127 - ((vp ^ vs) ? dq : (dq >> 1));
+				eb[kbase + j * nbits + q] = (int8_t)(vp ? -val : val);
+			}
+		}
+		kbase += cl * nbits;
+	}
+}
+
+// ---- launcher --------------------------------------------------------------------------------------
+cudaError_t launch_demod(const DemodArgs &a, const BurstTab *d_bts, const BurstTab *h_bts, int n_bt, int mode,
+                         cudaStream_t st)
+{
+	if (a.n <= 0)
+		return cudaSuccess;
+	int maxlen = 0, minlen = 1 << 30;
+	for (int i = 0; i < n_bt; i++) {
+		maxlen = h_bts[i].len > maxlen ? h_bts[i].len : maxlen;
+		minlen = h_bts[i].len < minlen ? h_bts[i].len : minlen;
+	}
+	if (maxlen != minlen)
+		return cudaErrorInvalidValue;      // detect needs length-compatible burst types
+	const int w = a.win_len - maxlen * a.sps + 1;
+	if (w < 1 || a.sps < 4 || a.sps > 16)
+		return cudaErrorInvalidValue;
+	const size_t wb = (warp_smem_bytes(a.win_len, maxlen, w) + 15) & ~(size_t)15;
+	const size_t smem = wb * DM_WARPS;
+	if (smem > 227 * 1024)
+		return cudaErrorInvalidValue;
+	static size_t attr_set[64] = {0};
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (dev >= 64 || attr_set[dev] < smem) {
+		cudaError_t e = cudaFuncSetAttribute(demod_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (e != cudaSuccess)
+			return e;
+		if (dev < 64)
+			attr_set[dev] = smem;
+	}
+	demod_kernel<<<(a.n + DM_WARPS - 1) / DM_WARPS, DM_WARPS * 32, smem, st>>>(a, d_bts, n_bt, mode, (int)wb);
+	return cudaGetLastError();
+}
+
+}  // namespace gmr1

@@ -1,9 +1,35 @@
 // launch.h - internal launcher entry points shared between the kernel translation units and
-// the C-ABI layer (api.cu).
+// the C-ABI layer (api_*.cu).
 #pragma once
 #include <cuda_runtime.h>
 #include "decode_unit.cuh"
 
 namespace gmr1 {
+
+// ---- stage 3
 cudaError_t launch_decode(int ch, const DecodeArgs &a, cudaStream_t st);
-}
+
+// ---- stage 2
+struct DemodArgs {
+	const float2  *iq;          // complex float samples (device)
+	const int64_t *ofs;         // [n] first sample of each burst window within iq, or NULL
+	int64_t        stride;      // used when ofs == NULL: window b starts at b*stride
+	int32_t        n, win_len, sps;
+	const float   *freq_shift;  // [n] rad/symbol or NULL (then freq_shift0)
+	float          freq_shift0;
+	const float   *e_toa;       // detect: [n] expected TOA or NULL (then e_toa0; < 0 = none)
+	float          e_toa0;
+	int8_t        *ebits;       // [n][ebits_stride]
+	int32_t        ebits_stride;
+	int32_t       *sync_id;     // [n] or NULL
+	int32_t       *bt_id;       // detect: [n] or NULL
+	float         *toa;         // [n] or NULL
+	float         *freq_err;    // [n] or NULL
+	float         *pwr;         // [n] or NULL (sync power; detect: after the e_toa weighting)
+};
+
+// d_bts: n_bt burst descriptors in device memory, h_bts: the same on the host (for geometry)
+cudaError_t launch_demod(const DemodArgs &a, const BurstTab *d_bts, const BurstTab *h_bts, int n_bt, int mode,
+                         cudaStream_t st);
+
+}  // namespace gmr1

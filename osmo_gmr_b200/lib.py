@@ -8,6 +8,8 @@ LIB_PATH = os.path.join(_HERE, "libgmr1_b200.so")
 
 _P = ctypes.c_void_p
 _I = ctypes.c_int
+_L = ctypes.c_int64
+_F = ctypes.c_float
 
 
 def build(verbose=False):
@@ -54,6 +56,10 @@ class Lib:
         "gmr1b200_tch9_decode_batch": [_P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _P],
         "gmr1b200_rach_decode_batch": [_P, _P, _P, _I, _P, _P, _P, _I, _P],
         "gmr1b200_xch_dc12_decode_batch": [_P, _P, _P, _P, _I, _P],
+        "gmr1b200_burst_len": [_I],
+        "gmr1b200_burst_ebits": [_I],
+        "gmr1b200_pi4cxpsk_demod_batch": [_I, _P, _L, _P, _L, _I, _I, _P, _F, _P, _I, _P, _P, _P, _P, _I, _P],
+        "gmr1b200_pi4cxpsk_detect_batch": [_P, _I, _P, _F, _P, _L, _P, _L, _I, _I, _P, _F, _P, _P, _P, _I, _P],
     }
 
     def __init__(self, path=LIB_PATH):

@@ -107,6 +107,38 @@ class Oracle:
         crc = self.c.gmr1_rach_decode(p(r), p(e), ctypes.c_uint8(int(sb_mask)), ctypes.byref(cv), c2)
         return r, crc, cv.value, list(c2)
 
+    # ---------------- SDR
+    def _burst(self, name):
+        return ctypes.addressof(ctypes.c_char.in_dll(self.c, f"gmr1_{name}_burst"))
+
+    def _cxvec(self, x):
+        x = np.ascontiguousarray(x, np.complex64)
+        return CxVec(len=x.shape[0], max_len=x.shape[0], flags=0, data=x.ctypes.data), x
+
+    def demod(self, name, window, sps, freq_shift):
+        """gmr1_pi4cxpsk_demod -> (rc, ebits, sync_id, toa, freq_err)"""
+        neb = {"bcch": 424, "dc2": 132, "dc6": 432, "dc12": 432, "nt3_speech": 212, "nt3_facch": 104,
+               "nt6": 434, "nt9": 662, "rach": 494, "sdcch": 208}[name]
+        cv, keep = self._cxvec(window)
+        eb = np.zeros(neb, np.int8)
+        sid, toa, fe = ctypes.c_int(-99), ctypes.c_float(), ctypes.c_float()
+        fn = self.c.gmr1_pi4cxpsk_demod
+        fn.argtypes = [P, P, ctypes.c_int, ctypes.c_float, P, P, P, P]
+        rc = fn(self._burst(name), ctypes.addressof(cv), sps, float(freq_shift), p(eb),
+                ctypes.addressof(sid), ctypes.addressof(toa), ctypes.addressof(fe))
+        return rc, eb, sid.value, toa.value, fe.value
+
+    def detect(self, names, e_toa, window, sps, freq_shift):
+        """gmr1_pi4cxpsk_detect -> (rc, bt_id, sync_id, toa)"""
+        cv, keep = self._cxvec(window)
+        arr = (P * (len(names) + 1))(*[self._burst(n) for n in names], None)
+        bt, sid, toa = ctypes.c_int(-99), ctypes.c_int(-99), ctypes.c_float()
+        fn = self.c.gmr1_pi4cxpsk_detect
+        fn.argtypes = [P, ctypes.c_float, P, ctypes.c_int, ctypes.c_float, P, P, P]
+        rc = fn(arr, float(e_toa), ctypes.addressof(cv), sps, float(freq_shift),
+                ctypes.addressof(bt), ctypes.addressof(sid), ctypes.addressof(toa))
+        return rc, bt.value, sid.value, toa.value
+
     def a5(self, n, key, fn, nbits):
         dl = np.zeros(nbits, np.uint8)
         k = np.ascontiguousarray(key, np.uint8)
