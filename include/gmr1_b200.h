@@ -160,6 +160,46 @@ int gmr1b200_pi4cxpsk_detect_batch(const int *burst_types, int n_types,
                                    int32_t *bt_id, int32_t *sync_id, float *toa,
                                    int n, void *stream);
 
+/* ---- transmit side: channel encoders (host code; used by the signal generator and tools) ----
+ * Bit-exact mirrors of the reference encoders; they run on the CPU on purpose (not the hot path). */
+
+/* replaces gmr1_bcch_encode (src/l1/bcch.c:59), gmr1_ccch_encode (ccch.c:59), gmr1_xch_dc12_encode
+ * (xch_dc12.c:63).  chan: 0 = BCCH (bits_e [n][424]), 1 = CCCH ([n][432]), 2 = DC12 ([n][432]);
+ * l2 [n][24]; bits_e are hard ubits. */
+int gmr1b200_xcch_encode_batch(int chan, gmr1b200_ubit_t *bits_e, const uint8_t *l2, int n);
+/* replaces gmr1_facch3_encode, src/l1/facch3.c:64.  bits_e [416], l2 [10], bits_s [32], ciph [384]/NULL */
+int gmr1b200_facch3_encode(gmr1b200_ubit_t *bits_e, const uint8_t *l2, const gmr1b200_ubit_t *bits_s,
+                           const gmr1b200_ubit_t *ciph);
+/* replaces gmr1_facch9_encode, src/l1/facch9.c:57.  bits_e [662], l2 [38], sacch [10], status [4], ciph [658]/NULL */
+int gmr1b200_facch9_encode(gmr1b200_ubit_t *bits_e, const uint8_t *l2, const gmr1b200_ubit_t *bits_sacch,
+                           const gmr1b200_ubit_t *bits_status, const gmr1b200_ubit_t *ciph);
+/* replaces gmr1_tch9_encode + gmr1_interleaver_init/fini, src/l1/tch9.c:93, interleave.c:95-130 */
+void *gmr1b200_tch9_interleaver_new(void);
+void gmr1b200_tch9_interleaver_free(void *interleaver);
+int gmr1b200_tch9_encode(gmr1b200_ubit_t *bits_e, const uint8_t *l2, int mode, const gmr1b200_ubit_t *bits_sacch,
+                         const gmr1b200_ubit_t *bits_status, const gmr1b200_ubit_t *ciph, void *interleaver);
+/* replaces gmr1_rach_encode, src/l1/rach.c:76.  bits_e [494], rach [18] */
+int gmr1b200_rach_encode(gmr1b200_ubit_t *bits_e, const uint8_t *rach, int sb_mask);
+/* replaces gmr1_tch3_encode, src/l1/tch3.c:60 - the reference passes the arguments of
+ * osmo_conv_encode in the wrong order (tch3.c:81), this one encodes what gmr1_tch3_decode decodes.
+ * bits_e [212], frame0/frame1 [10] MSB first, bits_s [4], ciph [208]/NULL, m = mux mode */
+int gmr1b200_tch3_encode(gmr1b200_ubit_t *bits_e, const uint8_t *frame0, const uint8_t *frame1,
+                         const gmr1b200_ubit_t *bits_s, const gmr1b200_ubit_t *ciph, int m);
+
+/* ---- workload synthesis: pi/4-CxPSK burst generator (GPU) -------------------------------------
+ * Not in the reference (its gmr1_pi4cxpsk_mod, src/sdr/pi4cxpsk.c:741, is 1 sample/symbol with no
+ * pulse or channel).  Writes n burst windows of win_len complex samples into iq: hard bits ->
+ * symbols per the burst format, pi/4 rotation, raised-cosine pulse (RRC 0.35 x RRC 0.35) at `sps`,
+ * symbol 0 at fractional sample position toa inside the window, carrier offset cfo (rad/symbol),
+ * phase (rad), amplitude amp, AWGN at Es/N0 = esn0_db (Philox4x32-10 keyed by seed, burst, sample).
+ * Each per-burst parameter is an array [n] or NULL (then the scalar that follows it applies). */
+int gmr1b200_synth_bursts(int burst_type, const gmr1b200_ubit_t *ebits, int ebits_stride, const int32_t *sync_id,
+                          int sps, int win_len, const float *toa, float toa0, const float *cfo, float cfo0,
+                          const float *phase, float phase0, const float *esn0_db, float esn0_db0,
+                          const float *amp, float amp0, uint64_t seed,
+                          float *iq, int64_t iq_len, const int64_t *win_ofs, int64_t win_stride,
+                          int n, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

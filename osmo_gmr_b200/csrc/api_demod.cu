@@ -8,7 +8,7 @@ using namespace gmr1;
 // device copy of the ten standard burst descriptors, one per device
 static BurstTab *g_d_bursts[64] = {nullptr};
 
-static cudaError_t device_bursts(const BurstTab **out)
+cudaError_t gmr1::device_bursts(const BurstTab **out)
 {
 	int dev = 0;
 	cudaError_t e = cudaGetDevice(&dev);
@@ -97,7 +97,55 @@ static int run_demod(const int *types, int n_types, int mode, DemodArgs a, int64
 	return s.finish(e, "pi4cxpsk kernel");
 }
 
+static int run_synth(int burst_type, SynthArgs a, int64_t iq_len, void *stream)
+{
+	if (burst_type < 0 || burst_type >= BT_COUNT || a.n < 0 || !a.ebits || !a.iq)
+		return set_err(-EINVAL, "synth_bursts: bad argument");
+	const BurstTab &t = burst_tab(burst_type);
+	if (a.sps < 1 || a.sps > 16 || a.win_len < 1 || a.ebits_stride < t.ebits)
+		return set_err(-EINVAL, "synth_bursts: bad sps / win_len / ebits_stride");
+	if (a.n == 0)
+		return 0;
+	if (!a.ofs && (a.stride < 0 || (int64_t)(a.n - 1) * a.stride + a.win_len > iq_len))
+		return set_err(-EINVAL, "synth_bursts: windows exceed iq_len");
+	const BurstTab *d_all = nullptr;
+	cudaError_t e = device_bursts(&d_all);
+	if (e != cudaSuccess)
+		return cuda_rc(e, "burst table upload");
+	const size_t n = (size_t)a.n;
+	Stage s(stream);
+	a.ebits = s.in(a.ebits, n * (size_t)a.ebits_stride);
+	a.sync_id = s.in(a.sync_id, n);
+	a.toa = s.in(a.toa, n);
+	a.cfo = s.in(a.cfo, n);
+	a.phase = s.in(a.phase, n);
+	a.esn0_db = s.in(a.esn0_db, n);
+	a.amp = s.in(a.amp, n);
+	a.ofs = s.in(a.ofs, n);
+	a.iq = (float2 *)s.out((float *)a.iq, (size_t)iq_len * 2);
+	if (!s.failed()) {
+		e = launch_synth(a, d_all + burst_type, (cudaStream_t)stream);
+		if (e == cudaSuccess)
+			g_launches.fetch_add(1);
+	}
+	return s.finish(e, "synth kernel");
+}
+
 extern "C" {
+
+int gmr1b200_synth_bursts(int burst_type, const uint8_t *ebits, int ebits_stride, const int32_t *sync_id,
+                          int sps, int win_len, const float *toa, float toa0, const float *cfo, float cfo0,
+                          const float *phase, float phase0, const float *esn0_db, float esn0_db0,
+                          const float *amp, float amp0, uint64_t seed,
+                          float *iq, int64_t iq_len, const int64_t *win_ofs, int64_t win_stride, int n, void *stream)
+{
+	SynthArgs a = {};
+	a.ebits = ebits; a.ebits_stride = ebits_stride; a.sync_id = sync_id; a.n = n; a.sps = sps; a.win_len = win_len;
+	a.toa = toa; a.toa0 = toa0; a.cfo = cfo; a.cfo0 = cfo0; a.phase = phase; a.phase0 = phase0;
+	a.esn0_db = esn0_db; a.esn0_db0 = esn0_db0; a.amp = amp; a.amp0 = amp0; a.seed = seed;
+	a.iq = (float2 *)iq; a.ofs = win_ofs; a.stride = win_stride;
+	return run_synth(burst_type, a, iq_len, stream);
+}
 
 int gmr1b200_burst_len(int bt)
 {

@@ -32,4 +32,21 @@ struct DemodArgs {
 cudaError_t launch_demod(const DemodArgs &a, const BurstTab *d_bts, const BurstTab *h_bts, int n_bt, int mode,
                          cudaStream_t st);
 
+// ---- workload synthesis
+struct SynthArgs {
+	const uint8_t *ebits;       // [n][ebits_stride] hard bits
+	int32_t        ebits_stride;
+	const int32_t *sync_id;     // [n] or NULL (0)
+	int32_t        n, sps, win_len;
+	const float   *toa, *cfo, *phase, *esn0_db, *amp;   // [n] each or NULL (then the *0 scalar)
+	float          toa0, cfo0, phase0, esn0_db0, amp0;
+	uint64_t       seed;
+	float2        *iq;
+	const int64_t *ofs;
+	int64_t        stride;
+};
+cudaError_t launch_synth(const SynthArgs &a, const BurstTab *d_bt, cudaStream_t st);
+// device copy of the standard burst descriptors (api_demod.cu)
+cudaError_t device_bursts(const BurstTab **out);
+
 }  // namespace gmr1

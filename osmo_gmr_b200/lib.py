@@ -56,6 +56,14 @@ class Lib:
         "gmr1b200_tch9_decode_batch": [_P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _P],
         "gmr1b200_rach_decode_batch": [_P, _P, _P, _I, _P, _P, _P, _I, _P],
         "gmr1b200_xch_dc12_decode_batch": [_P, _P, _P, _P, _I, _P],
+        "gmr1b200_xcch_encode_batch": [_I, _P, _P, _I],
+        "gmr1b200_facch3_encode": [_P, _P, _P, _P],
+        "gmr1b200_facch9_encode": [_P, _P, _P, _P, _P],
+        "gmr1b200_tch9_encode": [_P, _P, _I, _P, _P, _P, _P],
+        "gmr1b200_rach_encode": [_P, _P, _I],
+        "gmr1b200_tch3_encode": [_P, _P, _P, _P, _P, _I],
+        "gmr1b200_synth_bursts": [_I, _P, _I, _P, _I, _I, _P, _F, _P, _F, _P, _F, _P, _F, _P, _F, ctypes.c_uint64,
+                                  _P, _L, _P, _L, _I, _P],
         "gmr1b200_burst_len": [_I],
         "gmr1b200_burst_ebits": [_I],
         "gmr1b200_pi4cxpsk_demod_batch": [_I, _P, _L, _P, _L, _I, _I, _P, _F, _P, _I, _P, _P, _P, _P, _I, _P],
@@ -73,6 +81,9 @@ class Lib:
             fn = getattr(self.c, name)
             fn.argtypes = args
             fn.restype = _I
+        self.c.gmr1b200_tch9_interleaver_new.restype = _P
+        self.c.gmr1b200_tch9_interleaver_free.argtypes = [_P]
+        self.c.gmr1b200_tch9_interleaver_free.restype = None
         self.c.gmr1b200_last_error.restype = ctypes.c_char_p
         self.c.gmr1b200_version.restype = ctypes.c_char_p
         self.c.gmr1b200_kernel_launches.restype = ctypes.c_uint64

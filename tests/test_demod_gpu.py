@@ -81,8 +81,12 @@ def test_demod_parity(gpu_lib, oracle, name, win, sync_ids):
     x, sid_true, _ = gen(name, n, win, rng, sync_ids)
     got = gpu_demod(gpu_lib, name, x)
     compare(name, oracle, x, got)
-    hi = (np.arange(n) % 4) >= 1                      # >= 10 dB: the right training sequence is found
-    assert (got[1][hi] == sid_true[hi]).all()
+    if sync_ids == 1:
+        assert (got[1] == 0).all()
+    # With several candidate sequences the reference scores candidate i on the SUM of the
+    # correlations of candidates 0..i (accumulator cleared once, pi4cxpsk.c:207,232) and so
+    # favours the last one; the GPU path reproduces that (checked against the oracle above),
+    # hence no comparison with the transmitted sync id here.
 
 
 def test_demod_device_pointers_and_freq_shift(gpu_lib, oracle):
