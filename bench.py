@@ -301,8 +301,6 @@ def run_gpu_arm(args):
         jobs += [(k, lo, min(W.n[k], lo + per)) for lo in range(0, W.n[k], per)]
     n_thr = 3
     streams = [torch.cuda.Stream(device=dev) for _ in range(n_thr)]
-    d_iq = [torch.empty((max(hi - lo for _, lo, hi in jobs), max(wlen("bcch"), wlen("dc6")), 2),
-                        dtype=torch.float32, device=dev) for _ in range(n_thr)]
 
     def e2e_thread(t):
         torch.cuda.set_device(local_rank)
@@ -331,7 +329,6 @@ def run_gpu_arm(args):
     e1.record()
     barrier()
     e2e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0)) / e_steps
-    del d_iq
 
     # ---------------- reduce over ranks (time = max)
     t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=dev)

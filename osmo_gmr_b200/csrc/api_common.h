@@ -124,6 +124,18 @@ private:
 	}
 	void *scratch(size_t bytes)
 	{
+		// keep freed scratch in the stream-ordered pool instead of returning it to the driver at
+		// every synchronisation (the default release threshold is 0)
+		static bool pool_set[64] = {false};
+		int dev = 0;
+		if (cudaGetDevice(&dev) == cudaSuccess && dev < 64 && !pool_set[dev]) {
+			cudaMemPool_t pool;
+			if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+				uint64_t thr = UINT64_MAX;
+				cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+			}
+			pool_set[dev] = true;
+		}
 		void *d = nullptr;
 		cudaError_t e = cudaMallocAsync(&d, bytes, st_);
 		if (e != cudaSuccess) {
