@@ -65,52 +65,37 @@ __device__ __forceinline__ float2 mul_conj_sym(int sym, float2 g)
 }
 
 // Sinc interpolation of the real vector acc[0..len) at `early` and at `early + 2` (the late
-// gate), 10 taps either side, taps summed in index order by one lane each.  Both share the same
+// gate), 10 taps either side, one tap per lane, shuffle-tree sums.  Both share the same
 // 21 sinc values because (i+2) - (early+2) == i - early exactly in fp32 for the values that occur.
-__device__ __forceinline__ void interp_early_late(const float *acc, int len, float early, float *terms,
-                                                  int lane, float &ev, float &lv)
+__device__ __forceinline__ void interp_early_late(const float *acc, int len, float early, int lane,
+                                                  float &ev, float &lv)
 {
 	const int fe = (int)floorf(early);
+	float te = 0.0f, tl = 0.0f;
 	if (lane < 21) {
 		const int k = fe - 10 + lane;
 		const float s = sinc_f(PI_F * ((float)k - early));
-		terms[lane]      = (k >= 0 && k < len) ? acc[k] * s : 0.0f;
-		terms[32 + lane] = (k + 2 >= 0 && k + 2 < len) ? acc[k + 2] * s : 0.0f;
+		te = (k >= 0 && k < len) ? acc[k] * s : 0.0f;
+		tl = (k + 2 >= 0 && k + 2 < len) ? acc[k + 2] * s : 0.0f;
 	}
-	__syncwarp();
-	float sum = 0.0f;
-	if (lane < 2) {
-		const float *t = terms + 32 * lane;
-#pragma unroll
-		for (int i = 0; i < 21; i++)
-			sum += t[i];
-	}
-	__syncwarp();
-	ev = __shfl_sync(0xffffffffu, sum, 0);
-	lv = __shfl_sync(0xffffffffu, sum, 1);
+	ev = warp_sum(te);
+	lv = warp_sum(tl);
 }
 
-__device__ __forceinline__ float interp_point(const float *acc, int len, float pos, float *terms, int lane)
+__device__ __forceinline__ float interp_point(const float *acc, int len, float pos, int lane)
 {
 	const int fp = (int)floorf(pos);
+	float t = 0.0f;
 	if (lane < 21) {
 		const int k = fp - 10 + lane;
-		terms[lane] = (k >= 0 && k < len) ? acc[k] * sinc_f(PI_F * ((float)k - pos)) : 0.0f;
+		t = (k >= 0 && k < len) ? acc[k] * sinc_f(PI_F * ((float)k - pos)) : 0.0f;
 	}
-	__syncwarp();
-	float sum = 0.0f;
-	if (lane == 0) {
-#pragma unroll
-		for (int i = 0; i < 21; i++)
-			sum += terms[i];
-	}
-	__syncwarp();
-	return __shfl_sync(0xffffffffu, sum, 0);
+	return warp_sum(t);
 }
 
 // osmo_cxvec_peak_energy_find(acc, 3, PEAK_EARLY_LATE, &peak) on a real vector; all lanes
 // return the same position / peak value
-__device__ float peak_early_late(const float *acc, int w, float *terms, int lane, float &peak_val)
+__device__ float peak_early_late(const float *acc, int w, int lane, float &peak_val)
 {
 	const int win = w < 3 ? w : 3;
 	float best = 0.0f;
@@ -153,7 +138,7 @@ __device__ float peak_early_late(const float *acc, int w, float *terms, int lane
 	float early = (float)(mwi - 1), incr = 0.5f;
 	while (incr > (1.0f / 1024.0f)) {
 		float ev, lv;
-		interp_early_late(acc, w, early, terms, lane, ev, lv);
+		interp_early_late(acc, w, early, lane, ev, lv);
 		const float e2 = ev * ev, l2 = lv * lv;
 		if (e2 < l2)
 			early += incr;
@@ -164,40 +149,115 @@ __device__ float peak_early_late(const float *acc, int w, float *terms, int lane
 		incr *= 0.5f;
 	}
 	const float pos = early + 1.0f;
-	peak_val = interp_point(acc, w, pos, terms, lane);
+	peak_val = interp_point(acc, w, pos, lane);
 	return pos;
 }
 
-// Search all sync sequences of one burst type in the normalised/derotated window `y`.
-// Returns the winning sequence index (all lanes), its TOA and power (pi4cxpsk.c:184-268).
+// per-warp shared-memory slice
+struct WarpSmem {
+	float2 *win;     // [L]   raw window (never rewritten)
+	float  *accv;    // [w]   correlation magnitude accumulator
+	float2 *taps;    // [32]  rotated reference taps of the chunk being correlated
+};
+
+__device__ __forceinline__ WarpSmem carve(uint8_t *base, int L, int w)
+{
+	WarpSmem s;
+	s.win = (float2 *)base;
+	base += (size_t)((L + 1) & ~1) * 8;
+	s.taps = (float2 *)base;
+	base += 32 * 8;
+	s.accv = (float *)base;
+	return s;
+}
+
+static inline size_t warp_smem_bytes(int L, int w)
+{
+	return (size_t)((L + 1) & ~1) * 8 + 32 * 8 + (size_t)((w + 3) & ~3) * 4;
+}
+
+// window statistics of osmo_cxvec_sig_normalize: mean and 1/stddev.  One pass: the variance is
+// E|x|^2 - |E x|^2 with per-lane partial sums and a shuffle tree (the C path sums sequentially;
+// both are fp32 approximations of the same quantity, see the float contract above).
+struct Norm { float ar, ai, inv_sd; };
+
+__device__ __forceinline__ Norm load_stats(const float2 *__restrict__ x, int L, float2 *win, int lane)
+{
+	float sr = 0.0f, si = 0.0f, sq = 0.0f;
+	for (int i = lane; i < L; i += 32) {
+		const float2 v = __ldg(&x[i]);
+		win[i] = v;
+		sr += v.x;
+		si += v.y;
+		sq += v.x * v.x + v.y * v.y;
+	}
+	sr = warp_sum(sr);
+	si = warp_sum(si);
+	sq = warp_sum(sq);
+	Norm n;
+	n.ar = sr / (float)L;
+	n.ai = si / (float)L;
+	float var = sq / (float)L - (n.ar * n.ar + n.ai * n.ai);
+	float sd = var > 0.0f ? sqrtf(var) : 0.0f;
+	if (sd == 0.0f)
+		sd = 1.0f;
+	n.inv_sd = 1.0f / sd;
+	__syncwarp();
+	return n;
+}
+
+// Search all sync sequences of one burst type (pi4cxpsk.c:184-268) on the RAW window.
+//
+// The reference normalises and derotates every sample, y[i] = (x[i]-avg)/sd * e^{j*fs*i}, then
+// correlates y with the +-1/+-j training symbols and keeps |corr|.  Since only the magnitude is
+// used, the common factor e^{j*fs*(b0+m)} drops out and the rotation moves onto the <= 32
+// reference taps:  |corr[m]| = |sum_n t_n x[b0+m+n*sps] - avg*sum_n t_n| / sd,
+// t_n = conj(ref_n) e^{j*fs*sps*n}.  Same quantity, 60x fewer sincos.
 // accv is NOT cleared between sequences - the reference clears it once per call (:207) and
 // keeps adding (:232-233); tl restarts per sequence (:216).
-__device__ int sync_find(const BurstTab &bt, const float2 *y, int sps, int w, float *accv, float *terms,
+__device__ int sync_find(const BurstTab &bt, const WarpSmem &sm, const Norm &nm, float fs, int sps, int w,
                          int lane, float &toa, float &pwr)
 {
 	for (int m = lane; m < w; m += 32)
-		accv[m] = 0.0f;
-	__syncwarp();
+		sm.accv[m] = 0.0f;
 	float p_toa = 0.0f, p_pwr = 0.0f;
 	int p_idx = -1;
+	const float fstep = fs * (float)sps;
 	for (int s = 0; s < bt.n_sync; s++) {
 		int tl = 0;
 		for (int c = 0; c < bt.n_chunk[s]; c++) {
 			const int b0 = bt.s_pos[s][c] * sps, cl = bt.s_len[s][c];
+			// rotated taps + their sum
+			float tr = 0.0f, ti = 0.0f;
+			if (lane < cl) {
+				float sn, cs;
+				sincosf(fstep * (float)lane, &sn, &cs);
+				const float2 t = mul_conj_sym(bt.s_sym[s][c][lane], make_float2(cs, sn));
+				tr = t.x;
+				ti = t.y;
+			}
+			__syncwarp();
+			sm.taps[lane] = make_float2(tr, ti);
+			const float Rr = warp_sum(tr), Ri = warp_sum(ti);
+			const float cr0 = nm.ar * Rr - nm.ai * Ri, ci0 = nm.ar * Ri + nm.ai * Rr;   // avg * sum(taps)
+			__syncwarp();
 			for (int m = lane; m < w; m += 32) {
 				float cr = 0.0f, ci = 0.0f;
+				const float2 *g = sm.win + b0 + m;
 				for (int n = 0; n < cl; n++) {
-					const float2 p = mul_conj_sym(bt.s_sym[s][c][n], y[b0 + m + n * sps]);
-					cr += p.x;
-					ci += p.y;
+					const float2 t = sm.taps[n], v = g[n * sps];
+					cr += t.x * v.x - t.y * v.y;
+					ci += t.x * v.y + t.y * v.x;
 				}
-				accv[m] += cabs_f(cr, ci);
+				cr = (cr - cr0) * nm.inv_sd;
+				ci = (ci - ci0) * nm.inv_sd;
+				sm.accv[m] += sqrtf(cr * cr + ci * ci);
 			}
 			tl += cl;
 		}
 		__syncwarp();
 		float peak;
-		const float s_toa = peak_early_late(accv, w, terms, lane, peak);
+		const float s_toa = peak_early_late(sm.accv, w, lane, peak);
 		peak /= (float)tl;
 		const float s_pwr = peak * peak;
 		if (s_pwr > p_pwr) {
@@ -211,73 +271,8 @@ __device__ int sync_find(const BurstTab &bt, const float2 *y, int sps, int w, fl
 	return p_idx;
 }
 
-// per-warp shared-memory slice
-struct WarpSmem {
-	float2 *win;     // [L]   window, later normalised + derotated in place
-	float2 *z;       // [len] one sample per symbol
-	float  *accv;    // [w]
-	float  *terms;   // [64]
-};
-
-__device__ __forceinline__ WarpSmem carve(uint8_t *base, int L, int nsym, int w)
-{
-	WarpSmem s;
-	s.win = (float2 *)base;
-	base += (size_t)((L + 1) & ~1) * 8;
-	s.z = (float2 *)base;
-	base += (size_t)((nsym + 1) & ~1) * 8;
-	s.accv = (float *)base;
-	base += (size_t)((w + 3) & ~3) * 4;
-	s.terms = (float *)base;
-	return s;
-}
-
-static inline size_t warp_smem_bytes(int L, int nsym, int w)
-{
-	return (size_t)((L + 1) & ~1) * 8 + (size_t)((nsym + 1) & ~1) * 8 + (size_t)((w + 3) & ~3) * 4 + 64 * 4;
-}
-
-// load + osmo_cxvec_sig_normalize(in, 1, fs) into s.win; returns nothing, all lanes in step
-__device__ void load_normalize(const float2 *__restrict__ x, int L, float fs, float2 *win, int lane)
-{
-	float sr = 0.0f, si = 0.0f;
-	for (int i = lane; i < L; i += 32) {
-		const float2 v = __ldg(&x[i]);
-		win[i] = v;
-		sr += v.x;
-		si += v.y;
-	}
-	sr = warp_sum(sr);
-	si = warp_sum(si);
-	const float ar = sr / (float)L, ai = si / (float)L;
-	__syncwarp();
-	float acc = 0.0f;
-	for (int i = lane; i < L; i += 32) {
-		const float2 v = win[i];
-		const float dr = v.x - ar, di = v.y - ai;
-		acc += dr * dr + di * di;
-	}
-	acc = warp_sum(acc);
-	float sd = sqrtf(acc / (float)L);
-	if (sd == 0.0f)
-		sd = 1.0f;
-	for (int i = lane; i < L; i += 32) {
-		const float2 v = win[i];
-		float yr = (v.x - ar) / sd, yi = (v.y - ai) / sd;
-		if (fs != 0.0f) {
-			float sn, cs;
-			sincosf(fs * (float)i, &sn, &cs);
-			const float tr = yr * cs - yi * sn, ti = yr * sn + yi * cs;
-			yr = tr;
-			yi = ti;
-		}
-		win[i] = make_float2(yr, yi);
-	}
-	__syncwarp();
-}
-
 // ---- kernel ---------------------------------------------------------------------------------------
-// mode 0: demod (bt[0] only).  mode 1: detect among n_bt burst types (pi4cxpsk.c:617-682).
+// mode 0: demod (bts[0] only).  mode 1: detect among n_bt burst types (pi4cxpsk.c:617-682).
 __global__ void __launch_bounds__(DM_WARPS * 32)
 demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int mode, int warp_bytes)
 {
@@ -287,16 +282,16 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 	if (b >= a.n)
 		return;
 
-	const BurstTab &bt0 = bts[0];
+	const BurstTab &bt = bts[0];
 	const int sps = a.sps, L = a.win_len;
-	const int w = L - bt0.len * sps + 1;
-	WarpSmem s = carve(smem + (size_t)warp * warp_bytes, L, bt0.len, w);
+	const int w = L - bt.len * sps + 1;
+	const WarpSmem sm = carve(smem + (size_t)warp * warp_bytes, L, w);
 
 	const float2 *x = a.iq + (a.ofs ? a.ofs[b] : (int64_t)b * a.stride);
 	const float freq_shift = a.freq_shift ? a.freq_shift[b] : a.freq_shift0;
-	const float fs = (freq_shift - bt0.rotation) / (float)sps;
+	const float fs = (freq_shift - bt.rotation) / (float)sps;
 
-	load_normalize(x, L, fs, s.win, lane);
+	const Norm nm = load_stats(x, L, sm.win, lane);
 
 	if (mode == 1) {
 		const float e_toa = a.e_toa ? a.e_toa[b] : a.e_toa0;
@@ -304,7 +299,7 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 		float p_toa = 0.0f, p_pwr = 0.0f;
 		for (int id = 0; id < n_bt; id++) {
 			float toa, pwr;
-			const int sid = sync_find(bts[id], s.win, sps, w, s.accv, s.terms, lane, toa, pwr);
+			const int sid = sync_find(bts[id], sm, nm, fs, sps, w, lane, toa, pwr);
 			if (e_toa >= 0.0f)     // the reference divides by fabs() in double (pi4cxpsk.c:658-659)
 				pwr = (float)((double)pwr / fabs((double)(e_toa - toa)));
 			if (pwr > p_pwr) {
@@ -323,105 +318,114 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 		return;
 	}
 
-	const BurstTab &bt = bt0;
 	float toa, pwr;
-	const int sync_id = sync_find(bt, s.win, sps, w, s.accv, s.terms, lane, toa, pwr);
+	const int sync_id = sync_find(bt, sm, nm, fs, sps, w, lane, toa, pwr);
 	if (lane == 0) {
 		if (a.sync_id) a.sync_id[b] = sync_id;
 		if (a.toa) a.toa[b] = toa;
 		if (a.pwr) a.pwr[b] = pwr;
 	}
+	int8_t *eb = a.ebits + (size_t)b * a.ebits_stride;
 	if (sync_id < 0) {          // nothing correlated (all-zero input): the reference returns -errno
 		if (lane == 0 && a.freq_err) a.freq_err[b] = 0.0f;
 		for (int k = lane; k < bt.ebits; k += 32)
-			a.ebits[(size_t)b * a.ebits_stride + k] = 0;
+			eb[k] = 0;
 		return;
 	}
 
-	// align: one sample per symbol at the rounded TOA (sps >= 4 path, pi4cxpsk.c:286-297)
+	// symbol i sits at sample i*sps + d (sps >= 4 path of _gmr1_pi4cxpsk_align, :286-297)
 	const int d = (int)roundf(toa);
-	for (int i = lane; i < bt.len; i += 32) {
-		int q = i * sps + d;       // d >= -1; index -1 would read before the window: clamp
-		q = q < 0 ? 0 : (q >= L ? L - 1 : q);
-		s.z[i] = s.win[q];
-	}
-	__syncwarp();
+	auto sample_of = [&](int i) {
+		int q = i * sps + d;           // d >= -1; index -1 would read before the window: clamp
+		return q < 0 ? 0 : (q >= L ? L - 1 : q);
+	};
 
-	// fine frequency error from the chunk-to-chunk phase slope (pi4cxpsk.c:360-406)
+	// ---- training symbols, derotated exactly like the reference does every sample:
+	//      z = (x - avg)/sd * e^{j*fl32(fs*idx)}
+	// chunk correlations -> fine frequency error (:360-406); lane c owns chunk c
 	const int nch = bt.n_chunk[sync_id];
 	float ferr = 0.0f;
-	if (nch > 1) {
+	{
 		float cr = 0.0f, ci = 0.0f, pos = 0.0f;
-		if (lane < nch) {
+		if (lane < nch && nch > 1) {
 			const int p0 = bt.s_pos[sync_id][lane], cl = bt.s_len[sync_id][lane];
 			pos = (float)p0 + (float)cl / 2.0f;
 			for (int j = 0; j < cl; j++) {
-				const float2 p = mul_conj_sym(bt.s_sym[sync_id][lane][j], s.z[p0 + j]);
+				const int q = sample_of(p0 + j);
+				const float2 v = sm.win[q];
+				float sn, cs;
+				sincosf(fs * (float)q, &sn, &cs);
+				const float yr = (v.x - nm.ar) * nm.inv_sd, yi = (v.y - nm.ai) * nm.inv_sd;
+				const float2 p = mul_conj_sym(bt.s_sym[sync_id][lane][j],
+				                              make_float2(yr * cs - yi * sn, yr * sn + yi * cs));
 				cr += p.x;
 				ci += p.y;
 			}
 		}
-		float f = 0.0f;
-		for (int i = 1; i < nch; i++) {
-			const float ar = __shfl_sync(0xffffffffu, cr, i), ai = __shfl_sync(0xffffffffu, ci, i);
-			const float br = __shfl_sync(0xffffffffu, cr, i - 1), bi = __shfl_sync(0xffffffffu, ci, i - 1);
-			const float pa = __shfl_sync(0xffffffffu, pos, i), pb = __shfl_sync(0xffffffffu, pos, i - 1);
-			// corr[i] * conj(corr[i-1])
-			const float re = ar * br - ai * (-bi), im = ar * (-bi) + ai * br;
-			f += atan2f(im, re) / (pa - pb);
+		if (nch > 1) {
+			float f = 0.0f;
+			for (int i = 1; i < nch; i++) {
+				const float ar = __shfl_sync(0xffffffffu, cr, i), ai = __shfl_sync(0xffffffffu, ci, i);
+				const float br = __shfl_sync(0xffffffffu, cr, i - 1), bi = __shfl_sync(0xffffffffu, ci, i - 1);
+				const float pa = __shfl_sync(0xffffffffu, pos, i), pb = __shfl_sync(0xffffffffu, pos, i - 1);
+				// corr[i] * conj(corr[i-1])
+				const float re = ar * br + ai * bi, im = ai * br - ar * bi;
+				f += atan2f(im, re) / (pa - pb);
+			}
+			ferr = f / (float)(nch - 1);
 		}
-		ferr = f / (float)(nch - 1);
 	}
 	if (lane == 0 && a.freq_err) a.freq_err[b] = ferr;
 
-	// compensate (osmo_cxvec_rotate by -ferr), pi4cxpsk.c:574-575
-	if (ferr != 0.0f) {
-		for (int i = lane; i < bt.len; i += 32) {
-			float sn, cs;
-			sincosf((-ferr) * (float)i, &sn, &cs);
-			const float2 v = s.z[i];
-			s.z[i] = make_float2(v.x * cs - v.y * sn, v.x * sn + v.y * cs);
-		}
-		__syncwarp();
-	}
-
-	// phase reference from all sync chunks, one accumulator in symbol order (pi4cxpsk.c:415-433)
-	float pr = 0.0f, pi = 0.0f;
-	if (lane == 0) {
+	// ---- phase reference: sum over all training symbols after the -ferr rotation (:415-433, :574);
+	//      training symbols are spread over the lanes, the sum is a shuffle tree
+	float phi0;
+	{
+		float pr = 0.0f, pi = 0.0f;
 		for (int c = 0; c < nch; c++) {
 			const int p0 = bt.s_pos[sync_id][c], cl = bt.s_len[sync_id][c];
-			for (int j = 0; j < cl; j++) {
-				const float2 p = mul_conj_sym(bt.s_sym[sync_id][c][j], s.z[p0 + j]);
+			if (lane < cl) {
+				const int i = p0 + lane, q = sample_of(i);
+				const float2 v = sm.win[q];
+				float sn, cs;
+				sincosf(fs * (float)q, &sn, &cs);
+				float yr = (v.x - nm.ar) * nm.inv_sd, yi = (v.y - nm.ai) * nm.inv_sd;
+				float zr = yr * cs - yi * sn, zi = yr * sn + yi * cs;
+				if (ferr != 0.0f) {
+					sincosf((-ferr) * (float)i, &sn, &cs);
+					const float t = zr * cs - zi * sn;
+					zi = zr * sn + zi * cs;
+					zr = t;
+				}
+				const float2 p = mul_conj_sym(bt.s_sym[sync_id][c][lane], make_float2(zr, zi));
 				pr += p.x;
 				pi += p.y;
 			}
 		}
-		const float ab = cabs_f(pr, pi);
-		pr /= ab;
-		pi /= ab;
+		pr = warp_sum(pr);
+		pi = warp_sum(pi);
+		phi0 = atan2f(pi, pr);
 	}
-	pr = __shfl_sync(0xffffffffu, pr, 0);
-	pi = __shfl_sync(0xffffffffu, pi, 0);
 
-	// scale by conj(phasor), soft symbols, soft bits (pi4cxpsk.c:581, 442-503)
+	// ---- data symbols in the angle domain.  The reference rotates each sample three times
+	// (e^{j*fs*idx}, e^{-j*ferr*i}, conj(phasor)) and takes cargf(); the argument of that product
+	// is  arg(x - avg) + fl32(fs*idx) + fl32(-ferr*i) - arg(phasor)  (mod 2*pi), evaluated here in
+	// double so that the only float rounding left is the one atan2f of the raw sample.
 	const int nbits = bt.nbits, mask = (1 << nbits) - 1;
-	const float dd = (2.0f * PI_F) / (float)(1 << nbits);
-	const bool scale_real = (-pi == 0.0f);     // osmo_cxvec_scale takes the real path if imag == 0
-	int8_t *eb = a.ebits + (size_t)b * a.ebits_stride;
+	const double inv_dd = (double)(1 << nbits) / (2.0 * 3.14159265358979323846);
+	const double period = (double)(1 << nbits);
 	int kbase = 0;
 	for (int c = 0; c < bt.n_data; c++) {
 		const int p0 = bt.d_pos[c], cl = bt.d_len[c];
 		for (int j = lane; j < cl; j += 32) {
-			const float2 v = s.z[p0 + j];
-			float zr, zi;
-			if (scale_real) {
-				zr = v.x * pr;
-				zi = v.y * pr;
-			} else {
-				zr = v.x * pr - v.y * (-pi);
-				zi = v.x * (-pi) + v.y * pr;
-			}
-			const float sv = atan2f(zi, zr) / dd;
+			const int i = p0 + j, q = sample_of(i);
+			const float2 v = sm.win[q];
+			const float th = atan2f(v.y - nm.ai, v.x - nm.ar);
+			const float a1 = fs * (float)q;
+			const float a2 = ferr != 0.0f ? (-ferr) * (float)i : 0.0f;
+			double svd = ((double)th + (double)a1 + (double)a2 - (double)phi0) * inv_dd;
+			svd -= period * rint(svd / period);            // -> [-period/2, period/2]
+			const float sv = (float)svd;
 			const float svr = roundf(sv);
 			const int sp = (int)svr & mask;
 			const int ss = (svr > sv ? (sp - 1) : (sp + 1)) & mask;
@@ -429,10 +433,10 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 			// Gray map of the symbol index: {00, 01, 11, 10} (2 bits) / {0, 1} (1 bit), MSB first
 			const int gp = nbits == 2 ? (sp ^ (sp >> 1)) : sp;
 			const int gs = nbits == 2 ? (ss ^ (ss >> 1)) : ss;
-			for (int q = 0; q < nbits; q++) {
-				const int vp = (gp >> (nbits - 1 - q)) & 1, vs = (gs >> (nbits - 1 - q)) & 1;
+			for (int qb = 0; qb < nbits; qb++) {
+				const int vp = (gp >> (nbits - 1 - qb)) & 1, vs = (gs >> (nbits - 1 - qb)) & 1;
 				const int val = 127 - ((vp ^ vs) ? dq : (dq >> 1));
-				eb[kbase + j * nbits + q] = (int8_t)(vp ? -val : val);
+				eb[kbase + j * nbits + qb] = (int8_t)(vp ? -val : val);
 			}
 		}
 		kbase += cl * nbits;
@@ -455,7 +459,7 @@ cudaError_t launch_demod(const DemodArgs &a, const BurstTab *d_bts, const BurstT
 	const int w = a.win_len - maxlen * a.sps + 1;
 	if (w < 1 || a.sps < 4 || a.sps > 16)
 		return cudaErrorInvalidValue;
-	const size_t wb = (warp_smem_bytes(a.win_len, maxlen, w) + 15) & ~(size_t)15;
+	const size_t wb = (warp_smem_bytes(a.win_len, w) + 15) & ~(size_t)15;
 	const size_t smem = wb * DM_WARPS;
 	if (smem > 227 * 1024)
 		return cudaErrorInvalidValue;
