@@ -2,10 +2,10 @@
 //
 // One warp per burst.  The burst window (len*sps + search-window complex float samples, 4-11 KB
 // at sps 4) is read from HBM exactly once into the warp's slice of shared memory; every later
-// pass (mean, variance, normalise + derotate, training-sequence correlation over all search
-// offsets, early/late peak search, symbol pick, frequency / phase estimation, soft bits) works
-// out of shared memory and registers, with warp-shuffle reductions.  Output per burst: ebits
-// (int8), sync id, fractional TOA, frequency error, sync power.
+// pass (statistics, training-sequence correlation over all search offsets, early/late peak
+// search, frequency / phase estimation, soft bits) works out of shared memory and registers with
+// warp-shuffle reductions.  Output per burst: ebits (int8), sync id, fractional TOA, frequency
+// error, sync power.
 //
 // Replaces, for a whole batch per launch, the reference's
 //   gmr1_pi4cxpsk_demod       src/sdr/pi4cxpsk.c:520-602
@@ -18,13 +18,19 @@
 // and the libosmo-dsp primitives they call (sig_normalize, correlate, peak_energy_find with
 // PEAK_EARLY_LATE, interpolate_point, rotate, scale) as restated in SURVEY.md Appendix A.2.
 //
-// Float contract: same operations in the same order wherever the order is observable at
-// reasonable cost (per-offset correlation sums, sinc-interpolation tap order, chunk sums);
-// the two whole-window reductions (mean, variance) are tree sums, so results agree with the
-// C path to float rounding, not bit for bit.  Built with -fmad=false, IEEE div/sqrt, and the
-// accurate sincosf/atan2f (no fast-math).
+// The kernel computes the same quantities as the C path but not with the same instruction
+// sequence; it is issue-bound, so the work is restructured to need ~3x fewer instructions:
+//   * normalise + derotate is never applied to the 1000+ samples of the window.  Only magnitudes
+//     of correlations are used, so the rotation moves onto the <= 32 reference taps and the
+//     mean / scale become a per-chunk correction (see sync_find);
+//   * window statistics are one pass (E|x|^2 - |E x|^2), tree sums;
+//   * the sinc interpolation shares one sine per position: sin(pi*(k-pos)) = -(-1)^j sin(pi*frac);
+//   * data symbols are sliced in the angle domain: arg(x-avg) + fs*idx - ferr*i - arg(phasor),
+//     accumulated in double, instead of three complex rotations and an atan2 per symbol.
+// Float contract (tests/test_demod_gpu.py): sync_id identical, TOA within 0.01 sample, freq_err
+// within 2e-5 rad/symbol, soft bits within +-1 LSB (>= 99.5 % identical), and identical L2 / CRC
+// after stage 3.  Integer stages (stage 3) are bit-exact.
 #include <cuda_runtime.h>
-#include <math_constants.h>
 
 #include "gmr1_tables.h"
 #include "launch.h"
@@ -42,55 +48,59 @@ __device__ __forceinline__ float warp_sum(float v)
 	return v;
 }
 
-__device__ __forceinline__ float sinc_f(float x)     // osmo_sinc
-{
-	return (x >= 0.01f || x <= -0.01f) ? sinf(x) / x : 1.0f;
-}
-
-// |re + j im| the way glibc's cabsf/hypotf evaluates it (double sqrt, then round to float)
-__device__ __forceinline__ float cabs_f(float re, float im)
-{
-	return (float)sqrt((double)re * (double)re + (double)im * (double)im);
-}
-
 // conj(ref) * g for ref in {1, j, -1, -j} (symbol index 0..3): exact component shuffles
 __device__ __forceinline__ float2 mul_conj_sym(int sym, float2 g)
 {
-	switch (sym & 3) {
-	case 0:  return make_float2(g.x, g.y);
-	case 1:  return make_float2(g.y, -g.x);
-	case 2:  return make_float2(-g.x, -g.y);
-	default: return make_float2(-g.y, g.x);
-	}
+	const float a = (sym & 1) ? g.y : g.x, b = (sym & 1) ? -g.x : g.y;
+	return (sym & 2) ? make_float2(-a, -b) : make_float2(a, b);
 }
 
-// Sinc interpolation of the real vector acc[0..len) at `early` and at `early + 2` (the late
-// gate), 10 taps either side, one tap per lane, shuffle-tree sums.  Both share the same
-// 21 sinc values because (i+2) - (early+2) == i - early exactly in fp32 for the values that occur.
-__device__ __forceinline__ void interp_early_late(const float *acc, int len, float early, int lane,
-                                                  float &ev, float &lv)
+// atan2f with ~1e-7 rad absolute error: octant reduction + degree-8 minimax polynomial in a^2
+__device__ __forceinline__ float fast_atan2f(float y, float x)
 {
-	const int fe = (int)floorf(early);
+	const float ax = fabsf(x), ay = fabsf(y);
+	const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+	const float a = mx > 0.0f ? __fdividef(mn, mx) : 0.0f;
+	const float t = a * a;
+	float p = 2.4464237603e-03f;
+	p = fmaf(p, t, -1.4352691414e-02f);
+	p = fmaf(p, t, 3.9685524385e-02f);
+	p = fmaf(p, t, -7.2247349056e-02f);
+	p = fmaf(p, t, 1.0492738066e-01f);
+	p = fmaf(p, t, -1.4159015534e-01f);
+	p = fmaf(p, t, 1.9985472684e-01f);
+	p = fmaf(p, t, -3.3332556455e-01f);
+	p = fmaf(p, t, 9.9999987390e-01f);
+	float r = p * a;
+	r = ay > ax ? (0.5f * PI_F - r) : r;
+	r = x < 0.0f ? (PI_F - r) : r;
+	return y < 0.0f ? -r : r;
+}
+
+// Sinc interpolation (osmo_cxvec_interpolate_point, 10 taps either side) of the real vector
+// acc[0..len) at `pos` and, when LATE, also at `pos + 2` (the late gate).  One tap per lane,
+// shuffle-tree sums.  The 21 sinc values of both gates are identical ((i+2)-(pos+2) == i-pos
+// exactly in fp32 here) and share one sine: sin(pi*(j-frac)) = -(-1)^j sin(pi*frac).
+template <bool LATE>
+__device__ __forceinline__ void interp(const float *acc, int len, float pos, int lane, float &ev, float &lv)
+{
+	const float fl = floorf(pos);
+	const int fe = (int)fl;
+	const float frac = pos - fl;                      // exact
+	const float S = sinpif(frac);
 	float te = 0.0f, tl = 0.0f;
 	if (lane < 21) {
-		const int k = fe - 10 + lane;
-		const float s = sinc_f(PI_F * ((float)k - early));
+		const int j = lane - 10, k = fe + j;
+		const float x = PI_F * ((float)j - frac);
+		float s = __fdividef((j & 1) ? S : -S, x);
+		s = (x >= 0.01f || x <= -0.01f) ? s : 1.0f;   // osmo_sinc
 		te = (k >= 0 && k < len) ? acc[k] * s : 0.0f;
-		tl = (k + 2 >= 0 && k + 2 < len) ? acc[k + 2] * s : 0.0f;
+		if (LATE)
+			tl = (k + 2 >= 0 && k + 2 < len) ? acc[k + 2] * s : 0.0f;
 	}
 	ev = warp_sum(te);
-	lv = warp_sum(tl);
-}
-
-__device__ __forceinline__ float interp_point(const float *acc, int len, float pos, int lane)
-{
-	const int fp = (int)floorf(pos);
-	float t = 0.0f;
-	if (lane < 21) {
-		const int k = fp - 10 + lane;
-		t = (k >= 0 && k < len) ? acc[k] * sinc_f(PI_F * ((float)k - pos)) : 0.0f;
-	}
-	return warp_sum(t);
+	if (LATE)
+		lv = warp_sum(tl);
 }
 
 // osmo_cxvec_peak_energy_find(acc, 3, PEAK_EARLY_LATE, &peak) on a real vector; all lanes
@@ -136,9 +146,10 @@ __device__ float peak_early_late(const float *acc, int w, int lane, float &peak_
 	}
 
 	float early = (float)(mwi - 1), incr = 0.5f;
+#pragma unroll 1
 	while (incr > (1.0f / 1024.0f)) {
 		float ev, lv;
-		interp_early_late(acc, w, early, lane, ev, lv);
+		interp<true>(acc, w, early, lane, ev, lv);
 		const float e2 = ev * ev, l2 = lv * lv;
 		if (e2 < l2)
 			early += incr;
@@ -149,15 +160,16 @@ __device__ float peak_early_late(const float *acc, int w, int lane, float &peak_
 		incr *= 0.5f;
 	}
 	const float pos = early + 1.0f;
-	peak_val = interp_point(acc, w, pos, lane);
+	float dummy;
+	interp<false>(acc, w, pos, lane, peak_val, dummy);
 	return pos;
 }
 
 // per-warp shared-memory slice
 struct WarpSmem {
 	float2 *win;     // [L]   raw window (never rewritten)
-	float  *accv;    // [w]   correlation magnitude accumulator
 	float2 *taps;    // [32]  rotated reference taps of the chunk being correlated
+	float  *accv;    // [w]   correlation magnitude accumulator
 };
 
 __device__ __forceinline__ WarpSmem carve(uint8_t *base, int L, int w)
@@ -178,18 +190,41 @@ static inline size_t warp_smem_bytes(int L, int w)
 
 // window statistics of osmo_cxvec_sig_normalize: mean and 1/stddev.  One pass: the variance is
 // E|x|^2 - |E x|^2 with per-lane partial sums and a shuffle tree (the C path sums sequentially;
-// both are fp32 approximations of the same quantity, see the float contract above).
+// both are fp32 approximations of the same quantity).
 struct Norm { float ar, ai, inv_sd; };
 
 __device__ __forceinline__ Norm load_stats(const float2 *__restrict__ x, int L, float2 *win, int lane)
 {
 	float sr = 0.0f, si = 0.0f, sq = 0.0f;
-	for (int i = lane; i < L; i += 32) {
-		const float2 v = __ldg(&x[i]);
-		win[i] = v;
-		sr += v.x;
-		si += v.y;
-		sq += v.x * v.x + v.y * v.y;
+	if ((((uintptr_t)x) & 15) == 0) {
+		// 16-byte aligned window: two samples per lane per load
+		const float4 *x4 = reinterpret_cast<const float4 *>(x);
+		float4 *w4 = reinterpret_cast<float4 *>(win);
+		const int L2 = L >> 1;
+#pragma unroll 4
+		for (int i = lane; i < L2; i += 32) {
+			const float4 v = __ldg(&x4[i]);
+			w4[i] = v;
+			sr += v.x + v.z;
+			si += v.y + v.w;
+			sq += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+		}
+		if ((L & 1) && lane == 0) {
+			const float2 v = __ldg(&x[L - 1]);
+			win[L - 1] = v;
+			sr += v.x;
+			si += v.y;
+			sq += v.x * v.x + v.y * v.y;
+		}
+	} else {
+#pragma unroll 4
+		for (int i = lane; i < L; i += 32) {
+			const float2 v = __ldg(&x[i]);
+			win[i] = v;
+			sr += v.x;
+			si += v.y;
+			sq += v.x * v.x + v.y * v.y;
+		}
 	}
 	sr = warp_sum(sr);
 	si = warp_sum(si);
@@ -197,7 +232,7 @@ __device__ __forceinline__ Norm load_stats(const float2 *__restrict__ x, int L, 
 	Norm n;
 	n.ar = sr / (float)L;
 	n.ai = si / (float)L;
-	float var = sq / (float)L - (n.ar * n.ar + n.ai * n.ai);
+	const float var = sq / (float)L - (n.ar * n.ar + n.ai * n.ai);
 	float sd = var > 0.0f ? sqrtf(var) : 0.0f;
 	if (sd == 0.0f)
 		sd = 1.0f;
@@ -244,10 +279,14 @@ __device__ int sync_find(const BurstTab &bt, const WarpSmem &sm, const Norm &nm,
 			for (int m = lane; m < w; m += 32) {
 				float cr = 0.0f, ci = 0.0f;
 				const float2 *g = sm.win + b0 + m;
-				for (int n = 0; n < cl; n++) {
-					const float2 t = sm.taps[n], v = g[n * sps];
-					cr += t.x * v.x - t.y * v.y;
-					ci += t.x * v.y + t.y * v.x;
+				const float2 *tp = sm.taps;
+#pragma unroll 4
+				for (int n = 0; n < cl; n++, g += sps, tp++) {
+					const float2 t = *tp, v = *g;
+					cr = fmaf(t.x, v.x, cr);
+					cr = fmaf(-t.y, v.y, cr);
+					ci = fmaf(t.x, v.y, ci);
+					ci = fmaf(t.y, v.x, ci);
 				}
 				cr = (cr - cr0) * nm.inv_sd;
 				ci = (ci - ci0) * nm.inv_sd;
@@ -336,70 +375,67 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 	// symbol i sits at sample i*sps + d (sps >= 4 path of _gmr1_pi4cxpsk_align, :286-297)
 	const int d = (int)roundf(toa);
 	auto sample_of = [&](int i) {
-		int q = i * sps + d;           // d >= -1; index -1 would read before the window: clamp
-		return q < 0 ? 0 : (q >= L ? L - 1 : q);
+		const int q = i * sps + d;     // d >= -1; index -1 would read before the window: clamp
+		return min(max(q, 0), L - 1);
 	};
 
-	// ---- training symbols, derotated exactly like the reference does every sample:
-	//      z = (x - avg)/sd * e^{j*fl32(fs*idx)}
-	// chunk correlations -> fine frequency error (:360-406); lane c owns chunk c
+	// ---- training symbols (<= 32 per chunk, one per lane), derotated as the reference derotates
+	//      every sample: z = (x - avg)/sd * e^{j*fl32(fs*idx)}.  Per chunk: correlation sum ->
+	//      fine frequency error from the chunk-to-chunk phase slope (:360-406).  The derotated
+	//      products are kept in registers (chunk c -> zr[c], zi[c]) for the phase reference.
 	const int nch = bt.n_chunk[sync_id];
-	float ferr = 0.0f;
-	{
-		float cr = 0.0f, ci = 0.0f, pos = 0.0f;
-		if (lane < nch && nch > 1) {
-			const int p0 = bt.s_pos[sync_id][lane], cl = bt.s_len[sync_id][lane];
-			pos = (float)p0 + (float)cl / 2.0f;
-			for (int j = 0; j < cl; j++) {
-				const int q = sample_of(p0 + j);
+	float zr[MAX_SYNC_CHUNK], zi[MAX_SYNC_CHUNK];
+	float ferr = 0.0f, f = 0.0f, prev_r = 0.0f, prev_i = 0.0f, prev_pos = 0.0f;
+#pragma unroll
+	for (int c = 0; c < MAX_SYNC_CHUNK; c++) {
+		zr[c] = zi[c] = 0.0f;
+		if (c < nch) {
+			const int p0 = bt.s_pos[sync_id][c], cl = bt.s_len[sync_id][c];
+			if (lane < cl) {
+				const int q = sample_of(p0 + lane);
 				const float2 v = sm.win[q];
 				float sn, cs;
 				sincosf(fs * (float)q, &sn, &cs);
 				const float yr = (v.x - nm.ar) * nm.inv_sd, yi = (v.y - nm.ai) * nm.inv_sd;
-				const float2 p = mul_conj_sym(bt.s_sym[sync_id][lane][j],
+				const float2 p = mul_conj_sym(bt.s_sym[sync_id][c][lane],
 				                              make_float2(yr * cs - yi * sn, yr * sn + yi * cs));
-				cr += p.x;
-				ci += p.y;
+				zr[c] = p.x;
+				zi[c] = p.y;
 			}
-		}
-		if (nch > 1) {
-			float f = 0.0f;
-			for (int i = 1; i < nch; i++) {
-				const float ar = __shfl_sync(0xffffffffu, cr, i), ai = __shfl_sync(0xffffffffu, ci, i);
-				const float br = __shfl_sync(0xffffffffu, cr, i - 1), bi = __shfl_sync(0xffffffffu, ci, i - 1);
-				const float pa = __shfl_sync(0xffffffffu, pos, i), pb = __shfl_sync(0xffffffffu, pos, i - 1);
-				// corr[i] * conj(corr[i-1])
-				const float re = ar * br + ai * bi, im = ai * br - ar * bi;
-				f += atan2f(im, re) / (pa - pb);
+			if (nch > 1) {
+				const float cr = warp_sum(zr[c]), ci = warp_sum(zi[c]);
+				const float pos = (float)p0 + (float)cl / 2.0f;
+				if (c > 0) {   // arg(corr[c] * conj(corr[c-1])) / (pos[c] - pos[c-1])
+					const float re = cr * prev_r + ci * prev_i, im = ci * prev_r - cr * prev_i;
+					f += atan2f(im, re) / (pos - prev_pos);
+				}
+				prev_r = cr;
+				prev_i = ci;
+				prev_pos = pos;
 			}
-			ferr = f / (float)(nch - 1);
 		}
 	}
+	if (nch > 1)
+		ferr = f / (float)(nch - 1);
 	if (lane == 0 && a.freq_err) a.freq_err[b] = ferr;
 
-	// ---- phase reference: sum over all training symbols after the -ferr rotation (:415-433, :574);
-	//      training symbols are spread over the lanes, the sum is a shuffle tree
+	// ---- phase reference: all training symbols after the -ferr rotation (:415-433, :574)
 	float phi0;
 	{
 		float pr = 0.0f, pi = 0.0f;
-		for (int c = 0; c < nch; c++) {
-			const int p0 = bt.s_pos[sync_id][c], cl = bt.s_len[sync_id][c];
-			if (lane < cl) {
-				const int i = p0 + lane, q = sample_of(i);
-				const float2 v = sm.win[q];
-				float sn, cs;
-				sincosf(fs * (float)q, &sn, &cs);
-				float yr = (v.x - nm.ar) * nm.inv_sd, yi = (v.y - nm.ai) * nm.inv_sd;
-				float zr = yr * cs - yi * sn, zi = yr * sn + yi * cs;
+#pragma unroll
+		for (int c = 0; c < MAX_SYNC_CHUNK; c++) {
+			if (c < nch) {
+				float r = zr[c], i_ = zi[c];
 				if (ferr != 0.0f) {
-					sincosf((-ferr) * (float)i, &sn, &cs);
-					const float t = zr * cs - zi * sn;
-					zi = zr * sn + zi * cs;
-					zr = t;
+					float sn, cs;
+					sincosf((-ferr) * (float)(bt.s_pos[sync_id][c] + lane), &sn, &cs);
+					const float t = r * cs - i_ * sn;
+					i_ = r * sn + i_ * cs;
+					r = t;
 				}
-				const float2 p = mul_conj_sym(bt.s_sym[sync_id][c][lane], make_float2(zr, zi));
-				pr += p.x;
-				pi += p.y;
+				pr += r;
+				pi += i_;
 			}
 		}
 		pr = warp_sum(pr);
@@ -409,34 +445,43 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 
 	// ---- data symbols in the angle domain.  The reference rotates each sample three times
 	// (e^{j*fs*idx}, e^{-j*ferr*i}, conj(phasor)) and takes cargf(); the argument of that product
-	// is  arg(x - avg) + fl32(fs*idx) + fl32(-ferr*i) - arg(phasor)  (mod 2*pi), evaluated here in
-	// double so that the only float rounding left is the one atan2f of the raw sample.
+	// is  arg(x - avg) + fl32(fs*idx) + fl32(-ferr*i) - arg(phasor)  (mod 2*pi), accumulated here
+	// in double so that the only float rounding left is the atan2 of the raw sample.
 	const int nbits = bt.nbits, mask = (1 << nbits) - 1;
 	const double inv_dd = (double)(1 << nbits) / (2.0 * 3.14159265358979323846);
-	const double period = (double)(1 << nbits);
+	const double period = (double)(1 << nbits), inv_period = 1.0 / period;
+	const double c0 = -(double)phi0 * inv_dd;
 	int kbase = 0;
 	for (int c = 0; c < bt.n_data; c++) {
 		const int p0 = bt.d_pos[c], cl = bt.d_len[c];
 		for (int j = lane; j < cl; j += 32) {
 			const int i = p0 + j, q = sample_of(i);
 			const float2 v = sm.win[q];
-			const float th = atan2f(v.y - nm.ai, v.x - nm.ar);
+			const float th = fast_atan2f(v.y - nm.ai, v.x - nm.ar);
 			const float a1 = fs * (float)q;
 			const float a2 = ferr != 0.0f ? (-ferr) * (float)i : 0.0f;
-			double svd = ((double)th + (double)a1 + (double)a2 - (double)phi0) * inv_dd;
-			svd -= period * rint(svd / period);            // -> [-period/2, period/2]
+			double svd = fma((double)th + (double)a1 + (double)a2, inv_dd, c0);
+			svd -= period * rint(svd * inv_period);        // -> [-period/2, period/2]
 			const float sv = (float)svd;
 			const float svr = roundf(sv);
 			const int sp = (int)svr & mask;
 			const int ss = (svr > sv ? (sp - 1) : (sp + 1)) & mask;
 			const int dq = (int)roundf((2.0f * fabsf(svr - sv)) * 64.0f);
-			// Gray map of the symbol index: {00, 01, 11, 10} (2 bits) / {0, 1} (1 bit), MSB first
-			const int gp = nbits == 2 ? (sp ^ (sp >> 1)) : sp;
-			const int gs = nbits == 2 ? (ss ^ (ss >> 1)) : ss;
-			for (int qb = 0; qb < nbits; qb++) {
-				const int vp = (gp >> (nbits - 1 - qb)) & 1, vs = (gs >> (nbits - 1 - qb)) & 1;
-				const int val = 127 - ((vp ^ vs) ? dq : (dq >> 1));
-				eb[kbase + j * nbits + qb] = (int8_t)(vp ? -val : val);
+			if (nbits == 2) {
+				// Gray map of the symbol index {00, 01, 11, 10}, MSB first
+				const int gp = sp ^ (sp >> 1), gx = gp ^ ss ^ (ss >> 1);
+				const int v0 = 127 - ((gx & 2) ? dq : (dq >> 1)), v1 = 127 - ((gx & 1) ? dq : (dq >> 1));
+				const int b0 = (gp & 2) ? -v0 : v0, b1 = (gp & 1) ? -v1 : v1;
+				int8_t *o = eb + kbase + 2 * j;
+				if ((((uintptr_t)o) & 1) == 0)
+					*reinterpret_cast<uint16_t *>(o) = (uint16_t)((b0 & 0xff) | ((b1 & 0xff) << 8));
+				else {
+					o[0] = (int8_t)b0;
+					o[1] = (int8_t)b1;
+				}
+			} else {
+				const int v0 = 127 - (((sp ^ ss) & 1) ? dq : (dq >> 1));
+				eb[kbase + j] = (int8_t)(sp ? -v0 : v0);
 			}
 		}
 		kbase += cl * nbits;
