@@ -186,6 +186,47 @@ int gmr1b200_rach_encode(gmr1b200_ubit_t *bits_e, const uint8_t *rach, int sb_ma
 int gmr1b200_tch3_encode(gmr1b200_ubit_t *bits_e, const uint8_t *frame0, const uint8_t *frame1,
                          const gmr1b200_ubit_t *bits_s, const gmr1b200_ubit_t *ciph, int m);
 
+/* ---- stage 1: FCCH chirp acquisition ----------------------------------------------------------
+ * fcch_type: 0 = gmr1_fcch_burst (sweep 0.32, 117 symbols), 1 = gmr1_fcch3_lband_burst (0.32, 468),
+ * 2 = gmr1_fcch3_sband_burst (0.16, 468)  (reference src/sdr/fcch.c:50-70, sdr/fcch.h:42-44).
+ * Windows are addressed as for the demodulator (win_ofs / win_stride into iq). */
+
+/* replaces gmr1_fcch_rough, src/sdr/fcch.c:211 (sdr/fcch.h:47-49): coarse TOA of the strongest FCCH
+ * in each search window (gmr1_rx uses 330 ms = 30 888 samples at sps 4, src/gmr1_rx.c:612).
+ * toa [n] in samples; peak [n] (energy of the winning 5-symbol window, our extra) may be NULL. */
+int gmr1b200_fcch_rough_batch(int fcch_type, const float *iq, int64_t iq_len,
+                              const int64_t *win_ofs, int64_t win_stride, int win_len, int sps,
+                              const float *freq_shift, float freq_shift0,
+                              int32_t *toa, float *peak, int n, void *stream);
+
+/* replaces gmr1_fcch_fine, src/sdr/fcch.c:512 (sdr/fcch.h:55-57): each window is exactly
+ * burst_len*sps samples (else the reference returns -EINVAL); toa [n] samples, freq_error [n] rad/symbol */
+int gmr1b200_fcch_fine_batch(int fcch_type, const float *iq, int64_t iq_len,
+                             const int64_t *win_ofs, int64_t win_stride, int sps,
+                             const float *freq_shift, float freq_shift0,
+                             int32_t *toa, float *freq_error, int n, void *stream);
+
+/* replaces gmr1_fcch_snr, src/sdr/fcch.c:643 (sdr/fcch.h:59-61): snr [n] */
+int gmr1b200_fcch_snr_batch(int fcch_type, const float *iq, int64_t iq_len,
+                            const int64_t *win_ofs, int64_t win_stride, int sps,
+                            const float *freq_shift, float freq_shift0,
+                            float *snr, int n, void *stream);
+
+/* ---- DKAB and modulation order ------------------------------------------------------------------ */
+
+/* replaces gmr1_dkab_demod, src/sdr/dkab.c:187 (sdr/dkab.h:40-42).  p [n] DKAB position or NULL (p0);
+ * ebits [n][8] (written when rv == 0), toa [n], rv [n]: 0 = DKAB found, 1 = not a DKAB, -EINVAL window
+ * shorter than a DKAB burst */
+int gmr1b200_dkab_demod_batch(const float *iq, int64_t iq_len, const int64_t *win_ofs, int64_t win_stride,
+                              int win_len, int sps, const float *freq_shift, float freq_shift0,
+                              const int32_t *p, int p0, gmr1b200_sbit_t *ebits, float *toa, int32_t *rv,
+                              int n, void *stream);
+
+/* replaces gmr1_pi4cxpsk_mod_order, src/sdr/pi4cxpsk.c:693 (sdr/pi4cxpsk.h:112-113): order [n] = 2 or 4 */
+int gmr1b200_pi4cxpsk_mod_order_batch(const float *iq, int64_t iq_len, const int64_t *win_ofs, int64_t win_stride,
+                                      int win_len, int sps, const float *freq_shift, float freq_shift0,
+                                      int32_t *order, int n, void *stream);
+
 /* ---- workload synthesis: pi/4-CxPSK burst generator (GPU) -------------------------------------
  * Not in the reference (its gmr1_pi4cxpsk_mod, src/sdr/pi4cxpsk.c:741, is 1 sample/symbol with no
  * pulse or channel).  Writes n burst windows of win_len complex samples into iq: hard bits ->

@@ -1,0 +1,164 @@
+// api_sdr.cu - C ABI: FCCH acquisition, DKAB demodulation, modulation-order test (include/gmr1_b200.h)
+#include "../../include/gmr1_b200.h"
+#include "api_common.h"
+#include "launch.h"
+
+using namespace gmr1;
+
+// FCCH burst formats (reference src/sdr/fcch.c:50-70): sweep range, symbols
+static const struct { float freq; int len; } FCCH_TYPES[3] = {{0.32f, 117}, {0.32f, 468}, {0.16f, 468}};
+
+static int fcch_common(int type, FcchArgs &a, Stage &s, int64_t iq_len, const char *what)
+{
+	if (type < 0 || type > 2 || a.n < 0 || !a.iq || a.sps < 1 || a.sps > 16)
+		return set_err(-EINVAL, what);
+	a.freq = FCCH_TYPES[type].freq;
+	a.len = FCCH_TYPES[type].len;
+	if (a.n && !a.ofs && (a.stride < 0 || (int64_t)(a.n - 1) * a.stride + a.win_len > iq_len))
+		return set_err(-EINVAL, "fcch batch: windows exceed iq_len");
+	const size_t n = (size_t)a.n;
+	a.iq = (const float2 *)s.in((const float *)a.iq, (size_t)iq_len * 2);
+	a.ofs = s.in(a.ofs, n);
+	a.freq_shift = s.in(a.freq_shift, n);
+	a.toa = s.out(a.toa, n);
+	a.freq_error = s.out(a.freq_error, n);
+	a.snr = s.out(a.snr, n);
+	a.peak = s.out(a.peak, n);
+	return 0;
+}
+
+extern "C" {
+
+int gmr1b200_fcch_rough_batch(int fcch_type, const float *iq, int64_t iq_len, const int64_t *win_ofs,
+                              int64_t win_stride, int win_len, int sps, const float *freq_shift, float freq_shift0,
+                              int32_t *toa, float *peak, int n, void *stream)
+{
+	if (!toa)
+		return set_err(-EINVAL, "fcch_rough_batch: toa NULL");
+	FcchArgs a = {};
+	a.iq = (const float2 *)iq; a.ofs = win_ofs; a.stride = win_stride; a.n = n; a.win_len = win_len; a.sps = sps;
+	a.freq_shift = freq_shift; a.freq_shift0 = freq_shift0; a.toa = toa; a.peak = peak;
+	Stage s(stream);
+	int rc = fcch_common(fcch_type, a, s, iq_len, "fcch_rough_batch: bad argument");
+	if (rc)
+		return rc;
+	if (win_len / sps < a.len)
+		return set_err(-EINVAL, "fcch_rough_batch: window shorter than the FCCH burst");
+	if (n == 0)
+		return 0;
+	cudaError_t e = cudaSuccess;
+	if (!s.failed()) {
+		e = launch_fcch_rough(a, (cudaStream_t)stream);
+		if (e == cudaSuccess)
+			g_launches.fetch_add(1);
+	}
+	return s.finish(e, "fcch_rough kernel");
+}
+
+static int fine_or_snr(int mode, int fcch_type, const float *iq, int64_t iq_len, const int64_t *win_ofs,
+                       int64_t win_stride, int sps, const float *freq_shift, float freq_shift0,
+                       int32_t *toa, float *freq_error, float *snr, int n, void *stream)
+{
+	FcchArgs a = {};
+	a.iq = (const float2 *)iq; a.ofs = win_ofs; a.stride = win_stride; a.n = n; a.sps = sps;
+	a.freq_shift = freq_shift; a.freq_shift0 = freq_shift0; a.toa = toa; a.freq_error = freq_error; a.snr = snr;
+	if (fcch_type >= 0 && fcch_type <= 2)
+		a.win_len = FCCH_TYPES[fcch_type].len * sps;      // the reference insists on exactly this (fcch.c:546-551)
+	Stage s(stream);
+	int rc = fcch_common(fcch_type, a, s, iq_len, "fcch fine/snr batch: bad argument");
+	if (rc)
+		return rc;
+	if (n == 0)
+		return 0;
+	cudaError_t e = cudaSuccess;
+	if (!s.failed()) {
+		e = launch_fcch_fine(a, mode, (cudaStream_t)stream);
+		if (e == cudaSuccess)
+			g_launches.fetch_add(1);
+	}
+	return s.finish(e, "fcch_fine kernel");
+}
+
+int gmr1b200_fcch_fine_batch(int fcch_type, const float *iq, int64_t iq_len, const int64_t *win_ofs,
+                             int64_t win_stride, int sps, const float *freq_shift, float freq_shift0,
+                             int32_t *toa, float *freq_error, int n, void *stream)
+{
+	if (!toa || !freq_error)
+		return set_err(-EINVAL, "fcch_fine_batch: NULL output");
+	return fine_or_snr(0, fcch_type, iq, iq_len, win_ofs, win_stride, sps, freq_shift, freq_shift0,
+	                   toa, freq_error, nullptr, n, stream);
+}
+
+int gmr1b200_fcch_snr_batch(int fcch_type, const float *iq, int64_t iq_len, const int64_t *win_ofs,
+                            int64_t win_stride, int sps, const float *freq_shift, float freq_shift0,
+                            float *snr, int n, void *stream)
+{
+	if (!snr)
+		return set_err(-EINVAL, "fcch_snr_batch: NULL output");
+	return fine_or_snr(1, fcch_type, iq, iq_len, win_ofs, win_stride, sps, freq_shift, freq_shift0,
+	                   nullptr, nullptr, snr, n, stream);
+}
+
+static int misc_common(MiscArgs &a, Stage &s, int64_t iq_len)
+{
+	if (a.n < 0 || !a.iq || a.sps < 1 || a.sps > 16 || a.win_len < 1)
+		return set_err(-EINVAL, "sdr batch: bad argument");
+	if (a.n && !a.ofs && (a.stride < 0 || (int64_t)(a.n - 1) * a.stride + a.win_len > iq_len))
+		return set_err(-EINVAL, "sdr batch: windows exceed iq_len");
+	const size_t n = (size_t)a.n;
+	a.iq = (const float2 *)s.in((const float *)a.iq, (size_t)iq_len * 2);
+	a.ofs = s.in(a.ofs, n);
+	a.freq_shift = s.in(a.freq_shift, n);
+	a.dkab_p = s.in(a.dkab_p, n);
+	a.ebits = s.out(a.ebits, n * 8);
+	a.toa = s.out(a.toa, n);
+	a.rv = s.out(a.rv, n);
+	return 0;
+}
+
+int gmr1b200_dkab_demod_batch(const float *iq, int64_t iq_len, const int64_t *win_ofs, int64_t win_stride,
+                              int win_len, int sps, const float *freq_shift, float freq_shift0,
+                              const int32_t *p, int p0, int8_t *ebits, float *toa, int32_t *rv, int n, void *stream)
+{
+	if (!rv)
+		return set_err(-EINVAL, "dkab_demod_batch: rv NULL");
+	MiscArgs a = {};
+	a.iq = (const float2 *)iq; a.ofs = win_ofs; a.stride = win_stride; a.n = n; a.win_len = win_len; a.sps = sps;
+	a.freq_shift = freq_shift; a.freq_shift0 = freq_shift0; a.dkab_p = p; a.dkab_p0 = p0;
+	a.ebits = ebits; a.toa = toa; a.rv = rv;
+	Stage s(stream);
+	int rc = misc_common(a, s, iq_len);
+	if (rc || n == 0)
+		return rc;
+	cudaError_t e = cudaSuccess;
+	if (!s.failed()) {
+		e = launch_dkab(a, (cudaStream_t)stream);
+		if (e == cudaSuccess)
+			g_launches.fetch_add(1);
+	}
+	return s.finish(e, "dkab kernel");
+}
+
+int gmr1b200_pi4cxpsk_mod_order_batch(const float *iq, int64_t iq_len, const int64_t *win_ofs, int64_t win_stride,
+                                      int win_len, int sps, const float *freq_shift, float freq_shift0,
+                                      int32_t *order, int n, void *stream)
+{
+	if (!order)
+		return set_err(-EINVAL, "mod_order_batch: order NULL");
+	MiscArgs a = {};
+	a.iq = (const float2 *)iq; a.ofs = win_ofs; a.stride = win_stride; a.n = n; a.win_len = win_len; a.sps = sps;
+	a.freq_shift = freq_shift; a.freq_shift0 = freq_shift0; a.rv = order;
+	Stage s(stream);
+	int rc = misc_common(a, s, iq_len);
+	if (rc || n == 0)
+		return rc;
+	cudaError_t e = cudaSuccess;
+	if (!s.failed()) {
+		e = launch_mod_order(a, (cudaStream_t)stream);
+		if (e == cudaSuccess)
+			g_launches.fetch_add(1);
+	}
+	return s.finish(e, "mod_order kernel");
+}
+
+}  // extern "C"

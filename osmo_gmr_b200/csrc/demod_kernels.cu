@@ -31,6 +31,7 @@
 // within 2e-5 rad/symbol, soft bits within +-1 LSB (>= 99.5 % identical), and identical L2 / CRC
 // after stage 3.  Integer stages (stage 3) are bit-exact.
 #include <cuda_runtime.h>
+#include <math.h>
 
 #include "gmr1_tables.h"
 #include "launch.h"
@@ -39,6 +40,10 @@ namespace gmr1 {
 
 static constexpr int DM_WARPS = 4;
 static constexpr float PI_F = 3.14159265358979323846264338327f;
+
+// sin(pi * k / 512), k = 0..512: every position the early/late search visits is a multiple of
+// 1/512 (start integer, steps 1/2 .. 1/512), so the one sine an interpolation needs is a lookup
+__constant__ float c_sinpi512[513];
 
 __device__ __forceinline__ float warp_sum(float v)
 {
@@ -86,8 +91,8 @@ __device__ __forceinline__ void interp(const float *acc, int len, float pos, int
 {
 	const float fl = floorf(pos);
 	const int fe = (int)fl;
-	const float frac = pos - fl;                      // exact
-	const float S = sinpif(frac);
+	const float frac = pos - fl;                      // exact, a multiple of 1/512
+	const float S = c_sinpi512[(int)(frac * 512.0f)];
 	float te = 0.0f, tl = 0.0f;
 	if (lane < 21) {
 		const int j = lane - 10, k = fe + j;
@@ -98,9 +103,19 @@ __device__ __forceinline__ void interp(const float *acc, int len, float pos, int
 		if (LATE)
 			tl = (k + 2 >= 0 && k + 2 < len) ? acc[k + 2] * s : 0.0f;
 	}
-	ev = warp_sum(te);
-	if (LATE)
-		lv = warp_sum(tl);
+	if (LATE) {
+		// fold both sums into one tree: after the first exchange the lower half-warp carries the
+		// early terms, the upper half the late terms
+		const bool up = lane & 16;
+		float v = (up ? tl : te) + __shfl_xor_sync(0xffffffffu, up ? te : tl, 16);
+#pragma unroll
+		for (int o = 8; o; o >>= 1)
+			v += __shfl_xor_sync(0xffffffffu, v, o);
+		ev = __shfl_sync(0xffffffffu, v, 0);
+		lv = __shfl_sync(0xffffffffu, v, 16);
+	} else {
+		ev = warp_sum(te);
+	}
 }
 
 // osmo_cxvec_peak_energy_find(acc, 3, PEAK_EARLY_LATE, &peak) on a real vector; all lanes
@@ -193,7 +208,7 @@ static inline size_t warp_smem_bytes(int L, int w)
 // both are fp32 approximations of the same quantity).
 struct Norm { float ar, ai, inv_sd; };
 
-__device__ __forceinline__ Norm load_stats(const float2 *__restrict__ x, int L, float2 *win, int lane)
+__device__ __forceinline__ Norm load_stats(const float2 *__restrict__ x, int L, float2 *win, int lane, bool want_sd)
 {
 	float sr = 0.0f, si = 0.0f, sq = 0.0f;
 	if ((((uintptr_t)x) & 15) == 0) {
@@ -207,7 +222,12 @@ __device__ __forceinline__ Norm load_stats(const float2 *__restrict__ x, int L, 
 			w4[i] = v;
 			sr += v.x + v.z;
 			si += v.y + v.w;
-			sq += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+			if (want_sd) {
+				sq = fmaf(v.x, v.x, sq);
+				sq = fmaf(v.y, v.y, sq);
+				sq = fmaf(v.z, v.z, sq);
+				sq = fmaf(v.w, v.w, sq);
+			}
 		}
 		if ((L & 1) && lane == 0) {
 			const float2 v = __ldg(&x[L - 1]);
@@ -228,15 +248,21 @@ __device__ __forceinline__ Norm load_stats(const float2 *__restrict__ x, int L, 
 	}
 	sr = warp_sum(sr);
 	si = warp_sum(si);
-	sq = warp_sum(sq);
 	Norm n;
 	n.ar = sr / (float)L;
 	n.ai = si / (float)L;
-	const float var = sq / (float)L - (n.ar * n.ar + n.ai * n.ai);
-	float sd = var > 0.0f ? sqrtf(var) : 0.0f;
-	if (sd == 0.0f)
-		sd = 1.0f;
-	n.inv_sd = 1.0f / sd;
+	n.inv_sd = 1.0f;
+	if (want_sd) {
+		// The scale 1/stddev changes no decision and no soft bit (peak positions, phases and
+		// angles are scale invariant); it only sets the absolute value of the reported sync
+		// power, so the extra pass is skipped unless that output is requested.
+		sq = warp_sum(sq);
+		const float var = sq / (float)L - (n.ar * n.ar + n.ai * n.ai);
+		float sd = var > 0.0f ? sqrtf(var) : 0.0f;
+		if (sd == 0.0f)
+			sd = 1.0f;
+		n.inv_sd = 1.0f / sd;
+	}
 	__syncwarp();
 	return n;
 }
@@ -257,7 +283,8 @@ __device__ int sync_find(const BurstTab &bt, const WarpSmem &sm, const Norm &nm,
 		sm.accv[m] = 0.0f;
 	float p_toa = 0.0f, p_pwr = 0.0f;
 	int p_idx = -1;
-	const float fstep = fs * (float)sps;
+	float rot_s, rot_c;                               // e^{j*fs*sps*lane}: tap n of every chunk
+	sincosf((fs * (float)sps) * (float)lane, &rot_s, &rot_c);
 	for (int s = 0; s < bt.n_sync; s++) {
 		int tl = 0;
 		for (int c = 0; c < bt.n_chunk[s]; c++) {
@@ -265,9 +292,7 @@ __device__ int sync_find(const BurstTab &bt, const WarpSmem &sm, const Norm &nm,
 			// rotated taps + their sum
 			float tr = 0.0f, ti = 0.0f;
 			if (lane < cl) {
-				float sn, cs;
-				sincosf(fstep * (float)lane, &sn, &cs);
-				const float2 t = mul_conj_sym(bt.s_sym[s][c][lane], make_float2(cs, sn));
+				const float2 t = mul_conj_sym(bt.s_sym[s][c][lane], make_float2(rot_c, rot_s));
 				tr = t.x;
 				ti = t.y;
 			}
@@ -330,7 +355,7 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 	const float freq_shift = a.freq_shift ? a.freq_shift[b] : a.freq_shift0;
 	const float fs = (freq_shift - bt.rotation) / (float)sps;
 
-	const Norm nm = load_stats(x, L, sm.win, lane);
+	const Norm nm = load_stats(x, L, sm.win, lane, a.pwr != nullptr || (mode == 1 && (a.e_toa != nullptr || a.e_toa0 >= 0.0f)));
 
 	if (mode == 1) {
 		const float e_toa = a.e_toa ? a.e_toa[b] : a.e_toa0;
@@ -407,7 +432,7 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 				const float pos = (float)p0 + (float)cl / 2.0f;
 				if (c > 0) {   // arg(corr[c] * conj(corr[c-1])) / (pos[c] - pos[c-1])
 					const float re = cr * prev_r + ci * prev_i, im = ci * prev_r - cr * prev_i;
-					f += atan2f(im, re) / (pos - prev_pos);
+					f += fast_atan2f(im, re) / (pos - prev_pos);
 				}
 				prev_r = cr;
 				prev_i = ci;
@@ -440,7 +465,7 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 		}
 		pr = warp_sum(pr);
 		pi = warp_sum(pi);
-		phi0 = atan2f(pi, pr);
+		phi0 = fast_atan2f(pi, pr);
 	}
 
 	// ---- data symbols in the angle domain.  The reference rotates each sample three times
@@ -509,8 +534,19 @@ cudaError_t launch_demod(const DemodArgs &a, const BurstTab *d_bts, const BurstT
 	if (smem > 227 * 1024)
 		return cudaErrorInvalidValue;
 	static size_t attr_set[64] = {0};
+	static bool tab_up[64] = {false};
 	int dev = 0;
 	cudaGetDevice(&dev);
+	if (dev >= 64 || !tab_up[dev]) {
+		float h[513];
+		for (int k = 0; k <= 512; k++)
+			h[k] = (float)sin(3.14159265358979323846 * (double)k / 512.0);
+		cudaError_t e = cudaMemcpyToSymbol(c_sinpi512, h, sizeof(h));
+		if (e != cudaSuccess)
+			return e;
+		if (dev < 64)
+			tab_up[dev] = true;
+	}
 	if (dev >= 64 || attr_set[dev] < smem) {
 		cudaError_t e = cudaFuncSetAttribute(demod_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if (e != cudaSuccess)

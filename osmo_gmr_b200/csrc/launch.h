@@ -32,6 +32,40 @@ struct DemodArgs {
 cudaError_t launch_demod(const DemodArgs &a, const BurstTab *d_bts, const BurstTab *h_bts, int n_bt, int mode,
                          cudaStream_t st);
 
+// ---- stage 1: FCCH
+struct FcchArgs {
+	const float2  *iq;
+	const int64_t *ofs;
+	int64_t        stride;
+	int32_t        n, win_len, sps, len;   // len = FCCH burst length in symbols
+	float          freq;                   // chirp sweep (0.32 / 0.16)
+	const float   *freq_shift;
+	float          freq_shift0;
+	int32_t       *toa;                    // [n] samples
+	float         *freq_error;             // fine: [n] rad/symbol
+	float         *snr;                    // snr: [n]
+	float         *peak;                   // rough: [n] energy of the winning window, or NULL
+};
+cudaError_t launch_fcch_rough(const FcchArgs &a, cudaStream_t st);
+cudaError_t launch_fcch_fine(const FcchArgs &a, int mode, cudaStream_t st);
+
+// ---- DKAB / modulation order
+struct MiscArgs {
+	const float2  *iq;
+	const int64_t *ofs;
+	int64_t        stride;
+	int32_t        n, win_len, sps;
+	const float   *freq_shift;
+	float          freq_shift0;
+	const int32_t *dkab_p;                 // [n] DKAB position or NULL (then dkab_p0)
+	int32_t        dkab_p0;
+	int8_t        *ebits;                  // dkab: [n][8]
+	float         *toa;                    // dkab: [n]
+	int32_t       *rv;                     // dkab: 0 found / 1 not a DKAB / -EINVAL;  mod_order: 2 / 4
+};
+cudaError_t launch_dkab(const MiscArgs &a, cudaStream_t st);
+cudaError_t launch_mod_order(const MiscArgs &a, cudaStream_t st);
+
 // ---- workload synthesis
 struct SynthArgs {
 	const uint8_t *ebits;       // [n][ebits_stride] hard bits

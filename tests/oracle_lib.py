@@ -139,6 +139,49 @@ class Oracle:
                 ctypes.addressof(bt), ctypes.addressof(sid), ctypes.addressof(toa))
         return rc, bt.value, sid.value, toa.value
 
+    def _fcch(self, t):
+        name = ["gmr1_fcch_burst", "gmr1_fcch3_lband_burst", "gmr1_fcch3_sband_burst"][t]
+        return ctypes.addressof(ctypes.c_char.in_dll(self.c, name))
+
+    def fcch_rough(self, window, sps, freq_shift, t=0):
+        cv, keep = self._cxvec(window)
+        toa = ctypes.c_int(-99999)
+        fn = self.c.gmr1_fcch_rough
+        fn.argtypes = [P, P, ctypes.c_int, ctypes.c_float, P]
+        rc = fn(self._fcch(t), ctypes.addressof(cv), sps, float(freq_shift), ctypes.addressof(toa))
+        return rc, toa.value
+
+    def fcch_fine(self, window, sps, freq_shift, t=0):
+        cv, keep = self._cxvec(window)
+        toa, fe = ctypes.c_int(-99999), ctypes.c_float()
+        fn = self.c.gmr1_fcch_fine
+        fn.argtypes = [P, P, ctypes.c_int, ctypes.c_float, P, P]
+        rc = fn(self._fcch(t), ctypes.addressof(cv), sps, float(freq_shift), ctypes.addressof(toa), ctypes.addressof(fe))
+        return rc, toa.value, fe.value
+
+    def fcch_snr(self, window, sps, freq_shift, t=0):
+        cv, keep = self._cxvec(window)
+        snr = ctypes.c_float()
+        fn = self.c.gmr1_fcch_snr
+        fn.argtypes = [P, P, ctypes.c_int, ctypes.c_float, P]
+        rc = fn(self._fcch(t), ctypes.addressof(cv), sps, float(freq_shift), ctypes.addressof(snr))
+        return rc, snr.value
+
+    def dkab_demod(self, window, sps, freq_shift, pp):
+        cv, keep = self._cxvec(window)
+        eb = np.zeros(8, np.int8)
+        toa = ctypes.c_float()
+        fn = self.c.gmr1_dkab_demod
+        fn.argtypes = [P, ctypes.c_int, ctypes.c_float, ctypes.c_int, P, P]
+        rc = fn(ctypes.addressof(cv), sps, float(freq_shift), pp, p(eb), ctypes.addressof(toa))
+        return rc, eb, toa.value
+
+    def mod_order(self, window, sps, freq_shift):
+        cv, keep = self._cxvec(window)
+        fn = self.c.gmr1_pi4cxpsk_mod_order
+        fn.argtypes = [P, ctypes.c_int, ctypes.c_float]
+        return fn(ctypes.addressof(cv), sps, float(freq_shift))
+
     def a5(self, n, key, fn, nbits):
         dl = np.zeros(nbits, np.uint8)
         k = np.ascontiguousarray(key, np.uint8)

@@ -83,7 +83,12 @@ def modulate(name, ebits, sps, win, toa, cfo, phase, esn0_db, rng, sync_id=0, am
     """-> complex64 windows [n, len*sps + win].
     toa: position (samples, fractional) of symbol 0 within the window;  cfo: rad/symbol;
     phase: rad;  esn0_db: per burst (scalar or [n])."""
-    s = symbols(name, ebits, sync_id)
+    return modulate_symbols(symbols(name, ebits, sync_id), sps, win, toa, cfo, phase, esn0_db, rng, amp)
+
+
+def modulate_symbols(s, sps, win, toa, cfo, phase, esn0_db, rng, amp=1.0):
+    """pulse-shape arbitrary complex symbol rows [n, len] (0 = silent symbol)"""
+    s = np.atleast_2d(s)
     n, ln = s.shape
     L = ln * sps + win
     toa = np.broadcast_to(np.asarray(toa, np.float64), (n,))[:, None]
@@ -100,4 +105,30 @@ def modulate(name, ebits, sps, win, toa, cfo, phase, esn0_db, rng, sync_id=0, am
     x *= amp * np.exp(1j * (cfo * t + phase))
     sig = np.broadcast_to(amp * 10.0 ** (-np.asarray(esn0_db, np.float64) / 20.0) / np.sqrt(2.0), (n,))[:, None]
     x += sig * (rng.standard_normal((n, L)) + 1j * rng.standard_normal((n, L)))
+    return x.astype(np.complex64)
+
+
+def dkab_symbols(n, p, rng):
+    """DKAB: 117-symbol slot, silent except two 5-symbol keep-alive pulses at symbols 2+p and
+    2+p+59 (reference src/sdr/dkab.c:73-75), random BPSK with the continuous pi/4 rotation"""
+    s = np.zeros((n, 117), np.complex128)
+    for o in (2 + p, 2 + p + 59):
+        s[:, o:o + 5] = 1.0 - 2.0 * rng.integers(0, 2, (n, 5))
+    return s * np.exp(1j * (np.pi / 4) * np.arange(117))[None, :]
+
+
+def fcch_chirp(sps, freq=0.32, ln=117):
+    """real dual chirp sqrt(2) cos(freq*2pi/len * (t - len/2)^2), t in symbols (fcch.c:167-193)"""
+    t = np.arange(ln * sps) / sps - ln / 2.0
+    return np.sqrt(2.0) * np.cos(freq * 2 * np.pi / ln * t * t)
+
+
+def fcch_window(L, sps, pos, cfo, esn0_db, rng, freq=0.32, ln=117, amp=1.0):
+    """L-sample window of noise with one FCCH burst starting at integer sample `pos`, carrier
+    offset cfo (rad/symbol)"""
+    sig = amp * 10.0 ** (-esn0_db / 20.0) / np.sqrt(2.0)
+    x = sig * (rng.standard_normal(L) + 1j * rng.standard_normal(L))
+    c = fcch_chirp(sps, freq, ln)
+    n = np.arange(len(c))
+    x[pos:pos + len(c)] += amp * c * np.exp(1j * (cfo * n / sps + rng.uniform(0, 2 * np.pi)))
     return x.astype(np.complex64)

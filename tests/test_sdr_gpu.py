@@ -1,0 +1,102 @@
+"""GPU parity, stage 1 + small SDR entry points: FCCH rough / fine / snr, DKAB, modulation order
+vs the oracle (reference src/sdr/fcch.c, dkab.c, pi4cxpsk.c:693) on identical synthetic IQ."""
+import numpy as np
+import pytest
+
+import sigen
+
+pytestmark = pytest.mark.gpu
+SPS = 4
+
+
+def _iq(x):
+    return np.ascontiguousarray(x).view(np.float32)
+
+
+def test_fcch_rough(gpu_lib, oracle):
+    rng = np.random.default_rng(31)
+    n, L = 12, 30888                      # 330 ms at sps 4 (src/gmr1_rx.c:612)
+    pos = rng.integers(600, L - 1200, n)
+    x = np.stack([sigen.fcch_window(L, SPS, int(pos[i]), rng.uniform(-0.08, 0.08), [3.0, 10.0, 20.0][i % 3], rng)
+                  for i in range(n)])
+    fsh = np.where(np.arange(n) % 2, rng.uniform(-0.05, 0.05, n), 0.0).astype(np.float32)
+    toa = np.full(n, -1, np.int32)
+    peak = np.zeros(n, np.float32)
+    gpu_lib.call("gmr1b200_fcch_rough_batch", 0, _iq(x), n * L, None, L, L, SPS, fsh, 0.0, toa, peak, n, None)
+    same = 0
+    for i in range(n):
+        rc, t = oracle.fcch_rough(x[i], SPS, fsh[i])
+        assert rc == 0 and abs(int(toa[i]) - t) <= 1, (i, toa[i], t)
+        assert abs(t - pos[i]) <= 2 * SPS                  # the oracle itself finds the burst
+        same += int(toa[i] == t)
+    assert same >= n - 1
+
+
+def test_fcch_fine_and_snr(gpu_lib, oracle):
+    rng = np.random.default_rng(32)
+    n, W = 96, 117 * SPS
+    xs, fsh = [], []
+    for i in range(n):
+        off = int(rng.integers(-12, 13))                   # residual timing error after rough
+        full = sigen.fcch_window(W + 64, SPS, 32 + off, rng.uniform(-0.15, 0.15), [6.0, 12.0, 25.0][i % 3], rng)
+        xs.append(full[32:32 + W])
+        fsh.append(rng.uniform(-0.03, 0.03) if i % 2 else 0.0)
+    x = np.stack(xs)
+    fsh = np.array(fsh, np.float32)
+    toa = np.full(n, -999, np.int32)
+    fe = np.zeros(n, np.float32)
+    snr = np.zeros(n, np.float32)
+    gpu_lib.call("gmr1b200_fcch_fine_batch", 0, _iq(x), n * W, None, W, SPS, fsh, 0.0, toa, fe, n, None)
+    gpu_lib.call("gmr1b200_fcch_snr_batch", 0, _iq(x), n * W, None, W, SPS, fsh, 0.0, snr, n, None)
+    same = 0
+    for i in range(n):
+        rc, t, f = oracle.fcch_fine(x[i], SPS, fsh[i])
+        assert rc == 0 and abs(int(toa[i]) - t) <= 1 and abs(fe[i] - f) <= 1e-5, (i, toa[i], t, fe[i], f)
+        same += int(toa[i] == t)
+        rc, s = oracle.fcch_snr(x[i], SPS, fsh[i])
+        assert rc == 0 and abs(snr[i] - s) <= 2e-3 * abs(s), (i, snr[i], s)
+    assert same >= 0.97 * n
+
+
+def test_dkab(gpu_lib, oracle):
+    rng = np.random.default_rng(33)
+    n, win = 64, 6                          # gmr1_rx maps DKABs with the NT3 window (src/gmr1_rx.c:549)
+    p = rng.integers(0, 40, n).astype(np.int32)
+    L = 117 * SPS + win
+    x = np.zeros((n, L), np.complex64)
+    for i in range(n):
+        if i % 4 == 3:                       # not a DKAB: a full NT3 burst
+            hard = rng.integers(0, 2, (1, 212), dtype=np.uint8)
+            x[i] = sigen.modulate("nt3_speech", hard, SPS, win, rng.uniform(1, 5), 0.0, rng.uniform(0, 6), 15.0, rng)[0]
+        else:
+            x[i] = sigen.modulate_symbols(sigen.dkab_symbols(1, int(p[i]), rng), SPS, win, rng.uniform(1, 5), 0.0,
+                                          rng.uniform(0, 6), [10.0, 20.0, 30.0][i % 3], rng)[0]
+    eb = np.zeros((n, 8), np.int8)
+    toa = np.zeros(n, np.float32)
+    rv = np.full(n, -9, np.int32)
+    gpu_lib.call("gmr1b200_dkab_demod_batch", _iq(x), n * L, None, L, L, SPS, None, 0.0, p, 0, eb, toa, rv, n, None)
+    found = 0
+    for i in range(n):
+        rc, eb_o, toa_o = oracle.dkab_demod(x[i], SPS, 0.0, int(p[i]))
+        assert rv[i] == rc, (i, rv[i], rc)
+        assert abs(toa[i] - toa_o) <= 2e-3 * max(1.0, abs(toa_o)), (i, toa[i], toa_o)
+        if rc == 0:
+            found += 1
+            assert np.abs(eb[i].astype(int) - eb_o.astype(int)).max() <= 1, (i, eb[i], eb_o)
+    assert found >= n // 2
+
+
+def test_mod_order(gpu_lib, oracle):
+    rng = np.random.default_rng(34)
+    n, win = 40, 6
+    L = 117 * SPS + win
+    x = np.zeros((n, L), np.complex64)
+    for i in range(n):
+        name = "nt3_facch" if i % 2 else "nt3_speech"
+        hard = rng.integers(0, 2, (1, sigen.burst_ebits(name)), dtype=np.uint8)
+        x[i] = sigen.modulate(name, hard, SPS, win, 3.0, rng.uniform(-0.01, 0.01), rng.uniform(0, 6), 20.0, rng)[0]
+    order = np.zeros(n, np.int32)
+    gpu_lib.call("gmr1b200_pi4cxpsk_mod_order_batch", _iq(x), n * L, None, L, L, SPS, None, 0.0, order, n, None)
+    for i in range(n):
+        assert order[i] == oracle.mod_order(x[i], SPS, 0.0), i
+    assert (order[1::2] == 2).all() and (order[0::2] == 4).all()
