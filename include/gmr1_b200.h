@@ -93,6 +93,12 @@ int gmr1b200_tch9_decode_batch(uint8_t *l2, gmr1b200_sbit_t *bits_sacch, gmr1b20
                                const int32_t *prev1, const int32_t *prev2,
                                int32_t *conv_rv, int n, void *stream);
 
+/* Second half of gmr1_tch9_decode for callers that keep the reference's stateful interleaver:
+ * rows [n][648] are the soft bits AFTER decipher / descramble / gmr1_deinterleave_inter (tch9.c:150-165);
+ * this does the intra de-interleave, de-puncturing and Viterbi (tch9.c:166-174).  l2 as above. */
+int gmr1b200_tch9_decode_rows_batch(uint8_t *l2, const gmr1b200_sbit_t *rows, int mode,
+                                    int32_t *conv_rv, int n, void *stream);
+
 /* replaces gmr1_rach_decode, src/l1/rach.c:137 (l1/rach.h:38-39)
  * rach [n][18], bits_e [n][494], sb_mask [n] or NULL (then sb_mask0 for every unit),
  * crc_rv [n][2] or NULL, crc [n] = return value (crc_rv[0] || crc_rv[1]) */
@@ -178,6 +184,9 @@ void *gmr1b200_tch9_interleaver_new(void);
 void gmr1b200_tch9_interleaver_free(void *interleaver);
 int gmr1b200_tch9_encode(gmr1b200_ubit_t *bits_e, const uint8_t *l2, int mode, const gmr1b200_ubit_t *bits_sacch,
                          const gmr1b200_ubit_t *bits_status, const gmr1b200_ubit_t *ciph, void *interleaver);
+/* first half of gmr1_tch9_encode (tch9.c:105-107): conv-encode + puncture + intra interleave -> ep [648],
+ * for callers that keep the reference's stateful inter-burst interleaver object */
+int gmr1b200_tch9_encode_ep(gmr1b200_ubit_t *ep, const uint8_t *l2, int mode);
 /* replaces gmr1_rach_encode, src/l1/rach.c:76.  bits_e [494], rach [18] */
 int gmr1b200_rach_encode(gmr1b200_ubit_t *bits_e, const uint8_t *rach, int sb_mask);
 /* replaces gmr1_tch3_encode, src/l1/tch3.c:60 - the reference passes the arguments of
@@ -185,6 +194,56 @@ int gmr1b200_rach_encode(gmr1b200_ubit_t *bits_e, const uint8_t *rach, int sb_ma
  * bits_e [212], frame0/frame1 [10] MSB first, bits_s [4], ciph [208]/NULL, m = mux mode */
 int gmr1b200_tch3_encode(gmr1b200_ubit_t *bits_e, const uint8_t *frame0, const uint8_t *frame1,
                          const gmr1b200_ubit_t *bits_s, const gmr1b200_ubit_t *ciph, int m);
+
+/* Flattened burst-format descriptor for callers that bring their own format (the compat layer
+ * converts the reference's struct gmr1_pi4cxpsk_burst, sdr/pi4cxpsk.h:77-98, into this). */
+#define GMR1B200_MAX_SYNC        4     /* GMR1_MAX_SYNC      (sdr/pi4cxpsk.h:39) */
+#define GMR1B200_MAX_SYNC_CHUNK  6
+#define GMR1B200_MAX_SYNC_SYMS   32    /* GMR1_MAX_SYNC_SYMS (sdr/pi4cxpsk.h:40) */
+#define GMR1B200_MAX_DATA_CHUNK  6
+struct gmr1b200_burst_desc {
+	float   rotation;                 /* per-symbol rotation, rad (pi/4 or pi/2) */
+	int32_t nbits;                    /* bits per symbol, 1 or 2 */
+	int32_t len;                      /* symbols incl. guard */
+	int32_t ebits;                    /* soft bits produced */
+	int32_t n_sync;                   /* alternative training sequences */
+	int32_t n_chunk[GMR1B200_MAX_SYNC];
+	int16_t s_pos[GMR1B200_MAX_SYNC][GMR1B200_MAX_SYNC_CHUNK];
+	int16_t s_len[GMR1B200_MAX_SYNC][GMR1B200_MAX_SYNC_CHUNK];
+	uint8_t s_sym[GMR1B200_MAX_SYNC][GMR1B200_MAX_SYNC_CHUNK][GMR1B200_MAX_SYNC_SYMS]; /* phase index 0..3 (k*pi/2) */
+	int32_t n_data;
+	int16_t d_pos[GMR1B200_MAX_DATA_CHUNK];
+	int16_t d_len[GMR1B200_MAX_DATA_CHUNK];
+};
+/* copy of a built-in descriptor */
+int gmr1b200_burst_desc_get(int burst_type, struct gmr1b200_burst_desc *out);
+/* as gmr1b200_pi4cxpsk_demod_batch / _detect_batch with caller-supplied descriptors (host memory) */
+int gmr1b200_pi4cxpsk_demod_desc_batch(const struct gmr1b200_burst_desc *desc, const float *iq, int64_t iq_len,
+                                       const int64_t *win_ofs, int64_t win_stride, int win_len, int sps,
+                                       const float *freq_shift, float freq_shift0,
+                                       gmr1b200_sbit_t *ebits, int ebits_stride,
+                                       int32_t *sync_id, float *toa, float *freq_err, float *pwr,
+                                       int n, void *stream);
+int gmr1b200_pi4cxpsk_detect_desc_batch(const struct gmr1b200_burst_desc *descs, int n_types,
+                                        const float *e_toa, float e_toa0,
+                                        const float *iq, int64_t iq_len,
+                                        const int64_t *win_ofs, int64_t win_stride, int win_len, int sps,
+                                        const float *freq_shift, float freq_shift0,
+                                        int32_t *bt_id, int32_t *sync_id, float *toa,
+                                        int n, void *stream);
+
+/* replaces gmr1_fcch_rough_multi, src/sdr/fcch.c:341 (sdr/fcch.h:51-53): all overlapping FCCHs in one
+ * >= 650 ms window.  The 117-tap correlation runs on the GPU; the peak bookkeeping (two-cycle mixing,
+ * avg+3sigma threshold, sorted de-duplicated insert, fcch.c:373-483) is a few thousand scalar steps and
+ * runs on the host exactly as written there.  toa [N] out; returns the number of FCCHs found (>= 0) or
+ * -errno (-EINVAL: window shorter than 650 ms or the two cycles do not line up). */
+int gmr1b200_fcch_rough_multi(int fcch_type, const float *iq, int64_t win_len, int sps, float freq_shift,
+                              int32_t *toa, int N, void *stream);
+
+/* ---- A5 cipher stream (host; input to the ciphered decoders) ------------------------------------
+ * replaces gmr1_a5 / gmr1_a5_1, src/l1/a5.c:57,226 (l1/a5.h:37-41): n = 0 (all zero) or 1 (A5/1-GMR);
+ * key [8], dl / ul [nbits] ubits, either may be NULL */
+void gmr1b200_a5(int n, const uint8_t *key, uint32_t fn, int nbits, gmr1b200_ubit_t *dl, gmr1b200_ubit_t *ul);
 
 /* ---- stage 1: FCCH chirp acquisition ----------------------------------------------------------
  * fcch_type: 0 = gmr1_fcch_burst (sweep 0.32, 117 symbols), 1 = gmr1_fcch3_lband_burst (0.32, 468),

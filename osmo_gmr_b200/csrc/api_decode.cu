@@ -117,6 +117,16 @@ int gmr1b200_tch9_decode_batch(uint8_t *l2, int8_t *bits_sacch, int8_t *bits_sta
 	return run_decode(CH_TCH9_2K4 + mode, a, 662, 658, bytes[mode], stream);
 }
 
+int gmr1b200_tch9_decode_rows_batch(uint8_t *l2, const int8_t *rows, int mode, int32_t *conv_rv, int n, void *stream)
+{
+	if (mode < 0 || mode > 2)
+		return set_err(-EINVAL, "tch9_decode_rows_batch: mode must be 0 (2k4), 1 (4k8) or 2 (9k6)");
+	static const int bytes[3] = {18, 30, 60};
+	DecodeArgs a = {};
+	a.ebits = rows; a.n = n; a.l2 = l2; a.conv = conv_rv; a.t9_rows = 1;
+	return run_decode(CH_TCH9_2K4 + mode, a, 648, 0, bytes[mode], stream);
+}
+
 int gmr1b200_rach_decode_batch(uint8_t *rach, const int8_t *bits_e, const uint8_t *sb_mask, int sb_mask0,
                                int32_t *conv_rv, int32_t *crc_rv, int32_t *crc, int n, void *stream)
 {

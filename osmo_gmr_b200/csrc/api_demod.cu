@@ -29,16 +29,34 @@ cudaError_t gmr1::device_bursts(const BurstTab **out)
 	return cudaSuccess;
 }
 
-static int run_demod(const int *types, int n_types, int mode, DemodArgs a, int64_t iq_len, void *stream)
+static_assert(sizeof(gmr1b200_burst_desc) == sizeof(BurstTab), "public descriptor must mirror gmr1::BurstTab");
+
+static int run_demod(const int *types, int n_types, int mode, DemodArgs a, int64_t iq_len, void *stream,
+                     const BurstTab *custom = nullptr)
 {
 	if (a.n < 0 || !a.iq || n_types < 1 || n_types > 8 || a.win_len < 1)
 		return set_err(-EINVAL, "pi4cxpsk batch: bad argument");
-	for (int i = 0; i < n_types; i++)
+	for (int i = 0; i < n_types && !custom; i++)
 		if (types[i] < 0 || types[i] >= BT_COUNT)
 			return set_err(-EINVAL, "pi4cxpsk batch: unknown burst type");
+	for (int i = 0; i < n_types && custom; i++) {
+		const BurstTab &t = custom[i];
+		bool ok = t.nbits >= 1 && t.nbits <= 2 && t.len > 0 && t.len <= 468 && t.n_sync >= 1 && t.n_sync <= MAX_SYNC &&
+		          t.n_data >= 0 && t.n_data <= MAX_DATA_CHUNK;
+		for (int s = 0; ok && s < t.n_sync; s++) {
+			ok = t.n_chunk[s] >= 1 && t.n_chunk[s] <= MAX_SYNC_CHUNK;
+			for (int c = 0; ok && c < t.n_chunk[s]; c++)
+				ok = t.s_len[s][c] >= 1 && t.s_len[s][c] <= MAX_SYNC_SYMS && t.s_pos[s][c] >= 0 &&
+				     t.s_pos[s][c] + t.s_len[s][c] <= t.len;
+		}
+		for (int c = 0; ok && c < t.n_data; c++)
+			ok = t.d_pos[c] >= 0 && t.d_len[c] >= 0 && t.d_pos[c] + t.d_len[c] <= t.len;
+		if (!ok)
+			return set_err(-EINVAL, "pi4cxpsk batch: malformed burst descriptor");
+	}
 	if (a.sps < 4 || a.sps > 16)
 		return set_err(-EINVAL, "pi4cxpsk batch: sps must be 4..16");
-	const BurstTab &t0 = burst_tab(types[0]);
+	const BurstTab &t0 = custom ? custom[0] : burst_tab(types[0]);
 	if (a.win_len < t0.len * a.sps)
 		return set_err(-EINVAL, "pi4cxpsk batch: window shorter than the burst");
 	if (mode == 0 && (!a.ebits || a.ebits_stride < t0.ebits))
@@ -69,9 +87,11 @@ static int run_demod(const int *types, int n_types, int mode, DemodArgs a, int64
 	// the kernel takes a dense array of the selected descriptors
 	BurstTab h_sel[8];
 	for (int i = 0; i < n_types; i++)
-		h_sel[i] = burst_tab(types[i]);
+		h_sel[i] = custom ? custom[i] : burst_tab(types[i]);
 	const BurstTab *d_sel = nullptr;
-	if (n_types == 1) {
+	if (custom) {
+		d_sel = s.in(custom, (size_t)n_types);      // host descriptors: staged like any other input
+	} else if (n_types == 1) {
 		d_sel = d_all + types[0];
 	} else {
 		BurstTab *tmp = nullptr;
@@ -92,7 +112,7 @@ static int run_demod(const int *types, int n_types, int mode, DemodArgs a, int64
 		if (e == cudaSuccess)
 			g_launches.fetch_add(1);
 	}
-	if (n_types > 1 && d_sel)
+	if (!custom && n_types > 1 && d_sel)
 		cudaFreeAsync((void *)d_sel, (cudaStream_t)stream);
 	return s.finish(e, "pi4cxpsk kernel");
 }
@@ -145,6 +165,45 @@ int gmr1b200_synth_bursts(int burst_type, const uint8_t *ebits, int ebits_stride
 	a.esn0_db = esn0_db; a.esn0_db0 = esn0_db0; a.amp = amp; a.amp0 = amp0; a.seed = seed;
 	a.iq = (float2 *)iq; a.ofs = win_ofs; a.stride = win_stride;
 	return run_synth(burst_type, a, iq_len, stream);
+}
+
+int gmr1b200_burst_desc_get(int bt, struct gmr1b200_burst_desc *out)
+{
+	if (bt < 0 || bt >= BT_COUNT || !out)
+		return -EINVAL;
+	memcpy(out, &burst_tab(bt), sizeof(*out));
+	return 0;
+}
+
+int gmr1b200_pi4cxpsk_demod_desc_batch(const struct gmr1b200_burst_desc *desc, const float *iq, int64_t iq_len,
+                                       const int64_t *win_ofs, int64_t win_stride, int win_len, int sps,
+                                       const float *freq_shift, float freq_shift0, int8_t *ebits, int ebits_stride,
+                                       int32_t *sync_id, float *toa, float *freq_err, float *pwr, int n, void *stream)
+{
+	if (!desc)
+		return set_err(-EINVAL, "pi4cxpsk_demod_desc_batch: desc NULL");
+	DemodArgs a = {};
+	a.iq = (const float2 *)iq; a.ofs = win_ofs; a.stride = win_stride; a.n = n; a.win_len = win_len; a.sps = sps;
+	a.freq_shift = freq_shift; a.freq_shift0 = freq_shift0; a.e_toa0 = -1.0f;
+	a.ebits = ebits; a.ebits_stride = ebits_stride; a.sync_id = sync_id; a.toa = toa; a.freq_err = freq_err; a.pwr = pwr;
+	const int dummy = 0;
+	return run_demod(&dummy, 1, 0, a, iq_len, stream, reinterpret_cast<const BurstTab *>(desc));
+}
+
+int gmr1b200_pi4cxpsk_detect_desc_batch(const struct gmr1b200_burst_desc *descs, int n_types, const float *e_toa,
+                                        float e_toa0, const float *iq, int64_t iq_len, const int64_t *win_ofs,
+                                        int64_t win_stride, int win_len, int sps, const float *freq_shift,
+                                        float freq_shift0, int32_t *bt_id, int32_t *sync_id, float *toa, int n,
+                                        void *stream)
+{
+	if (!descs)
+		return set_err(-EINVAL, "pi4cxpsk_detect_desc_batch: descs NULL");
+	DemodArgs a = {};
+	a.iq = (const float2 *)iq; a.ofs = win_ofs; a.stride = win_stride; a.n = n; a.win_len = win_len; a.sps = sps;
+	a.freq_shift = freq_shift; a.freq_shift0 = freq_shift0; a.e_toa = e_toa; a.e_toa0 = e_toa0;
+	a.bt_id = bt_id; a.sync_id = sync_id; a.toa = toa;
+	const int dummy[8] = {0};
+	return run_demod(dummy, n_types, 1, a, iq_len, stream, reinterpret_cast<const BurstTab *>(descs));
 }
 
 int gmr1b200_burst_len(int bt)

@@ -62,6 +62,14 @@ int gmr1b200_tch9_encode(uint8_t *bits_e, const uint8_t *l2, int mode, const uin
 	return 0;
 }
 
+int gmr1b200_tch9_encode_ep(uint8_t *ep, const uint8_t *l2, int mode)
+{
+	if (!ep || !l2 || mode < 0 || mode > 2)
+		return -EINVAL;
+	encode_tch9_ep(ep, l2, mode);
+	return 0;
+}
+
 int gmr1b200_rach_encode(uint8_t *bits_e, const uint8_t *rach, int sb_mask)
 {
 	if (!bits_e || !rach)

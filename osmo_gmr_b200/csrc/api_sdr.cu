@@ -3,6 +3,10 @@
 #include "api_common.h"
 #include "launch.h"
 
+#include <math.h>
+#include <stdlib.h>
+#include <vector>
+
 using namespace gmr1;
 
 // FCCH burst formats (reference src/sdr/fcch.c:50-70): sweep range, symbols
@@ -53,6 +57,141 @@ int gmr1b200_fcch_rough_batch(int fcch_type, const float *iq, int64_t iq_len, co
 			g_launches.fetch_add(1);
 	}
 	return s.finish(e, "fcch_rough kernel");
+}
+
+// ---- multi-FCCH acquisition: GPU correlation + the reference's scalar peak bookkeeping ----------
+// (src/sdr/fcch.c:264-326 _peak_record, :373-483)
+static void peak_record(int burst_len, int *toa, float *pwr, int *n, int N, int Lp, int sps, int peak_toa, float peak_pwr)
+{
+	int has_dupe = 0;
+	const int th = (burst_len * sps) >> 1;
+	for (int i = 0; i < *n; i++) {
+		const int d = (toa[i] % Lp) - (peak_toa % Lp);
+		if (abs(d) > th)
+			continue;
+		if (pwr[i] > peak_pwr) {            // an equal-or-stronger twin is already recorded
+			if (!has_dupe)
+				has_dupe = 1;
+			continue;
+		}
+		for (int j = i; j < *n - 1; j++) {  // drop the weaker twin
+			toa[j] = toa[j + 1];
+			pwr[j] = pwr[j + 1];
+		}
+		*n -= 1;
+		has_dupe = -1;
+	}
+	if (has_dupe > 0)
+		return;
+	int i;
+	for (i = 0; i < *n; i++)
+		if (peak_pwr > pwr[i])
+			break;
+	if (i == N)
+		return;
+	for (int j = N - 1; j > i; j--) {
+		toa[j] = toa[j - 1];
+		pwr[j] = pwr[j - 1];
+	}
+	toa[i] = peak_toa;
+	pwr[i] = peak_pwr;
+	if (*n != N)
+		*n += 1;
+}
+
+int gmr1b200_fcch_rough_multi(int fcch_type, const float *iq, int64_t win_len, int sps, float freq_shift,
+                              int32_t *peaks_toa, int N, void *stream)
+{
+	if (fcch_type < 0 || fcch_type > 2 || !iq || !peaks_toa || N < 1 || sps < 1 || sps > 16)
+		return set_err(-EINVAL, "fcch_rough_multi: bad argument");
+	const int sym_rate = 23400;
+	if (win_len < ((int64_t)650 * sym_rate * sps) / 1000)      // fcch.c:355
+		return set_err(-EINVAL, "fcch_rough_multi: needs 650 ms of signal");
+	const int blen = FCCH_TYPES[fcch_type].len;
+	const int l = (int)(win_len / sps), nc = l - blen + 1;
+	std::vector<float> pw((size_t)nc);
+	{
+		FcchArgs a = {};
+		a.iq = (const float2 *)iq; a.stride = 0; a.n = 1; a.win_len = (int)win_len; a.sps = sps;
+		a.freq_shift0 = freq_shift;
+		Stage s(stream);
+		int dummy_toa;
+		a.toa = &dummy_toa;
+		int rc = fcch_common(fcch_type, a, s, win_len, "fcch_rough_multi: bad argument");
+		if (rc)
+			return rc;
+		a.en_out = s.out(pw.data(), (size_t)nc);
+		cudaError_t e = cudaSuccess;
+		if (!s.failed()) {
+			e = launch_fcch_rough(a, (cudaStream_t)stream);
+			if (e == cudaSuccess)
+				g_launches.fetch_add(1);
+		}
+		rc = s.finish(e, "fcch_rough kernel");
+		if (rc)
+			return rc;
+	}
+	float *corr_pwr = pw.data();
+	int Lw = (320 * sym_rate) / 1000 + blen, Lp = (320 * sym_rate) / 1000;
+	int pwr_max_idx = 0;
+	float pwr_max = 0.0f;
+	for (int i = 0; i < nc; i++)
+		if (corr_pwr[i] > pwr_max && i < Lw) {
+			pwr_max = corr_pwr[i];
+			pwr_max_idx = i;
+		}
+	// the twin one period later, +-10 symbols (fcch.c:397-430)
+	float pwrs[2] = {0.0f, 0.0f}, peaks[2] = {0.0f, 0.0f};
+	for (int i = -10; i <= 10; i++) {
+		int j = pwr_max_idx + i;
+		if (j > 0 && j < nc) {
+			pwrs[0] += corr_pwr[j];
+			peaks[0] += corr_pwr[j] * j;
+		}
+		j += Lp;
+		if (j > 0 && j < nc) {
+			pwrs[1] += corr_pwr[j];
+			peaks[1] += corr_pwr[j] * j;
+		}
+	}
+	peaks[0] /= pwrs[0];
+	peaks[1] /= pwrs[1];
+	const int nLp = (int)round(peaks[1] - peaks[0]);
+	if (abs(nLp - Lp) > 10)
+		return set_err(-EINVAL, "fcch_rough_multi: FCCH period mismatch");
+	Lp = nLp;
+	if (Lw + Lp > nc)
+		Lw = nc - Lp;
+	float avg = 0.0f;
+	for (int i = 0; i < Lw; i++) {          // geometric mix of the two cycles (fcch.c:435-441)
+		const float v = sqrtf(corr_pwr[i] * corr_pwr[i + Lp]);
+		corr_pwr[i] = v;
+		avg += v;
+	}
+	avg /= Lw;
+	float stddev = 0.0f;
+	for (int i = 0; i < Lw; i++) {
+		const float v = corr_pwr[i] - avg;
+		stddev += v * v;
+	}
+	stddev = sqrtf(stddev / Lw);
+	const float th = avg + 3.0f * stddev;
+	std::vector<float> peaks_pwr((size_t)N, 0.0f);
+	int peaks_cnt = 0;
+	for (int i = 1, in_peak = 0; i < Lw - 1; i++) {
+		if (corr_pwr[i] > th) {
+			if (in_peak)
+				continue;
+			in_peak = 1;
+			const float p_pwr = corr_pwr[i - 1] + corr_pwr[i] + corr_pwr[i + 1];
+			const float p_fpos = (-corr_pwr[i - 1] + corr_pwr[i + 1]) / p_pwr;
+			const int p_pos = (int)round((i + p_fpos) * sps);
+			peak_record(blen, peaks_toa, peaks_pwr.data(), &peaks_cnt, N, Lp, sps, p_pos, p_pwr);
+		} else {
+			in_peak = 0;
+		}
+	}
+	return peaks_cnt;
 }
 
 static int fine_or_snr(int mode, int fcch_type, const float *iq, int64_t iq_len, const int64_t *win_ofs,

@@ -29,6 +29,8 @@ struct DecodeArgs {
 	const uint8_t *sb_mask;   // rach: [n] or NULL (then sb_mask0 for all)
 	int32_t        sb_mask0;
 	int32_t        tch3_m;    // tch3 multiplexing mode (0 / 1)
+	int32_t        t9_rows;   // tch9: ebits is [n][648] already deciphered / descrambled / inter-burst
+	                          //       de-interleaved (what gmr1_deinterleave_inter returns); no side outputs
 };
 
 // device-resident (or host, in the emulation) tables one channel needs
@@ -65,7 +67,9 @@ template <int CH>
 GMR1_HD int8_t stage_elem(const TabRef &tb, const DecodeArgs &a, int unit, int r)
 {
 	constexpr bool T9 = (CH == CH_TCH9_2K4 || CH == CH_TCH9_4K8 || CH == CH_TCH9_9K6);
-	if (T9) {
+	if (T9 && a.t9_rows) {
+		return a.ebits[(size_t)unit * 648 + r];
+	} else if (T9) {
 		const uint16_t w = tb.t9_src[r];
 		const int age = (w >> 10) & 3, s = w & G_IDX;
 		int u = unit;
@@ -107,7 +111,7 @@ GMR1_HD void decode_unit_k5(const TabRef &tb, const DecodeArgs &a, int unit,
 			for (int j = 0; j < 8; j++)     // facch3.c:141-142 (status bits are not ciphered)
 				a.bits_s[(size_t)unit * 32 + 8 * b + j] = a.ebits[(size_t)unit * 416 + 104 * b + 22 + j] < 0;
 	}
-	if (T9 || F9) {
+	if ((T9 && !a.t9_rows) || F9) {
 		const int8_t *e = a.ebits + (size_t)unit * 662;
 		if (a.status)
 			for (int i = 0; i < 4; i++)     // facch9.c:118

@@ -141,6 +141,24 @@ void interleaver_init(Interleaver *il)
 	memset(il, 0, sizeof(*il));
 }
 
+// conv-encode + puncture + intra-burst interleave(81): the 648 bits that enter the inter-burst interleaver
+void encode_tch9_ep(uint8_t *ep, const uint8_t *l2, int mode)
+{
+	const int ch = CH_TCH9_2K4 + mode;
+	const ChanTab &t = chan_tab(ch);
+	uint8_t u[480], c[MAX_CODED], rx[648];
+	std::vector<uint8_t> keep(MAX_CODED);
+	const int n_coded = chan_keep_mask(ch, keep.data(), MAX_CODED);
+	unpack_lsb(u, l2, 0, t.len);
+	conv_encode_full(ch, u, c);
+	int q = 0;
+	for (int k = 0; k < n_coded; k++)
+		if (keep[k])
+			rx[q++] = c[k];
+	for (int kc = 0; kc < 648; kc++)
+		ep[81 * ((5 * kc) & 7) + (kc >> 3)] = rx[kc];
+}
+
 void encode_tch9(uint8_t *bits_e, const uint8_t *l2, int mode, const uint8_t *sacch, const uint8_t *status,
                  const uint8_t *ciph, Interleaver *il)
 {

@@ -16,6 +16,7 @@ void encode_facch9(uint8_t *bits_e, const uint8_t *l2, const uint8_t *sacch, con
 void interleaver_init(Interleaver *il);
 void encode_tch9(uint8_t *bits_e, const uint8_t *l2, int mode, const uint8_t *sacch, const uint8_t *status,
                  const uint8_t *ciph, Interleaver *il);
+void encode_tch9_ep(uint8_t *ep, const uint8_t *l2, int mode);
 void encode_rach(uint8_t *bits_e, const uint8_t *rach, uint8_t sb_mask);
 void encode_tch3(uint8_t *bits_e, const uint8_t *frame0, const uint8_t *frame1, const uint8_t *bits_s,
                  const uint8_t *ciph, int m);

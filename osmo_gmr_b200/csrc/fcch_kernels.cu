@@ -147,6 +147,13 @@ __global__ void __launch_bounds__(FR_T) fcch_rough_kernel(const FcchArgs a)
 	}
 	__syncthreads();
 
+	if (a.en_out) {        // multi-FCCH: hand the correlation power to the host-side peak bookkeeping
+		float *o = a.en_out + (size_t)b * nc;
+		for (int i = tid; i < nc; i += FR_T)
+			o[i] = en[i];
+		return;
+	}
+
 	// highest-energy window of 5 (osmo_cxvec_peak_energy_find, PEAK_WEIGH_WIN), fcch.c:238
 	const int win = nc < 5 ? nc : 5;
 	float best = 0.0f;

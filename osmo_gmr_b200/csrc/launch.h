@@ -45,6 +45,8 @@ struct FcchArgs {
 	float         *freq_error;             // fine: [n] rad/symbol
 	float         *snr;                    // snr: [n]
 	float         *peak;                   // rough: [n] energy of the winning window, or NULL
+	float         *en_out;                 // rough: if set, [n][win_len/sps - len + 1] |corr|^2 is written and
+	                                       //        the peak search is left to the caller (rough_multi)
 };
 cudaError_t launch_fcch_rough(const FcchArgs &a, cudaStream_t st);
 cudaError_t launch_fcch_fine(const FcchArgs &a, int mode, cudaStream_t st);

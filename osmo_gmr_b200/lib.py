@@ -54,6 +54,9 @@ class Lib:
         "gmr1b200_facch9_decode_batch": [_P, _P, _P, _P, _P, _P, _P, _I, _P],
         "gmr1b200_tch3_decode_batch": [_P, _P, _P, _P, _P, _I, _P, _P, _I, _P],
         "gmr1b200_tch9_decode_batch": [_P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _P],
+        "gmr1b200_tch9_decode_rows_batch": [_P, _P, _I, _P, _I, _P],
+        "gmr1b200_pi4cxpsk_demod_desc_batch": [_P, _P, _L, _P, _L, _I, _I, _P, _F, _P, _I, _P, _P, _P, _P, _I, _P],
+        "gmr1b200_fcch_rough_multi": [_I, _P, _L, _I, _F, _P, _I, _P],
         "gmr1b200_rach_decode_batch": [_P, _P, _P, _I, _P, _P, _P, _I, _P],
         "gmr1b200_xch_dc12_decode_batch": [_P, _P, _P, _P, _I, _P],
         "gmr1b200_xcch_encode_batch": [_I, _P, _P, _I],
