@@ -83,27 +83,26 @@ __device__ __forceinline__ float fast_atan2f(float y, float x)
 }
 
 // Sinc interpolation (osmo_cxvec_interpolate_point, 10 taps either side) of the real vector
-// acc[0..len) at `pos` and, when LATE, also at `pos + 2` (the late gate).  One tap per lane,
-// shuffle-tree sums.  The 21 sinc values of both gates are identical ((i+2)-(pos+2) == i-pos
-// exactly in fp32 here) and share one sine: sin(pi*(j-frac)) = -(-1)^j sin(pi*frac).
+// acc[0..len) at `pos` and, when LATE, also at `pos + 2` (the late gate).  One tap per lane
+// (lane j+10 <-> tap j = -10..10), one folded shuffle tree for both sums.  The 21 sinc values of
+// both gates are identical ((i+2)-(pos+2) == i-pos exactly in fp32 here) and share one sine:
+// sin(pi*(j-frac)) = -(-1)^j sin(pi*frac), looked up on the 1/512 grid the search visits.
+struct TapLane { float xj, sgn; int j; };      // per-lane constants: pi*j, -(-1)^j (0 for lanes >= 21)
+
 template <bool LATE>
-__device__ __forceinline__ void interp(const float *acc, int len, float pos, int lane, float &ev, float &lv)
+__device__ __forceinline__ void interp(const float *acc, int len, float pos, const TapLane &tp, int lane,
+                                       float &ev, float &lv)
 {
 	const float fl = floorf(pos);
-	const int fe = (int)fl;
 	const float frac = pos - fl;                      // exact, a multiple of 1/512
 	const float S = c_sinpi512[(int)(frac * 512.0f)];
-	float te = 0.0f, tl = 0.0f;
-	if (lane < 21) {
-		const int j = lane - 10, k = fe + j;
-		const float x = PI_F * ((float)j - frac);
-		float s = __fdividef((j & 1) ? S : -S, x);
-		s = (x >= 0.01f || x <= -0.01f) ? s : 1.0f;   // osmo_sinc
-		te = (k >= 0 && k < len) ? acc[k] * s : 0.0f;
-		if (LATE)
-			tl = (k + 2 >= 0 && k + 2 < len) ? acc[k + 2] * s : 0.0f;
-	}
+	const float x = fmaf(-PI_F, frac, tp.xj);         // pi*(j - frac)
+	float sv = __fdividef(tp.sgn * S, x);
+	sv = fabsf(x) >= 0.01f ? sv : (tp.sgn != 0.0f ? 1.0f : 0.0f);      // osmo_sinc
+	const int k = (int)fl + tp.j;
+	float te = ((unsigned)k < (unsigned)len) ? acc[k] * sv : 0.0f;
 	if (LATE) {
+		const float tl = ((unsigned)(k + 2) < (unsigned)len) ? acc[k + 2] * sv : 0.0f;
 		// fold both sums into one tree: after the first exchange the lower half-warp carries the
 		// early terms, the upper half the late terms
 		const bool up = lane & 16;
@@ -120,18 +119,15 @@ __device__ __forceinline__ void interp(const float *acc, int len, float pos, int
 
 // osmo_cxvec_peak_energy_find(acc, 3, PEAK_EARLY_LATE, &peak) on a real vector; all lanes
 // return the same position / peak value
-__device__ float peak_early_late(const float *acc, int w, int lane, float &peak_val)
+__device__ float peak_early_late(const float *acc, int w, const TapLane &tp, int lane, float &peak_val)
 {
 	const int win = w < 3 ? w : 3;
 	float best = 0.0f;
 	int best_idx = 0x7fffffff;
 	for (int idx = lane; idx < w; idx += 32) {
-		float val = 0.0f;
-		for (int hi = idx - win + 1; hi <= idx; hi++)
-			if (hi >= 0) {
-				const float a = acc[hi];
-				val += a * a;
-			}
+		const float a0 = acc[idx], a1 = idx >= 1 ? acc[idx - 1] : 0.0f, a2 = (idx >= 2 && win > 2) ? acc[idx - 2] : 0.0f;
+		// oldest sample first, products rounded separately as the C path does (no FMA contraction)
+		const float val = __fadd_rn(__fadd_rn(__fmul_rn(a2, a2), __fmul_rn(a1, a1)), __fmul_rn(a0, a0));
 		if (val > best) {
 			best = val;
 			best_idx = idx;
@@ -162,21 +158,18 @@ __device__ float peak_early_late(const float *acc, int w, int lane, float &peak_
 
 	float early = (float)(mwi - 1), incr = 0.5f;
 #pragma unroll 1
-	while (incr > (1.0f / 1024.0f)) {
+	for (int it = 0; it < 9; it++) {                  // incr = 1/2 .. 1/512 (> 1/1024)
 		float ev, lv;
-		interp<true>(acc, w, early, lane, ev, lv);
+		interp<true>(acc, w, early, tp, lane, ev, lv);
 		const float e2 = ev * ev, l2 = lv * lv;
-		if (e2 < l2)
-			early += incr;
-		else if (e2 > l2)
-			early -= incr;
-		else
+		if (e2 == l2)
 			break;
+		early += e2 < l2 ? incr : -incr;
 		incr *= 0.5f;
 	}
 	const float pos = early + 1.0f;
 	float dummy;
-	interp<false>(acc, w, pos, lane, peak_val, dummy);
+	interp<false>(acc, w, pos, tp, lane, peak_val, dummy);
 	return pos;
 }
 
@@ -185,6 +178,8 @@ struct WarpSmem {
 	float2 *win;     // [L]   raw window (never rewritten)
 	float2 *taps;    // [32]  rotated reference taps of the chunk being correlated
 	float  *accv;    // [w]   correlation magnitude accumulator
+	float2 *zbuf;    // [MAX_TRAIN] derotated training symbols x conj(reference)
+	int     L;
 };
 
 __device__ __forceinline__ WarpSmem carve(uint8_t *base, int L, int w)
@@ -195,12 +190,17 @@ __device__ __forceinline__ WarpSmem carve(uint8_t *base, int L, int w)
 	s.taps = (float2 *)base;
 	base += 32 * 8;
 	s.accv = (float *)base;
+	base += (size_t)((w + 3) & ~3) * 4;
+	s.zbuf = (float2 *)base;
+	s.L = L;
 	return s;
 }
 
+static constexpr int MAX_TRAIN = 104;     // RACH: 17 + 32 + 32 + 17 + 1 = 99 training symbols
+
 static inline size_t warp_smem_bytes(int L, int w)
 {
-	return (size_t)((L + 1) & ~1) * 8 + 32 * 8 + (size_t)((w + 3) & ~3) * 4;
+	return (size_t)((L + 1) & ~1) * 8 + 32 * 8 + (size_t)((w + 3) & ~3) * 4 + MAX_TRAIN * 8;
 }
 
 // window statistics of osmo_cxvec_sig_normalize: mean and 1/stddev.  One pass: the variance is
@@ -208,7 +208,8 @@ static inline size_t warp_smem_bytes(int L, int w)
 // both are fp32 approximations of the same quantity).
 struct Norm { float ar, ai, inv_sd; };
 
-__device__ __forceinline__ Norm load_stats(const float2 *__restrict__ x, int L, float2 *win, int lane, bool want_sd)
+template <bool WANT_SD>
+__device__ __forceinline__ Norm load_stats_t(const float2 *__restrict__ x, int L, float2 *win, int lane)
 {
 	float sr = 0.0f, si = 0.0f, sq = 0.0f;
 	if ((((uintptr_t)x) & 15) == 0) {
@@ -222,7 +223,7 @@ __device__ __forceinline__ Norm load_stats(const float2 *__restrict__ x, int L, 
 			w4[i] = v;
 			sr += v.x + v.z;
 			si += v.y + v.w;
-			if (want_sd) {
+			if (WANT_SD) {
 				sq = fmaf(v.x, v.x, sq);
 				sq = fmaf(v.y, v.y, sq);
 				sq = fmaf(v.z, v.z, sq);
@@ -234,7 +235,8 @@ __device__ __forceinline__ Norm load_stats(const float2 *__restrict__ x, int L, 
 			win[L - 1] = v;
 			sr += v.x;
 			si += v.y;
-			sq += v.x * v.x + v.y * v.y;
+			if (WANT_SD)
+				sq += v.x * v.x + v.y * v.y;
 		}
 	} else {
 #pragma unroll 4
@@ -243,7 +245,8 @@ __device__ __forceinline__ Norm load_stats(const float2 *__restrict__ x, int L, 
 			win[i] = v;
 			sr += v.x;
 			si += v.y;
-			sq += v.x * v.x + v.y * v.y;
+			if (WANT_SD)
+				sq += v.x * v.x + v.y * v.y;
 		}
 	}
 	sr = warp_sum(sr);
@@ -252,10 +255,10 @@ __device__ __forceinline__ Norm load_stats(const float2 *__restrict__ x, int L, 
 	n.ar = sr / (float)L;
 	n.ai = si / (float)L;
 	n.inv_sd = 1.0f;
-	if (want_sd) {
+	if (WANT_SD) {
 		// The scale 1/stddev changes no decision and no soft bit (peak positions, phases and
 		// angles are scale invariant); it only sets the absolute value of the reported sync
-		// power, so the extra pass is skipped unless that output is requested.
+		// power, so the extra work is skipped unless that output is requested.
 		sq = warp_sum(sq);
 		const float var = sq / (float)L - (n.ar * n.ar + n.ai * n.ai);
 		float sd = var > 0.0f ? sqrtf(var) : 0.0f;
@@ -265,6 +268,11 @@ __device__ __forceinline__ Norm load_stats(const float2 *__restrict__ x, int L, 
 	}
 	__syncwarp();
 	return n;
+}
+
+__device__ __forceinline__ Norm load_stats(const float2 *__restrict__ x, int L, float2 *win, int lane, bool want_sd)
+{
+	return want_sd ? load_stats_t<true>(x, L, win, lane) : load_stats_t<false>(x, L, win, lane);
 }
 
 // Search all sync sequences of one burst type (pi4cxpsk.c:184-268) on the RAW window.
@@ -277,7 +285,7 @@ __device__ __forceinline__ Norm load_stats(const float2 *__restrict__ x, int L, 
 // accv is NOT cleared between sequences - the reference clears it once per call (:207) and
 // keeps adding (:232-233); tl restarts per sequence (:216).
 __device__ int sync_find(const BurstTab &bt, const WarpSmem &sm, const Norm &nm, float fs, int sps, int w,
-                         int lane, float &toa, float &pwr)
+                         const TapLane &tpl, int lane, float &toa, float &pwr)
 {
 	for (int m = lane; m < w; m += 32)
 		sm.accv[m] = 0.0f;
@@ -301,27 +309,35 @@ __device__ int sync_find(const BurstTab &bt, const WarpSmem &sm, const Norm &nm,
 			const float Rr = warp_sum(tr), Ri = warp_sum(ti);
 			const float cr0 = nm.ar * Rr - nm.ai * Ri, ci0 = nm.ar * Ri + nm.ai * Rr;   // avg * sum(taps)
 			__syncwarp();
+			// taps beyond cl are zero (lanes >= cl wrote 0), so the tap loop runs in whole groups of 4.
+			// The up to 3 zero taps may read up to 3*sps samples past the window: that lands in this
+			// warp's taps / accv / zbuf area, which only ever holds finite floats (zeroed at start),
+			// and 0 * finite adds nothing.
+			const int cl4 = (cl + 3) & ~3;
 			for (int m = lane; m < w; m += 32) {
 				float cr = 0.0f, ci = 0.0f;
 				const float2 *g = sm.win + b0 + m;
 				const float2 *tp = sm.taps;
-#pragma unroll 4
-				for (int n = 0; n < cl; n++, g += sps, tp++) {
-					const float2 t = *tp, v = *g;
-					cr = fmaf(t.x, v.x, cr);
-					cr = fmaf(-t.y, v.y, cr);
-					ci = fmaf(t.x, v.y, ci);
-					ci = fmaf(t.y, v.x, ci);
+				for (int n = 0; n < cl4; n += 4, tp += 4, g += 4 * sps) {
+#pragma unroll
+					for (int u = 0; u < 4; u++) {
+						const float2 t = tp[u], v = g[u * sps];
+						cr = fmaf(t.x, v.x, cr);
+						cr = fmaf(-t.y, v.y, cr);
+						ci = fmaf(t.x, v.y, ci);
+						ci = fmaf(t.y, v.x, ci);
+					}
 				}
 				cr = (cr - cr0) * nm.inv_sd;
 				ci = (ci - ci0) * nm.inv_sd;
-				sm.accv[m] += sqrtf(cr * cr + ci * ci);
+				const float e = fmaf(cr, cr, ci * ci);
+				sm.accv[m] += e > 0.0f ? e * rsqrtf(e) : 0.0f;
 			}
 			tl += cl;
 		}
 		__syncwarp();
 		float peak;
-		const float s_toa = peak_early_late(sm.accv, w, lane, peak);
+		const float s_toa = peak_early_late(sm.accv, w, tpl, lane, peak);
 		peak /= (float)tl;
 		const float s_pwr = peak * peak;
 		if (s_pwr > p_pwr) {
@@ -336,168 +352,245 @@ __device__ int sync_find(const BurstTab &bt, const WarpSmem &sm, const Norm &nm,
 }
 
 // ---- kernel ---------------------------------------------------------------------------------------
+// Flattened symbol lists of the burst format, built once per CTA in shared memory: the training
+// symbols of every sync sequence (position, reference symbol, chunk) and the data symbols in
+// output order.  One lane per symbol then needs no per-chunk control flow.
+struct FlatTab {
+	uint16_t d_pos[480];
+	uint16_t t_pos[MAX_SYNC][MAX_TRAIN];
+	uint8_t  t_sym[MAX_SYNC][MAX_TRAIN];
+	uint8_t  t_chunk[MAX_SYNC][MAX_TRAIN];
+	int32_t  n_train[MAX_SYNC];
+	int32_t  n_dsym;
+};
+
+__device__ void build_flat(const BurstTab &bt, FlatTab &ft)
+{
+	for (int t = threadIdx.x; t < 480; t += blockDim.x) {
+		int acc = 0, pos = 0;
+		for (int c = 0; c < bt.n_data; c++) {
+			if (t >= acc && t < acc + bt.d_len[c])
+				pos = bt.d_pos[c] + (t - acc);
+			acc += bt.d_len[c];
+		}
+		ft.d_pos[t] = (uint16_t)pos;
+		if (t == 0)
+			ft.n_dsym = acc;
+	}
+	for (int s = 0; s < bt.n_sync; s++)
+		for (int t = threadIdx.x; t < MAX_TRAIN; t += blockDim.x) {
+			int acc = 0, pos = 0, sym = 0, ch = 0;
+			for (int c = 0; c < bt.n_chunk[s]; c++) {
+				const int cl = bt.s_len[s][c];
+				if (t >= acc && t < acc + cl) {
+					pos = bt.s_pos[s][c] + (t - acc);
+					sym = bt.s_sym[s][c][t - acc];
+					ch = c;
+				}
+				acc += cl;
+			}
+			ft.t_pos[s][t] = (uint16_t)pos;
+			ft.t_sym[s][t] = (uint8_t)sym;
+			ft.t_chunk[s][t] = (uint8_t)ch;
+			if (t == 0)
+				ft.n_train[s] = acc;
+		}
+}
+
+// folded shuffle tree for a (re, im) pair: returns both sums in all lanes
+__device__ __forceinline__ float2 warp_sum2(float a, float b, int lane)
+{
+	const bool up = lane & 16;
+	float v = (up ? b : a) + __shfl_xor_sync(0xffffffffu, up ? a : b, 16);
+#pragma unroll
+	for (int o = 8; o; o >>= 1)
+		v += __shfl_xor_sync(0xffffffffu, v, o);
+	return make_float2(__shfl_sync(0xffffffffu, v, 0), __shfl_sync(0xffffffffu, v, 16));
+}
+
 // mode 0: demod (bts[0] only).  mode 1: detect among n_bt burst types (pi4cxpsk.c:617-682).
-__global__ void __launch_bounds__(DM_WARPS * 32)
+// Persistent: each warp strides over the bursts of the batch.
+__global__ void __launch_bounds__(DM_WARPS * 32, 6)
 demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int mode, int warp_bytes)
 {
 	extern __shared__ __align__(16) uint8_t smem[];
+	__shared__ FlatTab ft;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int b = blockIdx.x * DM_WARPS + warp;
-	if (b >= a.n)
-		return;
-
 	const BurstTab &bt = bts[0];
 	const int sps = a.sps, L = a.win_len;
 	const int w = L - bt.len * sps + 1;
 	const WarpSmem sm = carve(smem + (size_t)warp * warp_bytes, L, w);
 
-	const float2 *x = a.iq + (a.ofs ? a.ofs[b] : (int64_t)b * a.stride);
-	const float freq_shift = a.freq_shift ? a.freq_shift[b] : a.freq_shift0;
-	const float fs = (freq_shift - bt.rotation) / (float)sps;
+	if (mode == 0)
+		build_flat(bt, ft);
+	// the area behind the window must only ever hold finite values (see sync_find)
+	for (int i = lane; i < 32; i += 32)
+		sm.taps[i] = make_float2(0.0f, 0.0f);
+	for (int i = lane; i < ((w + 3) & ~3); i += 32)
+		sm.accv[i] = 0.0f;
+	for (int i = lane; i < MAX_TRAIN; i += 32)
+		sm.zbuf[i] = make_float2(0.0f, 0.0f);
+	__syncthreads();
 
-	const Norm nm = load_stats(x, L, sm.win, lane, a.pwr != nullptr || (mode == 1 && (a.e_toa != nullptr || a.e_toa0 >= 0.0f)));
+	TapLane tpl;
+	tpl.j = lane - 10;
+	tpl.xj = PI_F * (float)(lane - 10);
+	tpl.sgn = lane < 21 ? (((lane - 10) & 1) ? 1.0f : -1.0f) : 0.0f;
 
-	if (mode == 1) {
-		const float e_toa = a.e_toa ? a.e_toa[b] : a.e_toa0;
-		int p_id = -1, p_sid = -1;
-		float p_toa = 0.0f, p_pwr = 0.0f;
-		for (int id = 0; id < n_bt; id++) {
-			float toa, pwr;
-			const int sid = sync_find(bts[id], sm, nm, fs, sps, w, lane, toa, pwr);
-			if (e_toa >= 0.0f)     // the reference divides by fabs() in double (pi4cxpsk.c:658-659)
-				pwr = (float)((double)pwr / fabs((double)(e_toa - toa)));
-			if (pwr > p_pwr) {
-				p_id = id;
-				p_sid = sid;
-				p_pwr = pwr;
-				p_toa = toa;
+	const bool want_sd = a.pwr != nullptr || (mode == 1 && (a.e_toa != nullptr || a.e_toa0 >= 0.0f));
+	const int nbits = bt.nbits, mask = (1 << nbits) - 1;
+	const double inv_dd = (double)(1 << nbits) / (2.0 * 3.14159265358979323846);
+	const double period = (double)(1 << nbits), inv_period = 1.0 / period;
+
+	for (int b = blockIdx.x * DM_WARPS + warp; b < a.n; b += gridDim.x * DM_WARPS) {
+		const float2 *x = a.iq + (a.ofs ? a.ofs[b] : (int64_t)b * a.stride);
+		const float freq_shift = a.freq_shift ? a.freq_shift[b] : a.freq_shift0;
+		const float fs = (freq_shift - bt.rotation) / (float)sps;
+
+		__syncwarp();
+		const Norm nm = load_stats(x, L, sm.win, lane, want_sd);
+
+		if (mode == 1) {
+			const float e_toa = a.e_toa ? a.e_toa[b] : a.e_toa0;
+			int p_id = -1, p_sid = -1;
+			float p_toa = 0.0f, p_pwr = 0.0f;
+			for (int id = 0; id < n_bt; id++) {
+				float toa, pwr;
+				const int sid = sync_find(bts[id], sm, nm, fs, sps, w, tpl, lane, toa, pwr);
+				if (e_toa >= 0.0f)     // the reference divides by fabs() in double (pi4cxpsk.c:658-659)
+					pwr = (float)((double)pwr / fabs((double)(e_toa - toa)));
+				if (pwr > p_pwr) {
+					p_id = id;
+					p_sid = sid;
+					p_pwr = pwr;
+					p_toa = toa;
+				}
 			}
+			if (lane == 0) {
+				if (a.bt_id) a.bt_id[b] = p_id;
+				if (a.sync_id) a.sync_id[b] = p_sid;
+				if (a.toa) a.toa[b] = p_toa;
+				if (a.pwr) a.pwr[b] = p_pwr;
+			}
+			continue;
 		}
+
+		float toa, pwr;
+		const int sync_id = sync_find(bt, sm, nm, fs, sps, w, tpl, lane, toa, pwr);
 		if (lane == 0) {
-			if (a.bt_id) a.bt_id[b] = p_id;
-			if (a.sync_id) a.sync_id[b] = p_sid;
-			if (a.toa) a.toa[b] = p_toa;
-			if (a.pwr) a.pwr[b] = p_pwr;
+			if (a.sync_id) a.sync_id[b] = sync_id;
+			if (a.toa) a.toa[b] = toa;
+			if (a.pwr) a.pwr[b] = pwr;
 		}
-		return;
-	}
+		int8_t *eb = a.ebits + (size_t)b * a.ebits_stride;
+		if (sync_id < 0) {          // nothing correlated (all-zero input): the reference returns -errno
+			if (lane == 0 && a.freq_err) a.freq_err[b] = 0.0f;
+			for (int k = lane; k < bt.ebits; k += 32)
+				eb[k] = 0;
+			continue;
+		}
 
-	float toa, pwr;
-	const int sync_id = sync_find(bt, sm, nm, fs, sps, w, lane, toa, pwr);
-	if (lane == 0) {
-		if (a.sync_id) a.sync_id[b] = sync_id;
-		if (a.toa) a.toa[b] = toa;
-		if (a.pwr) a.pwr[b] = pwr;
-	}
-	int8_t *eb = a.ebits + (size_t)b * a.ebits_stride;
-	if (sync_id < 0) {          // nothing correlated (all-zero input): the reference returns -errno
-		if (lane == 0 && a.freq_err) a.freq_err[b] = 0.0f;
-		for (int k = lane; k < bt.ebits; k += 32)
-			eb[k] = 0;
-		return;
-	}
+		// symbol i sits at sample i*sps + d (sps >= 4 path of _gmr1_pi4cxpsk_align, :286-297)
+		const int d = (int)roundf(toa);
+		auto sample_of = [&](int i) {
+			const int q = i * sps + d;     // d >= -1; index -1 would read before the window: clamp
+			return min(max(q, 0), L - 1);
+		};
 
-	// symbol i sits at sample i*sps + d (sps >= 4 path of _gmr1_pi4cxpsk_align, :286-297)
-	const int d = (int)roundf(toa);
-	auto sample_of = [&](int i) {
-		const int q = i * sps + d;     // d >= -1; index -1 would read before the window: clamp
-		return min(max(q, 0), L - 1);
-	};
-
-	// ---- training symbols (<= 32 per chunk, one per lane), derotated as the reference derotates
-	//      every sample: z = (x - avg)/sd * e^{j*fl32(fs*idx)}.  Per chunk: correlation sum ->
-	//      fine frequency error from the chunk-to-chunk phase slope (:360-406).  The derotated
-	//      products are kept in registers (chunk c -> zr[c], zi[c]) for the phase reference.
-	const int nch = bt.n_chunk[sync_id];
-	float zr[MAX_SYNC_CHUNK], zi[MAX_SYNC_CHUNK];
-	float ferr = 0.0f, f = 0.0f, prev_r = 0.0f, prev_i = 0.0f, prev_pos = 0.0f;
+		// ---- training symbols, one per lane, derotated as the reference derotates every sample:
+		//      z = (x - avg)/sd * e^{j*fl32(fs*idx)}, times conj(reference symbol).  Per-chunk sums ->
+		//      fine frequency error from the chunk-to-chunk phase slope (:360-406).
+		const int nch = bt.n_chunk[sync_id], ntr = ft.n_train[sync_id];
+		float cr[MAX_SYNC_CHUNK], ci[MAX_SYNC_CHUNK];
 #pragma unroll
-	for (int c = 0; c < MAX_SYNC_CHUNK; c++) {
-		zr[c] = zi[c] = 0.0f;
-		if (c < nch) {
-			const int p0 = bt.s_pos[sync_id][c], cl = bt.s_len[sync_id][c];
-			if (lane < cl) {
-				const int q = sample_of(p0 + lane);
+		for (int c = 0; c < MAX_SYNC_CHUNK; c++)
+			cr[c] = ci[c] = 0.0f;
+		for (int t0 = 0; t0 < ntr; t0 += 32) {
+			const int t = t0 + lane;
+			if (t < ntr) {
+				const int pos = ft.t_pos[sync_id][t], q = sample_of(pos), ch = ft.t_chunk[sync_id][t];
 				const float2 v = sm.win[q];
 				float sn, cs;
 				sincosf(fs * (float)q, &sn, &cs);
 				const float yr = (v.x - nm.ar) * nm.inv_sd, yi = (v.y - nm.ai) * nm.inv_sd;
-				const float2 p = mul_conj_sym(bt.s_sym[sync_id][c][lane],
-				                              make_float2(yr * cs - yi * sn, yr * sn + yi * cs));
-				zr[c] = p.x;
-				zi[c] = p.y;
-			}
-			if (nch > 1) {
-				const float cr = warp_sum(zr[c]), ci = warp_sum(zi[c]);
-				const float pos = (float)p0 + (float)cl / 2.0f;
-				if (c > 0) {   // arg(corr[c] * conj(corr[c-1])) / (pos[c] - pos[c-1])
-					const float re = cr * prev_r + ci * prev_i, im = ci * prev_r - cr * prev_i;
-					f += fast_atan2f(im, re) / (pos - prev_pos);
-				}
-				prev_r = cr;
-				prev_i = ci;
-				prev_pos = pos;
-			}
-		}
-	}
-	if (nch > 1)
-		ferr = f / (float)(nch - 1);
-	if (lane == 0 && a.freq_err) a.freq_err[b] = ferr;
-
-	// ---- phase reference: all training symbols after the -ferr rotation (:415-433, :574)
-	float phi0;
-	{
-		float pr = 0.0f, pi = 0.0f;
+				const float2 z = mul_conj_sym(ft.t_sym[sync_id][t], make_float2(yr * cs - yi * sn, yr * sn + yi * cs));
+				sm.zbuf[t] = z;
 #pragma unroll
-		for (int c = 0; c < MAX_SYNC_CHUNK; c++) {
-			if (c < nch) {
-				float r = zr[c], i_ = zi[c];
-				if (ferr != 0.0f) {
-					float sn, cs;
-					sincosf((-ferr) * (float)(bt.s_pos[sync_id][c] + lane), &sn, &cs);
-					const float t = r * cs - i_ * sn;
-					i_ = r * sn + i_ * cs;
-					r = t;
-				}
-				pr += r;
-				pi += i_;
+				for (int c = 0; c < MAX_SYNC_CHUNK; c++)
+					if (ch == c) {
+						cr[c] += z.x;
+						ci[c] += z.y;
+					}
 			}
 		}
-		pr = warp_sum(pr);
-		pi = warp_sum(pi);
-		phi0 = fast_atan2f(pi, pr);
-	}
+		float ferr = 0.0f;
+		if (nch > 1) {
+			float f = 0.0f, prev_r = 0.0f, prev_i = 0.0f, prev_pos = 0.0f;
+#pragma unroll
+			for (int c = 0; c < MAX_SYNC_CHUNK; c++)
+				if (c < nch) {
+					const float2 sum = warp_sum2(cr[c], ci[c], lane);
+					const float pos = (float)bt.s_pos[sync_id][c] + (float)bt.s_len[sync_id][c] / 2.0f;
+					if (c > 0) {   // arg(corr[c] * conj(corr[c-1])) / (pos[c] - pos[c-1])
+						const float re = sum.x * prev_r + sum.y * prev_i, im = sum.y * prev_r - sum.x * prev_i;
+						f += fast_atan2f(im, re) / (pos - prev_pos);
+					}
+					prev_r = sum.x;
+					prev_i = sum.y;
+					prev_pos = pos;
+				}
+			ferr = f / (float)(nch - 1);
+		}
+		if (lane == 0 && a.freq_err) a.freq_err[b] = ferr;
 
-	// ---- data symbols in the angle domain.  The reference rotates each sample three times
-	// (e^{j*fs*idx}, e^{-j*ferr*i}, conj(phasor)) and takes cargf(); the argument of that product
-	// is  arg(x - avg) + fl32(fs*idx) + fl32(-ferr*i) - arg(phasor)  (mod 2*pi), accumulated here
-	// in double so that the only float rounding left is the atan2 of the raw sample.
-	const int nbits = bt.nbits, mask = (1 << nbits) - 1;
-	const double inv_dd = (double)(1 << nbits) / (2.0 * 3.14159265358979323846);
-	const double period = (double)(1 << nbits), inv_period = 1.0 / period;
-	const double c0 = -(double)phi0 * inv_dd;
-	int kbase = 0;
-	for (int c = 0; c < bt.n_data; c++) {
-		const int p0 = bt.d_pos[c], cl = bt.d_len[c];
-		for (int j = lane; j < cl; j += 32) {
-			const int i = p0 + j, q = sample_of(i);
+		// ---- phase reference: all training symbols after the -ferr rotation (:415-433, :574)
+		float phi0;
+		{
+			float pr = 0.0f, pi = 0.0f;
+			__syncwarp();
+			for (int t0 = 0; t0 < ntr; t0 += 32) {
+				const int t = t0 + lane;
+				if (t < ntr) {
+					float2 z = sm.zbuf[t];
+					if (ferr != 0.0f) {
+						float sn, cs;
+						sincosf((-ferr) * (float)ft.t_pos[sync_id][t], &sn, &cs);
+						z = make_float2(z.x * cs - z.y * sn, z.x * sn + z.y * cs);
+					}
+					pr += z.x;
+					pi += z.y;
+				}
+			}
+			const float2 sum = warp_sum2(pr, pi, lane);
+			phi0 = fast_atan2f(sum.y, sum.x);
+		}
+
+		// ---- data symbols in the angle domain, one per lane in output order.  The reference rotates
+		// each sample three times (e^{j*fs*idx}, e^{-j*ferr*i}, conj(phasor)) and takes cargf(); the
+		// argument of that product is  arg(x - avg) + fl32(fs*idx) + fl32(-ferr*i) - arg(phasor)
+		// (mod 2*pi), accumulated here in double so that the only float rounding left is the atan2 of
+		// the raw sample.
+		const double c0 = -(double)phi0 * inv_dd;
+		const int nds = ft.n_dsym;
+		for (int t = lane; t < nds; t += 32) {
+			const int i = ft.d_pos[t], q = sample_of(i);
 			const float2 v = sm.win[q];
 			const float th = fast_atan2f(v.y - nm.ai, v.x - nm.ar);
 			const float a1 = fs * (float)q;
-			const float a2 = ferr != 0.0f ? (-ferr) * (float)i : 0.0f;
+			const float a2 = (-ferr) * (float)i;
 			double svd = fma((double)th + (double)a1 + (double)a2, inv_dd, c0);
 			svd -= period * rint(svd * inv_period);        // -> [-period/2, period/2]
 			const float sv = (float)svd;
-			const float svr = roundf(sv);
+			const float svr = rintf(sv);                   // (ties differ from roundf only on exact .5)
 			const int sp = (int)svr & mask;
 			const int ss = (svr > sv ? (sp - 1) : (sp + 1)) & mask;
-			const int dq = (int)roundf((2.0f * fabsf(svr - sv)) * 64.0f);
+			const int dq = __float2int_rn(128.0f * fabsf(svr - sv));
 			if (nbits == 2) {
 				// Gray map of the symbol index {00, 01, 11, 10}, MSB first
 				const int gp = sp ^ (sp >> 1), gx = gp ^ ss ^ (ss >> 1);
 				const int v0 = 127 - ((gx & 2) ? dq : (dq >> 1)), v1 = 127 - ((gx & 1) ? dq : (dq >> 1));
 				const int b0 = (gp & 2) ? -v0 : v0, b1 = (gp & 1) ? -v1 : v1;
-				int8_t *o = eb + kbase + 2 * j;
+				int8_t *o = eb + 2 * t;
 				if ((((uintptr_t)o) & 1) == 0)
 					*reinterpret_cast<uint16_t *>(o) = (uint16_t)((b0 & 0xff) | ((b1 & 0xff) << 8));
 				else {
@@ -506,10 +599,9 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 				}
 			} else {
 				const int v0 = 127 - (((sp ^ ss) & 1) ? dq : (dq >> 1));
-				eb[kbase + j] = (int8_t)(sp ? -v0 : v0);
+				eb[t] = (int8_t)(sp ? -v0 : v0);
 			}
 		}
-		kbase += cl * nbits;
 	}
 }
 
@@ -554,7 +646,21 @@ cudaError_t launch_demod(const DemodArgs &a, const BurstTab *d_bts, const BurstT
 		if (dev < 64)
 			attr_set[dev] = smem;
 	}
-	demod_kernel<<<(a.n + DM_WARPS - 1) / DM_WARPS, DM_WARPS * 32, smem, st>>>(a, d_bts, n_bt, mode, (int)wb);
+	// persistent warps: enough CTAs to fill the machine at the occupancy shared memory allows
+	static int n_sm[64] = {0};
+	if (dev >= 64 || !n_sm[dev]) {
+		int v = 148;
+		cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+		if (dev < 64)
+			n_sm[dev] = v;
+	}
+	const int sms = dev < 64 ? n_sm[dev] : 148;
+	int per_sm = (int)((227 * 1024) / (smem + sizeof(FlatTab) + 1024));
+	per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+	int grid = (a.n + DM_WARPS - 1) / DM_WARPS;
+	if (grid > sms * per_sm)
+		grid = sms * per_sm;
+	demod_kernel<<<grid, DM_WARPS * 32, smem, st>>>(a, d_bts, n_bt, mode, (int)wb);
 	return cudaGetLastError();
 }
 
