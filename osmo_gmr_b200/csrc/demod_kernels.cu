@@ -32,6 +32,7 @@
 // after stage 3.  Integer stages (stage 3) are bit-exact.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <string.h>
 
 #include "gmr1_tables.h"
 #include "launch.h"
@@ -173,34 +174,43 @@ __device__ float peak_early_late(const float *acc, int w, const TapLane &tp, int
 	return pos;
 }
 
+// Correlation regions: the only samples that are read more than once are those the training-
+// sequence search touches (chunk position .. + (len-1)*sps + search offsets).  They are the union of
+// a few short intervals (~300 of the 1016 samples of a BCCH window) and are the only part of the
+// window kept in shared memory, which is what lets 32 warps share an SM.  Symbol samples are read
+// once each, straight from global memory (L2 hits: the warp streamed the window moments before).
+static constexpr int MAX_REGIONS = 8;
+struct Regions {
+	int32_t n, total;                       // number of regions, samples in all of them
+	int32_t start[MAX_REGIONS], len[MAX_REGIONS], off[MAX_REGIONS];   // window sample, length, smem offset
+};
+
 // per-warp shared-memory slice
 struct WarpSmem {
-	float2 *win;     // [L]   raw window (never rewritten)
+	float2 *reg;     // [regions.total] raw samples of the correlation regions
 	float2 *taps;    // [32]  rotated reference taps of the chunk being correlated
 	float  *accv;    // [w]   correlation magnitude accumulator
 	float2 *zbuf;    // [MAX_TRAIN] derotated training symbols x conj(reference)
-	int     L;
 };
 
-__device__ __forceinline__ WarpSmem carve(uint8_t *base, int L, int w)
+static constexpr int MAX_TRAIN = 104;     // RACH: 17 + 32 + 32 + 17 + 1 = 99 training symbols
+
+__device__ __forceinline__ WarpSmem carve(uint8_t *base, int nreg, int w)
 {
 	WarpSmem s;
-	s.win = (float2 *)base;
-	base += (size_t)((L + 1) & ~1) * 8;
+	s.reg = (float2 *)base;
+	base += (size_t)((nreg + 1) & ~1) * 8;
 	s.taps = (float2 *)base;
 	base += 32 * 8;
 	s.accv = (float *)base;
 	base += (size_t)((w + 3) & ~3) * 4;
 	s.zbuf = (float2 *)base;
-	s.L = L;
 	return s;
 }
 
-static constexpr int MAX_TRAIN = 104;     // RACH: 17 + 32 + 32 + 17 + 1 = 99 training symbols
-
-static inline size_t warp_smem_bytes(int L, int w)
+static inline size_t warp_smem_bytes(int nreg, int w)
 {
-	return (size_t)((L + 1) & ~1) * 8 + 32 * 8 + (size_t)((w + 3) & ~3) * 4 + MAX_TRAIN * 8;
+	return (size_t)((nreg + 1) & ~1) * 8 + 32 * 8 + (size_t)((w + 3) & ~3) * 4 + MAX_TRAIN * 8;
 }
 
 // window statistics of osmo_cxvec_sig_normalize: mean and 1/stddev.  One pass: the variance is
@@ -209,18 +219,16 @@ static inline size_t warp_smem_bytes(int L, int w)
 struct Norm { float ar, ai, inv_sd; };
 
 template <bool WANT_SD>
-__device__ __forceinline__ Norm load_stats_t(const float2 *__restrict__ x, int L, float2 *win, int lane)
+__device__ __forceinline__ Norm load_stats_t(const float2 *__restrict__ x, int L, int lane)
 {
 	float sr = 0.0f, si = 0.0f, sq = 0.0f;
 	if ((((uintptr_t)x) & 15) == 0) {
 		// 16-byte aligned window: two samples per lane per load
 		const float4 *x4 = reinterpret_cast<const float4 *>(x);
-		float4 *w4 = reinterpret_cast<float4 *>(win);
 		const int L2 = L >> 1;
-#pragma unroll 4
+#pragma unroll 8
 		for (int i = lane; i < L2; i += 32) {
 			const float4 v = __ldg(&x4[i]);
-			w4[i] = v;
 			sr += v.x + v.z;
 			si += v.y + v.w;
 			if (WANT_SD) {
@@ -232,17 +240,15 @@ __device__ __forceinline__ Norm load_stats_t(const float2 *__restrict__ x, int L
 		}
 		if ((L & 1) && lane == 0) {
 			const float2 v = __ldg(&x[L - 1]);
-			win[L - 1] = v;
 			sr += v.x;
 			si += v.y;
 			if (WANT_SD)
 				sq += v.x * v.x + v.y * v.y;
 		}
 	} else {
-#pragma unroll 4
+#pragma unroll 8
 		for (int i = lane; i < L; i += 32) {
 			const float2 v = __ldg(&x[i]);
-			win[i] = v;
 			sr += v.x;
 			si += v.y;
 			if (WANT_SD)
@@ -266,13 +272,25 @@ __device__ __forceinline__ Norm load_stats_t(const float2 *__restrict__ x, int L
 			sd = 1.0f;
 		n.inv_sd = 1.0f / sd;
 	}
-	__syncwarp();
 	return n;
 }
 
-__device__ __forceinline__ Norm load_stats(const float2 *__restrict__ x, int L, float2 *win, int lane, bool want_sd)
+__device__ __forceinline__ Norm load_stats(const float2 *__restrict__ x, int L, int lane, bool want_sd)
 {
-	return want_sd ? load_stats_t<true>(x, L, win, lane) : load_stats_t<false>(x, L, win, lane);
+	return want_sd ? load_stats_t<true>(x, L, lane) : load_stats_t<false>(x, L, lane);
+}
+
+// copy the correlation regions of this window into the warp's shared memory
+__device__ __forceinline__ void load_regions(const float2 *__restrict__ x, const Regions &rg, float2 *reg, int lane)
+{
+	for (int r = 0; r < rg.n; r++) {
+		const float2 *src = x + rg.start[r];
+		float2 *dst = reg + rg.off[r];
+#pragma unroll 4
+		for (int i = lane; i < rg.len[r]; i += 32)
+			dst[i] = __ldg(&src[i]);
+	}
+	__syncwarp();
 }
 
 // Search all sync sequences of one burst type (pi4cxpsk.c:184-268) on the RAW window.
@@ -284,8 +302,8 @@ __device__ __forceinline__ Norm load_stats(const float2 *__restrict__ x, int L, 
 // t_n = conj(ref_n) e^{j*fs*sps*n}.  Same quantity, 60x fewer sincos.
 // accv is NOT cleared between sequences - the reference clears it once per call (:207) and
 // keeps adding (:232-233); tl restarts per sequence (:216).
-__device__ int sync_find(const BurstTab &bt, const WarpSmem &sm, const Norm &nm, float fs, int sps, int w,
-                         const TapLane &tpl, int lane, float &toa, float &pwr)
+__device__ int sync_find(const BurstTab &bt, const WarpSmem &sm, const Regions &rg, const Norm &nm, float fs, int sps,
+                         int w, const TapLane &tpl, int lane, float &toa, float &pwr)
 {
 	for (int m = lane; m < w; m += 32)
 		sm.accv[m] = 0.0f;
@@ -310,13 +328,17 @@ __device__ int sync_find(const BurstTab &bt, const WarpSmem &sm, const Norm &nm,
 			const float cr0 = nm.ar * Rr - nm.ai * Ri, ci0 = nm.ar * Ri + nm.ai * Rr;   // avg * sum(taps)
 			__syncwarp();
 			// taps beyond cl are zero (lanes >= cl wrote 0), so the tap loop runs in whole groups of 4.
-			// The up to 3 zero taps may read up to 3*sps samples past the window: that lands in this
-			// warp's taps / accv / zbuf area, which only ever holds finite floats (zeroed at start),
-			// and 0 * finite adds nothing.
+			// The up to 3 zero taps may read up to 3*sps samples past their region: that lands in this
+			// warp's other regions / taps / accv / zbuf, which only ever hold finite floats, and
+			// 0 * finite adds nothing.
 			const int cl4 = (cl + 3) & ~3;
+			int roff = 0;
+			for (int r = 0; r < rg.n; r++)
+				if (b0 >= rg.start[r] && b0 < rg.start[r] + rg.len[r])
+					roff = rg.off[r] + (b0 - rg.start[r]);
 			for (int m = lane; m < w; m += 32) {
 				float cr = 0.0f, ci = 0.0f;
-				const float2 *g = sm.win + b0 + m;
+				const float2 *g = sm.reg + roff + m;
 				const float2 *tp = sm.taps;
 				for (int n = 0; n < cl4; n += 4, tp += 4, g += 4 * sps) {
 #pragma unroll
@@ -410,8 +432,9 @@ __device__ __forceinline__ float2 warp_sum2(float a, float b, int lane)
 
 // mode 0: demod (bts[0] only).  mode 1: detect among n_bt burst types (pi4cxpsk.c:617-682).
 // Persistent: each warp strides over the bursts of the batch.
-__global__ void __launch_bounds__(DM_WARPS * 32, 6)
-demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int mode, int warp_bytes)
+__global__ void __launch_bounds__(DM_WARPS * 32, 8)
+demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int mode, int warp_bytes,
+             const __grid_constant__ Regions rg)
 {
 	extern __shared__ __align__(16) uint8_t smem[];
 	__shared__ FlatTab ft;
@@ -419,11 +442,13 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 	const BurstTab &bt = bts[0];
 	const int sps = a.sps, L = a.win_len;
 	const int w = L - bt.len * sps + 1;
-	const WarpSmem sm = carve(smem + (size_t)warp * warp_bytes, L, w);
+	const WarpSmem sm = carve(smem + (size_t)warp * warp_bytes, rg.total, w);
 
 	if (mode == 0)
 		build_flat(bt, ft);
 	// the area behind the window must only ever hold finite values (see sync_find)
+	for (int i = lane; i < ((rg.total + 1) & ~1); i += 32)
+		sm.reg[i] = make_float2(0.0f, 0.0f);
 	for (int i = lane; i < 32; i += 32)
 		sm.taps[i] = make_float2(0.0f, 0.0f);
 	for (int i = lane; i < ((w + 3) & ~3); i += 32)
@@ -448,7 +473,8 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 		const float fs = (freq_shift - bt.rotation) / (float)sps;
 
 		__syncwarp();
-		const Norm nm = load_stats(x, L, sm.win, lane, want_sd);
+		const Norm nm = load_stats(x, L, lane, want_sd);
+		load_regions(x, rg, sm.reg, lane);
 
 		if (mode == 1) {
 			const float e_toa = a.e_toa ? a.e_toa[b] : a.e_toa0;
@@ -456,7 +482,7 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 			float p_toa = 0.0f, p_pwr = 0.0f;
 			for (int id = 0; id < n_bt; id++) {
 				float toa, pwr;
-				const int sid = sync_find(bts[id], sm, nm, fs, sps, w, tpl, lane, toa, pwr);
+				const int sid = sync_find(bts[id], sm, rg, nm, fs, sps, w, tpl, lane, toa, pwr);
 				if (e_toa >= 0.0f)     // the reference divides by fabs() in double (pi4cxpsk.c:658-659)
 					pwr = (float)((double)pwr / fabs((double)(e_toa - toa)));
 				if (pwr > p_pwr) {
@@ -476,7 +502,7 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 		}
 
 		float toa, pwr;
-		const int sync_id = sync_find(bt, sm, nm, fs, sps, w, tpl, lane, toa, pwr);
+		const int sync_id = sync_find(bt, sm, rg, nm, fs, sps, w, tpl, lane, toa, pwr);
 		if (lane == 0) {
 			if (a.sync_id) a.sync_id[b] = sync_id;
 			if (a.toa) a.toa[b] = toa;
@@ -509,7 +535,7 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 			const int t = t0 + lane;
 			if (t < ntr) {
 				const int pos = ft.t_pos[sync_id][t], q = sample_of(pos), ch = ft.t_chunk[sync_id][t];
-				const float2 v = sm.win[q];
+				const float2 v = __ldg(&x[q]);
 				float sn, cs;
 				sincosf(fs * (float)q, &sn, &cs);
 				const float yr = (v.x - nm.ar) * nm.inv_sd, yi = (v.y - nm.ai) * nm.inv_sd;
@@ -574,7 +600,7 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 		const int nds = ft.n_dsym;
 		for (int t = lane; t < nds; t += 32) {
 			const int i = ft.d_pos[t], q = sample_of(i);
-			const float2 v = sm.win[q];
+			const float2 v = __ldg(&x[q]);
 			const float th = fast_atan2f(v.y - nm.ai, v.x - nm.ar);
 			const float a1 = fs * (float)q;
 			const float a2 = (-ferr) * (float)i;
@@ -621,7 +647,44 @@ cudaError_t launch_demod(const DemodArgs &a, const BurstTab *d_bts, const BurstT
 	const int w = a.win_len - maxlen * a.sps + 1;
 	if (w < 1 || a.sps < 4 || a.sps > 16)
 		return cudaErrorInvalidValue;
-	const size_t wb = (warp_smem_bytes(a.win_len, w) + 15) & ~(size_t)15;
+	// union of the intervals the training-sequence search reads, over all types / sequences / chunks
+	Regions rg;
+	memset(&rg, 0, sizeof(rg));
+	{
+		struct Iv { int lo, hi; } iv[64];
+		int ni = 0;
+		for (int i = 0; i < n_bt; i++)
+			for (int s = 0; s < h_bts[i].n_sync; s++)
+				for (int c = 0; c < h_bts[i].n_chunk[s]; c++) {
+					int lo = h_bts[i].s_pos[s][c] * a.sps;
+					int hi = lo + (h_bts[i].s_len[s][c] - 1 + 3) * a.sps + w;     // + 3 zero-padded taps
+					hi = hi > a.win_len ? a.win_len : hi;
+					if (ni < 64 && lo < hi)
+						iv[ni++] = {lo, hi};
+				}
+		for (int i = 1; i < ni; i++)                      // insertion sort by start
+			for (int j = i; j > 0 && iv[j].lo < iv[j - 1].lo; j--) {
+				Iv t = iv[j]; iv[j] = iv[j - 1]; iv[j - 1] = t;
+			}
+		for (int i = 0; i < ni; i++) {
+			if (rg.n && iv[i].lo <= rg.start[rg.n - 1] + rg.len[rg.n - 1]) {
+				const int hi = rg.start[rg.n - 1] + rg.len[rg.n - 1];
+				if (iv[i].hi > hi)
+					rg.len[rg.n - 1] = iv[i].hi - rg.start[rg.n - 1];
+			} else {
+				if (rg.n == MAX_REGIONS)
+					return cudaErrorInvalidValue;
+				rg.start[rg.n] = iv[i].lo;
+				rg.len[rg.n] = iv[i].hi - iv[i].lo;
+				rg.n++;
+			}
+		}
+		for (int r = 0; r < rg.n; r++) {
+			rg.off[r] = rg.total;
+			rg.total += (rg.len[r] + 1) & ~1;
+		}
+	}
+	const size_t wb = (warp_smem_bytes(rg.total, w) + 15) & ~(size_t)15;
 	const size_t smem = wb * DM_WARPS;
 	if (smem > 227 * 1024)
 		return cudaErrorInvalidValue;
@@ -660,7 +723,7 @@ cudaError_t launch_demod(const DemodArgs &a, const BurstTab *d_bts, const BurstT
 	int grid = (a.n + DM_WARPS - 1) / DM_WARPS;
 	if (grid > sms * per_sm)
 		grid = sms * per_sm;
-	demod_kernel<<<grid, DM_WARPS * 32, smem, st>>>(a, d_bts, n_bt, mode, (int)wb);
+	demod_kernel<<<grid, DM_WARPS * 32, smem, st>>>(a, d_bts, n_bt, mode, (int)wb, rg);
 	return cudaGetLastError();
 }
 
