@@ -32,6 +32,7 @@
 // after stage 3.  Integer stages (stage 3) are bit-exact.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "gmr1_tables.h"
@@ -54,6 +55,15 @@ __device__ __forceinline__ float warp_sum(float v)
 	return v;
 }
 
+// One out-of-line copy of the accurate sincosf (its large-argument slow path is ~150 instructions;
+// inlined at every call site it pushed the kernel past the instruction cache).
+__device__ __noinline__ float2 sincos_acc(float x)
+{
+	float sn, cs;
+	sincosf(x, &sn, &cs);
+	return make_float2(cs, sn);
+}
+
 // conj(ref) * g for ref in {1, j, -1, -j} (symbol index 0..3): exact component shuffles
 __device__ __forceinline__ float2 mul_conj_sym(int sym, float2 g)
 {
@@ -62,7 +72,7 @@ __device__ __forceinline__ float2 mul_conj_sym(int sym, float2 g)
 }
 
 // atan2f with ~1e-7 rad absolute error: octant reduction + degree-8 minimax polynomial in a^2
-__device__ __forceinline__ float fast_atan2f(float y, float x)
+__device__ __noinline__ float fast_atan2f(float y, float x)
 {
 	const float ax = fabsf(x), ay = fabsf(y);
 	const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
@@ -226,7 +236,7 @@ __device__ __forceinline__ Norm load_stats_t(const float2 *__restrict__ x, int L
 		// 16-byte aligned window: two samples per lane per load
 		const float4 *x4 = reinterpret_cast<const float4 *>(x);
 		const int L2 = L >> 1;
-#pragma unroll 8
+#pragma unroll 4
 		for (int i = lane; i < L2; i += 32) {
 			const float4 v = __ldg(&x4[i]);
 			sr += v.x + v.z;
@@ -246,7 +256,7 @@ __device__ __forceinline__ Norm load_stats_t(const float2 *__restrict__ x, int L
 				sq += v.x * v.x + v.y * v.y;
 		}
 	} else {
-#pragma unroll 8
+#pragma unroll 4
 		for (int i = lane; i < L; i += 32) {
 			const float2 v = __ldg(&x[i]);
 			sr += v.x;
@@ -309,8 +319,8 @@ __device__ int sync_find(const BurstTab &bt, const WarpSmem &sm, const Regions &
 		sm.accv[m] = 0.0f;
 	float p_toa = 0.0f, p_pwr = 0.0f;
 	int p_idx = -1;
-	float rot_s, rot_c;                               // e^{j*fs*sps*lane}: tap n of every chunk
-	sincosf((fs * (float)sps) * (float)lane, &rot_s, &rot_c);
+	const float2 rot = sincos_acc((fs * (float)sps) * (float)lane);     // e^{j*fs*sps*lane}: tap n of every chunk
+	const float rot_c = rot.x, rot_s = rot.y;
 	for (int s = 0; s < bt.n_sync; s++) {
 		int tl = 0;
 		for (int c = 0; c < bt.n_chunk[s]; c++) {
@@ -432,8 +442,9 @@ __device__ __forceinline__ float2 warp_sum2(float a, float b, int lane)
 
 // mode 0: demod (bts[0] only).  mode 1: detect among n_bt burst types (pi4cxpsk.c:617-682).
 // Persistent: each warp strides over the bursts of the batch.
+template <int MODE>
 __global__ void __launch_bounds__(DM_WARPS * 32, 8)
-demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int mode, int warp_bytes,
+demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int warp_bytes,
              const __grid_constant__ Regions rg)
 {
 	extern __shared__ __align__(16) uint8_t smem[];
@@ -444,7 +455,7 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 	const int w = L - bt.len * sps + 1;
 	const WarpSmem sm = carve(smem + (size_t)warp * warp_bytes, rg.total, w);
 
-	if (mode == 0)
+	if (MODE == 0)
 		build_flat(bt, ft);
 	// the area behind the window must only ever hold finite values (see sync_find)
 	for (int i = lane; i < ((rg.total + 1) & ~1); i += 32)
@@ -462,7 +473,7 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 	tpl.xj = PI_F * (float)(lane - 10);
 	tpl.sgn = lane < 21 ? (((lane - 10) & 1) ? 1.0f : -1.0f) : 0.0f;
 
-	const bool want_sd = a.pwr != nullptr || (mode == 1 && (a.e_toa != nullptr || a.e_toa0 >= 0.0f));
+	const bool want_sd = a.pwr != nullptr || (MODE == 1 && (a.e_toa != nullptr || a.e_toa0 >= 0.0f));
 	const int nbits = bt.nbits, mask = (1 << nbits) - 1;
 	const double inv_dd = (double)(1 << nbits) / (2.0 * 3.14159265358979323846);
 	const double period = (double)(1 << nbits), inv_period = 1.0 / period;
@@ -476,7 +487,7 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 		const Norm nm = load_stats(x, L, lane, want_sd);
 		load_regions(x, rg, sm.reg, lane);
 
-		if (mode == 1) {
+		if (MODE == 1) {
 			const float e_toa = a.e_toa ? a.e_toa[b] : a.e_toa0;
 			int p_id = -1, p_sid = -1;
 			float p_toa = 0.0f, p_pwr = 0.0f;
@@ -527,44 +538,40 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 		//      z = (x - avg)/sd * e^{j*fl32(fs*idx)}, times conj(reference symbol).  Per-chunk sums ->
 		//      fine frequency error from the chunk-to-chunk phase slope (:360-406).
 		const int nch = bt.n_chunk[sync_id], ntr = ft.n_train[sync_id];
-		float cr[MAX_SYNC_CHUNK], ci[MAX_SYNC_CHUNK];
-#pragma unroll
-		for (int c = 0; c < MAX_SYNC_CHUNK; c++)
-			cr[c] = ci[c] = 0.0f;
 		for (int t0 = 0; t0 < ntr; t0 += 32) {
 			const int t = t0 + lane;
 			if (t < ntr) {
-				const int pos = ft.t_pos[sync_id][t], q = sample_of(pos), ch = ft.t_chunk[sync_id][t];
+				const int pos = ft.t_pos[sync_id][t], q = sample_of(pos);
 				const float2 v = __ldg(&x[q]);
-				float sn, cs;
-				sincosf(fs * (float)q, &sn, &cs);
+				const float2 e = sincos_acc(fs * (float)q);
+				const float cs = e.x, sn = e.y;
 				const float yr = (v.x - nm.ar) * nm.inv_sd, yi = (v.y - nm.ai) * nm.inv_sd;
-				const float2 z = mul_conj_sym(ft.t_sym[sync_id][t], make_float2(yr * cs - yi * sn, yr * sn + yi * cs));
-				sm.zbuf[t] = z;
-#pragma unroll
-				for (int c = 0; c < MAX_SYNC_CHUNK; c++)
-					if (ch == c) {
-						cr[c] += z.x;
-						ci[c] += z.y;
-					}
+				sm.zbuf[t] = mul_conj_sym(ft.t_sym[sync_id][t], make_float2(yr * cs - yi * sn, yr * sn + yi * cs));
 			}
 		}
+		__syncwarp();
 		float ferr = 0.0f;
 		if (nch > 1) {
 			float f = 0.0f, prev_r = 0.0f, prev_i = 0.0f, prev_pos = 0.0f;
-#pragma unroll
-			for (int c = 0; c < MAX_SYNC_CHUNK; c++)
-				if (c < nch) {
-					const float2 sum = warp_sum2(cr[c], ci[c], lane);
-					const float pos = (float)bt.s_pos[sync_id][c] + (float)bt.s_len[sync_id][c] / 2.0f;
-					if (c > 0) {   // arg(corr[c] * conj(corr[c-1])) / (pos[c] - pos[c-1])
-						const float re = sum.x * prev_r + sum.y * prev_i, im = sum.y * prev_r - sum.x * prev_i;
-						f += fast_atan2f(im, re) / (pos - prev_pos);
+#pragma unroll 1
+			for (int c = 0; c < nch; c++) {
+				float cr = 0.0f, ci = 0.0f;
+				for (int t = lane; t < ntr; t += 32)
+					if (ft.t_chunk[sync_id][t] == c) {
+						const float2 z = sm.zbuf[t];
+						cr += z.x;
+						ci += z.y;
 					}
-					prev_r = sum.x;
-					prev_i = sum.y;
-					prev_pos = pos;
+				const float2 sum = warp_sum2(cr, ci, lane);
+				const float pos = (float)bt.s_pos[sync_id][c] + (float)bt.s_len[sync_id][c] / 2.0f;
+				if (c > 0) {   // arg(corr[c] * conj(corr[c-1])) / (pos[c] - pos[c-1])
+					const float re = sum.x * prev_r + sum.y * prev_i, im = sum.y * prev_r - sum.x * prev_i;
+					f += fast_atan2f(im, re) / (pos - prev_pos);
 				}
+				prev_r = sum.x;
+				prev_i = sum.y;
+				prev_pos = pos;
+			}
 			ferr = f / (float)(nch - 1);
 		}
 		if (lane == 0 && a.freq_err) a.freq_err[b] = ferr;
@@ -573,15 +580,13 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 		float phi0;
 		{
 			float pr = 0.0f, pi = 0.0f;
-			__syncwarp();
 			for (int t0 = 0; t0 < ntr; t0 += 32) {
 				const int t = t0 + lane;
 				if (t < ntr) {
 					float2 z = sm.zbuf[t];
 					if (ferr != 0.0f) {
-						float sn, cs;
-						sincosf((-ferr) * (float)ft.t_pos[sync_id][t], &sn, &cs);
-						z = make_float2(z.x * cs - z.y * sn, z.x * sn + z.y * cs);
+						const float2 e = sincos_acc((-ferr) * (float)ft.t_pos[sync_id][t]);
+						z = make_float2(z.x * e.x - z.y * e.y, z.x * e.y + z.y * e.x);
 					}
 					pr += z.x;
 					pi += z.y;
@@ -703,7 +708,9 @@ cudaError_t launch_demod(const DemodArgs &a, const BurstTab *d_bts, const BurstT
 			tab_up[dev] = true;
 	}
 	if (dev >= 64 || attr_set[dev] < smem) {
-		cudaError_t e = cudaFuncSetAttribute(demod_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		cudaError_t e = cudaFuncSetAttribute(demod_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (e == cudaSuccess)
+			e = cudaFuncSetAttribute(demod_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if (e != cudaSuccess)
 			return e;
 		if (dev < 64)
@@ -720,10 +727,18 @@ cudaError_t launch_demod(const DemodArgs &a, const BurstTab *d_bts, const BurstT
 	const int sms = dev < 64 ? n_sm[dev] : 148;
 	int per_sm = (int)((227 * 1024) / (smem + sizeof(FlatTab) + 1024));
 	per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+	if (const char *e = getenv("GMR1B200_DEMOD_CTAS")) {     // tuning knob: resident CTAs per SM
+		const int v = atoi(e);
+		if (v >= 1 && v < per_sm)
+			per_sm = v;
+	}
 	int grid = (a.n + DM_WARPS - 1) / DM_WARPS;
 	if (grid > sms * per_sm)
 		grid = sms * per_sm;
-	demod_kernel<<<grid, DM_WARPS * 32, smem, st>>>(a, d_bts, n_bt, mode, (int)wb, rg);
+	if (mode == 0)
+		demod_kernel<0><<<grid, DM_WARPS * 32, smem, st>>>(a, d_bts, n_bt, (int)wb, rg);
+	else
+		demod_kernel<1><<<grid, DM_WARPS * 32, smem, st>>>(a, d_bts, n_bt, (int)wb, rg);
 	return cudaGetLastError();
 }
 
