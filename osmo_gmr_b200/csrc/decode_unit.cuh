@@ -136,18 +136,34 @@ GMR1_HD void decode_unit_k5(const TabRef &tb, const DecodeArgs &a, int unit,
 	if (a.conv)
 		a.conv[unit] = (int32_t)ae[0];
 
-	// traceback into LSB-first packed bytes, reusing the (now dead) staged row
+	// traceback into LSB-first packed bytes, reusing the (now dead) staged row.  Flush steps first
+	// (no output), then the data steps in groups of 8 = one output byte each.
 	uint8_t *out = (uint8_t *)row;
 	{
+		unsigned st = 0;
+		for (int i = tb.n_steps - 1; i >= tb.len; i--) {
+			const unsigned bit = (dec[(size_t)i * T + t] >> st) & 1u;
+			st = (st >> 1) | (bit << (C::K - 2));
+		}
+		int i = tb.len - 1;
 		unsigned acc = 0;
-		auto emit = [&](int i, unsigned bit) {
-			acc |= bit << (i & 7);
-			if ((i & 7) == 0) {
-				out[i >> 3] = (uint8_t)acc;
-				acc = 0;
+		for (; (i & 7) != 7; i--) {          // ragged top byte (len not a multiple of 8)
+			acc |= (st & 1u) << (i & 7);
+			const unsigned bit = (dec[(size_t)i * T + t] >> st) & 1u;
+			st = (st >> 1) | (bit << (C::K - 2));
+		}
+		if ((tb.len & 7) != 0)
+			out[tb.len >> 3] = (uint8_t)acc;
+		for (; i >= 7; i -= 8) {
+			acc = 0;
+#pragma unroll
+			for (int b = 7; b >= 0; b--) {
+				acc |= (st & 1u) << b;
+				const unsigned bit = (dec[(size_t)(i - 7 + b) * T + t] >> st) & 1u;
+				st = (st >> 1) | (bit << (C::K - 2));
 			}
-		};
-		traceback<C>(dec, T, t, tb.n_steps, tb.len, 0u, emit);
+			out[i >> 3] = (uint8_t)acc;
+		}
 	}
 
 	constexpr int NB = chan_l2_bytes(CH);

@@ -312,9 +312,12 @@ __device__ __forceinline__ void load_regions(const float2 *__restrict__ x, const
 // t_n = conj(ref_n) e^{j*fs*sps*n}.  Same quantity, 60x fewer sincos.
 // accv is NOT cleared between sequences - the reference clears it once per call (:207) and
 // keeps adding (:232-233); tl restarts per sequence (:216).
-__device__ int sync_find(const BurstTab &bt, const WarpSmem &sm, const Regions &rg, const Norm &nm, float fs, int sps,
-                         int w, const TapLane &tpl, int lane, float &toa, float &pwr)
+template <int SPS>     // SPS > 0: compile-time samples per symbol (4 is the fast path), 0: run-time
+__device__ int sync_find(const BurstTab &bt, const WarpSmem &sm, const uint16_t (*roff_tab)[MAX_SYNC_CHUNK],
+                         const Norm &nm, float fs, int sps_rt, int w, const TapLane &tpl, int lane, float &toa,
+                         float &pwr)
 {
+	const int sps = SPS > 0 ? SPS : sps_rt;
 	for (int m = lane; m < w; m += 32)
 		sm.accv[m] = 0.0f;
 	float p_toa = 0.0f, p_pwr = 0.0f;
@@ -324,7 +327,7 @@ __device__ int sync_find(const BurstTab &bt, const WarpSmem &sm, const Regions &
 	for (int s = 0; s < bt.n_sync; s++) {
 		int tl = 0;
 		for (int c = 0; c < bt.n_chunk[s]; c++) {
-			const int b0 = bt.s_pos[s][c] * sps, cl = bt.s_len[s][c];
+			const int cl = bt.s_len[s][c];
 			// rotated taps + their sum
 			float tr = 0.0f, ti = 0.0f;
 			if (lane < cl) {
@@ -342,10 +345,7 @@ __device__ int sync_find(const BurstTab &bt, const WarpSmem &sm, const Regions &
 			// warp's other regions / taps / accv / zbuf, which only ever hold finite floats, and
 			// 0 * finite adds nothing.
 			const int cl4 = (cl + 3) & ~3;
-			int roff = 0;
-			for (int r = 0; r < rg.n; r++)
-				if (b0 >= rg.start[r] && b0 < rg.start[r] + rg.len[r])
-					roff = rg.off[r] + (b0 - rg.start[r]);
+			const int roff = roff_tab[s][c];
 			for (int m = lane; m < w; m += 32) {
 				float cr = 0.0f, ci = 0.0f;
 				const float2 *g = sm.reg + roff + m;
@@ -388,6 +388,7 @@ __device__ int sync_find(const BurstTab &bt, const WarpSmem &sm, const Regions &
 // symbols of every sync sequence (position, reference symbol, chunk) and the data symbols in
 // output order.  One lane per symbol then needs no per-chunk control flow.
 struct FlatTab {
+	uint16_t roff[8][MAX_SYNC][MAX_SYNC_CHUNK];   // smem offset (in samples) of each chunk's first sample
 	uint16_t d_pos[480];
 	uint16_t t_pos[MAX_SYNC][MAX_TRAIN];
 	uint8_t  t_sym[MAX_SYNC][MAX_TRAIN];
@@ -442,7 +443,7 @@ __device__ __forceinline__ float2 warp_sum2(float a, float b, int lane)
 
 // mode 0: demod (bts[0] only).  mode 1: detect among n_bt burst types (pi4cxpsk.c:617-682).
 // Persistent: each warp strides over the bursts of the batch.
-template <int MODE>
+template <int MODE, int SPS>
 __global__ void __launch_bounds__(DM_WARPS * 32, 8)
 demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int warp_bytes,
              const __grid_constant__ Regions rg)
@@ -451,12 +452,21 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 	__shared__ FlatTab ft;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const BurstTab &bt = bts[0];
-	const int sps = a.sps, L = a.win_len;
+	const int sps = SPS > 0 ? SPS : a.sps, L = a.win_len;
 	const int w = L - bt.len * sps + 1;
 	const WarpSmem sm = carve(smem + (size_t)warp * warp_bytes, rg.total, w);
 
 	if (MODE == 0)
 		build_flat(bt, ft);
+	for (int i = threadIdx.x; i < n_bt * MAX_SYNC * MAX_SYNC_CHUNK; i += blockDim.x) {
+		const int ty = i / (MAX_SYNC * MAX_SYNC_CHUNK), sq = (i / MAX_SYNC_CHUNK) % MAX_SYNC, c = i % MAX_SYNC_CHUNK;
+		const int b0 = bts[ty].s_pos[sq][c] * a.sps;
+		int roff = 0;
+		for (int r = 0; r < rg.n; r++)
+			if (b0 >= rg.start[r] && b0 < rg.start[r] + rg.len[r])
+				roff = rg.off[r] + (b0 - rg.start[r]);
+		ft.roff[ty][sq][c] = (uint16_t)roff;
+	}
 	// the area behind the window must only ever hold finite values (see sync_find)
 	for (int i = lane; i < ((rg.total + 1) & ~1); i += 32)
 		sm.reg[i] = make_float2(0.0f, 0.0f);
@@ -493,7 +503,7 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 			float p_toa = 0.0f, p_pwr = 0.0f;
 			for (int id = 0; id < n_bt; id++) {
 				float toa, pwr;
-				const int sid = sync_find(bts[id], sm, rg, nm, fs, sps, w, tpl, lane, toa, pwr);
+				const int sid = sync_find<SPS>(bts[id], sm, ft.roff[id], nm, fs, sps, w, tpl, lane, toa, pwr);
 				if (e_toa >= 0.0f)     // the reference divides by fabs() in double (pi4cxpsk.c:658-659)
 					pwr = (float)((double)pwr / fabs((double)(e_toa - toa)));
 				if (pwr > p_pwr) {
@@ -513,7 +523,7 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 		}
 
 		float toa, pwr;
-		const int sync_id = sync_find(bt, sm, rg, nm, fs, sps, w, tpl, lane, toa, pwr);
+		const int sync_id = sync_find<SPS>(bt, sm, ft.roff[0], nm, fs, sps, w, tpl, lane, toa, pwr);
 		if (lane == 0) {
 			if (a.sync_id) a.sync_id[b] = sync_id;
 			if (a.toa) a.toa[b] = toa;
@@ -708,9 +718,11 @@ cudaError_t launch_demod(const DemodArgs &a, const BurstTab *d_bts, const BurstT
 			tab_up[dev] = true;
 	}
 	if (dev >= 64 || attr_set[dev] < smem) {
-		cudaError_t e = cudaFuncSetAttribute(demod_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (e == cudaSuccess)
-			e = cudaFuncSetAttribute(demod_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		cudaError_t e = cudaSuccess;
+		const void *fns[4] = {(const void *)demod_kernel<0, 4>, (const void *)demod_kernel<0, 0>,
+		                      (const void *)demod_kernel<1, 4>, (const void *)demod_kernel<1, 0>};
+		for (int i = 0; i < 4 && e == cudaSuccess; i++)
+			e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if (e != cudaSuccess)
 			return e;
 		if (dev < 64)
@@ -735,10 +747,14 @@ cudaError_t launch_demod(const DemodArgs &a, const BurstTab *d_bts, const BurstT
 	int grid = (a.n + DM_WARPS - 1) / DM_WARPS;
 	if (grid > sms * per_sm)
 		grid = sms * per_sm;
-	if (mode == 0)
-		demod_kernel<0><<<grid, DM_WARPS * 32, smem, st>>>(a, d_bts, n_bt, (int)wb, rg);
+	if (mode == 0 && a.sps == 4)
+		demod_kernel<0, 4><<<grid, DM_WARPS * 32, smem, st>>>(a, d_bts, n_bt, (int)wb, rg);
+	else if (mode == 0)
+		demod_kernel<0, 0><<<grid, DM_WARPS * 32, smem, st>>>(a, d_bts, n_bt, (int)wb, rg);
+	else if (a.sps == 4)
+		demod_kernel<1, 4><<<grid, DM_WARPS * 32, smem, st>>>(a, d_bts, n_bt, (int)wb, rg);
 	else
-		demod_kernel<1><<<grid, DM_WARPS * 32, smem, st>>>(a, d_bts, n_bt, (int)wb, rg);
+		demod_kernel<1, 0><<<grid, DM_WARPS * 32, smem, st>>>(a, d_bts, n_bt, (int)wb, rg);
 	return cudaGetLastError();
 }
 

@@ -70,18 +70,26 @@ GMR1_HD int gather_sbit(const int8_t *row, uint16_t w)
 
 // ---- one trellis step --------------------------------------------------------------------
 // DW = number of 32-bit decision words per step (NS/32 rounded up)
+// branch metric of one soft bit against a transmitted 0 (+127) / 1 (-127): ((is -+ 127)^2) >> 9,
+// nothing for an erased (0) soft bit
+GMR1_HD void soft_metrics(int is, uint32_t &m0, uint32_t &m1)
+{
+	const int d0 = is - 127, d1 = is + 127;
+	m0 = is ? (uint32_t)((d0 * d0) >> 9) : 0u;
+	m1 = is ? (uint32_t)((d1 * d1) >> 9) : 0u;
+}
+
+// One trellis step from `ae` into `nae` (callers ping-pong the two arrays so that no register
+// copies are needed).  DW = number of 32-bit decision words per step (NS/32 rounded up).
 template <class C, bool FLUSH_STEP>
-GMR1_HD void acs_step(uint32_t (&ae)[C::NS], const int (&v)[C::N], uint32_t (&dec)[(C::NS + 31) / 32])
+GMR1_HD void acs_step(const uint32_t (&ae)[C::NS], uint32_t (&nae)[C::NS], const int (&v)[C::N],
+                      uint32_t (&dec)[(C::NS + 31) / 32])
 {
 	constexpr int N = C::N, NS = C::NS, H = NS / 2;
 	uint32_t m0[N], m1[N];
 #pragma unroll
-	for (int j = 0; j < N; j++) {
-		int is = v[j];
-		int d0 = is - 127, d1 = is + 127;
-		m0[j] = is ? (uint32_t)((d0 * d0) >> 9) : 0u;
-		m1[j] = is ? (uint32_t)((d1 * d1) >> 9) : 0u;
-	}
+	for (int j = 0; j < N; j++)
+		soft_metrics(v[j], m0[j], m1[j]);
 	// all 2^N branch sums, built by doubling (entries that no transition uses are dead code)
 	uint32_t bm[1 << N];
 	bm[0] = 0;
@@ -94,7 +102,6 @@ GMR1_HD void acs_step(uint32_t (&ae)[C::NS], const int (&v)[C::N], uint32_t (&de
 			bm[2 * o]     = base + m0[j];
 		}
 	}
-	uint32_t nae[NS];
 #pragma unroll
 	for (int i = 0; i < (NS + 31) / 32; i++)
 		dec[i] = 0;
@@ -116,9 +123,6 @@ GMR1_HD void acs_step(uint32_t (&ae)[C::NS], const int (&v)[C::N], uint32_t (&de
 			nae[2 * k + 1] = MAX_AE;
 		}
 	}
-#pragma unroll
-	for (int s = 0; s < NS; s++)
-		ae[s] = nae[s];
 }
 
 // decision storage: word w of step i of thread t lives at dec[(i*DW + w)*T + t] (T = threads
@@ -128,31 +132,59 @@ template <> struct DecWord<16> { using type = uint16_t; };
 
 // ---- forward pass over n steps ------------------------------------------------------------
 // g: gather program (N words per step), g2: optional second source averaged in (RACH)
+template <class C, bool HAS_G2>
+GMR1_HD void fetch_inputs(int (&v)[C::N], const int8_t *row, const uint16_t *g, const uint16_t *g2, int i)
+{
+#pragma unroll
+	for (int j = 0; j < C::N; j++) {
+		int s = gather_sbit(row, g[i * C::N + j]);
+		if (HAS_G2) {
+			const uint16_t w2 = g2[i * C::N + j];
+			if (w2 != G_ERASED)
+				s = (s + gather_sbit(row, w2)) >> 1;    // rach.c:159-160
+		}
+		v[j] = s;
+	}
+}
+
+template <class C, bool STORE>
+GMR1_HD void store_dec(const uint32_t (&dec)[(C::NS + 31) / 32], typename DecWord<C::NS>::type *dec_base, int T, int t, int i)
+{
+	constexpr int DW = (C::NS + 31) / 32;
+	if (STORE) {
+#pragma unroll
+		for (int w = 0; w < DW; w++)
+			dec_base[(size_t)(i * DW + w) * T + t] = (typename DecWord<C::NS>::type)dec[w];
+	}
+}
+
 template <class C, bool FLUSH_STEP, bool STORE, bool HAS_G2>
 GMR1_HD void forward(uint32_t (&ae)[C::NS], const int8_t *row, const uint16_t *g, const uint16_t *g2,
                      int step0, int nsteps, typename DecWord<C::NS>::type *dec_base, int T, int t)
 {
 	constexpr int DW = (C::NS + 31) / 32;
-	for (int i = step0; i < step0 + nsteps; i++) {
+	uint32_t tmp[C::NS];
+	int i = step0;
+	const int end = step0 + nsteps;
+	for (; i + 1 < end; i += 2) {           // two steps per iteration: ae -> tmp -> ae
 		int v[C::N];
-#pragma unroll
-		for (int j = 0; j < C::N; j++) {
-			const uint16_t w = g[i * C::N + j];
-			int s = gather_sbit(row, w);
-			if (HAS_G2) {
-				const uint16_t w2 = g2[i * C::N + j];
-				if (w2 != G_ERASED)
-					s = (s + gather_sbit(row, w2)) >> 1;    // rach.c:159-160
-			}
-			v[j] = s;
-		}
 		uint32_t dec[DW];
-		acs_step<C, FLUSH_STEP>(ae, v, dec);
-		if (STORE) {
+		fetch_inputs<C, HAS_G2>(v, row, g, g2, i);
+		acs_step<C, FLUSH_STEP>(ae, tmp, v, dec);
+		store_dec<C, STORE>(dec, dec_base, T, t, i);
+		fetch_inputs<C, HAS_G2>(v, row, g, g2, i + 1);
+		acs_step<C, FLUSH_STEP>(tmp, ae, v, dec);
+		store_dec<C, STORE>(dec, dec_base, T, t, i + 1);
+	}
+	if (i < end) {
+		int v[C::N];
+		uint32_t dec[DW];
+		fetch_inputs<C, HAS_G2>(v, row, g, g2, i);
+		acs_step<C, FLUSH_STEP>(ae, tmp, v, dec);
+		store_dec<C, STORE>(dec, dec_base, T, t, i);
 #pragma unroll
-			for (int w = 0; w < DW; w++)
-				dec_base[(size_t)(i * DW + w) * T + t] = (typename DecWord<C::NS>::type)dec[w];
-		}
+		for (int s = 0; s < C::NS; s++)
+			ae[s] = tmp[s];
 	}
 }
 
