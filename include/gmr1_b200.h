@@ -131,6 +131,14 @@ enum gmr1b200_burst_type {
 	GMR1B200_BT_COUNT
 };
 
+/* Reference quirk switch.  _gmr1_pi4cxpsk_sync_find clears its correlation accumulator once per call,
+ * not once per candidate training sequence (src/sdr/pi4cxpsk.c:207 vs :232-233), so for formats with
+ * several sequences (NT3-FACCH, NT6, NT9, SDCCH) candidate i is scored on the sum of candidates 0..i and
+ * the last one always wins.  Default (0) reproduces that bit for bit; 1 scores every candidate on its own
+ * correlation (what the code evidently intends; needed to tell FACCH9 from TCH9).  Process-wide; returns
+ * the previous setting. */
+int gmr1b200_set_sync_accumulator_reset(int on);
+
 /* symbols (incl. guard) and soft bits of a burst type; -EINVAL for a bad id */
 int gmr1b200_burst_len(int burst_type);
 int gmr1b200_burst_ebits(int burst_type);

@@ -143,6 +143,8 @@ static int sync_find(struct gmr1_pi4cxpsk_burst *bt, struct osmo_cxvec *burst, i
 		float s_toa, s_pwr;
 		float complex s_peak;
 		int tl = 0;
+		if (i > 0 && getenv("GMR1_ORACLE_SYNC_RESET"))     /* opt-in, NOT the reference: see gmr1_b200.h */
+			memset(corr->data, 0, sizeof(float complex) * corr->max_len);
 		for (cs = bt->sync[i]; cs->pos >= 0; cs++) {
 			osmo_cxvec_init_from_data(&win, &burst->data[cs->pos * sps], (cs->len * sps) + w - 1);
 			osmo_cxvec_correlate(cs->_ref, &win, sps, tmp);

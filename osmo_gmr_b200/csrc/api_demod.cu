@@ -29,6 +29,8 @@ cudaError_t gmr1::device_bursts(const BurstTab **out)
 	return cudaSuccess;
 }
 
+static std::atomic<int> g_sync_reset{0};
+
 static_assert(sizeof(gmr1b200_burst_desc) == sizeof(BurstTab), "public descriptor must mirror gmr1::BurstTab");
 
 static int run_demod(const int *types, int n_types, int mode, DemodArgs a, int64_t iq_len, void *stream,
@@ -56,6 +58,7 @@ static int run_demod(const int *types, int n_types, int mode, DemodArgs a, int64
 	}
 	if (a.sps < 4 || a.sps > 16)
 		return set_err(-EINVAL, "pi4cxpsk batch: sps must be 4..16");
+	a.sync_reset = g_sync_reset.load();
 	const BurstTab &t0 = custom ? custom[0] : burst_tab(types[0]);
 	if (a.win_len < t0.len * a.sps)
 		return set_err(-EINVAL, "pi4cxpsk batch: window shorter than the burst");
@@ -165,6 +168,11 @@ int gmr1b200_synth_bursts(int burst_type, const uint8_t *ebits, int ebits_stride
 	a.esn0_db = esn0_db; a.esn0_db0 = esn0_db0; a.amp = amp; a.amp0 = amp0; a.seed = seed;
 	a.iq = (float2 *)iq; a.ofs = win_ofs; a.stride = win_stride;
 	return run_synth(burst_type, a, iq_len, stream);
+}
+
+int gmr1b200_set_sync_accumulator_reset(int on)
+{
+	return g_sync_reset.exchange(on ? 1 : 0);
 }
 
 int gmr1b200_burst_desc_get(int bt, struct gmr1b200_burst_desc *out)

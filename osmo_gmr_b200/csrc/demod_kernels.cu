@@ -314,8 +314,8 @@ __device__ __forceinline__ void load_regions(const float2 *__restrict__ x, const
 // keeps adding (:232-233); tl restarts per sequence (:216).
 template <int SPS>     // SPS > 0: compile-time samples per symbol (4 is the fast path), 0: run-time
 __device__ int sync_find(const BurstTab &bt, const WarpSmem &sm, const uint16_t (*roff_tab)[MAX_SYNC_CHUNK],
-                         const Norm &nm, float fs, int sps_rt, int w, const TapLane &tpl, int lane, float &toa,
-                         float &pwr)
+                         const Norm &nm, float fs, int sps_rt, int w, const TapLane &tpl, int lane, bool sync_reset,
+                         float &toa, float &pwr)
 {
 	const int sps = SPS > 0 ? SPS : sps_rt;
 	for (int m = lane; m < w; m += 32)
@@ -326,6 +326,11 @@ __device__ int sync_find(const BurstTab &bt, const WarpSmem &sm, const uint16_t 
 	const float rot_c = rot.x, rot_s = rot.y;
 	for (int s = 0; s < bt.n_sync; s++) {
 		int tl = 0;
+		if (sync_reset && s > 0) {           // opt-in: score every candidate on its own correlation
+			__syncwarp();
+			for (int m = lane; m < w; m += 32)
+				sm.accv[m] = 0.0f;
+		}
 		for (int c = 0; c < bt.n_chunk[s]; c++) {
 			const int cl = bt.s_len[s][c];
 			// rotated taps + their sum
@@ -503,7 +508,7 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 			float p_toa = 0.0f, p_pwr = 0.0f;
 			for (int id = 0; id < n_bt; id++) {
 				float toa, pwr;
-				const int sid = sync_find<SPS>(bts[id], sm, ft.roff[id], nm, fs, sps, w, tpl, lane, toa, pwr);
+				const int sid = sync_find<SPS>(bts[id], sm, ft.roff[id], nm, fs, sps, w, tpl, lane, a.sync_reset != 0, toa, pwr);
 				if (e_toa >= 0.0f)     // the reference divides by fabs() in double (pi4cxpsk.c:658-659)
 					pwr = (float)((double)pwr / fabs((double)(e_toa - toa)));
 				if (pwr > p_pwr) {
@@ -523,7 +528,7 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 		}
 
 		float toa, pwr;
-		const int sync_id = sync_find<SPS>(bt, sm, ft.roff[0], nm, fs, sps, w, tpl, lane, toa, pwr);
+		const int sync_id = sync_find<SPS>(bt, sm, ft.roff[0], nm, fs, sps, w, tpl, lane, a.sync_reset != 0, toa, pwr);
 		if (lane == 0) {
 			if (a.sync_id) a.sync_id[b] = sync_id;
 			if (a.toa) a.toa[b] = toa;

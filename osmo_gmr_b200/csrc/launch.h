@@ -26,6 +26,7 @@ struct DemodArgs {
 	float         *toa;         // [n] or NULL
 	float         *freq_err;    // [n] or NULL
 	float         *pwr;         // [n] or NULL (sync power; detect: after the e_toa weighting)
+	int32_t        sync_reset;  // 0 = reference behaviour (accumulator never cleared between candidate sequences)
 };
 
 // d_bts: n_bt burst descriptors in device memory, h_bts: the same on the host (for geometry)
