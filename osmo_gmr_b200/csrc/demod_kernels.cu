@@ -55,6 +55,17 @@ __device__ __forceinline__ float warp_sum(float v)
 	return v;
 }
 
+// folded shuffle tree for a (re, im) pair: returns both sums in all lanes
+__device__ __forceinline__ float2 warp_sum2(float a, float b, int lane)
+{
+	const bool up = lane & 16;
+	float v = (up ? b : a) + __shfl_xor_sync(0xffffffffu, up ? a : b, 16);
+#pragma unroll
+	for (int o = 8; o; o >>= 1)
+		v += __shfl_xor_sync(0xffffffffu, v, o);
+	return make_float2(__shfl_sync(0xffffffffu, v, 0), __shfl_sync(0xffffffffu, v, 16));
+}
+
 // One out-of-line copy of the accurate sincosf (its large-argument slow path is ~150 instructions;
 // inlined at every call site it pushed the kernel past the instruction cache).
 __device__ __noinline__ float2 sincos_acc(float x)
@@ -72,7 +83,7 @@ __device__ __forceinline__ float2 mul_conj_sym(int sym, float2 g)
 }
 
 // atan2f with ~1e-7 rad absolute error: octant reduction + degree-8 minimax polynomial in a^2
-__device__ __noinline__ float fast_atan2f(float y, float x)
+__device__ __forceinline__ float fast_atan2f_inl(float y, float x)
 {
 	const float ax = fabsf(x), ay = fabsf(y);
 	const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
@@ -93,39 +104,27 @@ __device__ __noinline__ float fast_atan2f(float y, float x)
 	return y < 0.0f ? -r : r;
 }
 
-// Sinc interpolation (osmo_cxvec_interpolate_point, 10 taps either side) of the real vector
-// acc[0..len) at `pos` and, when LATE, also at `pos + 2` (the late gate).  One tap per lane
-// (lane j+10 <-> tap j = -10..10), one folded shuffle tree for both sums.  The 21 sinc values of
-// both gates are identical ((i+2)-(pos+2) == i-pos exactly in fp32 here) and share one sine:
+__device__ __noinline__ float fast_atan2f(float y, float x) { return fast_atan2f_inl(y, x); }
+
+// Sinc interpolation (osmo_cxvec_interpolate_point, 10 taps either side) of the real correlation
+// accumulator, inside the early/late search.  One tap per lane (lane j+10 <-> tap j = -10..10), one
+// folded shuffle tree for the early and the late gate.  The 21 sinc values of both gates are
+// identical ((i+2)-(pos+2) == i-pos exactly in fp32 here) and share one sine:
 // sin(pi*(j-frac)) = -(-1)^j sin(pi*frac), looked up on the 1/512 grid the search visits.
 struct TapLane { float xj, sgn; int j; };      // per-lane constants: pi*j, -(-1)^j (0 for lanes >= 21)
 
-template <bool LATE>
-__device__ __forceinline__ void interp(const float *acc, int len, float pos, const TapLane &tp, int lane,
-                                       float &ev, float &lv)
+__device__ __forceinline__ float ld_acc(const float *acc, int k, int len)
 {
-	const float fl = floorf(pos);
-	const float frac = pos - fl;                      // exact, a multiple of 1/512
+	return ((unsigned)k < (unsigned)len) ? acc[k] : 0.0f;
+}
+
+// sinc weight of this lane's tap for a position with fractional part `frac` (a multiple of 1/512)
+__device__ __forceinline__ float tap_weight(const TapLane &tp, float frac)
+{
 	const float S = c_sinpi512[(int)(frac * 512.0f)];
 	const float x = fmaf(-PI_F, frac, tp.xj);         // pi*(j - frac)
-	float sv = __fdividef(tp.sgn * S, x);
-	sv = fabsf(x) >= 0.01f ? sv : (tp.sgn != 0.0f ? 1.0f : 0.0f);      // osmo_sinc
-	const int k = (int)fl + tp.j;
-	float te = ((unsigned)k < (unsigned)len) ? acc[k] * sv : 0.0f;
-	if (LATE) {
-		const float tl = ((unsigned)(k + 2) < (unsigned)len) ? acc[k + 2] * sv : 0.0f;
-		// fold both sums into one tree: after the first exchange the lower half-warp carries the
-		// early terms, the upper half the late terms
-		const bool up = lane & 16;
-		float v = (up ? tl : te) + __shfl_xor_sync(0xffffffffu, up ? te : tl, 16);
-#pragma unroll
-		for (int o = 8; o; o >>= 1)
-			v += __shfl_xor_sync(0xffffffffu, v, o);
-		ev = __shfl_sync(0xffffffffu, v, 0);
-		lv = __shfl_sync(0xffffffffu, v, 16);
-	} else {
-		ev = warp_sum(te);
-	}
+	const float sv = __fdividef(tp.sgn * S, x);
+	return fabsf(x) >= 0.01f ? sv : (tp.sgn != 0.0f ? 1.0f : 0.0f);      // osmo_sinc
 }
 
 // osmo_cxvec_peak_energy_find(acc, 3, PEAK_EARLY_LATE, &peak) on a real vector; all lanes
@@ -167,11 +166,28 @@ __device__ float peak_early_late(const float *acc, int w, const TapLane &tp, int
 		}
 	}
 
+	// The search starts at mwi-1 and moves by less than 1 in total, so floor(early) is mwi-2 or
+	// mwi-1 (mwi-1 .. mwi for the final interpolation): tap j of this lane only ever reads
+	// acc[mwi-2+j .. mwi+2+j].  Preload those five values once.
+	const int kb = mwi - 2 + tp.j;
+	const float c0 = ld_acc(acc, kb, w), c1 = ld_acc(acc, kb + 1, w), c2 = ld_acc(acc, kb + 2, w),
+	            c3 = ld_acc(acc, kb + 3, w), c4 = ld_acc(acc, kb + 4, w);
+	const float fbase = (float)(mwi - 2);
+	const bool up = lane & 16;
+
 	float early = (float)(mwi - 1), incr = 0.5f;
 #pragma unroll 1
 	for (int it = 0; it < 9; it++) {                  // incr = 1/2 .. 1/512 (> 1/1024)
-		float ev, lv;
-		interp<true>(acc, w, early, tp, lane, ev, lv);
+		const float fl = floorf(early);
+		const float wgt = tap_weight(tp, early - fl);
+		const bool hi = fl != fbase;                  // floor(early) == mwi-1
+		const float te = (hi ? c1 : c0) * wgt, tl = (hi ? c3 : c2) * wgt;      // early gate, late gate (+2)
+		// one folded shuffle tree for both sums: lower half-warp ends with early, upper with late
+		float v = (up ? tl : te) + __shfl_xor_sync(0xffffffffu, up ? te : tl, 16);
+#pragma unroll
+		for (int o = 8; o; o >>= 1)
+			v += __shfl_xor_sync(0xffffffffu, v, o);
+		const float ev = __shfl_sync(0xffffffffu, v, 0), lv = __shfl_sync(0xffffffffu, v, 16);
 		const float e2 = ev * ev, l2 = lv * lv;
 		if (e2 == l2)
 			break;
@@ -179,8 +195,13 @@ __device__ float peak_early_late(const float *acc, int w, const TapLane &tp, int
 		incr *= 0.5f;
 	}
 	const float pos = early + 1.0f;
-	float dummy;
-	interp<false>(acc, w, pos, tp, lane, peak_val, dummy);
+	{
+		const float fl = floorf(pos);
+		const float wgt = tap_weight(tp, pos - fl);
+		const int sel = (int)(fl - fbase);            // 1, 2 (or 3 when early ended on mwi exactly)
+		const float cv = sel <= 1 ? c1 : (sel == 2 ? c2 : (sel == 3 ? c3 : c4));
+		peak_val = warp_sum(cv * wgt);
+	}
 	return pos;
 }
 
@@ -342,7 +363,8 @@ __device__ int sync_find(const BurstTab &bt, const WarpSmem &sm, const uint16_t 
 			}
 			__syncwarp();
 			sm.taps[lane] = make_float2(tr, ti);
-			const float Rr = warp_sum(tr), Ri = warp_sum(ti);
+			const float2 Rs = warp_sum2(tr, ti, lane);
+			const float Rr = Rs.x, Ri = Rs.y;
 			const float cr0 = nm.ar * Rr - nm.ai * Ri, ci0 = nm.ar * Ri + nm.ai * Rr;   // avg * sum(taps)
 			__syncwarp();
 			// taps beyond cl are zero (lanes >= cl wrote 0), so the tap loop runs in whole groups of 4.
@@ -368,7 +390,9 @@ __device__ int sync_find(const BurstTab &bt, const WarpSmem &sm, const uint16_t 
 				cr = (cr - cr0) * nm.inv_sd;
 				ci = (ci - ci0) * nm.inv_sd;
 				const float e = fmaf(cr, cr, ci * ci);
-				sm.accv[m] += e > 0.0f ? e * rsqrtf(e) : 0.0f;
+				float rs;
+				asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(e));
+				sm.accv[m] += e > 0.0f ? e * rs : 0.0f;
 			}
 			tl += cl;
 		}
@@ -433,17 +457,6 @@ __device__ void build_flat(const BurstTab &bt, FlatTab &ft)
 			if (t == 0)
 				ft.n_train[s] = acc;
 		}
-}
-
-// folded shuffle tree for a (re, im) pair: returns both sums in all lanes
-__device__ __forceinline__ float2 warp_sum2(float a, float b, int lane)
-{
-	const bool up = lane & 16;
-	float v = (up ? b : a) + __shfl_xor_sync(0xffffffffu, up ? a : b, 16);
-#pragma unroll
-	for (int o = 8; o; o >>= 1)
-		v += __shfl_xor_sync(0xffffffffu, v, o);
-	return make_float2(__shfl_sync(0xffffffffu, v, 0), __shfl_sync(0xffffffffu, v, 16));
 }
 
 // mode 0: demod (bts[0] only).  mode 1: detect among n_bt burst types (pi4cxpsk.c:617-682).
@@ -553,6 +566,8 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 		//      z = (x - avg)/sd * e^{j*fl32(fs*idx)}, times conj(reference symbol).  Per-chunk sums ->
 		//      fine frequency error from the chunk-to-chunk phase slope (:360-406).
 		const int nch = bt.n_chunk[sync_id], ntr = ft.n_train[sync_id];
+		float2 z0 = make_float2(0.0f, 0.0f);     // training symbol `lane` (round 0) stays in registers
+		int ch0 = -1;
 		for (int t0 = 0; t0 < ntr; t0 += 32) {
 			const int t = t0 + lane;
 			if (t < ntr) {
@@ -561,7 +576,12 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 				const float2 e = sincos_acc(fs * (float)q);
 				const float cs = e.x, sn = e.y;
 				const float yr = (v.x - nm.ar) * nm.inv_sd, yi = (v.y - nm.ai) * nm.inv_sd;
-				sm.zbuf[t] = mul_conj_sym(ft.t_sym[sync_id][t], make_float2(yr * cs - yi * sn, yr * sn + yi * cs));
+				const float2 z = mul_conj_sym(ft.t_sym[sync_id][t], make_float2(yr * cs - yi * sn, yr * sn + yi * cs));
+				sm.zbuf[t] = z;
+				if (t0 == 0) {
+					z0 = z;
+					ch0 = ft.t_chunk[sync_id][t];
+				}
 			}
 		}
 		__syncwarp();
@@ -570,8 +590,8 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 			float f = 0.0f, prev_r = 0.0f, prev_i = 0.0f, prev_pos = 0.0f;
 #pragma unroll 1
 			for (int c = 0; c < nch; c++) {
-				float cr = 0.0f, ci = 0.0f;
-				for (int t = lane; t < ntr; t += 32)
+				float cr = ch0 == c ? z0.x : 0.0f, ci = ch0 == c ? z0.y : 0.0f;
+				for (int t = 32 + lane; t < ntr; t += 32)      // only RACH has more than 32 training symbols
 					if (ft.t_chunk[sync_id][t] == c) {
 						const float2 z = sm.zbuf[t];
 						cr += z.x;
@@ -618,10 +638,11 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 		// the raw sample.
 		const double c0 = -(double)phi0 * inv_dd;
 		const int nds = ft.n_dsym;
+		const bool eb_even = (((uintptr_t)eb) & 1) == 0;
 		for (int t = lane; t < nds; t += 32) {
 			const int i = ft.d_pos[t], q = sample_of(i);
 			const float2 v = __ldg(&x[q]);
-			const float th = fast_atan2f(v.y - nm.ai, v.x - nm.ar);
+			const float th = fast_atan2f_inl(v.y - nm.ai, v.x - nm.ar);
 			const float a1 = fs * (float)q;
 			const float a2 = (-ferr) * (float)i;
 			double svd = fma((double)th + (double)a1 + (double)a2, inv_dd, c0);
@@ -629,23 +650,25 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 			const float sv = (float)svd;
 			const float svr = rintf(sv);                   // (ties differ from roundf only on exact .5)
 			const int sp = (int)svr & mask;
-			const int ss = (svr > sv ? (sp - 1) : (sp + 1)) & mask;
+			const bool below = svr > sv;                   // second-nearest symbol is sp-1, else sp+1
 			const int dq = __float2int_rn(128.0f * fabsf(svr - sv));
+			const int v_far = 127 - dq, v_near = 127 - (dq >> 1);     // bit that flips towards the neighbour / bit that does not
 			if (nbits == 2) {
-				// Gray map of the symbol index {00, 01, 11, 10}, MSB first
-				const int gp = sp ^ (sp >> 1), gx = gp ^ ss ^ (ss >> 1);
-				const int v0 = 127 - ((gx & 2) ? dq : (dq >> 1)), v1 = 127 - ((gx & 1) ? dq : (dq >> 1));
-				const int b0 = (gp & 2) ? -v0 : v0, b1 = (gp & 1) ? -v1 : v1;
+				// Gray map {00, 01, 11, 10}, MSB first.  sp -> sp+1 flips the LSB when sp is even, the MSB
+				// when sp is odd; sp -> sp-1 the other way round.
+				const int gp = sp ^ (sp >> 1);
+				const bool msb_flips = ((sp & 1) != 0) != below;
+				const int m1 = msb_flips ? v_far : v_near, m0 = msb_flips ? v_near : v_far;
+				const int b1 = (gp & 2) ? -m1 : m1, b0 = (gp & 1) ? -m0 : m0;      // first, second soft bit
 				int8_t *o = eb + 2 * t;
-				if ((((uintptr_t)o) & 1) == 0)
-					*reinterpret_cast<uint16_t *>(o) = (uint16_t)((b0 & 0xff) | ((b1 & 0xff) << 8));
+				if (eb_even)
+					*reinterpret_cast<uint16_t *>(o) = (uint16_t)((b1 & 0xff) | ((b0 & 0xff) << 8));
 				else {
-					o[0] = (int8_t)b0;
-					o[1] = (int8_t)b1;
+					o[0] = (int8_t)b1;
+					o[1] = (int8_t)b0;
 				}
 			} else {
-				const int v0 = 127 - (((sp ^ ss) & 1) ? dq : (dq >> 1));
-				eb[t] = (int8_t)(sp ? -v0 : v0);
+				eb[t] = (int8_t)(sp ? -v_far : v_far);     // one bit per symbol: both neighbours flip it
 			}
 		}
 	}
