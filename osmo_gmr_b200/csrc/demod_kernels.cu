@@ -373,26 +373,50 @@ __device__ int sync_find(const BurstTab &bt, const WarpSmem &sm, const uint16_t 
 			// 0 * finite adds nothing.
 			const int cl4 = (cl + 3) & ~3;
 			const int roff = roff_tab[s][c];
-			for (int m = lane; m < w; m += 32) {
-				float cr = 0.0f, ci = 0.0f;
-				const float2 *g = sm.reg + roff + m;
+			// up to three search offsets per lane (m, m+32, m+64) share every tap load
+			for (int m0 = lane; m0 < w; m0 += 96) {
+				float cr[3] = {0.0f, 0.0f, 0.0f}, ci[3] = {0.0f, 0.0f, 0.0f};
+				const float2 *g = sm.reg + roff + m0;
 				const float2 *tp = sm.taps;
+				const int nr = (w - m0 + 31) >> 5;          // rounds this lane takes part in (uniform except the tail)
+				const bool r1 = m0 + 32 < w, r2 = m0 + 64 < w;
+				(void)nr;
 				for (int n = 0; n < cl4; n += 4, tp += 4, g += 4 * sps) {
 #pragma unroll
 					for (int u = 0; u < 4; u++) {
-						const float2 t = tp[u], v = g[u * sps];
-						cr = fmaf(t.x, v.x, cr);
-						cr = fmaf(-t.y, v.y, cr);
-						ci = fmaf(t.x, v.y, ci);
-						ci = fmaf(t.y, v.x, ci);
+						const float2 t = tp[u];
+						const float2 v0 = g[u * sps];
+						cr[0] = fmaf(t.x, v0.x, cr[0]);
+						cr[0] = fmaf(-t.y, v0.y, cr[0]);
+						ci[0] = fmaf(t.x, v0.y, ci[0]);
+						ci[0] = fmaf(t.y, v0.x, ci[0]);
+						if (__any_sync(0xffffffffu, r1)) {
+							const float2 v1 = g[u * sps + 32];
+							cr[1] = fmaf(t.x, v1.x, cr[1]);
+							cr[1] = fmaf(-t.y, v1.y, cr[1]);
+							ci[1] = fmaf(t.x, v1.y, ci[1]);
+							ci[1] = fmaf(t.y, v1.x, ci[1]);
+						}
+						if (__any_sync(0xffffffffu, r2)) {
+							const float2 v2 = g[u * sps + 64];
+							cr[2] = fmaf(t.x, v2.x, cr[2]);
+							cr[2] = fmaf(-t.y, v2.y, cr[2]);
+							ci[2] = fmaf(t.x, v2.y, ci[2]);
+							ci[2] = fmaf(t.y, v2.x, ci[2]);
+						}
 					}
 				}
-				cr = (cr - cr0) * nm.inv_sd;
-				ci = (ci - ci0) * nm.inv_sd;
-				const float e = fmaf(cr, cr, ci * ci);
-				float rs;
-				asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(e));
-				sm.accv[m] += e > 0.0f ? e * rs : 0.0f;
+#pragma unroll
+				for (int r = 0; r < 3; r++) {
+					const int m = m0 + 32 * r;
+					if (m < w) {
+						const float xr = (cr[r] - cr0) * nm.inv_sd, xi = (ci[r] - ci0) * nm.inv_sd;
+						const float e = fmaf(xr, xr, xi * xi);
+						float rs;
+						asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(e));
+						sm.accv[m] += e > 0.0f ? e * rs : 0.0f;
+					}
+				}
 			}
 			tl += cl;
 		}
