@@ -374,13 +374,14 @@ __device__ int sync_find(const BurstTab &bt, const WarpSmem &sm, const uint16_t 
 			const int cl4 = (cl + 3) & ~3;
 			const int roff = roff_tab[s][c];
 			// up to three search offsets per lane (m, m+32, m+64) share every tap load
-			for (int m0 = lane; m0 < w; m0 += 96) {
+			for (int mb = 0; mb < w; mb += 96) {
+				const int m0 = mb + lane;
+				if (m0 >= w)
+					continue;
 				float cr[3] = {0.0f, 0.0f, 0.0f}, ci[3] = {0.0f, 0.0f, 0.0f};
 				const float2 *g = sm.reg + roff + m0;
 				const float2 *tp = sm.taps;
-				const int nr = (w - m0 + 31) >> 5;          // rounds this lane takes part in (uniform except the tail)
-				const bool r1 = m0 + 32 < w, r2 = m0 + 64 < w;
-				(void)nr;
+				const bool r1 = mb + 32 < w, r2 = mb + 64 < w;      // warp-uniform: some lane has a 2nd / 3rd offset
 				for (int n = 0; n < cl4; n += 4, tp += 4, g += 4 * sps) {
 #pragma unroll
 					for (int u = 0; u < 4; u++) {
@@ -390,14 +391,14 @@ __device__ int sync_find(const BurstTab &bt, const WarpSmem &sm, const uint16_t 
 						cr[0] = fmaf(-t.y, v0.y, cr[0]);
 						ci[0] = fmaf(t.x, v0.y, ci[0]);
 						ci[0] = fmaf(t.y, v0.x, ci[0]);
-						if (__any_sync(0xffffffffu, r1)) {
+						if (r1) {
 							const float2 v1 = g[u * sps + 32];
 							cr[1] = fmaf(t.x, v1.x, cr[1]);
 							cr[1] = fmaf(-t.y, v1.y, cr[1]);
 							ci[1] = fmaf(t.x, v1.y, ci[1]);
 							ci[1] = fmaf(t.y, v1.x, ci[1]);
 						}
-						if (__any_sync(0xffffffffu, r2)) {
+						if (r2) {
 							const float2 v2 = g[u * sps + 64];
 							cr[2] = fmaf(t.x, v2.x, cr[2]);
 							cr[2] = fmaf(-t.y, v2.y, cr[2]);
