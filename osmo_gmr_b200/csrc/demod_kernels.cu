@@ -324,6 +324,29 @@ __device__ __forceinline__ void load_regions(const float2 *__restrict__ x, const
 	__syncwarp();
 }
 
+// complex multiply-accumulate of the (zero-padded to a multiple of 4) rotated taps against R search
+// offsets 32 samples apart; one tap load serves all R
+template <int R>
+__device__ __forceinline__ void corr_taps(const float2 *g, const float2 *tp, int cl4, int sps,
+                                          float (&cr)[3], float (&ci)[3])
+{
+#pragma unroll 1
+	for (int n = 0; n < cl4; n += 4, tp += 4, g += 4 * sps) {
+#pragma unroll
+		for (int u = 0; u < 4; u++) {
+			const float2 t = tp[u];
+#pragma unroll
+			for (int r = 0; r < R; r++) {
+				const float2 v = g[u * sps + 32 * r];
+				cr[r] = fmaf(t.x, v.x, cr[r]);
+				cr[r] = fmaf(-t.y, v.y, cr[r]);
+				ci[r] = fmaf(t.x, v.y, ci[r]);
+				ci[r] = fmaf(t.y, v.x, ci[r]);
+			}
+		}
+	}
+}
+
 // Search all sync sequences of one burst type (pi4cxpsk.c:184-268) on the RAW window.
 //
 // The reference normalises and derotates every sample, y[i] = (x[i]-avg)/sd * e^{j*fs*i}, then
@@ -382,31 +405,12 @@ __device__ int sync_find(const BurstTab &bt, const WarpSmem &sm, const uint16_t 
 				const float2 *g = sm.reg + roff + m0;
 				const float2 *tp = sm.taps;
 				const bool r1 = mb + 32 < w, r2 = mb + 64 < w;      // warp-uniform: some lane has a 2nd / 3rd offset
-				for (int n = 0; n < cl4; n += 4, tp += 4, g += 4 * sps) {
-#pragma unroll
-					for (int u = 0; u < 4; u++) {
-						const float2 t = tp[u];
-						const float2 v0 = g[u * sps];
-						cr[0] = fmaf(t.x, v0.x, cr[0]);
-						cr[0] = fmaf(-t.y, v0.y, cr[0]);
-						ci[0] = fmaf(t.x, v0.y, ci[0]);
-						ci[0] = fmaf(t.y, v0.x, ci[0]);
-						if (r1) {
-							const float2 v1 = g[u * sps + 32];
-							cr[1] = fmaf(t.x, v1.x, cr[1]);
-							cr[1] = fmaf(-t.y, v1.y, cr[1]);
-							ci[1] = fmaf(t.x, v1.y, ci[1]);
-							ci[1] = fmaf(t.y, v1.x, ci[1]);
-						}
-						if (r2) {
-							const float2 v2 = g[u * sps + 64];
-							cr[2] = fmaf(t.x, v2.x, cr[2]);
-							cr[2] = fmaf(-t.y, v2.y, cr[2]);
-							ci[2] = fmaf(t.x, v2.y, ci[2]);
-							ci[2] = fmaf(t.y, v2.x, ci[2]);
-						}
-					}
-				}
+				if (r2)
+					corr_taps<3>(g, tp, cl4, sps, cr, ci);
+				else if (r1)
+					corr_taps<2>(g, tp, cl4, sps, cr, ci);
+				else
+					corr_taps<1>(g, tp, cl4, sps, cr, ci);
 #pragma unroll
 				for (int r = 0; r < 3; r++) {
 					const int m = m0 + 32 * r;
