@@ -147,8 +147,8 @@ int gmr1b200_burst_ebits(int burst_type);
  *   iq          interleaved (re, im) float32, iq_len complex samples in total
  *   win_ofs     [n] first complex sample of each window, or NULL: window b starts at b*win_stride
  *   win_len     complex samples per window (same for the whole batch) = burst_len*sps + search
- *   sps         samples per symbol, 4..16 (the sps < 4 interpolating path of the reference,
- *               pi4cxpsk.c:298-343, is not implemented: -EINVAL)
+ *   sps         samples per symbol, 1..16 (4 = compile-time fast path; sps < 4 takes the reference's
+ *               sinc-interpolating symbol alignment, pi4cxpsk.c:298-343)
  *   freq_shift  [n] rad/symbol pre-rotation (the reference's freq_shift argument) or NULL,
  *               then freq_shift0 applies to every burst
  *   ebits       [n][ebits_stride] soft bits out (ebits_stride >= burst ebits)

@@ -56,8 +56,8 @@ static int run_demod(const int *types, int n_types, int mode, DemodArgs a, int64
 		if (!ok)
 			return set_err(-EINVAL, "pi4cxpsk batch: malformed burst descriptor");
 	}
-	if (a.sps < 4 || a.sps > 16)
-		return set_err(-EINVAL, "pi4cxpsk batch: sps must be 4..16");
+	if (a.sps < 1 || a.sps > 16)
+		return set_err(-EINVAL, "pi4cxpsk batch: sps must be 1..16");
 	a.sync_reset = g_sync_reset.load();
 	const BurstTab &t0 = custom ? custom[0] : burst_tab(types[0]);
 	if (a.win_len < t0.len * a.sps)

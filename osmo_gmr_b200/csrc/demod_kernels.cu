@@ -356,7 +356,7 @@ __device__ __forceinline__ void corr_taps(const float2 *g, const float2 *tp, int
 // t_n = conj(ref_n) e^{j*fs*sps*n}.  Same quantity, 60x fewer sincos.
 // accv is NOT cleared between sequences - the reference clears it once per call (:207) and
 // keeps adding (:232-233); tl restarts per sequence (:216).
-template <int SPS>     // SPS > 0: compile-time samples per symbol (4 is the fast path), 0: run-time
+template <int SPS>     // SPS > 0: compile-time samples per symbol (4 is the fast path), <= 0: run-time
 __device__ int sync_find(const BurstTab &bt, const WarpSmem &sm, const uint16_t (*roff_tab)[MAX_SYNC_CHUNK],
                          const Norm &nm, float fs, int sps_rt, int w, const TapLane &tpl, int lane, bool sync_reset,
                          float &toa, float &pwr)
@@ -439,6 +439,35 @@ __device__ int sync_find(const BurstTab &bt, const WarpSmem &sm, const uint16_t 
 	toa = p_toa;
 	pwr = p_pwr;
 	return p_idx;
+}
+
+// sps < 4 (pi4cxpsk.c:298-343): symbols are not picked but interpolated.  y[k] = normalised, derotated
+// sample k (0 outside the window, as osmo_cxvec_convolve treats it); with a fractional offset of more
+// than 0.1 sample the symbol is the 21-tap sinc interpolation sum_j sinc(pi*((j-10)+frac)) * y[q+10-j].
+__device__ __forceinline__ float2 norm_rot_sample(const float2 *__restrict__ x, int L, int k, const Norm &nm, float fs)
+{
+	if (k < 0 || k >= L)
+		return make_float2(0.0f, 0.0f);
+	const float2 v = __ldg(&x[k]);
+	const float2 e = sincos_acc(fs * (float)k);
+	const float yr = (v.x - nm.ar) * nm.inv_sd, yi = (v.y - nm.ai) * nm.inv_sd;
+	return make_float2(yr * e.x - yi * e.y, yr * e.y + yi * e.x);
+}
+
+__device__ float2 lowsps_symbol(const float2 *__restrict__ x, int L, int q, bool interp, float frac, const Norm &nm, float fs)
+{
+	if (!interp)
+		return norm_rot_sample(x, L, q, nm, fs);
+	float sr = 0.0f, si = 0.0f;
+#pragma unroll 1
+	for (int j = 0; j < 21; j++) {
+		const float xa = PI_F * ((float)(j - 10) + frac);
+		const float tap = (xa >= 0.01f || xa <= -0.01f) ? sinf(xa) / xa : 1.0f;
+		const float2 y = norm_rot_sample(x, L, q + 10 - j, nm, fs);
+		sr = fmaf(tap, y.x, sr);
+		si = fmaf(tap, y.y, si);
+	}
+	return make_float2(sr, si);
 }
 
 // ---- kernel ---------------------------------------------------------------------------------------
@@ -584,8 +613,11 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 			continue;
 		}
 
-		// symbol i sits at sample i*sps + d (sps >= 4 path of _gmr1_pi4cxpsk_align, :286-297)
+		// symbol i sits at sample i*sps + d (sps >= 4 path of _gmr1_pi4cxpsk_align, :286-297); for
+		// sps < 4 (SPS == -1) the fractional part is interpolated when it exceeds 0.1 sample (:298-343)
 		const int d = (int)roundf(toa);
+		const float ofs_frac = toa - (float)d;
+		const bool interp = SPS < 0 && fabsf(ofs_frac) > 0.1f;
 		auto sample_of = [&](int i) {
 			const int q = i * sps + d;     // d >= -1; index -1 would read before the window: clamp
 			return min(max(q, 0), L - 1);
@@ -600,12 +632,18 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 		for (int t0 = 0; t0 < ntr; t0 += 32) {
 			const int t = t0 + lane;
 			if (t < ntr) {
-				const int pos = ft.t_pos[sync_id][t], q = sample_of(pos);
-				const float2 v = __ldg(&x[q]);
-				const float2 e = sincos_acc(fs * (float)q);
-				const float cs = e.x, sn = e.y;
-				const float yr = (v.x - nm.ar) * nm.inv_sd, yi = (v.y - nm.ai) * nm.inv_sd;
-				const float2 z = mul_conj_sym(ft.t_sym[sync_id][t], make_float2(yr * cs - yi * sn, yr * sn + yi * cs));
+				const int pos = ft.t_pos[sync_id][t];
+				float2 y;
+				if (SPS < 0) {
+					y = lowsps_symbol(x, L, pos * sps + d, interp, ofs_frac, nm, fs);
+				} else {
+					const int q = sample_of(pos);
+					const float2 v = __ldg(&x[q]);
+					const float2 e = sincos_acc(fs * (float)q);
+					const float yr = (v.x - nm.ar) * nm.inv_sd, yi = (v.y - nm.ai) * nm.inv_sd;
+					y = make_float2(yr * e.x - yi * e.y, yr * e.y + yi * e.x);
+				}
+				const float2 z = mul_conj_sym(ft.t_sym[sync_id][t], y);
 				sm.zbuf[t] = z;
 				if (t0 == 0) {
 					z0 = z;
@@ -669,10 +707,18 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 		const int nds = ft.n_dsym;
 		const bool eb_even = (((uintptr_t)eb) & 1) == 0;
 		for (int t = lane; t < nds; t += 32) {
-			const int i = ft.d_pos[t], q = sample_of(i);
-			const float2 v = __ldg(&x[q]);
-			const float th = fast_atan2f_inl(v.y - nm.ai, v.x - nm.ar);
-			const float a1 = fs * (float)q;
+			const int i = ft.d_pos[t];
+			float th, a1;
+			if (SPS < 0) {           // interpolated symbol already carries the derotation
+				const float2 z = lowsps_symbol(x, L, i * sps + d, interp, ofs_frac, nm, fs);
+				th = fast_atan2f_inl(z.y, z.x);
+				a1 = 0.0f;
+			} else {
+				const int q = sample_of(i);
+				const float2 v = __ldg(&x[q]);
+				th = fast_atan2f_inl(v.y - nm.ai, v.x - nm.ar);
+				a1 = fs * (float)q;
+			}
 			const float a2 = (-ferr) * (float)i;
 			double svd = fma((double)th + (double)a1 + (double)a2, inv_dd, c0);
 			svd -= period * rint(svd * inv_period);        // -> [-period/2, period/2]
@@ -717,7 +763,7 @@ cudaError_t launch_demod(const DemodArgs &a, const BurstTab *d_bts, const BurstT
 	if (maxlen != minlen)
 		return cudaErrorInvalidValue;      // detect needs length-compatible burst types
 	const int w = a.win_len - maxlen * a.sps + 1;
-	if (w < 1 || a.sps < 4 || a.sps > 16)
+	if (w < 1 || a.sps < 1 || a.sps > 16)
 		return cudaErrorInvalidValue;
 	// union of the intervals the training-sequence search reads, over all types / sequences / chunks
 	Regions rg;
@@ -776,9 +822,10 @@ cudaError_t launch_demod(const DemodArgs &a, const BurstTab *d_bts, const BurstT
 	}
 	if (dev >= 64 || attr_set[dev] < smem) {
 		cudaError_t e = cudaSuccess;
-		const void *fns[4] = {(const void *)demod_kernel<0, 4>, (const void *)demod_kernel<0, 0>,
-		                      (const void *)demod_kernel<1, 4>, (const void *)demod_kernel<1, 0>};
-		for (int i = 0; i < 4 && e == cudaSuccess; i++)
+		const void *fns[5] = {(const void *)demod_kernel<0, 4>, (const void *)demod_kernel<0, 0>,
+		                      (const void *)demod_kernel<1, 4>, (const void *)demod_kernel<1, 0>,
+		                      (const void *)demod_kernel<0, -1>};
+		for (int i = 0; i < 5 && e == cudaSuccess; i++)
 			e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if (e != cudaSuccess)
 			return e;
@@ -804,7 +851,9 @@ cudaError_t launch_demod(const DemodArgs &a, const BurstTab *d_bts, const BurstT
 	int grid = (a.n + DM_WARPS - 1) / DM_WARPS;
 	if (grid > sms * per_sm)
 		grid = sms * per_sm;
-	if (mode == 0 && a.sps == 4)
+	if (mode == 0 && a.sps < 4)
+		demod_kernel<0, -1><<<grid, DM_WARPS * 32, smem, st>>>(a, d_bts, n_bt, (int)wb, rg);
+	else if (mode == 0 && a.sps == 4)
 		demod_kernel<0, 4><<<grid, DM_WARPS * 32, smem, st>>>(a, d_bts, n_bt, (int)wb, rg);
 	else if (mode == 0)
 		demod_kernel<0, 0><<<grid, DM_WARPS * 32, smem, st>>>(a, d_bts, n_bt, (int)wb, rg);
