@@ -4,8 +4,8 @@ on B200, config 2 of BASELINE.json: batched BCCH / DC6(CCCH) bursts, 1024 ARFCNs
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-One "step" = one pass of the hot path over the whole batch (4 kernel launches: demod BCCH, decode
-BCCH, demod DC6, decode CCCH).  `value` = bursts/s with the IQ resident in HBM; `e2e` = the same
+One "step" = one pass of the hot path over the whole batch: FCCH acquisition of every ARFCN (rough
+over a 330 ms window + fine), then demod BCCH, decode BCCH, demod DC6, decode CCCH (6 kernel launches).  `value` = bursts/s with the IQ resident in HBM; `e2e` = the same
 through the C ABI with HOST (pinned) IQ in and host L2/CRC out, copies inside the timed region.
 Multi-GPU: ARFCNs are independent, each rank owns its own 1024 ARFCNs (weak scaling), no data-path
 collective; torch.distributed is used only for the barrier and the max-over-ranks of the time.
@@ -35,6 +35,7 @@ CHAN = {"bcch": 0, "dc6": 1}                      # gmr1b200_xcch_encode_batch c
 # algorithmic bytes per burst of the demod kernel: window in + ebits + 16 B metadata out
 DEMOD_BYTES = {k: 8 * (LEN[k] * SPS + WIN[k]) + EBITS[k] + 16 for k in WIN}
 SNR_GRID = np.array([6.0, 10.0, 15.0, 30.0], np.float32)
+FCCH_WIN = (330 * 23400 * SPS) // 1000            # 30 888 samples
 
 
 def wlen(kind):
@@ -209,8 +210,43 @@ class Workload:
             self.sid[kind] = torch.empty(n, dtype=torch.int32, device=dev)
             self.toa[kind] = torch.empty(n, dtype=torch.float32, device=dev)
 
+        # one 330 ms FCCH search window per ARFCN (gmr1_rx.c:612): noise + one dual chirp at a random
+        # offset with up to +-1 kHz of carrier offset; acquired once per step (rough + fine)
+        self.n_arfcn = n_arfcn
+        rng = np.random.default_rng(seed + 99)
+        self.fcch_pos = rng.integers(600, FCCH_WIN - 1200, n_arfcn)
+        self.fcch_cfo = rng.uniform(-0.27, 0.27, n_arfcn)
+        t = (np.arange(117 * SPS) / SPS) - 58.5
+        chirp = np.sqrt(2.0) * np.cos(0.32 * 2 * np.pi / 117 * t * t)
+        fw = torch.empty((n_arfcn, FCCH_WIN, 2), dtype=torch.float32, device=dev)
+        for lo in range(0, n_arfcn, 128):
+            hi = min(n_arfcn, lo + 128)
+            x = 0.3 * (rng.standard_normal((hi - lo, FCCH_WIN)) + 1j * rng.standard_normal((hi - lo, FCCH_WIN)))
+            for i in range(lo, hi):
+                k = np.arange(117 * SPS)
+                x[i - lo, self.fcch_pos[i]:self.fcch_pos[i] + 117 * SPS] += chirp * np.exp(1j * self.fcch_cfo[i] * k / SPS)
+            fw[lo:hi] = torch.from_numpy(np.ascontiguousarray(x.astype(np.complex64)).view(np.float32).reshape(hi - lo, FCCH_WIN, 2)).to(dev)
+        self.fcch_iq = fw
+        self.fcch_toa = torch.empty(n_arfcn, dtype=torch.int32, device=dev)
+        self.fcch_fine_ofs = torch.empty(n_arfcn, dtype=torch.int64, device=dev)
+        self.fcch_fine_toa = torch.empty(n_arfcn, dtype=torch.int32, device=dev)
+        self.fcch_ferr = torch.empty(n_arfcn, dtype=torch.float32, device=dev)
+        self.fcch_base = torch.arange(n_arfcn, dtype=torch.int64, device=dev) * FCCH_WIN
+
     def total(self):
         return self.n["bcch"] + self.n["dc6"]
+
+    def fcch(self, stream, torch_stream):
+        """FCCH acquisition of every ARFCN: rough TOA over the 330 ms window, then the fine timing /
+        frequency estimate on the 117-symbol burst found (fcch_single_init, gmr1_rx.c:606-639)"""
+        n = self.n_arfcn
+        self.L.call("gmr1b200_fcch_rough_batch", 0, self.fcch_iq, n * FCCH_WIN, None, FCCH_WIN, FCCH_WIN, SPS,
+                    None, 0.0, self.fcch_toa, None, n, stream)
+        with self.torch.cuda.stream(torch_stream):     # window offsets for the fine stage: base + clamp(toa)
+            self.torch.add(self.fcch_base, self.fcch_toa.clamp(0, FCCH_WIN - 117 * SPS).to(self.torch.int64),
+                           out=self.fcch_fine_ofs)
+        self.L.call("gmr1b200_fcch_fine_batch", 0, self.fcch_iq, n * FCCH_WIN, self.fcch_fine_ofs, 0, SPS,
+                    None, 0.0, self.fcch_fine_toa, self.fcch_ferr, n, stream)
 
     def demod(self, kind, stream, iq=None, lo=0, hi=None, eb=None):
         hi = self.n[kind] if hi is None else hi
@@ -265,6 +301,13 @@ def run_gpu_arm(args):
         runs demod -> decode on its own stream so that the decode (integer-ALU-bound) of one half
         shares the SMs with the demod of the other; the per-kernel event timers are only meaningful
         with --streams 1 (serial), which is how the roofline pass below is run."""
+        if timers is not None:
+            f0, f1 = ev(), ev()
+            f0.record(stream)
+        W.fcch(stream.cuda_stream, stream)
+        if timers is not None:
+            f1.record(stream)
+            timers.append(("fcch", f0, f1))
         for kind, st in (("bcch", stream), ("dc6", stream2 if (two and timers is None) else stream)):
             if timers is not None:
                 a, b = ev(), ev()
@@ -315,6 +358,9 @@ def run_gpu_arm(args):
     host_crc = {k: torch.empty(W.n[k], dtype=torch.int32).pin_memory() for k in W.iq}
     for k in W.iq:
         host_iq[k].copy_(W.iq[k])
+    host_fcch = torch.empty(W.fcch_iq.shape, dtype=torch.float32).pin_memory()
+    host_fcch.copy_(W.fcch_iq)
+    host_fcch_out = torch.empty((2, W.n_arfcn), dtype=torch.float32).pin_memory()
     torch.cuda.synchronize()
     jobs = []
     for k in ("bcch", "dc6"):
@@ -326,6 +372,15 @@ def run_gpu_arm(args):
     def e2e_thread(t):
         torch.cuda.set_device(local_rank)
         s = streams[t].cuda_stream
+        if t == 0:
+            # FCCH windows of every ARFCN: host -> device, acquire, TOA / frequency error back to the host
+            with torch.cuda.stream(streams[0]):
+                W.fcch_iq.copy_(host_fcch, non_blocking=True)
+            W.fcch(s, streams[0])
+            with torch.cuda.stream(streams[0]):
+                host_fcch_out[0].copy_((W.fcch_toa + W.fcch_fine_toa).to(torch.float32), non_blocking=True)
+                host_fcch_out[1].copy_(W.fcch_ferr, non_blocking=True)
+            streams[0].synchronize()
         for k, lo, hi in jobs[t::n_thr]:
             # host IQ -> (library stages it) -> demod -> ebits stay on the device -> decode -> host L2/CRC
             W.demod(k, s, iq=host_iq[k][lo:hi], lo=lo, hi=hi)
@@ -369,6 +424,16 @@ def run_gpu_arm(args):
         return
 
     # ---------------- roofline of the dominant kernel (demod), timed live with CUDA events
+    fcc = [(k, a, b) for k, a, b in timers if k == "fcch"]
+    timers = [t for t in timers if t[0] != "fcch"]
+    fcch_ms = sum(a.elapsed_time(b) for _, a, b in fcc) / max(1, len(fcc))
+    toa_err = (W.fcch_toa.cpu().numpy() + W.fcch_fine_toa.cpu().numpy() - W.fcch_pos)
+    ferr_hz = W.fcch_ferr.cpu().numpy() * 23400.0 / (2 * np.pi) - W.fcch_cfo * 23400.0 / (2 * np.pi)
+    fcch = {"acquisitions_per_step": W.n_arfcn, "ms_per_step": fcch_ms,
+            "acquisitions_per_s": W.n_arfcn / (fcch_ms * 1e-3),
+            "window_bytes": FCCH_WIN * 8, "achieved_gbs": W.n_arfcn * (FCCH_WIN * 8 + 3752) / (fcch_ms * 1e-3) / 1e9,
+            "found_frac": float((np.abs(toa_err) <= 2).mean()), "freq_err_rms_hz": float(np.sqrt((ferr_hz ** 2).mean())),
+            "what": "gmr1_fcch_rough over a 330 ms window + gmr1_fcch_fine, once per ARFCN per step"}
     dem = [(k, a, b) for k, a, b in timers if not k.startswith("decode_")]
     dec = [(k[7:], a, b) for k, a, b in timers if k.startswith("decode_")]
     dem_ms = sum(a.elapsed_time(b) for _, a, b in dem)
@@ -432,18 +497,20 @@ def run_gpu_arm(args):
         "config": {"workload": "config2: batched BCCH + DC6/CCCH bursts (pi/4-CQPSK demod + K5 r1/2 Viterbi + CRC16), "
                                f"{args.arfcns} ARFCNs x {args.bursts_per_arfcn} bursts per GPU, sps 4",
                    "bursts_per_gpu": nb, "iq_bytes_per_gpu": int(sum(W.iq[k].numel() * 4 for k in W.iq)),
+                   "fcch_iq_bytes_per_gpu": int(W.fcch_iq.numel() * 4),
                    "l2_flush": "inputs (2.1 GB) larger than L2", "esn0_db": [6, 10, 15, 30],
                    "parallelism": f"arfcn-sharded x{world}, no collective",
                    "streams_per_gpu": args.streams},
         "crc_ok_frac": crc_ok,
         "e2e": {"value": nb * world / (e2e_ms * 1e-3), "unit": "bursts/s",
-                "h2d_bytes_per_step": int(sum(W.iq[k].numel() * 4 for k in W.iq)),
-                "d2h_bytes_per_step": int(nb * 28), "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(sum(W.iq[k].numel() * 4 for k in W.iq) + W.fcch_iq.numel() * 4),
+                "d2h_bytes_per_step": int(nb * 28 + W.n_arfcn * 8), "ms_per_step": e2e_ms,
                 "how": f"{len(jobs)} chunks on {n_thr} host threads/streams through gmr1b200_*_batch with pinned "
                        "host IQ in and host L2/CRC out", "same_results_as_device_path": e2e_same},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "viterbi": viterbi,
+        "fcch": fcch,
         "cpu_baseline": cpu,
         "clocks": sampler.summary(),
     }
