@@ -53,6 +53,26 @@ def burst_params(n, kind, seed):
     )
 
 
+def fcch_windows(n_arfcn, seed, lo=0, hi=None):
+    """One 330 ms FCCH search window per ARFCN (gmr1_rx.c:612): noise + one dual chirp at a random offset with
+    up to +-1 kHz of carrier offset.  Returns (pos, cfo) for all ARFCNs and a generator of (lo, hi, complex64)."""
+    rng = np.random.default_rng(seed)
+    pos = rng.integers(600, FCCH_WIN - 1200, n_arfcn)
+    cfo = rng.uniform(-0.27, 0.27, n_arfcn)
+    k = np.arange(117 * SPS)
+    t = k / SPS - 58.5
+    chirp = np.sqrt(2.0) * np.cos(0.32 * 2 * np.pi / 117 * t * t)
+
+    def blocks():
+        for b0 in range(0, n_arfcn, 128):
+            b1 = min(n_arfcn, b0 + 128)
+            x = 0.3 * (rng.standard_normal((b1 - b0, FCCH_WIN)) + 1j * rng.standard_normal((b1 - b0, FCCH_WIN)))
+            for i in range(b0, b1):
+                x[i - b0, pos[i]:pos[i] + 117 * SPS] += chirp * np.exp(1j * cfo[i] * k / SPS)
+            yield b0, b1, x.astype(np.complex64)
+    return pos, cfo, blocks()
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU reference arm (also the cpu_baseline leg): the ONLY place bench.py executes oracle/
 # ------------------------------------------------------------------------------------------------
@@ -62,6 +82,16 @@ def _cpu_worker(job):
     import oracle_lib
     o = oracle_lib.load()
     x = np.load(path, mmap_mode="r")
+    if kind == "fcch":                      # rough + fine acquisition, as Workload.fcch() does on the GPU
+        out = np.zeros((hi - lo, 2), np.float64)
+        t0 = time.perf_counter()
+        for i in range(lo, hi):
+            w = np.array(x[i])
+            _, toa = o.fcch_rough(w, SPS, 0.0)
+            a = min(max(toa, 0), FCCH_WIN - 117 * SPS)
+            _, ftoa, ferr = o.fcch_fine(w[a:a + 117 * SPS], SPS, 0.0)
+            out[i - lo] = (toa + ftoa, ferr)
+        return lo, out, None, time.perf_counter() - t0, o.kind
     chan = "bcch" if kind == "bcch" else "ccch"
     l2 = np.zeros((hi - lo, 24), np.uint8)
     crc = np.zeros(hi - lo, np.int32)
@@ -78,7 +108,10 @@ def cpu_reference_pass(files, cores):
     jobs = []
     for kind, (path, n) in files.items():
         per = max(1, (n + cores - 1) // cores)
+        if kind == "fcch":
+            per = max(1, min(per, 8))           # short jobs, scheduled first, so they spread over the cores
         jobs += [(path, kind, lo, min(n, lo + per)) for lo in range(0, n, per)]
+    jobs.sort(key=lambda j: j[1] != "fcch")
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
         pool.map(_cpu_noop, range(cores))                       # start the workers outside the timing
@@ -88,13 +121,20 @@ def cpu_reference_pass(files, cores):
     out = {}
     okind = res[0][4]
     for kind, (path, n) in files.items():
+        if kind == "fcch":
+            acq = np.zeros((n, 2), np.float64)
+            for (p, k, lo, hi), r in zip(jobs, res):
+                if k == kind:
+                    acq[lo:hi] = r[1]
+            out[kind] = acq
+            continue
         l2 = np.zeros((n, 24), np.uint8)
         crc = np.zeros(n, np.int32)
         for (p, k, lo, hi), r in zip(jobs, res):
             if k == kind:
                 l2[lo:hi], crc[lo:hi] = r[1], r[2]
         out[kind] = (l2, crc)
-    return sum(n for _, n in files.values()), wall, out, okind
+    return sum(n for k, (_, n) in files.items() if k != "fcch"), wall, out, okind
 
 
 def _cpu_noop(i):
@@ -128,6 +168,11 @@ def run_reference_arm(args):
         path = os.path.join(shm_dir(), f"gmr1_bench_ref_{kind}_{os.getpid()}.npy")
         np.save(path, np.concatenate(xs))
         files[kind] = (path, per_kind)
+    n_f = max(1, 2 * per_kind // 256)               # one FCCH acquisition per 256 bursts, as in config 2
+    _, _, blocks = fcch_windows(n_f, 176)
+    path = os.path.join(shm_dir(), f"gmr1_bench_ref_fcch_{os.getpid()}.npy")
+    np.save(path, np.concatenate([x for _, _, x in blocks]))
+    files["fcch"] = (path, n_f)
     times = []
     for step in range(args.warmup + args.steps):
         nb, wall, _, okind = cpu_reference_pass(files, cores)
@@ -142,9 +187,9 @@ def run_reference_arm(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic",
         "config": {"workload": "config2: BCCH + DC6/CCCH pi/4-CQPSK demod + K5 r1/2 Viterbi + CRC16, sps 4",
-                   "bursts_per_step": nb, "sample": f"{per_kind} BCCH + {per_kind} DC6 bursts (numpy generator)"},
+                   "bursts_per_step": nb, "sample": f"{per_kind} BCCH + {per_kind} DC6 bursts + {n_f} FCCH windows (numpy generator)"},
         "cpu_baseline": {"value": val, "unit": "bursts/s", "cores": cores, "kind": okind,
-                         "sample": f"{nb} bursts per step, one process per core"},
+                         "sample": f"{nb} bursts + {n_f} FCCH acquisitions per step, one process per core"},
         "e2e": {"value": val, "unit": "bursts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -213,19 +258,10 @@ class Workload:
         # one 330 ms FCCH search window per ARFCN (gmr1_rx.c:612): noise + one dual chirp at a random
         # offset with up to +-1 kHz of carrier offset; acquired once per step (rough + fine)
         self.n_arfcn = n_arfcn
-        rng = np.random.default_rng(seed + 99)
-        self.fcch_pos = rng.integers(600, FCCH_WIN - 1200, n_arfcn)
-        self.fcch_cfo = rng.uniform(-0.27, 0.27, n_arfcn)
-        t = (np.arange(117 * SPS) / SPS) - 58.5
-        chirp = np.sqrt(2.0) * np.cos(0.32 * 2 * np.pi / 117 * t * t)
+        self.fcch_pos, self.fcch_cfo, blocks = fcch_windows(n_arfcn, seed + 99)
         fw = torch.empty((n_arfcn, FCCH_WIN, 2), dtype=torch.float32, device=dev)
-        for lo in range(0, n_arfcn, 128):
-            hi = min(n_arfcn, lo + 128)
-            x = 0.3 * (rng.standard_normal((hi - lo, FCCH_WIN)) + 1j * rng.standard_normal((hi - lo, FCCH_WIN)))
-            for i in range(lo, hi):
-                k = np.arange(117 * SPS)
-                x[i - lo, self.fcch_pos[i]:self.fcch_pos[i] + 117 * SPS] += chirp * np.exp(1j * self.fcch_cfo[i] * k / SPS)
-            fw[lo:hi] = torch.from_numpy(np.ascontiguousarray(x.astype(np.complex64)).view(np.float32).reshape(hi - lo, FCCH_WIN, 2)).to(dev)
+        for lo, hi, x in blocks:
+            fw[lo:hi] = torch.from_numpy(x.view(np.float32).reshape(hi - lo, FCCH_WIN, 2)).to(dev)
         self.fcch_iq = fw
         self.fcch_toa = torch.empty(n_arfcn, dtype=torch.int32, device=dev)
         self.fcch_fine_ofs = torch.empty(n_arfcn, dtype=torch.int64, device=dev)
@@ -473,20 +509,30 @@ def run_gpu_arm(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        m = min(W.n["bcch"], max(1024, 512 * cores))
+        m = min(W.n["bcch"], max(1024, 4096 * cores))      # ~20 core-seconds of reference C work
+        n_f = min(W.n_arfcn, max(1, 2 * m // args.bursts_per_arfcn))
         files = {}
         for k in ("bcch", "dc6"):
             x = W.iq[k][:m].cpu().numpy().view(np.complex64).reshape(m, wlen(k))
             path = os.path.join(shm_dir(), f"gmr1_bench_{k}_{os.getpid()}.npy")
             np.save(path, x)
             files[k] = (path, m)
+        path = os.path.join(shm_dir(), f"gmr1_bench_fcch_{os.getpid()}.npy")
+        np.save(path, W.fcch_iq[:n_f].cpu().numpy().view(np.complex64).reshape(n_f, FCCH_WIN))
+        files["fcch"] = (path, n_f)
         nbc, wall, out, okind = cpu_reference_pass(files, cores)
         for path, _ in files.values():
             os.unlink(path)
+        acq = out.pop("fcch")
+        g_toa = (W.fcch_toa + W.fcch_fine_toa)[:n_f].cpu().numpy()
+        fcch["toa_identical_to_reference"] = bool((acq[:, 0] == g_toa).all())
+        fcch["freq_err_max_abs_diff_vs_reference_rad_per_sym"] = float(
+            np.abs(acq[:, 1] - W.fcch_ferr[:n_f].cpu().numpy()).max())
         same = all(bool((out[k][0] == W.l2[k][:m].cpu().numpy()).all()) and
                    bool((out[k][1] == W.crc[k][:m].cpu().numpy()).all()) for k in out)
         cpu = {"value": nbc / wall, "unit": "bursts/s", "cores": cores, "kind": okind,
-               "sample": f"first {m} BCCH + {m} DC6 bursts of the GPU workload, one process per core, {wall:.2f} s",
+               "sample": f"first {m} BCCH + {m} DC6 bursts and {n_f} FCCH windows of the GPU workload, one process "
+                         f"per core, {wall:.2f} s wall",
                "l2_crc_identical_to_gpu": same}
 
     line = {
