@@ -264,10 +264,8 @@ class Workload:
             fw[lo:hi] = torch.from_numpy(x.view(np.float32).reshape(hi - lo, FCCH_WIN, 2)).to(dev)
         self.fcch_iq = fw
         self.fcch_toa = torch.empty(n_arfcn, dtype=torch.int32, device=dev)
-        self.fcch_fine_ofs = torch.empty(n_arfcn, dtype=torch.int64, device=dev)
-        self.fcch_fine_toa = torch.empty(n_arfcn, dtype=torch.int32, device=dev)
+        self.fcch_align = torch.empty(n_arfcn, dtype=torch.int32, device=dev)
         self.fcch_ferr = torch.empty(n_arfcn, dtype=torch.float32, device=dev)
-        self.fcch_base = torch.arange(n_arfcn, dtype=torch.int64, device=dev) * FCCH_WIN
 
     def total(self):
         return self.n["bcch"] + self.n["dc6"]
@@ -276,13 +274,8 @@ class Workload:
         """FCCH acquisition of every ARFCN: rough TOA over the 330 ms window, then the fine timing /
         frequency estimate on the 117-symbol burst found (fcch_single_init, gmr1_rx.c:606-639)"""
         n = self.n_arfcn
-        self.L.call("gmr1b200_fcch_rough_batch", 0, self.fcch_iq, n * FCCH_WIN, None, FCCH_WIN, FCCH_WIN, SPS,
-                    None, 0.0, self.fcch_toa, None, n, stream)
-        with self.torch.cuda.stream(torch_stream):     # window offsets for the fine stage: base + clamp(toa)
-            self.torch.add(self.fcch_base, self.fcch_toa.clamp(0, FCCH_WIN - 117 * SPS).to(self.torch.int64),
-                           out=self.fcch_fine_ofs)
-        self.L.call("gmr1b200_fcch_fine_batch", 0, self.fcch_iq, n * FCCH_WIN, self.fcch_fine_ofs, 0, SPS,
-                    None, 0.0, self.fcch_fine_toa, self.fcch_ferr, n, stream)
+        self.L.call("gmr1b200_fcch_acquire_batch", 0, self.fcch_iq, n * FCCH_WIN, None, FCCH_WIN, FCCH_WIN, SPS,
+                    self.fcch_toa, self.fcch_align, self.fcch_ferr, n, stream)
 
     def demod(self, kind, stream, iq=None, lo=0, hi=None, eb=None):
         hi = self.n[kind] if hi is None else hi
@@ -414,7 +407,7 @@ def run_gpu_arm(args):
                 W.fcch_iq.copy_(host_fcch, non_blocking=True)
             W.fcch(s, streams[0])
             with torch.cuda.stream(streams[0]):
-                host_fcch_out[0].copy_((W.fcch_toa + W.fcch_fine_toa).to(torch.float32), non_blocking=True)
+                host_fcch_out[0].copy_(W.fcch_align.to(torch.float32), non_blocking=True)
                 host_fcch_out[1].copy_(W.fcch_ferr, non_blocking=True)
             streams[0].synchronize()
         for k, lo, hi in jobs[t::n_thr]:
@@ -463,7 +456,7 @@ def run_gpu_arm(args):
     fcc = [(k, a, b) for k, a, b in timers if k == "fcch"]
     timers = [t for t in timers if t[0] != "fcch"]
     fcch_ms = sum(a.elapsed_time(b) for _, a, b in fcc) / max(1, len(fcc))
-    toa_err = (W.fcch_toa.cpu().numpy() + W.fcch_fine_toa.cpu().numpy() - W.fcch_pos)
+    toa_err = W.fcch_align.cpu().numpy() - W.fcch_pos
     ferr_hz = W.fcch_ferr.cpu().numpy() * 23400.0 / (2 * np.pi) - W.fcch_cfo * 23400.0 / (2 * np.pi)
     fcch = {"acquisitions_per_step": W.n_arfcn, "ms_per_step": fcch_ms,
             "acquisitions_per_s": W.n_arfcn / (fcch_ms * 1e-3),
@@ -524,7 +517,7 @@ def run_gpu_arm(args):
         for path, _ in files.values():
             os.unlink(path)
         acq = out.pop("fcch")
-        g_toa = (W.fcch_toa + W.fcch_fine_toa)[:n_f].cpu().numpy()
+        g_toa = W.fcch_align[:n_f].cpu().numpy()
         fcch["toa_identical_to_reference"] = bool((acq[:, 0] == g_toa).all())
         fcch["freq_err_max_abs_diff_vs_reference_rad_per_sym"] = float(
             np.abs(acq[:, 1] - W.fcch_ferr[:n_f].cpu().numpy()).max())

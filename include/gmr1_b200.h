@@ -273,6 +273,15 @@ int gmr1b200_fcch_fine_batch(int fcch_type, const float *iq, int64_t iq_len,
                              const float *freq_shift, float freq_shift0,
                              int32_t *toa, float *freq_error, int n, void *stream);
 
+/* replaces fcch_single_init, src/gmr1_rx.c:606-639, for n channels in two launches with no host round
+ * trip: gmr1_fcch_rough (freq_shift 0) over each search window, then gmr1_fcch_fine (freq_shift 0) on the
+ * burst_len*sps samples at the rough TOA.  align [n] = rough + fine TOA in samples from the window start
+ * (what the reference accumulates into chan_desc.align), freq_error [n] rad/symbol; rough_toa [n] may be
+ * NULL.  win_ofs / win_stride / win_len describe the SEARCH windows. */
+int gmr1b200_fcch_acquire_batch(int fcch_type, const float *iq, int64_t iq_len,
+                                const int64_t *win_ofs, int64_t win_stride, int win_len, int sps,
+                                int32_t *rough_toa, int32_t *align, float *freq_error, int n, void *stream);
+
 /* replaces gmr1_fcch_snr, src/sdr/fcch.c:643 (sdr/fcch.h:59-61): snr [n] */
 int gmr1b200_fcch_snr_batch(int fcch_type, const float *iq, int64_t iq_len,
                             const int64_t *win_ofs, int64_t win_stride, int sps,

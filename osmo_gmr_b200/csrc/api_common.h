@@ -70,6 +70,9 @@ public:
 		return (T *)d;
 	}
 
+	// device-only scratch that lives until finish()
+	template <class T> T *tmp(size_t count) { return failed_ ? nullptr : (T *)scratch(count * sizeof(T)); }
+
 	bool failed() const { return failed_; }
 	int rc() const { return rc_; }
 

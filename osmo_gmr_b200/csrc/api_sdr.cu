@@ -228,6 +228,45 @@ int gmr1b200_fcch_fine_batch(int fcch_type, const float *iq, int64_t iq_len, con
 	                   toa, freq_error, nullptr, n, stream);
 }
 
+int gmr1b200_fcch_acquire_batch(int fcch_type, const float *iq, int64_t iq_len, const int64_t *win_ofs,
+                                int64_t win_stride, int win_len, int sps, int32_t *rough_toa, int32_t *align,
+                                float *freq_error, int n, void *stream)
+{
+	if (!align || !freq_error)
+		return set_err(-EINVAL, "fcch_acquire_batch: NULL output");
+	FcchArgs a = {};
+	a.iq = (const float2 *)iq; a.ofs = win_ofs; a.stride = win_stride; a.n = n; a.win_len = win_len; a.sps = sps;
+	a.toa = rough_toa;
+	Stage s(stream);
+	int rc = fcch_common(fcch_type, a, s, iq_len, "fcch_acquire_batch: bad argument");
+	if (rc)
+		return rc;
+	if (win_len / sps < a.len)
+		return set_err(-EINVAL, "fcch_acquire_batch: window shorter than the FCCH burst");
+	if (n == 0)
+		return 0;
+	if (!a.toa)
+		a.toa = s.tmp<int32_t>((size_t)n);
+	FcchArgs f = a;                      // fine stage on the burst the rough stage found (gmr1_rx.c:626-636)
+	f.rel = a.toa;
+	f.rel_max = win_len - a.len * sps;
+	f.rel_add = 1;
+	f.win_len = a.len * sps;
+	f.toa = s.out(align, (size_t)n);
+	f.freq_error = s.out(freq_error, (size_t)n);
+	cudaError_t e = cudaSuccess;
+	if (!s.failed()) {
+		e = launch_fcch_rough(a, (cudaStream_t)stream);
+		if (e == cudaSuccess) {
+			g_launches.fetch_add(1);
+			e = launch_fcch_fine(f, 0, (cudaStream_t)stream);
+			if (e == cudaSuccess)
+				g_launches.fetch_add(1);
+		}
+	}
+	return s.finish(e, "fcch_acquire kernels");
+}
+
 int gmr1b200_fcch_snr_batch(int fcch_type, const float *iq, int64_t iq_len, const int64_t *win_ofs,
                             int64_t win_stride, int sps, const float *freq_shift, float freq_shift0,
                             float *snr, int n, void *stream)

@@ -51,20 +51,35 @@ __device__ __forceinline__ void block_sum3(float &a, float &b, float &c, float *
 	a = warp_sum_f(a); b = warp_sum_f(b); c = warp_sum_f(c);
 }
 
-// padded index: one spare slot every 8 so that threads 8 outputs apart hit different banks
-__device__ __forceinline__ int pad8(int i) { return i + (i >> 3); }
+// Shared layout of the decimated window: interleaved (re, im), every group of 8 samples (16 floats)
+// padded to 20 floats.  A thread owns 8 consecutive outputs and pulls whole groups with four
+// LDS.128; lanes are 20 words apart, so each quarter-warp covers all 32 banks exactly once.
+static constexpr int FR_GRP = 20;
+__device__ __forceinline__ int widx(int i) { return (i >> 3) * FR_GRP + (i & 7) * 2; }
 
-__global__ void __launch_bounds__(FR_T) fcch_rough_kernel(const FcchArgs a)
+// (cr, ci) += r * (wr, wi): one packed FFMA2 on sm_100a
+__device__ __forceinline__ void fma2(float2 &c, float r, const float2 w)
+{
+	unsigned long long cc = *reinterpret_cast<unsigned long long *>(&c);
+	const float2 rr2 = make_float2(r, r);
+	asm("fma.rn.f32x2 %0, %1, %2, %0;"
+	    : "+l"(cc)
+	    : "l"(*reinterpret_cast<const unsigned long long *>(&rr2)), "l"(*reinterpret_cast<const unsigned long long *>(&w)));
+	c = *reinterpret_cast<float2 *>(&cc);
+}
+
+__global__ void __launch_bounds__(FR_T, 2) fcch_rough_kernel(const FcchArgs a)
 {
 	extern __shared__ __align__(16) uint8_t smem[];
 	const int tid = threadIdx.x, b = blockIdx.x;
 	const int sps = a.sps, L = a.win_len, len = a.len;
 	const int l = L / sps;                 // decimated length
 	const int nc = l - len + 1;            // correlation outputs
-	float *sre = (float *)smem;            // [pad8(l)+8] decimated, normalised samples (SoA)
-	float *sim = sre + pad8(l) + 8;
-	float *ref = sim + pad8(l) + 8;        // [len]
-	float *red = ref + ((len + 3) & ~3);   // [96] reduction scratch
+	const int lenp = (len + 7) & ~7;       // taps, zero-padded to whole groups
+	const int ng = (l + lenp + 15) >> 3;   // sample groups incl. the zero tail the padded taps touch
+	float *w   = (float *)smem;            // [ng * FR_GRP] decimated, normalised samples
+	float *ref = w + ng * FR_GRP;          // [lenp]
+	float *red = ref + lenp;               // [96] reduction scratch
 	float *en  = red + 96;                 // [nc] |corr|^2
 
 	const float2 *x = a.iq + (a.ofs ? a.ofs[b] : (int64_t)b * a.stride);
@@ -73,23 +88,36 @@ __global__ void __launch_bounds__(FR_T) fcch_rough_kernel(const FcchArgs a)
 	// dual-chirp reference at 1 sample/symbol (fcch.c:167-193)
 	{
 		const float phase_base = a.freq * 2.0f * PI_F / (float)len, halfpos = (float)len / 2.0f;
-		for (int i = tid; i < len; i += FR_T) {
+		for (int i = tid; i < lenp; i += FR_T) {
 			const float pos = (float)i - halfpos;
-			ref[i] = sqrtf(2.0f) * cosf(phase_base * (pos * pos));
+			ref[i] = i < len ? sqrtf(2.0f) * cosf(phase_base * (pos * pos)) : 0.0f;
 		}
 	}
+	for (int i = l + tid; i < ng * 8; i += FR_T) {
+		w[widx(i)] = 0.0f;
+		w[widx(i) + 1] = 0.0f;
+	}
 
-	// statistics over ALL samples (sig_normalize averages before decimating); keep every sps-th
+	// statistics over ALL samples (sig_normalize averages before decimating); keep every sps-th.
+	// (symbol, phase) of sample i are carried along instead of dividing by the runtime sps.
 	float sr = 0.0f, si = 0.0f, sq = 0.0f;
-	for (int i = tid; i < L; i += FR_T) {
-		const float2 v = __ldg(&x[i]);
-		sr += v.x;
-		si += v.y;
-		sq = fmaf(v.x, v.x, sq);
-		sq = fmaf(v.y, v.y, sq);
-		if (i % sps == 0 && i / sps < l) {
-			sre[pad8(i / sps)] = v.x;
-			sim[pad8(i / sps)] = v.y;
+	{
+		const int dq = FR_T / sps, dr = FR_T % sps;
+		int sym = tid / sps, ph = tid % sps;
+		for (int i = tid; i < L; i += FR_T) {
+			const float2 v = __ldg(&x[i]);
+			sr += v.x;
+			si += v.y;
+			sq = fmaf(v.x, v.x, sq);
+			sq = fmaf(v.y, v.y, sq);
+			if (ph == 0 && sym < l)
+				*reinterpret_cast<float2 *>(&w[widx(sym)]) = v;
+			sym += dq;
+			ph += dr;
+			if (ph >= sps) {
+				ph -= sps;
+				sym++;
+			}
 		}
 	}
 	block_sum3(sr, si, sq, red);
@@ -99,7 +127,8 @@ __global__ void __launch_bounds__(FR_T) fcch_rough_kernel(const FcchArgs a)
 	if (sd == 0.0f)
 		sd = 1.0f;
 	for (int i = tid; i < l; i += FR_T) {
-		float yr = (sre[pad8(i)] - ar) / sd, yi = (sim[pad8(i)] - ai) / sd;
+		float2 *p = reinterpret_cast<float2 *>(&w[widx(i)]);
+		float yr = (p->x - ar) / sd, yi = (p->y - ai) / sd;
 		if (freq_shift != 0.0f) {
 			float sn, cs;
 			sincosf(freq_shift * (float)i, &sn, &cs);
@@ -107,43 +136,51 @@ __global__ void __launch_bounds__(FR_T) fcch_rough_kernel(const FcchArgs a)
 			yi = yr * sn + yi * cs;
 			yr = tr;
 		}
-		sre[pad8(i)] = yr;
-		sim[pad8(i)] = yi;
+		*p = make_float2(yr, yi);
 	}
 	__syncthreads();
 
-	// sliding correlation: thread -> FR_TILE consecutive outputs, samples slide through registers
+	// sliding correlation: thread -> 8 consecutive outputs; the 8-sample register window slides one
+	// whole group per iteration (after tap u the slot u is refilled with sample u of the next group)
 	for (int m0 = tid * FR_TILE; m0 < nc; m0 += FR_T * FR_TILE) {
-		float cr[FR_TILE], ci[FR_TILE], wr[FR_TILE], wi[FR_TILE];
+		float2 c[FR_TILE], win[FR_TILE];
+		const float4 *gp = reinterpret_cast<const float4 *>(w + (m0 >> 3) * FR_GRP);
 #pragma unroll
-		for (int t = 0; t < FR_TILE; t++) {
-			cr[t] = ci[t] = 0.0f;
-			const int i = min(m0 + t, l - 1);
-			wr[t] = sre[pad8(i)];
-			wi[t] = sim[pad8(i)];
+		for (int q = 0; q < 4; q++) {
+			const float4 v = gp[q];
+			win[2 * q] = make_float2(v.x, v.y);
+			win[2 * q + 1] = make_float2(v.z, v.w);
+			c[2 * q] = c[2 * q + 1] = make_float2(0.0f, 0.0f);
 		}
-		for (int n0 = 0; n0 < len; n0 += FR_TILE) {
+		const float4 *rp = reinterpret_cast<const float4 *>(ref);
+#pragma unroll 1
+		for (int g = 0; g < (lenp >> 3); g++) {
+			gp += FR_GRP / 4;
+			float2 nxt[FR_TILE];
+			float r[FR_TILE];
+#pragma unroll
+			for (int q = 0; q < 4; q++) {
+				const float4 v = gp[q];
+				nxt[2 * q] = make_float2(v.x, v.y);
+				nxt[2 * q + 1] = make_float2(v.z, v.w);
+			}
+			{
+				const float4 r0 = rp[2 * g], r1 = rp[2 * g + 1];
+				r[0] = r0.x; r[1] = r0.y; r[2] = r0.z; r[3] = r0.w;
+				r[4] = r1.x; r[5] = r1.y; r[6] = r1.z; r[7] = r1.w;
+			}
 #pragma unroll
 			for (int u = 0; u < FR_TILE; u++) {
-				const int n = n0 + u;
-				if (n < len) {
-					const float r = ref[n];
 #pragma unroll
-					for (int t = 0; t < FR_TILE; t++) {
-						// window register (u + t) % FR_TILE holds sample m0 + n + t
-						cr[t] = fmaf(r, wr[(u + t) % FR_TILE], cr[t]);
-						ci[t] = fmaf(r, wi[(u + t) % FR_TILE], ci[t]);
-					}
-					const int i = min(m0 + n + FR_TILE, l - 1);
-					wr[u] = sre[pad8(i)];
-					wi[u] = sim[pad8(i)];
-				}
+				for (int t = 0; t < FR_TILE; t++)       // slot (u + t) % 8 holds sample m0 + 8 g + u + t
+					fma2(c[t], r[u], win[(u + t) % FR_TILE]);
+				win[u] = nxt[u];
 			}
 		}
 #pragma unroll
 		for (int t = 0; t < FR_TILE; t++)
 			if (m0 + t < nc)
-				en[m0 + t] = cr[t] * cr[t] + ci[t] * ci[t];
+				en[m0 + t] = c[t].x * c[t].x + c[t].y * c[t].y;
 	}
 	__syncthreads();
 
@@ -245,46 +282,65 @@ __device__ float peak_weigh5(const float *re, const float *im, int n, int lane)
 	return sw > 0.0f ? mw / sw : (float)max_idx;
 }
 
-static constexpr int FF_WARPS = 4;
+static constexpr int FF_T = 128;            // threads per fine CTA (one CTA per burst)
 
 // mode 0: fine (toa + freq_error), mode 1: snr
-__global__ void __launch_bounds__(FF_WARPS * 32) fcch_fine_kernel(const FcchArgs a, int mode)
+// One CTA per burst.  Warp 0 does the window statistics (lane-strided, the summation order the
+// parity tests were pinned with), all threads mix and run the DFT (one bin per thread, both chirp
+// directions in the same pass over the twiddle table held in shared memory - the table index differs
+// per lane, which a __constant__ table would serialise), warps 0 / 1 search the two spectra.
+__global__ void __launch_bounds__(FF_T) fcch_fine_kernel(const FcchArgs a, int mode)
 {
 	extern __shared__ __align__(16) uint8_t smem[];
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int b = blockIdx.x * FF_WARPS + warp;
-	if (b >= a.n)
-		return;
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int b = blockIdx.x;
 	const int len = a.len, sps = a.sps, L = a.win_len;
 	const int lp = (len + 3) & ~3;
-	float *base = (float *)smem + (size_t)warp * lp * 6;
-	float *ur = base, *ui = base + lp;            // mix with up chirp (or dual chirp) -> spectrum in
-	float *dr = base + 2 * lp, *di = base + 3 * lp;
-	float *Ur = base + 4 * lp, *Ui = base + 5 * lp;   // spectrum out (reused for both DFTs)
+	float4 *mix = (float4 *)smem;                    // [lp] (up.re, up.im, down.re, down.im) spectra in
+	float2 *tw = (float2 *)(mix + lp);               // [lp] e^{-2 pi i k / len}
+	float *Ur = (float *)(tw + lp), *Ui = Ur + lp;   // up (or dual) spectrum
+	float *Dr = Ui + lp, *Di = Dr + lp;              // down spectrum
+	float *stat = Di + lp;                           // [4] ar, ai, sd, -; [4..5] peaks
 
-	const float2 *x = a.iq + (a.ofs ? a.ofs[b] : (int64_t)b * a.stride);
+	int64_t base = a.ofs ? a.ofs[b] : (int64_t)b * a.stride;
+	int rel = 0;
+	if (a.rel) {                                     // chained after the rough stage (fcch_single_init)
+		rel = min(max(a.rel[b], 0), a.rel_max);
+		base += rel;
+	}
+	const float2 *x = a.iq + base;
 	const float freq_shift = a.freq_shift ? a.freq_shift[b] : a.freq_shift0;
 
+	for (int k = tid; k < len; k += FF_T)
+		tw[k] = c_tw[k];
+
 	// sig_normalize(burst_in, sps, freq_shift): statistics over all samples, keep every sps-th
-	float sr = 0.0f, si = 0.0f, sq = 0.0f;
-	for (int i = lane; i < L; i += 32) {
-		const float2 v = __ldg(&x[i]);
-		sr += v.x;
-		si += v.y;
-		sq = fmaf(v.x, v.x, sq);
-		sq = fmaf(v.y, v.y, sq);
+	if (warp == 0) {
+		float sr = 0.0f, si = 0.0f, sq = 0.0f;
+		for (int i = lane; i < L; i += 32) {
+			const float2 v = __ldg(&x[i]);
+			sr += v.x;
+			si += v.y;
+			sq = fmaf(v.x, v.x, sq);
+			sq = fmaf(v.y, v.y, sq);
+		}
+		sr = warp_sum_f(sr); si = warp_sum_f(si); sq = warp_sum_f(sq);
+		const float ar = sr / (float)L, ai = si / (float)L;
+		const float var = sq / (float)L - (ar * ar + ai * ai);
+		float sd = var > 0.0f ? sqrtf(var) : 0.0f;
+		if (sd == 0.0f)
+			sd = 1.0f;
+		if (lane == 0) {
+			stat[0] = ar; stat[1] = ai; stat[2] = sd;
+		}
 	}
-	sr = warp_sum_f(sr); si = warp_sum_f(si); sq = warp_sum_f(sq);
-	const float ar = sr / (float)L, ai = si / (float)L;
-	const float var = sq / (float)L - (ar * ar + ai * ai);
-	float sd = var > 0.0f ? sqrtf(var) : 0.0f;
-	if (sd == 0.0f)
-		sd = 1.0f;
+	__syncthreads();
+	const float ar = stat[0], ai = stat[1], sd = stat[2];
 
 	const float sq2d2 = sqrtf(2.0f) / 2.0f;
 	const float phase_base = a.freq * 2.0f * PI_F / (float)len, halfpos = (float)len / 2.0f;
 	const int mid = len >> 1;
-	for (int i = lane; i < len; i += 32) {
+	for (int i = tid; i < len; i += FF_T) {
 		const float2 v = __ldg(&x[i * sps]);
 		float yr = (v.x - ar) / sd, yi = (v.y - ai) / sd;
 		if (freq_shift != 0.0f) {
@@ -307,42 +363,50 @@ __global__ void __launch_bounds__(FF_WARPS * 32) fcch_fine_kernel(const FcchArgs
 			double dsn, dcs;
 			sincos((double)ang, &dsn, &dcs);
 			const float fr = (float)dcs, fi = (float)dsn;
-			ur[i] = mur * fr - mui * fi; ui[i] = mur * fi + mui * fr;
-			dr[i] = mdr * fr - mdi * fi; di[i] = mdr * fi + mdi * fr;
+			mix[i] = make_float4(mur * fr - mui * fi, mur * fi + mui * fr,
+			                     mdr * fr - mdi * fi, mdr * fi + mdi * fr);
 		} else {
 			const float dual = sqrtf(2.0f) * cosf(ph);               // fcch.c:183-189, :678-679
-			ur[i] = yr * dual;
-			ui[i] = yi * dual;
+			mix[i] = make_float4(yr * dual, yi * dual, 0.0f, 0.0f);
 		}
 	}
-	__syncwarp();
+	__syncthreads();
 
 	// forward DFT by direct evaluation: X[k] = sum_n x[n] W^(k*n mod len)
-	float peak[2] = {0.0f, 0.0f};
-	const int ndft = mode == 0 ? 2 : 1;
-	for (int t = 0; t < ndft; t++) {
-		const float *xr = t ? dr : ur, *xi = t ? di : ui;
-		for (int k = lane; k < len; k += 32) {
-			float accr = 0.0f, acci = 0.0f;
-			int idx = 0;
-			for (int n = 0; n < len; n++) {
-				const float2 w = c_tw[idx];
-				const float vr = xr[n], vi = xi[n];
-				accr = fmaf(vr, w.x, accr);
-				accr = fmaf(-vi, w.y, accr);
-				acci = fmaf(vr, w.y, acci);
-				acci = fmaf(vi, w.x, acci);
-				idx += k;
-				idx -= idx >= len ? len : 0;
-			}
-			Ur[k] = accr;
-			Ui[k] = acci;
+	for (int k = tid; k < len; k += FF_T) {
+		float ur = 0.0f, ui = 0.0f, dr = 0.0f, di = 0.0f;
+		int idx = 0;
+		for (int n = 0; n < len; n++) {
+			const float2 t = tw[idx];
+			const float4 v = mix[n];
+			ur = fmaf(v.x, t.x, ur);
+			ur = fmaf(-v.y, t.y, ur);
+			ui = fmaf(v.x, t.y, ui);
+			ui = fmaf(v.y, t.x, ui);
+			dr = fmaf(v.z, t.x, dr);
+			dr = fmaf(-v.w, t.y, dr);
+			di = fmaf(v.z, t.y, di);
+			di = fmaf(v.w, t.x, di);
+			idx += k;
+			idx -= idx >= len ? len : 0;
 		}
-		__syncwarp();
-		if (mode == 0)
-			peak[t] = peak_weigh5(Ur, Ui, len, lane);
-		__syncwarp();
+		Ur[k] = ur; Ui[k] = ui;
+		Dr[k] = dr; Di[k] = di;
 	}
+	__syncthreads();
+	float peak[2] = {0.0f, 0.0f};
+	if (mode == 0) {
+		if (warp < 2) {
+			const float p = peak_weigh5(warp ? Dr : Ur, warp ? Di : Ui, len, lane);
+			if (lane == 0)
+				stat[4 + warp] = p;
+		}
+		__syncthreads();
+		peak[0] = stat[4];
+		peak[1] = stat[5];
+	}
+	if (warp != 0)
+		return;
 
 	if (mode == 0) {
 		if (lane == 0) {
@@ -355,7 +419,7 @@ __global__ void __launch_bounds__(FF_WARPS * 32) fcch_fine_kernel(const FcchArgs
 			const float chirp_rate = (2.0f * a.freq * sym_rate * sym_rate) / (float)(len * 1000);
 			const float toa_ms = ((peak_up - peak_down) / 2.0f) / chirp_rate;
 			const float toa_samples = (toa_ms * sym_rate * (float)sps) / 1000.0f;
-			a.toa[b] = (int)round((double)toa_samples);
+			a.toa[b] = (int)round((double)toa_samples) + (a.rel_add ? rel : 0);
 		}
 	} else {
 		// six strongest bins, descending (osmo_cxvec_peaks_scan); ratio of top 2 over bins 5, 6
@@ -397,8 +461,8 @@ cudaError_t launch_fcch_rough(const FcchArgs &a, cudaStream_t st)
 	const int l = a.win_len / a.sps, nc = l - a.len + 1;
 	if (nc < 1 || a.len > MAX_FCCH_LEN)
 		return cudaErrorInvalidValue;
-	const int pl = l + (l >> 3) + 8;
-	const size_t smem = sizeof(float) * ((size_t)2 * pl + ((a.len + 3) & ~3) + 96 + nc);
+	const int lenp = (a.len + 7) & ~7, ng = (l + lenp + 15) >> 3;
+	const size_t smem = sizeof(float) * ((size_t)ng * FR_GRP + lenp + 96 + nc);
 	if (smem > 227 * 1024)
 		return cudaErrorInvalidValue;
 	static size_t attr_set[64] = {0};
@@ -437,8 +501,8 @@ cudaError_t launch_fcch_fine(const FcchArgs &a, int mode, cudaStream_t st)
 		if (dev < 64)
 			tw_len[dev] = a.len;
 	}
-	const size_t smem = sizeof(float) * 6 * ((a.len + 3) & ~3) * FF_WARPS;
-	fcch_fine_kernel<<<(a.n + FF_WARPS - 1) / FF_WARPS, FF_WARPS * 32, smem, st>>>(a, mode);
+	const size_t smem = sizeof(float) * (10 * ((a.len + 3) & ~3) + 8);
+	fcch_fine_kernel<<<a.n, FF_T, smem, st>>>(a, mode);
 	return cudaGetLastError();
 }
 

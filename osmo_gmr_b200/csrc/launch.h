@@ -38,6 +38,8 @@ struct FcchArgs {
 	const float2  *iq;
 	const int64_t *ofs;
 	int64_t        stride;
+	const int32_t *rel;                    // fine: optional [n] extra offset (the rough TOA), clamped to [0, rel_max]
+	int32_t        rel_max, rel_add;       //       rel_add: write toa = rel + fine TOA (the channel alignment)
 	int32_t        n, win_len, sps, len;   // len = FCCH burst length in symbols
 	float          freq;                   // chirp sweep (0.32 / 0.16)
 	const float   *freq_shift;

@@ -58,6 +58,33 @@ def test_fcch_fine_and_snr(gpu_lib, oracle):
     assert same >= 0.97 * n
 
 
+@pytest.mark.parametrize("sps,ftype", [(4, 0), (2, 0), (1, 0), (3, 0), (4, 1)])
+def test_fcch_acquire(gpu_lib, oracle, sps, ftype):
+    """fcch_single_init (src/gmr1_rx.c:606-639) in one call: rough over the search window, fine on the burst
+    found; every other sps the reference accepts and the 12-slot FCCH3 format too."""
+    rng = np.random.default_rng(33 + sps + 10 * ftype)
+    blen = [117, 468, 468][ftype]
+    n, L = 10, (330 * 23400 * sps) // 1000 + (0 if ftype == 0 else 468 * sps)
+    pos = rng.integers(150 * sps, L - (blen + 150) * sps, n)
+    cfo = rng.uniform(-0.2, 0.2, n) * (1.0 if ftype == 0 else 0.25)
+    x = np.stack([sigen.fcch_window(L, sps, int(pos[i]), cfo[i], [4.0, 10.0, 20.0][i % 3], rng,
+                                    [0.32, 0.32, 0.16][ftype], blen) for i in range(n)])
+    rough = np.full(n, -1, np.int32)
+    align = np.full(n, -1, np.int32)
+    fe = np.zeros(n, np.float32)
+    gpu_lib.call("gmr1b200_fcch_acquire_batch", ftype, _iq(x), n * L, None, L, L, sps, rough, align, fe, n, None)
+    same = 0
+    for i in range(n):
+        rc, t = oracle.fcch_rough(x[i], sps, 0.0, ftype)
+        assert rc == 0 and abs(int(rough[i]) - t) <= 1, (i, rough[i], t)
+        a = int(rough[i])                                   # fine stage judged on the GPU's own rough TOA
+        rc, ft, f = oracle.fcch_fine(x[i][a:a + blen * sps], sps, 0.0, ftype)
+        assert rc == 0 and abs(int(align[i]) - (a + ft)) <= 1 and abs(fe[i] - f) <= 1e-5, (i, align[i], a + ft, fe[i], f)
+        same += int(rough[i] == t and align[i] == a + ft)
+        assert abs(int(align[i]) - pos[i]) <= 3 * sps and abs(fe[i] - cfo[i]) < 0.02
+    assert same >= n - 1
+
+
 def test_dkab(gpu_lib, oracle):
     rng = np.random.default_rng(33)
     n, win = 64, 6                          # gmr1_rx maps DKABs with the NT3 window (src/gmr1_rx.c:549)
