@@ -41,6 +41,9 @@
 namespace gmr1 {
 
 static constexpr int DM_WARPS = 4;
+#ifndef DM_MIN_CTAS
+#define DM_MIN_CTAS 8          // resident CTAs per SM the register allocation is capped for
+#endif
 static constexpr float PI_F = 3.14159265358979323846264338327f;
 
 // sin(pi * k / 512), k = 0..512: every position the early/late search visits is a multiple of
@@ -143,14 +146,12 @@ __device__ float peak_early_late(const float *acc, int w, const TapLane &tp, int
 			best_idx = idx;
 		}
 	}
-#pragma unroll
-	for (int o = 16; o; o >>= 1) {
-		const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-		const int oi = __shfl_xor_sync(0xffffffffu, best_idx, o);
-		if (ov > best || (ov == best && oi < best_idx)) {
-			best = ov;
-			best_idx = oi;
-		}
+	{	// warp argmax (largest value, lowest index on ties): energies are >= +0, so their bit patterns
+		// order like unsigned integers and two redux instructions replace the shuffle tree
+		const unsigned vb = __float_as_uint(best);
+		const unsigned mx = __reduce_max_sync(0xffffffffu, vb);
+		best_idx = (int)__reduce_min_sync(0xffffffffu, vb == mx ? (unsigned)best_idx : 0xffffffffu);
+		best = __uint_as_float(mx);
 	}
 	int max_idx = (best > 0.0f) ? best_idx - win + 1 : 0;
 	if (max_idx < 0)
@@ -211,37 +212,44 @@ __device__ float peak_early_late(const float *acc, int w, const TapLane &tp, int
 // window kept in shared memory, which is what lets 32 warps share an SM.  Symbol samples are read
 // once each, straight from global memory (L2 hits: the warp streamed the window moments before).
 static constexpr int MAX_REGIONS = 8;
+static constexpr int MAX_BT = 8;            // burst types one detect call may choose from
 struct Regions {
 	int32_t n, total;                       // number of regions, samples in all of them
 	int32_t start[MAX_REGIONS], len[MAX_REGIONS], off[MAX_REGIONS];   // window sample, length, smem offset
+	int32_t n_slot;                         // training chunks of all types / sequences, numbered densely:
+	uint8_t slot[MAX_BT][MAX_SYNC][MAX_SYNC_CHUNK];   // their rotated taps are cached per warp (build_taps)
 };
 
 // per-warp shared-memory slice
 struct WarpSmem {
 	float2 *reg;     // [regions.total] raw samples of the correlation regions
-	float2 *taps;    // [32]  rotated reference taps of the chunk being correlated
+	float2 *taps;    // [n_slot][32]  rotated reference taps of every training chunk (zero beyond its length)
+	float2 *tsum;    // [n_slot]      sum of each chunk's taps
 	float  *accv;    // [w]   correlation magnitude accumulator
 	float2 *zbuf;    // [MAX_TRAIN] derotated training symbols x conj(reference)
 };
 
 static constexpr int MAX_TRAIN = 104;     // RACH: 17 + 32 + 32 + 17 + 1 = 99 training symbols
 
-__device__ __forceinline__ WarpSmem carve(uint8_t *base, int nreg, int w)
+__device__ __forceinline__ WarpSmem carve(uint8_t *base, int nreg, int w, int nslot)
 {
 	WarpSmem s;
 	s.reg = (float2 *)base;
 	base += (size_t)((nreg + 1) & ~1) * 8;
 	s.taps = (float2 *)base;
-	base += 32 * 8;
+	base += (size_t)nslot * 32 * 8;
+	s.tsum = (float2 *)base;
+	base += (size_t)((nslot + 1) & ~1) * 8;
 	s.accv = (float *)base;
-	base += (size_t)((w + 3) & ~3) * 4;
+	base += (size_t)((w + 31) & ~31) * 4;
 	s.zbuf = (float2 *)base;
 	return s;
 }
 
-static inline size_t warp_smem_bytes(int nreg, int w)
+static inline size_t warp_smem_bytes(int nreg, int w, int nslot)
 {
-	return (size_t)((nreg + 1) & ~1) * 8 + 32 * 8 + (size_t)((w + 3) & ~3) * 4 + MAX_TRAIN * 8;
+	return (size_t)((nreg + 1) & ~1) * 8 + (size_t)nslot * 32 * 8 + (size_t)((nslot + 1) & ~1) * 8 +
+	       (size_t)((w + 31) & ~31) * 4 + MAX_TRAIN * 8;
 }
 
 // window statistics of osmo_cxvec_sig_normalize: mean and 1/stddev.  One pass: the variance is
@@ -249,17 +257,27 @@ static inline size_t warp_smem_bytes(int nreg, int w)
 // both are fp32 approximations of the same quantity).
 struct Norm { float ar, ai, inv_sd; };
 
+// dst4 (optional): for every pair of samples of the window, the float4 slot of the warp's region buffer
+// it belongs to (0xffff: none) - the correlation regions are then filled from the same loads and the
+// separate load_regions pass (a second trip to L2) is not needed.
 template <bool WANT_SD>
-__device__ __forceinline__ Norm load_stats_t(const float2 *__restrict__ x, int L, int lane)
+__device__ __forceinline__ Norm load_stats_t(const float2 *__restrict__ x, int L, int lane,
+                                             const bool FILL, const uint16_t *dst4, float2 *reg)
 {
 	float sr = 0.0f, si = 0.0f, sq = 0.0f;
 	if ((((uintptr_t)x) & 15) == 0) {
 		// 16-byte aligned window: two samples per lane per load
 		const float4 *x4 = reinterpret_cast<const float4 *>(x);
+		float4 *reg4 = reinterpret_cast<float4 *>(reg);
 		const int L2 = L >> 1;
 #pragma unroll 4
 		for (int i = lane; i < L2; i += 32) {
 			const float4 v = __ldg(&x4[i]);
+			if (FILL) {
+				const unsigned d = dst4[i];
+				if (d != 0xffffu)
+					reg4[d] = v;
+			}
 			sr += v.x + v.z;
 			si += v.y + v.w;
 			if (WANT_SD) {
@@ -271,14 +289,19 @@ __device__ __forceinline__ Norm load_stats_t(const float2 *__restrict__ x, int L
 		}
 		if ((L & 1) && lane == 0) {
 			const float2 v = __ldg(&x[L - 1]);
+			if (FILL) {
+				const unsigned d = dst4[L2];
+				if (d != 0xffffu)
+					reg[2 * d] = v;
+			}
 			sr += v.x;
 			si += v.y;
 			if (WANT_SD)
 				sq += v.x * v.x + v.y * v.y;
 		}
 	} else {
-#pragma unroll 4
-		for (int i = lane; i < L; i += 32) {
+#pragma unroll 1
+		for (int i = lane; i < L; i += 32) {        // 8-byte aligned window (odd sample offset): cold path
 			const float2 v = __ldg(&x[i]);
 			sr += v.x;
 			si += v.y;
@@ -306,45 +329,77 @@ __device__ __forceinline__ Norm load_stats_t(const float2 *__restrict__ x, int L
 	return n;
 }
 
-__device__ __forceinline__ Norm load_stats(const float2 *__restrict__ x, int L, int lane, bool want_sd)
-{
-	return want_sd ? load_stats_t<true>(x, L, lane) : load_stats_t<false>(x, L, lane);
-}
-
 // copy the correlation regions of this window into the warp's shared memory
-__device__ __forceinline__ void load_regions(const float2 *__restrict__ x, const Regions &rg, float2 *reg, int lane)
+// (fallback for windows that are not 16-byte aligned or too long for the pair table; the usual path
+// fills the regions from the loads of the statistics pass)
+__device__ __noinline__ void load_regions(const float2 *__restrict__ x, int L, const Regions &rg, float2 *reg, int lane)
 {
 	for (int r = 0; r < rg.n; r++) {
 		const float2 *src = x + rg.start[r];
 		float2 *dst = reg + rg.off[r];
-#pragma unroll 4
-		for (int i = lane; i < rg.len[r]; i += 32)
+		const int n = min(rg.len[r], L - rg.start[r]);      // lengths are rounded up to even
+#pragma unroll 1
+		for (int i = lane; i < n; i += 32)
 			dst[i] = __ldg(&src[i]);
 	}
 	__syncwarp();
 }
 
+// c += s * v on the packed FP32 pipe (one FFMA2 instead of two FFMA)
+__device__ __forceinline__ void fma2s(float2 &c, float sc, const float2 v)
+{
+	unsigned long long cc = *reinterpret_cast<unsigned long long *>(&c);
+	const float2 ss = make_float2(sc, sc);
+	asm("fma.rn.f32x2 %0, %1, %2, %0;"
+	    : "+l"(cc)
+	    : "l"(*reinterpret_cast<const unsigned long long *>(&ss)), "l"(*reinterpret_cast<const unsigned long long *>(&v)));
+	c = *reinterpret_cast<float2 *>(&cc);
+}
+
 // complex multiply-accumulate of the (zero-padded to a multiple of 4) rotated taps against R search
-// offsets 32 samples apart; one tap load serves all R
+// offsets 32 samples apart; one tap load serves all R.  Accumulates P = sum t.re * x and Q = sum t.im * x
+// (two FFMA2 per tap and offset); the correlation is (P.re - Q.im, P.im + Q.re).
 template <int R>
 __device__ __forceinline__ void corr_taps(const float2 *g, const float2 *tp, int cl4, int sps,
-                                          float (&cr)[3], float (&ci)[3])
+                                          float2 (&P)[3], float2 (&Q)[3])
 {
 #pragma unroll 1
 	for (int n = 0; n < cl4; n += 4, tp += 4, g += 4 * sps) {
+		const float4 t01 = *reinterpret_cast<const float4 *>(tp), t23 = *reinterpret_cast<const float4 *>(tp + 2);
+		const float tr[4] = {t01.x, t01.z, t23.x, t23.z}, ti[4] = {t01.y, t01.w, t23.y, t23.w};
 #pragma unroll
 		for (int u = 0; u < 4; u++) {
-			const float2 t = tp[u];
 #pragma unroll
 			for (int r = 0; r < R; r++) {
 				const float2 v = g[u * sps + 32 * r];
-				cr[r] = fmaf(t.x, v.x, cr[r]);
-				cr[r] = fmaf(-t.y, v.y, cr[r]);
-				ci[r] = fmaf(t.x, v.y, ci[r]);
-				ci[r] = fmaf(t.y, v.x, ci[r]);
+				fma2s(P[r], tr[u], v);
+				fma2s(Q[r], ti[u], v);
 			}
 		}
 	}
+}
+
+// Rotated reference taps of every training chunk for the frequency shift fs: t_n = conj(ref_n) e^{j*fs*sps*n},
+// and their sums.  Depends on the burst only through fs, so each warp rebuilds them only when fs changes
+// (never, when the batch shares one freq_shift).
+__device__ void build_taps(const BurstTab *__restrict__ bts, int n_bt, const Regions &rg, const WarpSmem &sm,
+                           float fs, int sps, int lane)
+{
+	const float2 rot = sincos_acc((fs * (float)sps) * (float)lane);     // e^{j*fs*sps*lane}: tap n of every chunk
+	__syncwarp();
+	for (int ty = 0; ty < n_bt; ty++)
+		for (int s = 0; s < bts[ty].n_sync; s++)
+			for (int c = 0; c < bts[ty].n_chunk[s]; c++) {
+				const int slot = rg.slot[ty][s][c];
+				float2 t = make_float2(0.0f, 0.0f);
+				if (lane < bts[ty].s_len[s][c])
+					t = mul_conj_sym(bts[ty].s_sym[s][c][lane], rot);
+				sm.taps[slot * 32 + lane] = t;
+				const float2 Rs = warp_sum2(t.x, t.y, lane);
+				if (lane == 0)
+					sm.tsum[slot] = Rs;
+			}
+	__syncwarp();
 }
 
 // Search all sync sequences of one burst type (pi4cxpsk.c:184-268) on the RAW window.
@@ -358,72 +413,63 @@ __device__ __forceinline__ void corr_taps(const float2 *g, const float2 *tp, int
 // keeps adding (:232-233); tl restarts per sequence (:216).
 template <int SPS>     // SPS > 0: compile-time samples per symbol (4 is the fast path), <= 0: run-time
 __device__ int sync_find(const BurstTab &bt, const WarpSmem &sm, const uint16_t (*roff_tab)[MAX_SYNC_CHUNK],
-                         const Norm &nm, float fs, int sps_rt, int w, const TapLane &tpl, int lane, bool sync_reset,
-                         float &toa, float &pwr)
+                         const uint8_t (*slot_tab)[MAX_SYNC_CHUNK], const Norm &nm, int sps_rt, int w,
+                         const TapLane &tpl, int lane, bool sync_reset, float &toa, float &pwr)
 {
 	const int sps = SPS > 0 ? SPS : sps_rt;
-	for (int m = lane; m < w; m += 32)
-		sm.accv[m] = 0.0f;
 	float p_toa = 0.0f, p_pwr = 0.0f;
 	int p_idx = -1;
-	const float2 rot = sincos_acc((fs * (float)sps) * (float)lane);     // e^{j*fs*sps*lane}: tap n of every chunk
-	const float rot_c = rot.x, rot_s = rot.y;
 	for (int s = 0; s < bt.n_sync; s++) {
 		int tl = 0;
-		if (sync_reset && s > 0) {           // opt-in: score every candidate on its own correlation
-			__syncwarp();
-			for (int m = lane; m < w; m += 32)
-				sm.accv[m] = 0.0f;
-		}
-		for (int c = 0; c < bt.n_chunk[s]; c++) {
-			const int cl = bt.s_len[s][c];
-			// rotated taps + their sum
-			float tr = 0.0f, ti = 0.0f;
-			if (lane < cl) {
-				const float2 t = mul_conj_sym(bt.s_sym[s][c][lane], make_float2(rot_c, rot_s));
-				tr = t.x;
-				ti = t.y;
-			}
-			__syncwarp();
-			sm.taps[lane] = make_float2(tr, ti);
-			const float2 Rs = warp_sum2(tr, ti, lane);
-			const float Rr = Rs.x, Ri = Rs.y;
-			const float cr0 = nm.ar * Rr - nm.ai * Ri, ci0 = nm.ar * Ri + nm.ai * Rr;   // avg * sum(taps)
-			__syncwarp();
-			// taps beyond cl are zero (lanes >= cl wrote 0), so the tap loop runs in whole groups of 4.
-			// The up to 3 zero taps may read up to 3*sps samples past their region: that lands in this
-			// warp's other regions / taps / accv / zbuf, which only ever hold finite floats, and
-			// 0 * finite adds nothing.
-			const int cl4 = (cl + 3) & ~3;
-			const int roff = roff_tab[s][c];
-			// up to three search offsets per lane (m, m+32, m+64) share every tap load
-			for (int mb = 0; mb < w; mb += 96) {
-				const int m0 = mb + lane;
-				if (m0 >= w)
-					continue;
-				float cr[3] = {0.0f, 0.0f, 0.0f}, ci[3] = {0.0f, 0.0f, 0.0f};
-				const float2 *g = sm.reg + roff + m0;
-				const float2 *tp = sm.taps;
-				const bool r1 = mb + 32 < w, r2 = mb + 64 < w;      // warp-uniform: some lane has a 2nd / 3rd offset
+		const bool fresh = s == 0 || sync_reset;      // sync_reset (opt-in): score every candidate on its own correlation
+		__syncwarp();
+		// up to three search offsets per lane (m, m+32, m+64) share every tap load; their |corr| sums over
+		// the chunks stay in registers.  Offsets >= w are computed too (accv is padded to whole rows of 32,
+		// the samples they read are whatever finite values follow the region) and never looked at.
+		for (int mb = 0; mb < w; mb += 96) {
+			const int m0 = mb + lane;
+			const bool r1 = mb + 32 < w, r2 = mb + 64 < w;      // warp-uniform: the rows of 32 offsets in use
+			float acc[3];
+#pragma unroll
+			for (int r = 0; r < 3; r++)
+				acc[r] = fresh ? 0.0f : sm.accv[m0 + 32 * r];
+			tl = 0;
+			for (int c = 0; c < bt.n_chunk[s]; c++) {
+				const int cl = bt.s_len[s][c];
+				const int slot = slot_tab[s][c];
+				const float2 Rs = sm.tsum[slot];
+				const float cr0 = nm.ar * Rs.x - nm.ai * Rs.y, ci0 = nm.ar * Rs.y + nm.ai * Rs.x;   // avg * sum(taps)
+				// taps beyond cl are zero, so the tap loop runs in whole groups of 4.  The up to 3 zero taps
+				// may read up to 3*sps samples past their region: that lands in this warp's other regions /
+				// taps / accv / zbuf, which only ever hold finite floats, and 0 * finite adds nothing.
+				const int cl4 = (cl + 3) & ~3;
+				float2 P[3], Q[3];
+#pragma unroll
+				for (int r = 0; r < 3; r++)
+					P[r] = Q[r] = make_float2(0.0f, 0.0f);
+				const float2 *g = sm.reg + roff_tab[s][c] + m0;
+				const float2 *tp = sm.taps + slot * 32;
 				if (r2)
-					corr_taps<3>(g, tp, cl4, sps, cr, ci);
+					corr_taps<3>(g, tp, cl4, sps, P, Q);
 				else if (r1)
-					corr_taps<2>(g, tp, cl4, sps, cr, ci);
+					corr_taps<2>(g, tp, cl4, sps, P, Q);
 				else
-					corr_taps<1>(g, tp, cl4, sps, cr, ci);
+					corr_taps<1>(g, tp, cl4, sps, P, Q);
 #pragma unroll
 				for (int r = 0; r < 3; r++) {
-					const int m = m0 + 32 * r;
-					if (m < w) {
-						const float xr = (cr[r] - cr0) * nm.inv_sd, xi = (ci[r] - ci0) * nm.inv_sd;
-						const float e = fmaf(xr, xr, xi * xi);
-						float rs;
-						asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(e));
-						sm.accv[m] += e > 0.0f ? e * rs : 0.0f;
-					}
+					const float xr = ((P[r].x - Q[r].y) - cr0) * nm.inv_sd, xi = ((P[r].y + Q[r].x) - ci0) * nm.inv_sd;
+					const float e = fmaf(xr, xr, xi * xi);
+					float rs;
+					asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(e));
+					acc[r] += e > 0.0f ? e * rs : 0.0f;
 				}
+				tl += cl;
 			}
-			tl += cl;
+			sm.accv[m0] = acc[0];
+			if (r1)
+				sm.accv[m0 + 32] = acc[1];
+			if (r2)
+				sm.accv[m0 + 64] = acc[2];
 		}
 		__syncwarp();
 		float peak;
@@ -474,14 +520,17 @@ __device__ float2 lowsps_symbol(const float2 *__restrict__ x, int L, int q, bool
 // Flattened symbol lists of the burst format, built once per CTA in shared memory: the training
 // symbols of every sync sequence (position, reference symbol, chunk) and the data symbols in
 // output order.  One lane per symbol then needs no per-chunk control flow.
+static constexpr int MAX_DST4 = 1280;     // windows up to 2560 samples fill their regions in the statistics pass
 struct FlatTab {
-	uint16_t roff[8][MAX_SYNC][MAX_SYNC_CHUNK];   // smem offset (in samples) of each chunk's first sample
+	uint16_t roff[MAX_BT][MAX_SYNC][MAX_SYNC_CHUNK];   // smem offset (in samples) of each chunk's first sample
 	uint16_t d_pos[480];
 	uint16_t t_pos[MAX_SYNC][MAX_TRAIN];
 	uint8_t  t_sym[MAX_SYNC][MAX_TRAIN];
 	uint8_t  t_chunk[MAX_SYNC][MAX_TRAIN];
 	int32_t  n_train[MAX_SYNC];
 	int32_t  n_dsym;
+	int32_t  dst_ok;                 // dst4 is valid (the window has at most 2 * MAX_DST4 samples)
+	uint16_t dst4[MAX_DST4 + 1];     // pair of samples -> float4 slot of the region buffer, 0xffff: not in a region
 };
 
 __device__ void build_flat(const BurstTab &bt, FlatTab &ft)
@@ -518,9 +567,10 @@ __device__ void build_flat(const BurstTab &bt, FlatTab &ft)
 }
 
 // mode 0: demod (bts[0] only).  mode 1: detect among n_bt burst types (pi4cxpsk.c:617-682).
+// NB = bits per symbol of bts[0] (compile time: the soft-bit mapping is straight-line code).
 // Persistent: each warp strides over the bursts of the batch.
-template <int MODE, int SPS>
-__global__ void __launch_bounds__(DM_WARPS * 32, 8)
+template <int MODE, int SPS, int NB>
+__global__ void __launch_bounds__(DM_WARPS * 32, DM_MIN_CTAS)
 demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int warp_bytes,
              const __grid_constant__ Regions rg)
 {
@@ -530,7 +580,7 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 	const BurstTab &bt = bts[0];
 	const int sps = SPS > 0 ? SPS : a.sps, L = a.win_len;
 	const int w = L - bt.len * sps + 1;
-	const WarpSmem sm = carve(smem + (size_t)warp * warp_bytes, rg.total, w);
+	const WarpSmem sm = carve(smem + (size_t)warp * warp_bytes, rg.total, w, rg.n_slot);
 
 	if (MODE == 0)
 		build_flat(bt, ft);
@@ -543,12 +593,24 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 				roff = rg.off[r] + (b0 - rg.start[r]);
 		ft.roff[ty][sq][c] = (uint16_t)roff;
 	}
+	if (threadIdx.x == 0)
+		ft.dst_ok = (L >> 1) <= MAX_DST4;
+	if ((L >> 1) <= MAX_DST4)
+		for (int i = threadIdx.x; i <= (L >> 1); i += blockDim.x) {      // region starts / lengths are even
+			unsigned d = 0xffffu;
+			for (int r = 0; r < rg.n; r++)
+				if (2 * i >= rg.start[r] && 2 * i < rg.start[r] + rg.len[r])
+					d = (unsigned)((rg.off[r] + 2 * i - rg.start[r]) >> 1);
+			ft.dst4[i] = (uint16_t)d;
+		}
 	// the area behind the window must only ever hold finite values (see sync_find)
 	for (int i = lane; i < ((rg.total + 1) & ~1); i += 32)
 		sm.reg[i] = make_float2(0.0f, 0.0f);
-	for (int i = lane; i < 32; i += 32)
+	for (int i = lane; i < rg.n_slot * 32; i += 32)
 		sm.taps[i] = make_float2(0.0f, 0.0f);
-	for (int i = lane; i < ((w + 3) & ~3); i += 32)
+	for (int i = lane; i < ((rg.n_slot + 1) & ~1); i += 32)
+		sm.tsum[i] = make_float2(0.0f, 0.0f);
+	for (int i = lane; i < ((w + 31) & ~31); i += 32)
 		sm.accv[i] = 0.0f;
 	for (int i = lane; i < MAX_TRAIN; i += 32)
 		sm.zbuf[i] = make_float2(0.0f, 0.0f);
@@ -560,9 +622,12 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 	tpl.sgn = lane < 21 ? (((lane - 10) & 1) ? 1.0f : -1.0f) : 0.0f;
 
 	const bool want_sd = a.pwr != nullptr || (MODE == 1 && (a.e_toa != nullptr || a.e_toa0 >= 0.0f));
-	const int nbits = bt.nbits, mask = (1 << nbits) - 1;
-	const double inv_dd = (double)(1 << nbits) / (2.0 * 3.14159265358979323846);
-	const double period = (double)(1 << nbits), inv_period = 1.0 / period;
+	constexpr int mask = (1 << NB) - 1;
+	constexpr float period = (float)(1 << NB), inv_period = 1.0f / period;
+	constexpr float inv_dd = period * 0.15915494309189533577f;        // symbol steps per radian
+	// 2*pi = TWO_PI_HI + TWO_PI_LO, TWO_PI_HI with 9 significant bits: k * TWO_PI_HI is exact for |k| < 2^15
+	constexpr float TWO_PI_HI = 6.28125f, TWO_PI_LO = 1.9353071795864769e-3f, INV_2PI = 0.15915494309189533577f;
+	float fs_taps = __int_as_float(0x7fc00000);     // frequency shift the cached taps were built for (NaN: none)
 
 	for (int b = blockIdx.x * DM_WARPS + warp; b < a.n; b += gridDim.x * DM_WARPS) {
 		const float2 *x = a.iq + (a.ofs ? a.ofs[b] : (int64_t)b * a.stride);
@@ -570,8 +635,26 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 		const float fs = (freq_shift - bt.rotation) / (float)sps;
 
 		__syncwarp();
-		const Norm nm = load_stats(x, L, lane, want_sd);
-		load_regions(x, rg, sm.reg, lane);
+		if (fs != fs_taps) {
+			build_taps(bts, n_bt, rg, sm, fs, sps, lane);
+			fs_taps = fs;
+		}
+		// aligned windows fill the correlation regions from the loads of the statistics pass
+		const bool fill = ft.dst_ok && (((uintptr_t)x) & 15) == 0;
+		const Norm nm = want_sd ? load_stats_t<true>(x, L, lane, fill, ft.dst4, sm.reg)
+		                        : load_stats_t<false>(x, L, lane, fill, ft.dst4, sm.reg);
+		if (!fill)
+			load_regions(x, L, rg, sm.reg, lane);
+		else
+			__syncwarp();
+		{	// pull the window this warp works on next into L2 while it computes on this one
+			const int bn = b + gridDim.x * DM_WARPS;
+			if (bn < a.n) {
+				const char *xn = (const char *)(a.iq + (a.ofs ? a.ofs[bn] : (int64_t)bn * a.stride));
+				for (int o = lane * 128; o < L * 8; o += 32 * 128)
+					asm volatile("prefetch.global.L2 [%0];" ::"l"(xn + o));
+			}
+		}
 
 		if (MODE == 1) {
 			const float e_toa = a.e_toa ? a.e_toa[b] : a.e_toa0;
@@ -579,7 +662,8 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 			float p_toa = 0.0f, p_pwr = 0.0f;
 			for (int id = 0; id < n_bt; id++) {
 				float toa, pwr;
-				const int sid = sync_find<SPS>(bts[id], sm, ft.roff[id], nm, fs, sps, w, tpl, lane, a.sync_reset != 0, toa, pwr);
+				const int sid = sync_find<SPS>(bts[id], sm, ft.roff[id], rg.slot[id], nm, sps, w, tpl, lane,
+				                               a.sync_reset != 0, toa, pwr);
 				if (e_toa >= 0.0f)     // the reference divides by fabs() in double (pi4cxpsk.c:658-659)
 					pwr = (float)((double)pwr / fabs((double)(e_toa - toa)));
 				if (pwr > p_pwr) {
@@ -599,7 +683,8 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 		}
 
 		float toa, pwr;
-		const int sync_id = sync_find<SPS>(bt, sm, ft.roff[0], nm, fs, sps, w, tpl, lane, a.sync_reset != 0, toa, pwr);
+		const int sync_id = sync_find<SPS>(bt, sm, ft.roff[0], rg.slot[0], nm, sps, w, tpl, lane, a.sync_reset != 0,
+		                                   toa, pwr);
 		if (lane == 0) {
 			if (a.sync_id) a.sync_id[b] = sync_id;
 			if (a.toa) a.toa[b] = toa;
@@ -701,34 +786,23 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 		// ---- data symbols in the angle domain, one per lane in output order.  The reference rotates
 		// each sample three times (e^{j*fs*idx}, e^{-j*ferr*i}, conj(phasor)) and takes cargf(); the
 		// argument of that product is  arg(x - avg) + fl32(fs*idx) + fl32(-ferr*i) - arg(phasor)
-		// (mod 2*pi), accumulated here in double so that the only float rounding left is the atan2 of
-		// the raw sample.
-		const double c0 = -(double)phi0 * inv_dd;
+		// (mod 2*pi).  fl32(fs*idx) reaches a few hundred radians, so it is reduced mod 2*pi first
+		// (Cody-Waite, exact to ~1e-8 rad); the remaining three float additions of values below 2*pi
+		// keep the sum within ~5e-7 rad, 4e-5 of a soft-bit step.
 		const int nds = ft.n_dsym;
+		const float nferr = -ferr, nphi0 = -phi0;
 		const bool eb_even = (((uintptr_t)eb) & 1) == 0;
-		for (int t = lane; t < nds; t += 32) {
-			const int i = ft.d_pos[t];
-			float th, a1;
-			if (SPS < 0) {           // interpolated symbol already carries the derotation
-				const float2 z = lowsps_symbol(x, L, i * sps + d, interp, ofs_frac, nm, fs);
-				th = fast_atan2f_inl(z.y, z.x);
-				a1 = 0.0f;
-			} else {
-				const int q = sample_of(i);
-				const float2 v = __ldg(&x[q]);
-				th = fast_atan2f_inl(v.y - nm.ai, v.x - nm.ar);
-				a1 = fs * (float)q;
-			}
-			const float a2 = (-ferr) * (float)i;
-			double svd = fma((double)th + (double)a1 + (double)a2, inv_dd, c0);
-			svd -= period * rint(svd * inv_period);        // -> [-period/2, period/2]
-			const float sv = (float)svd;
+		// soft bits of data symbol t (burst position i) whose derotated angle, before the -ferr*i and
+		// -phase corrections, is ang
+		auto emit = [&](int t, int i, float ang) {
+			float sv = ((ang + nferr * (float)i) + nphi0) * inv_dd;
+			sv = fmaf(-period, rintf(sv * inv_period), sv);        // -> [-period/2, period/2]
 			const float svr = rintf(sv);                   // (ties differ from roundf only on exact .5)
 			const int sp = (int)svr & mask;
 			const bool below = svr > sv;                   // second-nearest symbol is sp-1, else sp+1
 			const int dq = __float2int_rn(128.0f * fabsf(svr - sv));
 			const int v_far = 127 - dq, v_near = 127 - (dq >> 1);     // bit that flips towards the neighbour / bit that does not
-			if (nbits == 2) {
+			if (NB == 2) {
 				// Gray map {00, 01, 11, 10}, MSB first.  sp -> sp+1 flips the LSB when sp is even, the MSB
 				// when sp is odd; sp -> sp-1 the other way round.
 				const int gp = sp ^ (sp >> 1);
@@ -744,6 +818,37 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 				}
 			} else {
 				eb[t] = (int8_t)(sp ? -v_far : v_far);     // one bit per symbol: both neighbours flip it
+			}
+		};
+		if (SPS < 0) {               // interpolated symbols already carry the derotation
+			for (int t = lane; t < nds; t += 32) {
+				const int i = ft.d_pos[t];
+				const float2 z = lowsps_symbol(x, L, i * sps + d, interp, ofs_frac, nm, fs);
+				emit(t, i, fast_atan2f_inl(z.y, z.x));
+			}
+		} else {
+			// four symbols per lane and pass: the four sample loads (L2 hits) are in flight together
+#pragma unroll 1
+			for (int t0 = lane; t0 < nds; t0 += 128) {
+				int ii[4], qq[4];
+				float2 v[4];
+#pragma unroll
+				for (int u = 0; u < 4; u++) {
+					ii[u] = ft.d_pos[min(t0 + 32 * u, nds - 1)];
+					qq[u] = sample_of(ii[u]);
+					v[u] = __ldg(&x[qq[u]]);
+				}
+#pragma unroll
+				for (int u = 0; u < 4; u++) {
+					if (t0 + 32 * u < nds) {
+						const float th = fast_atan2f_inl(v[u].y - nm.ai, v[u].x - nm.ar);
+						const float a1 = fs * (float)qq[u];
+						const float k = rintf(a1 * INV_2PI);
+						float r = fmaf(k, -TWO_PI_HI, a1);
+						r = fmaf(k, -TWO_PI_LO, r);
+						emit(t0 + 32 * u, ii[u], th + r);
+					}
+				}
 			}
 		}
 	}
@@ -777,6 +882,8 @@ cudaError_t launch_demod(const DemodArgs &a, const BurstTab *d_bts, const BurstT
 					int lo = h_bts[i].s_pos[s][c] * a.sps;
 					int hi = lo + (h_bts[i].s_len[s][c] - 1 + 3) * a.sps + w;     // + 3 zero-padded taps
 					hi = hi > a.win_len ? a.win_len : hi;
+					lo &= ~1;                     // whole pairs of samples (16-byte stores into the region buffer)
+					hi = (hi + 1) & ~1;
 					if (ni < 64 && lo < hi)
 						iv[ni++] = {lo, hi};
 				}
@@ -801,8 +908,14 @@ cudaError_t launch_demod(const DemodArgs &a, const BurstTab *d_bts, const BurstT
 			rg.off[r] = rg.total;
 			rg.total += (rg.len[r] + 1) & ~1;
 		}
+		if (n_bt > MAX_BT)
+			return cudaErrorInvalidValue;
+		for (int i = 0; i < n_bt; i++)
+			for (int s = 0; s < h_bts[i].n_sync; s++)
+				for (int c = 0; c < h_bts[i].n_chunk[s]; c++)
+					rg.slot[i][s][c] = (uint8_t)rg.n_slot++;
 	}
-	const size_t wb = (warp_smem_bytes(rg.total, w) + 15) & ~(size_t)15;
+	const size_t wb = (warp_smem_bytes(rg.total, w, rg.n_slot) + 15) & ~(size_t)15;
 	const size_t smem = wb * DM_WARPS;
 	if (smem > 227 * 1024)
 		return cudaErrorInvalidValue;
@@ -822,10 +935,11 @@ cudaError_t launch_demod(const DemodArgs &a, const BurstTab *d_bts, const BurstT
 	}
 	if (dev >= 64 || attr_set[dev] < smem) {
 		cudaError_t e = cudaSuccess;
-		const void *fns[5] = {(const void *)demod_kernel<0, 4>, (const void *)demod_kernel<0, 0>,
-		                      (const void *)demod_kernel<1, 4>, (const void *)demod_kernel<1, 0>,
-		                      (const void *)demod_kernel<0, -1>};
-		for (int i = 0; i < 5 && e == cudaSuccess; i++)
+		const void *fns[8] = {(const void *)demod_kernel<0, 4, 1>, (const void *)demod_kernel<0, 4, 2>,
+		                      (const void *)demod_kernel<0, 0, 1>, (const void *)demod_kernel<0, 0, 2>,
+		                      (const void *)demod_kernel<0, -1, 1>, (const void *)demod_kernel<0, -1, 2>,
+		                      (const void *)demod_kernel<1, 4, 2>, (const void *)demod_kernel<1, 0, 2>};
+		for (int i = 0; i < 8 && e == cudaSuccess; i++)
 			e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if (e != cudaSuccess)
 			return e;
@@ -842,7 +956,7 @@ cudaError_t launch_demod(const DemodArgs &a, const BurstTab *d_bts, const BurstT
 	}
 	const int sms = dev < 64 ? n_sm[dev] : 148;
 	int per_sm = (int)((227 * 1024) / (smem + sizeof(FlatTab) + 1024));
-	per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+	per_sm = per_sm < 1 ? 1 : (per_sm > DM_MIN_CTAS ? DM_MIN_CTAS : per_sm);
 	if (const char *e = getenv("GMR1B200_DEMOD_CTAS")) {     // tuning knob: resident CTAs per SM
 		const int v = atoi(e);
 		if (v >= 1 && v < per_sm)
@@ -851,16 +965,21 @@ cudaError_t launch_demod(const DemodArgs &a, const BurstTab *d_bts, const BurstT
 	int grid = (a.n + DM_WARPS - 1) / DM_WARPS;
 	if (grid > sms * per_sm)
 		grid = sms * per_sm;
-	if (mode == 0 && a.sps < 4)
-		demod_kernel<0, -1><<<grid, DM_WARPS * 32, smem, st>>>(a, d_bts, n_bt, (int)wb, rg);
-	else if (mode == 0 && a.sps == 4)
-		demod_kernel<0, 4><<<grid, DM_WARPS * 32, smem, st>>>(a, d_bts, n_bt, (int)wb, rg);
-	else if (mode == 0)
-		demod_kernel<0, 0><<<grid, DM_WARPS * 32, smem, st>>>(a, d_bts, n_bt, (int)wb, rg);
-	else if (a.sps == 4)
-		demod_kernel<1, 4><<<grid, DM_WARPS * 32, smem, st>>>(a, d_bts, n_bt, (int)wb, rg);
+	const int nb = h_bts[0].nbits;
+	if (nb != 1 && nb != 2)
+		return cudaErrorInvalidValue;
+#define DM_LAUNCH(M, S, B) demod_kernel<M, S, B><<<grid, DM_WARPS * 32, smem, st>>>(a, d_bts, n_bt, (int)wb, rg)
+	if (mode == 0 && a.sps < 4) {
+		if (nb == 1) DM_LAUNCH(0, -1, 1); else DM_LAUNCH(0, -1, 2);
+	} else if (mode == 0 && a.sps == 4) {
+		if (nb == 1) DM_LAUNCH(0, 4, 1); else DM_LAUNCH(0, 4, 2);
+	} else if (mode == 0) {
+		if (nb == 1) DM_LAUNCH(0, 0, 1); else DM_LAUNCH(0, 0, 2);
+	} else if (a.sps == 4)
+		DM_LAUNCH(1, 4, 2);
 	else
-		demod_kernel<1, 0><<<grid, DM_WARPS * 32, smem, st>>>(a, d_bts, n_bt, (int)wb, rg);
+		DM_LAUNCH(1, 0, 2);
+#undef DM_LAUNCH
 	return cudaGetLastError();
 }
 

@@ -4,7 +4,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgmr1_b200.so")
+LIB_PATH = os.environ.get("GMR1B200_LIB") or os.path.join(_HERE, "libgmr1_b200.so")   # env: A/B builds only
 
 _P = ctypes.c_void_p
 _I = ctypes.c_int
