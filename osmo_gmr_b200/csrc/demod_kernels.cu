@@ -121,15 +121,6 @@ __device__ __forceinline__ float ld_acc(const float *acc, int k, int len)
 	return ((unsigned)k < (unsigned)len) ? acc[k] : 0.0f;
 }
 
-// sinc weight of this lane's tap for a position with fractional part `frac` (a multiple of 1/512)
-__device__ __forceinline__ float tap_weight(const TapLane &tp, float frac)
-{
-	const float S = c_sinpi512[(int)(frac * 512.0f)];
-	const float x = fmaf(-PI_F, frac, tp.xj);         // pi*(j - frac)
-	const float sv = __fdividef(tp.sgn * S, x);
-	return fabsf(x) >= 0.01f ? sv : (tp.sgn != 0.0f ? 1.0f : 0.0f);      // osmo_sinc
-}
-
 // osmo_cxvec_peak_energy_find(acc, 3, PEAK_EARLY_LATE, &peak) on a real vector; all lanes
 // return the same position / peak value
 __device__ float peak_early_late(const float *acc, int w, const TapLane &tp, int lane, float &peak_val)
@@ -169,36 +160,54 @@ __device__ float peak_early_late(const float *acc, int w, const TapLane &tp, int
 
 	// The search starts at mwi-1 and moves by less than 1 in total, so floor(early) is mwi-2 or
 	// mwi-1 (mwi-1 .. mwi for the final interpolation): tap j of this lane only ever reads
-	// acc[mwi-2+j .. mwi+2+j].  Preload those five values once.
+	// acc[mwi-2+j .. mwi+2+j].  Preload those five values once, with the sign -(-1)^j of the tap folded in.
 	const int kb = mwi - 2 + tp.j;
-	const float c0 = ld_acc(acc, kb, w), c1 = ld_acc(acc, kb + 1, w), c2 = ld_acc(acc, kb + 2, w),
-	            c3 = ld_acc(acc, kb + 3, w), c4 = ld_acc(acc, kb + 4, w);
-	const float fbase = (float)(mwi - 2);
+	const float c0 = tp.sgn * ld_acc(acc, kb, w), c1 = tp.sgn * ld_acc(acc, kb + 1, w), c2 = tp.sgn * ld_acc(acc, kb + 2, w),
+	            c3 = tp.sgn * ld_acc(acc, kb + 3, w), c4 = tp.sgn * ld_acc(acc, kb + 4, w);
+	const float fbase = (float)(mwi - 2), fj = (float)tp.j;
 	const bool up = lane & 16;
 
-	float early = (float)(mwi - 1), incr = 0.5f;
+	// Step 1 sits on an integer position: the interpolation there is the sample itself.
+	float early = (float)(mwi - 1), incr = 0.25f;
+	bool live;
+	{
+		const float e = ld_acc(acc, mwi - 1, w), l = ld_acc(acc, mwi + 1, w);
+		const float e2 = e * e, l2 = l * l;
+		live = e2 != l2;
+		early += e2 < l2 ? 0.5f : (live ? -0.5f : 0.0f);
+	}
+	// Steps 2..9 (incr = 1/4 .. 1/512, the reference stops when incr <= 1/1024) visit positions with a
+	// fractional part f in (0, 1): every sinc weight is sin(pi f) * -(-1)^j / (pi (j - f)), and the early and
+	// the late gate share f, so the comparison e^2 < l^2 only needs  sum_j -(-1)^j acc[.+j] / (j - f)
+	// for the two gates - no sine, one reciprocal per tap.
+	if (live) {
 #pragma unroll 1
-	for (int it = 0; it < 9; it++) {                  // incr = 1/2 .. 1/512 (> 1/1024)
-		const float fl = floorf(early);
-		const float wgt = tap_weight(tp, early - fl);
-		const bool hi = fl != fbase;                  // floor(early) == mwi-1
-		const float te = (hi ? c1 : c0) * wgt, tl = (hi ? c3 : c2) * wgt;      // early gate, late gate (+2)
-		// one folded shuffle tree for both sums: lower half-warp ends with early, upper with late
-		float v = (up ? tl : te) + __shfl_xor_sync(0xffffffffu, up ? te : tl, 16);
+		for (int it = 1; it < 9; it++) {
+			const float fl = floorf(early);
+			float r;
+			asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fj - (early - fl)));
+			const bool hi = fl != fbase;                  // floor(early) == mwi-1
+			const float te = (hi ? c1 : c0) * r, tl = (hi ? c3 : c2) * r;      // early gate, late gate (+2)
+			// one folded shuffle tree for both sums: lower half-warp ends with early, upper with late
+			float v = (up ? tl : te) + __shfl_xor_sync(0xffffffffu, up ? te : tl, 16);
 #pragma unroll
-		for (int o = 8; o; o >>= 1)
-			v += __shfl_xor_sync(0xffffffffu, v, o);
-		const float ev = __shfl_sync(0xffffffffu, v, 0), lv = __shfl_sync(0xffffffffu, v, 16);
-		const float e2 = ev * ev, l2 = lv * lv;
-		if (e2 == l2)
-			break;
-		early += e2 < l2 ? incr : -incr;
-		incr *= 0.5f;
+			for (int o = 8; o; o >>= 1)
+				v += __shfl_xor_sync(0xffffffffu, v, o);
+			const float ov = __shfl_xor_sync(0xffffffffu, v, 16);     // the other gate
+			const float e2 = up ? ov * ov : v * v, l2 = up ? v * v : ov * ov;
+			if (e2 == l2)
+				break;
+			early += e2 < l2 ? incr : -incr;
+			incr *= 0.5f;
+		}
 	}
 	const float pos = early + 1.0f;
 	{
-		const float fl = floorf(pos);
-		const float wgt = tap_weight(tp, pos - fl);
+		// value at the peak: the full sinc weights (osmo_sinc: 1 within |x| < 0.01), one sine from the table
+		const float fl = floorf(pos), frac = pos - fl;
+		const float S = c_sinpi512[(int)(frac * 512.0f)];
+		const float x = fmaf(-PI_F, frac, tp.xj);         // pi*(j - frac)
+		const float wgt = fabsf(x) >= 0.01f ? __fdividef(S, x) : tp.sgn;
 		const int sel = (int)(fl - fbase);            // 1, 2 (or 3 when early ended on mwi exactly)
 		const float cv = sel <= 1 ? c1 : (sel == 2 ? c2 : (sel == 3 ? c3 : c4));
 		peak_val = warp_sum(cv * wgt);
@@ -647,15 +656,6 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 			load_regions(x, L, rg, sm.reg, lane);
 		else
 			__syncwarp();
-		{	// pull the window this warp works on next into L2 while it computes on this one
-			const int bn = b + gridDim.x * DM_WARPS;
-			if (bn < a.n) {
-				const char *xn = (const char *)(a.iq + (a.ofs ? a.ofs[bn] : (int64_t)bn * a.stride));
-				for (int o = lane * 128; o < L * 8; o += 32 * 128)
-					asm volatile("prefetch.global.L2 [%0];" ::"l"(xn + o));
-			}
-		}
-
 		if (MODE == 1) {
 			const float e_toa = a.e_toa ? a.e_toa[b] : a.e_toa0;
 			int p_id = -1, p_sid = -1;
