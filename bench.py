@@ -156,7 +156,7 @@ def run_reference_arm(args):
     import sigen
     o = oracle_lib.load()
     cores = os.cpu_count() or 1
-    per_kind = min(16384, 256 * cores)             # bounded sample: ~0.25 ms of C work per burst
+    per_kind = min(32768, 1024 * cores)            # bounded sample: ~0.15 ms of C work per burst and core
     files = {}
     for kind in ("bcch", "dc6"):
         p = burst_params(per_kind, kind, 77 + BT[kind])
