@@ -253,6 +253,14 @@ int gmr1b200_fcch_rough_multi(int fcch_type, const float *iq, int64_t win_len, i
  * key [8], dl / ul [nbits] ubits, either may be NULL */
 void gmr1b200_a5(int n, const uint8_t *key, uint32_t fn, int nbits, gmr1b200_ubit_t *dl, gmr1b200_ubit_t *ul);
 
+/* The same for n (Kc, frame number) pairs in one launch on the device: unit i gets
+ * gmr1_a5(alg[i] or alg0, key + 8 i, fn[i], nbits, dl + i*stride, ul + i*stride), src/l1/a5.c:57.  The rows
+ * are what the ciphered *_decode_batch entry points take as ciph, so the masks need never exist on the host.
+ * dl or ul may be NULL; stride >= nbits (the stride - nbits bytes behind each row are unspecified afterwards);
+ * every pointer host or device memory. */
+int gmr1b200_a5_batch(const int32_t *alg, int alg0, const uint8_t *key, const uint32_t *fn, int nbits, int stride,
+                      gmr1b200_ubit_t *dl, gmr1b200_ubit_t *ul, int n, void *stream);
+
 /* ---- stage 1: FCCH chirp acquisition ----------------------------------------------------------
  * fcch_type: 0 = gmr1_fcch_burst (sweep 0.32, 117 symbols), 1 = gmr1_fcch3_lband_burst (0.32, 468),
  * 2 = gmr1_fcch3_sband_burst (0.16, 468)  (reference src/sdr/fcch.c:50-70, sdr/fcch.h:42-44).

@@ -340,3 +340,25 @@ int gmr1b200_pi4cxpsk_mod_order_batch(const float *iq, int64_t iq_len, const int
 }
 
 }  // extern "C"
+
+extern "C" int gmr1b200_a5_batch(const int32_t *alg, int alg0, const uint8_t *key, const uint32_t *fn, int nbits,
+                                 int stride, uint8_t *dl, uint8_t *ul, int n, void *stream)
+{
+	if (n < 0 || nbits < 0 || stride < nbits || (!dl && !ul) || (n && (!key || !fn)))
+		return set_err(-EINVAL, "a5_batch: bad argument");
+	if (n == 0 || nbits == 0)
+		return 0;
+	Stage s(stream);
+	A5Args a = {};
+	a.alg = s.in(alg, (size_t)n); a.alg0 = alg0;
+	a.key = s.in(key, (size_t)n * 8); a.fn = s.in(fn, (size_t)n);
+	a.n = n; a.nbits = nbits; a.stride = stride;
+	a.dl = s.out(dl, (size_t)n * stride); a.ul = s.out(ul, (size_t)n * stride);
+	cudaError_t e = cudaSuccess;
+	if (!s.failed()) {
+		e = launch_a5(a, (cudaStream_t)stream);
+		if (e == cudaSuccess)
+			g_launches.fetch_add(1);
+	}
+	return s.finish(e, "a5 kernel");
+}

@@ -71,6 +71,17 @@ struct MiscArgs {
 cudaError_t launch_dkab(const MiscArgs &a, cudaStream_t st);
 cudaError_t launch_mod_order(const MiscArgs &a, cudaStream_t st);
 
+// ---- A5 keystreams
+struct A5Args {
+	const int32_t *alg;          // [n] 0 / 1 or NULL (then alg0)
+	int32_t        alg0;
+	const uint8_t *key;          // [n][8]
+	const uint32_t *fn;          // [n]
+	int32_t        n, nbits, stride;
+	uint8_t       *dl, *ul;      // [n][stride] ubits, either may be NULL
+};
+cudaError_t launch_a5(const A5Args &a, cudaStream_t st);
+
 // ---- workload synthesis
 struct SynthArgs {
 	const uint8_t *ebits;       // [n][ebits_stride] hard bits

@@ -182,11 +182,12 @@ class Oracle:
         fn.argtypes = [P, ctypes.c_int, ctypes.c_float]
         return fn(ctypes.addressof(cv), sps, float(freq_shift))
 
-    def a5(self, n, key, fn, nbits):
+    def a5(self, n, key, fn, nbits, both=False):
         dl = np.zeros(nbits, np.uint8)
+        ul = np.zeros(nbits, np.uint8)
         k = np.ascontiguousarray(key, np.uint8)
-        self.c.gmr1_a5(n, p(k), ctypes.c_uint32(fn), nbits, p(dl), None)
-        return dl
+        self.c.gmr1_a5(n, p(k), ctypes.c_uint32(fn), nbits, p(dl), p(ul) if both else None)
+        return (dl, ul) if both else dl
 
 
 def load():

@@ -44,6 +44,12 @@ def test_tch3_speech_ciphered(gpu_lib, oracle):
     f0 = rng.integers(0, 256, (n, 10), dtype=np.uint8)
     f1 = rng.integers(0, 256, (n, 10), dtype=np.uint8)
     ciph = np.stack([oracle.a5(1 if i % 2 else 0, key, 1000 + i, 208) for i in range(n)])   # A5/1 and A5/0 halves
+    # the same masks from the device-side generator; the decoder below consumes these
+    alg = (np.arange(n) % 2).astype(np.int32)
+    ciph_g = np.zeros((n, 208), np.uint8)
+    gpu_lib.call("gmr1b200_a5_batch", alg, 0, np.tile(key, (n, 1)), (1000 + np.arange(n)).astype(np.uint32), 208, 208,
+                 ciph_g, None, n, None)
+    assert (ciph_g == ciph).all()
     hard = np.zeros((n, 212), np.uint8)
     for i in range(n):
         gpu_lib.call("gmr1b200_tch3_encode", hard[i], f0[i], f1[i], rng.integers(0, 2, 4, dtype=np.uint8), ciph[i], 0)
@@ -51,7 +57,7 @@ def test_tch3_speech_ciphered(gpu_lib, oracle):
     eb, _, _ = _demod(gpu_lib, "nt3_speech", x)
     g0 = np.zeros((n, 10), np.uint8)
     g1 = np.zeros((n, 10), np.uint8)
-    gpu_lib.call("gmr1b200_tch3_decode_batch", g0, g1, None, eb, ciph, 0, None, None, n, None)
+    gpu_lib.call("gmr1b200_tch3_decode_batch", g0, g1, None, eb, ciph_g, 0, None, None, n, None)
     for i in range(n):
         _, eb_o, _, _, _ = oracle.demod("nt3_speech", x[i], SPS, 0.0)
         o0, o1, _, _, _ = oracle.tch3_decode(eb_o, ciph[i], 0)

@@ -1,6 +1,7 @@
 """GPU parity: CUDA channel-decode kernels through the C ABI vs the oracle, bit-exact.
 Sizes straddle the 128-codeword CTA tile so both the TMA bulk path (full tiles) and the
 cooperative tail path are exercised; host-pointer and device-pointer entry are both covered."""
+import numpy as np
 import pytest
 
 import decode_parity as dp
@@ -59,3 +60,33 @@ def test_empty_and_single(gpu_lib, oracle):
     gpu_lib.call("gmr1b200_bcch_decode_batch", l2, e, None, None, 0, None)   # n = 0 is a no-op
     be = GpuBackend(gpu_lib)
     dp.check_simple(be, oracle, "bcch", CH["BCCH"], 424, 9, 29)               # < one tile
+
+
+@pytest.mark.parametrize("nbits,stride", [(208, 208), (658, 658), (658, 660), (96, 100), (5, 7)])
+def test_a5_batch(gpu_lib, oracle, nbits, stride):
+    """gmr1b200_a5_batch vs gmr1_a5 (src/l1/a5.c:57): downlink and uplink streams, A5/0 and A5/1 units mixed,
+    word-aligned and odd row strides, host and device pointers"""
+    rng = np.random.default_rng(nbits * 7 + stride)
+    n = 300
+    keys = rng.integers(0, 256, (n, 8), dtype=np.uint8)
+    keys[0] = 0
+    keys[1] = 255
+    fn = rng.integers(0, 1 << 19, n).astype(np.uint32)
+    fn[:3] = [0, (1 << 19) - 1, 0x5a5a5]
+    alg = rng.integers(0, 2, n).astype(np.int32)
+    alg[:3] = 1
+    dl = np.full((n, stride), 9, np.uint8)
+    ul = np.full((n, stride), 9, np.uint8)
+    gpu_lib.call("gmr1b200_a5_batch", alg, 0, keys, fn, nbits, stride, dl, ul, n, None)
+    for i in range(n):
+        d, u = oracle.a5(int(alg[i]), keys[i], int(fn[i]), nbits, both=True)
+        assert (dl[i, :nbits] == d).all() and (ul[i, :nbits] == u).all(), i
+    # downlink only, one algorithm for all, device memory
+    import torch
+    dk, dfn = torch.from_numpy(keys).cuda(), torch.from_numpy(fn.view(np.int32)).cuda()
+    ddl = torch.zeros((n, stride), dtype=torch.uint8, device="cuda")
+    gpu_lib.call("gmr1b200_a5_batch", None, 1, dk, dfn, nbits, stride, ddl, None, n, None)
+    torch.cuda.synchronize()
+    got = ddl.cpu().numpy()
+    for i in range(0, n, 17):
+        assert (got[i, :nbits] == oracle.a5(1, keys[i], int(fn[i]), nbits)).all(), i
