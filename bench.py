@@ -295,6 +295,10 @@ class Workload:
 
 
 def run_gpu_arm(args):
+    # the JSON line must be the only thing on stdout: library chatter (e.g. NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -553,7 +557,8 @@ def run_gpu_arm(args):
         "cpu_baseline": cpu,
         "clocks": sampler.summary(),
     }
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

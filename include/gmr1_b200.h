@@ -248,6 +248,25 @@ int gmr1b200_pi4cxpsk_detect_desc_batch(const struct gmr1b200_burst_desc *descs,
 int gmr1b200_fcch_rough_multi(int fcch_type, const float *iq, int64_t win_len, int sps, float freq_shift,
                               int32_t *toa, int N, void *stream);
 
+/* ---- receiver frame loop for n channels in lock step --------------------------------
+ * replaces process_bcch (src/gmr1_rx.c:853-895) with rx_bcch (:747-803), rx_ccch (:805-851, without the TCH3
+ * hand-off), bcch_tdma_align (:194-236), burst_map / burst_energy (:149-182) for n channels at once.
+ * Channel i is the recording iq[rec_ofs[i] .. + rec_len[i]) (complex samples) and starts as the reference's
+ * chan_desc after FCCH acquisition: align0[i] (samples from the start of the recording; what
+ * gmr1b200_fcch_acquire_batch returns plus the offset of its search window), freq_err0[i] (rad/symbol, NULL = 0),
+ * fn = sa_sirfn_delay = sa_bcch_stn = 0.  Frame by frame, every channel demodulates + decodes the BCCH burst
+ * (SI-relative frame 2 of 8) or the CCCH burst (frames 1, 3..7, only when the window energy reaches half of the
+ * last BCCH window's), feeds TOA / frequency error / SI1 timing of every good BCCH burst back into its state,
+ * and stops when fewer than two frames of samples remain; all of it on the device, no host round trip.
+ * Outputs, [n][max_frames] each (l2: [n][max_frames][24]): kind (0 nothing, 1 BCCH, 2 CCCH), fn (frame number
+ * the channel believed in), crc (0 ok, -1 where kind = 0), conv (Viterbi metric), l2; n_frames [n] frames
+ * walked; align_out / freq_err_out [n] final tracking state (may be NULL).  Frames beyond max_frames are not
+ * walked.  Every pointer host or device memory. */
+int gmr1b200_rx_bcch_batch(const float *iq, int64_t iq_len, const int64_t *rec_ofs, const int32_t *rec_len,
+                           const int32_t *align0, const float *freq_err0, int sps, int n, int max_frames,
+                           int32_t *kind, int32_t *fn, int32_t *crc, int32_t *conv, uint8_t *l2,
+                           int32_t *n_frames, int32_t *align_out, float *freq_err_out, void *stream);
+
 /* ---- A5 cipher stream (host; input to the ciphered decoders) ------------------------------------
  * replaces gmr1_a5 / gmr1_a5_1, src/l1/a5.c:57,226 (l1/a5.h:37-41): n = 0 (all zero) or 1 (A5/1-GMR);
  * key [8], dl / ul [nbits] ubits, either may be NULL */

@@ -107,7 +107,10 @@ __global__ void __launch_bounds__(TPC_T) decode_tpc_kernel(const DecodeArgs a)
 
 	const int tid = threadIdx.x;
 	const int base = blockIdx.x * TPC_T;
-	const int cnt = min(TPC_T, a.n - base);
+	const int n_eff = a.n_dev ? min(a.n, *a.n_dev) : a.n;
+	if (base >= n_eff)
+		return;                  // whole CTA, before any barrier
+	const int cnt = min(TPC_T, n_eff - base);
 
 	// ---- phase 1: stage the tile
 	const bool plain = !chan_is_t9(CH) && (chan_n_ciph(CH) == 0 || a.ciph == nullptr);
@@ -177,7 +180,7 @@ __global__ void __launch_bounds__(DC12_WARPS * 32) decode_dc12_kernel(const Deco
 	extern __shared__ __align__(16) uint8_t smem[];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int unit = blockIdx.x * DC12_WARPS + warp;
-	if (unit >= a.n)
+	if (unit >= (a.n_dev ? min(a.n, *a.n_dev) : a.n))
 		return;
 	Dc12Smem &s = reinterpret_cast<Dc12Smem *>(smem)[warp];
 	const uint16_t *g = c_g[CH_DC12];

@@ -31,6 +31,7 @@ struct DecodeArgs {
 	int32_t        tch3_m;    // tch3 multiplexing mode (0 / 1)
 	int32_t        t9_rows;   // tch9: ebits is [n][648] already deciphered / descrambled / inter-burst
 	                          //       de-interleaved (what gmr1_deinterleave_inter returns); no side outputs
+	const int32_t *n_dev;     // optional device-side unit count (<= n): units beyond it are skipped (rx scheduler)
 };
 
 // device-resident (or host, in the emulation) tables one channel needs

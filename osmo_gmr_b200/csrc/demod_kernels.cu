@@ -638,7 +638,8 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 	constexpr float TWO_PI_HI = 6.28125f, TWO_PI_LO = 1.9353071795864769e-3f, INV_2PI = 0.15915494309189533577f;
 	float fs_taps = __int_as_float(0x7fc00000);     // frequency shift the cached taps were built for (NaN: none)
 
-	for (int b = blockIdx.x * DM_WARPS + warp; b < a.n; b += gridDim.x * DM_WARPS) {
+	const int n_eff = a.n_dev ? min(a.n, *a.n_dev) : a.n;
+	for (int b = blockIdx.x * DM_WARPS + warp; b < n_eff; b += gridDim.x * DM_WARPS) {
 		const float2 *x = a.iq + (a.ofs ? a.ofs[b] : (int64_t)b * a.stride);
 		const float freq_shift = a.freq_shift ? a.freq_shift[b] : a.freq_shift0;
 		const float fs = (freq_shift - bt.rotation) / (float)sps;

@@ -27,6 +27,7 @@ struct DemodArgs {
 	float         *freq_err;    // [n] or NULL
 	float         *pwr;         // [n] or NULL (sync power; detect: after the e_toa weighting)
 	int32_t        sync_reset;  // 0 = reference behaviour (accumulator never cleared between candidate sequences)
+	const int32_t *n_dev;       // optional device-side burst count (<= n): bursts beyond it are skipped (rx scheduler)
 };
 
 // d_bts: n_bt burst descriptors in device memory, h_bts: the same on the host (for geometry)

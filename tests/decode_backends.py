@@ -18,7 +18,8 @@ L2B = {0: 24, 1: 24, 2: 10, 3: 38, 4: 18, 5: 30, 6: 60, 7: 18, 8: 10, 9: 24}
 class Args(ctypes.Structure):
     _fields_ = [("ebits", P), ("ciph", P), ("n", ctypes.c_int32), ("l2", P), ("l2b", P), ("conv", P), ("conv1", P),
                 ("crc", P), ("crc2", P), ("bits_s", P), ("sacch", P), ("status", P), ("prev1", P), ("prev2", P),
-                ("sb_mask", P), ("sb_mask0", ctypes.c_int32), ("tch3_m", ctypes.c_int32), ("t9_rows", ctypes.c_int32)]
+                ("sb_mask", P), ("sb_mask0", ctypes.c_int32), ("tch3_m", ctypes.c_int32), ("t9_rows", ctypes.c_int32),
+                ("n_dev", P)]
 
 
 def _p(a):

@@ -151,6 +151,14 @@ class Oracle:
         rc = fn(self._fcch(t), ctypes.addressof(cv), sps, float(freq_shift), ctypes.addressof(toa))
         return rc, toa.value
 
+    def fcch_rough_multi(self, window, sps, freq_shift, N=16, t=0):
+        cv, keep = self._cxvec(window)
+        toa = (ctypes.c_int * N)()
+        fn = self.c.gmr1_fcch_rough_multi
+        fn.argtypes = [P, P, ctypes.c_int, ctypes.c_float, P, ctypes.c_int]
+        rc = fn(self._fcch(t), ctypes.addressof(cv), sps, float(freq_shift), ctypes.addressof(toa), N)
+        return rc, [toa[i] for i in range(max(rc, 0))]
+
     def fcch_fine(self, window, sps, freq_shift, t=0):
         cv, keep = self._cxvec(window)
         toa, fe = ctypes.c_int(-99999), ctypes.c_float()

@@ -31,7 +31,15 @@ def make(enc_bcch, enc_ccch, seconds=2.2, esn0_db=15.0, cfo_hz=300.0, frac=0.37,
         else:
             kind = "bcch" if f % 8 == 2 else "dc6"
             l2 = rng.integers(0, 256, 24, dtype=np.uint8)
-            if kind == "bcch":
+            if kind == "bcch" and tdma_si1:
+                # SI1 with a segment 2Abis (bcch_tdma_align, gmr1_rx.c:194-236): SA_BCCH_STN 0 (the burst sits on
+                # slot 0), random SA_SIRFN_DELAY / superframe / multiframe -> the frame number jumps, its phase
+                # within the 8-frame SI cycle stays
+                l2[0] = 0x08 | (l2[0] & 0x07)
+                l2[9] = 0x80 | (l2[9] & 0x03)
+                l2[10] = (l2[10] & 0x80) | (int(rng.integers(0, 16)) << 3)
+                l2[11] &= 0x3f
+            elif kind == "bcch":
                 l2[0] = (l2[0] & 0x07) | 0x10            # not an SI1 header: bcch_tdma_align() is a no-op
             else:
                 l2[1] = 0x01                             # never an IMM.ASS (gmr1_rx.c:236-239)

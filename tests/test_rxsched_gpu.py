@@ -1,0 +1,129 @@
+"""Receiver frame loop for several channels at once: gmr1b200_rx_bcch_batch against the
+reference's own application (oracle/_ref/gmr1_rx = src/gmr1_rx.c linked to the reference C libraries) run
+once per recording.  Every channel must walk the same frames with the same frame numbers, find the same
+burst kinds behind the energy gate, and report the same CRC result for every burst; Viterbi metrics agree to
+the soft-bit tolerance, the final alignment to one sample."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import recording
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "gmr1_rx")
+SPS = 4
+START_DISCARD = 8000                              # gmr1_rx.c:56
+
+
+def _reference_runs(path):
+    """parse gmr1_rx's log into one list of frames per process_bcch() call"""
+    r = subprocess.run([REF_BIN, str(SPS), path], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    runs = []
+    for l in r.stderr.split("\n"):
+        m = re.match(r"\[\+\] Processing BCCH @(\d+) .*freq_err = (-?[\d.]+) Hz", l)
+        if m:
+            runs.append({"align": int(m.group(1)), "freq_hz": float(m.group(2)), "frames": []})
+            continue
+        if not runs:
+            continue
+        m = re.match(r"\[-\]  FN:\s*(-?\d+)", l)
+        if m:
+            runs[-1]["frames"].append({"fn": int(m.group(1)), "kind": 0, "crc": None, "conv": None})
+            continue
+        if l.startswith("[.]   BCCH"):
+            runs[-1]["frames"][-1]["kind"] = 1
+        elif l.startswith("[.]   CCCH"):
+            runs[-1]["frames"][-1]["kind"] = 2
+        m = re.match(r"crc=(-?\d+), conv=(-?\d+)", l)
+        if m:
+            runs[-1]["frames"][-1]["crc"] = int(m.group(1))
+            runs[-1]["frames"][-1]["conv"] = int(m.group(2))
+    return runs
+
+
+def _acquire_like_main(o, x):
+    """main() / fcch_single_init / fcch_multi_process of gmr1_rx.c:606-741 on the oracle's functions: the
+    (align, freq_err) every process_bcch() call starts from, with freq_err as the exact float"""
+    blen = 117 * SPS
+    align = START_DISCARD
+    rc, toa = o.fcch_rough(x[align:align + (330 * 23400 * SPS) // 1000], SPS, 0.0)
+    assert rc == 0
+    align += toa
+    rc, toa, ferr = o.fcch_fine(x[align:align + blen], SPS, 0.0)
+    assert rc == 0
+    align += toa
+    ferr = np.float32(ferr)
+    base = max(align - blen, 0)
+    n, mtoa = o.fcch_rough_multi(x[base:base + (650 * 23400 * SPS) // 1000], SPS, float(-ferr), 16)
+    assert n >= 1
+    out, ref_snr, ref_fe = [], 0.0, 0.0
+    for i in range(n):
+        rc, t, fe = o.fcch_fine(x[base + mtoa[i]:base + mtoa[i] + blen], SPS, float(-ferr))
+        assert rc == 0
+        rc, snr = o.fcch_snr(x[base + mtoa[i] + t:base + mtoa[i] + t + blen], SPS, float(-(ferr + np.float32(fe))))
+        if i == 0:
+            ref_snr, ref_fe = snr, fe
+        elif snr < 2.0 or snr < ref_snr / 6.0 or 23400.0 * abs(ref_fe - fe) / (2 * np.pi) > 500.0:
+            continue
+        out.append((base + mtoa[i] + t, float(ferr)))
+    return out
+
+
+def test_rx_bcch_batch_vs_gmr1_rx(gpu_lib, oracle, tmp_path):
+    if not os.path.exists(REF_BIN):
+        pytest.skip("oracle/_ref/gmr1_rx not built (needs /root/reference at build time)")
+    cases = [dict(esn0_db=15.0, cfo_hz=300.0, seed=1), dict(esn0_db=8.0, cfo_hz=-450.0, seed=2, seconds=2.6),
+             dict(esn0_db=12.0, cfo_hz=120.0, seed=3, tdma_si1=True), dict(esn0_db=4.0, cfo_hz=-60.0, seed=4, frac=0.81),
+             dict(esn0_db=20.0, cfo_hz=700.0, seed=5, tdma_si1=True, seconds=3.0, start=12345)]
+    recs, tasks, ref = [], [], []
+    for ci, kw in enumerate(cases):
+        x, _ = recording.make(lambda l2: oracle.encode("bcch", 424, l2), lambda l2: oracle.encode("ccch", 432, l2), **kw)
+        path = str(tmp_path / f"rec{ci}.cfile")
+        x.tofile(path)
+        runs = _reference_runs(path)
+        acq = _acquire_like_main(oracle, x)
+        assert [r["align"] for r in runs] == [a for a, _ in acq]            # the harness mirrors main()
+        for r, (a, fe) in zip(runs, acq):
+            assert abs(r["freq_hz"] - 23400.0 * fe / (2 * np.pi)) <= 0.06
+            tasks.append((ci, a, fe))
+            ref.append(r)
+        recs.append(x)
+    rec_len = np.array([len(x) for x in recs], np.int32)
+    rec_ofs = np.concatenate([[0], np.cumsum(rec_len[:-1])]).astype(np.int64)
+    iq = np.ascontiguousarray(np.concatenate(recs)).view(np.float32)
+    n = len(tasks)
+    t_ofs = np.array([rec_ofs[c] for c, _, _ in tasks], np.int64)
+    t_len = np.array([rec_len[c] for c, _, _ in tasks], np.int32)
+    align0 = np.array([a for _, a, _ in tasks], np.int32)
+    ferr0 = np.array([f for _, _, f in tasks], np.float32)
+    F = 96
+    kind = np.zeros((n, F), np.int32)
+    fn = np.zeros((n, F), np.int32)
+    crc = np.zeros((n, F), np.int32)
+    conv = np.zeros((n, F), np.int32)
+    l2 = np.zeros((n, F, 24), np.uint8)
+    nfr = np.zeros(n, np.int32)
+    align1 = np.zeros(n, np.int32)
+    ferr1 = np.zeros(n, np.float32)
+    gpu_lib.call("gmr1b200_rx_bcch_batch", iq, len(iq) // 2, t_ofs, t_len, align0, ferr0, SPS, n, F,
+                 kind, fn, crc, conv, l2, nfr, align1, ferr1, None)
+    n_burst = n_ok = 0
+    for i, r in enumerate(ref):
+        fr = r["frames"]
+        assert nfr[i] == len(fr), (i, nfr[i], len(fr))
+        for f, e in enumerate(fr):
+            assert fn[i, f] == e["fn"], (i, f)
+            rk = e["kind"] if e["crc"] is not None else 0       # "[.]   BCCH" is printed before the window is mapped
+            assert kind[i, f] == rk, (i, f, kind[i, f], rk)
+            if rk:
+                assert crc[i, f] == e["crc"], (i, f)
+                assert abs(int(conv[i, f]) - e["conv"]) <= 8, (i, f)
+                n_burst += 1
+                n_ok += e["crc"] == 0
+    assert n_burst >= 200 and n_ok >= 0.8 * n_burst
+    assert any(r["frames"][0]["fn"] != r["frames"][-1]["fn"] - len(r["frames"]) + 1 for r in ref)   # an SI1 re-timed a channel
