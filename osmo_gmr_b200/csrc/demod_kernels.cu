@@ -41,6 +41,14 @@
 namespace gmr1 {
 
 static constexpr int DM_WARPS = 4;
+#define DM_PRAGMA(x) _Pragma(#x)
+#define DM_UNROLL(n) DM_PRAGMA(unroll n)
+#ifndef DM_STATS_UNROLL
+#define DM_STATS_UNROLL 4      // 16-byte loads of the statistics pass in flight per lane
+#endif
+#ifndef DM_SYM_BATCH
+#define DM_SYM_BATCH 4         // data symbols per lane whose sample loads are issued together
+#endif
 #ifndef DM_MIN_CTAS
 #define DM_MIN_CTAS 8          // resident CTAs per SM the register allocation is capped for
 #endif
@@ -279,7 +287,7 @@ __device__ __forceinline__ Norm load_stats_t(const float2 *__restrict__ x, int L
 		const float4 *x4 = reinterpret_cast<const float4 *>(x);
 		float4 *reg4 = reinterpret_cast<float4 *>(reg);
 		const int L2 = L >> 1;
-#pragma unroll 4
+DM_UNROLL(DM_STATS_UNROLL)
 		for (int i = lane; i < L2; i += 32) {
 			const float4 v = __ldg(&x4[i]);
 			if (FILL) {
@@ -830,17 +838,17 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 		} else {
 			// four symbols per lane and pass: the four sample loads (L2 hits) are in flight together
 #pragma unroll 1
-			for (int t0 = lane; t0 < nds; t0 += 128) {
-				int ii[4], qq[4];
-				float2 v[4];
+			for (int t0 = lane; t0 < nds; t0 += 32 * DM_SYM_BATCH) {
+				int ii[DM_SYM_BATCH], qq[DM_SYM_BATCH];
+				float2 v[DM_SYM_BATCH];
 #pragma unroll
-				for (int u = 0; u < 4; u++) {
+				for (int u = 0; u < DM_SYM_BATCH; u++) {
 					ii[u] = ft.d_pos[min(t0 + 32 * u, nds - 1)];
 					qq[u] = sample_of(ii[u]);
 					v[u] = __ldg(&x[qq[u]]);
 				}
 #pragma unroll
-				for (int u = 0; u < 4; u++) {
+				for (int u = 0; u < DM_SYM_BATCH; u++) {
 					if (t0 + 32 * u < nds) {
 						const float th = fast_atan2f_inl(v[u].y - nm.ai, v[u].x - nm.ar);
 						const float a1 = fs * (float)qq[u];
