@@ -42,3 +42,15 @@ def gpu_lib():
     L = osmo_gmr_b200.lib()      # raises if the extension is missing: no CPU fallback
     L.init(0)
     return L
+
+
+@pytest.fixture
+def port_noquirk(monkeypatch):
+    """the oracle port with the sync accumulator reset per candidate (GMR1_ORACLE_SYNC_RESET)"""
+    import os
+    import subprocess
+    import oracle_lib
+    so = os.path.join(oracle_lib.ROOT, "oracle", "liboracle.so")
+    subprocess.check_call(["make", "-s", "-C", os.path.join(oracle_lib.ROOT, "oracle"), "liboracle.so"])
+    monkeypatch.setenv("GMR1_ORACLE_SYNC_RESET", "1")
+    return oracle_lib.Oracle(so, "port")

@@ -87,18 +87,6 @@ def test_facch3_four_bursts(gpu_lib, oracle):
     assert (crc == 0).mean() > 0.9 and (out[crc == 0] == l2[crc == 0]).all()
 
 
-@pytest.fixture
-def port_noquirk(monkeypatch):
-    """the oracle port with the sync accumulator reset per candidate (GMR1_ORACLE_SYNC_RESET)"""
-    import os
-    import subprocess
-    import oracle_lib
-    so = os.path.join(oracle_lib.ROOT, "oracle", "liboracle.so")
-    subprocess.check_call(["make", "-s", "-C", os.path.join(oracle_lib.ROOT, "oracle"), "liboracle.so"])
-    monkeypatch.setenv("GMR1_ORACLE_SYNC_RESET", "1")
-    return oracle_lib.Oracle(so, "port")
-
-
 def test_facch9_and_tch9_over_nt9(gpu_lib, oracle, port_noquirk):
     """NT9 carries FACCH9 (sync 0) or TCH9 (sync 1).  With the reference's accumulator quirk sync 1
     always wins and FACCH9 never decodes (checked: GPU == reference).  With the opt-in reset both
