@@ -53,6 +53,8 @@ static int run_decode(int ch, DecodeArgs a, int n_in, int n_ciph, int l2_bytes, 
 	a.bits_s = s.out(a.bits_s, n * bits_s_per);
 	a.sacch  = s.out(a.sacch, n * 10);
 	a.status = s.out(a.status, n * 4);
+	if (const size_t sb = decode_scratch_bytes(ch, a.n))
+		a.dec_scratch = s.tmp<uint8_t>(sb);
 	cudaError_t e = cudaSuccess;
 	if (!s.failed()) {
 		e = launch_decode(ch, a, (cudaStream_t)stream);

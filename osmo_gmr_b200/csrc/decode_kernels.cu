@@ -94,8 +94,12 @@ __global__ void __launch_bounds__(TPC_T) decode_tpc_kernel(const DecodeArgs a)
 	extern __shared__ __align__(16) uint8_t smem[];
 	constexpr int NIN = chan_n_in(CH), NROW = chan_n_row(CH);
 	int8_t *rows = (int8_t *)smem;                                    // [TPC_T][NROW], unpadded
-	uint8_t *dec = smem + tpc_rows_bytes(CH);                          // [steps][words][TPC_T]
-	uint64_t *bar = (uint64_t *)(dec + TPC_T * chan_dec_bytes(CH));
+	// survivor decisions [steps][words][slots]: in the caller's scratch (slot = unit, all units of the launch
+	// side by side: coalesced 64-byte stores per warp and step) or, without scratch, behind the rows in
+	// shared memory (slot = thread)
+	const bool gdec = a.dec_scratch != nullptr;
+	uint8_t *dec = gdec ? a.dec_scratch : smem + tpc_rows_bytes(CH);
+	uint64_t *bar = (uint64_t *)(smem + tpc_rows_bytes(CH) + (gdec ? 0 : TPC_T * chan_dec_bytes(CH)));
 
 	TabRef tb;
 	tb.g = c_g[CH];
@@ -136,10 +140,11 @@ __global__ void __launch_bounds__(TPC_T) decode_tpc_kernel(const DecodeArgs a)
 
 	// ---- phase 2: one codeword per thread
 	if (tid < cnt) {
+		const int T = gdec ? (int)gridDim.x * TPC_T : TPC_T, t = gdec ? base + tid : tid;
 		if constexpr (CH == CH_TCH3)
-			decode_unit_tch3(tb, a, base + tid, rows + tid * NROW, (uint32_t *)dec, TPC_T, tid);
+			decode_unit_tch3(tb, a, base + tid, rows + tid * NROW, (uint32_t *)dec, T, t);
 		else
-			decode_unit_k5<CH>(tb, a, base + tid, rows + tid * NROW, (uint16_t *)dec, TPC_T, tid);
+			decode_unit_k5<CH>(tb, a, base + tid, rows + tid * NROW, (uint16_t *)dec, T, t);
 	}
 }
 
@@ -158,7 +163,8 @@ static cudaError_t launch_tpc(const DecodeArgs &a, cudaStream_t st)
 			attr_done[dev] = true;
 	}
 	const int grid = (a.n + TPC_T - 1) / TPC_T;
-	decode_tpc_kernel<CH><<<grid, TPC_T, smem, st>>>(a);
+	const int smem_used = a.dec_scratch ? tpc_rows_bytes(CH) + 16 : smem;
+	decode_tpc_kernel<CH><<<grid, TPC_T, smem_used, st>>>(a);
 	return cudaGetLastError();
 }
 
@@ -294,6 +300,17 @@ static cudaError_t launch_dc12(const DecodeArgs &a, cudaStream_t st)
 	}
 	decode_dc12_kernel<<<(a.n + DC12_WARPS - 1) / DC12_WARPS, DC12_WARPS * 32, smem, st>>>(a);
 	return cudaGetLastError();
+}
+
+size_t decode_scratch_bytes(int ch, int n)
+{
+	if (n <= 0 || ch == CH_DC12 || ch < 0 || ch >= CH_COUNT)
+		return 0;
+	const size_t slots = (size_t)((n + TPC_T - 1) / TPC_T) * TPC_T;
+	switch (ch) {
+	case CH_TCH3: return slots * chan_dec_bytes(CH_TCH3);
+	default:      return slots * (size_t)(chan_n_steps(ch) * 2);
+	}
 }
 
 // ---- dispatch ------------------------------------------------------------------------------------

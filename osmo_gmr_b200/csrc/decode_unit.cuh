@@ -32,6 +32,8 @@ struct DecodeArgs {
 	int32_t        t9_rows;   // tch9: ebits is [n][648] already deciphered / descrambled / inter-burst
 	                          //       de-interleaved (what gmr1_deinterleave_inter returns); no side outputs
 	const int32_t *n_dev;     // optional device-side unit count (<= n): units beyond it are skipped (rx scheduler)
+	uint8_t       *dec_scratch;   // optional device scratch of decode_scratch_bytes(ch, n): the survivor decisions go
+	                          // there (step-major, coalesced) instead of shared memory, which doubles the resident CTAs
 };
 
 // device-resident (or host, in the emulation) tables one channel needs

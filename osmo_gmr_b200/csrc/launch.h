@@ -8,6 +8,8 @@ namespace gmr1 {
 
 // ---- stage 3
 cudaError_t launch_decode(int ch, const DecodeArgs &a, cudaStream_t st);
+// bytes of DecodeArgs::dec_scratch for n units of channel ch (0: the channel keeps its decisions on chip)
+size_t decode_scratch_bytes(int ch, int n);
 
 // ---- stage 2
 struct DemodArgs {

@@ -272,12 +272,13 @@ extern "C" int gmr1b200_rx_bcch_batch(const float *iq, int64_t iq_len, const int
 	RxLists ls = {};
 	ls.count = s.tmp<int32_t>(2);
 	// per list: window offsets, frequency shifts, soft bits, demod and decode outputs
-	int8_t *eb[2]; float *toa[2], *ferr[2]; int32_t *dcrc[2], *dconv[2]; uint8_t *dl2[2];
+	int8_t *eb[2]; float *toa[2], *ferr[2]; int32_t *dcrc[2], *dconv[2]; uint8_t *dl2[2], *dscr[2];
 	const int ebits[2] = {424, 432}, bt[2] = {BT_BCCH, BT_DC6}, ch[2] = {CH_BCCH, CH_CCCH};
 	for (int k = 0; k < 2; k++) {
 		ls.ofs[k] = s.tmp<int64_t>(N); ls.fs[k] = s.tmp<float>(N);
 		eb[k] = s.tmp<int8_t>(N * ebits[k]); toa[k] = s.tmp<float>(N); ferr[k] = s.tmp<float>(N);
 		dcrc[k] = s.tmp<int32_t>(N); dconv[k] = s.tmp<int32_t>(N); dl2[k] = s.tmp<uint8_t>(N * 24);
+		dscr[k] = s.tmp<uint8_t>(decode_scratch_bytes(ch[k], n));
 	}
 	if (s.failed())
 		return s.finish(cudaSuccess, "rx_bcch_batch: staging");
@@ -313,6 +314,7 @@ extern "C" int gmr1b200_rx_bcch_batch(const float *iq, int64_t iq_len, const int
 			DecodeArgs d = {};
 			d.ebits = eb[k]; d.n = n; d.l2 = dl2[k]; d.conv = dconv[k]; d.crc = dcrc[k];
 			d.n_dev = ls.count + k;
+			d.dec_scratch = dscr[k];
 			e = launch_decode(ch[k], d, cs);
 			launches += 2;
 		}

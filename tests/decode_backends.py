@@ -19,7 +19,7 @@ class Args(ctypes.Structure):
     _fields_ = [("ebits", P), ("ciph", P), ("n", ctypes.c_int32), ("l2", P), ("l2b", P), ("conv", P), ("conv1", P),
                 ("crc", P), ("crc2", P), ("bits_s", P), ("sacch", P), ("status", P), ("prev1", P), ("prev2", P),
                 ("sb_mask", P), ("sb_mask0", ctypes.c_int32), ("tch3_m", ctypes.c_int32), ("t9_rows", ctypes.c_int32),
-                ("n_dev", P)]
+                ("n_dev", P), ("dec_scratch", P)]
 
 
 def _p(a):
