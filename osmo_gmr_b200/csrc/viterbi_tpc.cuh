@@ -79,6 +79,16 @@ GMR1_HD void soft_metrics(int is, uint32_t &m0, uint32_t &m1)
 	m1 = is ? (uint32_t)((d1 * d1) >> 9) : 0u;
 }
 
+// (hi << 1) | (lo >> 31): shifts the sign of lo into hi
+GMR1_HD uint32_t funnel_l1(uint32_t lo, uint32_t hi)
+{
+#ifdef __CUDA_ARCH__
+	return __funnelshift_l(lo, hi, 1);
+#else
+	return (hi << 1) | (lo >> 31);
+#endif
+}
+
 // One trellis step from `ae` into `nae` (callers ping-pong the two arrays so that no register
 // copies are needed).  DW = number of 32-bit decision words per step (NS/32 rounded up).
 template <class C, bool FLUSH_STEP>
@@ -102,25 +112,40 @@ GMR1_HD void acs_step(const uint32_t (&ae)[C::NS], uint32_t (&nae)[C::NS], const
 			bm[2 * o]     = base + m0[j];
 		}
 	}
+	if (FLUSH_STEP) {
+		// only the 0-input branches; odd states become unreachable
 #pragma unroll
-	for (int i = 0; i < (NS + 31) / 32; i++)
-		dec[i] = 0;
+		for (int i = 0; i < (NS + 31) / 32; i++)
+			dec[i] = 0;
 #pragma unroll
-	for (int k = 0; k < H; k++) {
-		const uint32_t lo = ae[k], hi = ae[k + H];
-		{
-			const uint32_t a = lo + bm[C::out(k, 0)], b = hi + bm[C::out(k + H, 0)];
+		for (int k = 0; k < H; k++) {
+			const uint32_t a = ae[k] + bm[C::out(k, 0)], b = ae[k + H] + bm[C::out(k + H, 0)];
 			const bool d = b < a;
 			nae[2 * k] = d ? b : a;
 			dec[(2 * k) >> 5] |= d ? (1u << ((2 * k) & 31)) : 0u;
-		}
-		if (!FLUSH_STEP) {
-			const uint32_t a = lo + bm[C::out(k, 1)], b = hi + bm[C::out(k + H, 1)];
-			const bool d = b < a;
-			nae[2 * k + 1] = d ? b : a;
-			dec[(2 * k + 1) >> 5] |= d ? (1u << ((2 * k + 1) & 31)) : 0u;
-		} else {
 			nae[2 * k + 1] = MAX_AE;
+		}
+	} else {
+		// States from the highest down: the decision "b < a" is the sign of b - a (both below 2^25), shifted
+		// into the decision word from the right - one funnel shift per state, and the subtraction can issue
+		// on the multiply pipe (IMAD), which takes load off the integer ALU this kernel is bound by.
+		// Two partial words per 32 states keep the shift chains short.
+		constexpr int DW = (NS + 31) / 32, PER = NS / DW;          // states per decision word
+#pragma unroll
+		for (int w = DW - 1; w >= 0; w--) {
+			uint32_t acc_hi = 0, acc_lo = 0;
+#pragma unroll
+			for (int q = PER - 1; q >= 0; q--) {
+				const int s = w * PER + q, k = s >> 1, bit = s & 1;
+				const uint32_t a = ae[k] + bm[C::out(k, bit)], b = ae[k + H] + bm[C::out(k + H, bit)];
+				nae[s] = b < a ? b : a;
+				const uint32_t diff = b - a;                       // negative <=> b < a (strict: ties keep a)
+				if (q >= PER / 2)
+					acc_hi = funnel_l1(diff, acc_hi);
+				else
+					acc_lo = funnel_l1(diff, acc_lo);
+			}
+			dec[w] = (acc_hi << (PER / 2)) | acc_lo;
 		}
 	}
 }
