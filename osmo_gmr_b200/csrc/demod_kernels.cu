@@ -235,6 +235,12 @@ struct Regions {
 	int32_t start[MAX_REGIONS], len[MAX_REGIONS], off[MAX_REGIONS];   // window sample, length, smem offset
 	int32_t n_slot;                         // training chunks of all types / sequences, numbered densely:
 	uint8_t slot[MAX_BT][MAX_SYNC][MAX_SYNC_CHUNK];   // their rotated taps are cached per warp (build_taps)
+	// what the per-burst code needs of the burst descriptors, in the constant bank (uniform loads, no LSU)
+	uint8_t  n_sync[MAX_BT], n_chunk[MAX_BT][MAX_SYNC];
+	uint8_t  cl[MAX_BT][MAX_SYNC][MAX_SYNC_CHUNK];     // chunk length in symbols
+	uint16_t roff[MAX_BT][MAX_SYNC][MAX_SYNC_CHUNK];   // offset (samples) of the chunk's first sample in the region buffer
+	float    cpos[MAX_SYNC][MAX_SYNC_CHUNK];           // type 0: centre of the chunk in symbols (s_pos + s_len / 2)
+	float    rotation0;                                // type 0: per-symbol rotation
 };
 
 // per-warp shared-memory slice
@@ -429,15 +435,16 @@ __device__ void build_taps(const BurstTab *__restrict__ bts, int n_bt, const Reg
 // accv is NOT cleared between sequences - the reference clears it once per call (:207) and
 // keeps adding (:232-233); tl restarts per sequence (:216).
 template <int SPS>     // SPS > 0: compile-time samples per symbol (4 is the fast path), <= 0: run-time
-__device__ int sync_find(const BurstTab &bt, const WarpSmem &sm, const uint16_t (*roff_tab)[MAX_SYNC_CHUNK],
-                         const uint8_t (*slot_tab)[MAX_SYNC_CHUNK], const Norm &nm, int sps_rt, int w,
+__device__ int sync_find(const Regions &rg, int id, const WarpSmem &sm, const Norm &nm, int sps_rt, int w,
                          const TapLane &tpl, int lane, bool sync_reset, float &toa, float &pwr)
 {
 	const int sps = SPS > 0 ? SPS : sps_rt;
 	float p_toa = 0.0f, p_pwr = 0.0f;
 	int p_idx = -1;
-	for (int s = 0; s < bt.n_sync; s++) {
+	const int n_sync = rg.n_sync[id];
+	for (int s = 0; s < n_sync; s++) {
 		int tl = 0;
+		const int n_chunk = rg.n_chunk[id][s];
 		const bool fresh = s == 0 || sync_reset;      // sync_reset (opt-in): score every candidate on its own correlation
 		__syncwarp();
 		// up to three search offsets per lane (m, m+32, m+64) share every tap load; their |corr| sums over
@@ -451,9 +458,9 @@ __device__ int sync_find(const BurstTab &bt, const WarpSmem &sm, const uint16_t 
 			for (int r = 0; r < 3; r++)
 				acc[r] = fresh ? 0.0f : sm.accv[m0 + 32 * r];
 			tl = 0;
-			for (int c = 0; c < bt.n_chunk[s]; c++) {
-				const int cl = bt.s_len[s][c];
-				const int slot = slot_tab[s][c];
+			for (int c = 0; c < n_chunk; c++) {
+				const int cl = rg.cl[id][s][c];
+				const int slot = rg.slot[id][s][c];
 				const float2 Rs = sm.tsum[slot];
 				const float cr0 = nm.ar * Rs.x - nm.ai * Rs.y, ci0 = nm.ar * Rs.y + nm.ai * Rs.x;   // avg * sum(taps)
 				// taps beyond cl are zero, so the tap loop runs in whole groups of 4.  The up to 3 zero taps
@@ -464,7 +471,7 @@ __device__ int sync_find(const BurstTab &bt, const WarpSmem &sm, const uint16_t 
 #pragma unroll
 				for (int r = 0; r < 3; r++)
 					P[r] = Q[r] = make_float2(0.0f, 0.0f);
-				const float2 *g = sm.reg + roff_tab[s][c] + m0;
+				const float2 *g = sm.reg + rg.roff[id][s][c] + m0;
 				const float2 *tp = sm.taps + slot * 32;
 				if (r2)
 					corr_taps<3>(g, tp, cl4, sps, P, Q);
@@ -539,7 +546,6 @@ __device__ float2 lowsps_symbol(const float2 *__restrict__ x, int L, int q, bool
 // output order.  One lane per symbol then needs no per-chunk control flow.
 static constexpr int MAX_DST4 = 1280;     // windows up to 2560 samples fill their regions in the statistics pass
 struct FlatTab {
-	uint16_t roff[MAX_BT][MAX_SYNC][MAX_SYNC_CHUNK];   // smem offset (in samples) of each chunk's first sample
 	uint16_t d_pos[480];
 	uint16_t t_pos[MAX_SYNC][MAX_TRAIN];
 	uint8_t  t_sym[MAX_SYNC][MAX_TRAIN];
@@ -601,15 +607,6 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 
 	if (MODE == 0)
 		build_flat(bt, ft);
-	for (int i = threadIdx.x; i < n_bt * MAX_SYNC * MAX_SYNC_CHUNK; i += blockDim.x) {
-		const int ty = i / (MAX_SYNC * MAX_SYNC_CHUNK), sq = (i / MAX_SYNC_CHUNK) % MAX_SYNC, c = i % MAX_SYNC_CHUNK;
-		const int b0 = bts[ty].s_pos[sq][c] * a.sps;
-		int roff = 0;
-		for (int r = 0; r < rg.n; r++)
-			if (b0 >= rg.start[r] && b0 < rg.start[r] + rg.len[r])
-				roff = rg.off[r] + (b0 - rg.start[r]);
-		ft.roff[ty][sq][c] = (uint16_t)roff;
-	}
 	if (threadIdx.x == 0)
 		ft.dst_ok = (L >> 1) <= MAX_DST4;
 	if ((L >> 1) <= MAX_DST4)
@@ -650,7 +647,7 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 	for (int b = blockIdx.x * DM_WARPS + warp; b < n_eff; b += gridDim.x * DM_WARPS) {
 		const float2 *x = a.iq + (a.ofs ? a.ofs[b] : (int64_t)b * a.stride);
 		const float freq_shift = a.freq_shift ? a.freq_shift[b] : a.freq_shift0;
-		const float fs = (freq_shift - bt.rotation) / (float)sps;
+		const float fs = (freq_shift - rg.rotation0) / (float)sps;
 
 		__syncwarp();
 		if (fs != fs_taps) {
@@ -671,8 +668,7 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 			float p_toa = 0.0f, p_pwr = 0.0f;
 			for (int id = 0; id < n_bt; id++) {
 				float toa, pwr;
-				const int sid = sync_find<SPS>(bts[id], sm, ft.roff[id], rg.slot[id], nm, sps, w, tpl, lane,
-				                               a.sync_reset != 0, toa, pwr);
+				const int sid = sync_find<SPS>(rg, id, sm, nm, sps, w, tpl, lane, a.sync_reset != 0, toa, pwr);
 				if (e_toa >= 0.0f)     // the reference divides by fabs() in double (pi4cxpsk.c:658-659)
 					pwr = (float)((double)pwr / fabs((double)(e_toa - toa)));
 				if (pwr > p_pwr) {
@@ -692,8 +688,7 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 		}
 
 		float toa, pwr;
-		const int sync_id = sync_find<SPS>(bt, sm, ft.roff[0], rg.slot[0], nm, sps, w, tpl, lane, a.sync_reset != 0,
-		                                   toa, pwr);
+		const int sync_id = sync_find<SPS>(rg, 0, sm, nm, sps, w, tpl, lane, a.sync_reset != 0, toa, pwr);
 		if (lane == 0) {
 			if (a.sync_id) a.sync_id[b] = sync_id;
 			if (a.toa) a.toa[b] = toa;
@@ -720,7 +715,7 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 		// ---- training symbols, one per lane, derotated as the reference derotates every sample:
 		//      z = (x - avg)/sd * e^{j*fl32(fs*idx)}, times conj(reference symbol).  Per-chunk sums ->
 		//      fine frequency error from the chunk-to-chunk phase slope (:360-406).
-		const int nch = bt.n_chunk[sync_id], ntr = ft.n_train[sync_id];
+		const int nch = rg.n_chunk[0][sync_id], ntr = ft.n_train[sync_id];
 		float2 z0 = make_float2(0.0f, 0.0f);     // training symbol `lane` (round 0) stays in registers
 		int ch0 = -1;
 		for (int t0 = 0; t0 < ntr; t0 += 32) {
@@ -759,7 +754,7 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 						ci += z.y;
 					}
 				const float2 sum = warp_sum2(cr, ci, lane);
-				const float pos = (float)bt.s_pos[sync_id][c] + (float)bt.s_len[sync_id][c] / 2.0f;
+				const float pos = rg.cpos[sync_id][c];
 				if (c > 0) {   // arg(corr[c] * conj(corr[c-1])) / (pos[c] - pos[c-1])
 					const float re = sum.x * prev_r + sum.y * prev_i, im = sum.y * prev_r - sum.x * prev_i;
 					f += fast_atan2f(im, re) / (pos - prev_pos);
@@ -919,10 +914,23 @@ cudaError_t launch_demod(const DemodArgs &a, const BurstTab *d_bts, const BurstT
 		}
 		if (n_bt > MAX_BT)
 			return cudaErrorInvalidValue;
-		for (int i = 0; i < n_bt; i++)
-			for (int s = 0; s < h_bts[i].n_sync; s++)
-				for (int c = 0; c < h_bts[i].n_chunk[s]; c++)
+		for (int i = 0; i < n_bt; i++) {
+			rg.n_sync[i] = (uint8_t)h_bts[i].n_sync;
+			for (int s = 0; s < h_bts[i].n_sync; s++) {
+				rg.n_chunk[i][s] = (uint8_t)h_bts[i].n_chunk[s];
+				for (int c = 0; c < h_bts[i].n_chunk[s]; c++) {
 					rg.slot[i][s][c] = (uint8_t)rg.n_slot++;
+					rg.cl[i][s][c] = (uint8_t)h_bts[i].s_len[s][c];
+					const int b0 = h_bts[i].s_pos[s][c] * a.sps;
+					for (int r = 0; r < rg.n; r++)
+						if (b0 >= rg.start[r] && b0 < rg.start[r] + rg.len[r])
+							rg.roff[i][s][c] = (uint16_t)(rg.off[r] + (b0 - rg.start[r]));
+					if (i == 0)
+						rg.cpos[s][c] = (float)h_bts[0].s_pos[s][c] + (float)h_bts[0].s_len[s][c] / 2.0f;
+				}
+			}
+		}
+		rg.rotation0 = h_bts[0].rotation;
 	}
 	const size_t wb = (warp_smem_bytes(rg.total, w, rg.n_slot) + 15) & ~(size_t)15;
 	const size_t smem = wb * DM_WARPS;
