@@ -548,6 +548,7 @@ static constexpr int MAX_DST4 = 1280;     // windows up to 2560 samples fill the
 struct FlatTab {
 	uint16_t d_pos[480];
 	uint16_t t_pos[MAX_SYNC][MAX_TRAIN];
+	uint16_t t_off[MAX_SYNC][MAX_TRAIN];   // training symbol -> its sample in the region buffer, for TOA 0 (sps >= 4)
 	uint8_t  t_sym[MAX_SYNC][MAX_TRAIN];
 	uint8_t  t_chunk[MAX_SYNC][MAX_TRAIN];
 	int32_t  n_train[MAX_SYNC];
@@ -556,7 +557,7 @@ struct FlatTab {
 	uint16_t dst4[MAX_DST4 + 1];     // pair of samples -> float4 slot of the region buffer, 0xffff: not in a region
 };
 
-__device__ void build_flat(const BurstTab &bt, FlatTab &ft)
+__device__ void build_flat(const BurstTab &bt, FlatTab &ft, const Regions &rg, int sps)
 {
 	for (int t = threadIdx.x; t < 480; t += blockDim.x) {
 		int acc = 0, pos = 0;
@@ -571,17 +572,19 @@ __device__ void build_flat(const BurstTab &bt, FlatTab &ft)
 	}
 	for (int s = 0; s < bt.n_sync; s++)
 		for (int t = threadIdx.x; t < MAX_TRAIN; t += blockDim.x) {
-			int acc = 0, pos = 0, sym = 0, ch = 0;
+			int acc = 0, pos = 0, sym = 0, ch = 0, off = 0;
 			for (int c = 0; c < bt.n_chunk[s]; c++) {
 				const int cl = bt.s_len[s][c];
 				if (t >= acc && t < acc + cl) {
 					pos = bt.s_pos[s][c] + (t - acc);
 					sym = bt.s_sym[s][c][t - acc];
 					ch = c;
+					off = rg.roff[0][s][c] + (t - acc) * sps;
 				}
 				acc += cl;
 			}
 			ft.t_pos[s][t] = (uint16_t)pos;
+			ft.t_off[s][t] = (uint16_t)off;
 			ft.t_sym[s][t] = (uint8_t)sym;
 			ft.t_chunk[s][t] = (uint8_t)ch;
 			if (t == 0)
@@ -606,7 +609,7 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 	const WarpSmem sm = carve(smem + (size_t)warp * warp_bytes, rg.total, w, rg.n_slot);
 
 	if (MODE == 0)
-		build_flat(bt, ft);
+		build_flat(bt, ft, rg, sps);
 	if (threadIdx.x == 0)
 		ft.dst_ok = (L >> 1) <= MAX_DST4;
 	if ((L >> 1) <= MAX_DST4)
@@ -726,8 +729,10 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 				if (SPS < 0) {
 					y = lowsps_symbol(x, L, pos * sps + d, interp, ofs_frac, nm, fs);
 				} else {
+					// the training symbols lie inside the correlation regions: shared memory, not L2.  (d = -1
+					// reads the sample in front of the chunk: regions start one pair early for that.)
 					const int q = sample_of(pos);
-					const float2 v = __ldg(&x[q]);
+					const float2 v = sm.reg[(int)ft.t_off[sync_id][t] + d];
 					const float2 e = sincos_acc(fs * (float)q);
 					const float yr = (v.x - nm.ar) * nm.inv_sd, yi = (v.y - nm.ai) * nm.inv_sd;
 					y = make_float2(yr * e.x - yi * e.y, yr * e.y + yi * e.x);
@@ -885,6 +890,7 @@ cudaError_t launch_demod(const DemodArgs &a, const BurstTab *d_bts, const BurstT
 				for (int c = 0; c < h_bts[i].n_chunk[s]; c++) {
 					int lo = h_bts[i].s_pos[s][c] * a.sps;
 					int hi = lo + (h_bts[i].s_len[s][c] - 1 + 3) * a.sps + w;     // + 3 zero-padded taps
+					lo = lo >= 2 ? lo - 2 : 0;    // the symbol pick for TOA -0.5 .. 0 reads one sample in front
 					hi = hi > a.win_len ? a.win_len : hi;
 					lo &= ~1;                     // whole pairs of samples (16-byte stores into the region buffer)
 					hi = (hi + 1) & ~1;
