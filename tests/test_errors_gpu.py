@@ -1,0 +1,81 @@
+"""Error conventions at the drop-in boundary: the reference-named symbols of libgmr1_b200.so must
+return what the reference's functions return for the inputs the reference itself rejects or flags - hard errors
+as negative errno, soft conditions as positive values - and the batched entry points must reject malformed
+batches with -EINVAL and a message, doing no work.  The compat handle is the oracle's python wrapper pointed at
+libgmr1_b200.so: the very same calls go to both libraries."""
+import errno
+
+import numpy as np
+import pytest
+
+import oracle_lib
+import sigen
+from osmo_gmr_b200.lib import Gmr1Error, LIB_PATH
+
+pytestmark = pytest.mark.gpu
+SPS = 4
+
+
+@pytest.fixture(scope="module")
+def compat(gpu_lib):
+    return oracle_lib.Oracle(LIB_PATH, "b200")
+
+
+def test_reference_named_symbols_follow_the_reference(compat, oracle):
+    rng = np.random.default_rng(7)
+    noise = lambda n: (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    # gmr1_fcch_fine insists on exactly burst_len*sps samples (fcch.c:546-551)
+    for n in (117 * SPS - 4, 117 * SPS + 4):
+        x = noise(n)
+        assert compat.fcch_fine(x, SPS, 0.0)[0] == oracle.fcch_fine(x, SPS, 0.0)[0] == -errno.EINVAL
+    # gmr1_fcch_rough_multi needs 650 ms of signal (fcch.c:355-356)
+    x = noise((600 * 23400 * SPS) // 1000)
+    assert compat.fcch_rough_multi(x, SPS, 0.0)[0] == oracle.fcch_rough_multi(x, SPS, 0.0)[0] == -errno.EINVAL
+    # gmr1_dkab_demod: positive return for "not a DKAB" (dkab.c:138), 0 for a DKAB
+    w = noise(117 * SPS + 6)
+    r_ref, r_gpu = oracle.dkab_demod(w, SPS, 0.0, 5)[0], compat.dkab_demod(w, SPS, 0.0, 5)[0]
+    assert r_ref == r_gpu and r_ref >= 0
+    # all-zero window: nothing correlates; both report the same (negative) code and leave no soft bits
+    z = np.zeros(234 * SPS + 80, np.complex64)
+    rc_ref, eb_ref, _, _, _ = oracle.demod("bcch", z, SPS, 0.0)
+    rc_gpu, eb_gpu, _, _, _ = compat.demod("bcch", z, SPS, 0.0)
+    assert rc_ref == rc_gpu and rc_ref < 0 and not eb_gpu.any()
+    # a good burst through the same wrapper: success is 0 on both sides
+    hard = oracle.encode("bcch", 424, rng.integers(0, 256, 24, dtype=np.uint8))
+    x = sigen.modulate("bcch", hard[None, :], SPS, 80, 40.3, 0.004, 1.0, 20.0, rng)[0]
+    assert oracle.demod("bcch", x, SPS, 0.0)[0] == compat.demod("bcch", x, SPS, 0.0)[0] == 0
+
+
+def test_batched_entry_points_reject_malformed_batches(gpu_lib):
+    L = gpu_lib
+    n, wl = 4, 234 * SPS + 80
+    iq = np.zeros((n, wl, 2), np.float32)
+    eb = np.zeros((n, 424), np.int8)
+    l2 = np.zeros((n, 24), np.uint8)
+    before = L.kernel_launches()
+
+    def rejected(name, *args):
+        with pytest.raises(Gmr1Error) as e:
+            L.call(name, *args)
+        assert f"rc={-errno.EINVAL}" in str(e.value) and len(str(e.value)) > 20      # code and a message
+
+    rejected("gmr1b200_pi4cxpsk_demod_batch", 0, iq, n * wl, None, wl, wl, 0, None, 0.0, eb, 424, None, None, None, None, n, None)   # sps 0
+    rejected("gmr1b200_pi4cxpsk_demod_batch", 0, iq, n * wl, None, wl, wl, 17, None, 0.0, eb, 424, None, None, None, None, n, None)  # sps 17
+    rejected("gmr1b200_pi4cxpsk_demod_batch", 99, iq, n * wl, None, wl, wl, SPS, None, 0.0, eb, 424, None, None, None, None, n, None)  # burst type
+    rejected("gmr1b200_pi4cxpsk_demod_batch", 0, iq, n * wl, None, wl, wl, SPS, None, 0.0, eb, 100, None, None, None, None, n, None)  # ebits rows too short
+    rejected("gmr1b200_pi4cxpsk_demod_batch", 0, iq, n * wl, None, wl, 234 * SPS - 1, SPS, None, 0.0, eb, 424, None, None, None, None, n, None)  # window < burst
+    rejected("gmr1b200_pi4cxpsk_demod_batch", 0, iq, n * wl - 1, None, wl, wl, SPS, None, 0.0, eb, 424, None, None, None, None, n, None)  # windows exceed iq
+    rejected("gmr1b200_pi4cxpsk_demod_batch", 0, iq, n * wl, None, wl, wl, SPS, None, 0.0, None, 424, None, None, None, None, n, None)  # no output
+    rejected("gmr1b200_bcch_decode_batch", l2, None, None, None, n, None)                                                             # no input
+    rejected("gmr1b200_bcch_decode_batch", l2, eb, None, None, -1, None)                                                              # negative n
+    rejected("gmr1b200_fcch_rough_batch", 0, iq, n * wl, None, wl, 100, SPS, None, 0.0, np.zeros(n, np.int32), None, n, None)         # window < FCCH burst
+    rejected("gmr1b200_fcch_rough_batch", 7, iq, n * wl, None, wl, wl, SPS, None, 0.0, np.zeros(n, np.int32), None, n, None)          # FCCH type
+    rejected("gmr1b200_a5_batch", None, 1, np.zeros((n, 8), np.uint8), np.zeros(n, np.uint32), 208, 100, np.zeros((n, 208), np.uint8), None, n, None)  # stride < nbits
+    rejected("gmr1b200_rx_bcch_batch", iq, n * wl, np.zeros(n, np.int64), np.full(n, wl, np.int32), np.zeros(n, np.int32), None, SPS, n, 0,
+             np.zeros((n, 1), np.int32), np.zeros((n, 1), np.int32), np.zeros((n, 1), np.int32), np.zeros((n, 1), np.int32),
+             np.zeros((n, 1, 24), np.uint8), np.zeros(n, np.int32), None, None, None)                                                 # max_frames 0
+    assert L.kernel_launches() == before                                             # nothing was launched
+    # empty batches are fine and do nothing
+    assert L.call("gmr1b200_bcch_decode_batch", l2, eb, None, None, 0, None) == 0
+    assert L.call("gmr1b200_pi4cxpsk_demod_batch", 0, iq, n * wl, None, wl, wl, SPS, None, 0.0, eb, 424, None, None, None, None, 0, None) == 0
+    assert L.kernel_launches() == before
