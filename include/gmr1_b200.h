@@ -248,6 +248,16 @@ int gmr1b200_pi4cxpsk_detect_desc_batch(const struct gmr1b200_burst_desc *descs,
 int gmr1b200_fcch_rough_multi(int fcch_type, const float *iq, int64_t win_len, int sps, float freq_shift,
                               int32_t *toa, int N, void *stream);
 
+/* ---- burst window -> L2 in one call (the fused entry of SURVEY 8b) ----------------------------------
+ * gmr1_pi4cxpsk_demod + gmr1_{bcch,ccch,xch_dc12}_decode (rx_bcch / rx_ccch, src/gmr1_rx.c:747-851) for n
+ * windows: chan 0 = BCCH burst + BCCH decode, 1 = DC6 burst + CCCH decode, 2 = DC12 burst + DC12 decode.
+ * The soft bits stay in device memory.  l2 [n][24]; crc / conv / toa / freq_err [n], each may be NULL.
+ * Results are identical to calling gmr1b200_pi4cxpsk_demod_batch and the *_decode_batch one after the other. */
+int gmr1b200_rx_xcch_batch(int chan, const float *iq, int64_t iq_len, const int64_t *win_ofs, int64_t win_stride,
+                           int win_len, int sps, const float *freq_shift, float freq_shift0,
+                           uint8_t *l2, int32_t *crc, int32_t *conv, float *toa, float *freq_err,
+                           int n, void *stream);
+
 /* ---- receiver frame loop for n channels in lock step --------------------------------
  * replaces process_bcch (src/gmr1_rx.c:853-895) with rx_bcch (:747-803), rx_ccch (:805-851, without the TCH3
  * hand-off), bcch_tdma_align (:194-236), burst_map / burst_energy (:149-182) for n channels at once.

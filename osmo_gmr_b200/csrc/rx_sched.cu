@@ -331,3 +331,51 @@ extern "C" int gmr1b200_rx_bcch_batch(const float *iq, int64_t iq_len, const int
 	g_launches.fetch_add(launches);
 	return s.finish(e, "rx_bcch_batch kernels");
 }
+
+// ---- fused burst -> L2 for the common control channels ------------------------------------------------
+extern "C" int gmr1b200_rx_xcch_batch(int chan, const float *iq, int64_t iq_len, const int64_t *win_ofs,
+                                      int64_t win_stride, int win_len, int sps, const float *freq_shift,
+                                      float freq_shift0, uint8_t *l2, int32_t *crc, int32_t *conv, float *toa,
+                                      float *freq_err, int n, void *stream)
+{
+	if (chan < 0 || chan > 2 || !iq || !l2 || n < 0 || sps < 1 || sps > 16)
+		return set_err(-EINVAL, "rx_xcch_batch: bad argument");
+	const int bt = chan == 0 ? BT_BCCH : chan == 1 ? BT_DC6 : BT_DC12;
+	const int ch = chan == 0 ? CH_BCCH : chan == 1 ? CH_CCCH : CH_DC12;
+	const BurstTab &t = burst_tab(bt);
+	if (win_len < t.len * sps)
+		return set_err(-EINVAL, "rx_xcch_batch: window shorter than the burst");
+	if (n == 0)
+		return 0;
+	if (!win_ofs && (win_stride < 0 || (int64_t)(n - 1) * win_stride + win_len > iq_len))
+		return set_err(-EINVAL, "rx_xcch_batch: windows exceed iq_len");
+	const BurstTab *d_all = nullptr;
+	cudaError_t e = device_bursts(&d_all);
+	if (e != cudaSuccess)
+		return cuda_rc(e, "burst table upload");
+	cudaStream_t cs = (cudaStream_t)stream;
+	Stage s(stream);
+	const size_t N = (size_t)n;
+	DemodArgs a = {};
+	a.iq = (const float2 *)s.in(iq, (size_t)iq_len * 2);
+	a.ofs = s.in(win_ofs, N); a.stride = win_stride; a.n = n; a.win_len = win_len; a.sps = sps;
+	a.freq_shift = s.in(freq_shift, N); a.freq_shift0 = freq_shift0; a.e_toa0 = -1.0f;
+	a.ebits = s.tmp<int8_t>(N * t.ebits); a.ebits_stride = t.ebits;      // soft bits never leave the device
+	a.toa = s.out(toa, N); a.freq_err = s.out(freq_err, N);
+	DecodeArgs d = {};
+	d.ebits = a.ebits; d.n = n;
+	d.l2 = s.out(l2, N * 24); d.crc = s.out(crc, N); d.conv = s.out(conv, N);
+	if (const size_t sb = decode_scratch_bytes(ch, n))
+		d.dec_scratch = s.tmp<uint8_t>(sb);
+	if (!s.failed()) {
+		e = launch_demod(a, d_all + bt, &t, 1, 0, cs);
+		if (e == cudaSuccess) {
+			g_launches.fetch_add(1);
+			e = launch_decode(ch, d, cs);
+			if (e == cudaSuccess)
+				g_launches.fetch_add(1);
+		}
+	}
+	return s.finish(e, "rx_xcch_batch kernels");
+}
+

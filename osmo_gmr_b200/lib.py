@@ -67,6 +67,7 @@ class Lib:
         "gmr1b200_tch3_encode": [_P, _P, _P, _P, _P, _I],
         "gmr1b200_fcch_rough_batch": [_I, _P, _L, _P, _L, _I, _I, _P, _F, _P, _P, _I, _P],
         "gmr1b200_fcch_fine_batch": [_I, _P, _L, _P, _L, _I, _P, _F, _P, _P, _I, _P],
+        "gmr1b200_rx_xcch_batch": [_I, _P, _L, _P, _L, _I, _I, _P, _F, _P, _P, _P, _P, _P, _I, _P],
         "gmr1b200_rx_bcch_batch": [_P, _L, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P],
         "gmr1b200_a5_batch": [_P, _I, _P, _P, _I, _I, _P, _P, _I, _P],
         "gmr1b200_fcch_acquire_batch": [_I, _P, _L, _P, _L, _I, _I, _P, _P, _P, _I, _P],

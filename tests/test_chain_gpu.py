@@ -205,3 +205,33 @@ def test_fcch_search_over_frequency_grid(gpu_lib, oracle):
     fe = np.zeros(1, np.float32)
     gpu_lib.call("gmr1b200_fcch_fine_batch", 0, _iq(w), 468, None, 468, SPS, None, float(fsh[best]), t, fe, 1, None)
     assert abs(fe[0] * 23400.0 / (2 * np.pi) - (-200.0)) < 25.0
+
+
+@pytest.mark.parametrize("chan,name,neb", [(0, "bcch", 424), (1, "dc6", 432), (2, "dc12", 432)])
+def test_fused_burst_to_l2(gpu_lib, oracle, chan, name, neb):
+    """gmr1b200_rx_xcch_batch == demod_batch followed by the channel's decode_batch, and == the oracle's L2 / CRC"""
+    rng = np.random.default_rng(60 + chan)
+    n, win = 70, 40
+    l2 = rng.integers(0, 256, (n, 24), dtype=np.uint8)
+    enc = {0: "bcch", 1: "ccch", 2: "xch_dc12"}[chan]
+    hard = np.stack([oracle.encode(enc, neb, l2[i]) for i in range(n)])
+    x = _mod(name, hard, win, rng, snr_lo=8.0)
+    wl = x.shape[1]
+    out = np.zeros((n, 24), np.uint8)
+    crc = np.zeros(n, np.int32)
+    conv = np.zeros(n, np.int32)
+    toa = np.zeros(n, np.float32)
+    gpu_lib.call("gmr1b200_rx_xcch_batch", chan, np.ascontiguousarray(x).view(np.float32), n * wl, None, wl, wl, SPS,
+                 None, 0.0, out, crc, conv, toa, None, n, None)
+    eb, _, toa2 = _demod(gpu_lib, name, x)
+    out2 = np.zeros((n, 24), np.uint8)
+    crc2 = np.zeros(n, np.int32)
+    conv2 = np.zeros(n, np.int32)
+    dec = {0: "gmr1b200_bcch_decode_batch", 1: "gmr1b200_ccch_decode_batch", 2: "gmr1b200_xch_dc12_decode_batch"}[chan]
+    gpu_lib.call(dec, out2, eb, conv2, crc2, n, None)
+    assert (out == out2).all() and (crc == crc2).all() and (conv == conv2).all() and (toa == toa2).all()
+    for i in range(0, n, 5):
+        _, eb_o, _, _, _ = oracle.demod(name, x[i], SPS, 0.0)
+        l2_o, crc_o, _ = oracle.simple_decode(enc, eb_o)
+        assert crc[i] == crc_o and (out[i] == l2_o).all(), i
+    assert (crc == 0).mean() > 0.9 and (out[crc == 0] == l2[crc == 0]).all()
