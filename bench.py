@@ -327,17 +327,21 @@ def run_gpu_arm(args):
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
     stream2 = torch.cuda.Stream(device=dev)
-    two = args.streams == 2
+    stream3 = torch.cuda.Stream(device=dev)
+    three = args.streams >= 3
+    two = args.streams >= 2
 
     def step(timers=None):
         """one pass over the batch.  --streams 2: the BCCH and DC6/CCCH halves are independent, each
         runs demod -> decode on its own stream so that the decode (integer-ALU-bound) of one half
-        shares the SMs with the demod of the other; the per-kernel event timers are only meaningful
-        with --streams 1 (serial), which is how the roofline pass below is run."""
+        shares the SMs with the demod of the other; --streams 3 (default): the FCCH acquisitions, a third
+        independent piece of work, get their own stream too.  The per-kernel event timers are only
+        meaningful with --streams 1 (serial), which is how the roofline pass below is run."""
         if timers is not None:
             f0, f1 = ev(), ev()
             f0.record(stream)
-        W.fcch(stream.cuda_stream, stream)
+        sf = stream3 if (three and timers is None) else stream
+        W.fcch(sf.cuda_stream, sf)
         if timers is not None:
             f1.record(stream)
             timers.append(("fcch", f0, f1))
@@ -363,11 +367,14 @@ def run_gpu_arm(args):
     launches0 = L.kernel_launches()
     t_start, t_end = ev(), ev()
     stream2.wait_stream(stream)
+    stream3.wait_stream(stream)
     t_start.record(stream)
     stream2.wait_event(t_start)
+    stream3.wait_event(t_start)
     for _ in range(args.steps):
         step()
     stream.wait_stream(stream2)
+    stream.wait_stream(stream3)
     t_end.record(stream)
     barrier()
     launches = L.kernel_launches() - launches0
@@ -572,7 +579,7 @@ def main():
     ap.add_argument("--arfcns", type=int, default=1024)
     ap.add_argument("--bursts-per-arfcn", type=int, default=256)
     ap.add_argument("--e2e-chunks", type=int, default=8)
-    ap.add_argument("--streams", type=int, default=2, choices=[1, 2])
+    ap.add_argument("--streams", type=int, default=3, choices=[1, 2, 3])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
