@@ -49,6 +49,12 @@ static constexpr int DM_WARPS = 4;
 #ifndef DM_SYM_BATCH
 #define DM_SYM_BATCH 4         // data symbols per lane whose sample loads are issued together
 #endif
+#ifndef DM_OPT_ATAN
+#define DM_OPT_ATAN 1
+#endif
+#ifndef DM_OPT_LUT
+#define DM_OPT_LUT 1
+#endif
 #ifndef DM_MIN_CTAS
 #define DM_MIN_CTAS 8          // resident CTAs per SM the register allocation is capped for
 #endif
@@ -98,7 +104,15 @@ __device__ __forceinline__ float fast_atan2f_inl(float y, float x)
 {
 	const float ax = fabsf(x), ay = fabsf(y);
 	const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+	// mn / mx by one approximate reciprocal (__fdividef carries a denormal-scaling sequence, 9 instructions);
+	// mx == 0 implies mn == 0 and the product is 0
+#if DM_OPT_ATAN
+	float inv;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(fmaxf(mx, 1e-30f)));
+	const float a = mn * inv;
+#else
 	const float a = mx > 0.0f ? __fdividef(mn, mx) : 0.0f;
+#endif
 	const float t = a * a;
 	float p = 2.4464237603e-03f;
 	p = fmaf(p, t, -1.4352691414e-02f);
@@ -131,19 +145,31 @@ __device__ __forceinline__ float ld_acc(const float *acc, int k, int len)
 
 // osmo_cxvec_peak_energy_find(acc, 3, PEAK_EARLY_LATE, &peak) on a real vector; all lanes
 // return the same position / peak value
-__device__ float peak_early_late(const float *acc, int w, const TapLane &tp, int lane, float &peak_val)
+template <int ROWS>
+__device__ __forceinline__ float peak_early_late(const float *acc, int w, const TapLane &tp, int lane, float &peak_val)
 {
+	// acc[-2], acc[-1] are zero and the row of 32 that holds acc[w-1] is zero beyond it (sync_find), so the
+	// energy windows need no edge cases: val[idx] = acc[idx-2]^2 + acc[idx-1]^2 + acc[idx]^2
 	const int win = w < 3 ? w : 3;
 	float best = 0.0f;
 	int best_idx = 0x7fffffff;
-	for (int idx = lane; idx < w; idx += 32) {
-		const float a0 = acc[idx], a1 = idx >= 1 ? acc[idx - 1] : 0.0f, a2 = (idx >= 2 && win > 2) ? acc[idx - 2] : 0.0f;
+	auto scan = [&](int idx, bool check) {
+		const float a0 = acc[idx], a1 = acc[idx - 1], a2 = acc[idx - 2];
 		// oldest sample first, products rounded separately as the C path does (no FMA contraction)
 		const float val = __fadd_rn(__fadd_rn(__fmul_rn(a2, a2), __fmul_rn(a1, a1)), __fmul_rn(a0, a0));
-		if (val > best) {
+		if (val > best && (!check || idx < w)) {
 			best = val;
 			best_idx = idx;
 		}
+	};
+	if (ROWS > 0) {
+#pragma unroll
+		for (int r = 0; r < ROWS; r++)
+			scan(lane + 32 * r, r == ROWS - 1);
+	} else {
+#pragma unroll 1
+		for (int idx = lane; idx < w; idx += 32)
+			scan(idx, false);
 	}
 	{	// warp argmax (largest value, lowest index on ties): energies are >= +0, so their bit patterns
 		// order like unsigned integers and two redux instructions replace the shuffle tree
@@ -156,14 +182,18 @@ __device__ float peak_early_late(const float *acc, int w, const TapLane &tp, int
 	if (max_idx < 0)
 		max_idx = 0;
 
+	// strongest sample of the winning window (first one on ties); reads past w find the zero padding
 	int mwi = max_idx;
-	float mv = -1.0f;
-	for (int idx = max_idx; idx < max_idx + win; idx++) {
-		const float a = acc[idx], e = a * a;
-		if (e > mv) {
-			mv = e;
-			mwi = idx;
+	{
+		const float b0 = acc[max_idx], b1 = acc[max_idx + 1], b2 = acc[max_idx + 2];
+		const float e0 = b0 * b0, e1 = b1 * b1, e2 = b2 * b2;
+		float mv = e0;
+		if (win > 1 && e1 > mv) {
+			mv = e1;
+			mwi = max_idx + 1;
 		}
+		if (win > 2 && e2 > mv)
+			mwi = max_idx + 2;
 	}
 
 	// The search starts at mwi-1 and moves by less than 1 in total, so floor(early) is mwi-2 or
@@ -263,8 +293,8 @@ __device__ __forceinline__ WarpSmem carve(uint8_t *base, int nreg, int w, int ns
 	base += (size_t)nslot * 32 * 8;
 	s.tsum = (float2 *)base;
 	base += (size_t)((nslot + 1) & ~1) * 8;
-	s.accv = (float *)base;
-	base += (size_t)((w + 31) & ~31) * 4;
+	s.accv = (float *)base + 4;            // accv[-4..-1] and everything from accv[w] on stay zero (peak search padding)
+	base += (size_t)(((w + 31) & ~31) + 8) * 4;
 	s.zbuf = (float2 *)base;
 	return s;
 }
@@ -272,7 +302,7 @@ __device__ __forceinline__ WarpSmem carve(uint8_t *base, int nreg, int w, int ns
 static inline size_t warp_smem_bytes(int nreg, int w, int nslot)
 {
 	return (size_t)((nreg + 1) & ~1) * 8 + (size_t)nslot * 32 * 8 + (size_t)((nslot + 1) & ~1) * 8 +
-	       (size_t)((w + 31) & ~31) * 4 + MAX_TRAIN * 8;
+	       (size_t)(((w + 31) & ~31) + 8) * 4 + MAX_TRAIN * 8;
 }
 
 // window statistics of osmo_cxvec_sig_normalize: mean and 1/stddev.  One pass: the variance is
@@ -283,12 +313,12 @@ struct Norm { float ar, ai, inv_sd; };
 // dst4 (optional): for every pair of samples of the window, the float4 slot of the warp's region buffer
 // it belongs to (0xffff: none) - the correlation regions are then filled from the same loads and the
 // separate load_regions pass (a second trip to L2) is not needed.
-template <bool WANT_SD>
+template <bool WANT_SD, bool ALIGNED>       // ALIGNED: the caller has checked the 16-byte alignment (hot path)
 __device__ __forceinline__ Norm load_stats_t(const float2 *__restrict__ x, int L, int lane,
                                              const bool FILL, const uint16_t *dst4, float2 *reg)
 {
 	float sr = 0.0f, si = 0.0f, sq = 0.0f;
-	if ((((uintptr_t)x) & 15) == 0) {
+	if (ALIGNED || (((uintptr_t)x) & 15) == 0) {
 		// 16-byte aligned window: two samples per lane per load
 		const float4 *x4 = reinterpret_cast<const float4 *>(x);
 		float4 *reg4 = reinterpret_cast<float4 *>(reg);
@@ -368,6 +398,18 @@ __device__ __noinline__ void load_regions(const float2 *__restrict__ x, int L, c
 	__syncwarp();
 }
 
+// everything but the usual case (16-byte aligned window, regions filled on the fly, no sync power wanted),
+// out of line: the per-burst loop is instruction-cache sensitive and must stay compact
+__device__ __noinline__ Norm load_stats_cold(const float2 *__restrict__ x, int L, int lane, bool want_sd, bool fill,
+                                             const uint16_t *dst4, const Regions &rg, float2 *reg)
+{
+	const Norm n = want_sd ? load_stats_t<true, false>(x, L, lane, fill, dst4, reg)
+	                       : load_stats_t<false, false>(x, L, lane, fill, dst4, reg);
+	if (!fill)
+		load_regions(x, L, rg, reg, lane);
+	return n;
+}
+
 // c += s * v on the packed FP32 pipe (one FFMA2 instead of two FFMA)
 __device__ __forceinline__ void fma2s(float2 &c, float sc, const float2 v)
 {
@@ -434,70 +476,94 @@ __device__ void build_taps(const BurstTab *__restrict__ bts, int n_bt, const Reg
 // t_n = conj(ref_n) e^{j*fs*sps*n}.  Same quantity, 60x fewer sincos.
 // accv is NOT cleared between sequences - the reference clears it once per call (:207) and
 // keeps adding (:232-233); tl restarts per sequence (:216).
-template <int SPS>     // SPS > 0: compile-time samples per symbol (4 is the fast path), <= 0: run-time
-__device__ int sync_find(const Regions &rg, int id, const WarpSmem &sm, const Norm &nm, int sps_rt, int w,
-                         const TapLane &tpl, int lane, bool sync_reset, float &toa, float &pwr)
+// one block of up to 3 rows of 32 search offsets (m0, m0+32, m0+64), R of them in use: |corr| of every chunk of
+// sequence s added onto the accumulator rows
+template <int R, int SPS>
+__device__ __forceinline__ int corr_block(const Regions &rg, int id, int s, const WarpSmem &sm, const Norm &nm, int sps_rt,
+                                          int w, int m0, bool fresh)
 {
 	const int sps = SPS > 0 ? SPS : sps_rt;
+	const int n_chunk = rg.n_chunk[id][s];
+	float acc[R];
+#pragma unroll
+	for (int r = 0; r < R; r++)
+		acc[r] = (fresh || m0 + 32 * r >= w) ? 0.0f : sm.accv[m0 + 32 * r];
+	int tl = 0;
+#pragma unroll 1
+	for (int c = 0; c < n_chunk; c++) {
+		const int cl = rg.cl[id][s][c];
+		const int slot = rg.slot[id][s][c];
+		const float2 Rs = sm.tsum[slot];
+		const float cr0 = nm.ar * Rs.x - nm.ai * Rs.y, ci0 = nm.ar * Rs.y + nm.ai * Rs.x;   // avg * sum(taps)
+		// taps beyond cl are zero, so the tap loop runs in whole groups of 4.  The up to 3 zero taps
+		// may read up to 3*sps samples past their region: that lands in this warp's other regions /
+		// taps / accv / zbuf, which only ever hold finite floats, and 0 * finite adds nothing.
+		const int cl4 = (cl + 3) & ~3;
+		float2 P[3], Q[3];
+#pragma unroll
+		for (int r = 0; r < 3; r++)
+			P[r] = Q[r] = make_float2(0.0f, 0.0f);
+		corr_taps<R>(sm.reg + rg.roff[id][s][c] + m0, sm.taps + slot * 32, cl4, sps, P, Q);
+#pragma unroll
+		for (int r = 0; r < R; r++) {
+			const float xr = ((P[r].x - Q[r].y) - cr0) * nm.inv_sd, xi = ((P[r].y + Q[r].x) - ci0) * nm.inv_sd;
+			const float e = fmaf(xr, xr, xi * xi);
+			float rs;
+			asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(e));
+			acc[r] += e > 0.0f ? e * rs : 0.0f;
+		}
+		tl += cl;
+	}
+#pragma unroll
+	for (int r = 0; r < R; r++)
+		if (m0 + 32 * r < w)            // entries from w on stay zero
+			sm.accv[m0 + 32 * r] = acc[r];
+	return tl;
+}
+
+// any number of search offsets, 96 per pass (cold: the formats of the reference have w <= 81 at sps 4)
+template <int SPS>
+__device__ __noinline__ int corr_generic(const Regions &rg, int id, int s, const WarpSmem &sm, const Norm &nm, int sps_rt,
+                                         int w, int lane, bool fresh)
+{
+	int tl = 0;
+#pragma unroll 1
+	for (int mb = 0; mb < w; mb += 96) {
+		if (mb + 64 < w)
+			tl = corr_block<3, SPS>(rg, id, s, sm, nm, sps_rt, w, mb + lane, fresh);
+		else if (mb + 32 < w)
+			tl = corr_block<2, SPS>(rg, id, s, sm, nm, sps_rt, w, mb + lane, fresh);
+		else
+			tl = corr_block<1, SPS>(rg, id, s, sm, nm, sps_rt, w, mb + lane, fresh);
+	}
+	return tl;
+}
+
+// SPS > 0: compile-time samples per symbol (4 is the fast path), <= 0: run-time.
+// ROWS > 0: the search has at most 32 * ROWS offsets and exactly ROWS rows are computed (compile-time: the hot
+// path then holds one copy of the correlation loop - the kernel is instruction-cache sensitive); 0: any w.
+template <int SPS, int ROWS>
+__device__ __forceinline__ int sync_find(const Regions &rg, int id, const WarpSmem &sm, const Norm &nm, int sps_rt, int w,
+                         const TapLane &tpl, int lane, bool sync_reset, float &toa, float &pwr)
+{
 	float p_toa = 0.0f, p_pwr = 0.0f;
 	int p_idx = -1;
 	const int n_sync = rg.n_sync[id];
+#pragma unroll 1
 	for (int s = 0; s < n_sync; s++) {
-		int tl = 0;
-		const int n_chunk = rg.n_chunk[id][s];
 		const bool fresh = s == 0 || sync_reset;      // sync_reset (opt-in): score every candidate on its own correlation
 		__syncwarp();
 		// up to three search offsets per lane (m, m+32, m+64) share every tap load; their |corr| sums over
-		// the chunks stay in registers.  Offsets >= w are computed too (accv is padded to whole rows of 32,
-		// the samples they read are whatever finite values follow the region) and never looked at.
-		for (int mb = 0; mb < w; mb += 96) {
-			const int m0 = mb + lane;
-			const bool r1 = mb + 32 < w, r2 = mb + 64 < w;      // warp-uniform: the rows of 32 offsets in use
-			float acc[3];
-#pragma unroll
-			for (int r = 0; r < 3; r++)
-				acc[r] = fresh ? 0.0f : sm.accv[m0 + 32 * r];
-			tl = 0;
-			for (int c = 0; c < n_chunk; c++) {
-				const int cl = rg.cl[id][s][c];
-				const int slot = rg.slot[id][s][c];
-				const float2 Rs = sm.tsum[slot];
-				const float cr0 = nm.ar * Rs.x - nm.ai * Rs.y, ci0 = nm.ar * Rs.y + nm.ai * Rs.x;   // avg * sum(taps)
-				// taps beyond cl are zero, so the tap loop runs in whole groups of 4.  The up to 3 zero taps
-				// may read up to 3*sps samples past their region: that lands in this warp's other regions /
-				// taps / accv / zbuf, which only ever hold finite floats, and 0 * finite adds nothing.
-				const int cl4 = (cl + 3) & ~3;
-				float2 P[3], Q[3];
-#pragma unroll
-				for (int r = 0; r < 3; r++)
-					P[r] = Q[r] = make_float2(0.0f, 0.0f);
-				const float2 *g = sm.reg + rg.roff[id][s][c] + m0;
-				const float2 *tp = sm.taps + slot * 32;
-				if (r2)
-					corr_taps<3>(g, tp, cl4, sps, P, Q);
-				else if (r1)
-					corr_taps<2>(g, tp, cl4, sps, P, Q);
-				else
-					corr_taps<1>(g, tp, cl4, sps, P, Q);
-#pragma unroll
-				for (int r = 0; r < 3; r++) {
-					const float xr = ((P[r].x - Q[r].y) - cr0) * nm.inv_sd, xi = ((P[r].y + Q[r].x) - ci0) * nm.inv_sd;
-					const float e = fmaf(xr, xr, xi * xi);
-					float rs;
-					asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(e));
-					acc[r] += e > 0.0f ? e * rs : 0.0f;
-				}
-				tl += cl;
-			}
-			sm.accv[m0] = acc[0];
-			if (r1)
-				sm.accv[m0 + 32] = acc[1];
-			if (r2)
-				sm.accv[m0 + 64] = acc[2];
-		}
+		// the chunks stay in registers.  Offsets >= w are computed too (the samples they read are whatever
+		// finite values follow the region) and never stored.
+		int tl;
+		if (ROWS > 0)
+			tl = corr_block<(ROWS > 0 ? ROWS : 1), SPS>(rg, id, s, sm, nm, sps_rt, w, lane, fresh);
+		else
+			tl = corr_generic<SPS>(rg, id, s, sm, nm, sps_rt, w, lane, fresh);
 		__syncwarp();
 		float peak;
-		const float s_toa = peak_early_late(sm.accv, w, tpl, lane, peak);
+		const float s_toa = peak_early_late<ROWS>(sm.accv, w, tpl, lane, peak);
 		peak /= (float)tl;
 		const float s_pwr = peak * peak;
 		if (s_pwr > p_pwr) {
@@ -592,24 +658,65 @@ __device__ void build_flat(const BurstTab &bt, FlatTab &ft, const Regions &rg, i
 		}
 }
 
+// Soft bits of one data symbol (pi4cxpsk.c:468-503) for the symbol value sv = angle / (2*pi / 2^NB):
+// nearest symbol sp, distance to it d = round(128 * |round(sv) - sv|), each bit 127 - d (the bit that flips
+// towards the second-nearest symbol) or 127 - d/2 (the others), sign by the Gray bit.  NB == 2: first bit in
+// the low byte, second in the high byte.
+template <int NB>
+__device__ __forceinline__ unsigned soft_word(float sv)
+{
+	constexpr int mask = (1 << NB) - 1;
+	constexpr float period = (float)(1 << NB), inv_period = 1.0f / period;
+	sv = fmaf(-period, rintf(sv * inv_period), sv);        // -> [-period/2, period/2]
+	const float svr = rintf(sv);
+	const int sp = (int)svr & mask;
+	const bool below = svr > sv;                   // second-nearest symbol is sp-1, else sp+1
+	const int dq = __float2int_rn(128.0f * fabsf(svr - sv));
+	const int v_far = 127 - dq, v_near = 127 - (dq >> 1);
+	if (NB == 2) {
+		// Gray map {00, 01, 11, 10}, MSB first.  sp -> sp+1 flips the LSB when sp is even, the MSB
+		// when sp is odd; sp -> sp-1 the other way round.
+		const int gp = sp ^ (sp >> 1);
+		const bool msb_flips = ((sp & 1) != 0) != below;
+		const int m1 = msb_flips ? v_far : v_near, m0 = msb_flips ? v_near : v_far;
+		const int b1 = (gp & 2) ? -m1 : m1, b0 = (gp & 1) ? -m0 : m0;
+		return (unsigned)((b1 & 0xff) | ((b0 & 0xff) << 8));
+	}
+	return (unsigned)((sp ? -v_far : v_far) & 0xff);       // one bit per symbol: both neighbours flip it
+}
+
+// The soft word is piecewise constant in sv with every breakpoint on a multiple of 1/256 (symbol decision at
+// k + 1/2, `below` at k, the rounding of d at k +- (2n+1)/256), and periodic with 2^NB.  So it is a table
+// over floor(256 * sv) mod 256 * 2^NB, filled once per CTA from soft_word() at the cell centres; per symbol
+// that leaves a multiply, a float-to-int, a mask and a shared-memory load.
+static constexpr int LUT_CELLS = 256;
+
 // mode 0: demod (bts[0] only).  mode 1: detect among n_bt burst types (pi4cxpsk.c:617-682).
 // NB = bits per symbol of bts[0] (compile time: the soft-bit mapping is straight-line code).
 // Persistent: each warp strides over the bursts of the batch.
-template <int MODE, int SPS, int NB>
+template <int MODE, int SPS, int NB, int ROWS>
 __global__ void __launch_bounds__(DM_WARPS * 32, DM_MIN_CTAS)
 demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int warp_bytes,
              const __grid_constant__ Regions rg)
 {
 	extern __shared__ __align__(16) uint8_t smem[];
 	__shared__ FlatTab ft;
+#if DM_OPT_LUT
+	__shared__ uint16_t soft_lut[LUT_CELLS << NB];
+#endif
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const BurstTab &bt = bts[0];
 	const int sps = SPS > 0 ? SPS : a.sps, L = a.win_len;
 	const int w = L - bt.len * sps + 1;
 	const WarpSmem sm = carve(smem + (size_t)warp * warp_bytes, rg.total, w, rg.n_slot);
 
-	if (MODE == 0)
+	if (MODE == 0) {
 		build_flat(bt, ft, rg, sps);
+#if DM_OPT_LUT
+		for (int k = threadIdx.x; k < (LUT_CELLS << NB); k += blockDim.x)
+			soft_lut[k] = (uint16_t)soft_word<NB>(((float)k + 0.5f) * (1.0f / LUT_CELLS));
+#endif
+	}
 	if (threadIdx.x == 0)
 		ft.dst_ok = (L >> 1) <= MAX_DST4;
 	if ((L >> 1) <= MAX_DST4)
@@ -627,8 +734,8 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 		sm.taps[i] = make_float2(0.0f, 0.0f);
 	for (int i = lane; i < ((rg.n_slot + 1) & ~1); i += 32)
 		sm.tsum[i] = make_float2(0.0f, 0.0f);
-	for (int i = lane; i < ((w + 31) & ~31); i += 32)
-		sm.accv[i] = 0.0f;
+	for (int i = lane; i < ((w + 31) & ~31) + 8; i += 32)
+		sm.accv[i - 4] = 0.0f;
 	for (int i = lane; i < MAX_TRAIN; i += 32)
 		sm.zbuf[i] = make_float2(0.0f, 0.0f);
 	__syncthreads();
@@ -639,9 +746,7 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 	tpl.sgn = lane < 21 ? (((lane - 10) & 1) ? 1.0f : -1.0f) : 0.0f;
 
 	const bool want_sd = a.pwr != nullptr || (MODE == 1 && (a.e_toa != nullptr || a.e_toa0 >= 0.0f));
-	constexpr int mask = (1 << NB) - 1;
-	constexpr float period = (float)(1 << NB), inv_period = 1.0f / period;
-	constexpr float inv_dd = period * 0.15915494309189533577f;        // symbol steps per radian
+	constexpr float inv_dd256 = (float)(LUT_CELLS << NB) * 0.15915494309189533577f;     // table cells per radian
 	// 2*pi = TWO_PI_HI + TWO_PI_LO, TWO_PI_HI with 9 significant bits: k * TWO_PI_HI is exact for |k| < 2^15
 	constexpr float TWO_PI_HI = 6.28125f, TWO_PI_LO = 1.9353071795864769e-3f, INV_2PI = 0.15915494309189533577f;
 	float fs_taps = __int_as_float(0x7fc00000);     // frequency shift the cached taps were built for (NaN: none)
@@ -659,19 +764,16 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 		}
 		// aligned windows fill the correlation regions from the loads of the statistics pass
 		const bool fill = ft.dst_ok && (((uintptr_t)x) & 15) == 0;
-		const Norm nm = want_sd ? load_stats_t<true>(x, L, lane, fill, ft.dst4, sm.reg)
-		                        : load_stats_t<false>(x, L, lane, fill, ft.dst4, sm.reg);
-		if (!fill)
-			load_regions(x, L, rg, sm.reg, lane);
-		else
-			__syncwarp();
+		const Norm nm = (fill && !want_sd) ? load_stats_t<false, true>(x, L, lane, true, ft.dst4, sm.reg)
+		                                   : load_stats_cold(x, L, lane, want_sd, fill, ft.dst4, rg, sm.reg);
+		__syncwarp();
 		if (MODE == 1) {
 			const float e_toa = a.e_toa ? a.e_toa[b] : a.e_toa0;
 			int p_id = -1, p_sid = -1;
 			float p_toa = 0.0f, p_pwr = 0.0f;
 			for (int id = 0; id < n_bt; id++) {
 				float toa, pwr;
-				const int sid = sync_find<SPS>(rg, id, sm, nm, sps, w, tpl, lane, a.sync_reset != 0, toa, pwr);
+				const int sid = sync_find<SPS, ROWS>(rg, id, sm, nm, sps, w, tpl, lane, a.sync_reset != 0, toa, pwr);
 				if (e_toa >= 0.0f)     // the reference divides by fabs() in double (pi4cxpsk.c:658-659)
 					pwr = (float)((double)pwr / fabs((double)(e_toa - toa)));
 				if (pwr > p_pwr) {
@@ -691,7 +793,7 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 		}
 
 		float toa, pwr;
-		const int sync_id = sync_find<SPS>(rg, 0, sm, nm, sps, w, tpl, lane, a.sync_reset != 0, toa, pwr);
+		const int sync_id = sync_find<SPS, ROWS>(rg, 0, sm, nm, sps, w, tpl, lane, a.sync_reset != 0, toa, pwr);
 		if (lane == 0) {
 			if (a.sync_id) a.sync_id[b] = sync_id;
 			if (a.toa) a.toa[b] = toa;
@@ -700,6 +802,7 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 		int8_t *eb = a.ebits + (size_t)b * a.ebits_stride;
 		if (sync_id < 0) {          // nothing correlated (all-zero input): the reference returns -errno
 			if (lane == 0 && a.freq_err) a.freq_err[b] = 0.0f;
+#pragma unroll 1
 			for (int k = lane; k < bt.ebits; k += 32)
 				eb[k] = 0;
 			continue;
@@ -721,6 +824,7 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 		const int nch = rg.n_chunk[0][sync_id], ntr = ft.n_train[sync_id];
 		float2 z0 = make_float2(0.0f, 0.0f);     // training symbol `lane` (round 0) stays in registers
 		int ch0 = -1;
+#pragma unroll 1
 		for (int t0 = 0; t0 < ntr; t0 += 32) {
 			const int t = t0 + lane;
 			if (t < ntr) {
@@ -752,6 +856,7 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 #pragma unroll 1
 			for (int c = 0; c < nch; c++) {
 				float cr = ch0 == c ? z0.x : 0.0f, ci = ch0 == c ? z0.y : 0.0f;
+#pragma unroll 1
 				for (int t = 32 + lane; t < ntr; t += 32)      // only RACH has more than 32 training symbols
 					if (ft.t_chunk[sync_id][t] == c) {
 						const float2 z = sm.zbuf[t];
@@ -776,6 +881,7 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 		float phi0;
 		{
 			float pr = 0.0f, pi = 0.0f;
+#pragma unroll 1
 			for (int t0 = 0; t0 < ntr; t0 += 32) {
 				const int t = t0 + lane;
 				if (t < ntr) {
@@ -804,29 +910,22 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 		// soft bits of data symbol t (burst position i) whose derotated angle, before the -ferr*i and
 		// -phase corrections, is ang
 		auto emit = [&](int t, int i, float ang) {
-			float sv = ((ang + nferr * (float)i) + nphi0) * inv_dd;
-			sv = fmaf(-period, rintf(sv * inv_period), sv);        // -> [-period/2, period/2]
-			const float svr = rintf(sv);                   // (ties differ from roundf only on exact .5)
-			const int sp = (int)svr & mask;
-			const bool below = svr > sv;                   // second-nearest symbol is sp-1, else sp+1
-			const int dq = __float2int_rn(128.0f * fabsf(svr - sv));
-			const int v_far = 127 - dq, v_near = 127 - (dq >> 1);     // bit that flips towards the neighbour / bit that does not
+#if DM_OPT_LUT
+			const float sv = ((ang + nferr * (float)i) + nphi0) * inv_dd256;
+			const unsigned v = soft_lut[__float2int_rd(sv) & ((LUT_CELLS << NB) - 1)];
+#else
+			const unsigned v = soft_word<NB>(((ang + nferr * (float)i) + nphi0) * (inv_dd256 * (1.0f / LUT_CELLS)));
+#endif
 			if (NB == 2) {
-				// Gray map {00, 01, 11, 10}, MSB first.  sp -> sp+1 flips the LSB when sp is even, the MSB
-				// when sp is odd; sp -> sp-1 the other way round.
-				const int gp = sp ^ (sp >> 1);
-				const bool msb_flips = ((sp & 1) != 0) != below;
-				const int m1 = msb_flips ? v_far : v_near, m0 = msb_flips ? v_near : v_far;
-				const int b1 = (gp & 2) ? -m1 : m1, b0 = (gp & 1) ? -m0 : m0;      // first, second soft bit
 				int8_t *o = eb + 2 * t;
 				if (eb_even)
-					*reinterpret_cast<uint16_t *>(o) = (uint16_t)((b1 & 0xff) | ((b0 & 0xff) << 8));
+					*reinterpret_cast<uint16_t *>(o) = (uint16_t)v;
 				else {
-					o[0] = (int8_t)b1;
-					o[1] = (int8_t)b0;
+					o[0] = (int8_t)(v & 0xff);
+					o[1] = (int8_t)(v >> 8);
 				}
 			} else {
-				eb[t] = (int8_t)(sp ? -v_far : v_far);     // one bit per symbol: both neighbours flip it
+				eb[t] = (int8_t)v;
 			}
 		};
 		if (SPS < 0) {               // interpolated symbols already carry the derotation
@@ -958,11 +1057,14 @@ cudaError_t launch_demod(const DemodArgs &a, const BurstTab *d_bts, const BurstT
 	}
 	if (dev >= 64 || attr_set[dev] < smem) {
 		cudaError_t e = cudaSuccess;
-		const void *fns[8] = {(const void *)demod_kernel<0, 4, 1>, (const void *)demod_kernel<0, 4, 2>,
-		                      (const void *)demod_kernel<0, 0, 1>, (const void *)demod_kernel<0, 0, 2>,
-		                      (const void *)demod_kernel<0, -1, 1>, (const void *)demod_kernel<0, -1, 2>,
-		                      (const void *)demod_kernel<1, 4, 2>, (const void *)demod_kernel<1, 0, 2>};
-		for (int i = 0; i < 8 && e == cudaSuccess; i++)
+		const void *fns[] = {(const void *)demod_kernel<0, 4, 1, 0>, (const void *)demod_kernel<0, 4, 2, 0>,
+		                     (const void *)demod_kernel<0, 4, 1, 1>, (const void *)demod_kernel<0, 4, 2, 1>,
+		                     (const void *)demod_kernel<0, 4, 1, 2>, (const void *)demod_kernel<0, 4, 2, 2>,
+		                     (const void *)demod_kernel<0, 4, 1, 3>, (const void *)demod_kernel<0, 4, 2, 3>,
+		                     (const void *)demod_kernel<0, 0, 1, 0>, (const void *)demod_kernel<0, 0, 2, 0>,
+		                     (const void *)demod_kernel<0, -1, 1, 0>, (const void *)demod_kernel<0, -1, 2, 0>,
+		                     (const void *)demod_kernel<1, 4, 2, 0>, (const void *)demod_kernel<1, 0, 2, 0>};
+		for (size_t i = 0; i < sizeof(fns) / sizeof(fns[0]) && e == cudaSuccess; i++)
 			e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if (e != cudaSuccess)
 			return e;
@@ -978,7 +1080,7 @@ cudaError_t launch_demod(const DemodArgs &a, const BurstTab *d_bts, const BurstT
 			n_sm[dev] = v;
 	}
 	const int sms = dev < 64 ? n_sm[dev] : 148;
-	int per_sm = (int)((227 * 1024) / (smem + sizeof(FlatTab) + 1024));
+	int per_sm = (int)((228 * 1024) / (smem + sizeof(FlatTab) + 2 * (LUT_CELLS << 2) + 1024 + 64));
 	per_sm = per_sm < 1 ? 1 : (per_sm > DM_MIN_CTAS ? DM_MIN_CTAS : per_sm);
 	if (const char *e = getenv("GMR1B200_DEMOD_CTAS")) {     // tuning knob: resident CTAs per SM
 		const int v = atoi(e);
@@ -991,17 +1093,23 @@ cudaError_t launch_demod(const DemodArgs &a, const BurstTab *d_bts, const BurstT
 	const int nb = h_bts[0].nbits;
 	if (nb != 1 && nb != 2)
 		return cudaErrorInvalidValue;
-#define DM_LAUNCH(M, S, B) demod_kernel<M, S, B><<<grid, DM_WARPS * 32, smem, st>>>(a, d_bts, n_bt, (int)wb, rg)
+#define DM_LAUNCH(M, S, B, R) demod_kernel<M, S, B, R><<<grid, DM_WARPS * 32, smem, st>>>(a, d_bts, n_bt, (int)wb, rg)
+#define DM_LAUNCH_NB(M, S, R) do { if (nb == 1) DM_LAUNCH(M, S, 1, R); else DM_LAUNCH(M, S, 2, R); } while (0)
 	if (mode == 0 && a.sps < 4) {
-		if (nb == 1) DM_LAUNCH(0, -1, 1); else DM_LAUNCH(0, -1, 2);
+		DM_LAUNCH_NB(0, -1, 0);
 	} else if (mode == 0 && a.sps == 4) {
-		if (nb == 1) DM_LAUNCH(0, 4, 1); else DM_LAUNCH(0, 4, 2);
+		// the number of rows of 32 search offsets is a compile-time constant on the fast path
+		if (w <= 32)      DM_LAUNCH_NB(0, 4, 1);
+		else if (w <= 64) DM_LAUNCH_NB(0, 4, 2);
+		else if (w <= 96) DM_LAUNCH_NB(0, 4, 3);
+		else              DM_LAUNCH_NB(0, 4, 0);
 	} else if (mode == 0) {
-		if (nb == 1) DM_LAUNCH(0, 0, 1); else DM_LAUNCH(0, 0, 2);
+		DM_LAUNCH_NB(0, 0, 0);
 	} else if (a.sps == 4)
-		DM_LAUNCH(1, 4, 2);
+		DM_LAUNCH(1, 4, 2, 0);
 	else
-		DM_LAUNCH(1, 0, 2);
+		DM_LAUNCH(1, 0, 2, 0);
+#undef DM_LAUNCH_NB
 #undef DM_LAUNCH
 	return cudaGetLastError();
 }
