@@ -55,6 +55,15 @@ static constexpr int DM_WARPS = 4;
 #ifndef DM_OPT_LUT
 #define DM_OPT_LUT 1
 #endif
+#ifndef DM_OPT_FSC
+#define DM_OPT_FSC 1           // training symbols / phase reference: reduced-argument hardware sincos
+#endif
+#ifndef DM_PREFETCH
+#define DM_PREFETCH 1          // 1: own window into L2 at burst start, 2: next window at the start of the data symbols,
+#endif                         // 3: 1 + the first DM_PF_NEXT bytes of the next window at the start of the data symbols
+#ifndef DM_PF_NEXT
+#define DM_PF_NEXT 2048
+#endif
 #ifndef DM_MIN_CTAS
 #define DM_MIN_CTAS 8          // resident CTAs per SM the register allocation is capped for
 #endif
@@ -63,6 +72,13 @@ static constexpr float PI_F = 3.14159265358979323846264338327f;
 // sin(pi * k / 512), k = 0..512: every position the early/late search visits is a multiple of
 // 1/512 (start integer, steps 1/2 .. 1/512), so the one sine an interpolation needs is a lookup
 __constant__ float c_sinpi512[513];
+
+// whole window -> L2 with one bulk prefetch (TMA unit, no registers, no completion to wait for)
+__device__ __forceinline__ void prefetch_window_l2(const float2 *x, int bytes)
+{
+	if ((((uintptr_t)x) & 15) == 0)
+		asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(x), "r"(bytes & ~15) : "memory");
+}
 
 __device__ __forceinline__ float warp_sum(float v)
 {
@@ -90,6 +106,24 @@ __device__ __noinline__ float2 sincos_acc(float x)
 	float sn, cs;
 	sincosf(x, &sn, &cs);
 	return make_float2(cs, sn);
+}
+
+// e^{jx} for the per-symbol derotations of the hot path: x (up to a few hundred radians, fl32(fs * idx) as the
+// reference forms it) is reduced mod 2*pi with a two-constant Cody-Waite step (2*pi = HI + LO, HI has 9
+// significant bits, so k * HI is exact), then the hardware sine / cosine: ~5e-7 absolute error, against the
+// 3e-5 rad that move one soft bit by one LSB in 0.5 % of the symbols.
+__device__ __forceinline__ float2 sincos_red(float x)
+{
+#if DM_OPT_FSC
+	const float k = rintf(x * 0.15915494309189533577f);
+	float r = fmaf(k, -6.28125f, x);
+	r = fmaf(k, -1.9353071795864769e-3f, r);
+	float sn, cs;
+	__sincosf(r, &sn, &cs);
+	return make_float2(cs, sn);
+#else
+	return sincos_acc(x);
+#endif
 }
 
 // conj(ref) * g for ref in {1, j, -1, -j} (symbol index 0..3): exact component shuffles
@@ -757,6 +791,13 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 		const float freq_shift = a.freq_shift ? a.freq_shift[b] : a.freq_shift0;
 		const float fs = (freq_shift - rg.rotation0) / (float)sps;
 
+#if DM_PREFETCH == 1 || DM_PREFETCH == 3
+		// The statistics pass has 4 x 16 bytes per lane in flight (register budget) and would meet the DRAM
+		// latency four times per window; with the whole window requested up front, batches 2-4 find their
+		// lines in L2 or on the way.  No extra L2 footprint: it is this warp's own, current window.
+		if (lane == 0)
+			prefetch_window_l2(x, L * 8);
+#endif
 		__syncwarp();
 		if (fs != fs_taps) {
 			build_taps(bts, n_bt, rg, sm, fs, sps, lane);
@@ -837,7 +878,7 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 					// reads the sample in front of the chunk: regions start one pair early for that.)
 					const int q = sample_of(pos);
 					const float2 v = sm.reg[(int)ft.t_off[sync_id][t] + d];
-					const float2 e = sincos_acc(fs * (float)q);
+					const float2 e = sincos_red(fs * (float)q);
 					const float yr = (v.x - nm.ar) * nm.inv_sd, yi = (v.y - nm.ai) * nm.inv_sd;
 					y = make_float2(yr * e.x - yi * e.y, yr * e.y + yi * e.x);
 				}
@@ -887,7 +928,7 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 				if (t < ntr) {
 					float2 z = sm.zbuf[t];
 					if (ferr != 0.0f) {
-						const float2 e = sincos_acc((-ferr) * (float)ft.t_pos[sync_id][t]);
+						const float2 e = sincos_red((-ferr) * (float)ft.t_pos[sync_id][t]);
 						z = make_float2(z.x * e.x - z.y * e.y, z.x * e.y + z.y * e.x);
 					}
 					pr += z.x;
@@ -935,6 +976,14 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 				emit(t, i, fast_atan2f_inl(z.y, z.x));
 			}
 		} else {
+#if DM_PREFETCH >= 2
+			{	// the next window of this warp starts its way to L2 while the data symbols are sliced
+				const int bn = b + gridDim.x * DM_WARPS;
+				if (lane == 0 && bn < n_eff)
+					prefetch_window_l2(a.iq + (a.ofs ? a.ofs[bn] : (int64_t)bn * a.stride),
+					                   DM_PREFETCH == 3 ? min(L * 8, DM_PF_NEXT) : L * 8);
+			}
+#endif
 			// four symbols per lane and pass: the four sample loads (L2 hits) are in flight together
 #pragma unroll 1
 			for (int t0 = lane; t0 < nds; t0 += 32 * DM_SYM_BATCH) {
