@@ -653,11 +653,12 @@ struct FlatTab {
 	uint8_t  t_chunk[MAX_SYNC][MAX_TRAIN];
 	int32_t  n_train[MAX_SYNC];
 	int32_t  n_dsym;
+	int32_t  d_lo, d_hi;             // symbol-pick offsets (samples) for which every data symbol lies inside the window
 	int32_t  dst_ok;                 // dst4 is valid (the window has at most 2 * MAX_DST4 samples)
 	uint16_t dst4[MAX_DST4 + 1];     // pair of samples -> float4 slot of the region buffer, 0xffff: not in a region
 };
 
-__device__ void build_flat(const BurstTab &bt, FlatTab &ft, const Regions &rg, int sps)
+__device__ void build_flat(const BurstTab &bt, FlatTab &ft, const Regions &rg, int sps, int L)
 {
 	for (int t = threadIdx.x; t < 480; t += blockDim.x) {
 		int acc = 0, pos = 0;
@@ -669,6 +670,15 @@ __device__ void build_flat(const BurstTab &bt, FlatTab &ft, const Regions &rg, i
 		ft.d_pos[t] = (uint16_t)pos;
 		if (t == 0)
 			ft.n_dsym = acc;
+	}
+	if (threadIdx.x == 0) {
+		int lo = 1 << 30, hi = 0;
+		for (int c = 0; c < bt.n_data; c++) {
+			lo = min(lo, (int)bt.d_pos[c]);
+			hi = max(hi, bt.d_pos[c] + bt.d_len[c] - 1);
+		}
+		ft.d_lo = -lo * sps;
+		ft.d_hi = L - 1 - hi * sps;
 	}
 	for (int s = 0; s < bt.n_sync; s++)
 		for (int t = threadIdx.x; t < MAX_TRAIN; t += blockDim.x) {
@@ -745,7 +755,7 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 	const WarpSmem sm = carve(smem + (size_t)warp * warp_bytes, rg.total, w, rg.n_slot);
 
 	if (MODE == 0) {
-		build_flat(bt, ft, rg, sps);
+		build_flat(bt, ft, rg, sps, L);
 #if DM_OPT_LUT
 		for (int k = threadIdx.x; k < (LUT_CELLS << NB); k += blockDim.x)
 			soft_lut[k] = (uint16_t)soft_word<NB>(((float)k + 0.5f) * (1.0f / LUT_CELLS));
@@ -779,6 +789,9 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 	tpl.xj = PI_F * (float)(lane - 10);
 	tpl.sgn = lane < 21 ? (((lane - 10) & 1) ? 1.0f : -1.0f) : 0.0f;
 
+#if DM_OPT_LUT
+	const unsigned lut_s = (unsigned)__cvta_generic_to_shared(soft_lut);
+#endif
 	const bool want_sd = a.pwr != nullptr || (MODE == 1 && (a.e_toa != nullptr || a.e_toa0 >= 0.0f));
 	constexpr float inv_dd256 = (float)(LUT_CELLS << NB) * 0.15915494309189533577f;     // table cells per radian
 	// 2*pi = TWO_PI_HI + TWO_PI_LO, TWO_PI_HI with 9 significant bits: k * TWO_PI_HI is exact for |k| < 2^15
@@ -984,26 +997,57 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 					                   DM_PREFETCH == 3 ? min(L * 8, DM_PF_NEXT) : L * 8);
 			}
 #endif
-			// four symbols per lane and pass: the four sample loads (L2 hits) are in flight together
+			// DM_SYM_BATCH symbols per lane and pass: their sample loads (L2 hits) are in flight together and the
+			// angle arithmetic of the batch is straight-line code (indices past the end are clamped and only
+			// the store is predicated), so the independent chains interleave.
+			const int dc = min(max(d, ft.d_lo), ft.d_hi);        // no data symbol leaves the window (never binds for the standard formats)
+			const float2 *xd = x + dc;
+			const bool fast_store = NB == 1 || eb_even;
 #pragma unroll 1
 			for (int t0 = lane; t0 < nds; t0 += 32 * DM_SYM_BATCH) {
-				int ii[DM_SYM_BATCH], qq[DM_SYM_BATCH];
+				int ii[DM_SYM_BATCH];
 				float2 v[DM_SYM_BATCH];
 #pragma unroll
 				for (int u = 0; u < DM_SYM_BATCH; u++) {
 					ii[u] = ft.d_pos[min(t0 + 32 * u, nds - 1)];
-					qq[u] = sample_of(ii[u]);
-					v[u] = __ldg(&x[qq[u]]);
+					v[u] = __ldg(&xd[ii[u] * sps]);
 				}
+				unsigned sw[DM_SYM_BATCH];
 #pragma unroll
 				for (int u = 0; u < DM_SYM_BATCH; u++) {
-					if (t0 + 32 * u < nds) {
-						const float th = fast_atan2f_inl(v[u].y - nm.ai, v[u].x - nm.ar);
-						const float a1 = fs * (float)qq[u];
-						const float k = rintf(a1 * INV_2PI);
-						float r = fmaf(k, -TWO_PI_HI, a1);
-						r = fmaf(k, -TWO_PI_LO, r);
-						emit(t0 + 32 * u, ii[u], th + r);
+					const float th = fast_atan2f_inl(v[u].y - nm.ai, v[u].x - nm.ar);
+					const float a1 = fs * (float)(ii[u] * sps + dc);
+					const float k = rintf(a1 * INV_2PI);
+					float r = fmaf(k, -TWO_PI_HI, a1);
+					r = fmaf(k, -TWO_PI_LO, r);
+					const float sv = (((th + r) + nferr * (float)ii[u]) + nphi0) * inv_dd256;
+#if DM_OPT_LUT
+					const unsigned cell = (unsigned)__float2int_rd(sv) & ((LUT_CELLS << NB) - 1);
+					asm("ld.shared.u16 %0, [%1];" : "=r"(sw[u]) : "r"(lut_s + 2 * cell));
+#else
+					sw[u] = soft_word<NB>(sv * (1.0f / LUT_CELLS));
+#endif
+				}
+				if (fast_store) {
+#pragma unroll
+					for (int u = 0; u < DM_SYM_BATCH; u++)
+						if (t0 + 32 * u < nds) {
+							if (NB == 2)
+								reinterpret_cast<uint16_t *>(eb)[t0 + 32 * u] = (uint16_t)sw[u];
+							else
+								eb[t0 + 32 * u] = (int8_t)sw[u];
+						}
+				} else {
+#pragma unroll 1
+					for (int u = 0; u < DM_SYM_BATCH; u++) {     // odd output address: byte stores (cold)
+						unsigned val = sw[0];
+#pragma unroll
+						for (int k = 1; k < DM_SYM_BATCH; k++)
+							val = u == k ? sw[k] : val;
+						if (t0 + 32 * u < nds) {
+							eb[2 * (t0 + 32 * u)] = (int8_t)(val & 0xff);
+							eb[2 * (t0 + 32 * u) + 1] = (int8_t)(val >> 8);
+						}
 					}
 				}
 			}
