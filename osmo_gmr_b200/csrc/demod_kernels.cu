@@ -55,6 +55,9 @@ static constexpr int DM_WARPS = 4;
 #ifndef DM_OPT_LUT
 #define DM_OPT_LUT 1
 #endif
+#ifndef DM_OPT_RADIX
+#define DM_OPT_RADIX 1         // early/late search: three 8-point evaluations instead of eight sequential steps
+#endif
 #ifndef DM_OPT_FSC
 #define DM_OPT_FSC 1           // training symbols / phase reference: reduced-argument hardware sincos
 #endif
@@ -180,7 +183,7 @@ __device__ __forceinline__ float ld_acc(const float *acc, int k, int len)
 // osmo_cxvec_peak_energy_find(acc, 3, PEAK_EARLY_LATE, &peak) on a real vector; all lanes
 // return the same position / peak value
 template <int ROWS>
-__device__ __forceinline__ float peak_early_late(const float *acc, int w, const TapLane &tp, int lane, float &peak_val)
+__device__ __forceinline__ float peak_early_late(const float *acc, float *aw, int w, const TapLane &tp, int lane, float &peak_val)
 {
 	// acc[-2], acc[-1] are zero and the row of 32 that holds acc[w-1] is zero beyond it (sync_find), so the
 	// energy windows need no edge cases: val[idx] = acc[idx-2]^2 + acc[idx-1]^2 + acc[idx]^2
@@ -230,6 +233,94 @@ __device__ __forceinline__ float peak_early_late(const float *acc, int w, const 
 			mwi = max_idx + 2;
 	}
 
+#if DM_OPT_RADIX
+	// The search starts at mwi-1 and moves by less than 1 in total, so floor(early) is mwi-2 or mwi-1 (mwi-1 .. mwi
+	// for the final interpolation) and only acc[mwi-12 .. mwi+12] is ever read: copy that window (zero outside
+	// the vector, as the interpolation treats it) to aw[0..24], aw[25..27] = 0.
+	__syncwarp();
+	if (lane < 28)
+		aw[lane] = lane < 25 ? ld_acc(acc, mwi - 12 + lane, w) : 0.0f;
+	__syncwarp();
+	const float fbase = (float)(mwi - 2);
+
+	// Step 1 sits on an integer position: the interpolation there is the sample itself.
+	float early = (float)(mwi - 1);
+	bool live;
+	{
+		const float e = aw[11], l = aw[13];
+		const float e2 = e * e, l2 = l * l;
+		live = e2 != l2;
+		early += e2 < l2 ? 0.5f : (live ? -0.5f : 0.0f);
+	}
+	// Steps 2..9 (incr = 1/4 .. 1/512, the reference stops when incr <= 1/1024) visit positions with a
+	// fractional part f in (0, 1): every sinc weight is sin(pi f) * -(-1)^j / (pi (j - f)), and the early and
+	// the late gate share f, so the comparison e^2 < l^2 only needs  sum_j -(-1)^j acc[.+j] / (j - f)
+	// for the two gates - no sine, one reciprocal per tap.
+	// Three steps at a time: steps 2-4 can only visit early + m/8, m in {0, +-2, +-1, +-3} (then +- 1/16), steps
+	// 5-7 the same on a grid of 1/64, steps 8-9 on 1/512.  Each round evaluates the 8 grid points in parallel -
+	// one quad of lanes per point, 5-6 taps per lane - and then walks the three decisions on the ballots: same
+	// comparisons, same result, three dependent rounds instead of eight.
+	const int q = lane & 3;
+	const float fm = (float)((lane >> 2) - 3);                  // grid point of this quad (m = 4 is never visited)
+	const float fq = (float)(q - 10), sgn = (q & 1) ? 1.0f : -1.0f;     // first tap of this lane, -(-1)^j (j = q - 10 + 4k)
+	float h = 0.125f;
+#pragma unroll 1
+	for (int round = 0; round < 3 && live; round++, h *= 0.125f) {
+		const float pe = fmaf(fm, h, early);
+		const float fl = floorf(pe), f = pe - fl;
+		const float *ap = aw + q + (fl != fbase ? 1 : 0);       // early gate reads acc[floor(pe) + j], late gate + 2
+		float te = 0.0f, tl = 0.0f;
+#pragma unroll
+		for (int k = 0; k < 6; k++) {
+			float r;
+			asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((fq + (float)(4 * k)) - f));
+			if (k == 5)
+				r = q == 0 ? r : 0.0f;                          // j = q + 10: only tap 10 exists
+			te = fmaf(ap[4 * k], r, te);
+			tl = fmaf(ap[4 * k + 2], r, tl);
+		}
+		te *= sgn;
+		tl *= sgn;
+		te += __shfl_xor_sync(0xffffffffu, te, 1);
+		tl += __shfl_xor_sync(0xffffffffu, tl, 1);
+		te += __shfl_xor_sync(0xffffffffu, te, 2);
+		tl += __shfl_xor_sync(0xffffffffu, tl, 2);
+		const float e2 = te * te, l2 = tl * tl;
+		const unsigned right = __ballot_sync(0xffffffffu, e2 < l2), dead = __ballot_sync(0xffffffffu, e2 == l2);
+		// walk: bit 4*(m+3) of the ballots belongs to grid point m
+		int m = 0;
+		float half = 0.0f;                                      // last move, half a grid step
+		if ((dead >> 12) & 1) {
+			live = false;
+		} else {
+			m = ((right >> 12) & 1) ? 2 : -2;
+			if ((dead >> (4 * (m + 3))) & 1) {
+				live = false;
+			} else {
+				m += ((right >> (4 * (m + 3))) & 1) ? 1 : -1;
+				if (round < 2) {
+					if ((dead >> (4 * (m + 3))) & 1)
+						live = false;
+					else
+						half = ((right >> (4 * (m + 3))) & 1) ? 0.5f : -0.5f;
+				}
+			}
+		}
+		early = fmaf((float)m + half, h, early);
+	}
+	const float pos = early + 1.0f;
+	{
+		// value at the peak: the full sinc weights (osmo_sinc: 1 within |x| < 0.01), one sine from the table
+		const float fl = floorf(pos), frac = pos - fl;
+		const float S = c_sinpi512[(int)(frac * 512.0f)];
+		const float x = fmaf(-PI_F, frac, tp.xj);         // pi*(j - frac)
+		const float wgt = fabsf(x) >= 0.01f ? __fdividef(S, x) : tp.sgn;
+		const int sel = (int)(fl - fbase);            // 1, 2 (or 3 when early ended on mwi exactly)
+		const float cv = lane < 21 ? aw[lane + sel] : 0.0f;
+		peak_val = warp_sum(tp.sgn * cv * wgt);
+	}
+	return pos;
+#else
 	// The search starts at mwi-1 and moves by less than 1 in total, so floor(early) is mwi-2 or
 	// mwi-1 (mwi-1 .. mwi for the final interpolation): tap j of this lane only ever reads
 	// acc[mwi-2+j .. mwi+2+j].  Preload those five values once, with the sign -(-1)^j of the tap folded in.
@@ -285,6 +376,7 @@ __device__ __forceinline__ float peak_early_late(const float *acc, int w, const 
 		peak_val = warp_sum(cv * wgt);
 	}
 	return pos;
+#endif
 }
 
 // Correlation regions: the only samples that are read more than once are those the training-
@@ -597,7 +689,7 @@ __device__ __forceinline__ int sync_find(const Regions &rg, int id, const WarpSm
 			tl = corr_generic<SPS>(rg, id, s, sm, nm, sps_rt, w, lane, fresh);
 		__syncwarp();
 		float peak;
-		const float s_toa = peak_early_late<ROWS>(sm.accv, w, tpl, lane, peak);
+		const float s_toa = peak_early_late<ROWS>(sm.accv, reinterpret_cast<float *>(sm.zbuf), w, tpl, lane, peak);
 		peak /= (float)tl;
 		const float s_pwr = peak * peak;
 		if (s_pwr > p_pwr) {
