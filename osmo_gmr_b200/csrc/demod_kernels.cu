@@ -287,25 +287,18 @@ __device__ __forceinline__ float peak_early_late(const float *acc, float *aw, in
 		tl += __shfl_xor_sync(0xffffffffu, tl, 2);
 		const float e2 = te * te, l2 = tl * tl;
 		const unsigned right = __ballot_sync(0xffffffffu, e2 < l2), dead = __ballot_sync(0xffffffffu, e2 == l2);
-		// walk: bit 4*(m+3) of the ballots belongs to grid point m
-		int m = 0;
-		float half = 0.0f;                                      // last move, half a grid step
-		if ((dead >> 12) & 1) {
-			live = false;
-		} else {
-			m = ((right >> 12) & 1) ? 2 : -2;
-			if ((dead >> (4 * (m + 3))) & 1) {
-				live = false;
-			} else {
-				m += ((right >> (4 * (m + 3))) & 1) ? 1 : -1;
-				if (round < 2) {
-					if ((dead >> (4 * (m + 3))) & 1)
-						live = false;
-					else
-						half = ((right >> (4 * (m + 3))) & 1) ? 0.5f : -0.5f;
-				}
-			}
-		}
+		// walk: bit 4*(m+3) of the ballots belongs to grid point m.  stop = first level (0, 1, 2) whose point is
+		// dead (3: none); moves of levels past it are dropped.
+		const unsigned r0 = (right >> 12) & 1u, d0 = (dead >> 12) & 1u;
+		const int m1 = r0 ? 2 : -2;
+		const unsigned s1 = 4u * (unsigned)(m1 + 3);
+		const unsigned r1 = (right >> s1) & 1u, d1 = (dead >> s1) & 1u;
+		const int m2 = m1 + (r1 ? 1 : -1);
+		const unsigned s2 = 4u * (unsigned)(m2 + 3);
+		const unsigned r2 = (right >> s2) & 1u, d2 = ((dead >> s2) & 1u) | (round == 2 ? 1u : 0u);
+		const int m = d0 ? 0 : (d1 ? m1 : m2);
+		const float half = (d0 | d1 | d2) ? 0.0f : (r2 ? 0.5f : -0.5f);
+		live = !(d0 | d1 | (round < 2 ? d2 : 0u));
 		early = fmaf((float)m + half, h, early);
 	}
 	const float pos = early + 1.0f;
@@ -444,6 +437,7 @@ __device__ __forceinline__ Norm load_stats_t(const float2 *__restrict__ x, int L
                                              const bool FILL, const uint16_t *dst4, float2 *reg)
 {
 	float sr = 0.0f, si = 0.0f, sq = 0.0f;
+	float2 s2 = make_float2(0.0f, 0.0f);
 	if (ALIGNED || (((uintptr_t)x) & 15) == 0) {
 		// 16-byte aligned window: two samples per lane per load
 		const float4 *x4 = reinterpret_cast<const float4 *>(x);
@@ -457,8 +451,7 @@ DM_UNROLL(DM_STATS_UNROLL)
 				if (d != 0xffffu)
 					reg4[d] = v;
 			}
-			sr += v.x + v.z;
-			si += v.y + v.w;
+			s2 = __fadd2_rn(s2, __fadd2_rn(make_float2(v.x, v.y), make_float2(v.z, v.w)));     // two FADD2
 			if (WANT_SD) {
 				sq = fmaf(v.x, v.x, sq);
 				sq = fmaf(v.y, v.y, sq);
@@ -488,8 +481,8 @@ DM_UNROLL(DM_STATS_UNROLL)
 				sq += v.x * v.x + v.y * v.y;
 		}
 	}
-	sr = warp_sum(sr);
-	si = warp_sum(si);
+	sr = warp_sum(sr + s2.x);
+	si = warp_sum(si + s2.y);
 	Norm n;
 	n.ar = sr / (float)L;
 	n.ai = si / (float)L;
@@ -632,11 +625,12 @@ __device__ __forceinline__ int corr_block(const Regions &rg, int id, int s, cons
 		corr_taps<R>(sm.reg + rg.roff[id][s][c] + m0, sm.taps + slot * 32, cl4, sps, P, Q);
 #pragma unroll
 		for (int r = 0; r < R; r++) {
-			const float xr = ((P[r].x - Q[r].y) - cr0) * nm.inv_sd, xi = ((P[r].y + Q[r].x) - ci0) * nm.inv_sd;
-			const float e = fmaf(xr, xr, xi * xi);
-			float rs;
-			asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(e));
-			acc[r] += e > 0.0f ? e * rs : 0.0f;
+			// |corr| / sd: the scale is applied to the magnitude (one multiply instead of two), the square
+			// root is the approximate one (MUFU.SQRT, 0 -> 0)
+			const float xr = (P[r].x - Q[r].y) - cr0, xi = (P[r].y + Q[r].x) - ci0;
+			float mag;
+			asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(mag) : "f"(fmaf(xr, xr, xi * xi)));
+			acc[r] = fmaf(mag, nm.inv_sd, acc[r]);
 		}
 		tl += cl;
 	}
