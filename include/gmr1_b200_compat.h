@@ -155,4 +155,42 @@ void gmr1_scramble_ubit(ubit_t *out, const ubit_t *in, int len);
 void gmr1_a5(int n, uint8_t *key, uint32_t fn, int nbits, ubit_t *dl, ubit_t *ul);
 void gmr1_a5_1(uint8_t *key, uint32_t fn, int nbits, ubit_t *dl, ubit_t *ul);
 
+/* ---- l1/conv.h:36-44, l1/crc.h:36-38, l1/punct.h:38-106: the code tables as data symbols ----
+ * (libosmocore types as the reference's headers see them: osmocom/core/conv.h, osmocom/core/crcgen.h) */
+enum osmo_conv_term { CONV_TERM_FLUSH = 0, CONV_TERM_TRUNCATION, CONV_TERM_TAIL_BITING };
+struct osmo_conv_code {
+	int N;
+	int K;
+	int len;
+	enum osmo_conv_term term;
+	const uint8_t (*next_output)[2];
+	const uint8_t (*next_state)[2];
+	const uint8_t *next_term_output;
+	const uint8_t *next_term_state;
+	const int *puncture;
+};
+struct osmo_crc8gen_code  { int bits; uint8_t  poly, init, remainder; };
+struct osmo_crc16gen_code { int bits; uint16_t poly, init, remainder; };
+
+extern const struct osmo_conv_code gmr1_conv_k5_12, gmr1_conv_k5_13, gmr1_conv_k5_14, gmr1_conv_k5_15,
+                                   gmr1_conv_k6_14, gmr1_conv_k9_12, gmr1_conv_k9_13, gmr1_conv_k9_14,
+                                   gmr1_conv_tch3;
+extern const struct osmo_crc8gen_code  gmr1_crc8;
+extern const struct osmo_crc16gen_code gmr1_crc12, gmr1_crc16;
+
+struct gmr1_puncturer {                 /* l1/punct.h:38-43 */
+	int r;                              /* punctured bits */
+	int L;                              /* mask length (input bits) */
+	int N;                              /* code rate 1/N */
+	const uint8_t mask[];               /* L*N entries, 0 = punctured */
+};
+/* fills code->puncture (malloc'ed, -1 terminated, owned by the caller); -EINVAL on a rate mismatch */
+int gmr1_puncturer_generate(struct osmo_conv_code *code, const struct gmr1_puncturer *punct_pre,
+                            const struct gmr1_puncturer *punct_main, const struct gmr1_puncturer *punct_post,
+                            int repeat);
+/* the 51 masks gmr1_punct_<code>_<name> of l1/punct.h:56-106 */
+#define PUNCT(name, r, L, N, ...) extern const struct gmr1_puncturer gmr1_punct_##name;
+#include "gmr1_punct_masks.inc"
+#undef PUNCT
+
 #endif /* GMR1_B200_COMPAT_H */
