@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(FR_T, 2) fcch_rough_kernel(const FcchArgs a)
 	float *w   = (float *)smem;            // [ng * FR_GRP] decimated, normalised samples
 	float *ref = w + ng * FR_GRP;          // [lenp]
 	float *red = ref + lenp;               // [96] reduction scratch
-	float *en  = red + 96;                 // [nc] |corr|^2
+	float *en  = red + 96 + 4;             // [nc] |corr|^2, en[-4..-1] = 0 (energy windows need no edge cases)
 
 	const float2 *x = a.iq + (a.ofs ? a.ofs[b] : (int64_t)b * a.stride);
 	const float freq_shift = a.freq_shift ? a.freq_shift[b] : a.freq_shift0;
@@ -93,6 +93,8 @@ __global__ void __launch_bounds__(FR_T, 2) fcch_rough_kernel(const FcchArgs a)
 			ref[i] = i < len ? sqrtf(2.0f) * cosf(phase_base * (pos * pos)) : 0.0f;
 		}
 	}
+	if (tid < 4)
+		en[tid - 4] = 0.0f;
 	for (int i = l + tid; i < ng * 8; i += FR_T) {
 		w[widx(i)] = 0.0f;
 		w[widx(i) + 1] = 0.0f;
@@ -101,9 +103,37 @@ __global__ void __launch_bounds__(FR_T, 2) fcch_rough_kernel(const FcchArgs a)
 	// statistics over ALL samples (sig_normalize averages before decimating); keep every sps-th.
 	// (symbol, phase) of sample i are carried along instead of dividing by the runtime sps.
 	float sr = 0.0f, si = 0.0f, sq = 0.0f;
-	{
+	if (sps == 4 && (((uintptr_t)x) & 15) == 0) {
+		// four samples (one symbol) per thread and pass: two 16-byte loads, packed adds, the first sample is kept
+		const float4 *x4 = reinterpret_cast<const float4 *>(x);
+		const int nq = L >> 2;
+		float2 s2 = make_float2(0.0f, 0.0f), q2 = make_float2(0.0f, 0.0f);
+#pragma unroll 2
+		for (int i = tid; i < nq; i += FR_T) {
+			const float4 v0 = __ldg(&x4[2 * i]), v1 = __ldg(&x4[2 * i + 1]);
+			const float2 p0 = make_float2(v0.x, v0.y), p1 = make_float2(v0.z, v0.w), p2 = make_float2(v1.x, v1.y),
+			             p3 = make_float2(v1.z, v1.w);
+			s2 = __fadd2_rn(s2, __fadd2_rn(__fadd2_rn(p0, p1), __fadd2_rn(p2, p3)));
+			q2 = __ffma2_rn(p0, p0, q2);
+			q2 = __ffma2_rn(p1, p1, q2);
+			q2 = __ffma2_rn(p2, p2, q2);
+			q2 = __ffma2_rn(p3, p3, q2);
+			*reinterpret_cast<float2 *>(&w[widx(i)]) = p0;        // i < l = L / 4
+		}
+		sr = s2.x;
+		si = s2.y;
+		sq = q2.x + q2.y;
+		for (int i = 4 * nq + tid; i < L; i += FR_T) {           // L % 4 trailing samples (none is kept)
+			const float2 v = __ldg(&x[i]);
+			sr += v.x;
+			si += v.y;
+			sq = fmaf(v.x, v.x, sq);
+			sq = fmaf(v.y, v.y, sq);
+		}
+	} else {
 		const int dq = FR_T / sps, dr = FR_T % sps;
 		int sym = tid / sps, ph = tid % sps;
+#pragma unroll 1
 		for (int i = tid; i < L; i += FR_T) {
 			const float2 v = __ldg(&x[i]);
 			sr += v.x;
@@ -126,9 +156,10 @@ __global__ void __launch_bounds__(FR_T, 2) fcch_rough_kernel(const FcchArgs a)
 	float sd = var > 0.0f ? sqrtf(var) : 0.0f;
 	if (sd == 0.0f)
 		sd = 1.0f;
+	const float inv_sd = 1.0f / sd;        // a common scale: one reciprocal instead of two divisions per sample
 	for (int i = tid; i < l; i += FR_T) {
 		float2 *p = reinterpret_cast<float2 *>(&w[widx(i)]);
-		float yr = (p->x - ar) / sd, yi = (p->y - ai) / sd;
+		float yr = (p->x - ar) * inv_sd, yi = (p->y - ai) * inv_sd;
 		if (freq_shift != 0.0f) {
 			float sn, cs;
 			sincosf(freq_shift * (float)i, &sn, &cs);
@@ -153,30 +184,35 @@ __global__ void __launch_bounds__(FR_T, 2) fcch_rough_kernel(const FcchArgs a)
 			c[2 * q] = c[2 * q + 1] = make_float2(0.0f, 0.0f);
 		}
 		const float4 *rp = reinterpret_cast<const float4 *>(ref);
-#pragma unroll 1
-		for (int g = 0; g < (lenp >> 3); g++) {
+		// one group of 8 taps: `cur` holds samples m0 + 8g .. + 7, `nxt` is loaded with the following 8; output t
+		// of tap u reads sample u + t of the 16.  Two groups per iteration with the roles of the two register
+		// windows swapped, so no register is ever copied.
+		auto group = [&](int g, const float2 (&cur)[FR_TILE], float2 (&nxt)[FR_TILE]) {
 			gp += FR_GRP / 4;
-			float2 nxt[FR_TILE];
-			float r[FR_TILE];
 #pragma unroll
 			for (int q = 0; q < 4; q++) {
 				const float4 v = gp[q];
 				nxt[2 * q] = make_float2(v.x, v.y);
 				nxt[2 * q + 1] = make_float2(v.z, v.w);
 			}
-			{
-				const float4 r0 = rp[2 * g], r1 = rp[2 * g + 1];
-				r[0] = r0.x; r[1] = r0.y; r[2] = r0.z; r[3] = r0.w;
-				r[4] = r1.x; r[5] = r1.y; r[6] = r1.z; r[7] = r1.w;
-			}
+			const float4 r0 = rp[2 * g], r1 = rp[2 * g + 1];
+			const float r[FR_TILE] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-			for (int u = 0; u < FR_TILE; u++) {
+			for (int u = 0; u < FR_TILE; u++)
 #pragma unroll
-				for (int t = 0; t < FR_TILE; t++)       // slot (u + t) % 8 holds sample m0 + 8 g + u + t
-					fma2(c[t], r[u], win[(u + t) % FR_TILE]);
-				win[u] = nxt[u];
-			}
+				for (int t = 0; t < FR_TILE; t++)
+					fma2(c[t], r[u], u + t < FR_TILE ? cur[u + t] : nxt[u + t - FR_TILE]);
+		};
+		float2 alt[FR_TILE];
+		const int G = lenp >> 3;
+		int g = 0;
+#pragma unroll 1
+		for (; g + 1 < G; g += 2) {
+			group(g, win, alt);
+			group(g + 1, alt, win);
 		}
+		if (g < G)
+			group(g, win, alt);
 #pragma unroll
 		for (int t = 0; t < FR_TILE; t++)
 			if (m0 + t < nc)
@@ -196,10 +232,15 @@ __global__ void __launch_bounds__(FR_T, 2) fcch_rough_kernel(const FcchArgs a)
 	float best = 0.0f;
 	int best_idx = 0x7fffffff;
 	for (int idx = tid; idx < nc; idx += FR_T) {
-		float val = 0.0f;
-		for (int hi = idx - win + 1; hi <= idx; hi++)
-			if (hi >= 0)
-				val += en[hi];
+		float val;
+		if (win == 5) {          // oldest first, as the reference sums; the zeros in front of en[0] stand in for hi < 0
+			val = ((((0.0f + en[idx - 4]) + en[idx - 3]) + en[idx - 2]) + en[idx - 1]) + en[idx];
+		} else {
+			val = 0.0f;
+			for (int hi = idx - win + 1; hi <= idx; hi++)
+				if (hi >= 0)
+					val += en[hi];
+		}
 		if (val > best) {
 			best = val;
 			best_idx = idx;
@@ -462,7 +503,7 @@ cudaError_t launch_fcch_rough(const FcchArgs &a, cudaStream_t st)
 	if (nc < 1 || a.len > MAX_FCCH_LEN)
 		return cudaErrorInvalidValue;
 	const int lenp = (a.len + 7) & ~7, ng = (l + lenp + 15) >> 3;
-	const size_t smem = sizeof(float) * ((size_t)ng * FR_GRP + lenp + 96 + nc);
+	const size_t smem = sizeof(float) * ((size_t)ng * FR_GRP + lenp + 96 + 4 + nc);
 	if (smem > 227 * 1024)
 		return cudaErrorInvalidValue;
 	static size_t attr_set[64] = {0};
