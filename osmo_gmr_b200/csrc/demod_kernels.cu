@@ -738,6 +738,8 @@ struct FlatTab {
 	uint8_t  t_sym[MAX_SYNC][MAX_TRAIN];
 	uint8_t  t_chunk[MAX_SYNC][MAX_TRAIN];
 	int32_t  n_train[MAX_SYNC];
+	uint8_t  t_end[MAX_SYNC][32];              // training symbol t < 32 -> index after the last symbol of its chunk
+	uint8_t  c_start[MAX_SYNC][MAX_SYNC_CHUNK];   // chunk -> its first training symbol
 	int32_t  n_dsym;
 	int32_t  d_lo, d_hi;             // symbol-pick offsets (samples) for which every data symbol lies inside the window
 	int32_t  dst_ok;                 // dst4 is valid (the window has at most 2 * MAX_DST4 samples)
@@ -783,6 +785,17 @@ __device__ void build_flat(const BurstTab &bt, FlatTab &ft, const Regions &rg, i
 			ft.t_off[s][t] = (uint16_t)off;
 			ft.t_sym[s][t] = (uint8_t)sym;
 			ft.t_chunk[s][t] = (uint8_t)ch;
+			if (t < 32) {
+				int e = 0, a0 = 0;
+				for (int c = 0; c < bt.n_chunk[s]; c++) {
+					if (t >= a0 && t < a0 + bt.s_len[s][c])
+						e = a0 + bt.s_len[s][c];
+					if (t == 0)
+						ft.c_start[s][c] = (uint8_t)min(a0, 255);
+					a0 += bt.s_len[s][c];
+				}
+				ft.t_end[s][t] = (uint8_t)e;
+			}
 			if (t == 0)
 				ft.n_train[s] = acc;
 		}
@@ -820,6 +833,35 @@ __device__ __forceinline__ unsigned soft_word(float sv)
 // over floor(256 * sv) mod 256 * 2^NB, filled once per CTA from soft_word() at the cell centres; per symbol
 // that leaves a multiply, a float-to-int, a mask and a shared-memory load.
 static constexpr int LUT_CELLS = 256;
+
+// frequency error from the chunk-to-chunk phase slope (pi4cxpsk.c:360-406), any number of training symbols
+// (cold: only RACH has more than 32; the usual case is inlined in the kernel)
+__device__ __noinline__ float ferr_generic(const FlatTab &ft, const Regions &rg, const float2 *zbuf, int sync_id, int nch,
+                                           int ntr, float2 z0, int ch0, int lane)
+{
+	float f = 0.0f, prev_r = 0.0f, prev_i = 0.0f, prev_pos = 0.0f;
+#pragma unroll 1
+	for (int c = 0; c < nch; c++) {
+		float cr = ch0 == c ? z0.x : 0.0f, ci = ch0 == c ? z0.y : 0.0f;
+#pragma unroll 1
+		for (int t = 32 + lane; t < ntr; t += 32)
+			if (ft.t_chunk[sync_id][t] == c) {
+				const float2 z = zbuf[t];
+				cr += z.x;
+				ci += z.y;
+			}
+		const float2 sum = warp_sum2(cr, ci, lane);
+		const float pos = rg.cpos[sync_id][c];
+		if (c > 0) {   // arg(corr[c] * conj(corr[c-1])) / (pos[c] - pos[c-1])
+			const float re = sum.x * prev_r + sum.y * prev_i, im = sum.y * prev_r - sum.x * prev_i;
+			f += fast_atan2f(im, re) / (pos - prev_pos);
+		}
+		prev_r = sum.x;
+		prev_i = sum.y;
+		prev_pos = pos;
+	}
+	return f / (float)(nch - 1);
+}
 
 // mode 0: demod (bts[0] only).  mode 1: detect among n_bt burst types (pi4cxpsk.c:617-682).
 // NB = bits per symbol of bts[0] (compile time: the soft-bit mapping is straight-line code).
@@ -991,29 +1033,34 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 		}
 		__syncwarp();
 		float ferr = 0.0f;
-		if (nch > 1) {
-			float f = 0.0f, prev_r = 0.0f, prev_i = 0.0f, prev_pos = 0.0f;
-#pragma unroll 1
-			for (int c = 0; c < nch; c++) {
-				float cr = ch0 == c ? z0.x : 0.0f, ci = ch0 == c ? z0.y : 0.0f;
-#pragma unroll 1
-				for (int t = 32 + lane; t < ntr; t += 32)      // only RACH has more than 32 training symbols
-					if (ft.t_chunk[sync_id][t] == c) {
-						const float2 z = sm.zbuf[t];
-						cr += z.x;
-						ci += z.y;
-					}
-				const float2 sum = warp_sum2(cr, ci, lane);
-				const float pos = rg.cpos[sync_id][c];
-				if (c > 0) {   // arg(corr[c] * conj(corr[c-1])) / (pos[c] - pos[c-1])
-					const float re = sum.x * prev_r + sum.y * prev_i, im = sum.y * prev_r - sum.x * prev_i;
-					f += fast_atan2f(im, re) / (pos - prev_pos);
+		if (nch > 1 && ntr <= 32) {
+			// all chunk sums at once: segmented shuffle reduction over the training symbols in lanes 0..ntr-1
+			// (a lane adds the value `o` lanes up while that lane is still inside its chunk); the sum of chunk c
+			// ends in the chunk's first lane
+			float2 v = z0;
+			const int end = lane < ntr ? (int)ft.t_end[sync_id][lane] : 0;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) {
+				const float ur = __shfl_down_sync(0xffffffffu, v.x, o), ui = __shfl_down_sync(0xffffffffu, v.y, o);
+				if (lane + o < end) {
+					v.x += ur;
+					v.y += ui;
 				}
-				prev_r = sum.x;
-				prev_i = sum.y;
-				prev_pos = pos;
 			}
+			// lane c < nch: chunk c and chunk c-1, arg(corr[c] * conj(corr[c-1])) / (pos[c] - pos[c-1]) - the
+			// nch-1 angles in parallel lanes
+			const int c = min(lane, nch - 1), src = ft.c_start[sync_id][c], srcp = ft.c_start[sync_id][max(c - 1, 0)];
+			const float sr = __shfl_sync(0xffffffffu, v.x, src), si = __shfl_sync(0xffffffffu, v.y, src);
+			const float qr = __shfl_sync(0xffffffffu, v.x, srcp), qi = __shfl_sync(0xffffffffu, v.y, srcp);
+			const float re = sr * qr + si * qi, im = si * qr - sr * qi;
+			const float part = fast_atan2f_inl(im, re) / (rg.cpos[sync_id][c] - rg.cpos[sync_id][max(c - 1, 0)]);
+			float f = 0.0f;
+#pragma unroll 1
+			for (int k = 1; k < nch; k++)
+				f += __shfl_sync(0xffffffffu, part, k);
 			ferr = f / (float)(nch - 1);
+		} else if (nch > 1) {
+			ferr = ferr_generic(ft, rg, sm.zbuf, sync_id, nch, ntr, z0, ch0, lane);
 		}
 		if (lane == 0 && a.freq_err) a.freq_err[b] = ferr;
 
