@@ -290,6 +290,18 @@ void gmr1b200_a5(int n, const uint8_t *key, uint32_t fn, int nbits, gmr1b200_ubi
 int gmr1b200_a5_batch(const int32_t *alg, int alg0, const uint8_t *key, const uint32_t *fn, int nbits, int stride,
                       gmr1b200_ubit_t *dl, gmr1b200_ubit_t *ul, int n, void *stream);
 
+/* ---- decode results as GSMTAP records -------------------------------------------
+ * replaces, for a whole batch on the device, gmr1_gsmtap_makemsg (src/gsmtap.c:44-71, gmr1/gsmtap.h): record i is
+ * the 16-byte gsmtap_hdr {version 2, hdr_len 4, type GSMTAP_TYPE_GMR1_UM, timeslot tn[i], arfcn 0, signal 0, snr 0,
+ * frame_number htonl(fn[i]), sub_type chan_type[i], antenna 0, sub_slot 0, res 0} followed by len bytes of
+ * l2 + i*l2_stride, written to out + i*out_stride (out_stride >= 16 + len; the out_stride - 16 - len bytes behind a record are
+ * unspecified afterwards).
+ * chan_type / fn / tn may be NULL: then chan_type0 / fn0 + i / tn0 are used.  Every pointer host or device memory;
+ * with device pointers the records of a batch leave the GPU in one copy. */
+int gmr1b200_gsmtap_batch(const uint8_t *chan_type, int chan_type0, const uint32_t *fn, uint32_t fn0,
+                          const uint8_t *tn, int tn0, const uint8_t *l2, int l2_stride, int len,
+                          uint8_t *out, int out_stride, int n, void *stream);
+
 /* ---- stage 1: FCCH chirp acquisition ----------------------------------------------------------
  * fcch_type: 0 = gmr1_fcch_burst (sweep 0.32, 117 symbols), 1 = gmr1_fcch3_lband_burst (0.32, 468),
  * 2 = gmr1_fcch3_sband_burst (0.16, 468)  (reference src/sdr/fcch.c:50-70, sdr/fcch.h:42-44).

@@ -515,3 +515,27 @@ void gmr1_a5(int n, uint8_t *key, uint32_t fn, int nbits, ubit_t *dl, ubit_t *ul
 	} else if (n == 1)
 		gmr1_a5_1(key, fn, nbits, dl, ul);
 }
+
+/* ---- GSMTAP record (src/gsmtap.c:44-71): gsmtap_hdr + L2 in a libosmocore msgb -------------------------
+ * header: version GSMTAP_VERSION, hdr_len in 32-bit words, type GSMTAP_TYPE_GMR1_UM, timeslot, frame number in
+ * network byte order, sub_type = channel type; arfcn / signal / snr / antenna / sub-slot stay 0 */
+#include <arpa/inet.h>
+#include <osmocom/core/msgb.h>
+#include <osmocom/core/gsmtap.h>
+
+struct msgb *gmr1_gsmtap_makemsg(uint8_t chan_type, uint32_t fn, uint8_t tn, const uint8_t *l2, int len)
+{
+	struct msgb *m = msgb_alloc(sizeof(struct gsmtap_hdr) + len, "gmr1_gsmtap_tx");
+	if (!m)
+		return NULL;
+	struct gsmtap_hdr *h = (struct gsmtap_hdr *)msgb_put(m, sizeof(*h));
+	memset(h, 0, sizeof(*h));
+	h->version = GSMTAP_VERSION;
+	h->hdr_len = sizeof(*h) / 4;
+	h->type = GSMTAP_TYPE_GMR1_UM;
+	h->timeslot = tn;
+	h->frame_number = htonl(fn);
+	h->sub_type = chan_type;
+	memcpy(msgb_put(m, len), l2, len);
+	return m;
+}

@@ -362,3 +362,28 @@ extern "C" int gmr1b200_a5_batch(const int32_t *alg, int alg0, const uint8_t *ke
 	}
 	return s.finish(e, "a5 kernel");
 }
+
+extern "C" int gmr1b200_gsmtap_batch(const uint8_t *chan_type, int chan_type0, const uint32_t *fn, uint32_t fn0,
+                                     const uint8_t *tn, int tn0, const uint8_t *l2, int l2_stride, int len,
+                                     uint8_t *out, int out_stride, int n, void *stream)
+{
+	if (n < 0 || len < 0 || l2_stride < len || out_stride < 16 + len || (n && (!out || (len && !l2))))
+		return set_err(-EINVAL, "gsmtap_batch: bad argument");
+	if (n == 0)
+		return 0;
+	Stage s(stream);
+	GsmtapArgs a = {};
+	a.chan_type = s.in(chan_type, (size_t)n); a.chan_type0 = (uint8_t)chan_type0;
+	a.fn = s.in(fn, (size_t)n); a.fn0 = fn0;
+	a.tn = s.in(tn, (size_t)n); a.tn0 = (uint8_t)tn0;
+	a.l2 = s.in(l2, (size_t)n * l2_stride);
+	a.l2_stride = l2_stride; a.len = len; a.n = n; a.out_stride = out_stride;
+	a.out = s.out(out, (size_t)n * out_stride);
+	cudaError_t e = cudaSuccess;
+	if (!s.failed()) {
+		e = launch_gsmtap(a, (cudaStream_t)stream);
+		if (e == cudaSuccess)
+			g_launches.fetch_add(1);
+	}
+	return s.finish(e, "gsmtap kernel");
+}

@@ -85,6 +85,19 @@ struct A5Args {
 };
 cudaError_t launch_a5(const A5Args &a, cudaStream_t st);
 
+// ---- GSMTAP records of decoded units
+struct GsmtapArgs {
+	const uint8_t  *chan_type;   // [n] GSMTAP_GMR1_* sub-type or NULL (then chan_type0)
+	const uint32_t *fn;          // [n] frame numbers or NULL (then fn0 + i)
+	const uint8_t  *tn;          // [n] timeslots or NULL (then tn0)
+	uint8_t         chan_type0, tn0;
+	uint32_t        fn0;
+	const uint8_t  *l2;          // [n][l2_stride]
+	int32_t         l2_stride, len, n, out_stride;
+	uint8_t        *out;         // [n][out_stride], out_stride >= 16 + len
+};
+cudaError_t launch_gsmtap(const GsmtapArgs &a, cudaStream_t st);
+
 // ---- workload synthesis
 struct SynthArgs {
 	const uint8_t *ebits;       // [n][ebits_stride] hard bits

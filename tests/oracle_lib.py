@@ -197,6 +197,16 @@ class Oracle:
         self.c.gmr1_a5(n, p(k), ctypes.c_uint32(fn), nbits, p(dl), p(ul) if both else None)
         return (dl, ul) if both else dl
 
+    def gsmtap(self, chan_type, fn, tn, l2):
+        """gmr1_gsmtap_makemsg (src/gsmtap.c:44) -> the bytes of the message"""
+        self.c.gmr1_gsmtap_makemsg.restype = ctypes.c_void_p
+        l2 = np.ascontiguousarray(l2, np.uint8)
+        m = self.c.gmr1_gsmtap_makemsg(ctypes.c_uint8(chan_type), ctypes.c_uint32(fn), ctypes.c_uint8(tn), p(l2), len(l2))
+        n = ctypes.c_uint16.from_address(m).value                  # struct msgb { uint16_t len, alloc; uint8_t data[]; }
+        out = np.ctypeslib.as_array((ctypes.c_uint8 * n).from_address(m + 4)).copy()
+        self.c.msgb_free(ctypes.c_void_p(m))
+        return out
+
 
 def load():
     ref = os.path.join(ROOT, "oracle", "_ref", "libgmr1_ref.so")

@@ -70,6 +70,8 @@ def test_batched_entry_points_reject_malformed_batches(gpu_lib):
     rejected("gmr1b200_bcch_decode_batch", l2, eb, None, None, -1, None)                                                              # negative n
     rejected("gmr1b200_fcch_rough_batch", 0, iq, n * wl, None, wl, 100, SPS, None, 0.0, np.zeros(n, np.int32), None, n, None)         # window < FCCH burst
     rejected("gmr1b200_fcch_rough_batch", 7, iq, n * wl, None, wl, wl, SPS, None, 0.0, np.zeros(n, np.int32), None, n, None)          # FCCH type
+    rejected("gmr1b200_gsmtap_batch", None, 1, None, 0, None, 0, l2, 24, 24, np.zeros((n, 39), np.uint8), 39, n, None)   # record stride < 16 + len
+    rejected("gmr1b200_gsmtap_batch", None, 1, None, 0, None, 0, l2, 20, 24, np.zeros((n, 40), np.uint8), 40, n, None)   # l2 stride < len
     rejected("gmr1b200_a5_batch", None, 1, np.zeros((n, 8), np.uint8), np.zeros(n, np.uint32), 208, 100, np.zeros((n, 208), np.uint8), None, n, None)  # stride < nbits
     rejected("gmr1b200_rx_bcch_batch", iq, n * wl, np.zeros(n, np.int64), np.full(n, wl, np.int32), np.zeros(n, np.int32), None, SPS, n, 0,
              np.zeros((n, 1), np.int32), np.zeros((n, 1), np.int32), np.zeros((n, 1), np.int32), np.zeros((n, 1), np.int32),
