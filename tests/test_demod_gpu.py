@@ -74,7 +74,10 @@ def compare(name, oracle, x, got, freq_shift=None):
 
 @pytest.mark.parametrize("name,win,sync_ids", [
     ("bcch", 80, 1), ("dc6", 40, 1), ("nt3_speech", 6, 1), ("nt3_facch", 6, 2), ("nt9", 6, 2),
-    ("rach", 6, 1), ("sdcch", 40, 4), ("dc2", 24, 1), ("nt6", 6, 2), ("dc12", 40, 1)])
+    ("rach", 6, 1), ("sdcch", 40, 4), ("dc2", 24, 1), ("nt6", 6, 2), ("dc12", 40, 1),
+    # search windows of 1, 2 and 3 rows of 32 offsets and beyond (the kernel is specialised on the row count,
+    # more than 96 offsets take the generic loop)
+    ("bcch", 30, 1), ("bcch", 62, 1), ("bcch", 95, 1), ("bcch", 130, 1), ("nt9", 100, 2)])
 def test_demod_parity(gpu_lib, oracle, name, win, sync_ids):
     rng = np.random.default_rng(100 + sigen.BT_ID[name])
     n = 70
@@ -95,6 +98,40 @@ def test_demod_device_pointers_and_freq_shift(gpu_lib, oracle):
     fsh = rng.uniform(-0.01, 0.01, 40).astype(np.float32)
     got = gpu_demod(gpu_lib, "bcch", x, freq_shift=fsh, device=True)
     compare("bcch", oracle, x, got, freq_shift=fsh)
+
+
+def test_demod_hot_path_layouts(gpu_lib, oracle):
+    """The same bursts through the kernel's usual path (no sync power requested, 16-byte aligned windows, even
+    soft-bit rows) and through its out-of-line variants (odd soft-bit row stride -> byte stores, windows at an odd
+    sample offset -> unaligned statistics loop + separate region copy, sync power requested) give the same soft bits."""
+    rng = np.random.default_rng(77)
+    n = 48
+    x, _, _ = gen("bcch", n, 80, rng)
+    ref = gpu_demod(gpu_lib, "bcch", x)                      # sync power requested (cold statistics variant)
+    compare("bcch", oracle, x, ref)
+    wl = x.shape[1]
+    iq = np.ascontiguousarray(x).view(np.float32)
+
+    def run(iq_buf, iq_len, ofs, stride, eb_stride):
+        eb = np.full((n, eb_stride), 99, np.int8)
+        sid = np.full(n, -9, np.int32)
+        toa = np.zeros(n, np.float32)
+        fe = np.zeros(n, np.float32)
+        gpu_lib.call("gmr1b200_pi4cxpsk_demod_batch", sigen.BT_ID["bcch"], iq_buf, iq_len, ofs, stride, wl, 4, None, 0.0,
+                     eb, eb_stride, sid, toa, fe, None, n, None)
+        return eb, sid, toa, fe
+
+    for eb_stride in (424, 425, 431):
+        eb, sid, toa, fe = run(iq, n * wl, None, wl, eb_stride)
+        assert (eb[:, :424] == ref[0]).all() and (sid == ref[1]).all()
+        assert np.abs(toa - ref[2]).max() < 1e-6 and np.abs(fe - ref[3]).max() < 1e-7
+    # windows at odd sample offsets (8-byte but not 16-byte aligned)
+    pad = np.zeros((n, 2 * (wl + 1)), np.float32)
+    pad[:, 2:] = iq.reshape(n, 2 * wl)
+    ofs = (np.arange(n, dtype=np.int64) * (wl + 1) + 1)
+    eb, sid, toa, fe = run(pad, n * (wl + 1), ofs, 0, 424)
+    d = np.abs(eb.astype(int) - ref[0].astype(int))
+    assert (sid == ref[1]).all() and np.abs(toa - ref[2]).max() <= 0.004 and d.max() <= 1 and (d == 0).mean() > 0.999
 
 
 @pytest.mark.parametrize("name,chan,win", [("bcch", "bcch", 80), ("dc6", "ccch", 40)])
