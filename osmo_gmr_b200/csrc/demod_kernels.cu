@@ -34,6 +34,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <type_traits>
 
 #include "gmr1_tables.h"
 #include "launch.h"
@@ -872,7 +873,7 @@ __device__ __noinline__ float ferr_generic(const FlatTab &ft, const Regions &rg,
 // mode 0: demod (bts[0] only).  mode 1: detect among n_bt burst types (pi4cxpsk.c:617-682).
 // NB = bits per symbol of bts[0] (compile time: the soft-bit mapping is straight-line code).
 // Persistent: each warp strides over the bursts of the batch.
-template <int MODE, int SPS, int NB, int ROWS>
+template <int MODE, int SPS, int NB, int ROWS, int SYMB = DM_SYM_BATCH>
 __global__ void __launch_bounds__(DM_WARPS * 32, DM_MIN_CTAS)
 demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int warp_bytes,
              const __grid_constant__ Regions rg)
@@ -1142,18 +1143,20 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 			const int dc = min(max(d, ft.d_lo), ft.d_hi);        // no data symbol leaves the window (never binds for the standard formats)
 			const float2 *xd = x + dc;
 			const bool fast_store = NB == 1 || eb_even;
+			auto data_pass = [&](auto bsel) {
+			constexpr int B = decltype(bsel)::value;
 #pragma unroll 1
-			for (int t0 = lane; t0 < nds; t0 += 32 * DM_SYM_BATCH) {
-				int ii[DM_SYM_BATCH];
-				float2 v[DM_SYM_BATCH];
+			for (int t0 = lane; t0 < nds; t0 += 32 * B) {
+				int ii[B];
+				float2 v[B];
 #pragma unroll
-				for (int u = 0; u < DM_SYM_BATCH; u++) {
+				for (int u = 0; u < B; u++) {
 					ii[u] = ft.d_pos[min(t0 + 32 * u, nds - 1)];
 					v[u] = __ldg(&xd[ii[u] * sps]);
 				}
-				unsigned sw[DM_SYM_BATCH];
+				unsigned sw[B];
 #pragma unroll
-				for (int u = 0; u < DM_SYM_BATCH; u++) {
+				for (int u = 0; u < B; u++) {
 					const float th = fast_atan2f_inl(v[u].y - nm.ai, v[u].x - nm.ar);
 					const float a1 = fs * (float)(ii[u] * sps + dc);
 					const float k = rintf(a1 * INV_2PI);
@@ -1169,7 +1172,7 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 				}
 				if (fast_store) {
 #pragma unroll
-					for (int u = 0; u < DM_SYM_BATCH; u++)
+					for (int u = 0; u < B; u++)
 						if (t0 + 32 * u < nds) {
 							if (NB == 2)
 								reinterpret_cast<uint16_t *>(eb)[t0 + 32 * u] = (uint16_t)sw[u];
@@ -1178,10 +1181,10 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 						}
 				} else {
 #pragma unroll 1
-					for (int u = 0; u < DM_SYM_BATCH; u++) {     // odd output address: byte stores (cold)
+					for (int u = 0; u < B; u++) {     // odd output address: byte stores (cold)
 						unsigned val = sw[0];
 #pragma unroll
-						for (int k = 1; k < DM_SYM_BATCH; k++)
+						for (int k = 1; k < B; k++)
 							val = u == k ? sw[k] : val;
 						if (t0 + 32 * u < nds) {
 							eb[2 * (t0 + 32 * u)] = (int8_t)(val & 0xff);
@@ -1190,6 +1193,11 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 					}
 				}
 			}
+			};
+			// SYMB (template parameter, chosen by the launcher): formats with 7 rows of 32 data symbols (BCCH, DC6,
+			// NT6, SDCCH; DC12 has 14) go in batches of 7, everything else in batches of DM_SYM_BATCH - whichever
+			// leaves fewer empty rows.  One batch size per kernel: two copies of the pass do not fit the hot path.
+			data_pass(std::integral_constant<int, SYMB>());
 		}
 	}
 }
@@ -1293,6 +1301,10 @@ cudaError_t launch_demod(const DemodArgs &a, const BurstTab *d_bts, const BurstT
 		                     (const void *)demod_kernel<0, 4, 1, 1>, (const void *)demod_kernel<0, 4, 2, 1>,
 		                     (const void *)demod_kernel<0, 4, 1, 2>, (const void *)demod_kernel<0, 4, 2, 2>,
 		                     (const void *)demod_kernel<0, 4, 1, 3>, (const void *)demod_kernel<0, 4, 2, 3>,
+		                     (const void *)demod_kernel<0, 4, 1, 0, 7>, (const void *)demod_kernel<0, 4, 2, 0, 7>,
+		                     (const void *)demod_kernel<0, 4, 1, 1, 7>, (const void *)demod_kernel<0, 4, 2, 1, 7>,
+		                     (const void *)demod_kernel<0, 4, 1, 2, 7>, (const void *)demod_kernel<0, 4, 2, 2, 7>,
+		                     (const void *)demod_kernel<0, 4, 1, 3, 7>, (const void *)demod_kernel<0, 4, 2, 3, 7>,
 		                     (const void *)demod_kernel<0, 0, 1, 0>, (const void *)demod_kernel<0, 0, 2, 0>,
 		                     (const void *)demod_kernel<0, -1, 1, 0>, (const void *)demod_kernel<0, -1, 2, 0>,
 		                     (const void *)demod_kernel<1, 4, 2, 0>, (const void *)demod_kernel<1, 0, 2, 0>};
@@ -1326,7 +1338,21 @@ cudaError_t launch_demod(const DemodArgs &a, const BurstTab *d_bts, const BurstT
 	if (nb != 1 && nb != 2)
 		return cudaErrorInvalidValue;
 #define DM_LAUNCH(M, S, B, R) demod_kernel<M, S, B, R><<<grid, DM_WARPS * 32, smem, st>>>(a, d_bts, n_bt, (int)wb, rg)
-#define DM_LAUNCH_NB(M, S, R) do { if (nb == 1) DM_LAUNCH(M, S, 1, R); else DM_LAUNCH(M, S, 2, R); } while (0)
+#define DM_LAUNCH7(M, S, B, R) demod_kernel<M, S, B, R, 7><<<grid, DM_WARPS * 32, smem, st>>>(a, d_bts, n_bt, (int)wb, rg)
+#define DM_LAUNCH_NB(M, S, R) do { \
+		if (S == 4 && batch7) { if (nb == 1) DM_LAUNCH7(M, S, 1, R); else DM_LAUNCH7(M, S, 2, R); } \
+		else { if (nb == 1) DM_LAUNCH(M, S, 1, R); else DM_LAUNCH(M, S, 2, R); } \
+	} while (0)
+	// data symbols per lane and pass: batches of 7 when that leaves fewer empty rows of 32 symbols than batches of 4
+	bool batch7;
+	{
+		int nds = 0;
+		for (int c = 0; c < h_bts[0].n_data; c++)
+			nds += h_bts[0].d_len[c];
+		const int rows = (nds + 31) / 32;
+		const int waste7 = (7 - rows % 7) % 7, waste4 = (DM_SYM_BATCH - rows % DM_SYM_BATCH) % DM_SYM_BATCH;
+		batch7 = rows >= 7 && waste7 <= waste4;
+	}
 	if (mode == 0 && a.sps < 4) {
 		DM_LAUNCH_NB(0, -1, 0);
 	} else if (mode == 0 && a.sps == 4) {
@@ -1342,6 +1368,7 @@ cudaError_t launch_demod(const DemodArgs &a, const BurstTab *d_bts, const BurstT
 	else
 		DM_LAUNCH(1, 0, 2, 0);
 #undef DM_LAUNCH_NB
+#undef DM_LAUNCH7
 #undef DM_LAUNCH
 	return cudaGetLastError();
 }
