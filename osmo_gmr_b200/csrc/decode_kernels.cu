@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(DC12_WARPS * 32) decode_dc12_kernel(const Deco
 				st = (st >> 1) | (bit << 7);
 			}
 		if (a.crc)
-			a.crc[unit] = crc_check_packed(s.out, 0, 192, 0x1021, 16);
+			a.crc[unit] = crc16_check_packed(s.out, 192);
 		for (int i = 0; i < 24; i++)
 			a.l2[(size_t)unit * 24 + i] = s.out[i];
 	}

@@ -208,7 +208,7 @@ GMR1_HD void decode_unit_k5(const TabRef &tb, const DecodeArgs &a, int unit,
 		                       CH == CH_TCH9_2K4 ? 144 : CH == CH_TCH9_4K8 ? 240 :
 		                       CH == CH_TCH9_9K6 ? 480 : 192;
 		if (!T9) {
-			const int c = crc_check_packed(out, 0, n_data, 0x1021, 16);
+			const int c = crc16_check_packed(out, n_data);
 			if (a.crc)
 				a.crc[unit] = c;
 		}

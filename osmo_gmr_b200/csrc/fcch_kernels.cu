@@ -85,6 +85,19 @@ __global__ void __launch_bounds__(FR_T, 2) fcch_rough_kernel(const FcchArgs a)
 	const float2 *x = a.iq + (a.ofs ? a.ofs[b] : (int64_t)b * a.stride);
 	const float freq_shift = a.freq_shift ? a.freq_shift[b] : a.freq_shift0;
 
+#ifndef FR_PREFETCH
+#define FR_PREFETCH 1
+#endif
+#if FR_PREFETCH
+	// the whole search window (247 KB at sps 4) requested into L2 up front, 16 KB per bulk prefetch: the statistics
+	// pass below has 64 bytes per thread in flight and would otherwise run at DRAM latency
+	if ((((uintptr_t)x) & 15) == 0) {
+		const int chunk = 16384, bytes = (L * 8) & ~15;
+		for (int o = tid * chunk; o < bytes; o += FR_T * chunk)
+			asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((const char *)x + o), "r"(min(chunk, bytes - o))
+			             : "memory");
+	}
+#endif
 	// dual-chirp reference at 1 sample/symbol (fcch.c:167-193)
 	{
 		const float phase_base = a.freq * 2.0f * PI_F / (float)len, halfpos = (float)len / 2.0f;

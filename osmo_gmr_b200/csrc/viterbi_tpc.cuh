@@ -253,4 +253,71 @@ GMR1_HD int crc_check_packed(const uint8_t *p, int bit0, int n_data, unsigned po
 	return bad;
 }
 
+
+// ---- CRC16 (poly 0x1021, init 0) a byte at a time -------------------------------------------------------
+// Same register as the bit-serial loop above after every 8 bits: crc' = (crc << 8) ^ T[(crc >> 8) ^ b] with b = the
+// next 8 stream bits, first bit in the MSB.  The stream is LSB-first inside the packed bytes, hence the bit reversal.
+// 192 data bits cost 24 table steps instead of 192 bit steps (the check was 5 % of the BCCH decode kernel).
+struct Crc16Tab {
+	uint16_t v[256];
+	constexpr Crc16Tab() : v()
+	{
+		for (int i = 0; i < 256; i++) {
+			unsigned c = (unsigned)i << 8;
+			for (int k = 0; k < 8; k++)
+				c = (c & 0x8000u) ? ((c << 1) ^ 0x1021u) : (c << 1);
+			v[i] = (uint16_t)c;
+		}
+	}
+};
+#ifdef __CUDACC__
+static __device__ const Crc16Tab d_crc16_tab = Crc16Tab();      // global memory: per-lane indices (a __constant__ table would serialise)
+#endif
+static constexpr Crc16Tab h_crc16_tab = Crc16Tab();
+
+GMR1_HD unsigned crc16_tab(unsigned i)
+{
+#ifdef __CUDA_ARCH__
+	return __ldg(&d_crc16_tab.v[i]);
+#else
+	return h_crc16_tab.v[i];
+#endif
+}
+
+GMR1_HD unsigned rev8(unsigned b)
+{
+#ifdef __CUDA_ARCH__
+	return __brev(b) >> 24;
+#else
+	b = ((b & 0xf0u) >> 4) | ((b & 0x0fu) << 4);
+	b = ((b & 0xccu) >> 2) | ((b & 0x33u) << 2);
+	return ((b & 0xaau) >> 1) | ((b & 0x55u) << 1);
+#endif
+}
+
+// crc_check_packed(p, 0, n_data, 0x1021, 16) for data that starts on a byte boundary
+GMR1_HD int crc16_check_packed(const uint8_t *p, int n_data)
+{
+	unsigned crc = 0;
+	const int nb = n_data >> 3;
+	for (int i = 0; i < nb; i++)
+		crc = ((crc << 8) ^ crc16_tab(((crc >> 8) ^ rev8(p[i])) & 0xffu)) & 0xffffu;
+	for (int q = 8 * nb; q < n_data; q++) {                     // ragged tail, bit by bit
+		const unsigned b = (p[q >> 3] >> (q & 7)) & 1u;
+		crc ^= b << 15;
+		crc = ((crc & 0x8000u) ? ((crc << 1) ^ 0x1021u) : (crc << 1)) & 0xffffu;
+	}
+	// the 16 bits that follow the data, first one against the MSB of the register
+	unsigned rx = 0;
+	if ((n_data & 7) == 0) {
+		rx = (rev8(p[nb]) << 8) | rev8(p[nb + 1]);
+	} else {
+		for (int i = 0; i < 16; i++) {
+			const int q = n_data + i;
+			rx |= ((p[q >> 3] >> (q & 7)) & 1u) << (15 - i);
+		}
+	}
+	return rx != crc;
+}
+
 }  // namespace gmr1
