@@ -1013,6 +1013,7 @@ demod_kernel(const DemodArgs a, const BurstTab *__restrict__ bts, int n_bt, int 
 		const int nch = rg.n_chunk[0][sync_id], ntr = ft.n_train[sync_id];
 		float2 z0 = make_float2(0.0f, 0.0f);     // training symbol `lane` (round 0) stays in registers
 		int ch0 = -1;
+		__syncwarp();        // zbuf doubles as the peak search's window buffer (last read there: the peak value)
 #pragma unroll 1
 		for (int t0 = 0; t0 < ntr; t0 += 32) {
 			const int t = t0 + lane;
