@@ -133,11 +133,13 @@ GMR1_HD void decode_unit_k5(const TabRef &tb, const DecodeArgs &a, int unit,
 	for (int s = 0; s < C::NS; s++)
 		ae[s] = s ? MAX_AE : 0u;
 
-	forward<C, false, true, CH == CH_RACH>(ae, row, tb.g, tb.g2, 0, tb.len, dec, T, t);
-	forward<C, true,  true, CH == CH_RACH>(ae, row, tb.g, tb.g2, tb.len, C::K - 1, dec, T, t);
+	// path metrics relative to the all-zero branch of every step (acs_step REL): `off` is what they lack
+	uint32_t off = 0;
+	forward<C, false, true, CH == CH_RACH, true>(ae, row, tb.g, tb.g2, 0, tb.len, dec, T, t, off);
+	forward<C, true,  true, CH == CH_RACH, true>(ae, row, tb.g, tb.g2, tb.len, C::K - 1, dec, T, t, off);
 
 	if (a.conv)
-		a.conv[unit] = (int32_t)ae[0];
+		a.conv[unit] = (int32_t)(ae[0] + off);
 
 	// traceback into LSB-first packed bytes, reusing the (now dead) staged row.  Flush steps first
 	// (no output), then the data steps in groups of 8 = one output byte each.
@@ -237,7 +239,8 @@ GMR1_HD void decode_unit_tch3(const TabRef &tb, const DecodeArgs &a, int unit,
 		for (int s = 0; s < C::NS; s++)
 			ae[s] = s ? MAX_AE : 0u;
 		// seeding pass, no history kept
-		forward<C, false, false, false>(ae, row, g, nullptr, 0, 48, dec, T, t);
+		uint32_t unused = 0;
+		forward<C, false, false, false>(ae, row, g, nullptr, 0, 48, dec, T, t, unused);
 		uint32_t mn = MAX_AE;
 #pragma unroll
 		for (int s = 0; s < C::NS; s++)
@@ -245,7 +248,7 @@ GMR1_HD void decode_unit_tch3(const TabRef &tb, const DecodeArgs &a, int unit,
 #pragma unroll
 		for (int s = 0; s < C::NS; s++)
 			ae[s] -= mn;
-		forward<C, false, true, false>(ae, row, g, nullptr, 0, 48, dec, T, t);
+		forward<C, false, true, false>(ae, row, g, nullptr, 0, 48, dec, T, t, unused);
 		// end state: first state with the minimal metric
 		uint32_t best = MAX_AE;
 		unsigned end = 0xff;

@@ -91,9 +91,16 @@ GMR1_HD uint32_t funnel_l1(uint32_t lo, uint32_t hi)
 
 // One trellis step from `ae` into `nae` (callers ping-pong the two arrays so that no register
 // copies are needed).  DW = number of 32-bit decision words per step (NS/32 rounded up).
-template <class C, bool FLUSH_STEP>
+//
+// REL: branch metrics relative to the all-zero branch.  Every path takes exactly one branch per step, so taking
+// the same amount (the metric of output 0...0, sum of m0[j]) off all 2^N branch sums of a step changes no
+// decision; the path metrics then run `off` below their reference values (off = running sum of what was taken
+// off, handed back to the caller for conv_rv and the MAX_AE sentinel of the flush steps).  bm[0] becomes the
+// constant 0: the 2^(K-1-... ) transitions with an all-zero output need no add, and the branch sums need N - 1 adds
+// less.  Relative metrics can be negative: comparisons are signed (|values| < 2^25).
+template <class C, bool FLUSH_STEP, bool REL = false>
 GMR1_HD void acs_step(const uint32_t (&ae)[C::NS], uint32_t (&nae)[C::NS], const int (&v)[C::N],
-                      uint32_t (&dec)[(C::NS + 31) / 32])
+                      uint32_t (&dec)[(C::NS + 31) / 32], uint32_t &off)
 {
 	constexpr int N = C::N, NS = C::NS, H = NS / 2;
 	uint32_t m0[N], m1[N];
@@ -103,13 +110,27 @@ GMR1_HD void acs_step(const uint32_t (&ae)[C::NS], uint32_t (&nae)[C::NS], const
 	// all 2^N branch sums, built by doubling (entries that no transition uses are dead code)
 	uint32_t bm[1 << N];
 	bm[0] = 0;
+	if (REL) {
 #pragma unroll
-	for (int j = 0; j < N; j++) {
+		for (int j = 0; j < N; j++) {
+			const uint32_t dj = m1[j] - m0[j];
+			off += m0[j];
 #pragma unroll
-		for (int o = (1 << j) - 1; o >= 0; o--) {
-			uint32_t base = bm[o];
-			bm[2 * o + 1] = base + m1[j];
-			bm[2 * o]     = base + m0[j];
+			for (int o = (1 << j) - 1; o >= 0; o--) {
+				const uint32_t base = bm[o];
+				bm[2 * o + 1] = base + dj;
+				bm[2 * o]     = base;
+			}
+		}
+	} else {
+#pragma unroll
+		for (int j = 0; j < N; j++) {
+#pragma unroll
+			for (int o = (1 << j) - 1; o >= 0; o--) {
+				uint32_t base = bm[o];
+				bm[2 * o + 1] = base + m1[j];
+				bm[2 * o]     = base + m0[j];
+			}
 		}
 	}
 	if (FLUSH_STEP) {
@@ -120,10 +141,10 @@ GMR1_HD void acs_step(const uint32_t (&ae)[C::NS], uint32_t (&nae)[C::NS], const
 #pragma unroll
 		for (int k = 0; k < H; k++) {
 			const uint32_t a = ae[k] + bm[C::out(k, 0)], b = ae[k + H] + bm[C::out(k + H, 0)];
-			const bool d = b < a;
+			const bool d = REL ? (int32_t)(b - a) < 0 : b < a;
 			nae[2 * k] = d ? b : a;
 			dec[(2 * k) >> 5] |= d ? (1u << ((2 * k) & 31)) : 0u;
-			nae[2 * k + 1] = MAX_AE;
+			nae[2 * k + 1] = REL ? MAX_AE - off : MAX_AE;
 		}
 	} else {
 		// States from the highest down: the decision "b < a" is the sign of b - a (both below 2^25), shifted
@@ -138,8 +159,11 @@ GMR1_HD void acs_step(const uint32_t (&ae)[C::NS], uint32_t (&nae)[C::NS], const
 			for (int q = PER - 1; q >= 0; q--) {
 				const int s = w * PER + q, k = s >> 1, bit = s & 1;
 				const uint32_t a = ae[k] + bm[C::out(k, bit)], b = ae[k + H] + bm[C::out(k + H, bit)];
-				nae[s] = b < a ? b : a;
 				const uint32_t diff = b - a;                       // negative <=> b < a (strict: ties keep a)
+				if (REL)
+					nae[s] = (uint32_t)((int32_t)b < (int32_t)a ? (int32_t)b : (int32_t)a);
+				else
+					nae[s] = b < a ? b : a;
 				if (q >= PER / 2)
 					acc_hi = funnel_l1(diff, acc_hi);
 				else
@@ -183,9 +207,9 @@ GMR1_HD void store_dec(const uint32_t (&dec)[(C::NS + 31) / 32], typename DecWor
 	}
 }
 
-template <class C, bool FLUSH_STEP, bool STORE, bool HAS_G2>
+template <class C, bool FLUSH_STEP, bool STORE, bool HAS_G2, bool REL = false>
 GMR1_HD void forward(uint32_t (&ae)[C::NS], const int8_t *row, const uint16_t *g, const uint16_t *g2,
-                     int step0, int nsteps, typename DecWord<C::NS>::type *dec_base, int T, int t)
+                     int step0, int nsteps, typename DecWord<C::NS>::type *dec_base, int T, int t, uint32_t &off)
 {
 	constexpr int DW = (C::NS + 31) / 32;
 	uint32_t tmp[C::NS];
@@ -195,17 +219,17 @@ GMR1_HD void forward(uint32_t (&ae)[C::NS], const int8_t *row, const uint16_t *g
 		int v[C::N];
 		uint32_t dec[DW];
 		fetch_inputs<C, HAS_G2>(v, row, g, g2, i);
-		acs_step<C, FLUSH_STEP>(ae, tmp, v, dec);
+		acs_step<C, FLUSH_STEP, REL>(ae, tmp, v, dec, off);
 		store_dec<C, STORE>(dec, dec_base, T, t, i);
 		fetch_inputs<C, HAS_G2>(v, row, g, g2, i + 1);
-		acs_step<C, FLUSH_STEP>(tmp, ae, v, dec);
+		acs_step<C, FLUSH_STEP, REL>(tmp, ae, v, dec, off);
 		store_dec<C, STORE>(dec, dec_base, T, t, i + 1);
 	}
 	if (i < end) {
 		int v[C::N];
 		uint32_t dec[DW];
 		fetch_inputs<C, HAS_G2>(v, row, g, g2, i);
-		acs_step<C, FLUSH_STEP>(ae, tmp, v, dec);
+		acs_step<C, FLUSH_STEP, REL>(ae, tmp, v, dec, off);
 		store_dec<C, STORE>(dec, dec_base, T, t, i);
 #pragma unroll
 		for (int s = 0; s < C::NS; s++)
