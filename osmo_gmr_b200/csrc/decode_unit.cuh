@@ -239,28 +239,33 @@ GMR1_HD void decode_unit_tch3(const TabRef &tb, const DecodeArgs &a, int unit,
 		for (int s = 0; s < C::NS; s++)
 			ae[s] = s ? MAX_AE : 0u;
 		// seeding pass, no history kept
-		uint32_t unused = 0;
-		forward<C, false, false, false>(ae, row, g, nullptr, 0, 48, dec, T, t, unused);
-		uint32_t mn = MAX_AE;
+		// Path metrics relative to the all-zero branch of every step (acs_step REL, signed comparisons): the
+		// offset of the seeding pass drops out in the normalisation, the one of the second pass goes back into
+		// the reported metric.  (After the normalisation the smallest metric is 0 < MAX_AE, so an end state always
+		// exists: the reference's "no state" return cannot occur here.)
+		uint32_t off = 0;
+		forward<C, false, false, false, true>(ae, row, g, nullptr, 0, 48, dec, T, t, off);
+		int32_t mn = (int32_t)ae[0];
+#pragma unroll
+		for (int s = 1; s < C::NS; s++)
+			mn = (int32_t)ae[s] < mn ? (int32_t)ae[s] : mn;
 #pragma unroll
 		for (int s = 0; s < C::NS; s++)
-			mn = ae[s] < mn ? ae[s] : mn;
-#pragma unroll
-		for (int s = 0; s < C::NS; s++)
-			ae[s] -= mn;
-		forward<C, false, true, false>(ae, row, g, nullptr, 0, 48, dec, T, t, unused);
+			ae[s] -= (uint32_t)mn;
+		off = 0;
+		forward<C, false, true, false, true>(ae, row, g, nullptr, 0, 48, dec, T, t, off);
 		// end state: first state with the minimal metric
-		uint32_t best = MAX_AE;
-		unsigned end = 0xff;
+		int32_t best = (int32_t)ae[0];
+		unsigned end = 0;
 #pragma unroll
-		for (int s = 0; s < C::NS; s++)
-			if (ae[s] < best) {
-				best = ae[s];
+		for (int s = 1; s < C::NS; s++)
+			if ((int32_t)ae[s] < best) {
+				best = (int32_t)ae[s];
 				end = (unsigned)s;
 			}
 		int32_t *cv = f ? a.conv1 : a.conv;
 		if (cv)
-			cv[unit] = end == 0xff ? -1 : (int32_t)best;
+			cv[unit] = best + (int32_t)off;
 
 		// frame bits 0..47 from the decoder, 48..79 = sign of c[72..103]; MSB-first packing
 		uint32_t w0 = 0, w1 = 0, w2 = 0;        // bits 0..31, 32..63, 64..79
