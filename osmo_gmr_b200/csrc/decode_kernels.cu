@@ -130,7 +130,59 @@ __global__ void __launch_bounds__(TPC_T) decode_tpc_kernel(const DecodeArgs a)
 		}
 		__syncthreads();
 		mbar_wait(bar, 0);
+	} else if (chan_is_t9(CH) && !a.t9_rows) {
+		// TCH9 gathers three bursts per codeword through two index arrays: the predecessors of the tile's units
+		// go to shared memory first, so that an element costs one dependent global load instead of two, and
+		// four elements per thread are in flight (this staging, not the Viterbi, bounded the kernel: 8 resident
+		// warps per SM and a chain of three dependent loads per byte)
+		__shared__ int s_prev[2][TPC_T];
+		__shared__ uint16_t s_src[648];
+		s_prev[0][tid] = (tid < cnt && a.prev1) ? a.prev1[base + tid] : -1;
+		s_prev[1][tid] = (tid < cnt && a.prev2) ? a.prev2[base + tid] : -1;
+		for (int r = tid; r < 648; r += TPC_T)
+			s_src[r] = tb.t9_src[r];
+		__syncthreads();
+		// eight elements per thread and pass: source addresses first (shared-memory lookups only), then the eight
+		// byte loads back to back (clamped, so that they are unconditional), then the stores
+		constexpr int E = 8;
+		for (int idx0 = tid; idx0 < TPC_T * NROW; idx0 += TPC_T * E) {
+			const int8_t *src[E];
+			const uint8_t *csrc[E];
+			bool ok[E], flip[E];
+#pragma unroll
+			for (int e = 0; e < E; e++) {
+				const int idx = min(idx0 + e * TPC_T, TPC_T * NROW - 1);
+				const int tt = idx / NROW, r = idx - tt * NROW;
+				const uint16_t w = s_src[r];
+				const int age = (w >> 10) & 3, sidx = w & G_IDX;
+				const int u = age == 0 ? base + tt : s_prev[age - 1][tt];
+				ok[e] = tt < cnt && u >= 0;
+				flip[e] = (w & G_FLIP) != 0;
+				const size_t uu = (size_t)max(u, 0);
+				src[e] = a.ebits + uu * NIN + sidx;
+				csrc[e] = a.ciph ? a.ciph + uu * tb.n_ciph + tb.cmap[sidx] : nullptr;
+			}
+			int v[E];
+			unsigned c[E];
+#pragma unroll
+			for (int e = 0; e < E; e++) {
+				v[e] = *src[e];
+				c[e] = csrc[e] ? *csrc[e] : 0u;
+			}
+#pragma unroll
+			for (int e = 0; e < E; e++) {
+				int x = v[e];
+				if (c[e])
+					x = sbit_neg(x);
+				if (flip[e])
+					x = sbit_neg(x);
+				if (idx0 + e * TPC_T < TPC_T * NROW)
+					rows[idx0 + e * TPC_T] = ok[e] ? (int8_t)x : (int8_t)0;
+			}
+		}
+		__syncthreads();
 	} else {
+#pragma unroll 4
 		for (int idx = tid; idx < TPC_T * NROW; idx += TPC_T) {
 			const int tt = idx / NROW, r = idx - tt * NROW;
 			rows[idx] = (tt < cnt) ? stage_elem<CH>(tb, a, base + tt, r) : (int8_t)0;

@@ -66,6 +66,25 @@ GMR1_HD constexpr int chan_l2_bytes(int ch)
 // Default channels: the row is the ebits row with the cipher sign already applied
 // (reference: "if (ciph[i]) bits[i] *= -1", e.g. facch9.c:121-125).
 // TCH9: the row is the inter-burst-deinterleaved, descrambled vector (tch9.c:163-166).
+
+// TCH9, element r of the staged row of `unit`: p1 / p2 = index of the burst received one / two bursts earlier on
+// the same channel (-1: none), already looked up by the caller (the kernel keeps them in shared memory so that an
+// element costs one dependent global load, not two)
+GMR1_HD int8_t stage_elem_t9(const TabRef &tb, const DecodeArgs &a, int unit, int p1, int p2, int r)
+{
+	const uint16_t w = tb.t9_src[r];
+	const int age = (w >> 10) & 3, s = w & G_IDX;
+	const int u = age == 0 ? unit : (age == 1 ? p1 : p2);
+	if (u < 0)
+		return 0;
+	int v = a.ebits[(size_t)u * tb.n_in + s];
+	if (a.ciph && a.ciph[(size_t)u * tb.n_ciph + tb.cmap[s]])
+		v = sbit_neg(v);
+	if (w & G_FLIP)
+		v = sbit_neg(v);
+	return (int8_t)v;
+}
+
 template <int CH>
 GMR1_HD int8_t stage_elem(const TabRef &tb, const DecodeArgs &a, int unit, int r)
 {
@@ -73,19 +92,7 @@ GMR1_HD int8_t stage_elem(const TabRef &tb, const DecodeArgs &a, int unit, int r
 	if (T9 && a.t9_rows) {
 		return a.ebits[(size_t)unit * 648 + r];
 	} else if (T9) {
-		const uint16_t w = tb.t9_src[r];
-		const int age = (w >> 10) & 3, s = w & G_IDX;
-		int u = unit;
-		if (age == 1) u = a.prev1 ? a.prev1[unit] : -1;
-		if (age == 2) u = a.prev2 ? a.prev2[unit] : -1;
-		if (u < 0)
-			return 0;
-		int v = a.ebits[(size_t)u * tb.n_in + s];
-		if (a.ciph && a.ciph[(size_t)u * tb.n_ciph + tb.cmap[s]])
-			v = sbit_neg(v);
-		if (w & G_FLIP)
-			v = sbit_neg(v);
-		return (int8_t)v;
+		return stage_elem_t9(tb, a, unit, a.prev1 ? a.prev1[unit] : -1, a.prev2 ? a.prev2[unit] : -1, r);
 	} else {
 		int v = a.ebits[(size_t)unit * tb.n_in + r];
 		if (a.ciph) {
