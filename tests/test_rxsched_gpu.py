@@ -127,3 +127,18 @@ def test_rx_bcch_batch_vs_gmr1_rx(gpu_lib, oracle, tmp_path):
                 n_ok += e["crc"] == 0
     assert n_burst >= 200 and n_ok >= 0.8 * n_burst
     assert any(r["frames"][0]["fn"] != r["frames"][-1]["fn"] - len(r["frames"]) + 1 for r in ref)   # an SI1 re-timed a channel
+
+    # the same walk on a caller-owned stream with device-resident buffers: identical results
+    import torch
+    dev = torch.device("cuda", 0)
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        t_in = [d(iq), d(t_ofs), d(t_len), d(align0), d(ferr0)]
+        outs = [torch.zeros_like(d(a)) for a in (kind, fn, crc, conv, l2, nfr, align1, ferr1)]
+        gpu_lib.call("gmr1b200_rx_bcch_batch", t_in[0], len(iq) // 2, t_in[1], t_in[2], t_in[3], t_in[4], SPS, n, F,
+                     *outs, st.cuda_stream)
+    st.synchronize()
+    for got, want in zip(outs, (kind, fn, crc, conv, l2, nfr, align1, ferr1)):
+        assert (got.cpu().numpy() == want).all()
+
