@@ -271,7 +271,8 @@ int gmr1b200_rx_xcch_batch(int chan, const float *iq, int64_t iq_len, const int6
  * Outputs, [n][max_frames] each (l2: [n][max_frames][24]): kind (0 nothing, 1 BCCH, 2 CCCH), fn (frame number
  * the channel believed in), crc (0 ok, -1 where kind = 0), conv (Viterbi metric), l2; n_frames [n] frames
  * walked; align_out / freq_err_out [n] final tracking state (may be NULL).  Frames beyond max_frames are not
- * walked.  Every pointer host or device memory. */
+ * walked.  kind and crc are set for every frame slot; fn is written for the n_frames[i] walked frames of channel i,
+ * conv and l2 where kind != 0 - the other slots of fn / conv / l2 are unspecified.  Every pointer host or device memory. */
 int gmr1b200_rx_bcch_batch(const float *iq, int64_t iq_len, const int64_t *rec_ofs, const int32_t *rec_len,
                            const int32_t *align0, const float *freq_err0, int sps, int n, int max_frames,
                            int32_t *kind, int32_t *fn, int32_t *crc, int32_t *conv, uint8_t *l2,
