@@ -206,8 +206,35 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_evt = index, [], threading.Event()
+        # NVML in-process when the bindings are there (a sample per 2 ms: the timed region is tens of ms long),
+        # else one nvidia-smi call per sample (~50 ms each).  Initialised here, before the timed region starts.
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[index]) if vis and vis.split(",")[index].strip().isdigit() else index
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = [pynvml.nvmlClocksEventReasonHwSlowdown, pynvml.nvmlClocksEventReasonHwThermalSlowdown,
+                    pynvml.nvmlClocksEventReasonSwThermalSlowdown, pynvml.nvmlClocksEventReasonSwPowerCap]
+            self.nvml = (pynvml, h, pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM), get_reasons, bits)
+        except Exception:
+            self.nvml = None
 
     def run(self):
+        if self.nvml:
+            pynvml, h, mx, get_reasons, bits = self.nvml
+            try:
+                while not self.stop_evt.is_set():
+                    r = get_reasons(h)
+                    self.samples.append([str(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), str(mx)] +
+                                        ["Active" if r & b else "Not Active" for b in bits])
+                    self.stop_evt.wait(0.002)
+                return
+            except Exception:
+                pass
         while not self.stop_evt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
