@@ -1,16 +1,17 @@
 // demod_kernels.cu - stage 2 of the receive path on the GPU: batched pi/4-CxPSK burst demodulation.
 //
-// One warp per burst.  The burst window (len*sps + search-window complex float samples, 4-11 KB
-// at sps 4) is read from HBM exactly once into the warp's slice of shared memory; every later
-// pass (statistics, training-sequence correlation over all search offsets, early/late peak
-// search, frequency / phase estimation, soft bits) works out of shared memory and registers with
-// warp-shuffle reductions.  Output per burst: ebits (int8), sync id, fractional TOA, frequency
-// error, sync power.
+// One warp per burst, persistent warps (148 SMs x 8 CTAs x 4 warps stride over the batch).  The burst window
+// (len*sps + search-window complex float samples, 4-11 KB at sps 4) is requested into L2 with one bulk prefetch and
+// read from HBM exactly once (16-byte loads of the statistics pass).  Only the samples the training-sequence search
+// touches ("correlation regions", ~1/3 of the window) are kept in the warp's ~5 KB slice of shared memory, filled
+// from those same loads; the data-symbol samples are picked from L2 afterwards.  Statistics, correlation over all
+// search offsets, early/late peak search, frequency / phase estimation and soft bits run on registers, shared
+// memory and warp shuffles.  Output per burst: ebits (int8), sync id, fractional TOA, frequency error, sync power.
 //
 // Replaces, for a whole batch per launch, the reference's
 //   gmr1_pi4cxpsk_demod       src/sdr/pi4cxpsk.c:520-602
 //   _gmr1_pi4cxpsk_sync_find  :184-268   (incl. the never-reset accumulator quirk, :207/:232)
-//   _gmr1_pi4cxpsk_align      :280-348   (sps >= 4 path)
+//   _gmr1_pi4cxpsk_align      :280-348
 //   _gmr1_pi4cxpsk_freq_err   :360-406
 //   _gmr1_pi4cxpsk_phase      :415-433
 //   _gmr1_pi4cxpsk_soft_symbols / _soft_bits  :442-503
@@ -18,15 +19,20 @@
 // and the libosmo-dsp primitives they call (sig_normalize, correlate, peak_energy_find with
 // PEAK_EARLY_LATE, interpolate_point, rotate, scale) as restated in SURVEY.md Appendix A.2.
 //
-// The kernel computes the same quantities as the C path but not with the same instruction
-// sequence; it is issue-bound, so the work is restructured to need ~3x fewer instructions:
+// The kernel computes the same quantities as the C path but not with the same instruction sequence; it is bound
+// by instruction issue, so the work is restructured to need ~4x fewer instructions:
 //   * normalise + derotate is never applied to the 1000+ samples of the window.  Only magnitudes
 //     of correlations are used, so the rotation moves onto the <= 32 reference taps and the
-//     mean / scale become a per-chunk correction (see sync_find);
-//   * window statistics are one pass (E|x|^2 - |E x|^2), tree sums;
-//   * the sinc interpolation shares one sine per position: sin(pi*(k-pos)) = -(-1)^j sin(pi*frac);
-//   * data symbols are sliced in the angle domain: arg(x-avg) + fs*idx - ferr*i - arg(phasor),
-//     accumulated in double, instead of three complex rotations and an atan2 per symbol.
+//     mean / scale become a per-chunk correction (corr_block);
+//   * window statistics are one pass, tree sums;
+//   * the early/late search compares two sinc interpolations that share their fractional position (no sine,
+//     one reciprocal per tap) and takes three of its bisection steps per round (8 grid points in parallel);
+//   * data symbols are sliced in the angle domain: arg(x-avg) + fs*idx - ferr*i - arg(phasor) in fp32 with a
+//     Cody-Waite reduction of fs*idx, instead of three complex rotations and an atan2 per symbol; the soft bits
+//     come from a table over the symbol value in steps of 1/256.
+// LAYOUT RULE: the per-burst loop must fit the 32 KB instruction cache.  Variants that a launch does not execute
+// (sync power, unaligned windows, > 96 search offsets, > 32 training symbols) live in __noinline__ functions or in
+// other template instantiations (ROWS, SYMB), never inline in the hot path (profiles/README.md has the numbers).
 // Float contract (tests/test_demod_gpu.py): sync_id identical, TOA within 0.01 sample, freq_err
 // within 2e-5 rad/symbol, soft bits within +-1 LSB (>= 99.5 % identical), and identical L2 / CRC
 // after stage 3.  Integer stages (stage 3) are bit-exact.
