@@ -420,6 +420,18 @@ def run_gpu_arm(args):
 
     # ---------------- end to end: pinned host IQ in, host L2/CRC out, through the C ABI
     chunks = args.e2e_chunks
+    # the pinned staging buffers are allocated (first touched) from the CPUs next to this rank's GPU, so that with
+    # several ranks per host every H2D stream reads memory of its own NUMA node; the affinity is restored afterwards
+    old_affinity = None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        old_affinity = os.sched_getaffinity(0)
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        if not os.sched_getaffinity(0):
+            os.sched_setaffinity(0, old_affinity)
+    except Exception:
+        pass
     host_iq = {k: torch.empty(W.iq[k].shape, dtype=torch.float32).pin_memory() for k in W.iq}
     host_l2 = {k: torch.empty((W.n[k], 24), dtype=torch.uint8).pin_memory() for k in W.iq}
     host_crc = {k: torch.empty(W.n[k], dtype=torch.int32).pin_memory() for k in W.iq}
@@ -429,6 +441,11 @@ def run_gpu_arm(args):
     host_fcch.copy_(W.fcch_iq)
     host_fcch_out = torch.empty((2, W.n_arfcn), dtype=torch.float32).pin_memory()
     torch.cuda.synchronize()
+    if old_affinity:
+        try:
+            os.sched_setaffinity(0, old_affinity)
+        except Exception:
+            pass
     jobs = []
     for k in ("bcch", "dc6"):
         per = (W.n[k] + chunks - 1) // chunks
