@@ -128,3 +128,44 @@ def test_mod_order(gpu_lib, oracle):
         assert order[i] == oracle.mod_order(x[i], SPS, 0.0), i
     # the heuristic itself is allowed an occasional miss (parity with the oracle is the check above)
     assert (order[1::2] == 2).mean() >= 0.9 and (order[0::2] == 4).mean() >= 0.9
+
+
+def test_fcch_rough_multi(gpu_lib, oracle):
+    """gmr1b200_fcch_rough_multi vs gmr1_fcch_rough_multi (src/sdr/fcch.c:341-483): 650 ms windows with the FCCHs of
+    one, two and three cells (each twice, 7488 symbols apart), found with the same count and the same TOAs."""
+    rng = np.random.default_rng(21)
+    W = (650 * 23400 * SPS) // 1000
+    per = 7488 * SPS
+    chirp = sigen.fcch_chirp(SPS, 0.32, 117)
+    n_found = 0
+    for case, cells in enumerate([[(5000, 1.0)], [(5000, 1.0), (17000, 0.7)], [(1234, 0.8), (9000, 1.0), (23456, 0.6)],
+                                  [(29000, 1.0), (12000, 0.9)]]):
+        sig = 10.0 ** (-10.0 / 20.0) / np.sqrt(2.0)
+        x = sig * (rng.standard_normal(W) + 1j * rng.standard_normal(W))
+        for pos, amp in cells:
+            for k in range(2):
+                p0 = pos + k * per
+                cfo = 0.02 * (case - 1)
+                x[p0:p0 + len(chirp)] += amp * chirp * np.exp(1j * (cfo * np.arange(len(chirp)) / SPS + rng.uniform(0, 6.28)))
+        x = x.astype(np.complex64)
+        rc_o, toa_o = oracle.fcch_rough_multi(x, SPS, 0.0)
+        toa = np.zeros(16, np.int32)
+        rc = gpu_lib.call("gmr1b200_fcch_rough_multi", 0, np.ascontiguousarray(x).view(np.float32), W, SPS, 0.0, toa, 16, None)
+        assert rc == rc_o, (case, rc, rc_o)
+        assert rc_o == len(cells), (case, rc_o, toa_o)                       # the generator is understood by the reference
+        for a, b in zip(sorted(toa[:rc].tolist()), sorted(toa_o)):
+            assert abs(a - b) <= 1, (case, toa[:rc], toa_o)
+        for (pos, _), t in zip(sorted(cells), sorted(toa_o)):
+            assert abs(t - pos) <= 2 * SPS, (case, toa_o)
+        n_found += rc
+    assert n_found == 8
+    # noise only: whatever the reference answers (nothing found, or -EINVAL when the two cycles do not line up)
+    x = (rng.standard_normal(W) + 1j * rng.standard_normal(W)).astype(np.complex64)
+    rc_o, _ = oracle.fcch_rough_multi(x, SPS, 0.0)
+    toa = np.zeros(16, np.int32)
+    try:
+        rc = gpu_lib.call("gmr1b200_fcch_rough_multi", 0, np.ascontiguousarray(x).view(np.float32), W, SPS, 0.0, toa, 16, None)
+    except Exception as e:                                                   # the wrapper raises on negative codes
+        rc = -22 if "rc=-22" in str(e) else None
+    assert rc == rc_o or (rc_o > 0 and rc > 0), (rc, rc_o)
+
