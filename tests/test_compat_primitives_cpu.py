@@ -97,3 +97,30 @@ def test_a5(libs):
             for a, b in zip(*res):
                 assert (a == b).all()
             assert (res[0][0] == res[0][2]).all() and not res[0][3].any()
+
+
+class CxVec(ctypes.Structure):
+    _fields_ = [("len", ctypes.c_int), ("max_len", ctypes.c_int), ("flags", ctypes.c_int), ("data", P)]
+
+
+BURSTS = {"bcch": (424, 1), "dc2": (132, 1), "dc6": (432, 1), "dc12": (432, 1), "nt3_speech": (212, 1), "nt3_facch": (104, 2),
+          "nt6": (434, 2), "nt9": (662, 2), "rach": (494, 1), "sdcch": (208, 4)}
+
+
+def test_pi4cxpsk_mod(libs):
+    """gmr1_pi4cxpsk_mod (src/sdr/pi4cxpsk.c:741-800) over every exported burst descriptor and sync sequence: the same
+    1-sample-per-symbol burst as the reference (descriptor data symbols, Gray map, rotation)"""
+    rng = np.random.default_rng(5)
+    for name, (ebits, n_sync) in BURSTS.items():
+        hard = rng.integers(0, 2, ebits).astype(np.uint8)
+        for sid in range(n_sync):
+            res = []
+            for lib in libs:
+                desc = ctypes.c_char.in_dll(lib, f"gmr1_{name}_burst")
+                buf = np.zeros(1024, np.complex64)
+                cv = CxVec(0, 1024, 0, buf.ctypes.data_as(P))
+                rc = lib.gmr1_pi4cxpsk_mod(ctypes.c_void_p(ctypes.addressof(desc)), p(hard), sid, ctypes.byref(cv))
+                assert rc == 0, (name, rc)
+                res.append(buf[:cv.len].copy())
+            assert res[0].shape == res[1].shape and len(res[0]) > 70, name
+            assert np.abs(res[0] - res[1]).max() <= 1e-6, (name, sid)
