@@ -338,6 +338,26 @@ int gmr1b200_fcch_snr_batch(int fcch_type, const float *iq, int64_t iq_len,
                             const float *freq_shift, float freq_shift0,
                             float *snr, int n, void *stream);
 
+/* replaces fcch_multi_process, src/gmr1_rx.c:643-741, up to its callback, for n recordings: every
+ * FCCH a receiver should follow.  Recording i is iq[rec_ofs[i] .. + rec_len[i]) (complex samples); align[i] /
+ * freq_err[i] are its primary acquisition (gmr1b200_fcch_acquire_batch; freq_err NULL = 0).  Per recording:
+ * gmr1_fcch_rough_multi over the 650 ms that start one FCCH burst before align[i] (freq_shift -freq_err[i], up to 16
+ * peaks), gmr1_fcch_fine and gmr1_fcch_snr on each peak, then the reference's filter: the strongest peak always
+ * survives, another one only with snr >= 2, snr >= (strongest snr) / 6 and a frequency error within 500 Hz of the
+ * strongest's.  Correlation, fine and SNR stages are one launch each per 256 recordings; the scalar bookkeeping
+ * between them runs on the host as in gmr1b200_fcch_rough_multi.
+ * n_fcch [n]: survivors (0 .. max_cand, max_cand <= 16) or -EINVAL (fewer than 650 ms of samples behind the window
+ * start - the reference prints "Not enough samples" - or the two FCCH cycles do not line up, fcch.c:426).
+ * cand_align [n][max_cand]: alignment in samples from the start of the recording, strongest first: what
+ * process_bcch starts from (chan_desc.align, gmr1_rx.c:731), i.e. align0 of gmr1b200_rx_bcch_batch with the
+ * primary freq_err[i] as freq_err0.  cand_snr / cand_freq_err [n][max_cand] (linear SNR, fine frequency error in
+ * rad/symbol relative to freq_err[i]) may be NULL.  iq may be host or device memory; the per-recording arrays and
+ * the outputs are HOST memory (the call synchronises the stream three times per 256 recordings). */
+int gmr1b200_fcch_multi_batch(int fcch_type, const float *iq, int64_t iq_len, const int64_t *rec_ofs,
+                              const int32_t *rec_len, const int32_t *align, const float *freq_err, int sps, int n,
+                              int max_cand, int32_t *n_fcch, int32_t *cand_align, float *cand_snr,
+                              float *cand_freq_err, void *stream);
+
 /* ---- DKAB and modulation order ------------------------------------------------------------------ */
 
 /* replaces gmr1_dkab_demod, src/sdr/dkab.c:187 (sdr/dkab.h:40-42).  p [n] DKAB position or NULL (p0);

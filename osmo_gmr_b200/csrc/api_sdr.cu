@@ -99,39 +99,12 @@ static void peak_record(int burst_len, int *toa, float *pwr, int *n, int N, int 
 		*n += 1;
 }
 
-int gmr1b200_fcch_rough_multi(int fcch_type, const float *iq, int64_t win_len, int sps, float freq_shift,
-                              int32_t *peaks_toa, int N, void *stream)
+// everything of gmr1_fcch_rough_multi behind the correlation (fcch.c:385-483): strongest peak of the first
+// cycle, its twin one period later, geometric mix of the two cycles, avg + 3 sigma threshold, sorted
+// de-duplicated insert.  corr_pwr [nc] is overwritten.  Returns the number of FCCHs or -EINVAL.
+static int rough_multi_peaks(float *corr_pwr, int nc, int blen, int sps, int32_t *peaks_toa, int N)
 {
-	if (fcch_type < 0 || fcch_type > 2 || !iq || !peaks_toa || N < 1 || sps < 1 || sps > 16)
-		return set_err(-EINVAL, "fcch_rough_multi: bad argument");
 	const int sym_rate = 23400;
-	if (win_len < ((int64_t)650 * sym_rate * sps) / 1000)      // fcch.c:355
-		return set_err(-EINVAL, "fcch_rough_multi: needs 650 ms of signal");
-	const int blen = FCCH_TYPES[fcch_type].len;
-	const int l = (int)(win_len / sps), nc = l - blen + 1;
-	std::vector<float> pw((size_t)nc);
-	{
-		FcchArgs a = {};
-		a.iq = (const float2 *)iq; a.stride = 0; a.n = 1; a.win_len = (int)win_len; a.sps = sps;
-		a.freq_shift0 = freq_shift;
-		Stage s(stream);
-		int dummy_toa;
-		a.toa = &dummy_toa;
-		int rc = fcch_common(fcch_type, a, s, win_len, "fcch_rough_multi: bad argument");
-		if (rc)
-			return rc;
-		a.en_out = s.out(pw.data(), (size_t)nc);
-		cudaError_t e = cudaSuccess;
-		if (!s.failed()) {
-			e = launch_fcch_rough(a, (cudaStream_t)stream);
-			if (e == cudaSuccess)
-				g_launches.fetch_add(1);
-		}
-		rc = s.finish(e, "fcch_rough kernel");
-		if (rc)
-			return rc;
-	}
-	float *corr_pwr = pw.data();
 	int Lw = (320 * sym_rate) / 1000 + blen, Lp = (320 * sym_rate) / 1000;
 	int pwr_max_idx = 0;
 	float pwr_max = 0.0f;
@@ -158,7 +131,7 @@ int gmr1b200_fcch_rough_multi(int fcch_type, const float *iq, int64_t win_len, i
 	peaks[1] /= pwrs[1];
 	const int nLp = (int)round(peaks[1] - peaks[0]);
 	if (abs(nLp - Lp) > 10)
-		return set_err(-EINVAL, "fcch_rough_multi: FCCH period mismatch");
+		return -EINVAL;
 	Lp = nLp;
 	if (Lw + Lp > nc)
 		Lw = nc - Lp;
@@ -192,6 +165,212 @@ int gmr1b200_fcch_rough_multi(int fcch_type, const float *iq, int64_t win_len, i
 		}
 	}
 	return peaks_cnt;
+}
+
+int gmr1b200_fcch_rough_multi(int fcch_type, const float *iq, int64_t win_len, int sps, float freq_shift,
+                              int32_t *peaks_toa, int N, void *stream)
+{
+	if (fcch_type < 0 || fcch_type > 2 || !iq || !peaks_toa || N < 1 || sps < 1 || sps > 16)
+		return set_err(-EINVAL, "fcch_rough_multi: bad argument");
+	const int sym_rate = 23400;
+	if (win_len < ((int64_t)650 * sym_rate * sps) / 1000)      // fcch.c:355
+		return set_err(-EINVAL, "fcch_rough_multi: needs 650 ms of signal");
+	const int blen = FCCH_TYPES[fcch_type].len;
+	const int l = (int)(win_len / sps), nc = l - blen + 1;
+	std::vector<float> pw((size_t)nc);
+	{
+		FcchArgs a = {};
+		a.iq = (const float2 *)iq; a.stride = 0; a.n = 1; a.win_len = (int)win_len; a.sps = sps;
+		a.freq_shift0 = freq_shift;
+		Stage s(stream);
+		int dummy_toa;
+		a.toa = &dummy_toa;
+		int rc = fcch_common(fcch_type, a, s, win_len, "fcch_rough_multi: bad argument");
+		if (rc)
+			return rc;
+		a.en_out = s.out(pw.data(), (size_t)nc);
+		cudaError_t e = cudaSuccess;
+		if (!s.failed()) {
+			e = launch_fcch_rough(a, (cudaStream_t)stream);
+			if (e == cudaSuccess)
+				g_launches.fetch_add(1);
+		}
+		rc = s.finish(e, "fcch_rough kernel");
+		if (rc)
+			return rc;
+	}
+	const int cnt = rough_multi_peaks(pw.data(), nc, blen, sps, peaks_toa, N);
+	if (cnt < 0)
+		return set_err(cnt, "fcch_rough_multi: FCCH period mismatch");
+	return cnt;
+}
+
+// ---- fcch_multi_process (src/gmr1_rx.c:643-741) up to its callback, for n recordings -----------------
+// Per recording: all FCCHs of the 650 ms behind the primary one (rough_multi with the primary's frequency
+// error), fine TOA / frequency error and SNR of each, the reference's plausibility filter.  Three kernel
+// launches per chunk of recordings (correlation, fine, SNR); the scalar bookkeeping between them is the
+// reference's, on the host.
+int gmr1b200_fcch_multi_batch(int fcch_type, const float *iq, int64_t iq_len, const int64_t *rec_ofs,
+                              const int32_t *rec_len, const int32_t *align, const float *freq_err, int sps, int n,
+                              int max_cand, int32_t *n_fcch, int32_t *cand_align, float *cand_snr,
+                              float *cand_freq_err, void *stream)
+{
+	if (fcch_type < 0 || fcch_type > 2 || !iq || !rec_ofs || !rec_len || !align || n < 0 || sps < 1 || sps > 16 ||
+	    max_cand < 1 || max_cand > 16 || !n_fcch || !cand_align)
+		return set_err(-EINVAL, "fcch_multi_batch: bad argument");
+	if (n == 0)
+		return 0;
+	const int sym_rate = 23400, NPK = 16;                          // mtoa[16], gmr1_rx.c:647
+	const int blen = FCCH_TYPES[fcch_type].len;
+	const int W = (650 * sym_rate * sps) / 1000;                   // :661
+	const int nc = W / sps - blen + 1;
+	cudaStream_t cs = (cudaStream_t)stream;
+	Stage s(stream);
+	const float2 *d_iq = (const float2 *)s.in(iq, (size_t)iq_len * 2);
+	const int CH = 256;                                            // recordings per chunk (15 MB of correlation power)
+	int64_t *d_ofs = s.tmp<int64_t>((size_t)CH * NPK);
+	float *d_fs = s.tmp<float>((size_t)CH * NPK);
+	float *d_pw = s.tmp<float>((size_t)CH * nc);
+	int32_t *d_toa = s.tmp<int32_t>((size_t)CH * NPK);
+	float *d_fe = s.tmp<float>((size_t)CH * NPK), *d_snr = s.tmp<float>((size_t)CH * NPK);
+	if (s.failed())
+		return s.finish(cudaSuccess, "fcch_multi_batch: staging");
+	std::vector<float> pw((size_t)CH * nc), fs, fe, snr;
+	std::vector<int64_t> ofs;
+	std::vector<int32_t> toa, chan, base, mtoa, first, bad;
+	cudaError_t e = cudaSuccess;
+	uint64_t launches = 0;
+	auto up = [&](void *d, const void *h, size_t bytes) {
+		if (e == cudaSuccess)
+			e = cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, cs);
+	};
+	auto down = [&](void *h, const void *d, size_t bytes) {
+		if (e == cudaSuccess)
+			e = cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, cs);
+	};
+	for (int c0 = 0; c0 < n && e == cudaSuccess; c0 += CH) {
+		const int c1 = c0 + CH < n ? c0 + CH : n;
+		// 650 ms window one FCCH burst ahead of the primary alignment (:655-666)
+		chan.clear(); base.clear(); ofs.clear(); fs.clear();
+		for (int i = c0; i < c1; i++) {
+			int b = align[i] - blen * sps;
+			if (b < 0)
+				b = 0;
+			if (b + W > rec_len[i] || rec_ofs[i] < 0 || rec_ofs[i] + rec_len[i] > iq_len) {
+				n_fcch[i] = -EINVAL;                               // "Not enough samples"
+				continue;
+			}
+			chan.push_back(i); base.push_back(b);
+			ofs.push_back(rec_ofs[i] + b);
+			fs.push_back(-(freq_err ? freq_err[i] : 0.0f));        // :668
+		}
+		const int m = (int)chan.size();
+		if (!m)
+			continue;
+		up(d_ofs, ofs.data(), (size_t)m * sizeof(int64_t));
+		up(d_fs, fs.data(), (size_t)m * sizeof(float));
+		FcchArgs a = {};
+		a.iq = d_iq; a.ofs = d_ofs; a.n = m; a.win_len = W; a.sps = sps;
+		a.freq = FCCH_TYPES[fcch_type].freq; a.len = blen;
+		a.freq_shift = d_fs; a.toa = d_toa; a.en_out = d_pw;
+		if (e == cudaSuccess) {
+			e = launch_fcch_rough(a, cs);
+			launches++;
+		}
+		down(pw.data(), d_pw, (size_t)m * nc * sizeof(float));
+		if (e == cudaSuccess)
+			e = cudaStreamSynchronize(cs);
+		if (e != cudaSuccess)
+			break;
+		// candidates of every recording of the chunk, flattened
+		mtoa.clear(); first.assign((size_t)m + 1, 0); bad.assign((size_t)m, 0);
+		std::vector<int64_t> cofs;
+		std::vector<float> cfs;
+		for (int k = 0; k < m; k++) {
+			int32_t t[NPK];
+			const int cnt = rough_multi_peaks(&pw[(size_t)k * nc], nc, blen, sps, t, NPK);
+			bad[k] = cnt < 0 ? cnt : 0;                            // -EINVAL: the two cycles do not line up
+			for (int j = 0; j < cnt; j++) {
+				mtoa.push_back(t[j]);
+				cofs.push_back(ofs[k] + t[j]);                     // :682
+				cfs.push_back(fs[k]);
+			}
+			first[k + 1] = (int32_t)mtoa.size();
+		}
+		const int nk = (int)mtoa.size();
+		for (int k = 0; k < m; k++)
+			n_fcch[chan[k]] = bad[k];                              // 0 found so far, or the error
+		if (!nk)
+			continue;
+		toa.resize(nk); fe.resize(nk); snr.resize(nk);
+		up(d_ofs, cofs.data(), (size_t)nk * sizeof(int64_t));
+		up(d_fs, cfs.data(), (size_t)nk * sizeof(float));
+		FcchArgs f = {};
+		f.iq = d_iq; f.ofs = d_ofs; f.n = nk; f.win_len = blen * sps; f.sps = sps;
+		f.freq = a.freq; f.len = blen; f.freq_shift = d_fs; f.toa = d_toa; f.freq_error = d_fe;
+		if (e == cudaSuccess) {
+			e = launch_fcch_fine(f, 0, cs);                        // :684
+			launches++;
+		}
+		down(toa.data(), d_toa, (size_t)nk * sizeof(int32_t));
+		down(fe.data(), d_fe, (size_t)nk * sizeof(float));
+		if (e == cudaSuccess)
+			e = cudaStreamSynchronize(cs);
+		if (e != cudaSuccess)
+			break;
+		for (int j = 0; j < nk; j++) {                             // SNR at the fine position (:691-696)
+			cofs[j] += toa[j];
+			cfs[j] = -(-cfs[j] + fe[j]);
+		}
+		up(d_ofs, cofs.data(), (size_t)nk * sizeof(int64_t));
+		up(d_fs, cfs.data(), (size_t)nk * sizeof(float));
+		f.toa = nullptr; f.freq_error = nullptr; f.snr = d_snr;
+		if (e == cudaSuccess) {
+			e = launch_fcch_fine(f, 1, cs);
+			launches++;
+		}
+		down(snr.data(), d_snr, (size_t)nk * sizeof(float));
+		if (e == cudaSuccess)
+			e = cudaStreamSynchronize(cs);
+		if (e != cudaSuccess)
+			break;
+		// the strongest is the reference; the others must be strong enough and close in frequency (:702-717)
+		for (int k = 0; k < m; k++) {
+			const int i = chan[k];
+			if (bad[k])
+				continue;
+			float ref_snr = 0.0f, ref_fe = 0.0f;
+			int cnt = 0;
+			for (int j = first[k]; j < first[k + 1]; j++) {
+				if (j == first[k]) {
+					ref_snr = snr[j];
+					ref_fe = fe[j];
+				} else {
+					if (snr[j] < 2.0f)
+						continue;
+					if (snr[j] < ref_snr / 6.0f)
+						continue;
+					const float d = (float)fabs(ref_fe - fe[j]);
+					if ((sym_rate * d) / (2.0f * (float)M_PI) > 500.0f)
+						continue;
+				}
+				if (cnt < max_cand) {
+					const size_t o = (size_t)i * max_cand + cnt;
+					cand_align[o] = base[k] + mtoa[j] + toa[j];     // :738, where process_bcch starts
+					if (cand_snr)
+						cand_snr[o] = snr[j];
+					if (cand_freq_err)
+						cand_freq_err[o] = fe[j];
+				}
+				cnt++;
+			}
+			n_fcch[i] = cnt < max_cand ? cnt : max_cand;
+		}
+	}
+	g_launches.fetch_add(launches);
+	if (e != cudaSuccess)
+		cudaStreamSynchronize(cs);
+	return s.finish(e, "fcch_multi_batch kernels");
 }
 
 static int fine_or_snr(int mode, int fcch_type, const float *iq, int64_t iq_len, const int64_t *win_ofs,

@@ -65,6 +65,7 @@ class Lib:
         "gmr1b200_tch9_encode": [_P, _P, _I, _P, _P, _P, _P],
         "gmr1b200_rach_encode": [_P, _P, _I],
         "gmr1b200_tch3_encode": [_P, _P, _P, _P, _P, _I],
+        "gmr1b200_fcch_multi_batch": [_I, _P, _L, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P],
         "gmr1b200_fcch_rough_batch": [_I, _P, _L, _P, _L, _I, _I, _P, _F, _P, _P, _I, _P],
         "gmr1b200_fcch_fine_batch": [_I, _P, _L, _P, _L, _I, _P, _F, _P, _P, _I, _P],
         "gmr1b200_rx_xcch_batch": [_I, _P, _L, _P, _L, _I, _I, _P, _F, _P, _P, _P, _P, _P, _I, _P],

@@ -147,3 +147,71 @@ def test_rx_bcch_batch_vs_gmr1_rx(gpu_lib, oracle, tmp_path):
     dec = valid & (kind > 0)
     assert (got[3][dec] == conv[dec]).all() and (got[4][dec] == l2[dec]).all()
 
+
+
+def _multi_cell_recordings(oracle):
+    """recordings with the FCCH / BCCH / CCCH frames of one, two and three cells at different timings inside the
+    320 ms FCCH period; the third cell of the last one is 800 Hz away from the strongest and must be filtered"""
+    enc = (lambda l2: oracle.encode("bcch", 424, l2), lambda l2: oracle.encode("ccch", 432, l2))
+    mk = lambda amp, **kw: amp * recording.make(*enc, seconds=1.6, esn0_db=40.0, **kw)[0].astype(np.complex64)
+    noise = lambda seed, n: (0.12 * (np.random.default_rng(seed).standard_normal((n, 2)) @ np.array([1, 1j]))).astype(np.complex64)
+    recs = []
+    a = mk(1.0, cfo_hz=200.0, seed=11, start=9000)
+    recs.append(a + noise(1, len(a)))
+    b = mk(0.7, cfo_hz=260.0, seed=12, start=9000 + 11000)
+    recs.append(a + b + noise(2, len(a)))
+    c = mk(0.8, cfo_hz=-600.0, seed=13, start=9000 + 17000)
+    d = mk(0.6, cfo_hz=150.0, seed=14, start=9000 + 5000, frac=0.6)
+    recs.append(a + c + d + noise(3, len(a)))
+    return recs
+
+
+def test_fcch_multi_batch_vs_gmr1_rx(gpu_lib, oracle, tmp_path):
+    """gmr1b200_fcch_acquire_batch + gmr1b200_fcch_multi_batch against main() / fcch_single_init / fcch_multi_process of
+    the reference application (src/gmr1_rx.c:606-741): the same number of process_bcch() calls per recording, starting
+    at the same alignments (in the reference's order, strongest first; +-1 sample as for every FCCH TOA)."""
+    if not os.path.exists(REF_BIN):
+        pytest.skip("oracle/_ref/gmr1_rx not built (needs /root/reference at build time)")
+    recs = _multi_cell_recordings(oracle)
+    ref = []
+    for ci, x in enumerate(recs):
+        path = str(tmp_path / f"multi{ci}.cfile")
+        x.tofile(path)
+        ref.append([r["align"] for r in _reference_runs(path)])
+    assert [len(r) for r in ref] == [1, 2, 2], ref            # the generator is understood by the reference
+    n = len(recs)
+    rec_len = np.array([len(x) for x in recs], np.int32)
+    rec_ofs = np.concatenate([[0], np.cumsum(rec_len[:-1])]).astype(np.int64)
+    iq = np.ascontiguousarray(np.concatenate(recs)).view(np.float32)
+    W330 = (330 * 23400 * SPS) // 1000
+    align = np.zeros(n, np.int32)
+    ferr = np.zeros(n, np.float32)
+    gpu_lib.call("gmr1b200_fcch_acquire_batch", 0, iq, len(iq) // 2, rec_ofs + START_DISCARD, 0, W330, SPS,
+                 None, align, ferr, n, None)
+    align += START_DISCARD
+    M = 4
+    cnt = np.full(n, -99, np.int32)
+    cal = np.zeros((n, M), np.int32)
+    snr = np.zeros((n, M), np.float32)
+    cfe = np.zeros((n, M), np.float32)
+    gpu_lib.call("gmr1b200_fcch_multi_batch", 0, iq, len(iq) // 2, rec_ofs, rec_len, align, ferr, SPS, n, M,
+                 cnt, cal, snr, cfe, None)
+    for i in range(n):
+        assert cnt[i] == len(ref[i]), (i, cnt[i], cal[i], ref[i])
+        for a, b in zip(cal[i, :cnt[i]].tolist(), ref[i]):
+            assert abs(a - b) <= 1, (i, cal[i], ref[i])
+        assert (snr[i, :cnt[i]] >= 2.0).all() and abs(cfe[i, 0]) < 0.01          # residual of the primary acquisition: a few Hz
+    # the same with the recordings in device memory
+    import torch
+    cnt2 = np.full(n, -99, np.int32)
+    cal2 = np.zeros((n, M), np.int32)
+    d_iq = torch.from_numpy(iq).to("cuda:0")
+    gpu_lib.call("gmr1b200_fcch_multi_batch", 0, d_iq, len(iq) // 2, rec_ofs, rec_len, align, ferr, SPS, n, M,
+                 cnt2, cal2, None, None, None)
+    assert (cnt2 == cnt).all() and all((cal2[i, :cnt[i]] == cal[i, :cnt[i]]).all() for i in range(n))
+    # a recording with fewer than 650 ms behind the window start: the reference's "Not enough samples"
+    short_len = np.array([align[0] + 50000], np.int32)
+    c1 = np.zeros(1, np.int32)
+    gpu_lib.call("gmr1b200_fcch_multi_batch", 0, iq, len(iq) // 2, rec_ofs[:1], short_len, align[:1], ferr[:1], SPS, 1, M,
+                 c1, cal2[:1], None, None, None)
+    assert c1[0] == -22
