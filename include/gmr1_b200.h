@@ -259,8 +259,8 @@ int gmr1b200_rx_xcch_batch(int chan, const float *iq, int64_t iq_len, const int6
                            int n, void *stream);
 
 /* ---- receiver frame loop for n channels in lock step --------------------------------
- * replaces process_bcch (src/gmr1_rx.c:853-895) with rx_bcch (:747-803), rx_ccch (:805-851, without the TCH3
- * hand-off), bcch_tdma_align (:194-236), burst_map / burst_energy (:149-182) for n channels at once.
+ * replaces process_bcch (src/gmr1_rx.c:853-895) with rx_bcch (:747-803), rx_ccch (:805-851; the TCH3
+ * hand-off is reported by gmr1b200_rx_bcch_ass_batch below), bcch_tdma_align (:194-236), burst_map / burst_energy (:149-182) for n channels at once.
  * Channel i is the recording iq[rec_ofs[i] .. + rec_len[i]) (complex samples) and starts as the reference's
  * chan_desc after FCCH acquisition: align0[i] (samples from the start of the recording; what
  * gmr1b200_fcch_acquire_batch returns plus the offset of its search window), freq_err0[i] (rad/symbol, NULL = 0),
@@ -277,6 +277,20 @@ int gmr1b200_rx_bcch_batch(const float *iq, int64_t iq_len, const int64_t *rec_o
                            const int32_t *align0, const float *freq_err0, int sps, int n, int max_frames,
                            int32_t *kind, int32_t *fn, int32_t *crc, int32_t *conv, uint8_t *l2,
                            int32_t *n_frames, int32_t *align_out, float *freq_err_out, void *stream);
+
+/* The same walk, and the TCH3 hand-off of rx_ccch (src/gmr1_rx.c:836-841): a CCCH burst with a good CRC that is an
+ * IMMEDIATE ASSIGNMENT (ccch_is_imm_ass :236-239) initialises the channel's TCH3 state as rx_tch3_init does (:362-381).
+ * tch3 [n][4]: active (0 / 1), tn (receive timeslot) and p (DKAB position) from ccch_imm_ass_parse (:240-245), frame
+ * index (into the [max_frames] outputs) of the assignment, -1 without one; tch3_energy [n][2] (may be NULL):
+ * energy_burst = 0.75 x the CCCH energy gate at that frame (half the energy of the last BCCH window) and
+ * energy_dkab = energy_burst / 8.  A later IMM.ASS overwrites an earlier one, as in the reference.  The TCH3 burst
+ * loop that follows (rx_tch3 :538-600, on the traffic-channel recording) stays with the caller, who has everything it
+ * starts from: this record, fn of that frame, and the alignment / frequency tracking of the channel. */
+int gmr1b200_rx_bcch_ass_batch(const float *iq, int64_t iq_len, const int64_t *rec_ofs, const int32_t *rec_len,
+                               const int32_t *align0, const float *freq_err0, int sps, int n, int max_frames,
+                               int32_t *kind, int32_t *fn, int32_t *crc, int32_t *conv, uint8_t *l2,
+                               int32_t *n_frames, int32_t *align_out, float *freq_err_out,
+                               int32_t *tch3, float *tch3_energy, void *stream);
 
 /* ---- A5 cipher stream (host; input to the ciphered decoders) ------------------------------------
  * replaces gmr1_a5 / gmr1_a5_1, src/l1/a5.c:57,226 (l1/a5.h:37-41): n = 0 (all zero) or 1 (A5/1-GMR);

@@ -2,7 +2,9 @@
 // (SURVEY 8f N1).  Replaces, for a whole batch of channels per call,
 //   process_bcch      src/gmr1_rx.c:853-895   frame walk, which burst a frame carries
 //   rx_bcch           :747-803                BCCH burst: demod, decode, alignment / frequency tracking
-//   rx_ccch           :805-851                CCCH burst behind an energy gate (without the TCH3 hand-off)
+//   rx_ccch           :805-851                CCCH burst behind an energy gate; an IMM.ASS on it fills the
+//   rx_tch3_init / ccch_imm_ass_parse  :236-245,362-381   channel's TCH3 hand-off record (the TCH3 burst loop
+//                                             itself, rx_tch3 :538-600, stays with the caller)
 //   bcch_tdma_align   :194-236                SI1 / segment 2Abis -> frame number, SA_SIRFN_DELAY, SA_BCCH_STN
 //   burst_map / burst_energy  :149-182        window geometry, mean energy of the inner 30/32 of a window
 //
@@ -52,6 +54,8 @@ struct RxOut {                               // [n][max_frames] device memory (l
 	int32_t *kind, *fn, *crc, *conv;
 	uint8_t *l2;
 	int32_t *n_frames;                       // [n]
+	int32_t *tch3;                           // [n][4] active, tn, p, frame of the assignment; or NULL
+	float   *tch3_energy;                    // [n][2] energy_burst, energy_dkab; or NULL
 };
 
 // mean energy of the inner 30/32 of a window (burst_energy, gmr1_rx.c:172-182); warp-parallel partial sums
@@ -194,6 +198,19 @@ __global__ void __launch_bounds__(128) rx_update_kernel(RxState st, RxBurstOut b
 				}
 				st.align[i] = align;
 			}
+		} else if (crc == 0 && out.tch3 && l2[1] == 0x06 && l2[2] == 0x3f) {      // ccch_is_imm_ass :236-239
+			// rx_tch3_init(cd, l2, min_energy) with min_energy = bcch_energy / 2 (:836-838, :878); a later
+			// IMM.ASS re-initialises the state as in the reference
+			const float ref = st.bcch_energy[i] / 2.0f;
+			const float eb = ref * 0.75f;
+			out.tch3[4 * i + 0] = 1;
+			out.tch3[4 * i + 1] = ((l2[8] & 0x03) << 3) | (l2[9] >> 5);            // ccch_imm_ass_parse :240-245
+			out.tch3[4 * i + 2] = (l2[8] & 0xfc) >> 2;
+			out.tch3[4 * i + 3] = frame;
+			if (out.tch3_energy) {
+				out.tch3_energy[2 * i + 0] = eb;                                   // :372-373
+				out.tch3_energy[2 * i + 1] = eb / 8.0f;
+			}
 		}
 	}
 	out.crc[rec] = crc;
@@ -207,11 +224,18 @@ __global__ void __launch_bounds__(128) rx_update_kernel(RxState st, RxBurstOut b
 		st.done[i] = 1;
 }
 
-__global__ void rx_init_kernel(RxState st, const int32_t *align0, const float *freq_err0, int32_t *n_frames, int n)
+__global__ void rx_init_kernel(RxState st, const int32_t *align0, const float *freq_err0, int32_t *n_frames,
+                               int32_t *tch3, float *tch3_energy, int n)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n)
 		return;
+	if (tch3) {
+		tch3[4 * i + 0] = 0; tch3[4 * i + 1] = 0; tch3[4 * i + 2] = 0; tch3[4 * i + 3] = -1;
+	}
+	if (tch3_energy) {
+		tch3_energy[2 * i + 0] = 0.0f; tch3_energy[2 * i + 1] = 0.0f;
+	}
 	st.align[i] = align0[i];
 	st.freq_err[i] = freq_err0 ? freq_err0[i] : 0.0f;
 	st.fn[i] = 0;                                  // chan_desc is zeroed in main(), gmr1_rx.c:906
@@ -235,10 +259,11 @@ __global__ void rx_final_kernel(RxState st, int32_t *align, float *freq_err, int
 
 }  // namespace
 
-extern "C" int gmr1b200_rx_bcch_batch(const float *iq, int64_t iq_len, const int64_t *rec_ofs, const int32_t *rec_len,
-                                      const int32_t *align0, const float *freq_err0, int sps, int n, int max_frames,
-                                      int32_t *kind, int32_t *fn, int32_t *crc, int32_t *conv, uint8_t *l2,
-                                      int32_t *n_frames, int32_t *align_out, float *freq_err_out, void *stream)
+static int rx_bcch_walk(const float *iq, int64_t iq_len, const int64_t *rec_ofs, const int32_t *rec_len,
+                        const int32_t *align0, const float *freq_err0, int sps, int n, int max_frames,
+                        int32_t *kind, int32_t *fn, int32_t *crc, int32_t *conv, uint8_t *l2,
+                        int32_t *n_frames, int32_t *align_out, float *freq_err_out,
+                        int32_t *tch3, float *tch3_energy, void *stream)
 {
 	if (!iq || !rec_ofs || !rec_len || !align0 || n < 0 || max_frames < 1 || sps < 1 || sps > 16 || !kind || !fn ||
 	    !crc || !conv || !l2 || !n_frames)
@@ -262,6 +287,7 @@ extern "C" int gmr1b200_rx_bcch_batch(const float *iq, int64_t iq_len, const int
 	RxOut out = {};
 	out.kind = s.out(kind, NF); out.fn = s.out(fn, NF); out.crc = s.out(crc, NF); out.conv = s.out(conv, NF);
 	out.l2 = s.out(l2, NF * 24); out.n_frames = s.out(n_frames, N);
+	out.tch3 = s.out(tch3, N * 4); out.tch3_energy = s.out(tch3_energy, N * 2);
 	int32_t *d_align_out = s.out(align_out, N);
 	float *d_ferr_out = s.out(freq_err_out, N);
 
@@ -286,7 +312,7 @@ extern "C" int gmr1b200_rx_bcch_batch(const float *iq, int64_t iq_len, const int
 	// every recording must lie inside iq (checked on the host copy of the descriptors when they are host memory
 	// is not possible in general: the kernels bound every window by rec_len, the caller vouches for rec_ofs)
 	const int tb = 128, grid = (n + tb - 1) / tb;
-	rx_init_kernel<<<grid, tb, 0, cs>>>(st, d_align0, d_ferr0, out.n_frames, n);
+	rx_init_kernel<<<grid, tb, 0, cs>>>(st, d_align0, d_ferr0, out.n_frames, out.tch3, out.tch3_energy, n);
 	cudaMemsetAsync(out.kind, 0, NF * sizeof(int32_t), cs);
 	cudaMemsetAsync(out.crc, 0xff, NF * sizeof(int32_t), cs);
 	uint64_t launches = 1;
@@ -330,6 +356,27 @@ extern "C" int gmr1b200_rx_bcch_batch(const float *iq, int64_t iq_len, const int
 	}
 	g_launches.fetch_add(launches);
 	return s.finish(e, "rx_bcch_batch kernels");
+}
+
+extern "C" int gmr1b200_rx_bcch_batch(const float *iq, int64_t iq_len, const int64_t *rec_ofs, const int32_t *rec_len,
+                                      const int32_t *align0, const float *freq_err0, int sps, int n, int max_frames,
+                                      int32_t *kind, int32_t *fn, int32_t *crc, int32_t *conv, uint8_t *l2,
+                                      int32_t *n_frames, int32_t *align_out, float *freq_err_out, void *stream)
+{
+	return rx_bcch_walk(iq, iq_len, rec_ofs, rec_len, align0, freq_err0, sps, n, max_frames, kind, fn, crc, conv, l2,
+	                    n_frames, align_out, freq_err_out, nullptr, nullptr, stream);
+}
+
+extern "C" int gmr1b200_rx_bcch_ass_batch(const float *iq, int64_t iq_len, const int64_t *rec_ofs,
+                                          const int32_t *rec_len, const int32_t *align0, const float *freq_err0, int sps,
+                                          int n, int max_frames, int32_t *kind, int32_t *fn, int32_t *crc, int32_t *conv,
+                                          uint8_t *l2, int32_t *n_frames, int32_t *align_out, float *freq_err_out,
+                                          int32_t *tch3, float *tch3_energy, void *stream)
+{
+	if (!tch3)
+		return set_err(-EINVAL, "rx_bcch_ass_batch: tch3 NULL");
+	return rx_bcch_walk(iq, iq_len, rec_ofs, rec_len, align0, freq_err0, sps, n, max_frames, kind, fn, crc, conv, l2,
+	                    n_frames, align_out, freq_err_out, tch3, tch3_energy, stream);
 }
 
 // ---- fused burst -> L2 for the common control channels ------------------------------------------------

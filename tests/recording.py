@@ -13,8 +13,11 @@ SPS = 4
 FRAME = 24 * 39 * SPS
 
 
-def make(enc_bcch, enc_ccch, seconds=2.2, esn0_db=15.0, cfo_hz=300.0, frac=0.37, start=9000, seed=1, tdma_si1=False):
-    """enc_bcch / enc_ccch: l2[24] -> hard bits.  Returns (complex64 samples, list of (frame, kind, l2))."""
+def make(enc_bcch, enc_ccch, seconds=2.2, esn0_db=15.0, cfo_hz=300.0, frac=0.37, start=9000, seed=1, tdma_si1=False,
+         imm_ass=None):
+    """enc_bcch / enc_ccch: l2[24] -> hard bits.  imm_ass: {frame: (tn, p)} CCCH frames that carry an IMMEDIATE
+    ASSIGNMENT (ccch_is_imm_ass / ccch_imm_ass_parse, gmr1_rx.c:236-245).
+    Returns (complex64 samples, list of (frame, kind, l2))."""
     rng = np.random.default_rng(seed)
     n = int(seconds * 23400 * SPS)
     x = np.zeros(n, np.complex128)
@@ -43,6 +46,11 @@ def make(enc_bcch, enc_ccch, seconds=2.2, esn0_db=15.0, cfo_hz=300.0, frac=0.37,
                 l2[0] = (l2[0] & 0x07) | 0x10            # not an SI1 header: bcch_tdma_align() is a no-op
             else:
                 l2[1] = 0x01                             # never an IMM.ASS (gmr1_rx.c:236-239)
+                if imm_ass and f in imm_ass:
+                    tn, p = imm_ass[f]
+                    l2[1], l2[2] = 0x06, 0x3f
+                    l2[8] = ((p & 0x3f) << 2) | ((tn >> 3) & 0x03)
+                    l2[9] = ((tn & 0x07) << 5) | (l2[9] & 0x1f)
             hard = (enc_bcch if kind == "bcch" else enc_ccch)(l2)
             w = sigen.modulate(kind, hard[None, :], SPS, 32, 16.0 + frac, 0.0, 0.0, 200.0, rng)[0]
             x[pos - 16:pos - 16 + len(w)] += w

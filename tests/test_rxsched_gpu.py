@@ -39,6 +39,9 @@ def _reference_runs(path):
             runs[-1]["frames"][-1]["kind"] = 1
         elif l.startswith("[.]   CCCH"):
             runs[-1]["frames"][-1]["kind"] = 2
+        m = re.match(r"\[\+\] TCH3 assigned on TN (\d+)", l)
+        if m:
+            runs[-1].setdefault("ass", []).append((len(runs[-1]["frames"]) - 1, int(m.group(1))))
         m = re.match(r"crc=(-?\d+), conv=(-?\d+)", l)
         if m:
             runs[-1]["frames"][-1]["crc"] = int(m.group(1))
@@ -215,3 +218,56 @@ def test_fcch_multi_batch_vs_gmr1_rx(gpu_lib, oracle, tmp_path):
     gpu_lib.call("gmr1b200_fcch_multi_batch", 0, iq, len(iq) // 2, rec_ofs[:1], short_len, align[:1], ferr[:1], SPS, 1, M,
                  c1, cal2[:1], None, None, None)
     assert c1[0] == -22
+
+
+def test_rx_bcch_ass_batch_vs_gmr1_rx(gpu_lib, oracle, tmp_path):
+    """the TCH3 hand-off of the frame loop (rx_ccch -> rx_tch3_init, src/gmr1_rx.c:836-841,362-381): IMMEDIATE
+    ASSIGNMENTs on CCCH bursts are seen in the same frames with the same timeslot as by the reference application
+    ("[+] TCH3 assigned on TN"), DKAB position as sent, energy thresholds from the last BCCH window; the walk itself
+    is identical to gmr1b200_rx_bcch_batch."""
+    if not os.path.exists(REF_BIN):
+        pytest.skip("oracle/_ref/gmr1_rx not built (needs /root/reference at build time)")
+    enc = (lambda l2: oracle.encode("bcch", 424, l2), lambda l2: oracle.encode("ccch", 432, l2))
+    plans = [{5: (7, 3), 13: (21, 10)}, None, {4: (0, 63), 6: (31, 0), 7: (12, 33)}]
+    recs, ref, align0, ferr0 = [], [], [], []
+    for ci, plan in enumerate(plans):
+        x, _ = recording.make(*enc, seconds=1.8, esn0_db=14.0, cfo_hz=100.0 * (ci + 1), seed=30 + ci, imm_ass=plan)
+        path = str(tmp_path / f"ass{ci}.cfile")
+        x.tofile(path)
+        runs = _reference_runs(path)
+        assert len(runs) == 1
+        ref.append(runs[0])
+        a, fe = _acquire_like_main(oracle, x)[0]
+        assert a == runs[0]["align"]
+        align0.append(a)
+        ferr0.append(fe)
+        recs.append(x)
+        assert [(f, tn) for f, tn in runs[0].get("ass", [])] == sorted((f, tn) for f, (tn, _) in (plan or {}).items())
+    n = len(recs)
+    rec_len = np.array([len(x) for x in recs], np.int32)
+    rec_ofs = np.concatenate([[0], np.cumsum(rec_len[:-1])]).astype(np.int64)
+    iq = np.ascontiguousarray(np.concatenate(recs)).view(np.float32)
+    F = 48
+    mk = lambda *shape, dt=np.int32: np.zeros(shape, dt)
+    outs = [mk(n, F), mk(n, F), mk(n, F), mk(n, F), mk(n, F, 24, dt=np.uint8), mk(n), mk(n), mk(n, dt=np.float32)]
+    outs2 = [np.zeros_like(a) for a in outs]
+    tch3 = np.full((n, 4), 77, np.int32)
+    en = np.full((n, 2), 77.0, np.float32)
+    args = (iq, len(iq) // 2, rec_ofs, rec_len, np.array(align0, np.int32), np.array(ferr0, np.float32), SPS, n, F)
+    gpu_lib.call("gmr1b200_rx_bcch_ass_batch", *args, *outs, tch3, en, None)
+    gpu_lib.call("gmr1b200_rx_bcch_batch", *args, *outs2, None)
+    kind, nfr = outs[0], outs[5]
+    assert (outs2[0] == kind).all() and (outs2[2] == outs[2]).all() and (outs2[5] == nfr).all() and (outs2[6] == outs[6]).all()
+    for i, (plan, r) in enumerate(zip(plans, ref)):
+        assert nfr[i] == len(r["frames"])
+        if not plan:
+            assert tch3[i].tolist() == [0, 0, 0, -1] and (en[i] == 0.0).all()
+            continue
+        f_last, tn_last = r["ass"][-1]                       # a later IMM.ASS re-initialises the state
+        assert tch3[i].tolist() == [1, tn_last, plan[f_last][1], f_last], (i, tch3[i], r["ass"])
+        fb = max(f for f in range(f_last) if f % 8 == 2)     # last BCCH frame before the assignment
+        b = 9000 + fb * recording.FRAME - 40
+        w = recs[i][b:b + 1016]
+        e_bcch = float((np.abs(w[31:1016 - 31]) ** 2).sum() / 1016)
+        assert abs(en[i, 0] - 0.75 * e_bcch / 2) <= 0.02 * en[i, 0], (i, en[i], e_bcch)
+        assert en[i, 1] == np.float32(en[i, 0] / np.float32(8.0))

@@ -22,15 +22,19 @@ def main():
     args = ap.parse_args()
     import torch
     import osmo_gmr_b200
-    import oracle_lib            # test infrastructure: only its ENCODERS are used, to build the recordings
-    import recording
+    import recording             # the recording generator of the tests (numpy); nothing under oracle/ is used here
     L = osmo_gmr_b200.lib()
-    o = oracle_lib.load()
+
+    def enc(chan, nbits):        # the library's own channel encoders (gmr1b200_xcch_encode_batch, host code)
+        def f(l2):
+            out = np.zeros(nbits, np.uint8)
+            L.call("gmr1b200_xcch_encode_batch", chan, out, np.ascontiguousarray(l2, np.uint8), 1)
+            return out
+        return f
     SPS = 4
     base = []
     for seed, (snr, cfo) in enumerate([(15.0, 300.0), (10.0, -200.0), (12.0, 90.0), (20.0, 600.0)]):
-        x, _ = recording.make(lambda l2: o.encode("bcch", 424, l2), lambda l2: o.encode("ccch", 432, l2),
-                              esn0_db=snr, cfo_hz=cfo, seed=seed + 1)
+        x, _ = recording.make(enc(0, 424), enc(1, 432), esn0_db=snr, cfo_hz=cfo, seed=seed + 1)
         base.append(x)
     rl = len(base[0])
     n = args.channels
