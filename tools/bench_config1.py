@@ -1,0 +1,99 @@
+#!/usr/bin/env python
+"""Secondary measurement (BASELINE.json config 1 / SURVEY 8d "CPU path timing (a)"): ONE synthetic single-ARFCN
+recording (sps 4, 2.2 s, Es/N0 15 dB, CFO +300 Hz, tests/recording.py) through
+  (a) the reference application linked to the reference C libraries (oracle/_ref/gmr1_rx), wall time on one host core,
+  (b) the SAME unmodified application linked to libgmr1_b200.so (tests/dropin/_build/gmr1_rx_b200): every gmr1_* call is
+      an n = 1 batch with a synchronous H2D / kernel / D2H round trip - the drop-in at its worst operating point,
+  (c) the batched entry points on that one recording (fcch_acquire + fcch_multi + rx_bcch walk, host buffers).
+One channel cannot fill a GPU; the line exists so that the n = 1 cost of the boundary is on record next to the
+1024-channel numbers of bench.py.  Prints one JSON line."""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "gmr1_rx")
+GPU_BIN = os.path.join(ROOT, "tests", "dropin", "_build", "gmr1_rx_b200")
+SPS = 4
+
+
+def run_app(binary, path, reps):
+    best, bursts = None, 0
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        r = subprocess.run([binary, str(SPS), path], capture_output=True, text=True, timeout=600)
+        dt = time.perf_counter() - t0
+        if r.returncode:
+            return None, 0
+        bursts = sum(1 for l in r.stderr.split("\n") if l.startswith("crc="))
+        best = dt if best is None else min(best, dt)
+    return best, bursts
+
+
+def main():
+    import recording
+    import osmo_gmr_b200
+    L = osmo_gmr_b200.lib()
+
+    def enc(chan, nbits):
+        def f(l2):
+            out = np.zeros(nbits, np.uint8)
+            L.call("gmr1b200_xcch_encode_batch", chan, out, np.ascontiguousarray(l2, np.uint8), 1)
+            return out
+        return f
+
+    x, _ = recording.make(enc(0, 424), enc(1, 432), seconds=2.2, esn0_db=15.0, cfo_hz=300.0, seed=1)
+    d = tempfile.mkdtemp()
+    path = os.path.join(d, "cfg1.cfile")
+    x.tofile(path)
+    out = {"what": "config 1: one 2.2 s single-ARFCN recording, sps 4", "samples": int(len(x))}
+    if os.path.exists(REF_BIN):
+        t, b = run_app(REF_BIN, path, 3)
+        out["reference_app"] = {"wall_s": t, "bursts": b, "bursts_per_s": b / t if t else None, "cores": 1}
+    import torch
+    if not torch.cuda.is_available():
+        print(json.dumps(out))
+        return
+    L.init(0)
+    if os.path.exists(GPU_BIN):
+        t, b = run_app(GPU_BIN, path, 3)
+        out["dropin_app_n1_calls"] = {"wall_s": t, "bursts": b, "bursts_per_s": b / t if t else None,
+                                      "note": "includes process start and CUDA context creation"}
+    # (c) batched entry points on the one recording, host buffers in and out
+    iq = np.ascontiguousarray(x).view(np.float32)
+    n, F = 1, 64
+    rec_ofs, rec_len = np.zeros(1, np.int64), np.array([len(x)], np.int32)
+    W = (330 * 23400 * SPS) // 1000
+    best = None
+    for rep in range(4):
+        t0 = time.perf_counter()
+        align, ferr = np.zeros(1, np.int32), np.zeros(1, np.float32)
+        L.call("gmr1b200_fcch_acquire_batch", 0, iq, len(x), rec_ofs + 8000, 0, W, SPS, None, align, ferr, n, None)
+        align += 8000
+        cnt, cal = np.zeros(1, np.int32), np.zeros((1, 4), np.int32)
+        L.call("gmr1b200_fcch_multi_batch", 0, iq, len(x), rec_ofs, rec_len, align, ferr, SPS, n, 4, cnt, cal, None, None, None)
+        m = int(cnt[0])
+        kind, fn, crc, conv = (np.zeros((m, F), np.int32) for _ in range(4))
+        l2, nfr = np.zeros((m, F, 24), np.uint8), np.zeros(m, np.int32)
+        L.call("gmr1b200_rx_bcch_batch", iq, len(x), np.zeros(m, np.int64), np.full(m, len(x), np.int32),
+               np.ascontiguousarray(cal[0, :m]), np.full(m, ferr[0], np.float32), SPS, m, F,
+               kind, fn, crc, conv, l2, nfr, None, None, None)
+        dt = time.perf_counter() - t0
+        if rep:
+            best = dt if best is None else min(best, dt)
+    b = int((kind > 0).sum())
+    out["batched_api_one_channel"] = {"wall_s": best, "bursts": b, "bursts_per_s": b / best,
+                                      "crc_ok": int(((crc == 0) & (kind > 0)).sum()), "fcch_found": m,
+                                      "note": "warm process; 1.65 MB of IQ copied host to device once per call (three calls)"}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
