@@ -365,7 +365,8 @@ int gmr1b200_fcch_snr_batch(int fcch_type, const float *iq, int64_t iq_len,
  * cand_align [n][max_cand]: alignment in samples from the start of the recording, strongest first: what
  * process_bcch starts from (chan_desc.align, gmr1_rx.c:731), i.e. align0 of gmr1b200_rx_bcch_batch with the
  * primary freq_err[i] as freq_err0.  cand_snr / cand_freq_err [n][max_cand] (linear SNR, fine frequency error in
- * rad/symbol relative to freq_err[i]) may be NULL.  iq may be host or device memory; the per-recording arrays and
+ * rad/symbol relative to freq_err[i]) may be NULL; entries behind the n_fcch[i] survivors are unspecified.
+ * iq may be host or device memory; the per-recording arrays and
  * the outputs are HOST memory (the call synchronises the stream three times per 256 recordings). */
 int gmr1b200_fcch_multi_batch(int fcch_type, const float *iq, int64_t iq_len, const int64_t *rec_ofs,
                               const int32_t *rec_len, const int32_t *align, const float *freq_err, int sps, int n,
