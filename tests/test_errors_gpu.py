@@ -76,7 +76,20 @@ def test_batched_entry_points_reject_malformed_batches(gpu_lib):
     rejected("gmr1b200_rx_bcch_batch", iq, n * wl, np.zeros(n, np.int64), np.full(n, wl, np.int32), np.zeros(n, np.int32), None, SPS, n, 0,
              np.zeros((n, 1), np.int32), np.zeros((n, 1), np.int32), np.zeros((n, 1), np.int32), np.zeros((n, 1), np.int32),
              np.zeros((n, 1, 24), np.uint8), np.zeros(n, np.int32), None, None, None)                                                 # max_frames 0
+    i32 = lambda *shape: np.zeros(shape, np.int32)
+    walk_out = (i32(n, 1), i32(n, 1), i32(n, 1), i32(n, 1), np.zeros((n, 1, 24), np.uint8), i32(n), None, None)
+    rejected("gmr1b200_rx_bcch_ass_batch", iq, n * wl, np.zeros(n, np.int64), np.full(n, wl, np.int32), i32(n), None, SPS, n, 1,
+             *walk_out, None, None, None)                                                                                             # no hand-off record
+    multi = (np.zeros(n, np.int64), np.full(n, wl, np.int32), i32(n), None)
+    rejected("gmr1b200_fcch_multi_batch", 0, iq, n * wl, *multi, SPS, n, 17, i32(n), i32(n, 17), None, None, None)                    # more than 16 candidates
+    rejected("gmr1b200_fcch_multi_batch", 3, iq, n * wl, *multi, SPS, n, 4, i32(n), i32(n, 4), None, None, None)                      # FCCH type
+    rejected("gmr1b200_fcch_multi_batch", 0, iq, n * wl, *multi, SPS, n, 4, None, i32(n, 4), None, None, None)                        # no count output
     assert L.kernel_launches() == before                                             # nothing was launched
+    # recordings shorter than the 650 ms window are flagged one by one, without a launch (gmr1_rx.c:661-665)
+    cnt = np.full(n, 5, np.int32)
+    assert L.call("gmr1b200_fcch_multi_batch", 0, iq, n * wl, *multi, SPS, n, 4, cnt, i32(n, 4), None, None, None) == 0
+    assert (cnt == -errno.EINVAL).all() and L.kernel_launches() == before
+    assert L.call("gmr1b200_fcch_multi_batch", 0, iq, n * wl, *multi, SPS, 0, 4, cnt, i32(n, 4), None, None, None) == 0
     # empty batches are fine and do nothing
     assert L.call("gmr1b200_bcch_decode_batch", l2, eb, None, None, 0, None) == 0
     assert L.call("gmr1b200_pi4cxpsk_demod_batch", 0, iq, n * wl, None, wl, wl, SPS, None, 0.0, eb, 424, None, None, None, None, 0, None) == 0
