@@ -60,11 +60,25 @@ using CodeK9_13 = Code<3, 9, 0x1ed, 0x19b, 0x127>;
 // ---- soft-bit fetch through the gather program -------------------------------------------
 GMR1_HD int sbit_neg(int v) { return (int)(int8_t)(-v); }   // int8 negate, -128 stays -128
 
+// one staged soft bit.  On the device the rows live in shared memory and are read through their 32-bit shared
+// address: with a generic pointer the compiler re-derives the shared window base (S2UR CgaCtaId, ULEA, a move and a
+// three-input add) in front of every one of the 2 x 212 loads of a codeword.
+GMR1_HD int row_ld(const int8_t *row, unsigned idx)
+{
+#ifdef __CUDA_ARCH__
+	int v;
+	asm("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(row) + idx));
+	return v;
+#else
+	return row[idx];
+#endif
+}
+
 GMR1_HD int gather_sbit(const int8_t *row, uint16_t w)
 {
-	if (w == G_ERASED)
+	if (w & 0x8000u)                             // G_ERASED is the only program word with bit 15 set
 		return 0;
-	int v = row[w & G_IDX];
+	int v = row_ld(row, w & G_IDX);
 	return (w & G_FLIP) ? sbit_neg(v) : v;
 }
 
@@ -77,6 +91,15 @@ GMR1_HD void soft_metrics(int is, uint32_t &m0, uint32_t &m1)
 	const int d0 = is - 127, d1 = is + 127;
 	m0 = is ? (uint32_t)((d0 * d0) >> 9) : 0u;
 	m1 = is ? (uint32_t)((d1 * d1) >> 9) : 0u;
+}
+
+// the same as (m0, m1 - m0): (is + 127)^2 = (is - 127)^2 + 508 is, so the second square is one multiply-add on the
+// first, and the difference is 0 for an erased soft bit by itself (no second select)
+GMR1_HD void soft_metrics_rel(int is, uint32_t &m0, uint32_t &d)
+{
+	const int t = is - 127, a = t * t, r0 = a >> 9;
+	d = (uint32_t)(((a + 508 * is) >> 9) - r0);
+	m0 = is ? (uint32_t)r0 : 0u;
 }
 
 // (hi << 1) | (lo >> 31): shifts the sign of lo into hi
@@ -103,17 +126,21 @@ GMR1_HD void acs_step(const uint32_t (&ae)[C::NS], uint32_t (&nae)[C::NS], const
                       uint32_t (&dec)[(C::NS + 31) / 32], uint32_t &off)
 {
 	constexpr int N = C::N, NS = C::NS, H = NS / 2;
-	uint32_t m0[N], m1[N];
+	uint32_t m0[N], m1[N];                       // REL: m1 holds m1 - m0
 #pragma unroll
-	for (int j = 0; j < N; j++)
-		soft_metrics(v[j], m0[j], m1[j]);
+	for (int j = 0; j < N; j++) {
+		if (REL)
+			soft_metrics_rel(v[j], m0[j], m1[j]);
+		else
+			soft_metrics(v[j], m0[j], m1[j]);
+	}
 	// all 2^N branch sums, built by doubling (entries that no transition uses are dead code)
 	uint32_t bm[1 << N];
 	bm[0] = 0;
 	if (REL) {
 #pragma unroll
 		for (int j = 0; j < N; j++) {
-			const uint32_t dj = m1[j] - m0[j];
+			const uint32_t dj = m1[j];
 			off += m0[j];
 #pragma unroll
 			for (int o = (1 << j) - 1; o >= 0; o--) {
