@@ -54,6 +54,13 @@ template <> struct ChanCode<CH_TCH3>     { using type = CodeK7_12; };
 template <> struct ChanCode<CH_DC12>     { using type = CodeK9_13; };
 
 // bytes of packed L2 each unit produces
+// channels whose gather program has erased (punctured) positions; the others are verified to have none when the
+// tables are built (gmr1_tables.cpp: check_no_erasures)
+GMR1_HD constexpr bool chan_has_erasures(int ch)
+{
+	return !(ch == CH_BCCH || ch == CH_CCCH || ch == CH_FACCH3 || ch == CH_FACCH9);
+}
+
 GMR1_HD constexpr int chan_l2_bytes(int ch)
 {
 	return ch == CH_BCCH || ch == CH_CCCH || ch == CH_DC12 ? 24 :
@@ -142,8 +149,9 @@ GMR1_HD void decode_unit_k5(const TabRef &tb, const DecodeArgs &a, int unit,
 
 	// path metrics relative to the all-zero branch of every step (acs_step REL): `off` is what they lack
 	uint32_t off = 0;
-	forward<C, false, true, CH == CH_RACH, true>(ae, row, tb.g, tb.g2, 0, tb.len, dec, T, t, off);
-	forward<C, true,  true, CH == CH_RACH, true>(ae, row, tb.g, tb.g2, tb.len, C::K - 1, dec, T, t, off);
+	constexpr bool ER = chan_has_erasures(CH);
+	forward<C, false, true, CH == CH_RACH, true, ER>(ae, row, tb.g, tb.g2, 0, tb.len, dec, T, t, off);
+	forward<C, true,  true, CH == CH_RACH, true, ER>(ae, row, tb.g, tb.g2, tb.len, C::K - 1, dec, T, t, off);
 
 	if (a.conv)
 		a.conv[unit] = (int32_t)(ae[0] + off);

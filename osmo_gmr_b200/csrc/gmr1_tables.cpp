@@ -12,6 +12,8 @@
 // Nothing here is executed per burst: tables are built once and uploaded to __constant__.
 #include "gmr1_tables.h"
 
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <mutex>
 #include <vector>
@@ -295,7 +297,28 @@ static void build_all()
 	}
 }
 
-static void ensure() { std::call_once(g_once, build_all); }
+// The decode kernels of these four channels are compiled without the erased-position test (decode_unit.cuh:
+// chan_has_erasures): their programs must cover every coded bit of every trellis step.
+static void check_no_erasures()
+{
+	const int chans[4] = {CH_BCCH, CH_CCCH, CH_FACCH3, CH_FACCH9};
+	for (int c : chans) {
+		const ChanTab &t = g_chan[c];
+		for (int i = 0; i < t.n_steps * t.N; i++)
+			if (t.g[i] == G_ERASED) {
+				fprintf(stderr, "gmr1_tables: channel %d has an erased position at coded bit %d\n", c, i);
+				abort();
+			}
+	}
+}
+
+static void ensure()
+{
+	std::call_once(g_once, [] {
+		build_all();
+		check_no_erasures();
+	});
+}
 
 const ChanTab &chan_tab(int ch) { ensure(); return g_chan[ch]; }
 const uint8_t *scramble_seq() { ensure(); return g_scr; }

@@ -74,9 +74,12 @@ GMR1_HD int row_ld(const int8_t *row, unsigned idx)
 #endif
 }
 
+// ERASE = false: the program of this channel has no erased (punctured) position - checked when the tables are
+// built, gmr1_tables.cpp - so the test (a uniform branch in front of every load) is compiled out
+template <bool ERASE = true>
 GMR1_HD int gather_sbit(const int8_t *row, uint16_t w)
 {
-	if (w & 0x8000u)                             // G_ERASED is the only program word with bit 15 set
+	if (ERASE && (w & 0x8000u))                  // G_ERASED is the only program word with bit 15 set
 		return 0;
 	int v = row_ld(row, w & G_IDX);
 	return (w & G_FLIP) ? sbit_neg(v) : v;
@@ -208,12 +211,12 @@ template <> struct DecWord<16> { using type = uint16_t; };
 
 // ---- forward pass over n steps ------------------------------------------------------------
 // g: gather program (N words per step), g2: optional second source averaged in (RACH)
-template <class C, bool HAS_G2>
+template <class C, bool HAS_G2, bool ERASE = true>
 GMR1_HD void fetch_inputs(int (&v)[C::N], const int8_t *row, const uint16_t *g, const uint16_t *g2, int i)
 {
 #pragma unroll
 	for (int j = 0; j < C::N; j++) {
-		int s = gather_sbit(row, g[i * C::N + j]);
+		int s = gather_sbit<ERASE>(row, g[i * C::N + j]);
 		if (HAS_G2) {
 			const uint16_t w2 = g2[i * C::N + j];
 			if (w2 != G_ERASED)
@@ -234,7 +237,7 @@ GMR1_HD void store_dec(const uint32_t (&dec)[(C::NS + 31) / 32], typename DecWor
 	}
 }
 
-template <class C, bool FLUSH_STEP, bool STORE, bool HAS_G2, bool REL = false>
+template <class C, bool FLUSH_STEP, bool STORE, bool HAS_G2, bool REL = false, bool ERASE = true>
 GMR1_HD void forward(uint32_t (&ae)[C::NS], const int8_t *row, const uint16_t *g, const uint16_t *g2,
                      int step0, int nsteps, typename DecWord<C::NS>::type *dec_base, int T, int t, uint32_t &off)
 {
@@ -245,17 +248,17 @@ GMR1_HD void forward(uint32_t (&ae)[C::NS], const int8_t *row, const uint16_t *g
 	for (; i + 1 < end; i += 2) {           // two steps per iteration: ae -> tmp -> ae
 		int v[C::N];
 		uint32_t dec[DW];
-		fetch_inputs<C, HAS_G2>(v, row, g, g2, i);
+		fetch_inputs<C, HAS_G2, ERASE>(v, row, g, g2, i);
 		acs_step<C, FLUSH_STEP, REL>(ae, tmp, v, dec, off);
 		store_dec<C, STORE>(dec, dec_base, T, t, i);
-		fetch_inputs<C, HAS_G2>(v, row, g, g2, i + 1);
+		fetch_inputs<C, HAS_G2, ERASE>(v, row, g, g2, i + 1);
 		acs_step<C, FLUSH_STEP, REL>(tmp, ae, v, dec, off);
 		store_dec<C, STORE>(dec, dec_base, T, t, i + 1);
 	}
 	if (i < end) {
 		int v[C::N];
 		uint32_t dec[DW];
-		fetch_inputs<C, HAS_G2>(v, row, g, g2, i);
+		fetch_inputs<C, HAS_G2, ERASE>(v, row, g, g2, i);
 		acs_step<C, FLUSH_STEP, REL>(ae, tmp, v, dec, off);
 		store_dec<C, STORE>(dec, dec_base, T, t, i);
 #pragma unroll
