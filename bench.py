@@ -548,11 +548,11 @@ def run_gpu_arm(args):
     alu_peak = sms * 128 * 1.965e9            # int32 lane-ops/s at the max SM clock (128 lanes per SM)
     viterbi = {"kernel": "decode_tpc_kernel<BCCH|CCCH>", "codewords_per_s": dec_cw / (dec_ms * 1e-3),
                "acs_state_updates_per_s": 3392 * dec_cw / (dec_ms * 1e-3), "ms_per_launch": dec_ms / len(dec),
-               "thread_instr_per_state_update": 8.1,
-               "frac_of_int32_issue_peak": 8.1 * 3392 * dec_cw / (dec_ms * 1e-3) / alu_peak,
-               "note": "8.1 thread-instructions per state update all-in (gather, ACS, traceback, CRC, packing): 9.1 from ncu "
-                       "smsp__inst_executed on the previous build, less the 3 504 of 30 867 instructions per codeword that "
-                       "left the trellis loops since (static SASS count, 270 -> 237 per two steps); "
+               "thread_instr_per_state_update": 7.8,
+               "frac_of_int32_issue_peak": 7.8 * 3392 * dec_cw / (dec_ms * 1e-3) / alu_peak,
+               "note": "7.8 thread-instructions per state update all-in (gather, ACS, traceback, CRC, packing): 9.1 from ncu "
+                       "smsp__inst_executed on an earlier build, less the 4 564 of 30 867 instructions per codeword that "
+                       "left the trellis loops since (static SASS count, 270 -> 227 per two steps); "
                        "peak = SMs x 128 lanes x 1.965 GHz"}
 
     # ---------------- CPU baseline leg (rank 0, N = 1): reference C path on a bounded sample + parity
