@@ -62,3 +62,66 @@ def make(enc_bcch, enc_ccch, seconds=2.2, esn0_db=15.0, cfo_hz=300.0, frac=0.37,
     sig = 10.0 ** (-esn0_db / 20.0) / np.sqrt(2.0)
     x += sig * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
     return x.astype(np.complex64), truth
+
+
+def make_call(enc_bcch, enc_ccch, enc_speech, enc_facch3, plan, tn=7, p=3, ass_frame=3, kc=None, a5=None,
+              seconds=2.6, esn0_db=22.0, cfo_hz=100.0, frac=0.37, start=9000, seed=1):
+    """A BCCH recording whose CCCH burst in frame `ass_frame` is an IMMEDIATE ASSIGNMENT to timeslot `tn` with DKAB
+    position `p`, and the traffic-channel recording that goes with it (same clock: same length, carrier offset,
+    timing) - what `gmr1_rx sps bcch.cfile tch.cfile [key]` takes (src/gmr1_rx.c:538-600, rx_tch3).
+
+    plan: one character per frame from ass_frame on: 's' NT3 speech burst, 'f' NT3 FACCH3 burst (a codeword is four
+    consecutive 'f' frames starting where fn & 3 == 0), 'd' DKAB, '-' nothing.  Every FACCH3 burst carries sync
+    sequence 1: the reference's sync search never clears its accumulator between candidate sequences
+    (pi4cxpsk.c:207,232), so it always answers the last candidate and cannot demodulate a burst sent with sequence 0.
+    enc_speech(frame0[10], frame1[10], bits_s[4], ciph[208] or None) -> 212 hard bits;
+    enc_facch3(l2[10], bits_s[32], ciph[384] or None) -> 416 hard bits.  a5(kc, fn, nbits) -> cipher bits when the
+    FACCH3 codewords and the speech bursts after the first FACCH3 are to be ciphered (kc given).
+    Returns (bcch samples, tch samples, truth) with truth = list of (frame, kind, payload)."""
+    bcch, truth = make(enc_bcch, enc_ccch, seconds=seconds, esn0_db=esn0_db, cfo_hz=cfo_hz, frac=frac, start=start,
+                       seed=seed, imm_ass={ass_frame: (tn, p)})
+    rng = np.random.default_rng(seed + 1000)
+    n = len(bcch)
+    x = np.zeros(n, np.complex128)
+    ofs = SPS * tn * 39
+    sync_id, group, ciphered = 1, None, False
+    for k, what in enumerate(plan):
+        f = ass_frame + k
+        pos = start + f * FRAME + ofs
+        if pos + 117 * SPS + 64 > n:
+            break
+        if what == "s":
+            f0, f1 = rng.integers(0, 256, 10, dtype=np.uint8), rng.integers(0, 256, 10, dtype=np.uint8)
+            f0[6:] &= 0; f1[6:] &= 0                       # keep to the 48 protected bits: bytes 6..9 are class 2
+            bs = rng.integers(0, 2, 4, dtype=np.uint8)
+            c = a5(kc, f, 208) if (kc is not None and ciphered) else None
+            hard = enc_speech(f0, f1, bs, c)
+            w = sigen.modulate("nt3_speech", hard[None, :], SPS, 32, 16.0 + frac, 0.0, 0.0, 200.0, rng)[0]
+            truth.append((f, "tch3", (f0, f1)))
+        elif what == "f":
+            bi = f & 3
+            if bi == 0 or group is None:
+                l2 = rng.integers(0, 256, 10, dtype=np.uint8)
+                l2[3] = 0x01                               # never an ASSIGNMENT COMMAND 1 (gmr1_rx.c:247-251)
+                bs = rng.integers(0, 2, 32, dtype=np.uint8)
+                c = None
+                if kc is not None:
+                    c = np.concatenate([a5(kc, f - bi + i, 96) for i in range(4)])
+                group = (enc_facch3(l2, bs, c), l2)
+            hard = group[0][104 * bi:104 * bi + 104]
+            w = sigen.modulate("nt3_facch", hard[None, :], SPS, 32, 16.0 + frac, 0.0, 0.0, 200.0, rng, sync_id=sync_id)[0]
+            if bi == 3:
+                truth.append((f, "facch3", group[1]))
+                group = None
+                ciphered = kc is not None
+        elif what == "d":
+            w = sigen.modulate_symbols(sigen.dkab_symbols(1, p, rng), SPS, 32, 16.0 + frac, 0.0, 0.0, 200.0, rng)[0]
+            truth.append((f, "dkab", None))
+        else:
+            continue
+        x[pos - 16:pos - 16 + len(w)] += w
+    cfo = 2 * np.pi * cfo_hz / 23400.0
+    x *= np.exp(1j * (cfo * np.arange(n) / SPS + 0.7))
+    sig = 10.0 ** (-esn0_db / 20.0) / np.sqrt(2.0)
+    x += sig * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    return bcch, x.astype(np.complex64), truth
