@@ -49,3 +49,15 @@ extern "C" int gmr1_emu_decode(int ch, const DecodeArgs *a)
 extern "C" int gmr1_emu_keep_mask(int ch, uint8_t *mask, int max) { return chan_keep_mask(ch, mask, max); }
 extern "C" int gmr1_emu_code_output(int ch, int state, int bit) { return code_output(chan_code(ch), state, bit); }
 extern "C" int gmr1_emu_sizeof_args() { return (int)sizeof(DecodeArgs); }
+
+// ---- TCH3 burst-loop state machine (osmo_gmr_b200/csrc/tch3_state.cuh) -------------------------------
+#include "tch3_state.cuh"
+extern "C" int gmr1_emu_tch3_sizeof() { return (int)sizeof(Tch3State); }
+extern "C" void gmr1_emu_tch3_init(Tch3State *s, int8_t *eb, const uint8_t *imm_ass, float ref) { tch3_init(*s, eb, imm_ass, ref); }
+extern "C" int gmr1_emu_tch3_gate(Tch3State *s, float be) { return tch3_gate(*s, be); }
+extern "C" int gmr1_emu_tch3_dkab_result(Tch3State *s, float be, int rv) { return tch3_dkab_result(*s, be, rv); }
+extern "C" int gmr1_emu_tch3_facch_flush_before(const Tch3State *s, int sync_id) { return tch3_facch_flush_before(*s, sync_id); }
+extern "C" int gmr1_emu_tch3_facch_store(Tch3State *s, int8_t *eb, const int8_t *b, int sync_id, uint32_t fn) { return tch3_facch_store(*s, eb, b, sync_id, fn); }
+extern "C" int gmr1_emu_tch3_flush_first_try_ciphered(const Tch3State *s) { return tch3_flush_first_try_ciphered(*s); }
+extern "C" int gmr1_emu_tch3_flush_wants_retry(const Tch3State *s, int crc) { return tch3_flush_wants_retry(*s, crc); }
+extern "C" int gmr1_emu_tch3_flush_done(Tch3State *s, int8_t *eb, int crc, int retried) { return tch3_flush_done(*s, eb, crc, retried != 0); }
