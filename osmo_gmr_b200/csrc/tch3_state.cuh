@@ -4,6 +4,7 @@
 //   rx_tch3               :538-600                energy gate DKAB / burst, running energy averages, release
 //   _rx_tch3_facch        :455-494                FACCH3 codeword assembly over four frames
 //   _rx_tch3_facch_flush  :394-452                plain / ciphered decode attempts, cipher discovery, group reset
+//   rx_tch9_init, rx_tch9 :264-355                hand-off to the TCH9 loop by an ASSIGNMENT COMMAND 1, FACCH9 / TCH9 split
 // The signal processing between the decisions (burst_energy, gmr1_dkab_demod, gmr1_pi4cxpsk_detect / _demod, gmr1_a5,
 // gmr1_facch3_decode, gmr1_tch3_decode) is the batched kernels of this library.  These functions are what the state
 // kernels of the device-side loop run per channel; tests/test_tch3_state_emu.py runs this very code on the CPU, next to
@@ -119,6 +120,36 @@ GMR1_HD bool tch3_flush_done(Tch3State &s, int8_t *ebits, int crc, bool retried)
 	for (int i = 0; i < 4 * 104; i++)
 		ebits[i] = 0;
 	return crc == 0;
+}
+
+// ---- hand-off to the TCH9 burst loop (rx_tch9_init :264-275, facch3_is_ass_cmd_1 / facch3_ass_cmd_1_parse :247-257) ----
+struct Tch9State {                     // struct tch9_state, gmr1_rx.c:81-90 (the interleaver history lives beside it)
+	int32_t active, tn;
+};
+
+GMR1_HD bool facch3_is_ass_cmd_1(const uint8_t *l2) { return l2[3] == 0x06 && l2[4] == 0x2e; }
+
+// a good FACCH3 message that is an ASSIGNMENT COMMAND 1 starts the TCH9 loop on the timeslot it names (the caller
+// also resets the channel's depth-3 interleaver history, gmr1_interleaver_init :273)
+GMR1_HD bool tch9_init_from_facch3(Tch9State &s, const uint8_t *l2, bool crc_ok)
+{
+	if (!crc_ok || !facch3_is_ass_cmd_1(l2))
+		return false;
+	s.active = 1;
+	s.tn = ((l2[5] & 0x03) << 3) | (l2[6] >> 5);
+	return true;
+}
+
+// rx_tch9 :305-352: sync sequence 0 of the NT9 burst marks a FACCH9 message, anything else a TCH9 block; `avg` is the
+// mean soft-bit magnitude the reference prints with a TCH9 block
+GMR1_HD bool tch9_is_facch9(int sync_id) { return sync_id == 0; }
+
+GMR1_HD int tch9_avg_magnitude(const int8_t *ebits)
+{
+	int s = 0;
+	for (int i = 0; i < 662; i++)
+		s += ebits[i] < 0 ? -(int)ebits[i] : (int)ebits[i];
+	return s / 662;
 }
 
 }  // namespace gmr1

@@ -61,3 +61,6 @@ extern "C" int gmr1_emu_tch3_facch_store(Tch3State *s, int8_t *eb, const int8_t 
 extern "C" int gmr1_emu_tch3_flush_first_try_ciphered(const Tch3State *s) { return tch3_flush_first_try_ciphered(*s); }
 extern "C" int gmr1_emu_tch3_flush_wants_retry(const Tch3State *s, int crc) { return tch3_flush_wants_retry(*s, crc); }
 extern "C" int gmr1_emu_tch3_flush_done(Tch3State *s, int8_t *eb, int crc, int retried) { return tch3_flush_done(*s, eb, crc, retried != 0); }
+extern "C" int gmr1_emu_tch9_init_from_facch3(Tch9State *s, const uint8_t *l2, int crc_ok) { return tch9_init_from_facch3(*s, l2, crc_ok != 0); }
+extern "C" int gmr1_emu_tch9_is_facch9(int sync_id) { return tch9_is_facch9(sync_id); }
+extern "C" int gmr1_emu_tch9_avg_magnitude(const int8_t *eb) { return tch9_avg_magnitude(eb); }

@@ -65,7 +65,8 @@ def make(enc_bcch, enc_ccch, seconds=2.2, esn0_db=15.0, cfo_hz=300.0, frac=0.37,
 
 
 def make_call(enc_bcch, enc_ccch, enc_speech, enc_facch3, plan, tn=7, p=3, ass_frame=3, kc=None, a5=None,
-              seconds=2.6, esn0_db=22.0, cfo_hz=100.0, frac=0.37, start=9000, seed=1):
+              seconds=2.6, esn0_db=22.0, cfo_hz=100.0, frac=0.37, start=9000, seed=1,
+              csd=None):
     """A BCCH recording whose CCCH burst in frame `ass_frame` is an IMMEDIATE ASSIGNMENT to timeslot `tn` with DKAB
     position `p`, and the traffic-channel recording that goes with it (same clock: same length, carrier offset,
     timing) - what `gmr1_rx sps bcch.cfile tch.cfile [key]` takes (src/gmr1_rx.c:538-600, rx_tch3).
@@ -77,7 +78,12 @@ def make_call(enc_bcch, enc_ccch, enc_speech, enc_facch3, plan, tn=7, p=3, ass_f
     enc_speech(frame0[10], frame1[10], bits_s[4], ciph[208] or None) -> 212 hard bits;
     enc_facch3(l2[10], bits_s[32], ciph[384] or None) -> 416 hard bits.  a5(kc, fn, nbits) -> cipher bits when the
     FACCH3 codewords and the speech bursts after the first FACCH3 are to be ciphered (kc given).
-    Returns (bcch samples, tch samples, truth) with truth = list of (frame, kind, payload)."""
+    csd = (codeword, tn9, plan9, enc_tch9): the FACCH3 codeword number `codeword` (0 = first) carries an ASSIGNMENT
+    COMMAND 1 to timeslot tn9 (facch3_is_ass_cmd_1 / facch3_ass_cmd_1_parse, gmr1_rx.c:247-257), and a third recording
+    carries what plan9 says per frame from the frame after that codeword on: 't' = NT9 burst with a TCH9 block
+    (enc_tch9(fn) -> 662 hard bits, ciphered and interleaved by the caller's closure), '-' nothing (rx_tch9 :281-355).
+    Returns (bcch samples, tch samples, truth) with truth = list of (frame, kind, payload); with csd, a fourth
+    element: the csd samples."""
     bcch, truth = make(enc_bcch, enc_ccch, seconds=seconds, esn0_db=esn0_db, cfo_hz=cfo_hz, frac=frac, start=start,
                        seed=seed, imm_ass={ass_frame: (tn, p)})
     rng = np.random.default_rng(seed + 1000)
@@ -85,6 +91,7 @@ def make_call(enc_bcch, enc_ccch, enc_speech, enc_facch3, plan, tn=7, p=3, ass_f
     x = np.zeros(n, np.complex128)
     ofs = SPS * tn * 39
     sync_id, group, ciphered = 1, None, False
+    n_group, csd_from = 0, None
     for k, what in enumerate(plan):
         f = ass_frame + k
         pos = start + f * FRAME + ofs
@@ -103,6 +110,12 @@ def make_call(enc_bcch, enc_ccch, enc_speech, enc_facch3, plan, tn=7, p=3, ass_f
             if bi == 0 or group is None:
                 l2 = rng.integers(0, 256, 10, dtype=np.uint8)
                 l2[3] = 0x01                               # never an ASSIGNMENT COMMAND 1 (gmr1_rx.c:247-251)
+                if csd and n_group == csd[0]:
+                    l2[3], l2[4] = 0x06, 0x2e
+                    l2[5] = (l2[5] & 0xfc) | ((csd[1] >> 3) & 0x03)
+                    l2[6] = ((csd[1] & 0x07) << 5) | (l2[6] & 0x1f)
+                    csd_from = f - bi + 4
+                n_group += 1
                 bs = rng.integers(0, 2, 32, dtype=np.uint8)
                 c = None
                 if kc is not None:
@@ -121,7 +134,19 @@ def make_call(enc_bcch, enc_ccch, enc_speech, enc_facch3, plan, tn=7, p=3, ass_f
             continue
         x[pos - 16:pos - 16 + len(w)] += w
     cfo = 2 * np.pi * cfo_hz / 23400.0
-    x *= np.exp(1j * (cfo * np.arange(n) / SPS + 0.7))
+    rot = np.exp(1j * (cfo * np.arange(n) / SPS + 0.7))
     sig = 10.0 ** (-esn0_db / 20.0) / np.sqrt(2.0)
-    x += sig * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
-    return bcch, x.astype(np.complex64), truth
+    x = x * rot + sig * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    if not csd:
+        return bcch, x.astype(np.complex64), truth
+    y = np.zeros(n, np.complex128)
+    for k, what in enumerate(csd[2]):
+        f = csd_from + k
+        pos = start + f * FRAME + SPS * csd[1] * 39
+        if what != "t" or pos + 351 * SPS + 64 > n:
+            continue
+        w = sigen.modulate("nt9", csd[3](f)[None, :], SPS, 32, 16.0 + frac, 0.0, 0.0, 200.0, rng, sync_id=1)[0]
+        y[pos - 16:pos - 16 + len(w)] += w
+        truth.append((f, "tch9", None))
+    y = y * rot + sig * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    return bcch, x.astype(np.complex64), truth, y.astype(np.complex64)

@@ -41,7 +41,11 @@ def _roundf(t):
     return int(np.sign(t) * np.floor(abs(t) + 0.5))
 
 
-def _walk(o, emu, bcch, tch, kc):
+class Tch9State(ctypes.Structure):
+    _fields_ = [("active", ctypes.c_int32), ("tn", ctypes.c_int32)]
+
+
+def _walk(o, emu, bcch, tch, kc, csd=None):
     P = ctypes.c_void_p
     ptr = lambda a: a.ctypes.data_as(P)
     emu.gmr1_emu_tch3_gate.argtypes = [P, ctypes.c_float]
@@ -53,8 +57,12 @@ def _walk(o, emu, bcch, tch, kc):
     emu.gmr1_emu_tch3_flush_wants_retry.argtypes = [P, ctypes.c_int]
     emu.gmr1_emu_tch3_flush_done.argtypes = [P, P, ctypes.c_int, ctypes.c_int]
     assert emu.gmr1_emu_tch3_sizeof() == ctypes.sizeof(Tch3State)
+    emu.gmr1_emu_tch9_init_from_facch3.argtypes = [P, P, ctypes.c_int]
+    emu.gmr1_emu_tch9_avg_magnitude.argtypes = [P]
     st = Tch3State()
     sp = ctypes.addressof(st)
+    t9 = Tch9State()
+    il = o.interleaver()
     store = np.zeros(416, np.int8)
     (align, ferr), = _acquire_like_main(o, bcch)
     ferr = np.float32(ferr)
@@ -64,13 +72,15 @@ def _walk(o, emu, bcch, tch, kc):
     def flush(rec):
         masks = lambda: np.concatenate([o.a5(1, kc, int(st.bi_fn[i]), 96) for i in range(4)])
         ciph = masks() if emu.gmr1_emu_tch3_flush_first_try_ciphered(sp) else None
-        _, _, crc, conv = o.facch3_decode(store, ciph)
+        l2, _, crc, conv = o.facch3_decode(store, ciph)
         rec["flush"].append((crc, conv))
         retried = bool(emu.gmr1_emu_tch3_flush_wants_retry(sp, crc))
         if retried:
-            _, _, crc, conv = o.facch3_decode(store, masks())
+            l2, _, crc, conv = o.facch3_decode(store, masks())
             rec["flush"].append((crc, conv))
-        emu.gmr1_emu_tch3_flush_done(sp, ptr(store), crc, int(retried))
+        good = emu.gmr1_emu_tch3_flush_done(sp, ptr(store), crc, int(retried))
+        if csd is not None and emu.gmr1_emu_tch9_init_from_facch3(ctypes.addressof(t9), ptr(l2), good):   # :436-441
+            o.c.gmr1_interleaver_init(ctypes.byref(il), 3, 648)
 
     while True:
         rec = {"fn": fn, "kind": None, "crc": None, "conv": None, "tch": None, "flush": [], "assigned": None, "end": False}
@@ -126,6 +136,21 @@ def _walk(o, emu, bcch, tch, kc):
                         ciph = o.a5(st.ciph, kc, fn, 208)
                         f0, f1, _, c0, c1 = o.tch3_decode(eb, ciph, 0)
                         rec.update(frame0=bytes(f0), frame1=bytes(f1), conv0=c0, conv1=c1)
+        if t9.active:                                           # rx_tch9 :281-355
+            begin = align + SPS * t9.tn * 39 - 3
+            if begin + 1410 <= len(bcch):
+                w = csd[begin:begin + 1410]
+                rc, eb, sid, _, _ = o.demod("nt9", w, SPS, -ferr)
+                ciph = o.a5(1, kc, fn, 658)
+                rec["csd_sync"] = sid
+                if emu.gmr1_emu_tch9_is_facch9(sid):
+                    rec["csd"] = "facch9"
+                    _, _, _, crc, conv = o.facch9_decode(eb, ciph)
+                    rec.update(csd_crc=crc, csd_conv=conv)
+                else:
+                    rec["csd"] = "tch9"
+                    _, _, _, conv = o.tch9_decode(eb, 2, ciph, il)
+                    rec.update(conv9=conv, avg=emu.gmr1_emu_tch9_avg_magnitude(ptr(eb)))
         frames.append(rec)
         fn += 1
         align += FRAME
@@ -177,3 +202,55 @@ def test_state_machine_follows_the_reference_application(oracle, emu, tmp_path, 
         # (rate 1/4: each burst carries one generator's output) that decodes with a large metric
         assert any(e["flush"] and e["flush"][-1][0] != 0 for e in ref)
         assert any(e["flush"] and e["flush"][-1] != (0, 0) and e["flush"][-1][0] == 0 and e["flush"][-1][1] > 1000 for e in ref)
+
+
+def test_tch9_hand_off_follows_the_reference_application(oracle, emu, tmp_path):
+    """the same walk through an ASSIGNMENT COMMAND 1 on the FACCH3 into the TCH9 loop (rx_tch9_init / rx_tch9,
+    gmr1_rx.c:264-355): the reference application, given the third recording, starts the TCH9 loop in the frame the
+    command's codeword completes, on the timeslot it names, and reports the same Viterbi metric and soft-bit magnitude
+    for every frame from there on (bursts, silence, interleaver refill) as the product's state functions driving the
+    reference's signal processing."""
+    if not os.path.exists(REF_BIN):
+        pytest.skip("oracle/_ref/gmr1_rx not built (needs /root/reference at build time)")
+    import osmo_gmr_b200
+    L = osmo_gmr_b200.lib()
+
+    def enc_speech(f0, f1, bs, c):
+        out = np.zeros(212, np.uint8)
+        L.call("gmr1b200_tch3_encode", out, np.ascontiguousarray(f0), np.ascontiguousarray(f1),
+               np.ascontiguousarray(bs), c, 0)
+        return out
+
+    key = "0123456789abcdef"
+    kc = np.frombuffer(bytes.fromhex(key), np.uint8)
+    il_tx = oracle.interleaver()
+    rng = np.random.default_rng(3)
+
+    def enc_tch9(fn):
+        return oracle.tch9_encode(rng.integers(0, 256, 60, dtype=np.uint8), 2, rng.integers(0, 2, 10, dtype=np.uint8),
+                                  rng.integers(0, 2, 4, dtype=np.uint8), oracle.a5(1, kc, fn, 658), il_tx)
+
+    plan = "sssss" + "ffff" + "ssds" + "s" * 12 + "-" * 12
+    b, t, _, c = recording.make_call(lambda l2: oracle.encode("bcch", 424, l2), lambda l2: oracle.encode("ccch", 432, l2),
+                                     enc_speech, lambda l2, bs, cc: oracle.facch3_encode(l2, bs, cc), plan, tn=7, p=3,
+                                     ass_frame=3, kc=kc, a5=lambda k, fn, n: oracle.a5(1, k, fn, n), seed=5,
+                                     csd=(0, 12, "tttttt-tttt", enc_tch9))
+    paths = [str(tmp_path / f"{nm}.cfile") for nm in ("bcch", "tch", "csd")]
+    for path, x in zip(paths, (b, t, c)):
+        x.tofile(path)
+    r = subprocess.run([REF_BIN, "4", paths[0], paths[1], key, paths[2]], capture_output=True, text=True, timeout=300)
+    if os.path.exists("/tmp/csd.data"):              # the reference application dumps the TCH9 blocks there (gmr1_rx.c:340-346)
+        os.unlink("/tmp/csd.data")
+    assert r.returncode == 0, r.stderr[-2000:]
+    ref = rxlog.parse(r.stderr.split("\n"))
+    got = _walk(oracle, emu, b, t, kc, csd=c)
+    assert len(got) == len(ref)
+    keys = ("fn", "kind", "crc", "conv", "tch", "flush", "assigned", "end", "frame0", "frame1",
+            "csd", "csd_sync", "conv9", "avg", "csd_crc", "csd_conv")
+    for g, e in zip(got, ref):
+        for k in keys:
+            assert g.get(k) == e.get(k), (g["fn"], k, g.get(k), e.get(k))
+    first = min(e["fn"] for e in ref if e.get("csd"))
+    assert first == 11 and all(e.get("csd") for e in ref if e["fn"] >= first)      # codeword 0 = frames 8..11
+    good = [e["conv9"] for e in ref if e.get("conv9") is not None and e["conv9"] < 50]
+    assert len(good) >= 6                                                          # blocks decoded through the cipher and the interleaver
