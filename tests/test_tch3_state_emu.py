@@ -254,3 +254,38 @@ def test_tch9_hand_off_follows_the_reference_application(oracle, emu, tmp_path):
     assert first == 11 and all(e.get("csd") for e in ref if e["fn"] >= first)      # codeword 0 = frames 8..11
     good = [e["conv9"] for e in ref if e.get("conv9") is not None and e["conv9"] < 50]
     assert len(good) >= 6                                                          # blocks decoded through the cipher and the interleaver
+
+
+def test_state_functions_compile_for_the_device(tmp_path):
+    """the same header through nvcc for sm_100a (cross-compiled, no GPU needed): every state function instantiated in
+    a kernel, and no fused multiply-add in the running averages (the reference rounds the two products separately)"""
+    import shutil
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not found")
+    src = tmp_path / "t3.cu"
+    src.write_text('''
+#include "viterbi_tpc.cuh"
+#include "tch3_state.cuh"
+using namespace gmr1;
+__global__ void k(Tch3State *s, Tch9State *s9, int8_t *eb, const int8_t *b, const uint8_t *l2, const float *be, int *out, int n)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	tch3_init(s[i], eb + 416 * i, l2 + 24 * i, be[i]);
+	int r = tch3_gate(s[i], be[i]);
+	r += tch3_dkab_result(s[i], be[i], r & 1);
+	r += tch3_facch_flush_before(s[i], r & 1);
+	r += tch3_facch_store(s[i], eb + 416 * i, b + 104 * i, 1, (uint32_t)i);
+	r += tch3_flush_first_try_ciphered(s[i]) + tch3_flush_wants_retry(s[i], r & 1);
+	r += tch3_flush_done(s[i], eb + 416 * i, r & 1, true);
+	r += tch9_init_from_facch3(s9[i], l2 + 24 * i, true) + tch9_is_facch9(r & 1) + tch9_avg_magnitude(b + 662 * i);
+	out[i] = r;
+}
+''')
+    csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "osmo_gmr_b200", "csrc")
+    obj = str(tmp_path / "t3.o")
+    subprocess.check_call([nvcc, "-std=c++17", "--expt-relaxed-constexpr", "-gencode", "arch=compute_100a,code=sm_100a",
+                           "-I" + csrc, "-c", str(src), "-o", obj])
+    sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
+    assert "FMUL" in sass and "FFMA" not in sass
