@@ -289,3 +289,42 @@ __global__ void k(Tch3State *s, Tch9State *s9, int8_t *eb, const int8_t *b, cons
                            "-I" + csrc, "-c", str(src), "-o", obj])
     sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
     assert "FMUL" in sass and "FFMA" not in sass
+
+
+@pytest.mark.parametrize("seed", range(1, 9))
+def test_random_calls_follow_the_reference_application(oracle, emu, tmp_path, seed):
+    """random traffic plans, timeslots, DKAB positions, Es/N0 (10 / 14 / 22 dB) and carrier offsets, ciphered: whatever
+    the reference application makes of such a call (including what it misclassifies while its thresholds settle), the
+    walk driven by the product's state functions makes the same of it, frame for frame"""
+    if not os.path.exists(REF_BIN):
+        pytest.skip("oracle/_ref/gmr1_rx not built (needs /root/reference at build time)")
+    import osmo_gmr_b200
+    L = osmo_gmr_b200.lib()
+
+    def enc_speech(f0, f1, bs, c):
+        out = np.zeros(212, np.uint8)
+        L.call("gmr1b200_tch3_encode", out, np.ascontiguousarray(f0), np.ascontiguousarray(f1),
+               np.ascontiguousarray(bs), c, 0)
+        return out
+
+    key = "a1b2c3d4e5f60718"
+    kc = np.frombuffer(bytes.fromhex(key), np.uint8)
+    rng = np.random.default_rng(seed)
+    plan = "".join(rng.choice(list("sssfd-"), 34)) + "-" * 11
+    esn0, cfo = float(rng.choice([10.0, 14.0, 22.0])), float(rng.uniform(-400, 400))
+    b, t, _ = recording.make_call(lambda l2: oracle.encode("bcch", 424, l2), lambda l2: oracle.encode("ccch", 432, l2),
+                                  enc_speech, lambda l2, bs, c: oracle.facch3_encode(l2, bs, c), plan,
+                                  tn=int(rng.integers(0, 21)), p=int(rng.integers(0, 40)), ass_frame=3, kc=kc,
+                                  a5=lambda k, fn, n: oracle.a5(1, k, fn, n), seed=seed, esn0_db=esn0, cfo_hz=cfo)
+    pb, pt = str(tmp_path / "bcch.cfile"), str(tmp_path / "tch.cfile")
+    b.tofile(pb)
+    t.tofile(pt)
+    r = subprocess.run([REF_BIN, "4", pb, pt, key], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    ref = rxlog.parse(r.stderr.split("\n"))
+    got = _walk(oracle, emu, b, t, kc)
+    assert len(got) == len(ref) and any(e["tch"] for e in ref)
+    keys = ("fn", "kind", "crc", "conv", "tch", "flush", "assigned", "end", "bi", "sync_id", "frame0", "frame1", "conv0", "conv1")
+    for g, e in zip(got, ref):
+        for k in keys:
+            assert g.get(k) == e.get(k), (g["fn"], k, g.get(k), e.get(k))
