@@ -339,6 +339,8 @@ def run_gpu_arm(args):
     import osmo_gmr_b200
     L = osmo_gmr_b200.lib()
     L.init(local_rank)
+    if args.demod_generic:
+        L.call("gmr1b200_set_demod_generic", 1)
 
     W = Workload(L, torch, args.arfcns, args.bursts_per_arfcn, 1000 + rank, dev)
     nb = W.total()
@@ -627,6 +629,8 @@ def main():
     ap.add_argument("--e2e-chunks", type=int, default=8)
     ap.add_argument("--streams", type=int, default=3, choices=[1, 2, 3])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--demod-generic", action="store_true",
+                    help="A/B: force the generic demodulation kernel instead of the per-format ones")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

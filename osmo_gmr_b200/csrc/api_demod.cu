@@ -29,7 +29,6 @@ cudaError_t gmr1::device_bursts(const BurstTab **out)
 	return cudaSuccess;
 }
 
-static std::atomic<int> g_sync_reset{0};
 
 static_assert(sizeof(gmr1b200_burst_desc) == sizeof(BurstTab), "public descriptor must mirror gmr1::BurstTab");
 
@@ -58,7 +57,6 @@ static int run_demod(const int *types, int n_types, int mode, DemodArgs a, int64
 	}
 	if (a.sps < 1 || a.sps > 16)
 		return set_err(-EINVAL, "pi4cxpsk batch: sps must be 1..16");
-	a.sync_reset = g_sync_reset.load();
 	const BurstTab &t0 = custom ? custom[0] : burst_tab(types[0]);
 	if (a.win_len < t0.len * a.sps)
 		return set_err(-EINVAL, "pi4cxpsk batch: window shorter than the burst");
@@ -172,7 +170,12 @@ int gmr1b200_synth_bursts(int burst_type, const uint8_t *ebits, int ebits_stride
 
 int gmr1b200_set_sync_accumulator_reset(int on)
 {
-	return g_sync_reset.exchange(on ? 1 : 0);
+	return gmr1::g_sync_reset.exchange(on ? 1 : 0);
+}
+
+int gmr1b200_set_demod_generic(int on)
+{
+	return gmr1::g_demod_generic.exchange(on ? 1 : 0);
 }
 
 int gmr1b200_burst_desc_get(int bt, struct gmr1b200_burst_desc *out)

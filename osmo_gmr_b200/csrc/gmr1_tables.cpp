@@ -11,6 +11,7 @@
 //   burst formats ................ src/sdr/nb.c:34-377 (ETSI TS 101 376-5-2 section 7.4)
 // Nothing here is executed per burst: tables are built once and uploaded to __constant__.
 #include "gmr1_tables.h"
+#include "burst_formats.h"
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -334,45 +335,6 @@ int chan_keep_mask(int ch, uint8_t *mask, int max)
 }
 
 // ---------------------------------------------------------------------------- burst formats
-
-struct SyncDef { int pos; const char *syms; };          // syms: one digit per symbol, "" ends list
-struct DataDef { int pos, len; };
-struct BurstDef {
-	float rot_div;  // rotation = pi / rot_div
-	int nbits, len, ebits;
-	SyncDef sync[MAX_SYNC][MAX_SYNC_CHUNK];
-	DataDef data[MAX_DATA_CHUNK];
-};
-
-static const char S32x2[] = "22222222222222222222222222222222";
-
-static const BurstDef BURSTS[BT_COUNT] = {
-	/* BCCH  */ {4, 2, 234, 424, {{{28, "02200020222"}, {119, "220"}, {197, "220"}}},
-	             {{2, 26}, {39, 80}, {122, 75}, {200, 31}}},
-	/* DC2   */ {4, 2, 78, 132, {{{28, "0123030"}}}, {{2, 26}, {35, 40}}},
-	/* DC6   */ {4, 2, 234, 432, {{{28, "0002202"}, {119, "030"}, {197, "311"}}},
-	             {{2, 26}, {35, 84}, {122, 75}, {200, 31}}},
-	/* DC12  */ {2, 1, 468, 432, {{{10, "0010001111"}, {228, "00100011101"}, {447, "0010001111"}}},
-	             {{2, 8}, {20, 208}, {239, 208}, {457, 8}}},
-	/* NT3 S */ {4, 2, 117, 212, {{{28, "033123"}}}, {{2, 26}, {34, 80}}},
-	/* NT3 F */ {4, 1, 117, 104, {{{28, "10101010"}}, {{28, "11001001"}}}, {{2, 26}, {36, 78}}},
-	/* NT6   */ {4, 2, 234, 434,
-	             {{{28, "022323"}, {119, "010"}, {197, "230"}}, {{28, "000220"}, {119, "130"}, {197, "213"}}},
-	             {{2, 26}, {34, 85}, {122, 75}, {200, 31}}},
-	/* NT9   */ {4, 2, 351, 662,
-	             {{{28, "022323"}, {119, "122"}, {197, "010"}, {275, "230"}},
-	              {{28, "000220"}, {119, "020"}, {197, "130"}, {275, "213"}}},
-	             {{2, 26}, {34, 85}, {122, 75}, {200, 75}, {278, 70}}},
-	/* RACH  */ {4, 2, 351, 494,
-	             {{{78, "02200020222220220"}, {127, S32x2}, {191, S32x2}, {255, "02200020222220220"}, {347, "0"}}},
-	             {{2, 76}, {95, 32}, {159, 32}, {223, 32}, {272, 75}}},
-	/* SDCCH */ {4, 1, 234, 208,
-	             {{{28, "0101010"}, {115, "1010101"}, {197, "0101011"}},
-	              {{28, "0011001"}, {115, "1001100"}, {197, "1100111"}},
-	              {{28, "0000111"}, {115, "1000011"}, {197, "1100001"}},
-	              {{28, "0110100"}, {115, "1011010"}, {197, "0101101"}}},
-	             {{2, 26}, {35, 80}, {122, 75}, {204, 27}}},
-};
 
 static BurstTab g_burst[BT_COUNT];
 static std::once_flag g_burst_once;

@@ -2,6 +2,7 @@
 // the C-ABI layer (api_*.cu).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include "decode_unit.cuh"
 
 namespace gmr1 {
@@ -28,13 +29,21 @@ struct DemodArgs {
 	float         *toa;         // [n] or NULL
 	float         *freq_err;    // [n] or NULL
 	float         *pwr;         // [n] or NULL (sync power; detect: after the e_toa weighting)
-	int32_t        sync_reset;  // 0 = reference behaviour (accumulator never cleared between candidate sequences)
+	int32_t        sync_reset;  // filled in by launch_demod from g_sync_reset (callers leave it alone)
 	const int32_t *n_dev;       // optional device-side burst count (<= n): bursts beyond it are skipped (rx scheduler)
 };
 
+// gmr1b200_set_sync_accumulator_reset: 0 = reference behaviour (accumulator never cleared between candidate
+// sequences).  launch_demod applies it, so every caller (batch entry points, fused entries, frame loop) agrees.
+extern std::atomic<int> g_sync_reset;
 // d_bts: n_bt burst descriptors in device memory, h_bts: the same on the host (for geometry)
 cudaError_t launch_demod(const DemodArgs &a, const BurstTab *d_bts, const BurstTab *h_bts, int n_bt, int mode,
                          cudaStream_t st);
+
+// per-format kernels (demod_fast.cu): takes the batch when (standard burst type bt, sps 4, search width) is one of the
+// compiled combinations and returns true (*err = launch status); false: the generic kernel has to run
+extern std::atomic<int> g_demod_generic;      // gmr1b200_set_demod_generic
+bool launch_demod_fast(const DemodArgs &a, int bt, cudaStream_t st, cudaError_t *err);
 
 // ---- stage 1: FCCH
 struct FcchArgs {

@@ -80,6 +80,7 @@ class Lib:
         "gmr1b200_synth_bursts": [_I, _P, _I, _P, _I, _I, _P, _F, _P, _F, _P, _F, _P, _F, _P, _F, ctypes.c_uint64,
                                   _P, _L, _P, _L, _I, _P],
         "gmr1b200_set_sync_accumulator_reset": [_I],
+        "gmr1b200_set_demod_generic": [_I],
         "gmr1b200_burst_len": [_I],
         "gmr1b200_burst_ebits": [_I],
         "gmr1b200_pi4cxpsk_demod_batch": [_I, _P, _L, _P, _L, _I, _I, _P, _F, _P, _I, _P, _P, _P, _P, _I, _P],

@@ -78,11 +78,18 @@ def compare(name, oracle, x, got, freq_shift=None):
     # search windows of 1, 2 and 3 rows of 32 offsets and beyond (the kernel is specialised on the row count,
     # more than 96 offsets take the generic loop)
     ("bcch", 30, 1), ("bcch", 62, 1), ("bcch", 95, 1), ("bcch", 130, 1), ("nt9", 100, 2)])
-def test_demod_parity(gpu_lib, oracle, name, win, sync_ids):
+@pytest.mark.parametrize("generic", [0, 1])
+def test_demod_parity(gpu_lib, oracle, name, win, sync_ids, generic):
+    """generic = 0: the standard formats at their standard search widths run on the per-format kernels
+    (csrc/demod_fast.cu), everything else on the generic kernel; generic = 1: the generic kernel for all."""
     rng = np.random.default_rng(100 + sigen.BT_ID[name])
     n = 70
     x, sid_true, _ = gen(name, n, win, rng, sync_ids)
-    got = gpu_demod(gpu_lib, name, x)
+    prev = gpu_lib.call("gmr1b200_set_demod_generic", generic)
+    try:
+        got = gpu_demod(gpu_lib, name, x)
+    finally:
+        gpu_lib.call("gmr1b200_set_demod_generic", prev)
     compare(name, oracle, x, got)
     if sync_ids == 1:
         assert (got[1] == 0).all()
@@ -100,7 +107,16 @@ def test_demod_device_pointers_and_freq_shift(gpu_lib, oracle):
     compare("bcch", oracle, x, got, freq_shift=fsh)
 
 
-def test_demod_hot_path_layouts(gpu_lib, oracle):
+@pytest.mark.parametrize("generic", [0, 1])
+def test_demod_hot_path_layouts(gpu_lib, oracle, generic):
+    prev = gpu_lib.call("gmr1b200_set_demod_generic", generic)
+    try:
+        _hot_path_layouts(gpu_lib, oracle)
+    finally:
+        gpu_lib.call("gmr1b200_set_demod_generic", prev)
+
+
+def _hot_path_layouts(gpu_lib, oracle):
     """The same bursts through the kernel's usual path (no sync power requested, 16-byte aligned windows, even
     soft-bit rows) and through its out-of-line variants (odd soft-bit row stride -> byte stores, windows at an odd
     sample offset -> unaligned statistics loop + separate region copy, sync power requested) give the same soft bits."""

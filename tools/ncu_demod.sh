@@ -5,7 +5,7 @@ TAG=$1; shift
 mkdir -p gpurun_out
 one() {
 	GMR1B200_LIB=$2 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,launch__occupancy_limit_shared_mem,launch__occupancy_limit_registers \
-		--clock-control none -k regex:demod_kernel -s 4 -c 2 --csv --log-file gpurun_out/${TAG}_$1.csv \
+		--clock-control none -k regex:demod_ -s 4 -c 2 --csv --log-file gpurun_out/${TAG}_$1.csv \
 		python bench.py --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 	python - "$1" gpurun_out/${TAG}_$1.csv <<'PY'
 import csv, sys
