@@ -39,6 +39,19 @@
 #include "demod_common.cuh"
 #include "launch.h"
 
+#ifndef DMF_PREFETCH
+#define DMF_PREFETCH 1         // 0: none, 1: bulk L2 prefetch of the window at burst start, 2: per-lane L2 prefetches
+#endif
+#ifndef DMF_PF_FROM
+#define DMF_PF_FROM 4096       // DMF_PREFETCH 2: first byte of the window that is prefetched
+#endif
+#ifndef DMF_MIN_CTAS
+#define DMF_MIN_CTAS 8         // resident CTAs per SM the register allocation is capped for
+#endif
+#ifndef DMF_STATS_BATCH
+#define DMF_STATS_BATCH 8      // 16-byte loads of the statistics pass issued together
+#endif
+
 namespace gmr1 {
 
 // ---- compile-time loop: f(std::integral_constant<int, 0>) ... f(std::integral_constant<int, N-1>)
@@ -191,7 +204,7 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return _
 template <int BT, class G, bool WANT_SD>
 __device__ __forceinline__ FNorm stats_fill(const float2 *__restrict__ x, int lane, float2 *reg)
 {
-	constexpr int NP = G::L / 2, NIT = (NP + 31) / 32, BATCH = 8;
+	constexpr int NP = G::L / 2, NIT = (NP + 31) / 32, BATCH = DMF_STATS_BATCH;
 	const float4 *x4 = reinterpret_cast<const float4 *>(x) + lane;
 	float4 *reg4 = reinterpret_cast<float4 *>(reg) + lane;
 	float2 s0 = make_float2(0.0f, 0.0f), s1 = s0, q0 = s0, q1 = s0;
@@ -316,7 +329,7 @@ __device__ __noinline__ void fast_build_taps(const FastSmem sm, float fs, int la
 
 // ---- the kernel -----------------------------------------------------------------------------------------------------
 template <int BT, int W, bool WANT_SD>
-__global__ void __launch_bounds__(DM_WARPS * 32, 8)
+__global__ void __launch_bounds__(DM_WARPS * 32, DMF_MIN_CTAS)
 demod_fast_kernel(const DemodArgs a)
 {
 	using G = Geo<BT, W>;
@@ -396,8 +409,18 @@ demod_fast_kernel(const DemodArgs a)
 		const float freq_shift = a.freq_shift ? a.freq_shift[b] : a.freq_shift0;
 		const float fs = (freq_shift - rotation) / (float)FG_SPS;
 		const bool aligned = (((uintptr_t)x) & 15) == 0;
+#if DMF_PREFETCH == 1
+		// whole window -> L2 with one bulk prefetch (TMA unit, no registers, no completion to wait for)
 		if (lane == 0 && aligned)
 			asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(x), "n"(G::L * 8) : "memory");
+#elif DMF_PREFETCH == 2
+		// the part of the window the first batch of loads does not touch, one 128-byte line per lane and request
+		static_for<(G::L * 8 - DMF_PF_FROM + 4095) / 4096>([&](auto K) {
+			constexpr int o = DMF_PF_FROM + decltype(K)::value * 4096;
+			if (o + lane * 128 < G::L * 8)
+				asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(x) + o + lane * 128));
+		});
+#endif
 		__syncwarp();        // the previous burst's training symbols were read from the regions
 		if (fs != fs_taps) {
 			fast_build_taps<BT, G>(sm, fs, lane);
@@ -463,7 +486,7 @@ demod_fast_kernel(const DemodArgs a)
 						const float xr = P[r].x - Q[r].y, xi = P[r].y + Q[r].x;
 						float mag;
 						asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(mag) : "f"(fmaf(xr, xr, xi * xi)));
-						acc[r] = WANT_SD ? fmaf(mag, nm.inv_sd, acc[r]) : acc[r] + mag;
+						acc[r] += mag;      // unscaled: 1/stddev changes no decision, it only scales the reported power
 					}
 				});
 				__syncwarp();
@@ -485,7 +508,7 @@ demod_fast_kernel(const DemodArgs a)
 		if (lane == 0) {
 			if (a.sync_id) a.sync_id[b] = sync_id;
 			if (a.toa) a.toa[b] = toa;
-			if (WANT_SD && a.pwr) a.pwr[b] = pwr;
+			if (WANT_SD && a.pwr) a.pwr[b] = pwr * (nm.inv_sd * nm.inv_sd);
 		}
 		int8_t *eb = a.ebits + (size_t)b * a.ebits_stride;
 		if (sync_id < 0) {          // nothing correlated (all-zero input): the reference returns -errno
@@ -501,7 +524,7 @@ demod_fast_kernel(const DemodArgs a)
 		const int d = (int)df;
 
 		// ---- 4. training symbols, one per lane, derotated as the reference derotates every sample:
-		//      z = (x - avg)/sd * e^{j*fl32(fs*idx)}, times conj(reference symbol)
+		//      z = (x - avg) * e^{j*fl32(fs*idx)}, times conj(reference symbol)
 		float2 z = make_float2(0.0f, 0.0f);
 		if (lane < NTR) {
 			int sym = t_sym[0];
@@ -510,11 +533,7 @@ demod_fast_kernel(const DemodArgs a)
 				sym = sync_id == s ? t_sym[s] : sym;
 			const float2 v = sm.reg[t_roff + d];
 			const float2 e = sincos_red(fs * fmaf(t_posf, (float)FG_SPS, df));
-			float yr = v.x - nm.ar, yi = v.y - nm.ai;
-			if constexpr (WANT_SD) {
-				yr *= nm.inv_sd;
-				yi *= nm.inv_sd;
-			}
+			const float yr = v.x - nm.ar, yi = v.y - nm.ai;      // (the scale 1/sd does not change an angle)
 			z = mul_conj_sym(sym, make_float2(yr * e.x - yi * e.y, yr * e.y + yi * e.x));
 		}
 		float ferr = 0.0f;
@@ -689,7 +708,7 @@ bool launch_demod_fast(const DemodArgs &a, int bt, cudaStream_t st, cudaError_t 
 	}
 	const size_t smem = e->warp_bytes * DM_WARPS;
 	int per_sm = (int)((228 * 1024) / (smem + e->static_bytes + 1024 + 64));
-	per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+	per_sm = per_sm < 1 ? 1 : (per_sm > DMF_MIN_CTAS ? DMF_MIN_CTAS : per_sm);
 	if (const char *ev = getenv("GMR1B200_DEMOD_CTAS")) {     // tuning knob: resident CTAs per SM
 		const int v = atoi(ev);
 		if (v >= 1 && v < per_sm)

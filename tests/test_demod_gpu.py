@@ -99,6 +99,25 @@ def test_demod_parity(gpu_lib, oracle, name, win, sync_ids, generic):
     # hence no comparison with the transmitted sync id here.
 
 
+def test_sync_power_fast_vs_generic(gpu_lib):
+    """sync power (an output the reference computes only inside its detect function, pi4cxpsk.c:256-262): the
+    per-format kernels run the search on unscaled samples and scale the result, the generic kernel scales every
+    chunk correlation as the reference does - same number"""
+    rng = np.random.default_rng(3)
+    for name, win, sync_ids in (("bcch", 80, 1), ("nt3_facch", 6, 2), ("nt9", 6, 2)):
+        x, _, _ = gen(name, 40, win, rng, sync_ids)
+        fast = gpu_demod(gpu_lib, name, x)
+        prev = gpu_lib.call("gmr1b200_set_demod_generic", 1)
+        try:
+            generic = gpu_demod(gpu_lib, name, x)
+        finally:
+            gpu_lib.call("gmr1b200_set_demod_generic", prev)
+        assert (fast[1] == generic[1]).all() and np.abs(fast[2] - generic[2]).max() <= 0.004
+        assert (fast[4] > 0).all() and np.abs(fast[4] / generic[4] - 1).max() < 1e-3, name
+        d = np.abs(fast[0].astype(int) - generic[0].astype(int))
+        assert d.max() <= 1 and (d == 0).mean() > 0.995
+
+
 def test_demod_device_pointers_and_freq_shift(gpu_lib, oracle):
     rng = np.random.default_rng(7)
     x, _, _ = gen("bcch", 40, 80, rng)
