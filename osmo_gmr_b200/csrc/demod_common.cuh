@@ -26,6 +26,9 @@ static constexpr int DM_WARPS = 4;
 #ifndef DM_OPT_RADIX
 #define DM_OPT_RADIX 1         // early/late search: three 8-point evaluations instead of eight sequential steps
 #endif
+#ifndef DM_OPT_WALK
+#define DM_OPT_WALK 1          // early/late search: rounds unrolled, tie-free decision walk on the fast path
+#endif
 #ifndef DM_OPT_FSC
 #define DM_OPT_FSC 1           // training symbols / phase reference: reduced-argument hardware sincos
 #endif
@@ -232,8 +235,10 @@ __device__ __forceinline__ float peak_early_late(const float *acc, float *aw, in
 	const float fm = (float)((lane >> 2) - 3);                  // grid point of this quad (m = 4 is never visited)
 	const float fq = (float)(q - 10), sgn = (q & 1) ? 1.0f : -1.0f;     // first tap of this lane, -(-1)^j (j = q - 10 + 4k)
 	float h = 0.125f;
-#pragma unroll 1
-	for (int round = 0; round < 3 && live; round++, h *= 0.125f) {
+	DM_UNROLL(DM_OPT_WALK ? 3 : 1)
+	for (int round = 0; round < 3; round++, h *= 0.125f) {
+		if (!live)
+			break;
 		const float pe = fmaf(fm, h, early);
 		const float fl = floorf(pe), f = pe - fl;
 		const float *ap = aw + q + (fl != fbase ? 1 : 0);       // early gate reads acc[floor(pe) + j], late gate + 2
@@ -255,8 +260,23 @@ __device__ __forceinline__ float peak_early_late(const float *acc, float *aw, in
 		tl += __shfl_xor_sync(0xffffffffu, tl, 2);
 		const float e2 = te * te, l2 = tl * tl;
 		const unsigned right = __ballot_sync(0xffffffffu, e2 < l2), dead = __ballot_sync(0xffffffffu, e2 == l2);
-		// walk: bit 4*(m+3) of the ballots belongs to grid point m.  stop = first level (0, 1, 2) whose point is
-		// dead (3: none); moves of levels past it are dropped.
+		// walk: bit 4*(m+3) of the ballots belongs to grid point m.
+#if DM_OPT_WALK
+		if (dead == 0u) {
+			// usual case, no exact tie anywhere on the grid: step a moves +-2, step b +-1, step c +-1/2 (the last
+			// round has only steps a and b)
+			const unsigned s1 = (right & 0x1000u) ? 20u : 4u;
+			float mf = (right & 0x1000u) ? 2.0f : -2.0f;
+			const bool r1 = (right >> s1) & 1u;
+			const unsigned s2 = r1 ? s1 + 4u : s1 - 4u;
+			mf += r1 ? 1.0f : -1.0f;
+			if (round < 2)
+				mf += ((right >> s2) & 1u) ? 0.5f : -0.5f;
+			early = fmaf(mf, h, early);
+			continue;
+		}
+#endif
+		// stop = first level (0, 1, 2) whose point is dead (3: none); moves of levels past it are dropped.
 		const unsigned r0 = (right >> 12) & 1u, d0 = (dead >> 12) & 1u;
 		const int m1 = r0 ? 2 : -2;
 		const unsigned s1 = 4u * (unsigned)(m1 + 3);

@@ -49,7 +49,7 @@
 #define DMF_MIN_CTAS 8         // resident CTAs per SM the register allocation is capped for
 #endif
 #ifndef DMF_STATS_BATCH
-#define DMF_STATS_BATCH 8      // 16-byte loads of the statistics pass issued together
+#define DMF_STATS_BATCH 4      // 16-byte loads of the statistics pass issued together
 #endif
 
 namespace gmr1 {
@@ -167,7 +167,7 @@ struct Geo {
 	static constexpr int DB = (DROWS + DITER - 1) / DITER;
 	static constexpr int ACC_ALLOC = 4 + 32 * ROWS + 8;             // accv[-4 .. 32*ROWS+3]
 	static constexpr int WARP_BYTES = (REG_ALLOC * 8 + NSYNC * TAPS * 8 + ((NSYNC * NCH + 1) & ~1) * 8 + ACC_ALLOC * 4 +
-	                                   28 * 4 + 15) & ~15;
+	                                   32 * 4 + 15) & ~15;
 	static_assert(fg_ok(BT, W_), "burst format / search width not eligible for the per-format kernel");
 };
 
@@ -177,6 +177,7 @@ struct FastSmem {
 	float2 *tsum;    // [NSYNC][NCH]  sum of each chunk's taps
 	float  *accv;    // [-4 .. 32*ROWS+3] correlation magnitude accumulator, zero outside [0, W)
 	float  *aw;      // [28] early/late search window
+	float  *fs_taps; // frequency shift the cached taps were built for
 };
 
 template <class G>
@@ -192,6 +193,7 @@ __device__ __forceinline__ FastSmem fast_carve(uint8_t *base)
 	s.accv = (float *)base + 4;
 	base += G::ACC_ALLOC * 4;
 	s.aw = (float *)base;
+	s.fs_taps = s.aw + 28;
 	return s;
 }
 
@@ -337,6 +339,7 @@ demod_fast_kernel(const DemodArgs a)
 	extern __shared__ __align__(16) uint8_t smem[];
 	__shared__ uint16_t soft_lut[LUT_CELLS << NB];
 	__shared__ uint2 dtab[G::DROWS * 32];          // data symbol -> (byte offset of its sample for TOA 0, position as float)
+	__shared__ uint4 lane_tab[32];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const FastSmem sm = fast_carve<G>(smem + (size_t)warp * G::WARP_BYTES);
 
@@ -358,58 +361,76 @@ demod_fast_kernel(const DemodArgs a)
 		reinterpret_cast<float *>(smem + (size_t)warp * G::WARP_BYTES)[i] = 0.0f;
 	__syncthreads();
 
-	TapLane tpl;
-	tpl.j = lane - 10;
-	tpl.xj = PI_F * (float)(lane - 10);
-	tpl.sgn = lane < 21 ? (((lane - 10) & 1) ? 1.0f : -1.0f) : 0.0f;
-
-	// ---- the role of this lane in the training-symbol phase (training symbol t = lane), once per kernel
-	int t_roff = 0, t_end = 0, c_src = 0, c_srcp = 0;
-	float t_posf = 0.0f, c_invd = 0.0f;
-	static_for<NCH>([&](auto C) {
-		constexpr int c = decltype(C)::value, st = fg_cstart(BT, c), cl = fg_clen(BT, c);
-		if (lane >= st && lane < st + cl) {
-			t_roff = fg_roff(BT, W, c) + 2 + (lane - st) * FG_SPS;     // sample of the symbol for d = 0
-			t_posf = (float)(fg_cpos(BT, c) + lane - st);
-			t_end = st + cl;
-		}
-		if constexpr (c > 0) {
-			// lane c: angle between chunk c and chunk c-1 over the distance of their centres (pi4cxpsk.c:390-394)
-			constexpr float pc = (float)fg_cpos(BT, c) + (float)fg_clen(BT, c) / 2.0f;
-			constexpr float pp = (float)fg_cpos(BT, c - 1) + (float)fg_clen(BT, c - 1) / 2.0f;
-			if (lane == c) {
-				c_src = st;
-				c_srcp = fg_cstart(BT, c - 1);
-				c_invd = pc - pp;
-			}
-		}
-	});
-	// reference symbols of the training sequence(s), 2 bits per symbol, for this lane
-	int t_sym[G::NSYNC];
-	static_for<G::NSYNC>([&](auto S) {
-		constexpr int s = decltype(S)::value;
-		unsigned long long w64 = 0;
+	// ---- the role of a lane in the training-symbol phase (training symbol t = lane), computed once per CTA into shared
+	// memory and read back with one 16-byte load per burst: kept in registers across the burst loop these values get
+	// spilled or rematerialised (~60 instructions per burst, measured)
+	//   .x  byte offset of the symbol's sample for d = 0 in the region buffer
+	//   .y  burst position of the symbol (float)
+	//   .z  [7:0] end of the symbol's chunk (segmented sum)  [15:8] / [23:16] lane c >= 1: first symbol of chunk c / c-1
+	//       [24 + 2s +: 2] reference symbol of sequence s
+	//   .w  lane c >= 1: distance between the centres of chunks c and c-1 (float)
+	if (warp == 0) {
+		int t_roff = 0, t_end = 0, c_src = 0, c_srcp = 0, syms = 0;
+		float t_posf = 0.0f, c_dist = 1.0f;
 		static_for<NCH>([&](auto C) {
-			constexpr int c = decltype(C)::value;
-			static_for<fg_clen(BT, c)>([&](auto K) {
-				w64 |= (unsigned long long)bf_s_sym(BT, s, c, decltype(K)::value) << (2 * (fg_cstart(BT, c) + decltype(K)::value));
-			});
+			constexpr int c = decltype(C)::value, st = fg_cstart(BT, c), cl = fg_clen(BT, c);
+			if (lane >= st && lane < st + cl) {
+				t_roff = fg_roff(BT, W, c) + 2 + (lane - st) * FG_SPS;     // sample of the symbol for d = 0
+				t_posf = (float)(fg_cpos(BT, c) + lane - st);
+				t_end = st + cl;
+			}
+			if constexpr (c > 0) {
+				// lane c: angle between chunk c and chunk c-1 over the distance of their centres (pi4cxpsk.c:390-394)
+				constexpr float pc = (float)fg_cpos(BT, c) + (float)fg_clen(BT, c) / 2.0f;
+				constexpr float pp = (float)fg_cpos(BT, c - 1) + (float)fg_clen(BT, c - 1) / 2.0f;
+				if (lane == c) {
+					c_src = st;
+					c_srcp = fg_cstart(BT, c - 1);
+					c_dist = pc - pp;
+				}
+			}
 		});
-		t_sym[s] = (int)((w64 >> (2 * lane)) & 3);
-	});
+		static_for<G::NSYNC>([&](auto S) {
+			constexpr int s = decltype(S)::value;
+			unsigned long long w64 = 0;
+			static_for<NCH>([&](auto C) {
+				constexpr int c = decltype(C)::value;
+				static_for<fg_clen(BT, c)>([&](auto K) {
+					w64 |= (unsigned long long)bf_s_sym(BT, s, c, decltype(K)::value) << (2 * (fg_cstart(BT, c) + decltype(K)::value));
+				});
+			});
+			syms |= (int)((w64 >> (2 * lane)) & 3) << (2 * s);
+		});
+		lane_tab[lane] = make_uint4((unsigned)(t_roff * 8), __float_as_uint(t_posf),
+		                            (unsigned)(t_end | (c_src << 8) | (c_srcp << 16) | (syms << 24)), __float_as_uint(c_dist));
+	}
+	__syncthreads();
+	const unsigned lane_tab_s = (unsigned)__cvta_generic_to_shared(&lane_tab[lane]);
+	const unsigned reg_s = (unsigned)__cvta_generic_to_shared(sm.reg);
 
 	constexpr float inv_dd256x2 = 2.0f * (float)(LUT_CELLS << NB) * 0.15915494309189533577f;   // table BYTES per radian
 	constexpr float TWO_PI_HI = 6.28125f, TWO_PI_LO = 1.9353071795864769e-3f, INV_2PI = 0.15915494309189533577f;
 	constexpr float rotation = 3.14159265358979323846264338327f / BURSTS[BT].rot_div;
-	float fs_taps = __int_as_float(0x7fc00000);     // frequency shift the cached taps were built for (NaN: none)
+	// rotated taps: built once when the batch shares one frequency shift, else cached per warp and rebuilt when the
+	// shift changes (the shift they were built for sits in the warp's shared-memory slice, not in a register)
+	if (!a.freq_shift)
+		fast_build_taps<BT, G>(sm, (a.freq_shift0 - rotation) / (float)FG_SPS, lane);
+	else if (lane == 0)
+		*sm.fs_taps = __int_as_float(0x7fc00000);       // NaN: none
+	__syncwarp();
 
 	const int n_eff = a.n_dev ? min(a.n, *a.n_dev) : a.n;
-	for (int b = blockIdx.x * DM_WARPS + warp; b < n_eff; b += gridDim.x * DM_WARPS) {
+	const int b_step = gridDim.x * DM_WARPS;
+	for (int b = blockIdx.x * DM_WARPS + warp; b < n_eff; b += b_step) {
 		const float2 *x = a.iq + (a.ofs ? a.ofs[b] : (int64_t)b * a.stride);
 		const float freq_shift = a.freq_shift ? a.freq_shift[b] : a.freq_shift0;
 		const float fs = (freq_shift - rotation) / (float)FG_SPS;
 		const bool aligned = (((uintptr_t)x) & 15) == 0;
-#if DMF_PREFETCH == 1
+#if DMF_PREFETCH == 3
+		// first burst of this warp only: later windows were requested while the previous burst was sliced
+		if (lane == 0 && aligned && b < b_step)
+			asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(x), "n"(G::L * 8) : "memory");
+#elif DMF_PREFETCH == 1
 		// whole window -> L2 with one bulk prefetch (TMA unit, no registers, no completion to wait for)
 		if (lane == 0 && aligned)
 			asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(x), "n"(G::L * 8) : "memory");
@@ -422,9 +443,11 @@ demod_fast_kernel(const DemodArgs a)
 		});
 #endif
 		__syncwarp();        // the previous burst's training symbols were read from the regions
-		if (fs != fs_taps) {
+		if (a.freq_shift && fs != *sm.fs_taps) {
 			fast_build_taps<BT, G>(sm, fs, lane);
-			fs_taps = fs;
+			if (lane == 0)
+				*sm.fs_taps = fs;
+			__syncwarp();
 		}
 		FNorm nm;
 		if (aligned)
@@ -495,6 +518,10 @@ demod_fast_kernel(const DemodArgs a)
 					sm.accv[lane + 32 * r] = (32 * r + 31 < W || lane + 32 * r < W) ? acc[r] : 0.0f;
 				__syncwarp();
 				float peak;
+				TapLane tpl;
+				tpl.j = lane - 10;
+				tpl.xj = PI_F * (float)(lane - 10);
+				tpl.sgn = lane < 21 ? ((lane & 1) ? 1.0f : -1.0f) : 0.0f;
 				const float s_toa = peak_early_late<ROWS>(sm.accv, sm.aw, W, tpl, lane, peak);
 				peak *= 1.0f / (float)NTR;
 				const float s_pwr = peak * peak;
@@ -519,19 +546,31 @@ demod_fast_kernel(const DemodArgs a)
 			continue;
 		}
 
+#if DMF_PREFETCH == 3
+		{	// the next window of this warp starts its way to L2 while this burst's symbols are sliced
+			const int bn = b + b_step;
+			if (lane == 0 && bn < n_eff) {
+				const float2 *xn = a.iq + (a.ofs ? a.ofs[bn] : (int64_t)bn * a.stride);
+				if ((((uintptr_t)xn) & 15) == 0)
+					asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(xn), "n"(G::L * 8) : "memory");
+			}
+		}
+#endif
 		// symbol i sits at sample i*sps + d (sps >= 4 branch of _gmr1_pi4cxpsk_align, :286-297)
 		const float df = roundf(toa);
 		const int d = (int)df;
 
 		// ---- 4. training symbols, one per lane, derotated as the reference derotates every sample:
 		//      z = (x - avg) * e^{j*fl32(fs*idx)}, times conj(reference symbol)
+		uint4 lt;
+		asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lt.x), "=r"(lt.y), "=r"(lt.z), "=r"(lt.w) : "r"(lane_tab_s));
+		const float t_posf = __uint_as_float(lt.y);
+		const int t_end = (int)(lt.z & 0xffu), c_src = (int)((lt.z >> 8) & 0xffu), c_srcp = (int)((lt.z >> 16) & 0xffu);
 		float2 z = make_float2(0.0f, 0.0f);
 		if (lane < NTR) {
-			int sym = t_sym[0];
-#pragma unroll
-			for (int s = 1; s < G::NSYNC; s++)
-				sym = sync_id == s ? t_sym[s] : sym;
-			const float2 v = sm.reg[t_roff + d];
+			const int sym = (int)((lt.z >> (24 + 2 * sync_id)) & 3u);
+			float2 v;
+			asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(reg_s + lt.x + (unsigned)(d * 8)));
 			const float2 e = sincos_red(fs * fmaf(t_posf, (float)FG_SPS, df));
 			const float yr = v.x - nm.ar, yi = v.y - nm.ai;      // (the scale 1/sd does not change an angle)
 			z = mul_conj_sym(sym, make_float2(yr * e.x - yi * e.y, yr * e.y + yi * e.x));
@@ -553,7 +592,7 @@ demod_fast_kernel(const DemodArgs a)
 			const float sr = __shfl_sync(0xffffffffu, v.x, c_src), si = __shfl_sync(0xffffffffu, v.y, c_src);
 			const float qr = __shfl_sync(0xffffffffu, v.x, c_srcp), qi = __shfl_sync(0xffffffffu, v.y, c_srcp);
 			const float re = sr * qr + si * qi, im = si * qr - sr * qi;
-			const float part = fast_atan2f_inl(im, re) / c_invd;
+			const float part = fast_atan2f_inl(im, re) / __uint_as_float(lt.w);
 			float f = 0.0f;
 #pragma unroll
 			for (int k = 1; k < NCH; k++)
