@@ -45,6 +45,12 @@
 #ifndef DMF_PF_FROM
 #define DMF_PF_FROM 4096       // DMF_PREFETCH 2: first byte of the window that is prefetched
 #endif
+#ifndef DMF_CACHE_HINTS
+#define DMF_CACHE_HINTS 1      // bit 0: data-symbol loads (last use of the window) streaming, bit 1: soft-bit stores streaming
+#endif
+#ifndef DMF_CORR_PIPE
+#define DMF_CORR_PIPE 1        // correlation: samples of the next tap requested before the multiply-adds of this one
+#endif
 #ifndef DMF_MIN_CTAS
 #define DMF_MIN_CTAS 8         // resident CTAs per SM the register allocation is capped for
 #endif
@@ -426,7 +432,18 @@ demod_fast_kernel(const DemodArgs a)
 		const float freq_shift = a.freq_shift ? a.freq_shift[b] : a.freq_shift0;
 		const float fs = (freq_shift - rotation) / (float)FG_SPS;
 		const bool aligned = (((uintptr_t)x) & 15) == 0;
-#if DMF_PREFETCH == 3
+#if DMF_PREFETCH == 4
+		{	// one burst ahead: at the start of burst b the window of burst b + step is requested (the first burst: both)
+			if (lane == 0 && aligned && b < b_step)
+				asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(x), "n"(G::L * 8) : "memory");
+			const int bn = b + b_step;
+			if (lane == 0 && bn < n_eff) {
+				const float2 *xn = a.iq + (a.ofs ? a.ofs[bn] : (int64_t)bn * a.stride);
+				if ((((uintptr_t)xn) & 15) == 0)
+					asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(xn), "n"(G::L * 8) : "memory");
+			}
+		}
+#elif DMF_PREFETCH == 3
 		// first burst of this warp only: later windows were requested while the previous burst was sliced
 		if (lane == 0 && aligned && b < b_step)
 			asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(x), "n"(G::L * 8) : "memory");
@@ -486,6 +503,33 @@ demod_fast_kernel(const DemodArgs a)
 					}
 					const float2 *g = sm.reg + fg_roff(BT, W, c) + 2 + lane;        // sample of tap 0 for offset `lane`
 					const float4 *tp4 = reinterpret_cast<const float4 *>(tapb + fg_toff(BT, c));
+#if DMF_CORR_PIPE
+					// software pipeline: the samples of tap n+1 (and the taps of the next pair) are requested before the
+					// multiply-adds of tap n, so a shared-memory latency is covered by the warp's own arithmetic
+					float2 vb[2][ROWS];
+					float4 tb[2];
+					tb[0] = tp4[0];
+#pragma unroll
+					for (int r = 0; r < ROWS; r++)
+						vb[0][r] = g[32 * r];
+					static_for<cl>([&](auto N) {
+						constexpr int n = decltype(N)::value;
+						if constexpr (n + 1 < cl) {
+#pragma unroll
+							for (int r = 0; r < ROWS; r++)
+								vb[(n + 1) & 1][r] = g[32 * r + FG_SPS * (n + 1)];
+							if constexpr (((n + 1) & 1) == 0)
+								tb[((n + 1) >> 1) & 1] = tp4[(n + 1) >> 1];
+						}
+						const float4 t = tb[(n >> 1) & 1];
+						const float tr = (n & 1) ? t.z : t.x, ti = (n & 1) ? t.w : t.y;
+#pragma unroll
+						for (int r = 0; r < ROWS; r++) {
+							fma2s(P[r], tr, vb[n & 1][r]);
+							fma2s(Q[r], ti, vb[n & 1][r]);
+						}
+					});
+#else
 					static_for<(cl + 1) / 2>([&](auto N2) {
 						constexpr int n2 = decltype(N2)::value;
 						const float4 t = tp4[n2];                 // taps 2*n2, 2*n2+1
@@ -504,6 +548,7 @@ demod_fast_kernel(const DemodArgs a)
 							}
 						}
 					});
+#endif
 #pragma unroll
 					for (int r = 0; r < ROWS; r++) {
 						const float xr = P[r].x - Q[r].y, xi = P[r].y + Q[r].x;
@@ -628,7 +673,11 @@ demod_fast_kernel(const DemodArgs a)
 #pragma unroll
 				for (int u = 0; u < DB; u++) {
 					e[u] = dtab[min(row0 + u, G::DROWS - 1) * 32 + lane];
+#if DMF_CACHE_HINTS & 1
+					v[u] = __ldcs(reinterpret_cast<const float2 *>(xd + e[u].x));     // last use of the window: evict first
+#else
 					v[u] = __ldg(reinterpret_cast<const float2 *>(xd + e[u].x));
+#endif
 				}
 				unsigned sw[DB];
 #pragma unroll
@@ -649,10 +698,17 @@ demod_fast_kernel(const DemodArgs a)
 					for (int u = 0; u < DB; u++) {
 						const int t = (row0 + u) * 32 + lane;
 						if (t < G::NDS) {
+#if DMF_CACHE_HINTS & 2
+							if (NB == 2)
+								__stcs(reinterpret_cast<unsigned short *>(eb) + t, (unsigned short)sw[u]);
+							else
+								__stcs(reinterpret_cast<signed char *>(eb) + t, (signed char)sw[u]);
+#else
 							if (NB == 2)
 								reinterpret_cast<uint16_t *>(eb)[t] = (uint16_t)sw[u];
 							else
 								eb[t] = (int8_t)sw[u];
+#endif
 						}
 					}
 				} else {
