@@ -49,7 +49,7 @@
 #define DMF_CACHE_HINTS 1      // bit 0: data-symbol loads (last use of the window) streaming, bit 1: soft-bit stores streaming
 #endif
 #ifndef DMF_CORR_PIPE
-#define DMF_CORR_PIPE 1        // correlation: samples of the next tap requested before the multiply-adds of this one
+#define DMF_CORR_PIPE 0        // correlation: samples of the next tap requested before the multiply-adds of this one
 #endif
 #ifndef DMF_MIN_CTAS
 #define DMF_MIN_CTAS 8         // resident CTAs per SM the register allocation is capped for
