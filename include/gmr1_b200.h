@@ -26,6 +26,7 @@
 #ifndef GMR1_B200_H
 #define GMR1_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -408,6 +409,34 @@ int gmr1b200_synth_bursts(int burst_type, const gmr1b200_ubit_t *ebits, int ebit
                           const float *amp, float amp0, uint64_t seed,
                           float *iq, int64_t iq_len, const int64_t *win_ofs, int64_t win_stride,
                           int n, void *stream);
+
+/* ---- several GPUs of one box from one process: the device pool -------------------------------------
+ * The reference handles its channels one after the other in one thread (process loop over chan_desc,
+ * src/gmr1_rx.c:732-741).  ARFCNs never interact, so a pool shards them: ARFCN a is processed on device
+ * a mod G.  Every device has one feeder thread (bound to the CPUs next to the GPU when
+ * /sys/bus/pci/devices/<id>/local_cpulist names them), streams_per_dev streams and as many device buffers of
+ * chunk_bytes; host IQ travels in chunks (strided H2D copy of every G-th ARFCN -> the batched entry points above
+ * on device pointers -> strided D2H copy into the caller's result arrays).  No collective, no peer traffic.
+ * Host buffers should be page-locked (gmr1b200_host_alloc, or the caller's own cudaHostAlloc / torch pinned
+ * memory): pageable memory works but its copies are staged and synchronous.  Calls on one pool must not overlap. */
+struct gmr1b200_pool;
+int gmr1b200_pool_create(const int *devices /* [n_dev] CUDA ordinals, NULL: 0 .. n_dev-1 */, int n_dev,
+                         int streams_per_dev, int64_t chunk_bytes, struct gmr1b200_pool **out);
+void gmr1b200_pool_destroy(struct gmr1b200_pool *pool);
+int gmr1b200_pool_size(const struct gmr1b200_pool *pool);
+void *gmr1b200_host_alloc(size_t bytes);       /* page-locked, usable from every device; NULL on failure */
+void gmr1b200_host_free(void *p);
+
+/* gmr1b200_rx_xcch_batch over the pool: host_iq is [n_arfcn][per_arfcn][win_len] complex float (interleaved),
+ * results [n_arfcn][per_arfcn] (l2: x 24 bytes), crc / conv / toa may be NULL. */
+int gmr1b200_pool_rx_xcch(struct gmr1b200_pool *pool, int chan, const float *host_iq, int n_arfcn, int per_arfcn,
+                          int win_len, int sps, float freq_shift0,
+                          uint8_t *l2, int32_t *crc, int32_t *conv, float *toa);
+
+/* gmr1b200_fcch_acquire_batch over the pool: one search window of win_len complex samples per ARFCN,
+ * host_iq [n_arfcn][win_len]; align / freq_error [n_arfcn], rough [n_arfcn] or NULL. */
+int gmr1b200_pool_fcch_acquire(struct gmr1b200_pool *pool, int fcch_type, const float *host_iq, int n_arfcn,
+                               int win_len, int sps, int32_t *rough, int32_t *align, float *freq_error);
 
 #ifdef __cplusplus
 }

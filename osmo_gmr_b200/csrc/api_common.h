@@ -129,15 +129,14 @@ private:
 	{
 		// keep freed scratch in the stream-ordered pool instead of returning it to the driver at
 		// every synchronisation (the default release threshold is 0)
-		static bool pool_set[64] = {false};
+		static std::atomic<bool> pool_set[64];
 		int dev = 0;
-		if (cudaGetDevice(&dev) == cudaSuccess && dev < 64 && !pool_set[dev]) {
+		if (cudaGetDevice(&dev) == cudaSuccess && dev < 64 && !pool_set[dev].exchange(true)) {
 			cudaMemPool_t pool;
 			if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
 				uint64_t thr = UINT64_MAX;
 				cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
 			}
-			pool_set[dev] = true;
 		}
 		void *d = nullptr;
 		cudaError_t e = cudaMallocAsync(&d, bytes, st_);

@@ -1,6 +1,7 @@
 // api_decode.cu - C ABI: library state + batched channel-decode entry points (include/gmr1_b200.h)
 #include "../../include/gmr1_b200.h"
 #include "api_common.h"
+#include "build_id.h"
 #include "launch.h"
 
 namespace gmr1 {
@@ -24,7 +25,7 @@ int gmr1b200_init(int device)
 }
 
 const char *gmr1b200_last_error(void) { return g_err; }
-const char *gmr1b200_version(void) { return "gmr1_b200 0.1 (sm_100a)"; }
+const char *gmr1b200_version(void) { return "gmr1_b200 0.2 (sm_100a) build " GMR1B200_BUILD_ID; }
 uint64_t gmr1b200_kernel_launches(void) { return g_launches.load(); }
 
 }  // extern "C"

@@ -16,6 +16,7 @@ cudaError_t gmr1::device_bursts(const BurstTab **out)
 		return e;
 	if (dev >= 64)
 		return cudaErrorInvalidDevice;
+	GMR1_INIT_LOCK();
 	if (!g_d_bursts[dev]) {
 		BurstTab *d = nullptr;
 		if ((e = cudaMalloc(&d, sizeof(BurstTab) * BT_COUNT)) != cudaSuccess)

@@ -33,6 +33,7 @@ static bool g_tables_up[64] = {false};
 
 static cudaError_t upload_tables()
 {
+	GMR1_INIT_LOCK();
 	int dev = 0;
 	cudaError_t e = cudaGetDevice(&dev);
 	if (e != cudaSuccess)
@@ -203,6 +204,7 @@ __global__ void __launch_bounds__(TPC_T) decode_tpc_kernel(const DecodeArgs a)
 template <int CH>
 static cudaError_t launch_tpc(const DecodeArgs &a, cudaStream_t st)
 {
+	GMR1_INIT_LOCK();
 	static bool attr_done[64] = {false};
 	int dev = 0;
 	cudaGetDevice(&dev);
@@ -339,6 +341,7 @@ __global__ void __launch_bounds__(DC12_WARPS * 32) decode_dc12_kernel(const Deco
 
 static cudaError_t launch_dc12(const DecodeArgs &a, cudaStream_t st)
 {
+	GMR1_INIT_LOCK();
 	static bool attr_done[64] = {false};
 	int dev = 0;
 	cudaGetDevice(&dev);

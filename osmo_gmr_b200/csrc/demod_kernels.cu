@@ -927,6 +927,7 @@ cudaError_t launch_demod(const DemodArgs &a_in, const BurstTab *d_bts, const Bur
 	const size_t smem = wb * DM_WARPS;
 	if (smem > 227 * 1024)
 		return cudaErrorInvalidValue;
+	GMR1_INIT_LOCK();
 	static size_t attr_set[64] = {0};
 	static bool tab_up[64] = {false};
 	int dev = 0;

@@ -519,6 +519,7 @@ cudaError_t launch_fcch_rough(const FcchArgs &a, cudaStream_t st)
 	const size_t smem = sizeof(float) * ((size_t)ng * FR_GRP + lenp + 96 + 4 + nc);
 	if (smem > 227 * 1024)
 		return cudaErrorInvalidValue;
+	GMR1_INIT_LOCK();
 	static size_t attr_set[64] = {0};
 	int dev = 0;
 	cudaGetDevice(&dev);
@@ -539,6 +540,7 @@ cudaError_t launch_fcch_fine(const FcchArgs &a, int mode, cudaStream_t st)
 		return cudaSuccess;
 	if (a.len > MAX_FCCH_LEN || a.win_len != a.len * a.sps)
 		return cudaErrorInvalidValue;
+	GMR1_INIT_LOCK();       // (the twiddle table in __constant__ memory is per FCCH length: one length per device at a time)
 	static int tw_len[64] = {0};
 	int dev = 0;
 	cudaGetDevice(&dev);

@@ -21,6 +21,13 @@
 
 namespace gmr1 {
 
+std::mutex &init_mutex();
+std::mutex &init_mutex()
+{
+	static std::mutex m;
+	return m;
+}
+
 // ---------------------------------------------------------------------------- codes
 
 static const CodePoly POLY_K5_12 = {2, 5, {0x19, 0x17}};                   // 1+D3+D4 ; 1+D+D2+D4

@@ -3,9 +3,17 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <atomic>
+#include <mutex>
 #include "decode_unit.cuh"
 
 namespace gmr1 {
+
+// The lazy per-device initialisation inside the launchers (table uploads to __constant__ / __device__ memory,
+// cudaFuncSetAttribute, cached device properties) can be reached from several host threads at once (the device pool
+// of api_multi.cu runs one thread per GPU, callers may run one per stream): every launcher holds this lock from its
+// first look at that state until its kernel is enqueued.  Uncontended cost ~20 ns per launch.
+std::mutex &init_mutex();
+#define GMR1_INIT_LOCK() std::lock_guard<std::mutex> gmr1_init_lock_(gmr1::init_mutex())
 
 // ---- stage 3
 cudaError_t launch_decode(int ch, const DecodeArgs &a, cudaStream_t st);

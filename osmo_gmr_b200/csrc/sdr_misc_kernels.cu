@@ -193,6 +193,7 @@ cudaError_t launch_dkab(const MiscArgs &a, cudaStream_t st)
 	const size_t smem = (size_t)MW * ((a.win_len + 1) & ~1) * sizeof(float2);
 	if (smem > 227 * 1024)
 		return cudaErrorInvalidValue;
+	GMR1_INIT_LOCK();
 	static size_t attr_set[64] = {0};
 	int dev = 0;
 	cudaGetDevice(&dev);

@@ -81,6 +81,10 @@ class Lib:
                                   _P, _L, _P, _L, _I, _P],
         "gmr1b200_set_sync_accumulator_reset": [_I],
         "gmr1b200_set_demod_generic": [_I],
+        "gmr1b200_pool_create": [_P, _I, _I, _L, _P],
+        "gmr1b200_pool_size": [_P],
+        "gmr1b200_pool_rx_xcch": [_P, _I, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P],
+        "gmr1b200_pool_fcch_acquire": [_P, _I, _P, _I, _I, _I, _P, _P, _P],
         "gmr1b200_burst_len": [_I],
         "gmr1b200_burst_ebits": [_I],
         "gmr1b200_pi4cxpsk_demod_batch": [_I, _P, _L, _P, _L, _I, _I, _P, _F, _P, _I, _P, _P, _P, _P, _I, _P],
@@ -104,6 +108,12 @@ class Lib:
         self.c.gmr1b200_last_error.restype = ctypes.c_char_p
         self.c.gmr1b200_version.restype = ctypes.c_char_p
         self.c.gmr1b200_kernel_launches.restype = ctypes.c_uint64
+        self.c.gmr1b200_pool_destroy.argtypes = [_P]
+        self.c.gmr1b200_pool_destroy.restype = None
+        self.c.gmr1b200_host_alloc.argtypes = [ctypes.c_size_t]
+        self.c.gmr1b200_host_alloc.restype = _P
+        self.c.gmr1b200_host_free.argtypes = [_P]
+        self.c.gmr1b200_host_free.restype = None
 
     # -- helpers
     def _chk(self, rc, what):
@@ -119,6 +129,17 @@ class Lib:
 
     def init(self, device=0):
         return self._chk(self.c.gmr1b200_init(device), "init")
+
+    def pool_create(self, devices, streams_per_dev=3, chunk_bytes=64 << 20):
+        """gmr1b200_pool_create -> opaque handle (int); devices: list of CUDA ordinals"""
+        arr = (ctypes.c_int * len(devices))(*devices)
+        out = ctypes.c_void_p()
+        self._chk(self.c.gmr1b200_pool_create(ctypes.cast(arr, _P), len(devices), streams_per_dev, chunk_bytes,
+                                              ctypes.cast(ctypes.byref(out), _P)), "pool_create")
+        return out.value
+
+    def pool_destroy(self, pool):
+        self.c.gmr1b200_pool_destroy(pool)
 
     def call(self, name, *args):
         """Raw call by C name with pointer-like python objects converted."""

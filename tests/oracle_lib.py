@@ -208,13 +208,96 @@ class Oracle:
         return out
 
 
-def load():
-    ref = os.path.join(ROOT, "oracle", "_ref", "libgmr1_ref.so")
-    port = os.path.join(ROOT, "oracle", "liboracle.so")
+    # ---------------- batch loops in C (oracle/harness.c): n windows per call, no Python per burst
+    @staticmethod
+    def _iq(x):
+        x = np.ascontiguousarray(x, np.complex64)
+        assert x.ndim == 2
+        return x
+
+    def h_xcch(self, is_ccch, x, sps=4, freq_shift=0.0):
+        x = self._iq(x)
+        n, wl = x.shape
+        l2, crc, conv, toa = np.zeros((n, 24), np.uint8), np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.float32)
+        self.c.oh_xcch(int(is_ccch), p(x), n, wl, sps, ctypes.c_float(freq_shift), p(l2), p(crc), p(conv), p(toa))
+        return l2, crc, conv, toa
+
+    def h_tch3(self, x, ciph=None, m=0, sps=4):
+        x = self._iq(x)
+        n, wl = x.shape
+        f0, f1, bs, conv = np.zeros((n, 10), np.uint8), np.zeros((n, 10), np.uint8), np.zeros((n, 4), np.uint8), np.zeros((n, 2), np.int32)
+        ciph = None if ciph is None else np.ascontiguousarray(ciph, np.uint8)
+        self.c.oh_tch3(p(x), n, wl, sps, p(ciph), m, p(f0), p(f1), p(bs), p(conv))
+        return f0, f1, bs, conv
+
+    def h_facch3(self, x, sps=4):
+        x = self._iq(x)
+        n, wl = x.shape
+        g = n // 4
+        l2, bs, crc, sid = np.zeros((g, 10), np.uint8), np.zeros((g, 32), np.uint8), np.zeros(g, np.int32), np.zeros(4 * g, np.int32)
+        self.c.oh_facch3(p(x), g, wl, sps, p(l2), p(bs), p(crc), p(sid))
+        return l2, bs, crc, sid
+
+    def h_facch9(self, x, sps=4):
+        x = self._iq(x)
+        n, wl = x.shape
+        l2, crc, sid = np.zeros((n, 38), np.uint8), np.zeros(n, np.int32), np.zeros(n, np.int32)
+        self.c.oh_facch9(p(x), n, wl, sps, p(l2), p(crc), p(sid))
+        return l2, crc, sid
+
+    def h_tch9(self, x, n_burst, mode=2, sps=4):
+        x = self._iq(x)
+        n, wl = x.shape
+        nb = (18, 30, 60)[mode]
+        l2, conv = np.zeros((n, nb), np.uint8), np.zeros(n, np.int32)
+        self.c.oh_tch9(p(x), n // n_burst, n_burst, wl, sps, mode, p(l2), p(conv))
+        return l2, conv
+
+    def h_rach(self, x, sb_mask=None, sps=4):
+        x = self._iq(x)
+        n, wl = x.shape
+        r, crc = np.zeros((n, 18), np.uint8), np.zeros(n, np.int32)
+        sb = None if sb_mask is None else np.ascontiguousarray(sb_mask, np.uint8)
+        self.c.oh_rach(p(x), n, wl, sps, p(sb), p(r), p(crc))
+        return r, crc
+
+    def h_fcch_acquire(self, x, sps=4, freq_shift=0.0):
+        x = self._iq(x)
+        n, wl = x.shape
+        rough, align, ferr = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.float32)
+        self.c.oh_fcch_acquire(p(x), n, wl, sps, ctypes.c_float(freq_shift), p(rough), p(align), p(ferr))
+        return rough, align, ferr
+
+    def h_fcch_grid(self, x, shifts, sps=4):
+        x = self._iq(x)
+        n, wl = x.shape
+        sh = np.ascontiguousarray(shifts, np.float32)
+        toa = np.zeros((len(sh), n), np.int32)
+        self.c.oh_fcch_grid(p(x), n, wl, sps, p(sh), len(sh), p(toa))
+        return toa
+
+
+def host_has_avx2():
+    try:
+        flags = open("/proc/cpuinfo").read()
+        return all(f" {k}" in flags for k in ("avx2", "bmi2", "fma", "movbe"))
+    except OSError:
+        return False
+
+
+def load(fast=False):
+    """fast = True: the -march=x86-64-v3 build of the same sources when this host can run it (CPU timing legs);
+    float results are the same in both builds (-ffp-contract=off)."""
+    sfx = "_v3" if fast and host_has_avx2() else ""
+    ref = os.path.join(ROOT, "oracle", "_ref", f"libgmr1_ref{sfx}.so")
+    port = os.path.join(ROOT, "oracle", f"liboracle{sfx}.so")
     if not os.path.exists(ref) and os.path.isdir("/root/reference/src"):
         subprocess.call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"])
     if os.path.exists(ref):
-        return Oracle(ref, "reference")
-    if not os.path.exists(port):
-        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"])
-    return Oracle(port, "port")
+        o = Oracle(ref, "reference")
+    else:
+        if not os.path.exists(port):
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), os.path.basename(port)])
+        o = Oracle(port, "port")
+    o.flags = "-O2 -march=x86-64-v3 -ffp-contract=off" if sfx else "-O2 -ffp-contract=off"
+    return o
