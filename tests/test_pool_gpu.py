@@ -70,8 +70,7 @@ def test_pool_rx_xcch_and_fcch(gpu_lib, oracle, members):
 
 def test_pool_errors(gpu_lib):
     L = gpu_lib
-    import osmo_gmr_b200
-    with pytest.raises(osmo_gmr_b200.lib.Gmr1Error):
+    with pytest.raises(RuntimeError, match="no such device"):
         L.pool_create([99])
-    with pytest.raises(osmo_gmr_b200.lib.Gmr1Error):
+    with pytest.raises(RuntimeError, match="bad argument"):
         L.pool_create([0], streams_per_dev=0)
