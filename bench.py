@@ -1,16 +1,27 @@
 #!/usr/bin/env python
-"""bench.py - decoded bursts/s of the GMR-1 receive hot path (pi/4-CQPSK demod + Viterbi/CRC decode)
-on B200, config 2 of BASELINE.json: batched BCCH / DC6(CCCH) bursts, 1024 ARFCNs x 256 bursts per GPU.
+"""bench.py - decoded bursts/s of the GMR-1 receive hot path (FCCH acquisition + pi/4-CxPSK demod + Viterbi/CRC
+decode) on B200.  Headline workload = config 2 of BASELINE.json: batched BCCH / DC6(CCCH) bursts, 1024 ARFCNs x 256
+bursts per GPU.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-One "step" = one pass of the hot path over the whole batch: FCCH acquisition of every ARFCN (rough
-over a 330 ms window + fine), then demod BCCH, decode BCCH, demod DC6, decode CCCH (6 kernel launches).  `value` = bursts/s with the IQ resident in HBM; `e2e` = the same
-through the C ABI with HOST (pinned) IQ in and host L2/CRC out, copies inside the timed region.
-Multi-GPU: ARFCNs are independent, each rank owns its own 1024 ARFCNs (weak scaling), no data-path
-collective; torch.distributed is used only for the barrier and the max-over-ranks of the time.
-`--impl reference` times the reference's own C path (oracle/_ref, else the oracle port) on the
-host cores on a bounded sample of the same workload.
+One "step" = one pass of the hot path over the whole batch: FCCH acquisition of every ARFCN (rough over a 330 ms
+window + fine), then demod BCCH, decode BCCH, demod DC6, decode CCCH (6 kernel launches).
+  value            bursts/s over EXACTLY K steps with the IQ resident in HBM (CUDA events, max over ranks)
+  sustained        the same loop repeated until >= --min-seconds have passed (the K-step region is ~20 ms)
+  roofline         the demod kernels: algorithmic bytes / CUDA-event time of their launches (serial pass) / measured peak
+  e2e              the same step through the C ABI with pinned HOST IQ in and host L2/CRC out, copies inside the timed
+                   region; e2e.h2d_ceiling_gbs = the same bytes on the same threads / streams with no kernels
+  cpu_baseline     the reference's own C path (oracle/_ref, -O2 -march=x86-64-v3) on the host cores, compiled loops
+                   (oracle/harness.c), on the head of the same IQ; also the L2 / CRC parity check
+  configs          BASELINE configs 3 and 4 at full size (N = 1 only): bursts/s, per-kernel times, their own demod
+                   roofline, and a 4 096-burst-per-type comparison with the CPU reference
+  sweep            BASELINE config 5: ARFCN count 1k .. 64k in total, sharded over the ranks, 1 s recording slice per
+                   ARFCN (FCCH search + 25 bursts), device-resident and streamed from pinned host memory
+Multi-GPU: ARFCNs are independent, each rank owns its own ARFCNs (weak scaling), no data-path collective;
+torch.distributed is used only for the barrier and the max-over-ranks of the time.  --single-process (with --gpus N,
+not under torchrun) runs the end-to-end step of all N GPUs from ONE process through the library's device pool.
+`--impl reference` times the reference's own C path on the host cores on a bounded sample of the same workload.
 """
 import argparse
 import json
@@ -77,64 +88,61 @@ def fcch_windows(n_arfcn, seed, lo=0, hi=None):
 # CPU reference arm (also the cpu_baseline leg): the ONLY place bench.py executes oracle/
 # ------------------------------------------------------------------------------------------------
 def _cpu_worker(job):
-    path, kind, lo, hi = job
+    """one chunk of one burst type through the reference's C functions (compiled loops, oracle/harness.c)"""
+    path, kind, lo, hi, extra = job
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
-    o = oracle_lib.load()
-    x = np.load(path, mmap_mode="r")
-    if kind == "fcch":                      # rough + fine acquisition, as Workload.fcch() does on the GPU
-        out = np.zeros((hi - lo, 2), np.float64)
-        t0 = time.perf_counter()
-        for i in range(lo, hi):
-            w = np.array(x[i])
-            _, toa = o.fcch_rough(w, SPS, 0.0)
-            a = min(max(toa, 0), FCCH_WIN - 117 * SPS)
-            _, ftoa, ferr = o.fcch_fine(w[a:a + 117 * SPS], SPS, 0.0)
-            out[i - lo] = (toa + ftoa, ferr)
-        return lo, out, None, time.perf_counter() - t0, o.kind
-    chan = "bcch" if kind == "bcch" else "ccch"
-    l2 = np.zeros((hi - lo, 24), np.uint8)
-    crc = np.zeros(hi - lo, np.int32)
+    o = oracle_lib.load(fast=True)
+    x = np.ascontiguousarray(np.load(path, mmap_mode="r")[lo:hi])
+    sl = lambda key: None if extra.get(key) is None else np.ascontiguousarray(extra[key][lo:hi])
     t0 = time.perf_counter()
-    for i in range(lo, hi):
-        _, eb, _, _, _ = o.demod(kind, np.array(x[i]), SPS, 0.0)
-        l2[i - lo], crc[i - lo], _ = o.simple_decode(chan, eb)
-    return lo, l2, crc, time.perf_counter() - t0, o.kind
+    if kind == "fcch":                      # rough + fine acquisition, as Workload.fcch() does on the GPU
+        _, align, ferr = o.h_fcch_acquire(x, SPS, 0.0)
+        res = (align, ferr)
+    elif kind == "fcch_grid":
+        res = (o.h_fcch_grid(x, extra["shifts"], SPS),)
+    elif kind in ("bcch", "dc6"):
+        res = o.h_xcch(kind == "dc6", x, SPS, 0.0)[:2]
+    elif kind == "tch3":
+        res = o.h_tch3(x, sl("ciph"), 0, SPS)
+    elif kind == "facch3":
+        res = o.h_facch3(x, SPS)
+    elif kind == "facch9":
+        res = o.h_facch9(x, SPS)
+    elif kind == "tch9":
+        res = o.h_tch9(x, extra["n_burst"], 2, SPS)
+    elif kind == "rach":
+        res = o.h_rach(x, sl("sb_mask"), SPS)
+    else:
+        raise ValueError(kind)
+    return kind, lo, res, time.perf_counter() - t0, o.kind, o.flags
 
 
-def cpu_reference_pass(files, cores):
-    """files: {kind: (npy path, n)}; runs the reference C path over every burst on `cores` processes.
-    Returns (bursts, wall seconds, {kind: (l2, crc)}, oracle kind)."""
+def cpu_reference_pass(files, cores, pool=None):
+    """files: {kind: (npy path, n units, unit granularity, extra)}; runs the reference C path over everything on
+    `cores` processes.  Returns (wall seconds, {kind: tuple of result arrays}, oracle kind, compiler flags)."""
     jobs = []
-    for kind, (path, n) in files.items():
-        per = max(1, (n + cores - 1) // cores)
-        if kind == "fcch":
+    for kind, (path, n, gran, extra) in files.items():
+        per = max(gran, ((n + cores - 1) // cores + gran - 1) // gran * gran)
+        if kind.startswith("fcch"):
             per = max(1, min(per, 8))           # short jobs, scheduled first, so they spread over the cores
-        jobs += [(path, kind, lo, min(n, lo + per)) for lo in range(0, n, per)]
-    jobs.sort(key=lambda j: j[1] != "fcch")
-    ctx = mp.get_context("spawn")
-    with ctx.Pool(cores) as pool:
+        jobs += [(path, kind, lo, min(n, lo + per), extra) for lo in range(0, n, per)]
+    jobs.sort(key=lambda j: not j[1].startswith("fcch"))
+    own = pool is None
+    if own:
+        pool = mp.get_context("spawn").Pool(cores)
         pool.map(_cpu_noop, range(cores))                       # start the workers outside the timing
-        t0 = time.perf_counter()
-        res = pool.map(_cpu_worker, jobs)
-        wall = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    res = pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    if own:
+        pool.close()
     out = {}
-    okind = res[0][4]
-    for kind, (path, n) in files.items():
-        if kind == "fcch":
-            acq = np.zeros((n, 2), np.float64)
-            for (p, k, lo, hi), r in zip(jobs, res):
-                if k == kind:
-                    acq[lo:hi] = r[1]
-            out[kind] = acq
-            continue
-        l2 = np.zeros((n, 24), np.uint8)
-        crc = np.zeros(n, np.int32)
-        for (p, k, lo, hi), r in zip(jobs, res):
-            if k == kind:
-                l2[lo:hi], crc[lo:hi] = r[1], r[2]
-        out[kind] = (l2, crc)
-    return sum(n for k, (_, n) in files.items() if k != "fcch"), wall, out, okind
+    for kind in files:
+        parts = sorted((r for r in res if r[0] == kind), key=lambda r: r[1])
+        axis = 1 if kind == "fcch_grid" else 0
+        out[kind] = tuple(np.concatenate([p[2][i] for p in parts], axis=axis) for i in range(len(parts[0][2])))
+    return wall, out, res[0][4], res[0][5]
 
 
 def _cpu_noop(i):
@@ -146,17 +154,25 @@ def shm_dir():
     return d
 
 
+def save_shm(tag, x):
+    path = os.path.join(shm_dir(), f"gmr1_bench_{tag}_{os.getpid()}.npy")
+    np.save(path, x)
+    return path
+
+
 def run_reference_arm(args):
-    """bench.py --impl reference: pure CPU, numpy-generated bounded sample of the config-2 workload"""
+    """bench.py --impl reference: pure CPU (no kernel of this repo runs): the reference's C functions, one process per
+    host core, on a numpy-generated bounded sample of the config-2 workload (same burst formats, SNR grid, offsets and
+    burst : acquisition ratio as the GPU arm; rates are per burst, so the sample size does not enter the ratio)"""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
     import sigen
-    o = oracle_lib.load()
+    o = oracle_lib.load(fast=True)
     cores = os.cpu_count() or 1
-    per_kind = min(32768, 1024 * cores)            # bounded sample: ~0.15 ms of C work per burst and core
+    per_kind = min(32768, 1024 * cores)            # bounded sample: ~0.14 ms of C work per burst and core
     files = {}
     for kind in ("bcch", "dc6"):
         p = burst_params(per_kind, kind, 77 + BT[kind])
@@ -165,20 +181,20 @@ def run_reference_arm(args):
         rng = np.random.default_rng(5)
         xs = [sigen.modulate(kind, hard[i:i + 512], SPS, WIN[kind], p["toa"][i:i + 512], p["cfo"][i:i + 512],
                              p["phase"][i:i + 512], p["esn0"][i:i + 512], rng) for i in range(0, per_kind, 512)]
-        path = os.path.join(shm_dir(), f"gmr1_bench_ref_{kind}_{os.getpid()}.npy")
-        np.save(path, np.concatenate(xs))
-        files[kind] = (path, per_kind)
+        files[kind] = (save_shm("ref_" + kind, np.concatenate(xs)), per_kind, 1, {})
     n_f = max(1, 2 * per_kind // 256)               # one FCCH acquisition per 256 bursts, as in config 2
     _, _, blocks = fcch_windows(n_f, 176)
-    path = os.path.join(shm_dir(), f"gmr1_bench_ref_fcch_{os.getpid()}.npy")
-    np.save(path, np.concatenate([x for _, _, x in blocks]))
-    files["fcch"] = (path, n_f)
+    files["fcch"] = (save_shm("ref_fcch", np.concatenate([x for _, _, x in blocks])), n_f, 1, {})
+    nb = 2 * per_kind
     times = []
+    pool = mp.get_context("spawn").Pool(cores)
+    pool.map(_cpu_noop, range(cores))
     for step in range(args.warmup + args.steps):
-        nb, wall, _, okind = cpu_reference_pass(files, cores)
+        wall, _, okind, flags = cpu_reference_pass(files, cores, pool)
         if step >= args.warmup:
             times.append(wall)
-    for path, _ in files.values():
+    pool.close()
+    for path, _, _, _ in files.values():
         os.unlink(path)
     t = float(np.mean(times))
     val = nb / t
@@ -187,13 +203,189 @@ def run_reference_arm(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic",
         "config": {"workload": "config2: BCCH + DC6/CCCH pi/4-CQPSK demod + K5 r1/2 Viterbi + CRC16, sps 4",
-                   "bursts_per_step": nb, "sample": f"{per_kind} BCCH + {per_kind} DC6 bursts + {n_f} FCCH windows (numpy generator)"},
-        "cpu_baseline": {"value": val, "unit": "bursts/s", "cores": cores, "kind": okind,
-                         "sample": f"{nb} bursts + {n_f} FCCH acquisitions per step, one process per core"},
+                   "bursts_per_step": nb,
+                   "sample": f"{per_kind} BCCH + {per_kind} DC6 bursts + {n_f} FCCH windows per step: a bounded SAMPLE of the "
+                             "GPU arm's workload (same formats, 6/10/15/30 dB grid, offsets, burst : acquisition ratio), made by "
+                             "the numpy generator tests/sigen.py because no GPU code may run in this arm; rates are per burst"},
+        "cpu_baseline": {"value": val, "unit": "bursts/s", "cores": cores, "kind": okind, "flags": flags,
+                         "sample": f"{nb} bursts + {n_f} FCCH acquisitions per step, one process per core, compiled loops "
+                                   "(oracle/harness.c) around the reference's own functions"},
         "e2e": {"value": val, "unit": "bursts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE config 5: ARFCN sweep, 1 s recording slice per ARFCN, device-resident and host-streamed
+# ------------------------------------------------------------------------------------------------
+def run_sweep(L, torch, dist, dev, world, rank, barrier, totals, chunk_arfcns):
+    """Every rank processes total / world ARFCNs of each sweep point in chunks of <= chunk_arfcns slices (748.8 KB of
+    IQ each): FCCH rough + fine once per slice, then its 25 bursts (4 BCCH, 12 CCCH, 9 NT3 speech) demodulated and
+    decoded in place by window offsets.  'resident': the chunk lies in HBM; 'streamed': every chunk is copied from pinned
+    host memory first (two streams, two device buffers, copy of chunk i+1 overlaps the kernels of chunk i) and its
+    results go back to pinned host memory.  The pinned ring holds ONE chunk of distinct IQ that every copy re-reads
+    (the bytes over PCIe are real, the content repeats).  Times are max over ranks."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import workloads as wl
+    C = chunk_arfcns
+    ck = wl.Config5Chunk(L, torch, dev, C, seed=5000 + rank)
+    host = torch.empty(ck.iq.shape, dtype=torch.float32).pin_memory()
+    host.copy_(ck.iq)
+    dbuf = [torch.empty_like(ck.iq), torch.empty_like(ck.iq)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    res_host = [ck.result_buffers(pinned=True) for _ in range(2)]
+    for s in range(2):
+        ck.process(ck.iq, streams[s].cuda_stream, C, s)
+    torch.cuda.synchronize()
+    sane = ck.sane()
+    out = []
+    for total in totals:
+        n_local = total // world
+        if n_local < 1:
+            continue
+        chunks = [C] * (n_local // C) + ([n_local % C] if n_local % C else [])
+
+        def resident():
+            for i, c in enumerate(chunks):
+                ck.process(ck.iq, streams[i % 2].cuda_stream, c, i % 2)
+
+        def streamed():
+            for i, c in enumerate(chunks):
+                s = i % 2
+                with torch.cuda.stream(streams[s]):
+                    dbuf[s][:c].copy_(host[:c], non_blocking=True)
+                ck.process(dbuf[s], streams[s].cuda_stream, c, s)
+                with torch.cuda.stream(streams[s]):
+                    ck.results_to_host(res_host[s], c, s)
+
+        times = {}
+        for name, fn in (("resident", resident), ("streamed", streamed)):
+            fn()
+            barrier()
+            t0 = time.perf_counter()
+            fn()
+            for s in streams:
+                s.synchronize()
+            barrier()
+            t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            times[name] = float(t[0])
+        n_all = n_local * world
+        out.append({"arfcns": n_all, "bursts": n_all * 25, "acquisitions": n_all,
+                    "resident_bursts_per_s": n_all * 25 / times["resident"], "resident_ms": 1e3 * times["resident"],
+                    "streamed_bursts_per_s": n_all * 25 / times["streamed"], "streamed_ms": 1e3 * times["streamed"],
+                    "streamed_h2d_gbs": n_all * wl.SLICE * 8 / times["streamed"] / 1e9})
+    return {"what": "config 5: per ARFCN a 1 s slice (748.8 KB): FCCH rough + fine, then 25 bursts (4 BCCH, 12 CCCH, 9 NT3 "
+                    f"speech / TCH3) cut by window offsets; chunks of {C} ARFCNs; total ARFCNs sharded over {world} rank(s)",
+            "chunk_decodes_correctly": bool(sane), "points": out}
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE configs 3 and 4 at full size (one GPU): throughput, demod roofline, parity of the head vs the CPU reference
+# ------------------------------------------------------------------------------------------------
+def run_configs(L, torch, dev, peak_gbs, cores, scale, reps, n_check):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import workloads as wl
+    out = {}
+    pool = None
+    if cores:
+        pool = mp.get_context("spawn").Pool(cores)
+        pool.map(_cpu_noop, range(cores))
+    for cid in ("3", "4"):
+        if cid == "3":
+            w = wl.Config3(L, torch, dev, arfcns=max(8, int(4096 * scale)), frames=128, n_check=n_check)
+            dem = [("demod_nt3_speech", "nt3_speech", w.n_sp), ("demod_nt3_facch", "nt3_facch", w.n_fa)]
+            name = f"config3: NT3 traffic, {w.n_sp} speech bursts (TCH3, half A5/1) + {w.n_fa} FACCH3 bursts"
+        else:
+            w = wl.Config4(L, torch, dev, arfcns=max(8, int(8192 * scale)), per=64, n_check=n_check)
+            dem = [("demod_nt9_facch9", "nt9", w.n_f9), ("demod_nt9_tch9", "nt9", w.n_t9), ("demod_rach", "rach", w.n_ra)]
+            name = (f"config4: {w.n_f9} FACCH9 + {w.n_t9} TCH9-9k6 (chains of 3) over NT9, {w.n_ra} RACH, "
+                    f"{w.arfcns} x 5-shift FCCH search + fine")
+        tm = wl.Timer(torch)
+        steps = w.steps()
+        for k, f in steps.items():
+            tm.run(k, f, reps)
+        tm.run("whole_chain", w.run, reps)
+        byt = sum(wl.demod_bytes(L, bt) * n for _, bt, n in dem)
+        dem_ms = sum(tm.ms[k] for k, _, _ in dem)
+        rec = {"workload": name, "bursts": w.n_bursts, "iq_bytes": int(w.iq_bytes),
+               "bursts_per_s": w.n_bursts / tm.ms["whole_chain"] * 1e3, "ms": {k: round(v, 4) for k, v in tm.ms.items()},
+               "roofline": {"bound": "hbm", "kernel": "demod kernels of this config", "achieved": byt / dem_ms / 1e6,
+                            "peak": peak_gbs, "unit": "GB/s", "frac": byt / dem_ms / 1e6 / peak_gbs,
+                            "per_format": {k: wl.demod_bytes(L, bt) * n / tm.ms[k] / 1e6 / peak_gbs for k, bt, n in dem}}}
+        if cid == "3":
+            rec["tch3_acs_per_s"] = w.n_sp * 12288 / tm.ms["decode_tch3"] * 1e3
+        else:
+            rec["fcch_searches_per_s"] = w.arfcns * 5 / tm.ms["fcch_5_shift_search_and_fine"] * 1e3
+            rec["fcch_share_of_chain"] = tm.ms["fcch_5_shift_search_and_fine"] / tm.ms["whole_chain"]
+        if pool is not None:
+            head = w.head()
+            files = {}
+            for kind, (x, extra) in w.head_iq().items():
+                gran = {"facch3": 4, "tch9": 3}.get(kind, 1)
+                files[kind] = (save_shm(f"cfg{cid}_{kind}", x), len(x), gran, extra)
+            wall, cpu, okind, flags = cpu_reference_pass(files, cores, pool)
+            for path, _, _, _ in files.values():
+                os.unlink(path)
+            same, info = w.compare(head, cpu)
+            units = sum(n for k, (_, n, _, _) in files.items() if not k.startswith("fcch"))
+            rec["parity_vs_cpu_reference"] = {"units_per_type": w.n_check, "identical": same, "all_identical": all(same.values()),
+                                              "oracle": okind, **info}
+            rec["cpu_baseline"] = {"value": units / wall, "unit": "bursts/s", "cores": cores, "kind": okind, "flags": flags,
+                                   "sample": f"head of the GPU workload: {w.n_check} units per burst type"
+                                             + (", 256 x 5 FCCH searches" if cid == "4" else "")}
+        out[cid] = rec
+        del w
+        torch.cuda.empty_cache()
+    if pool is not None:
+        pool.close()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# the end-to-end step of several GPUs from ONE process (library device pool, csrc/api_multi.cu)
+# ------------------------------------------------------------------------------------------------
+def run_pool_e2e(L, torch, W, host_iq, host_fcch, n_gpus, steps):
+    """host IQ of n_gpus x (this GPU's ARFCNs) in pinned memory -> gmr1b200_pool_fcch_acquire + gmr1b200_pool_rx_xcch
+    (BCCH, DC6): ARFCN a is processed on device a mod n_gpus, host-side gather of L2 / CRC.  The content of ARFCN a
+    is that of local ARFCN a mod 1024, so the results must equal the device-resident pass replicated."""
+    have = torch.cuda.device_count()
+    if have < n_gpus:
+        return {"skipped": f"{have} GPU(s) visible, {n_gpus} asked for"}
+    per = {k: W.n[k] // W.n_arfcn for k in W.iq}
+    rep = lambda t: t.repeat((n_gpus,) + (1,) * (t.dim() - 1)).pin_memory()
+    iq = {k: rep(host_iq[k]) for k in W.iq}
+    fc = rep(host_fcch)
+    n_arfcn = W.n_arfcn * n_gpus
+    l2 = {k: torch.empty((W.n[k] * n_gpus, 24), dtype=torch.uint8).pin_memory() for k in W.iq}
+    crc = {k: torch.empty(W.n[k] * n_gpus, dtype=torch.int32).pin_memory() for k in W.iq}
+    align = torch.empty(n_arfcn, dtype=torch.int32).pin_memory()
+    ferr = torch.empty(n_arfcn, dtype=torch.float32).pin_memory()
+    pool = L.pool_create(list(range(n_gpus)), streams_per_dev=3, chunk_bytes=64 << 20)
+
+    def step():
+        L.call("gmr1b200_pool_fcch_acquire", pool, 0, fc, n_arfcn, FCCH_WIN, SPS, None, align, ferr)
+        for k in W.iq:
+            L.call("gmr1b200_pool_rx_xcch", pool, CHAN[k], iq[k], n_arfcn, per[k], wlen(k), SPS, 0.0, l2[k], crc[k], None, None)
+
+    try:
+        step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        dt = (time.perf_counter() - t0) / steps
+    finally:
+        L.pool_destroy(pool)
+    same = all(bool((l2[k].view(n_gpus, -1) == W.l2[k].cpu().view(1, -1)).all()) and
+               bool((crc[k].view(n_gpus, -1) == W.crc[k].cpu().view(1, -1)).all()) for k in W.iq)
+    nb = sum(W.n.values()) * n_gpus
+    h2d = sum(t.numel() * 4 for t in iq.values()) + fc.numel() * 4
+    return {"devices": n_gpus, "value": nb / dt, "unit": "bursts/s", "ms_per_step": 1e3 * dt,
+            "h2d_bytes_per_step": int(h2d), "h2d_gbs_total": h2d / dt / 1e9, "same_results_as_device_path": same,
+            "how": "one process, gmr1b200_pool_*: one feeder thread + 3 streams per GPU, ARFCN a on device a mod G, 64 MB chunks"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -408,6 +600,25 @@ def run_gpu_arm(args):
     barrier()
     launches = L.kernel_launches() - launches0
     ms_total = t_start.elapsed_time(t_end)
+    # the same loop until >= --min-seconds have passed (the K-step region above is the contract's number; at ~1 ms per
+    # step it is only ~20 ms long, so the long run sits next to it)
+    s_steps, s_ms = 0, 0.0
+    if args.min_seconds > 0:
+        per = max(ms_total / args.steps, 1e-3)
+        s_steps = int(np.ceil(1e3 * args.min_seconds / per))
+        s0, s1 = ev(), ev()
+        stream2.wait_stream(stream)
+        stream3.wait_stream(stream)
+        s0.record(stream)
+        stream2.wait_event(s0)
+        stream3.wait_event(s0)
+        for _ in range(s_steps):
+            step()
+        stream.wait_stream(stream2)
+        stream.wait_stream(stream3)
+        s1.record(stream)
+        barrier()
+        s_ms = s0.elapsed_time(s1)
     # roofline pass: the same K steps serially on one stream with CUDA events around every demod launch
     timers = []
     r_start, r_end = ev(), ev()
@@ -479,6 +690,33 @@ def run_gpu_arm(args):
         for t in th:
             t.join()
 
+    # the ceiling under the end-to-end number: the same bytes from the same pinned buffers on the same threads and
+    # streams, copies only (no kernels, no results)
+    def h2d_thread(t):
+        torch.cuda.set_device(local_rank)
+        with torch.cuda.stream(streams[t]):
+            if t == 0:
+                W.fcch_iq.copy_(host_fcch, non_blocking=True)
+            for k, lo, hi in jobs[t::n_thr]:
+                W.iq[k][lo:hi].copy_(host_iq[k][lo:hi], non_blocking=True)
+        streams[t].synchronize()
+
+    def threads_step(fn):
+        th = [threading.Thread(target=fn, args=(t,)) for t in range(n_thr)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+
+    threads_step(h2d_thread)
+    barrier()
+    p_steps = 3
+    t0 = time.perf_counter()
+    for _ in range(p_steps):
+        threads_step(h2d_thread)
+    barrier()
+    h2d_ms = 1e3 * (time.perf_counter() - t0) / p_steps
+
     for _ in range(2):
         e2e_step()
     barrier()
@@ -493,16 +731,30 @@ def run_gpu_arm(args):
     e2e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0)) / e_steps
 
     # ---------------- reduce over ranks (time = max)
-    t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, e2e_ms, h2d_ms, s_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms = float(t[0]), float(t[1])
+    ms_total, e2e_ms, h2d_ms, s_ms = (float(v) for v in t)
     ms_step = ms_total / args.steps
 
     crc_ok = float(sum(int((W.crc[k] == 0).sum()) for k in W.crc)) / nb
     # the e2e pass must have produced the same answers as the device-resident pass
     e2e_same = all(bool((host_l2[k] == W.l2[k].cpu()).all()) and bool((host_crc[k] == W.crc[k].cpu()).all())
                    for k in W.l2)
+
+    # ---------------- the whole end-to-end step of several GPUs from ONE process through the library's device pool
+    pool_e2e = None
+    if args.single_process and world == 1 and args.gpus > 1:
+        pool_e2e = run_pool_e2e(L, torch, W, host_iq, host_fcch, args.gpus, min(args.steps, 5))
+
+    # ---------------- config 5 sweep (all ranks)
+    sweep = None
+    del host_iq, host_fcch
+    if not args.no_sweep:
+        totals = [1024 * k for k in (1, 2, 4, 8, 16, 32, 64)]
+        if args.sweep_max:
+            totals = [t for t in totals if t <= args.sweep_max]
+        sweep = run_sweep(L, torch, dist if world > 1 else None, dev, world, rank, barrier, totals, args.sweep_chunk)
 
     if rank != 0:
         if world > 1:
@@ -534,59 +786,84 @@ def run_gpu_arm(args):
         peak, peak_src = float(mp_["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
     except Exception:
         pass
-    traffic = None
+    # ncu counters of the dominant kernels (DRAM bytes, warp-instructions per launch): read from the committed summary
+    # of tools/kernel_counters.py, and only used when that summary was taken on the build that is being timed
+    traffic, counters, build = None, None, L.version().split("build ")[-1]
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "demod_traffic.json")))["dram_bytes_per_launch"]
+        kc = json.load(open(os.path.join(ROOT, "profiles", "kernel_counters.json")))
+        if kc.get("build") == build:
+            counters = kc["kernels"]
+            d = [v for k, v in counters.items() if k.startswith("demod")]
+            traffic = sum(v["dram_bytes"] for v in d) / len(d)
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": "demod_kernel (BCCH + DC6 launches)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "kernel_share_of_step": dem_ms / ms_serial, "measured_in": "serial pass (1 stream), same K steps",
                 "serial_ms_per_step": ms_serial / args.steps,
-                "bytes_per_launch": dem_bytes / len(timers), "ms_per_launch": dem_ms / len(timers)}
+                "bytes_per_launch": dem_bytes / len(timers), "ms_per_launch": dem_ms / len(timers),
+                "traffic_source": ("profiles/kernel_counters.json (ncu, this build)" if traffic else
+                                   "none: profiles/kernel_counters.json is absent or from another build"),
+                "per_format": {k: DEMOD_BYTES[k] * W.n[k] / (sum(a.elapsed_time(b) for kk, a, b in dem if kk == k) /
+                                                               sum(1 for kk, _, _ in dem if kk == k) * 1e-3) / 1e9 / peak
+                               for k in W.n}}
 
     # Viterbi kernel: integer-ALU-bound; 212 trellis steps x 16 states per BCCH/CCCH codeword
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     alu_peak = sms * 128 * 1.965e9            # int32 lane-ops/s at the max SM clock (128 lanes per SM)
     viterbi = {"kernel": "decode_tpc_kernel<BCCH|CCCH>", "codewords_per_s": dec_cw / (dec_ms * 1e-3),
                "acs_state_updates_per_s": 3392 * dec_cw / (dec_ms * 1e-3), "ms_per_launch": dec_ms / len(dec),
-               "thread_instr_per_state_update": 7.8,
-               "frac_of_int32_issue_peak": 7.8 * 3392 * dec_cw / (dec_ms * 1e-3) / alu_peak,
-               "note": "7.8 thread-instructions per state update all-in (gather, ACS, traceback, CRC, packing): 9.1 from ncu "
-                       "smsp__inst_executed on an earlier build, less the 4 564 of 30 867 instructions per codeword that "
-                       "left the trellis loops since (static SASS count, 270 -> 227 per two steps); "
+               "thread_instr_per_state_update": None, "frac_of_int32_issue_peak": None,
+               "note": "ACS rate is measured here; instructions per state update come from ncu smsp__inst_executed of "
+                       "this build (profiles/kernel_counters.json) and are omitted when that file is from another build; "
                        "peak = SMs x 128 lanes x 1.965 GHz"}
+    if counters:
+        d = [v for k, v in counters.items() if k.startswith("decode")]
+        if d:
+            ipu = sum(v["warp_inst"] for v in d) * 32.0 / (sum(v["units"] for v in d) * 3392)
+            viterbi["thread_instr_per_state_update"] = ipu
+            viterbi["frac_of_int32_issue_peak"] = ipu * 3392 * dec_cw / (dec_ms * 1e-3) / alu_peak
 
     # ---------------- CPU baseline leg (rank 0, N = 1): reference C path on a bounded sample + parity
-    cpu = None
+    cpu, configs = None, None
+    cores = os.cpu_count() or 1
     if world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
         m = min(W.n["bcch"], max(1024, 4096 * cores))      # ~20 core-seconds of reference C work
         n_f = min(W.n_arfcn, max(1, 2 * m // args.bursts_per_arfcn))
         files = {}
         for k in ("bcch", "dc6"):
             x = W.iq[k][:m].cpu().numpy().view(np.complex64).reshape(m, wlen(k))
-            path = os.path.join(shm_dir(), f"gmr1_bench_{k}_{os.getpid()}.npy")
-            np.save(path, x)
-            files[k] = (path, m)
-        path = os.path.join(shm_dir(), f"gmr1_bench_fcch_{os.getpid()}.npy")
-        np.save(path, W.fcch_iq[:n_f].cpu().numpy().view(np.complex64).reshape(n_f, FCCH_WIN))
-        files["fcch"] = (path, n_f)
-        nbc, wall, out, okind = cpu_reference_pass(files, cores)
-        for path, _ in files.values():
+            files[k] = (save_shm(k, x), m, 1, {})
+        files["fcch"] = (save_shm("fcch", W.fcch_iq[:n_f].cpu().numpy().view(np.complex64).reshape(n_f, FCCH_WIN)), n_f, 1, {})
+        pool = mp.get_context("spawn").Pool(cores)
+        pool.map(_cpu_noop, range(cores))
+        wall, out, okind, flags = cpu_reference_pass(files, cores, pool)
+        # one core alone on a slice of the same sample (BASELINE.md run B2: bursts/s/core)
+        m1 = min(m, 2048)
+        one = {k: (files[k][0], m1, m1, {}) for k in ("bcch", "dc6")}
+        one["fcch"] = (files["fcch"][0], max(1, 2 * m1 // args.bursts_per_arfcn), 8, {})
+        wall1, _, _, _ = cpu_reference_pass(one, 1, pool)
+        pool.close()
+        for path, _, _, _ in files.values():
             os.unlink(path)
         acq = out.pop("fcch")
         g_toa = W.fcch_align[:n_f].cpu().numpy()
-        fcch["toa_identical_to_reference"] = bool((acq[:, 0] == g_toa).all())
+        fcch["toa_identical_to_reference"] = bool((acq[0] == g_toa).all())
         fcch["freq_err_max_abs_diff_vs_reference_rad_per_sym"] = float(
-            np.abs(acq[:, 1] - W.fcch_ferr[:n_f].cpu().numpy()).max())
+            np.abs(acq[1] - W.fcch_ferr[:n_f].cpu().numpy()).max())
         same = all(bool((out[k][0] == W.l2[k][:m].cpu().numpy()).all()) and
                    bool((out[k][1] == W.crc[k][:m].cpu().numpy()).all()) for k in out)
-        cpu = {"value": nbc / wall, "unit": "bursts/s", "cores": cores, "kind": okind,
+        cpu = {"value": 2 * m / wall, "unit": "bursts/s", "cores": cores, "kind": okind, "flags": flags,
                "sample": f"first {m} BCCH + {m} DC6 bursts and {n_f} FCCH windows of the GPU workload, one process "
-                         f"per core, {wall:.2f} s wall",
+                         f"per core, compiled loops (oracle/harness.c), {wall:.2f} s wall",
+               "single_core_bursts_per_s": 2 * m1 / wall1,
                "l2_crc_identical_to_gpu": same}
 
+    # ---------------- BASELINE configs 3 and 4 at full size (N = 1)
+    if world == 1 and not args.no_configs:
+        configs = run_configs(L, torch, dev, peak, 0 if args.no_cpu_baseline else cores, args.config_scale, 5, 4096)
+
+    h2d_bytes = int(sum(W.iq[k].numel() * 4 for k in W.iq) + W.fcch_iq.numel() * 4)
     line = {
         "metric": "decoded bursts/s (FCCH sync+demod+Viterbi)", "value": nb * world / (ms_step * 1e-3),
         "unit": "bursts/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -600,9 +877,18 @@ def run_gpu_arm(args):
                    "parallelism": f"arfcn-sharded x{world}, no collective",
                    "streams_per_gpu": args.streams},
         "crc_ok_frac": crc_ok,
+        "sustained": {"steps": s_steps, "seconds": s_ms * 1e-3,
+                      "value": (nb * world * s_steps / (s_ms * 1e-3)) if s_ms > 0 else None, "unit": "bursts/s",
+                      "what": "the same step loop run for >= --min-seconds after the K-step region"},
         "e2e": {"value": nb * world / (e2e_ms * 1e-3), "unit": "bursts/s",
-                "h2d_bytes_per_step": int(sum(W.iq[k].numel() * 4 for k in W.iq) + W.fcch_iq.numel() * 4),
+                "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": int(nb * 28 + W.n_arfcn * 8), "ms_per_step": e2e_ms,
+                "h2d_gbs_per_gpu": h2d_bytes / (e2e_ms * 1e-3) / 1e9,
+                "h2d_ceiling_gbs_per_gpu": h2d_bytes / (h2d_ms * 1e-3) / 1e9,
+                "frac_of_ceiling": h2d_ms / e2e_ms,
+                "ceiling_how": "the same pinned buffers, chunks, threads and streams with the copies only (no kernels), "
+                               "all ranks at once, max over ranks",
+                "single_process_pool": pool_e2e,
                 "how": f"{len(jobs)} chunks on {n_thr} host threads/streams through gmr1b200_*_batch with pinned "
                        "host IQ in and host L2/CRC out", "same_results_as_device_path": e2e_same},
         "gpu_launches": int(launches),
@@ -610,6 +896,9 @@ def run_gpu_arm(args):
         "viterbi": viterbi,
         "fcch": fcch,
         "cpu_baseline": cpu,
+        "configs": configs,
+        "sweep": sweep,
+        "build": L.version(),
         "clocks": sampler.summary(),
     }
     sys.stdout.flush()
@@ -629,6 +918,15 @@ def main():
     ap.add_argument("--e2e-chunks", type=int, default=8)
     ap.add_argument("--streams", type=int, default=3, choices=[1, 2, 3])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip BASELINE configs 3 and 4")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the config-5 ARFCN sweep")
+    ap.add_argument("--config-scale", type=float, default=1.0, help="fraction of the ARFCN counts of configs 3 / 4")
+    ap.add_argument("--sweep-max", type=int, default=0, help="largest total ARFCN count of the sweep (0: 65536)")
+    ap.add_argument("--sweep-chunk", type=int, default=1024, help="ARFCN slices per streamed chunk")
+    ap.add_argument("--min-seconds", type=float, default=1.0, help="length of the sustained run (0: skip)")
+    ap.add_argument("--single-process", action="store_true",
+                    help="with --gpus N (not under torchrun): additionally run the end-to-end step of all N GPUs from "
+                         "this one process through the library's device pool")
     ap.add_argument("--demod-generic", action="store_true",
                     help="A/B: force the generic demodulation kernel instead of the per-format ones")
     args = ap.parse_args()
