@@ -300,6 +300,38 @@ int gmr1b200_rx_bcch_ass_batch(const float *iq, int64_t iq_len, const int64_t *r
                                int32_t *n_frames, int32_t *align_out, float *freq_err_out,
                                int32_t *tch3, float *tch3_energy, void *stream);
 
+/* ---- the whole receiver frame loop, traffic channels included ----------------------------------
+ * replaces process_bcch (src/gmr1_rx.c:853-895) with everything it calls per frame: rx_bcch / rx_ccch (as
+ * gmr1b200_rx_bcch_batch above), rx_tch3 (:538-600) once an IMMEDIATE ASSIGNMENT has been seen on the CCCH - energy
+ * gate, gmr1_dkab_demod or gmr1_pi4cxpsk_detect, running energy averages, release after ten silent frames, FACCH3
+ * assembly over four frames with the plain attempt / ciphered retry / cipher discovery of _rx_tch3_facch_flush
+ * (:394-452), speech bursts through gmr1_a5 + gmr1_tch3_decode - and rx_tch9 (:276-355) once a good FACCH3 message is
+ * an ASSIGNMENT COMMAND 1: NT9 demodulation, FACCH9 (sync sequence 0) or TCH9-9k6 through the channel's depth-3
+ * interleaver history.  n channels in lock step, all state on the device, no host round trip.
+ *   tch_ofs [n]   first sample of the channel's traffic-carrier recording in iq (what gmr1_rx takes as its second
+ *                 file), -1 = none; csd_ofs [n] or NULL the same for the TCH9 carrier (fourth argument of gmr1_rx);
+ *                 both recordings are as long as the BCCH one (rec_len), as the reference assumes (:163)
+ *   kc [n][8]     cipher keys, NULL = all zero
+ * Control-channel outputs as gmr1b200_rx_bcch_batch.  Per channel and frame, [n][max_frames]:
+ *   tch_rec [12]  int32: [0] GMR1B200_TCH_* of the frame, [1] 1 = the channel was released in this frame ("END"),
+ *                 [2] sync id of a FACCH3 burst, [3] FACCH3 decode attempts made in this frame (0, 1, 2),
+ *                 [4] [5] crc / Viterbi metric of the first attempt, [6] [7] of the ciphered retry,
+ *                 [8] [9] Viterbi metrics of the two speech frames, [10] timeslot of an IMM.ASS seen in this frame or -1,
+ *                 [11] 1 = tch_data holds a good FACCH3 message
+ *   tch_data [20] speech: frame0 | frame1 (10 bytes each, as gmr1_tch3_decode); FACCH3: the 10-byte L2 message
+ *   csd_rec [6]   int32: [0] GMR1B200_CSD_*, [1] sync id, [2] crc (FACCH9), [3] Viterbi metric, [4] mean soft-bit
+ *                 magnitude (TCH9, what the reference prints as avg), [5] reserved
+ *   csd_data [60] FACCH9: 38-byte L2; TCH9: the 60-byte block
+ * Every pointer host or device memory. */
+enum { GMR1B200_TCH_NONE = 0, GMR1B200_TCH_DKAB = 1, GMR1B200_TCH_DKAB_MISS = 2, GMR1B200_TCH_FACCH3 = 3,
+       GMR1B200_TCH_SPEECH = 4 };
+enum { GMR1B200_CSD_NONE = 0, GMR1B200_CSD_FACCH9 = 1, GMR1B200_CSD_TCH9 = 2 };
+int gmr1b200_rx_call_batch(const float *iq, int64_t iq_len, const int64_t *rec_ofs, const int32_t *rec_len,
+                           const int64_t *tch_ofs, const int64_t *csd_ofs, const uint8_t *kc,
+                           const int32_t *align0, const float *freq_err0, int sps, int n, int max_frames,
+                           int32_t *kind, int32_t *fn, int32_t *crc, int32_t *conv, uint8_t *l2, int32_t *n_frames,
+                           int32_t *tch_rec, uint8_t *tch_data, int32_t *csd_rec, uint8_t *csd_data, void *stream);
+
 /* ---- A5 cipher stream (host; input to the ciphered decoders) ------------------------------------
  * replaces gmr1_a5 / gmr1_a5_1, src/l1/a5.c:57,226 (l1/a5.h:37-41): n = 0 (all zero) or 1 (A5/1-GMR);
  * key [8], dl / ul [nbits] ubits, either may be NULL */

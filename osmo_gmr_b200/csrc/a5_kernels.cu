@@ -71,7 +71,7 @@ __device__ __forceinline__ void emit(A51 &s, uint8_t *row, int nbits, bool word_
 __global__ void __launch_bounds__(128) a5_kernel(const A5Args a)
 {
 	const int t = blockIdx.x * blockDim.x + threadIdx.x;
-	if (t >= a.n)
+	if (t >= (a.n_dev ? min(a.n, *a.n_dev * (a.n_dev_mul ? a.n_dev_mul : 1)) : a.n))
 		return;
 	uint8_t *dl = a.dl ? a.dl + (size_t)t * a.stride : nullptr;
 	uint8_t *ul = a.ul ? a.ul + (size_t)t * a.stride : nullptr;

@@ -87,6 +87,7 @@ struct MiscArgs {
 	int8_t        *ebits;                  // dkab: [n][8]
 	float         *toa;                    // dkab: [n]
 	int32_t       *rv;                     // dkab: 0 found / 1 not a DKAB / -EINVAL;  mod_order: 2 / 4
+	const int32_t *n_dev;                  // optional device-side unit count (<= n): units beyond it are skipped (rx scheduler)
 };
 cudaError_t launch_dkab(const MiscArgs &a, cudaStream_t st);
 cudaError_t launch_mod_order(const MiscArgs &a, cudaStream_t st);
@@ -99,6 +100,8 @@ struct A5Args {
 	const uint32_t *fn;          // [n]
 	int32_t        n, nbits, stride;
 	uint8_t       *dl, *ul;      // [n][stride] ubits, either may be NULL
+	const int32_t *n_dev;        // optional device-side unit count (<= n): units beyond it are skipped (rx scheduler)
+	int32_t        n_dev_mul;    // ... times this factor (0 = 1): e.g. four A5 streams per FACCH3 codeword
 };
 cudaError_t launch_a5(const A5Args &a, cudaStream_t st);
 

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(MW * 32) dkab_kernel(const MiscArgs a)
 	extern __shared__ __align__(16) uint8_t smem[];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int b = blockIdx.x * MW + warp;
-	if (b >= a.n)
+	if (b >= (a.n_dev ? min(a.n, *a.n_dev) : a.n))
 		return;
 	const int sps = a.sps, L = a.win_len;
 	float2 *y = (float2 *)smem + (size_t)warp * ((L + 1) & ~1);
