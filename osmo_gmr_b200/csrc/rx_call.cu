@@ -144,8 +144,9 @@ struct T3In {                                         // results of the first-st
 
 // after gmr1_dkab_demod / gmr1_pi4cxpsk_detect (:558-598)
 __global__ void __launch_bounds__(128) t3_route_kernel(RxState st, CallState cs, T3In in, int32_t *tch_rec, int n,
-                                                       int frame, int max_frames)
+                                                       const int *frame_p, int max_frames)
 {
+	const int frame = *frame_p;
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n)
 		return;
@@ -267,8 +268,10 @@ struct T3Res {                                        // per list entry
 
 // the end of _rx_tch3_facch_flush (:417-449), speech results, the frame's record
 __global__ void __launch_bounds__(128) t3_result_kernel(RxState st, CallState cs, Flush fl, T3Res r, const int32_t *tch3_ass,
-                                                        int32_t *tch_rec, uint8_t *tch_data, int n, int frame, int max_frames)
+                                                        int32_t *tch_rec, uint8_t *tch_data, int n, const int *frame_p,
+                                                        int max_frames)
 {
+	const int frame = *frame_p;
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n)
 		return;
@@ -360,8 +363,9 @@ struct T9Res {
 // rx_tch9 after the demodulation (:305-352): one warp per entry
 __global__ void __launch_bounds__(128) t9_result_kernel(CallState cs, const int32_t *idx, const int32_t *count, int8_t *eb,
                                                         uint8_t *ciph, T9Res r, int32_t *csd_rec, uint8_t *csd_data, int n,
-                                                        int frame, int max_frames)
+                                                        const int *frame_p, int max_frames)
 {
+	const int frame = *frame_p;
 	const int p = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
 	if (p >= min(n, *count))
 		return;
@@ -423,13 +427,14 @@ extern "C" int gmr1b200_rx_call_batch(const float *iq, int64_t iq_len, const int
 		return set_err(-EINVAL, "rx_call_batch: bad argument");
 	if (n == 0)
 		return 0;
-	cudaStream_t cs = (cudaStream_t)stream;
+	WalkStream ws(stream);
+	cudaStream_t cs = ws.get();
 	const BurstTab *d_all = nullptr;
 	cudaError_t e = device_bursts(&d_all);
 	if (e != cudaSuccess)
 		return cuda_rc(e, "burst table upload");
 
-	Stage s(stream);
+	Stage s((void *)cs);
 	const size_t N = (size_t)n, NF = N * (size_t)max_frames;
 	const float2 *d_iq = (const float2 *)s.in(iq, (size_t)iq_len * 2);
 	RxState st = {};
@@ -520,8 +525,10 @@ extern "C" int gmr1b200_rx_call_batch(const float *iq, int64_t iq_len, const int
 		scr_f9 = s.tmp<uint8_t>(decode_scratch_bytes(CH_FACCH9, n));
 		scr_t9 = s.tmp<uint8_t>(decode_scratch_bytes(CH_TCH9_9K6, n));
 	}
+	int *d_frame = s.tmp<int>(1);
 	if (s.failed())
 		return s.finish(cudaSuccess, "rx_call_batch: staging");
+	cudaMemsetAsync(d_frame, 0, sizeof(int), cs);
 
 	const int tb = 128, grid = (n + tb - 1) / tb, wgrid = (n + 3) / 4;
 	rx_init_kernel<<<grid, tb, 0, cs>>>(st, d_align0, d_ferr0, out.n_frames, out.tch3, nullptr, n);
@@ -573,7 +580,9 @@ extern "C" int gmr1b200_rx_call_batch(const float *iq, int64_t iq_len, const int
 		launches += 2;
 		return launch_a5(a, cs);
 	};
-	for (int f = 0; f < max_frames && e == cudaSuccess; f++) {
+	// the launches of one frame (identical for every frame: the frame index lives in d_frame)
+	auto frame = [&]() -> cudaError_t {
+		cudaError_t e = cudaSuccess;
 		// ---- control channels (as rx_bcch_walk)
 		rx_prep_kernel<<<wgrid, 128, 0, cs>>>(d_iq, st, n, sps);
 		rx_compact_kernel<<<1, 1024, 0, cs>>>(st, ls, n);
@@ -589,7 +598,7 @@ extern "C" int gmr1b200_rx_call_batch(const float *iq, int64_t iq_len, const int
 			a.n_dev = ls.count + k;
 			e = launch_demod(a, d_all + bt[k], &burst_tab(bt[k]), 1, 0, cs);
 			if (e != cudaSuccess)
-				break;
+				return e;
 			DecodeArgs d = {};
 			d.ebits = eb[k]; d.n = n; d.l2 = dl2[k]; d.conv = dconv[k]; d.crc = dcrc[k];
 			d.n_dev = ls.count + k;
@@ -598,8 +607,8 @@ extern "C" int gmr1b200_rx_call_batch(const float *iq, int64_t iq_len, const int
 			launches += 2;
 		}
 		if (e != cudaSuccess)
-			break;
-		rx_update_kernel<<<grid, tb, 0, cs>>>(st, bo, out, n, sps, f, max_frames, c.t3, c.t3_store, false);
+			return e;
+		rx_update_kernel<<<grid, tb, 0, cs>>>(st, bo, out, n, sps, d_frame, max_frames, c.t3, c.t3_store, false);
 		// ---- rx_tch3
 		t3_prep_kernel<<<wgrid, 128, 0, cs>>>(d_iq, st, c, n, sps);
 		compact_kernel<2><<<1, 1024, 0, cs>>>(c.key, c.wofs, st.freq_err, c.pay, n, c.slot, la);
@@ -609,41 +618,41 @@ extern "C" int gmr1b200_rx_call_batch(const float *iq, int64_t iq_len, const int
 			m.iq = d_iq; m.ofs = la.ofs; m.n = n; m.win_len = wl3; m.sps = sps; m.freq_shift = la.fs; m.dkab_p = la.pay;
 			m.toa = dk_toa; m.rv = dk_rv; m.n_dev = la.count;
 			if ((e = launch_dkab(m, cs)) != cudaSuccess)
-				break;
+				return e;
 			DemodArgs a = {};
 			a.iq = d_iq; a.ofs = la.ofs + N; a.n = n; a.sps = sps; a.win_len = wl3; a.freq_shift = la.fs + N;
 			a.e_toa0 = (float)(win3 >> 1);                                         // :587-591
 			a.bt_id = det_bt; a.n_dev = la.count + 1;
 			if ((e = launch_demod(a, d_det, h_det, 2, 1, cs)) != cudaSuccess)
-				break;
+				return e;
 			launches += 2;
 		}
 		T3In in = {dk_rv, det_bt};
-		t3_route_kernel<<<grid, tb, 0, cs>>>(st, c, in, d_trec, n, f, max_frames);
+		t3_route_kernel<<<grid, tb, 0, cs>>>(st, c, in, d_trec, n, d_frame, max_frames);
 		compact_kernel<2><<<1, 1024, 0, cs>>>(c.key2, c.wofs, st.freq_err, c.pay, n, c.slot2, lb);
 		launches += 2;
 		if ((e = demod(BT_NT3_FACCH, lb.ofs, lb.fs, lb.count, wl3, f_eb, 104, f_sync)) != cudaSuccess)
-			break;
+			return e;
 		if ((e = demod(BT_NT3_SPEECH, lb.ofs + N, lb.fs + N, lb.count + 1, wl3, s_eb, 212, nullptr)) != cudaSuccess)
-			break;
+			return e;
 		// speech: A5 mask of (Kc, fn) where the channel is known to be ciphered, TCH3 decode (:518-524)
 		if ((e = a5(lb.idx + N, lb.count + 1, 1, nullptr, lb.pay + N, 0, 208, s_ciph)) != cudaSuccess)
-			break;
+			return e;
 		{
 			DecodeArgs d = {};
 			d.ebits = s_eb; d.ciph = s_ciph; d.n = n; d.l2 = s_f0; d.l2b = s_f1; d.conv = s_c0; d.conv1 = s_c1;
 			d.tch3_m = 0; d.n_dev = lb.count + 1; d.dec_scratch = scr_t3;
 			if ((e = launch_decode(CH_TCH3, d, cs)) != cudaSuccess)
-				break;
+				return e;
 			launches++;
 		}
 		// FACCH3: store / flush, then both decode attempts of every flushed codeword
 		t3_facch_kernel<<<wgrid, 128, 0, cs>>>(st, c, lb.idx, lb.count, f_eb, f_sync, fl, n);
 		launches++;
 		if ((e = a5(lb.idx, lb.count, 4, fl.fn, fl.ciph, 0, 96, x_mask[0])) != cudaSuccess)
-			break;
+			return e;
 		if ((e = a5(lb.idx, lb.count, 4, fl.fn, nullptr, 1, 96, x_mask[1])) != cudaSuccess)
-			break;
+			return e;
 		for (int k = 0; k < 2 && e == cudaSuccess; k++) {
 			DecodeArgs d = {};
 			d.ebits = fl.eb; d.ciph = x_mask[k]; d.n = n; d.l2 = x_l2[k]; d.conv = x_conv[k]; d.crc = x_crc[k];
@@ -652,14 +661,14 @@ extern "C" int gmr1b200_rx_call_batch(const float *iq, int64_t iq_len, const int
 			launches++;
 		}
 		if (e != cudaSuccess)
-			break;
+			return e;
 		T3Res r = {};
 		r.f_sync = f_sync;
 		for (int k = 0; k < 2; k++) {
 			r.x_crc[k] = x_crc[k]; r.x_conv[k] = x_conv[k]; r.x_l2[k] = x_l2[k];
 		}
 		r.s_f0 = s_f0; r.s_f1 = s_f1; r.s_c0 = s_c0; r.s_c1 = s_c1;
-		t3_result_kernel<<<grid, tb, 0, cs>>>(st, c, fl, r, out.tch3, d_trec, d_tdat, n, f, max_frames);
+		t3_result_kernel<<<grid, tb, 0, cs>>>(st, c, fl, r, out.tch3, d_trec, d_tdat, n, d_frame, max_frames);
 		launches++;
 		// ---- rx_tch9
 		if (csd_ofs) {
@@ -667,28 +676,54 @@ extern "C" int gmr1b200_rx_call_batch(const float *iq, int64_t iq_len, const int
 			compact_kernel<1><<<1, 1024, 0, cs>>>(c.key9, c.wofs9, st.freq_err, nullptr, n, c.slot9, l9);
 			launches += 2;
 			if ((e = demod(BT_NT9, l9.ofs, l9.fs, l9.count, wl9, t_eb, 662, t_sync)) != cudaSuccess)
-				break;
+				return e;
 			if ((e = a5(l9.idx, l9.count, 1, nullptr, nullptr, 1, 658, t_ciph)) != cudaSuccess)      // :308, :322
-				break;
+				return e;
 			t9_route_kernel<<<grid, tb, 0, cs>>>(c, l9.idx, l9.count, t_prev1, t_prev2, n);
 			DecodeArgs d = {};
 			d.ebits = t_eb; d.ciph = t_ciph; d.n = n; d.l2 = t_l2f; d.conv = t_fconv; d.crc = t_fcrc;
 			d.n_dev = l9.count; d.dec_scratch = scr_f9;
 			if ((e = launch_decode(CH_FACCH9, d, cs)) != cudaSuccess)
-				break;
+				return e;
 			DecodeArgs d9 = {};
 			d9.ebits = t_eb; d9.ciph = t_ciph; d9.n = n; d9.l2 = t_l2t; d9.conv = t_tconv; d9.prev1 = t_prev1; d9.prev2 = t_prev2;
 			d9.n_dev = l9.count; d9.dec_scratch = scr_t9;
 			if ((e = launch_decode(CH_TCH9_9K6, d9, cs)) != cudaSuccess)
-				break;
+				return e;
 			T9Res r9 = {t_sync, t_fcrc, t_fconv, t_tconv, t_l2f, t_l2t};
-			t9_result_kernel<<<wgrid, 128, 0, cs>>>(c, l9.idx, l9.count, t_eb, t_ciph, r9, d_crec, d_cdat, n, f, max_frames);
+			t9_result_kernel<<<wgrid, 128, 0, cs>>>(c, l9.idx, l9.count, t_eb, t_ciph, r9, d_crec, d_cdat, n, d_frame, max_frames);
 			launches += 4;
 		}
-		rx_advance_kernel<<<grid, tb, 0, cs>>>(st, out.n_frames, n, sps, f);
-		launches += 2;
-		e = cudaGetLastError();
+		rx_advance_kernel<<<grid, tb, 0, cs>>>(st, out.n_frames, n, sps, d_frame);
+		rx_tick_kernel<<<1, 1, 0, cs>>>(d_frame);
+		launches += 3;
+		return cudaGetLastError();
+	};
+	FrameGraph fg(cs);
+	bool graph = false;
+	uint64_t per_frame = 0;
+	for (int f = 0; f < max_frames && e == cudaSuccess; f++) {
+		if (f == 1 && max_frames >= 4 && ws.capturable()) {
+			if (fg.begin() == cudaSuccess) {
+				const uint64_t keep = launches;
+				const cudaError_t ce = frame();          // captured, not executed
+				launches = keep;
+				if (ce == cudaSuccess && fg.end() == cudaSuccess)
+					graph = true;
+				else
+					fg.abort();
+			} else
+				cudaGetLastError();
+		}
+		const uint64_t l0 = launches;
+		e = graph ? fg.launch() : frame();
+		if (!graph)
+			per_frame = launches - l0;
+		else
+			launches += per_frame;
 	}
 	g_launches.fetch_add(launches);
-	return s.finish(e, "rx_call_batch kernels");
+	const int rc = s.finish(e, "rx_call_batch kernels");
+	ws.join();
+	return rc;
 }

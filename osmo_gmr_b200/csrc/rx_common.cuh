@@ -9,6 +9,10 @@
 #include "launch.h"
 #include "tch3_state.cuh"
 
+#include <stdlib.h>
+#include <mutex>
+#include <vector>
+
 using namespace gmr1;
 
 namespace {
@@ -149,10 +153,13 @@ struct RxBurstOut {                          // outputs of the two demod + decod
 
 // t3 / t3_store (optional): the channel's TCH3 state and FACCH3 soft-bit store, initialised by an IMM.ASS exactly as
 // rx_tch3_init does (the whole-call walk); advance = false leaves the step to the next frame to rx_advance_kernel
+// (the frame index comes from a device counter, so that the launches of one frame are the same for every frame
+// and can be replayed as a CUDA graph: rx_tick_kernel closes a frame)
 __global__ void __launch_bounds__(128) rx_update_kernel(RxState st, RxBurstOut bo, RxOut out, int n, int sps,
-                                                        int frame, int max_frames, Tch3State *t3, int8_t *t3_store,
-                                                        bool advance)
+                                                        const int *frame_p, int max_frames, Tch3State *t3,
+                                                        int8_t *t3_store, bool advance)
 {
+	const int frame = *frame_p;
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n || st.done[i])
 		return;
@@ -220,8 +227,9 @@ __global__ void __launch_bounds__(128) rx_update_kernel(RxState st, RxBurstOut b
 }
 
 // next frame (process_bcch :884-891), for walks that do more per frame after rx_update_kernel
-__global__ void __launch_bounds__(128) rx_advance_kernel(RxState st, int32_t *n_frames, int n, int sps, int frame)
+__global__ void __launch_bounds__(128) rx_advance_kernel(RxState st, int32_t *n_frames, int n, int sps, const int *frame_p)
 {
+	const int frame = *frame_p;
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n || st.done[i])
 		return;
@@ -254,6 +262,121 @@ __global__ void rx_init_kernel(RxState st, const int32_t *align0, const float *f
 	st.done[i] = 0;
 	n_frames[i] = 0;
 }
+
+__global__ void rx_tick_kernel(int *frame_p) { *frame_p += 1; }
+
+// ---- one frame's launches as a CUDA graph ----------------------------------------------------------------------------
+// The walks enqueue the same sequence of small dependent kernels for every frame (449 launches per BCCH / CCCH walk,
+// ~40 per frame with the traffic channels): frame 0 is launched directly (it also runs the launchers' lazy
+// initialisation, which must not happen inside a capture), frame 1 is captured into a graph, frames 1 .. F-1 replay it.
+// Executable graphs are destroyed later, when an event recorded behind their last launch has completed.
+class FrameGraph {
+public:
+	explicit FrameGraph(cudaStream_t cs) : cs_(cs) { sweep(false); }
+	static bool enabled()
+	{
+		static const bool off = [] { const char *e = getenv("GMR1B200_RX_NOGRAPH"); return e && atoi(e) != 0; }();
+		return !off;
+	}
+	cudaError_t begin() { return cudaStreamBeginCapture(cs_, cudaStreamCaptureModeThreadLocal); }
+	cudaError_t end()
+	{
+		cudaError_t e = cudaStreamEndCapture(cs_, &g_);
+		if (e == cudaSuccess)
+			e = cudaGraphInstantiate(&ex_, g_, 0);
+		return e;
+	}
+	void abort()
+	{
+		cudaGraph_t g = nullptr;
+		cudaStreamEndCapture(cs_, &g);
+		if (g)
+			cudaGraphDestroy(g);
+		cudaGetLastError();
+	}
+	cudaError_t launch() { return cudaGraphLaunch(ex_, cs_); }
+	~FrameGraph()
+	{
+		if (!ex_ && !g_)
+			return;
+		Dead d = {ex_, g_, nullptr};
+		if (cudaEventCreateWithFlags(&d.done, cudaEventDisableTiming) == cudaSuccess)
+			cudaEventRecord(d.done, cs_);
+		std::lock_guard<std::mutex> lk(mu());
+		dead().push_back(d);
+	}
+
+private:
+	struct Dead { cudaGraphExec_t ex; cudaGraph_t g; cudaEvent_t done; };
+	static std::mutex &mu() { static std::mutex m; return m; }
+	static std::vector<Dead> &dead() { static std::vector<Dead> v; return v; }
+	static void sweep(bool all)
+	{
+		std::lock_guard<std::mutex> lk(mu());
+		auto &v = dead();
+		for (size_t i = 0; i < v.size();) {
+			if (all || !v[i].done || cudaEventQuery(v[i].done) == cudaSuccess) {
+				if (v[i].ex) cudaGraphExecDestroy(v[i].ex);
+				if (v[i].g) cudaGraphDestroy(v[i].g);
+				if (v[i].done) cudaEventDestroy(v[i].done);
+				v[i] = v.back();
+				v.pop_back();
+			} else
+				i++;
+		}
+		cudaGetLastError();
+	}
+	cudaStream_t cs_;
+	cudaGraph_t g_ = nullptr;
+	cudaGraphExec_t ex_ = nullptr;
+};
+
+// The legacy default stream cannot be captured: a walk called with stream = NULL runs on an internal stream that is
+// ordered behind the default stream at entry and in front of it at exit (same semantics for the caller).
+class WalkStream {
+public:
+	explicit WalkStream(void *user) : user_((cudaStream_t)user), cs_((cudaStream_t)user)
+	{
+		if (user_ || !FrameGraph::enabled())
+			return;
+		static thread_local cudaStream_t own[64] = {nullptr};
+		int dev = 0;
+		if (cudaGetDevice(&dev) != cudaSuccess || dev >= 64)
+			return;
+		if (!own[dev] && cudaStreamCreateWithFlags(&own[dev], cudaStreamNonBlocking) != cudaSuccess) {
+			own[dev] = nullptr;
+			cudaGetLastError();
+			return;
+		}
+		cudaEvent_t ev;
+		if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess)
+			return;
+		cudaEventRecord(ev, user_);
+		cudaStreamWaitEvent(own[dev], ev, 0);
+		cudaEventDestroy(ev);
+		cs_ = own[dev];
+		forked_ = true;
+	}
+	cudaStream_t get() const { return cs_; }
+	bool capturable() const { return cs_ != nullptr && FrameGraph::enabled(); }
+	void join()
+	{
+		if (!forked_)
+			return;
+		cudaEvent_t ev;
+		if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess) {
+			cudaEventRecord(ev, cs_);
+			cudaStreamWaitEvent(user_, ev, 0);
+			cudaEventDestroy(ev);
+		}
+		forked_ = false;
+	}
+	~WalkStream() { join(); }
+
+private:
+	cudaStream_t user_, cs_;
+	bool forked_ = false;
+};
 
 __global__ void rx_final_kernel(RxState st, int32_t *align, float *freq_err, int n)
 {

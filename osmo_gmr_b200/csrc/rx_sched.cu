@@ -30,13 +30,14 @@ static int rx_bcch_walk(const float *iq, int64_t iq_len, const int64_t *rec_ofs,
 		return set_err(-EINVAL, "rx_bcch_batch: bad argument");
 	if (n == 0)
 		return 0;
-	cudaStream_t cs = (cudaStream_t)stream;
+	WalkStream ws(stream);
+	cudaStream_t cs = ws.get();
 	const BurstTab *d_all = nullptr;
 	cudaError_t e = device_bursts(&d_all);
 	if (e != cudaSuccess)
 		return cuda_rc(e, "burst table upload");
 
-	Stage s(stream);
+	Stage s((void *)cs);
 	const size_t N = (size_t)n, NF = N * (size_t)max_frames;
 	const float2 *d_iq = (const float2 *)s.in(iq, (size_t)iq_len * 2);
 	RxState st = {};
@@ -80,12 +81,17 @@ static int rx_bcch_walk(const float *iq, int64_t iq_len, const int64_t *rec_ofs,
 	for (int k = 0; k < 2; k++) {
 		bo.toa[k] = toa[k]; bo.ferr[k] = ferr[k]; bo.crc[k] = dcrc[k]; bo.conv[k] = dconv[k]; bo.l2[k] = dl2[k];
 	}
+	int *d_frame = s.tmp<int>(1);
+	if (s.failed())
+		return s.finish(cudaSuccess, "rx_bcch_batch: staging");
+	cudaMemsetAsync(d_frame, 0, sizeof(int), cs);
 	e = cudaGetLastError();
-	for (int f = 0; f < max_frames && e == cudaSuccess; f++) {
+	// the launches of one frame (identical for every frame: the frame index lives in d_frame)
+	auto frame = [&]() -> cudaError_t {
+		cudaError_t fe = cudaSuccess;
 		rx_prep_kernel<<<(n + 3) / 4, 128, 0, cs>>>(d_iq, st, n, sps);
 		rx_compact_kernel<<<1, 1024, 0, cs>>>(st, ls, n);
-		launches += 2;
-		for (int k = 0; k < 2 && e == cudaSuccess; k++) {
+		for (int k = 0; k < 2 && fe == cudaSuccess; k++) {
 			DemodArgs a = {};
 			a.iq = d_iq; a.ofs = ls.ofs[k]; a.n = n; a.sps = sps;
 			a.win_len = BURST_SYMS * sps + (k == 0 ? 20 : 10) * sps;
@@ -94,28 +100,46 @@ static int rx_bcch_walk(const float *iq, int64_t iq_len, const int64_t *rec_ofs,
 			a.ebits = eb[k]; a.ebits_stride = ebits[k];
 			a.toa = toa[k]; a.freq_err = ferr[k];
 			a.n_dev = ls.count + k;
-			e = launch_demod(a, d_all + bt[k], &burst_tab(bt[k]), 1, 0, cs);
-			if (e != cudaSuccess)
+			fe = launch_demod(a, d_all + bt[k], &burst_tab(bt[k]), 1, 0, cs);
+			if (fe != cudaSuccess)
 				break;
 			DecodeArgs d = {};
 			d.ebits = eb[k]; d.n = n; d.l2 = dl2[k]; d.conv = dconv[k]; d.crc = dcrc[k];
 			d.n_dev = ls.count + k;
 			d.dec_scratch = dscr[k];
-			e = launch_decode(ch[k], d, cs);
-			launches += 2;
+			fe = launch_decode(ch[k], d, cs);
 		}
-		if (e != cudaSuccess)
-			break;
-		rx_update_kernel<<<grid, tb, 0, cs>>>(st, bo, out, n, sps, f, max_frames, nullptr, nullptr, true);
-		launches += 1;
-		e = cudaGetLastError();
+		if (fe != cudaSuccess)
+			return fe;
+		rx_update_kernel<<<grid, tb, 0, cs>>>(st, bo, out, n, sps, d_frame, max_frames, nullptr, nullptr, true);
+		rx_tick_kernel<<<1, 1, 0, cs>>>(d_frame);
+		return cudaGetLastError();
+	};
+	const int per_frame = 8;
+	FrameGraph fg(cs);
+	bool graph = false;
+	for (int f = 0; f < max_frames && e == cudaSuccess; f++) {
+		if (f == 1 && max_frames >= 4 && ws.capturable()) {
+			if (fg.begin() == cudaSuccess) {
+				const cudaError_t ce = frame();
+				if (ce == cudaSuccess && fg.end() == cudaSuccess)
+					graph = true;
+				else
+					fg.abort();
+			} else
+				cudaGetLastError();
+		}
+		e = graph ? fg.launch() : frame();
+		launches += per_frame;
 	}
 	if (e == cudaSuccess) {
 		rx_final_kernel<<<grid, tb, 0, cs>>>(st, d_align_out, d_ferr_out, n);
 		e = cudaGetLastError();
 	}
 	g_launches.fetch_add(launches);
-	return s.finish(e, "rx_bcch_batch kernels");
+	const int rc = s.finish(e, "rx_bcch_batch kernels");
+	ws.join();
+	return rc;
 }
 
 extern "C" int gmr1b200_rx_bcch_batch(const float *iq, int64_t iq_len, const int64_t *rec_ofs, const int32_t *rec_len,
