@@ -45,6 +45,11 @@ int gmr1b200_init(int device);
 const char *gmr1b200_last_error(void);
 /* Library version string. */
 const char *gmr1b200_version(void);
+/* Calling-thread promise: until switched off again, every pointer this thread passes to a batched entry point is HOST
+ * memory.  The library then skips the per-pointer classification and stages through a per-thread page-locked arena
+ * (one H2D copy per input, one D2H copy for all outputs of a call).  Set by the n = 1 wrappers of the reference's own
+ * symbols (csrc/compat.c); returns the previous setting. */
+int gmr1b200_host_hint(int on);
 /* Number of CUDA kernels this library has launched in this process (all threads). */
 uint64_t gmr1b200_kernel_launches(void);
 
@@ -285,6 +290,13 @@ int gmr1b200_rx_bcch_batch(const float *iq, int64_t iq_len, const int64_t *rec_o
                            const int32_t *align0, const float *freq_err0, int sps, int n, int max_frames,
                            int32_t *kind, int32_t *fn, int32_t *crc, int32_t *conv, uint8_t *l2,
                            int32_t *n_frames, int32_t *align_out, float *freq_err_out, void *stream);
+
+/* Scheduling switch of the two walks above (testing / A-B measurements).  Default (0): every channel is paced by its own
+ * BCCH bursts - the only frames that change its tracking state - so a call alternates "BCCH frame of every channel"
+ * and "all frames up to the next BCCH frame of every channel, as one batch": two dependent rounds of kernels per eight
+ * frames.  1: all channels frame by frame in lock step (eight rounds per eight frames, each frame's launches replayed
+ * as a CUDA graph).  Same results, record for record.  Process-wide; returns the previous setting. */
+int gmr1b200_set_rx_lockstep(int on);
 
 /* The same walk, and the TCH3 hand-off of rx_ccch (src/gmr1_rx.c:836-841): a CCCH burst with a good CRC that is an
  * IMMEDIATE ASSIGNMENT (ccch_is_imm_ass :236-239) initialises the channel's TCH3 state as rx_tch3_init does (:362-381).

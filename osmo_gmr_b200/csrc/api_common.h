@@ -34,6 +34,19 @@ inline int cuda_rc(cudaError_t e, const char *what)
 	return set_err(-EIO, what, e);
 }
 
+// Per-thread staging arena for callers that pass HOST pointers only and say so (gmr1b200_host_hint, set by the n = 1
+// compat wrappers of compat.c): one page-locked host buffer and one device buffer of the same size, kept for the life
+// of the thread.  A call then costs one H2D copy per input, the kernel launches, ONE D2H copy for all outputs and one
+// synchronisation - no cudaPointerGetAttributes, no cudaMallocAsync / cudaFreeAsync, no pageable-memory staging by the
+// driver.  (The link-level drop-in spent ~1 ms per n = 1 call on those; profiles/README.md has the breakdown.)
+struct HostArena {
+	char  *h = nullptr, *d = nullptr;
+	size_t cap = 0, want = 0;
+	bool   busy = false;         // one Stage at a time (a nested Stage stages the ordinary way)
+};
+extern thread_local int g_host_hint;
+HostArena &host_arena();          // this thread's arena for the current device (allocated / grown between calls)
+
 // Stage: resolves each pointer argument of a batched call to a device pointer.
 //   in(p, bytes)   host  -> device scratch + H2D copy on the stream;   device -> p itself
 //   out(p, bytes)  host  -> device scratch, D2H copy queued for finish(); device -> p itself
@@ -41,8 +54,22 @@ inline int cuda_rc(cudaError_t e, const char *what)
 //                  involved, releases scratch (stream-ordered)
 class Stage {
 public:
-	explicit Stage(void *stream) : st_((cudaStream_t)stream) {}
-	~Stage() { release(); }
+	explicit Stage(void *stream) : st_((cudaStream_t)stream)
+	{
+		if (g_host_hint) {
+			ar_ = &host_arena();
+			if (!ar_->h || ar_->busy)
+				ar_ = nullptr;
+			else
+				ar_->busy = true;
+		}
+	}
+	~Stage()
+	{
+		release();
+		if (ar_)
+			ar_->busy = false;
+	}
 
 	template <class T> const T *in(const T *p, size_t count)
 	{
@@ -50,10 +77,16 @@ public:
 			return p;
 		if (is_device(p))
 			return p;
-		void *d = scratch(count * sizeof(T));
+		const size_t bytes = count * sizeof(T);
+		if (char *a = arena(bytes)) {
+			memcpy(ar_->h + (a - ar_->d), p, bytes);
+			check(cudaMemcpyAsync(a, ar_->h + (a - ar_->d), bytes, cudaMemcpyHostToDevice, st_), "H2D copy");
+			return (const T *)a;
+		}
+		void *d = scratch(bytes);
 		if (!d)
 			return nullptr;
-		check(cudaMemcpyAsync(d, p, count * sizeof(T), cudaMemcpyHostToDevice, st_), "H2D copy");
+		check(cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, st_), "H2D copy");
 		return (const T *)d;
 	}
 
@@ -63,15 +96,30 @@ public:
 			return p;
 		if (is_device(p))
 			return p;
-		void *d = scratch(count * sizeof(T));
+		const size_t bytes = count * sizeof(T);
+		if (char *a = arena(bytes)) {
+			const size_t off = (size_t)(a - ar_->d);
+			out_lo_ = off < out_lo_ ? off : out_lo_;
+			out_hi_ = off + bytes > out_hi_ ? off + bytes : out_hi_;
+			backs_.push_back({p, a, bytes, true});
+			return (T *)a;
+		}
+		void *d = scratch(bytes);
 		if (!d)
 			return nullptr;
-		backs_.push_back({p, d, count * sizeof(T)});
+		backs_.push_back({p, d, bytes, false});
 		return (T *)d;
 	}
 
 	// device-only scratch that lives until finish()
-	template <class T> T *tmp(size_t count) { return failed_ ? nullptr : (T *)scratch(count * sizeof(T)); }
+	template <class T> T *tmp(size_t count)
+	{
+		if (failed_)
+			return nullptr;
+		if (char *a = arena(count * sizeof(T)))
+			return (T *)a;
+		return (T *)scratch(count * sizeof(T));
+	}
 
 	bool failed() const { return failed_; }
 	int rc() const { return rc_; }
@@ -82,9 +130,14 @@ public:
 			failed_ = true;
 			rc_ = cuda_rc(launch_err, what);
 		}
-		if (!failed_)
+		if (!failed_) {
+			if (out_hi_ > out_lo_)       // every arena output in one copy
+				check(cudaMemcpyAsync(ar_->h + out_lo_, ar_->d + out_lo_, out_hi_ - out_lo_, cudaMemcpyDeviceToHost, st_),
+				      "D2H copy");
 			for (auto &b : backs_)
-				check(cudaMemcpyAsync(b.host, b.dev, b.bytes, cudaMemcpyDeviceToHost, st_), "D2H copy");
+				if (!b.arena)
+					check(cudaMemcpyAsync(b.host, b.dev, b.bytes, cudaMemcpyDeviceToHost, st_), "D2H copy");
+		}
 		if (host_involved_ || failed_) {
 			cudaError_t e = cudaStreamSynchronize(st_);
 			if (e != cudaSuccess && !failed_) {
@@ -92,18 +145,38 @@ public:
 				rc_ = cuda_rc(e, what);
 			}
 		}
+		if (!failed_)
+			for (auto &b : backs_)
+				if (b.arena)
+					memcpy(b.host, ar_->h + ((char *)b.dev - ar_->d), b.bytes);
 		release();
 		return rc_;
 	}
 
 private:
-	struct Back { void *host, *dev; size_t bytes; };
+	struct Back { void *host, *dev; size_t bytes; bool arena; };
 	cudaStream_t st_;
 	std::vector<void *> tmp_;
 	std::vector<Back> backs_;
 	bool host_involved_ = false, failed_ = false;
 	int rc_ = 0;
+	HostArena *ar_ = nullptr;
+	size_t cur_ = 0, out_lo_ = (size_t)-1, out_hi_ = 0;
 
+	// bump allocation in the thread's arena (256-byte granules); NULL: not in arena mode or the arena is full - the
+	// arena then grows before the thread's next call
+	char *arena(size_t bytes)
+	{
+		if (!ar_)
+			return nullptr;
+		const size_t need = (bytes + 255) & ~(size_t)255;
+		ar_->want = ar_->want > cur_ + need ? ar_->want : cur_ + need;
+		if (cur_ + need > ar_->cap)
+			return nullptr;
+		char *p = ar_->d + cur_;
+		cur_ += need;
+		return p;
+	}
 	void check(cudaError_t e, const char *what)
 	{
 		if (e != cudaSuccess && !failed_) {
@@ -113,6 +186,10 @@ private:
 	}
 	bool is_device(const void *p)
 	{
+		if (g_host_hint) {              // the caller vouches: host memory
+			host_involved_ = true;
+			return false;
+		}
 		cudaPointerAttributes at;
 		cudaError_t e = cudaPointerGetAttributes(&at, p);
 		if (e != cudaSuccess) {

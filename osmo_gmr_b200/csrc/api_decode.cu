@@ -6,6 +6,39 @@
 
 namespace gmr1 {
 thread_local char g_err[512] = "";
+thread_local int gmr1::g_host_hint = 0;
+
+// this thread's staging arena for the current device: 4 MB to start with (a 650 ms FCCH window is 0.5 MB), grown
+// between calls to twice what the largest call so far would have needed
+HostArena &gmr1::host_arena()
+{
+	static thread_local HostArena ar[16];
+	int dev = 0;
+	cudaGetDevice(&dev);
+	HostArena &a = ar[dev & 15];
+	if (a.busy)
+		return a;
+	const size_t want = a.want > a.cap ? 2 * a.want : ((size_t)4 << 20);
+	if (!a.h || a.want > a.cap) {
+		if (a.h) {
+			cudaDeviceSynchronize();
+			cudaFreeHost(a.h);
+			cudaFree(a.d);
+			a.h = a.d = nullptr;
+			a.cap = 0;
+		}
+		char *h = nullptr, *d = nullptr;
+		if (cudaHostAlloc((void **)&h, want, cudaHostAllocPortable) == cudaSuccess && cudaMalloc((void **)&d, want) == cudaSuccess) {
+			a.h = h;
+			a.d = d;
+			a.cap = want;
+		} else {
+			if (h) cudaFreeHost(h);
+			cudaGetLastError();
+		}
+	}
+	return a;
+}
 std::atomic<uint64_t> g_launches{0};
 }
 
@@ -25,6 +58,12 @@ int gmr1b200_init(int device)
 }
 
 const char *gmr1b200_last_error(void) { return g_err; }
+int gmr1b200_host_hint(int on)
+{
+	const int prev = g_host_hint;
+	g_host_hint = on ? 1 : 0;
+	return prev;
+}
 const char *gmr1b200_version(void) { return "gmr1_b200 0.2 (sm_100a) build " GMR1B200_BUILD_ID; }
 uint64_t gmr1b200_kernel_launches(void) { return g_launches.load(); }
 

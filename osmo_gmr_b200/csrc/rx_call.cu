@@ -43,75 +43,6 @@ struct CallState {
 	int64_t   *wofs, *wofs9;                          // [n] absolute window start of the traffic / CSD window
 };
 
-template <int NL>
-struct Lists {                                        // NL compacted lists over the channels, [NL][n] each
-	int32_t *count;                                   // [NL]
-	int32_t *idx;                                     // channel of an entry
-	int64_t *ofs;                                     // absolute window start
-	float   *fs;                                      // freq_shift = -freq_err
-	int32_t *pay;                                     // payload (DKAB position / cipher flag)
-};
-
-// ordered compaction of the channels by key (0 = in no list, k = list k-1); one CTA
-template <int NL>
-__global__ void __launch_bounds__(1024) compact_kernel(const int32_t *key, const int64_t *wofs, const float *freq_err,
-                                                       const int32_t *pay, int n, int32_t *slot, Lists<NL> ls)
-{
-	__shared__ int wtot[NL][32], wbase[NL][32], base[NL];
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	if (tid < NL)
-		base[tid] = 0;
-	__syncthreads();
-	for (int i0 = 0; i0 < n; i0 += 1024) {
-		const int i = i0 + tid;
-		const int k0 = i < n ? key[i] : 0;
-		int pos[NL];
-#pragma unroll
-		for (int k = 0; k < NL; k++) {
-			const unsigned m = __ballot_sync(0xffffffffu, k0 == k + 1);
-			pos[k] = __popc(m & ((1u << lane) - 1u));
-			if (lane == 0)
-				wtot[k][warp] = __popc(m);
-		}
-		__syncthreads();
-		if (warp == 0) {
-#pragma unroll
-			for (int k = 0; k < NL; k++) {
-				const int v = wtot[k][lane];
-				int s = v;
-#pragma unroll
-				for (int o = 1; o < 32; o <<= 1) {
-					const int t = __shfl_up_sync(0xffffffffu, s, o);
-					if (lane >= o)
-						s += t;
-				}
-				wbase[k][lane] = base[k] + s - v;
-			}
-		}
-		__syncthreads();
-		if (k0 > 0 && k0 <= NL) {
-			int p = 0;
-#pragma unroll
-			for (int k = 0; k < NL; k++)
-				if (k0 == k + 1)
-					p = wbase[k][warp] + pos[k];
-			slot[i] = p;
-			const size_t e = (size_t)(k0 - 1) * n + p;
-			ls.idx[e] = i;
-			ls.ofs[e] = wofs[i];
-			ls.fs[e] = -freq_err[i];
-			if (pay)
-				ls.pay[e] = pay[i];
-		}
-		__syncthreads();
-		if (tid < NL)
-			base[tid] = wbase[tid][31] + wtot[tid][31];
-		__syncthreads();
-	}
-	if (tid < NL)
-		ls.count[tid] = base[tid];
-}
-
 // rx_tch3 up to the energy gate (:538-585)
 __global__ void __launch_bounds__(128) t3_prep_kernel(const float2 *__restrict__ iq, RxState st, CallState cs, int n, int sps)
 {

@@ -81,6 +81,7 @@ class Lib:
                                   _P, _L, _P, _L, _I, _P],
         "gmr1b200_set_sync_accumulator_reset": [_I],
         "gmr1b200_set_demod_generic": [_I],
+        "gmr1b200_set_rx_lockstep": [_I],
         "gmr1b200_rx_call_batch": [_P, _L, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
         "gmr1b200_pool_create": [_P, _I, _I, _L, _P],
         "gmr1b200_pool_size": [_P],

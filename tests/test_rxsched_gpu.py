@@ -77,7 +77,16 @@ def _acquire_like_main(o, x):
     return out
 
 
-def test_rx_bcch_batch_vs_gmr1_rx(gpu_lib, oracle, tmp_path):
+@pytest.fixture(params=[0, 1], ids=["paced", "lockstep"])
+def walk_mode(request, gpu_lib):
+    """both schedules of the frame walk (gmr1b200_set_rx_lockstep): paced by each channel's BCCH bursts (default) and
+    frame by frame in lock step"""
+    prev = gpu_lib.call("gmr1b200_set_rx_lockstep", request.param)
+    yield request.param
+    gpu_lib.call("gmr1b200_set_rx_lockstep", prev)
+
+
+def test_rx_bcch_batch_vs_gmr1_rx(gpu_lib, oracle, tmp_path, walk_mode):
     if not os.path.exists(REF_BIN):
         pytest.skip("oracle/_ref/gmr1_rx not built (needs /root/reference at build time)")
     cases = [dict(esn0_db=15.0, cfo_hz=300.0, seed=1), dict(esn0_db=8.0, cfo_hz=-450.0, seed=2, seconds=2.6),
@@ -220,7 +229,7 @@ def test_fcch_multi_batch_vs_gmr1_rx(gpu_lib, oracle, tmp_path):
     assert c1[0] == -22
 
 
-def test_rx_bcch_ass_batch_vs_gmr1_rx(gpu_lib, oracle, tmp_path):
+def test_rx_bcch_ass_batch_vs_gmr1_rx(gpu_lib, oracle, tmp_path, walk_mode):
     """the TCH3 hand-off of the frame loop (rx_ccch -> rx_tch3_init, src/gmr1_rx.c:836-841,362-381): IMMEDIATE
     ASSIGNMENTs on CCCH bursts are seen in the same frames with the same timeslot as by the reference application
     ("[+] TCH3 assigned on TN"), DKAB position as sent, energy thresholds from the last BCCH window; the walk itself

@@ -19,11 +19,13 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--channels", type=int, default=4096)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--lockstep", action="store_true", help="frame-by-frame schedule instead of the BCCH-paced one")
     args = ap.parse_args()
     import torch
     import osmo_gmr_b200
     import recording             # the recording generator of the tests (numpy); nothing under oracle/ is used here
     L = osmo_gmr_b200.lib()
+    L.call("gmr1b200_set_rx_lockstep", 1 if args.lockstep else 0)
 
     def enc(chan, nbits):        # the library's own channel encoders (gmr1b200_xcch_encode_batch, host code)
         def f(l2):
@@ -72,7 +74,7 @@ def main():
     bursts = int((kind > 0).sum())
     ms = float(np.mean(times))
     print(json.dumps({"what": "gmr1b200_rx_bcch_batch: BCCH/CCCH frame loop with tracking feedback, device-resident",
-                      "channels": n, "frames_per_channel": int(out["nfr"].cpu().numpy().max()), "bursts": bursts,
+                      "schedule": "lockstep" if args.lockstep else "paced", "channels": n, "frames_per_channel": int(out["nfr"].cpu().numpy().max()), "bursts": bursts,
                       "crc_ok_frac": float((crc[kind > 0] == 0).mean()), "ms": ms, "bursts_per_s": bursts / (ms * 1e-3),
                       "iq_bytes": int(iq.numel() * 4), "kernel_launches": int(launches)}))
 
