@@ -6,11 +6,11 @@
 
 namespace gmr1 {
 thread_local char g_err[512] = "";
-thread_local int gmr1::g_host_hint = 0;
+thread_local int g_host_hint = 0;
 
 // this thread's staging arena for the current device: 4 MB to start with (a 650 ms FCCH window is 0.5 MB), grown
 // between calls to twice what the largest call so far would have needed
-HostArena &gmr1::host_arena()
+HostArena &host_arena()
 {
 	static thread_local HostArena ar[16];
 	int dev = 0;

@@ -13,6 +13,11 @@
 #include <stdlib.h>
 #include <string.h>
 
+/* Every pointer the reference's API hands us is host memory: say so for the duration of the batched call, so that the
+ * library stages through its per-thread page-locked arena instead of classifying and allocating per pointer. */
+#define HOSTCALL(call) __extension__({ const int hint_ = gmr1b200_host_hint(1); const int rv_ = (call); \
+                                       gmr1b200_host_hint(hint_); rv_; })
+
 #define PI_F 3.14159265358979323846264338327f
 
 /* ------------------------------------------------------------------ burst format data symbols */
@@ -149,9 +154,9 @@ int gmr1_pi4cxpsk_demod(struct gmr1_pi4cxpsk_burst *burst_type, struct osmo_cxve
 	int rv = desc_from_burst(burst_type, &d);
 	if (rv)
 		return rv;
-	rv = gmr1b200_pi4cxpsk_demod_desc_batch(&d, (const float *)burst_in->data, burst_in->len, NULL, 0,
+	rv = HOSTCALL(gmr1b200_pi4cxpsk_demod_desc_batch(&d, (const float *)burst_in->data, burst_in->len, NULL, 0,
 	                                        burst_in->len, sps, NULL, freq_shift, ebits, d.ebits,
-	                                        &sid, &toa, &fe, NULL, 1, NULL);
+	                                        &sid, &toa, &fe, NULL, 1, NULL));
 	if (rv)
 		return rv;
 	if (sid < 0)
@@ -175,8 +180,8 @@ int gmr1_pi4cxpsk_detect(struct gmr1_pi4cxpsk_burst **burst_types, float e_toa, 
 		if ((rv = desc_from_burst(burst_types[n], &d[n])))
 			return rv;
 	}
-	rv = gmr1b200_pi4cxpsk_detect_desc_batch(d, n, NULL, e_toa, (const float *)burst_in->data, burst_in->len,
-	                                         NULL, 0, burst_in->len, sps, NULL, freq_shift, &bt, &sid, &toa, 1, NULL);
+	rv = HOSTCALL(gmr1b200_pi4cxpsk_detect_desc_batch(d, n, NULL, e_toa, (const float *)burst_in->data, burst_in->len,
+	                                         NULL, 0, burst_in->len, sps, NULL, freq_shift, &bt, &sid, &toa, 1, NULL));
 	if (rv)
 		return rv;
 	if (bt_id_p) *bt_id_p = bt;
@@ -188,8 +193,8 @@ int gmr1_pi4cxpsk_detect(struct gmr1_pi4cxpsk_burst **burst_types, float e_toa, 
 int gmr1_pi4cxpsk_mod_order(struct osmo_cxvec *burst_in, int sps, float freq_shift)
 {
 	int32_t order = 0;
-	int rv = gmr1b200_pi4cxpsk_mod_order_batch((const float *)burst_in->data, burst_in->len, NULL, 0, burst_in->len,
-	                                           sps, NULL, freq_shift, &order, 1, NULL);
+	int rv = HOSTCALL(gmr1b200_pi4cxpsk_mod_order_batch((const float *)burst_in->data, burst_in->len, NULL, 0, burst_in->len,
+	                                           sps, NULL, freq_shift, &order, 1, NULL));
 	return rv ? rv : order;
 }
 
@@ -238,8 +243,8 @@ static int fcch_type_of(const struct gmr1_fcch_burst *bt)
 int gmr1_fcch_rough(const struct gmr1_fcch_burst *burst_type, struct osmo_cxvec *win, int sps, float freq_shift, int *toa)
 {
 	int32_t t = 0;
-	int rv = gmr1b200_fcch_rough_batch(fcch_type_of(burst_type), (const float *)win->data, win->len, NULL, 0,
-	                                   win->len, sps, NULL, freq_shift, &t, NULL, 1, NULL);
+	int rv = HOSTCALL(gmr1b200_fcch_rough_batch(fcch_type_of(burst_type), (const float *)win->data, win->len, NULL, 0,
+	                                   win->len, sps, NULL, freq_shift, &t, NULL, 1, NULL));
 	if (!rv)
 		*toa = t;
 	return rv;
@@ -248,8 +253,8 @@ int gmr1_fcch_rough(const struct gmr1_fcch_burst *burst_type, struct osmo_cxvec 
 int gmr1_fcch_rough_multi(const struct gmr1_fcch_burst *burst_type, struct osmo_cxvec *win, int sps,
                           float freq_shift, int *toa, int N)
 {
-	return gmr1b200_fcch_rough_multi(fcch_type_of(burst_type), (const float *)win->data, win->len, sps, freq_shift,
-	                                 (int32_t *)toa, N, NULL);
+	return HOSTCALL(gmr1b200_fcch_rough_multi(fcch_type_of(burst_type), (const float *)win->data, win->len, sps, freq_shift,
+	                                 (int32_t *)toa, N, NULL));
 }
 
 int gmr1_fcch_fine(const struct gmr1_fcch_burst *burst_type, struct osmo_cxvec *burst_in, int sps, float freq_shift,
@@ -260,8 +265,8 @@ int gmr1_fcch_fine(const struct gmr1_fcch_burst *burst_type, struct osmo_cxvec *
 	int rv;
 	if (!burst_type || burst_in->len / sps != burst_type->len)     /* fcch.c:546-551 */
 		return -EINVAL;
-	rv = gmr1b200_fcch_fine_batch(fcch_type_of(burst_type), (const float *)burst_in->data, burst_in->len, NULL, 0,
-	                              sps, NULL, freq_shift, &t, &fe, 1, NULL);
+	rv = HOSTCALL(gmr1b200_fcch_fine_batch(fcch_type_of(burst_type), (const float *)burst_in->data, burst_in->len, NULL, 0,
+	                              sps, NULL, freq_shift, &t, &fe, 1, NULL));
 	if (!rv) {
 		*toa = t;
 		*freq_error = fe;
@@ -274,15 +279,15 @@ int gmr1_fcch_snr(const struct gmr1_fcch_burst *burst_type, struct osmo_cxvec *b
 {
 	if (!burst_type || burst_in->len / sps != burst_type->len)
 		return -EINVAL;
-	return gmr1b200_fcch_snr_batch(fcch_type_of(burst_type), (const float *)burst_in->data, burst_in->len, NULL, 0,
-	                               sps, NULL, freq_shift, snr, 1, NULL);
+	return HOSTCALL(gmr1b200_fcch_snr_batch(fcch_type_of(burst_type), (const float *)burst_in->data, burst_in->len, NULL, 0,
+	                               sps, NULL, freq_shift, snr, 1, NULL));
 }
 
 int gmr1_dkab_demod(struct osmo_cxvec *burst_in, int sps, float freq_shift, int p, sbit_t *ebits, float *toa_p)
 {
 	int32_t rv = 0;
-	int rc = gmr1b200_dkab_demod_batch((const float *)burst_in->data, burst_in->len, NULL, 0, burst_in->len, sps,
-	                                   NULL, freq_shift, NULL, p, ebits, toa_p, &rv, 1, NULL);
+	int rc = HOSTCALL(gmr1b200_dkab_demod_batch((const float *)burst_in->data, burst_in->len, NULL, 0, burst_in->len, sps,
+	                                   NULL, freq_shift, NULL, p, ebits, toa_p, &rv, 1, NULL));
 	return rc ? rc : rv;
 }
 
@@ -291,7 +296,7 @@ int gmr1_dkab_demod(struct osmo_cxvec *burst_in, int sps, float freq_shift, int 
 int gmr1_bcch_decode(uint8_t *l2, const sbit_t *bits_e, int *conv_rv)
 {
 	int32_t crc = 1, cv = 0;
-	int rc = gmr1b200_bcch_decode_batch(l2, bits_e, &cv, &crc, 1, NULL);
+	int rc = HOSTCALL(gmr1b200_bcch_decode_batch(l2, bits_e, &cv, &crc, 1, NULL));
 	if (conv_rv) *conv_rv = cv;
 	return rc ? rc : crc;
 }
@@ -299,7 +304,7 @@ int gmr1_bcch_decode(uint8_t *l2, const sbit_t *bits_e, int *conv_rv)
 int gmr1_ccch_decode(uint8_t *l2, const sbit_t *bits_e, int *conv_rv)
 {
 	int32_t crc = 1, cv = 0;
-	int rc = gmr1b200_ccch_decode_batch(l2, bits_e, &cv, &crc, 1, NULL);
+	int rc = HOSTCALL(gmr1b200_ccch_decode_batch(l2, bits_e, &cv, &crc, 1, NULL));
 	if (conv_rv) *conv_rv = cv;
 	return rc ? rc : crc;
 }
@@ -307,7 +312,7 @@ int gmr1_ccch_decode(uint8_t *l2, const sbit_t *bits_e, int *conv_rv)
 int gmr1_xch_dc12_decode(uint8_t *l2, const sbit_t *bits_e, int *conv_rv)
 {
 	int32_t crc = 1, cv = 0;
-	int rc = gmr1b200_xch_dc12_decode_batch(l2, bits_e, &cv, &crc, 1, NULL);
+	int rc = HOSTCALL(gmr1b200_xch_dc12_decode_batch(l2, bits_e, &cv, &crc, 1, NULL));
 	if (conv_rv) *conv_rv = cv;
 	return rc ? rc : crc;
 }
@@ -315,7 +320,7 @@ int gmr1_xch_dc12_decode(uint8_t *l2, const sbit_t *bits_e, int *conv_rv)
 int gmr1_facch3_decode(uint8_t *l2, ubit_t *bits_s, const sbit_t *bits_e, const ubit_t *ciph, int *conv_rv)
 {
 	int32_t crc = 1, cv = 0;
-	int rc = gmr1b200_facch3_decode_batch(l2, bits_s, bits_e, ciph, &cv, &crc, 1, NULL);
+	int rc = HOSTCALL(gmr1b200_facch3_decode_batch(l2, bits_s, bits_e, ciph, &cv, &crc, 1, NULL));
 	if (conv_rv) *conv_rv = cv;
 	return rc ? rc : crc;
 }
@@ -324,7 +329,7 @@ int gmr1_facch9_decode(uint8_t *l2, sbit_t *bits_sacch, sbit_t *bits_status, con
                        const ubit_t *ciph, int *conv_rv)
 {
 	int32_t crc = 1, cv = 0;
-	int rc = gmr1b200_facch9_decode_batch(l2, bits_sacch, bits_status, bits_e, ciph, &cv, &crc, 1, NULL);
+	int rc = HOSTCALL(gmr1b200_facch9_decode_batch(l2, bits_sacch, bits_status, bits_e, ciph, &cv, &crc, 1, NULL));
 	if (conv_rv) *conv_rv = cv;
 	return rc ? rc : crc;
 }
@@ -333,7 +338,7 @@ void gmr1_tch3_decode(uint8_t *frame0, uint8_t *frame1, ubit_t *bits_s, const sb
                       int m, int *conv0_rv, int *conv1_rv)
 {
 	int32_t c0 = 0, c1 = 0;
-	gmr1b200_tch3_decode_batch(frame0, frame1, bits_s, bits_e, ciph, m, &c0, &c1, 1, NULL);
+	HOSTCALL(gmr1b200_tch3_decode_batch(frame0, frame1, bits_s, bits_e, ciph, m, &c0, &c1, 1, NULL));
 	if (conv0_rv) *conv0_rv = c0;
 	if (conv1_rv) *conv1_rv = c1;
 }
@@ -341,7 +346,7 @@ void gmr1_tch3_decode(uint8_t *frame0, uint8_t *frame1, ubit_t *bits_s, const sb
 int gmr1_rach_decode(uint8_t *rach, const sbit_t *bits_e, uint8_t sb_mask, int *conv_rv, int *crc_rv)
 {
 	int32_t crc = 1, cv = 0, c2[2] = { 1, 1 };
-	int rc = gmr1b200_rach_decode_batch(rach, bits_e, NULL, sb_mask, &cv, c2, &crc, 1, NULL);
+	int rc = HOSTCALL(gmr1b200_rach_decode_batch(rach, bits_e, NULL, sb_mask, &cv, c2, &crc, 1, NULL));
 	if (conv_rv) *conv_rv = cv;
 	if (crc_rv) { crc_rv[0] = c2[0]; crc_rv[1] = c2[1]; }
 	return rc ? rc : crc;
@@ -369,7 +374,7 @@ void gmr1_tch9_decode(uint8_t *l2, sbit_t *bits_sacch, sbit_t *bits_status, cons
 	memcpy(x + 52, my + 62, 596);
 	gmr1_scramble_sbit(x, x, 648);
 	gmr1_deinterleave_inter(il, x, x);
-	gmr1b200_tch9_decode_rows_batch(l2, x, (int)mode, &cv, 1, NULL);
+	HOSTCALL(gmr1b200_tch9_decode_rows_batch(l2, x, (int)mode, &cv, 1, NULL));
 	if (conv_rv) *conv_rv = cv;
 }
 
