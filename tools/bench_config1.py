@@ -66,6 +66,50 @@ def main():
         t, b = run_app(GPU_BIN, path, 3)
         out["dropin_app_n1_calls"] = {"wall_s": t, "bursts": b, "bursts_per_s": b / t if t else None,
                                       "note": "includes process start and CUDA context creation"}
+    # (b') where the drop-in's time goes: context creation in a fresh process, the first n = 1 call (lazy table uploads,
+    #      module load), warm n = 1 calls through the reference's own symbols (gmr1_pi4cxpsk_demod, gmr1_bcch_decode)
+    code = r"""
+import ctypes, json, sys, time
+import numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+t0 = time.perf_counter()
+import osmo_gmr_b200
+L = osmo_gmr_b200.lib()
+t1 = time.perf_counter()
+L.init(0)
+t2 = time.perf_counter()
+import oracle_lib
+c = L.c
+class CxVec(ctypes.Structure):
+    _fields_ = [("len", ctypes.c_int), ("max_len", ctypes.c_int), ("flags", ctypes.c_int), ("data", ctypes.c_void_p)]
+x = (np.random.default_rng(0).standard_normal(1016 * 2) * 0.3).astype(np.float32)
+cv = CxVec(1016, 1016, 0, x.ctypes.data)
+eb = np.zeros(424, np.int8); sid = ctypes.c_int(); toa = ctypes.c_float(); fe = ctypes.c_float()
+bt = ctypes.addressof(ctypes.c_char.in_dll(c, "gmr1_bcch_burst"))
+c.gmr1_pi4cxpsk_demod.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_float] + [ctypes.c_void_p] * 4
+def demod():
+    return c.gmr1_pi4cxpsk_demod(bt, ctypes.addressof(cv), 4, 0.0, eb.ctypes.data, ctypes.addressof(sid), ctypes.addressof(toa), ctypes.addressof(fe))
+t3 = time.perf_counter(); demod(); t4 = time.perf_counter()
+l2 = np.zeros(24, np.uint8); conv = ctypes.c_int()
+c.gmr1_bcch_decode.argtypes = [ctypes.c_void_p] * 3
+def decode():
+    return c.gmr1_bcch_decode(l2.ctypes.data, eb.ctypes.data, ctypes.addressof(conv))
+decode(); t5 = time.perf_counter()
+N = 300
+for _ in range(20): demod(); decode()
+a = time.perf_counter()
+for _ in range(N): demod()
+b = time.perf_counter()
+for _ in range(N): decode()
+d = time.perf_counter()
+print(json.dumps({"import_and_dlopen_s": t1 - t0, "cuda_context_s": t2 - t1, "first_demod_call_s": t4 - t3, "first_decode_call_s": t5 - t4,
+                  "warm_demod_call_us": 1e6 * (b - a) / N, "warm_decode_call_us": 1e6 * (d - b) / N}))
+""" % (ROOT, os.path.join(ROOT, "tests"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    try:
+        out["dropin_breakdown"] = json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception:
+        out["dropin_breakdown"] = {"error": r.stderr[-500:]}
     # (c) batched entry points on the one recording, host buffers in and out
     iq = np.ascontiguousarray(x).view(np.float32)
     n, F = 1, 64
