@@ -254,10 +254,10 @@ int gmr1b200_pi4cxpsk_detect_desc_batch(const struct gmr1b200_burst_desc *descs,
                                         int n, void *stream);
 
 /* replaces gmr1_fcch_rough_multi, src/sdr/fcch.c:341 (sdr/fcch.h:51-53): all overlapping FCCHs in one
- * >= 650 ms window.  The 117-tap correlation runs on the GPU; the peak bookkeeping (two-cycle mixing,
- * avg+3sigma threshold, sorted de-duplicated insert, fcch.c:373-483) is a few thousand scalar steps and
- * runs on the host exactly as written there.  toa [N] out; returns the number of FCCHs found (>= 0) or
- * -errno (-EINVAL: window shorter than 650 ms or the two cycles do not line up). */
+ * >= 650 ms window.  The 117-tap correlation and the peak bookkeeping (two-cycle mixing, avg + 3 sigma
+ * threshold, sorted de-duplicated insert, fcch.c:373-483, in the reference's summation order) both run on the
+ * GPU.  toa [N] out (host memory; the 16 strongest at most, as gmr1_rx asks for); returns the number of FCCHs
+ * found (>= 0) or -errno (-EINVAL: window shorter than 650 ms or the two cycles do not line up). */
 int gmr1b200_fcch_rough_multi(int fcch_type, const float *iq, int64_t win_len, int sps, float freq_shift,
                               int32_t *toa, int N, void *stream);
 

@@ -59,9 +59,49 @@ int gmr1b200_fcch_rough_batch(int fcch_type, const float *iq, int64_t iq_len, co
 	return s.finish(e, "fcch_rough kernel");
 }
 
-// ---- multi-FCCH acquisition: GPU correlation + the reference's scalar peak bookkeeping ----------
-// (src/sdr/fcch.c:264-326 _peak_record, :373-483)
-static void peak_record(int burst_len, int *toa, float *pwr, int *n, int N, int Lp, int sps, int peak_toa, float peak_pwr)
+// ---- fcch_multi_process (src/gmr1_rx.c:643-741) up to its callback, for n recordings, on the device -----------------
+// Per recording: all FCCHs of the 650 ms behind the primary one (gmr1_fcch_rough_multi with the primary's frequency
+// error: the 117-tap correlation by fcch_rough_kernel, the peak bookkeeping of src/sdr/fcch.c:264-326, 385-483 by
+// multi_peaks_kernel), fine TOA / frequency error and SNR of each candidate (fcch_fine_kernel over the [n][16]
+// candidate slots), the reference's plausibility filter (multi_filter_kernel).  Everything is enqueued on the
+// caller's stream; there is no host round trip inside the call.
+namespace {
+
+constexpr int NPK = 16;                                            // mtoa[16], gmr1_rx.c:647
+
+struct MultiSt {                                                   // device memory
+	int64_t *w_ofs;                                                // [n] 650 ms window of a recording
+	float   *w_fs;                                                 // [n] -freq_err of the primary FCCH
+	int32_t *w_skip, *base;                                        // [n]
+	float   *pw;                                                   // [n][nc] correlation power
+	int32_t *cnt;                                                  // [n] peaks found (or -EINVAL)
+	int32_t *mtoa;                                                 // [n][16]
+	int64_t *c_ofs;                                                // [n][16] candidate burst
+	float   *c_fs;
+	int32_t *c_skip, *c_toa;
+	float   *c_fe, *c_snr;
+};
+
+// window one FCCH burst ahead of the primary alignment (gmr1_rx.c:655-668)
+__global__ void multi_prep_kernel(MultiSt m, const int64_t *rec_ofs, const int32_t *rec_len, const int32_t *align,
+                                  const float *freq_err, int64_t iq_len, int blen, int sps, int W, int32_t *n_fcch, int n)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n)
+		return;
+	int b = align[i] - blen * sps;
+	if (b < 0)
+		b = 0;
+	const bool bad = b + W > rec_len[i] || rec_ofs[i] < 0 || rec_ofs[i] + rec_len[i] > iq_len;
+	m.w_skip[i] = bad;
+	m.base[i] = b;
+	m.w_ofs[i] = bad ? 0 : rec_ofs[i] + b;
+	m.w_fs[i] = -(freq_err ? freq_err[i] : 0.0f);
+	n_fcch[i] = bad ? -EINVAL : 0;                                 // "Not enough samples"
+}
+
+// _peak_record, src/sdr/fcch.c:264-326
+__device__ void peak_record_dev(int burst_len, int *toa, float *pwr, int *n, int N, int Lp, int sps, int peak_toa, float peak_pwr)
 {
 	int has_dupe = 0;
 	const int th = (burst_len * sps) >> 1;
@@ -99,74 +139,202 @@ static void peak_record(int burst_len, int *toa, float *pwr, int *n, int N, int 
 		*n += 1;
 }
 
-// everything of gmr1_fcch_rough_multi behind the correlation (fcch.c:385-483): strongest peak of the first
-// cycle, its twin one period later, geometric mix of the two cycles, avg + 3 sigma threshold, sorted
-// de-duplicated insert.  corr_pwr [nc] is overwritten.  Returns the number of FCCHs or -EINVAL.
-static int rough_multi_peaks(float *corr_pwr, int nc, int blen, int sps, int32_t *peaks_toa, int N)
+// everything of gmr1_fcch_rough_multi behind the correlation (fcch.c:385-483), one warp per recording: the lanes bring
+// the correlation power through shared memory in coalesced tiles, lane 0 does the arithmetic in the reference's order
+// (its running sums are sequential float additions; the threshold is compared against them)
+constexpr int MP_TILE = 1024;
+__global__ void __launch_bounds__(32) multi_peaks_kernel(MultiSt m, int nc, int blen, int sps, int n)
 {
+	__shared__ float tile[MP_TILE + 2];
+	__shared__ int s_toa[NPK];
+	__shared__ float s_pwr[NPK];
+	const int r = blockIdx.x, lane = threadIdx.x;
+	if (r >= n || m.w_skip[r])
+		return;
+	float *pw = m.pw + (size_t)r * nc;
 	const int sym_rate = 23400;
 	int Lw = (320 * sym_rate) / 1000 + blen, Lp = (320 * sym_rate) / 1000;
-	int pwr_max_idx = 0;
-	float pwr_max = 0.0f;
-	for (int i = 0; i < nc; i++)
-		if (corr_pwr[i] > pwr_max && i < Lw) {
-			pwr_max = corr_pwr[i];
-			pwr_max_idx = i;
+	// strongest sample of the first cycle, first one on ties (:385-392)
+	float best = 0.0f;
+	int best_i = 0x7fffffff;
+	for (int i = lane; i < nc && i < Lw; i += 32)
+		if (pw[i] > best) {
+			best = pw[i];
+			best_i = i;
 		}
-	// the twin one period later, +-10 symbols (fcch.c:397-430)
-	float pwrs[2] = {0.0f, 0.0f}, peaks[2] = {0.0f, 0.0f};
-	for (int i = -10; i <= 10; i++) {
-		int j = pwr_max_idx + i;
-		if (j > 0 && j < nc) {
-			pwrs[0] += corr_pwr[j];
-			peaks[0] += corr_pwr[j] * j;
-		}
-		j += Lp;
-		if (j > 0 && j < nc) {
-			pwrs[1] += corr_pwr[j];
-			peaks[1] += corr_pwr[j] * j;
-		}
+#pragma unroll
+	for (int o = 16; o; o >>= 1) {
+		const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+		const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+		if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
 	}
-	peaks[0] /= pwrs[0];
-	peaks[1] /= pwrs[1];
-	const int nLp = (int)round(peaks[1] - peaks[0]);
-	if (abs(nLp - Lp) > 10)
-		return -EINVAL;
-	Lp = nLp;
+	const int pwr_max_idx = best > 0.0f ? best_i : 0;
+	int cnt = 0, err = 0;
+	if (lane == 0) {
+		// the twin one period later, +-10 symbols (:397-430)
+		float pwrs[2] = {0.0f, 0.0f}, peaks[2] = {0.0f, 0.0f};
+		for (int i = -10; i <= 10; i++) {
+			int j = pwr_max_idx + i;
+			if (j > 0 && j < nc) {
+				pwrs[0] += pw[j];
+				peaks[0] += pw[j] * j;
+			}
+			j += Lp;
+			if (j > 0 && j < nc) {
+				pwrs[1] += pw[j];
+				peaks[1] += pw[j] * j;
+			}
+		}
+		peaks[0] /= pwrs[0];
+		peaks[1] /= pwrs[1];
+		const int nLp = (int)round((double)(peaks[1] - peaks[0]));
+		if (abs(nLp - Lp) > 10)
+			err = 1;
+		Lp = nLp;
+	}
+	err = __shfl_sync(0xffffffffu, err, 0);
+	Lp = __shfl_sync(0xffffffffu, Lp, 0);
+	if (err) {
+		if (lane == 0)
+			m.cnt[r] = -EINVAL;
+		return;
+	}
 	if (Lw + Lp > nc)
 		Lw = nc - Lp;
+	// geometric mix of the two cycles (:435-441), in place; its mean, sequentially
 	float avg = 0.0f;
-	for (int i = 0; i < Lw; i++) {          // geometric mix of the two cycles (fcch.c:435-441)
-		const float v = sqrtf(corr_pwr[i] * corr_pwr[i + Lp]);
-		corr_pwr[i] = v;
-		avg += v;
-	}
-	avg /= Lw;
-	float stddev = 0.0f;
-	for (int i = 0; i < Lw; i++) {
-		const float v = corr_pwr[i] - avg;
-		stddev += v * v;
-	}
-	stddev = sqrtf(stddev / Lw);
-	const float th = avg + 3.0f * stddev;
-	std::vector<float> peaks_pwr((size_t)N, 0.0f);
-	int peaks_cnt = 0;
-	for (int i = 1, in_peak = 0; i < Lw - 1; i++) {
-		if (corr_pwr[i] > th) {
-			if (in_peak)
-				continue;
-			in_peak = 1;
-			const float p_pwr = corr_pwr[i - 1] + corr_pwr[i] + corr_pwr[i + 1];
-			const float p_fpos = (-corr_pwr[i - 1] + corr_pwr[i + 1]) / p_pwr;
-			const int p_pos = (int)round((i + p_fpos) * sps);
-			peak_record(blen, peaks_toa, peaks_pwr.data(), &peaks_cnt, N, Lp, sps, p_pos, p_pwr);
-		} else {
-			in_peak = 0;
+	for (int t0 = 0; t0 < Lw; t0 += MP_TILE) {
+		const int tn = min(MP_TILE, Lw - t0);
+		for (int i = lane; i < tn; i += 32) {
+			const float v = sqrtf(pw[t0 + i] * pw[t0 + i + Lp]);
+			tile[i] = v;
 		}
+		__syncwarp();
+		for (int i = lane; i < tn; i += 32)
+			pw[t0 + i] = tile[i];
+		if (lane == 0)
+			for (int i = 0; i < tn; i++)
+				avg += tile[i];
+		__syncwarp();
 	}
-	return peaks_cnt;
+	avg = __shfl_sync(0xffffffffu, avg, 0) / Lw;
+	float stddev = 0.0f;
+	for (int t0 = 0; t0 < Lw; t0 += MP_TILE) {
+		const int tn = min(MP_TILE, Lw - t0);
+		for (int i = lane; i < tn; i += 32)
+			tile[i] = pw[t0 + i];
+		__syncwarp();
+		if (lane == 0)
+			for (int i = 0; i < tn; i++) {
+				const float v = tile[i] - avg;
+				stddev += v * v;
+			}
+		__syncwarp();
+	}
+	const float th = avg + 3.0f * sqrtf(__shfl_sync(0xffffffffu, stddev, 0) / Lw);
+	// peaks above the threshold, 3-point centroid, sorted de-duplicated insert (:454-481)
+	if (lane < NPK) {
+		s_toa[lane] = 0;
+		s_pwr[lane] = 0.0f;
+	}
+	__syncwarp();
+	int in_peak = 0;
+	for (int t0 = 1; t0 < Lw - 1; t0 += MP_TILE) {
+		const int tn = min(MP_TILE, Lw - 1 - t0);
+		for (int i = lane; i < tn + 2; i += 32)                    // tile[k] = pw[t0 - 1 + k]
+			tile[i] = pw[t0 - 1 + i];
+		__syncwarp();
+		if (lane == 0)
+			for (int k = 0; k < tn; k++) {
+				const int i = t0 + k;
+				if (tile[k + 1] > th) {
+					if (in_peak)
+						continue;
+					in_peak = 1;
+					const float p_pwr = tile[k] + tile[k + 1] + tile[k + 2];
+					const float p_fpos = (-tile[k] + tile[k + 2]) / p_pwr;
+					const int p_pos = (int)round((double)(((float)i + p_fpos) * (float)sps));
+					peak_record_dev(blen, s_toa, s_pwr, &cnt, NPK, Lp, sps, p_pos, p_pwr);
+				} else {
+					in_peak = 0;
+				}
+			}
+		__syncwarp();
+	}
+	if (lane == 0)
+		m.cnt[r] = cnt;
+	__syncwarp();
+	if (lane < NPK)
+		m.mtoa[r * NPK + lane] = s_toa[lane];
 }
 
+// candidate slots of every recording: the burst at each rough position (gmr1_rx.c:680-684)
+__global__ void multi_cand_kernel(MultiSt m, int n)
+{
+	const int e = blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= n * NPK)
+		return;
+	const int r = e / NPK, j = e % NPK;
+	const bool live = !m.w_skip[r] && j < m.cnt[r];
+	m.c_skip[e] = !live;
+	m.c_ofs[e] = live ? m.w_ofs[r] + m.mtoa[e] : 0;
+	m.c_fs[e] = m.w_fs[r];
+}
+
+// SNR at the fine position, with the fine frequency error taken off (:691-696)
+__global__ void multi_snr_prep_kernel(MultiSt m, int n)
+{
+	const int e = blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= n * NPK || m.c_skip[e])
+		return;
+	m.c_ofs[e] += m.c_toa[e];
+	m.c_fs[e] = -(-m.c_fs[e] + m.c_fe[e]);
+}
+
+// the strongest is the reference; the others must be strong enough and close in frequency (:702-738)
+__global__ void multi_filter_kernel(MultiSt m, int max_cand, int32_t *n_fcch, int32_t *cand_align, float *cand_snr,
+                                    float *cand_freq_err, int n)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n || m.w_skip[i])
+		return;
+	if (m.cnt[i] < 0) {
+		n_fcch[i] = m.cnt[i];
+		return;
+	}
+	float ref_snr = 0.0f, ref_fe = 0.0f;
+	int cnt = 0;
+	for (int j = 0; j < m.cnt[i]; j++) {
+		const int e = i * NPK + j;
+		const float snr = m.c_snr[e], fe = m.c_fe[e];
+		if (j == 0) {
+			ref_snr = snr;
+			ref_fe = fe;
+		} else {
+			if (snr < 2.0f)
+				continue;
+			if (snr < ref_snr / 6.0f)
+				continue;
+			const float d = fabsf(ref_fe - fe);
+			if ((23400 * d) / (2.0f * (float)M_PI) > 500.0f)
+				continue;
+		}
+		if (cnt < max_cand) {
+			const size_t o = (size_t)i * max_cand + cnt;
+			cand_align[o] = m.base[i] + m.mtoa[e] + m.c_toa[e];     // :738, where process_bcch starts
+			if (cand_snr)
+				cand_snr[o] = snr;
+			if (cand_freq_err)
+				cand_freq_err[o] = fe;
+		}
+		cnt++;
+	}
+	n_fcch[i] = cnt < max_cand ? cnt : max_cand;
+}
+
+}  // namespace
+
+// replaces gmr1_fcch_rough_multi for one window: the same two kernels with n = 1
 int gmr1b200_fcch_rough_multi(int fcch_type, const float *iq, int64_t win_len, int sps, float freq_shift,
                               int32_t *peaks_toa, int N, void *stream)
 {
@@ -177,39 +345,41 @@ int gmr1b200_fcch_rough_multi(int fcch_type, const float *iq, int64_t win_len, i
 		return set_err(-EINVAL, "fcch_rough_multi: needs 650 ms of signal");
 	const int blen = FCCH_TYPES[fcch_type].len;
 	const int l = (int)(win_len / sps), nc = l - blen + 1;
-	std::vector<float> pw((size_t)nc);
+	cudaStream_t cs = (cudaStream_t)stream;
+	int32_t cnt = 0, mtoa[NPK] = {0};
+	int rc;
 	{
-		FcchArgs a = {};
-		a.iq = (const float2 *)iq; a.stride = 0; a.n = 1; a.win_len = (int)win_len; a.sps = sps;
-		a.freq_shift0 = freq_shift;
 		Stage s(stream);
-		int dummy_toa;
-		a.toa = &dummy_toa;
-		int rc = fcch_common(fcch_type, a, s, win_len, "fcch_rough_multi: bad argument");
-		if (rc)
-			return rc;
-		a.en_out = s.out(pw.data(), (size_t)nc);
+		const float2 *d_iq = (const float2 *)s.in(iq, (size_t)win_len * 2);
+		MultiSt m = {};
+		m.w_skip = s.tmp<int32_t>(1); m.pw = s.tmp<float>((size_t)nc); m.c_toa = s.tmp<int32_t>(1);
+		m.cnt = s.out(&cnt, 1); m.mtoa = s.out(mtoa, NPK);
 		cudaError_t e = cudaSuccess;
 		if (!s.failed()) {
-			e = launch_fcch_rough(a, (cudaStream_t)stream);
-			if (e == cudaSuccess)
-				g_launches.fetch_add(1);
+			cudaMemsetAsync(m.w_skip, 0, sizeof(int32_t), cs);
+			cudaMemsetAsync(m.cnt, 0, sizeof(int32_t), cs);
+			FcchArgs a = {};
+			a.iq = d_iq; a.stride = 0; a.n = 1; a.win_len = (int)win_len; a.sps = sps;
+			a.freq = FCCH_TYPES[fcch_type].freq; a.len = blen; a.freq_shift0 = freq_shift;
+			a.toa = m.c_toa; a.en_out = m.pw;
+			e = launch_fcch_rough(a, cs);
+			if (e == cudaSuccess) {
+				multi_peaks_kernel<<<1, 32, 0, cs>>>(m, nc, blen, sps, 1);
+				e = cudaGetLastError();
+				g_launches.fetch_add(2);
+			}
 		}
-		rc = s.finish(e, "fcch_rough kernel");
-		if (rc)
-			return rc;
+		rc = s.finish(e, "fcch_rough_multi kernels");       // cnt / mtoa are host memory: finish() synchronises
 	}
-	const int cnt = rough_multi_peaks(pw.data(), nc, blen, sps, peaks_toa, N);
+	if (rc)
+		return rc;
 	if (cnt < 0)
 		return set_err(cnt, "fcch_rough_multi: FCCH period mismatch");
-	return cnt;
+	for (int i = 0; i < cnt && i < N; i++)
+		peaks_toa[i] = mtoa[i];
+	return cnt < N ? cnt : N;
 }
 
-// ---- fcch_multi_process (src/gmr1_rx.c:643-741) up to its callback, for n recordings -----------------
-// Per recording: all FCCHs of the 650 ms behind the primary one (rough_multi with the primary's frequency
-// error), fine TOA / frequency error and SNR of each, the reference's plausibility filter.  Three kernel
-// launches per chunk of recordings (correlation, fine, SNR); the scalar bookkeeping between them is the
-// reference's, on the host.
 int gmr1b200_fcch_multi_batch(int fcch_type, const float *iq, int64_t iq_len, const int64_t *rec_ofs,
                               const int32_t *rec_len, const int32_t *align, const float *freq_err, int sps, int n,
                               int max_cand, int32_t *n_fcch, int32_t *cand_align, float *cand_snr,
@@ -220,156 +390,69 @@ int gmr1b200_fcch_multi_batch(int fcch_type, const float *iq, int64_t iq_len, co
 		return set_err(-EINVAL, "fcch_multi_batch: bad argument");
 	if (n == 0)
 		return 0;
-	const int sym_rate = 23400, NPK = 16;                          // mtoa[16], gmr1_rx.c:647
+	const int sym_rate = 23400;
 	const int blen = FCCH_TYPES[fcch_type].len;
 	const int W = (650 * sym_rate * sps) / 1000;                   // :661
 	const int nc = W / sps - blen + 1;
 	cudaStream_t cs = (cudaStream_t)stream;
 	Stage s(stream);
+	const size_t N = (size_t)n;
 	const float2 *d_iq = (const float2 *)s.in(iq, (size_t)iq_len * 2);
-	const int CH = 256;                                            // recordings per chunk (15 MB of correlation power)
-	int64_t *d_ofs = s.tmp<int64_t>((size_t)CH * NPK);
-	float *d_fs = s.tmp<float>((size_t)CH * NPK);
-	float *d_pw = s.tmp<float>((size_t)CH * nc);
-	int32_t *d_toa = s.tmp<int32_t>((size_t)CH * NPK);
-	float *d_fe = s.tmp<float>((size_t)CH * NPK), *d_snr = s.tmp<float>((size_t)CH * NPK);
+	const int64_t *d_rec_ofs = s.in(rec_ofs, N);
+	const int32_t *d_rec_len = s.in(rec_len, N), *d_align = s.in(align, N);
+	const float *d_ferr = s.in(freq_err, N);
+	int32_t *d_nf = s.out(n_fcch, N), *d_ca = s.out(cand_align, N * max_cand);
+	float *d_cs = s.out(cand_snr, N * max_cand), *d_cf = s.out(cand_freq_err, N * max_cand);
+	const int CH = 2048;                                           // recordings per chunk (124 MB of correlation power)
+	const size_t C = (size_t)(n < CH ? n : CH);
+	MultiSt m = {};
+	m.w_ofs = s.tmp<int64_t>(N); m.w_fs = s.tmp<float>(N); m.w_skip = s.tmp<int32_t>(N); m.base = s.tmp<int32_t>(N);
+	m.pw = s.tmp<float>(C * nc);
+	m.cnt = s.tmp<int32_t>(N); m.mtoa = s.tmp<int32_t>(N * NPK);
+	m.c_ofs = s.tmp<int64_t>(N * NPK); m.c_fs = s.tmp<float>(N * NPK); m.c_skip = s.tmp<int32_t>(N * NPK);
+	m.c_toa = s.tmp<int32_t>(N * NPK); m.c_fe = s.tmp<float>(N * NPK); m.c_snr = s.tmp<float>(N * NPK);
 	if (s.failed())
 		return s.finish(cudaSuccess, "fcch_multi_batch: staging");
-	std::vector<float> pw((size_t)CH * nc), fs, fe, snr;
-	std::vector<int64_t> ofs;
-	std::vector<int32_t> toa, chan, base, mtoa, first, bad;
-	cudaError_t e = cudaSuccess;
+	const int tb = 128;
 	uint64_t launches = 0;
-	auto up = [&](void *d, const void *h, size_t bytes) {
-		if (e == cudaSuccess)
-			e = cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, cs);
-	};
-	auto down = [&](void *h, const void *d, size_t bytes) {
-		if (e == cudaSuccess)
-			e = cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, cs);
-	};
-	for (int c0 = 0; c0 < n && e == cudaSuccess; c0 += CH) {
-		const int c1 = c0 + CH < n ? c0 + CH : n;
-		// 650 ms window one FCCH burst ahead of the primary alignment (:655-666)
-		chan.clear(); base.clear(); ofs.clear(); fs.clear();
-		for (int i = c0; i < c1; i++) {
-			int b = align[i] - blen * sps;
-			if (b < 0)
-				b = 0;
-			if (b + W > rec_len[i] || rec_ofs[i] < 0 || rec_ofs[i] + rec_len[i] > iq_len) {
-				n_fcch[i] = -EINVAL;                               // "Not enough samples"
-				continue;
-			}
-			chan.push_back(i); base.push_back(b);
-			ofs.push_back(rec_ofs[i] + b);
-			fs.push_back(-(freq_err ? freq_err[i] : 0.0f));        // :668
-		}
-		const int m = (int)chan.size();
-		if (!m)
-			continue;
-		up(d_ofs, ofs.data(), (size_t)m * sizeof(int64_t));
-		up(d_fs, fs.data(), (size_t)m * sizeof(float));
+	multi_prep_kernel<<<(n + tb - 1) / tb, tb, 0, cs>>>(m, d_rec_ofs, d_rec_len, d_align, d_ferr, iq_len, blen, sps, W, d_nf, n);
+	cudaMemsetAsync(m.cnt, 0, N * sizeof(int32_t), cs);
+	cudaError_t e = cudaGetLastError();
+	launches++;
+	for (int c0 = 0; c0 < n && e == cudaSuccess; c0 += CH) {       // correlation + peak bookkeeping, chunk by chunk
+		const int c = n - c0 < CH ? n - c0 : CH;
 		FcchArgs a = {};
-		a.iq = d_iq; a.ofs = d_ofs; a.n = m; a.win_len = W; a.sps = sps;
+		a.iq = d_iq; a.ofs = m.w_ofs + c0; a.n = c; a.win_len = W; a.sps = sps;
 		a.freq = FCCH_TYPES[fcch_type].freq; a.len = blen;
-		a.freq_shift = d_fs; a.toa = d_toa; a.en_out = d_pw;
-		if (e == cudaSuccess) {
-			e = launch_fcch_rough(a, cs);
-			launches++;
-		}
-		down(pw.data(), d_pw, (size_t)m * nc * sizeof(float));
-		if (e == cudaSuccess)
-			e = cudaStreamSynchronize(cs);
-		if (e != cudaSuccess)
+		a.freq_shift = m.w_fs + c0; a.toa = m.c_toa; a.en_out = m.pw; a.skip = m.w_skip + c0;
+		if ((e = launch_fcch_rough(a, cs)) != cudaSuccess)
 			break;
-		// candidates of every recording of the chunk, flattened
-		mtoa.clear(); first.assign((size_t)m + 1, 0); bad.assign((size_t)m, 0);
-		std::vector<int64_t> cofs;
-		std::vector<float> cfs;
-		for (int k = 0; k < m; k++) {
-			int32_t t[NPK];
-			const int cnt = rough_multi_peaks(&pw[(size_t)k * nc], nc, blen, sps, t, NPK);
-			bad[k] = cnt < 0 ? cnt : 0;                            // -EINVAL: the two cycles do not line up
-			for (int j = 0; j < cnt; j++) {
-				mtoa.push_back(t[j]);
-				cofs.push_back(ofs[k] + t[j]);                     // :682
-				cfs.push_back(fs[k]);
-			}
-			first[k + 1] = (int32_t)mtoa.size();
-		}
-		const int nk = (int)mtoa.size();
-		for (int k = 0; k < m; k++)
-			n_fcch[chan[k]] = bad[k];                              // 0 found so far, or the error
-		if (!nk)
-			continue;
-		toa.resize(nk); fe.resize(nk); snr.resize(nk);
-		up(d_ofs, cofs.data(), (size_t)nk * sizeof(int64_t));
-		up(d_fs, cfs.data(), (size_t)nk * sizeof(float));
+		MultiSt mc = m;
+		mc.w_skip += c0; mc.cnt += c0; mc.mtoa += (size_t)c0 * NPK;
+		multi_peaks_kernel<<<c, 32, 0, cs>>>(mc, nc, blen, sps, c);
+		e = cudaGetLastError();
+		launches += 2;
+	}
+	if (e == cudaSuccess) {
+		const int ne = n * NPK;
+		multi_cand_kernel<<<(ne + tb - 1) / tb, tb, 0, cs>>>(m, n);
 		FcchArgs f = {};
-		f.iq = d_iq; f.ofs = d_ofs; f.n = nk; f.win_len = blen * sps; f.sps = sps;
-		f.freq = a.freq; f.len = blen; f.freq_shift = d_fs; f.toa = d_toa; f.freq_error = d_fe;
+		f.iq = d_iq; f.ofs = m.c_ofs; f.n = ne; f.win_len = blen * sps; f.sps = sps;
+		f.freq = FCCH_TYPES[fcch_type].freq; f.len = blen; f.freq_shift = m.c_fs; f.skip = m.c_skip;
+		f.toa = m.c_toa; f.freq_error = m.c_fe;
+		e = launch_fcch_fine(f, 0, cs);                            // :684
 		if (e == cudaSuccess) {
-			e = launch_fcch_fine(f, 0, cs);                        // :684
-			launches++;
+			multi_snr_prep_kernel<<<(ne + tb - 1) / tb, tb, 0, cs>>>(m, n);
+			f.toa = nullptr; f.freq_error = nullptr; f.snr = m.c_snr;
+			e = launch_fcch_fine(f, 1, cs);                        // :694
 		}
-		down(toa.data(), d_toa, (size_t)nk * sizeof(int32_t));
-		down(fe.data(), d_fe, (size_t)nk * sizeof(float));
-		if (e == cudaSuccess)
-			e = cudaStreamSynchronize(cs);
-		if (e != cudaSuccess)
-			break;
-		for (int j = 0; j < nk; j++) {                             // SNR at the fine position (:691-696)
-			cofs[j] += toa[j];
-			cfs[j] = -(-cfs[j] + fe[j]);
-		}
-		up(d_ofs, cofs.data(), (size_t)nk * sizeof(int64_t));
-		up(d_fs, cfs.data(), (size_t)nk * sizeof(float));
-		f.toa = nullptr; f.freq_error = nullptr; f.snr = d_snr;
 		if (e == cudaSuccess) {
-			e = launch_fcch_fine(f, 1, cs);
-			launches++;
+			multi_filter_kernel<<<(n + tb - 1) / tb, tb, 0, cs>>>(m, max_cand, d_nf, d_ca, d_cs, d_cf, n);
+			e = cudaGetLastError();
 		}
-		down(snr.data(), d_snr, (size_t)nk * sizeof(float));
-		if (e == cudaSuccess)
-			e = cudaStreamSynchronize(cs);
-		if (e != cudaSuccess)
-			break;
-		// the strongest is the reference; the others must be strong enough and close in frequency (:702-717)
-		for (int k = 0; k < m; k++) {
-			const int i = chan[k];
-			if (bad[k])
-				continue;
-			float ref_snr = 0.0f, ref_fe = 0.0f;
-			int cnt = 0;
-			for (int j = first[k]; j < first[k + 1]; j++) {
-				if (j == first[k]) {
-					ref_snr = snr[j];
-					ref_fe = fe[j];
-				} else {
-					if (snr[j] < 2.0f)
-						continue;
-					if (snr[j] < ref_snr / 6.0f)
-						continue;
-					const float d = (float)fabs(ref_fe - fe[j]);
-					if ((sym_rate * d) / (2.0f * (float)M_PI) > 500.0f)
-						continue;
-				}
-				if (cnt < max_cand) {
-					const size_t o = (size_t)i * max_cand + cnt;
-					cand_align[o] = base[k] + mtoa[j] + toa[j];     // :738, where process_bcch starts
-					if (cand_snr)
-						cand_snr[o] = snr[j];
-					if (cand_freq_err)
-						cand_freq_err[o] = fe[j];
-				}
-				cnt++;
-			}
-			n_fcch[i] = cnt < max_cand ? cnt : max_cand;
-		}
+		launches += 5;
 	}
 	g_launches.fetch_add(launches);
-	if (e != cudaSuccess)
-		cudaStreamSynchronize(cs);
 	return s.finish(e, "fcch_multi_batch kernels");
 }
 

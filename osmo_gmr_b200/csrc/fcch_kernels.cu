@@ -72,6 +72,8 @@ __global__ void __launch_bounds__(FR_T, 2) fcch_rough_kernel(const FcchArgs a)
 {
 	extern __shared__ __align__(16) uint8_t smem[];
 	const int tid = threadIdx.x, b = blockIdx.x;
+	if (a.skip && a.skip[b])
+		return;
 	const int sps = a.sps, L = a.win_len, len = a.len;
 	const int l = L / sps;                 // decimated length
 	const int nc = l - len + 1;            // correlation outputs
@@ -348,6 +350,8 @@ __global__ void __launch_bounds__(FF_T) fcch_fine_kernel(const FcchArgs a, int m
 	extern __shared__ __align__(16) uint8_t smem[];
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int b = blockIdx.x;
+	if (a.skip && a.skip[b])
+		return;
 	const int len = a.len, sps = a.sps, L = a.win_len;
 	const int lp = (len + 3) & ~3;
 	float4 *mix = (float4 *)smem;                    // [lp] (up.re, up.im, down.re, down.im) spectra in

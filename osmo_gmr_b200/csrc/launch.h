@@ -70,6 +70,7 @@ struct FcchArgs {
 	float         *peak;                   // rough: [n] energy of the winning window, or NULL
 	float         *en_out;                 // rough: if set, [n][win_len/sps - len + 1] |corr|^2 is written and
 	                                       //        the peak search is left to the caller (rough_multi)
+	const int32_t *skip;                   // optional [n]: entry b is left alone when skip[b] != 0 (device-side lists)
 };
 cudaError_t launch_fcch_rough(const FcchArgs &a, cudaStream_t st);
 cudaError_t launch_fcch_fine(const FcchArgs &a, int mode, cudaStream_t st);
