@@ -382,6 +382,15 @@ int gmr1b200_fcch_rough_batch(int fcch_type, const float *iq, int64_t iq_len,
                               const float *freq_shift, float freq_shift0,
                               int32_t *toa, float *peak, int n, void *stream);
 
+/* gmr1_fcch_rough for a GRID of frequency shifts per window (the "+-frequency-offset FCCH search" of a receiver that
+ * does not know its carrier offset yet: n_shifts calls of gmr1_fcch_rough, src/sdr/fcch.c:211, with freq_shift =
+ * shifts[k], on the same window).  The window is read, averaged, decimated and normalised once; the shift moves
+ * onto the 117 reference taps, and a pair of shifts +-f shares its two real-tap correlations.  shifts [n_shifts]
+ * host memory (1..16, rad/symbol); toa [n_shifts][n], peak [n_shifts][n] or NULL (energy of the winning window). */
+int gmr1b200_fcch_rough_grid_batch(int fcch_type, const float *iq, int64_t iq_len, const int64_t *win_ofs,
+                                   int64_t win_stride, int win_len, int sps, const float *shifts, int n_shifts,
+                                   int32_t *toa, float *peak, int n, void *stream);
+
 /* replaces gmr1_fcch_fine, src/sdr/fcch.c:512 (sdr/fcch.h:55-57): each window is exactly
  * burst_len*sps samples (else the reference returns -EINVAL); toa [n] samples, freq_error [n] rad/symbol */
 int gmr1b200_fcch_fine_batch(int fcch_type, const float *iq, int64_t iq_len,

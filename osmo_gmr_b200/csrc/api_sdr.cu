@@ -480,6 +480,46 @@ static int fine_or_snr(int mode, int fcch_type, const float *iq, int64_t iq_len,
 	return s.finish(e, "fcch_fine kernel");
 }
 
+int gmr1b200_fcch_rough_grid_batch(int fcch_type, const float *iq, int64_t iq_len, const int64_t *win_ofs,
+                                   int64_t win_stride, int win_len, int sps, const float *shifts, int n_shifts,
+                                   int32_t *toa, float *peak, int n, void *stream)
+{
+	if (!toa || !shifts || n_shifts < 1 || n_shifts > 16)
+		return set_err(-EINVAL, "fcch_rough_grid_batch: bad argument");
+	FcchArgs a = {};
+	a.iq = (const float2 *)iq; a.ofs = win_ofs; a.stride = win_stride; a.n = n; a.win_len = win_len; a.sps = sps;
+	Stage s(stream);
+	int rc = fcch_common(fcch_type, a, s, iq_len, "fcch_rough_grid_batch: bad argument");
+	if (rc)
+		return rc;
+	if (win_len / sps < a.len)
+		return set_err(-EINVAL, "fcch_rough_grid_batch: window shorter than the FCCH burst");
+	if (n == 0)
+		return 0;
+	const size_t N = (size_t)n;
+	int32_t *d_toa = s.out(toa, N * n_shifts);
+	float *d_peak = s.out(peak, N * n_shifts);
+	cudaError_t e = cudaSuccess;
+	if (!s.failed()) {
+		e = launch_fcch_grid(a, shifts, n_shifts, d_toa, d_peak, (cudaStream_t)stream);
+		if (e == cudaSuccess) {
+			g_launches.fetch_add(1);
+		} else if (e == cudaErrorNotSupported) {       // geometry outside the grid kernel: one search per shift
+			cudaGetLastError();
+			e = cudaSuccess;
+			for (int k = 0; k < n_shifts && e == cudaSuccess; k++) {
+				FcchArgs b = a;
+				b.freq_shift0 = shifts[k];
+				b.toa = d_toa + N * k;
+				b.peak = d_peak ? d_peak + N * k : nullptr;
+				e = launch_fcch_rough(b, (cudaStream_t)stream);
+				g_launches.fetch_add(1);
+			}
+		}
+	}
+	return s.finish(e, "fcch_rough_grid kernel");
+}
+
 int gmr1b200_fcch_fine_batch(int fcch_type, const float *iq, int64_t iq_len, const int64_t *win_ofs,
                              int64_t win_stride, int sps, const float *freq_shift, float freq_shift0,
                              int32_t *toa, float *freq_error, int n, void *stream)

@@ -17,6 +17,7 @@
 // +-1 sample and require >= 99 % equal); freq_error within 1e-5 rad/symbol; SNR within 1e-3 relative.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "launch.h"
 
@@ -516,6 +517,13 @@ cudaError_t launch_fcch_rough(const FcchArgs &a, cudaStream_t st)
 {
 	if (a.n <= 0)
 		return cudaSuccess;
+	static const bool old_only = [] { const char *e = getenv("GMR1B200_FCCH_OLD"); return e && atoi(e) != 0; }();
+	if (!a.en_out && !old_only) {          // the search itself: second-generation kernel where it applies
+		const cudaError_t ge = launch_fcch_grid(a, nullptr, 0, nullptr, nullptr, st);
+		if (ge != cudaErrorNotSupported)
+			return ge;
+		cudaGetLastError();
+	}
 	const int l = a.win_len / a.sps, nc = l - a.len + 1;
 	if (nc < 1 || a.len > MAX_FCCH_LEN)
 		return cudaErrorInvalidValue;

@@ -73,6 +73,10 @@ struct FcchArgs {
 	const int32_t *skip;                   // optional [n]: entry b is left alone when skip[b] != 0 (device-side lists)
 };
 cudaError_t launch_fcch_rough(const FcchArgs &a, cudaStream_t st);
+// second-generation coarse search (fcch_grid.cu): shifts == NULL: one search per window with the window's own shift;
+// else n_shifts searches per window sharing one pass over the samples, toa / peak [n_shifts][n].
+// cudaErrorNotSupported: geometry outside the kernel's range, use launch_fcch_rough
+cudaError_t launch_fcch_grid(const FcchArgs &a, const float *shifts, int n_shifts, int32_t *toa, float *peak, cudaStream_t st);
 cudaError_t launch_fcch_fine(const FcchArgs &a, int mode, cudaStream_t st);
 
 // ---- DKAB / modulation order

@@ -73,6 +73,7 @@ class Lib:
         "gmr1b200_rx_bcch_ass_batch": [_P, _L, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
         "gmr1b200_a5_batch": [_P, _I, _P, _P, _I, _I, _P, _P, _I, _P],
         "gmr1b200_gsmtap_batch": [_P, _I, _P, ctypes.c_uint32, _P, _I, _P, _I, _I, _P, _I, _I, _P],
+        "gmr1b200_fcch_rough_grid_batch": [_I, _P, _L, _P, _L, _I, _I, _P, _I, _P, _P, _I, _P],
         "gmr1b200_fcch_acquire_batch": [_I, _P, _L, _P, _L, _I, _I, _P, _P, _P, _I, _P],
         "gmr1b200_fcch_snr_batch": [_I, _P, _L, _P, _L, _I, _P, _F, _P, _I, _P],
         "gmr1b200_dkab_demod_batch": [_P, _L, _P, _L, _I, _I, _P, _F, _P, _I, _P, _P, _P, _I, _P],

@@ -32,6 +32,40 @@ def test_fcch_rough(gpu_lib, oracle):
     assert same >= n - 1
 
 
+@pytest.mark.parametrize("grid", [[0.0, 0.27, -0.27, 0.54, -0.54], [0.1], [-0.2, 0.0], [0.05, 0.1, 0.15, -0.15]])
+def test_fcch_rough_grid(gpu_lib, oracle, grid):
+    """gmr1b200_fcch_rough_grid_batch: every shift of the grid answers what gmr1_fcch_rough (src/sdr/fcch.c:211)
+    answers for that freq_shift on the same window - paired (+-f), unpaired and zero shifts, ragged window
+    lengths (the last round of outputs partly empty), host and strided windows."""
+    rng = np.random.default_rng(131 + len(grid))
+    n, L = 10, 30888 - 4 * 37
+    stride = L + 24
+    pos = rng.integers(600, L - 1200, n)
+    cfo = rng.choice(np.array(grid, np.float64), n) * -1.0 + rng.uniform(-0.05, 0.05, n)
+    buf = np.zeros((n, stride), np.complex64)
+    for i in range(n):
+        buf[i, :L] = sigen.fcch_window(L, SPS, int(pos[i]), cfo[i], [3.0, 10.0, 20.0][i % 3], rng)
+    g = np.array(grid, np.float32)
+    toa = np.full((len(grid), n), -1, np.int32)
+    peak = np.zeros((len(grid), n), np.float32)
+    gpu_lib.call("gmr1b200_fcch_rough_grid_batch", 0, _iq(buf), n * stride, None, stride, L, SPS, g, len(grid), toa,
+                 peak, n, None)
+    same = 0
+    for k, fs in enumerate(grid):
+        for i in range(n):
+            rc, t = oracle.fcch_rough(buf[i, :L], SPS, float(g[k]))
+            assert rc == 0 and abs(int(toa[k, i]) - t) <= 1, (k, i, toa[k, i], t)
+            same += int(toa[k, i] == t)
+    assert same >= len(grid) * n - 2
+    assert (peak > 0).all()
+    # single-shift entry on the same windows: same answers as the grid's column
+    t1 = np.full(n, -1, np.int32)
+    p1 = np.zeros(n, np.float32)
+    gpu_lib.call("gmr1b200_fcch_rough_batch", 0, _iq(buf), n * stride, None, stride, L, SPS, None, float(g[0]), t1, p1, n,
+                 None)
+    assert (t1 == toa[0]).all() and np.allclose(p1, peak[0], rtol=1e-4)
+
+
 def test_fcch_fine_and_snr(gpu_lib, oracle):
     rng = np.random.default_rng(32)
     n, W = 96, 117 * SPS
