@@ -14,6 +14,7 @@
 // osmo_crc*gen_check_bits of the reference (see decode_unit.cuh for file:line).
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "decode_unit.cuh"
 #include "tma.cuh"
@@ -21,7 +22,10 @@
 
 namespace gmr1 {
 
-static constexpr int TPC_T = 128;    // threads (= codewords) per CTA
+static constexpr int TPC_T = 128;    // codewords per CTA
+// threads per CTA: one per codeword, or - PAIR - one per two codewords (viterbi_p16.cuh: thread i takes codewords
+// i and i + 64 of the tile)
+__host__ __device__ constexpr int tpc_threads(bool pair) { return pair ? TPC_T / 2 : TPC_T; }
 
 // ---- device tables --------------------------------------------------------------------------
 __constant__ uint16_t c_g[CH_COUNT][MAX_CODED];     // gather programs (uniform access)
@@ -85,15 +89,16 @@ __host__ __device__ constexpr int chan_dec_bytes(int ch)
 __host__ __device__ constexpr int tpc_rows_bytes(int ch) { return (TPC_T * chan_n_row(ch) + 15) & ~15; }
 __host__ __device__ constexpr int tpc_smem_bytes(int ch)
 {
-	return tpc_rows_bytes(ch) + TPC_T * chan_dec_bytes(ch) + 16;
+	return tpc_rows_bytes(ch) + TPC_T * chan_dec_bytes(ch) + 16 + (int)sizeof(P16Lut);
 }
 
 // ---- thread-per-codeword kernel ------------------------------------------------------------------
-template <int CH>
-__global__ void __launch_bounds__(TPC_T) decode_tpc_kernel(const DecodeArgs a)
+template <int CH, bool PAIR>
+__global__ void __launch_bounds__(tpc_threads(PAIR)) decode_tpc_kernel(const DecodeArgs a)
 {
 	extern __shared__ __align__(16) uint8_t smem[];
-	constexpr int NIN = chan_n_in(CH), NROW = chan_n_row(CH);
+	constexpr int NIN = chan_n_in(CH), NROW = chan_n_row(CH), NT = tpc_threads(PAIR);
+
 	int8_t *rows = (int8_t *)smem;                                    // [TPC_T][NROW], unpadded
 	// survivor decisions [steps][words][slots]: in the caller's scratch (slot = unit, all units of the launch
 	// side by side: coalesced 64-byte stores per warp and step) or, without scratch, behind the rows in
@@ -101,6 +106,7 @@ __global__ void __launch_bounds__(TPC_T) decode_tpc_kernel(const DecodeArgs a)
 	const bool gdec = a.dec_scratch != nullptr;
 	uint8_t *dec = gdec ? a.dec_scratch : smem + tpc_rows_bytes(CH);
 	uint64_t *bar = (uint64_t *)(smem + tpc_rows_bytes(CH) + (gdec ? 0 : TPC_T * chan_dec_bytes(CH)));
+	P16Lut *lut = (P16Lut *)(bar + 2);                                // PAIR: soft bit -> packed metrics
 
 	TabRef tb;
 	tb.g = c_g[CH];
@@ -116,6 +122,10 @@ __global__ void __launch_bounds__(TPC_T) decode_tpc_kernel(const DecodeArgs a)
 	if (base >= n_eff)
 		return;                  // whole CTA, before any barrier
 	const int cnt = min(TPC_T, n_eff - base);
+	if constexpr (PAIR) {
+		for (int i = tid; i < 512; i += NT)
+			(&lut->plain[0])[i] = p16_lut_word(i);                    // visible after the barrier that ends phase 1
+	}
 
 	// ---- phase 1: stage the tile
 	const bool plain = !chan_is_t9(CH) && (chan_n_ciph(CH) == 0 || a.ciph == nullptr);
@@ -138,21 +148,23 @@ __global__ void __launch_bounds__(TPC_T) decode_tpc_kernel(const DecodeArgs a)
 		// warps per SM and a chain of three dependent loads per byte)
 		__shared__ int s_prev[2][TPC_T];
 		__shared__ uint16_t s_src[648];
-		s_prev[0][tid] = (tid < cnt && a.prev1) ? a.prev1[base + tid] : -1;
-		s_prev[1][tid] = (tid < cnt && a.prev2) ? a.prev2[base + tid] : -1;
-		for (int r = tid; r < 648; r += TPC_T)
+		for (int u = tid; u < TPC_T; u += NT) {
+			s_prev[0][u] = (u < cnt && a.prev1) ? a.prev1[base + u] : -1;
+			s_prev[1][u] = (u < cnt && a.prev2) ? a.prev2[base + u] : -1;
+		}
+		for (int r = tid; r < 648; r += NT)
 			s_src[r] = tb.t9_src[r];
 		__syncthreads();
 		// eight elements per thread and pass: source addresses first (shared-memory lookups only), then the eight
 		// byte loads back to back (clamped, so that they are unconditional), then the stores
 		constexpr int E = 8;
-		for (int idx0 = tid; idx0 < TPC_T * NROW; idx0 += TPC_T * E) {
+		for (int idx0 = tid; idx0 < TPC_T * NROW; idx0 += NT * E) {
 			const int8_t *src[E];
 			const uint8_t *csrc[E];
 			bool ok[E], flip[E];
 #pragma unroll
 			for (int e = 0; e < E; e++) {
-				const int idx = min(idx0 + e * TPC_T, TPC_T * NROW - 1);
+				const int idx = min(idx0 + e * NT, TPC_T * NROW - 1);
 				const int tt = idx / NROW, r = idx - tt * NROW;
 				const uint16_t w = s_src[r];
 				const int age = (w >> 10) & 3, sidx = w & G_IDX;
@@ -177,22 +189,32 @@ __global__ void __launch_bounds__(TPC_T) decode_tpc_kernel(const DecodeArgs a)
 					x = sbit_neg(x);
 				if (flip[e])
 					x = sbit_neg(x);
-				if (idx0 + e * TPC_T < TPC_T * NROW)
-					rows[idx0 + e * TPC_T] = ok[e] ? (int8_t)x : (int8_t)0;
+				if (idx0 + e * NT < TPC_T * NROW)
+					rows[idx0 + e * NT] = ok[e] ? (int8_t)x : (int8_t)0;
 			}
 		}
 		__syncthreads();
 	} else {
 #pragma unroll 4
-		for (int idx = tid; idx < TPC_T * NROW; idx += TPC_T) {
+		for (int idx = tid; idx < TPC_T * NROW; idx += NT) {
 			const int tt = idx / NROW, r = idx - tt * NROW;
 			rows[idx] = (tt < cnt) ? stage_elem<CH>(tb, a, base + tt, r) : (int8_t)0;
 		}
 		__syncthreads();
 	}
 
-	// ---- phase 2: one codeword per thread
-	if (tid < cnt) {
+	// ---- phase 2: one codeword (PAIR: two) per thread
+	if constexpr (PAIR) {
+		if (tid < cnt) {
+			const int T = gdec ? (int)gridDim.x * NT : NT, t = gdec ? (int)blockIdx.x * NT + tid : tid;
+			if constexpr (CH == CH_TCH3)
+				decode_pair_tch3(tb, a, lut, base + tid, base + tid + NT, tid + NT < cnt, rows + tid * NROW,
+				                 rows + (tid + NT) * NROW, (uint32_t *)dec, T, t);
+			else
+				decode_pair_k5<CH>(tb, a, lut, base + tid, base + tid + NT, tid + NT < cnt, rows + tid * NROW,
+				                   rows + (tid + NT) * NROW, (uint32_t *)dec, T, t);
+		}
+	} else if (tid < cnt) {
 		const int T = gdec ? (int)gridDim.x * TPC_T : TPC_T, t = gdec ? base + tid : tid;
 		if constexpr (CH == CH_TCH3)
 			decode_unit_tch3(tb, a, base + tid, rows + tid * NROW, (uint32_t *)dec, T, t);
@@ -201,24 +223,40 @@ __global__ void __launch_bounds__(TPC_T) decode_tpc_kernel(const DecodeArgs a)
 	}
 }
 
-template <int CH>
+// Two codewords per thread (viterbi_p16.cuh) pay where REGISTERS bound the resident warps: TCH3 (64 path metrics per
+// thread, 143 registers, 12 warps per SM).  The K5 channels are bound by the shared memory their soft-bit rows take
+// (54 .. 85 KB per 128 codewords): two codewords per thread halve the resident warps there and win nothing (A/B in
+// profiles/README.md), so they stay on one codeword per thread.  GMR1B200_DECODE_P16 = 0: one per thread everywhere,
+// = 1: two per thread everywhere (results are identical in every setting).
+static int decode_p16_mode()
+{
+	static const int m = [] { const char *e = getenv("GMR1B200_DECODE_P16"); return e ? (atoi(e) != 0 ? 1 : 0) : -1; }();
+	return m;
+}
+
+template <int CH, bool PAIR = false>
 static cudaError_t launch_tpc(const DecodeArgs &a, cudaStream_t st)
 {
+	if constexpr (!PAIR) {
+		const int m = decode_p16_mode();
+		if (m == 1 || (m < 0 && CH == CH_TCH3))
+			return launch_tpc<CH, true>(a, st);
+	}
 	GMR1_INIT_LOCK();
 	static bool attr_done[64] = {false};
 	int dev = 0;
 	cudaGetDevice(&dev);
 	constexpr int smem = tpc_smem_bytes(CH);
 	if (dev >= 64 || !attr_done[dev]) {
-		cudaError_t e = cudaFuncSetAttribute(decode_tpc_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		cudaError_t e = cudaFuncSetAttribute(decode_tpc_kernel<CH, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 		if (e != cudaSuccess)
 			return e;
 		if (dev < 64)
 			attr_done[dev] = true;
 	}
 	const int grid = (a.n + TPC_T - 1) / TPC_T;
-	const int smem_used = a.dec_scratch ? tpc_rows_bytes(CH) + 16 : smem;
-	decode_tpc_kernel<CH><<<grid, TPC_T, smem_used, st>>>(a);
+	const int smem_used = (a.dec_scratch ? tpc_rows_bytes(CH) + 16 : smem - (int)sizeof(P16Lut)) + (PAIR ? (int)sizeof(P16Lut) : 0);
+	decode_tpc_kernel<CH, PAIR><<<grid, tpc_threads(PAIR), smem_used, st>>>(a);
 	return cudaGetLastError();
 }
 

@@ -6,6 +6,7 @@
 // (tch9.c:140), gmr1_rach_decode (rach.c:137), gmr1_tch3_decode (tch3.c:124).
 #pragma once
 #include "viterbi_tpc.cuh"
+#include "viterbi_p16.cuh"
 
 namespace gmr1 {
 
@@ -61,6 +62,14 @@ GMR1_HD constexpr bool chan_has_erasures(int ch)
 	return !(ch == CH_BCCH || ch == CH_CCCH || ch == CH_FACCH3 || ch == CH_FACCH9);
 }
 
+// info bits per codeword (the data steps of the forward pass)
+GMR1_HD constexpr int chan_len_of(int ch)
+{
+	return ch == CH_BCCH || ch == CH_CCCH || ch == CH_DC12 ? 208 : ch == CH_FACCH3 ? 92 :
+	       ch == CH_FACCH9 ? 316 : ch == CH_TCH9_2K4 ? 144 : ch == CH_TCH9_4K8 ? 240 :
+	       ch == CH_TCH9_9K6 ? 480 : ch == CH_RACH ? 159 : 48;
+}
+
 GMR1_HD constexpr int chan_l2_bytes(int ch)
 {
 	return ch == CH_BCCH || ch == CH_CCCH || ch == CH_DC12 ? 24 :
@@ -114,15 +123,12 @@ GMR1_HD int8_t stage_elem(const TabRef &tb, const DecodeArgs &a, int unit, int r
 // ---- per-unit decode, flush-terminated K5 channels ------------------------------------------
 // row: staged soft bits of this unit (n_row bytes, overwritten with the packed output bits),
 // dec: decision storage [n_steps][T] words, t: this thread's slot
+// side outputs that are plain copies of (deciphered) soft bits
 template <int CH>
-GMR1_HD void decode_unit_k5(const TabRef &tb, const DecodeArgs &a, int unit,
-                            int8_t *row, uint16_t *dec, int T, int t)
+GMR1_HD void k5_side_outputs(const DecodeArgs &a, int unit)
 {
-	using C = typename ChanCode<CH>::type;
 	constexpr bool T9 = (CH == CH_TCH9_2K4 || CH == CH_TCH9_4K8 || CH == CH_TCH9_9K6);
 	constexpr bool F9 = (CH == CH_FACCH9);
-
-	// side outputs that are plain copies of (deciphered) soft bits
 	if (CH == CH_FACCH3 && a.bits_s) {
 		for (int b = 0; b < 4; b++)
 			for (int j = 0; j < 8; j++)     // facch3.c:141-142 (status bits are not ciphered)
@@ -141,6 +147,17 @@ GMR1_HD void decode_unit_k5(const TabRef &tb, const DecodeArgs &a, int unit,
 				a.sacch[(size_t)unit * 10 + i] = (int8_t)v;
 			}
 	}
+}
+
+template <int CH>
+GMR1_HD void k5_outputs(const DecodeArgs &a, int unit, uint8_t *out);
+
+template <int CH>
+GMR1_HD void decode_unit_k5(const TabRef &tb, const DecodeArgs &a, int unit,
+                            int8_t *row, uint16_t *dec, int T, int t)
+{
+	using C = typename ChanCode<CH>::type;
+	k5_side_outputs<CH>(a, unit);
 
 	uint32_t ae[C::NS];
 #pragma unroll
@@ -185,7 +202,14 @@ GMR1_HD void decode_unit_k5(const TabRef &tb, const DecodeArgs &a, int unit,
 			out[i >> 3] = (uint8_t)acc;
 		}
 	}
+	k5_outputs<CH>(a, unit, out);
+}
 
+// CRC(s) and packed L2 of one unit from the decoded bits (LSB-first packed bytes in `out`)
+template <int CH>
+GMR1_HD void k5_outputs(const DecodeArgs &a, int unit, uint8_t *out)
+{
+	constexpr bool T9 = (CH == CH_TCH9_2K4 || CH == CH_TCH9_4K8 || CH == CH_TCH9_9K6);
 	constexpr int NB = chan_l2_bytes(CH);
 	uint8_t *l2 = a.l2 + (size_t)unit * NB;
 
@@ -236,6 +260,99 @@ GMR1_HD void decode_unit_k5(const TabRef &tb, const DecodeArgs &a, int unit,
 			l2[i] = (uint8_t)byte;
 		}
 	}
+}
+
+// ---- TWO units per thread, flush-terminated K5 channels (viterbi_p16.cuh) -------------------------------------
+// unit A in the low, unit B in the high halves.  okB = false: there is no unit B (ragged tail of the batch; its staged
+// row is all zeros), nothing is written for it.  dec: [n_steps][T] 32-bit words, t: this thread's slot.
+template <int CH>
+GMR1_HD void decode_pair_k5(const TabRef &tb, const DecodeArgs &a, const P16Lut *lut, int unitA, int unitB, bool okB,
+                            int8_t *rowA, int8_t *rowB, uint32_t *dec, int T, int t)
+{
+	using C = typename ChanCode<CH>::type;
+	static_assert(C::NS == 16, "K = 5 codes");
+	k5_side_outputs<CH>(a, unitA);
+	if (okB)
+		k5_side_outputs<CH>(a, unitB);
+
+	uint32_t ae[C::NS], tmp[C::NS];
+#pragma unroll
+	for (int s = 0; s < C::NS; s++)
+		ae[s] = s ? P16_UNREACHABLE : 0u;
+	uint32_t offA = 0, offB = 0;
+	constexpr bool ER = chan_has_erasures(CH), G2 = CH == CH_RACH;
+	constexpr bool RN = p16_needs_renorm(C::N, C::K, chan_len_of(CH) + C::K - 1);
+	p16_forward<C, true, G2, ER, RN>(ae, lut, rowA, rowB, tb.g, tb.g2, 0, tb.len, dec, T, t, offA, offB);
+	if (RN)
+		p16_renorm<C>(ae, offA, offB);
+	p16_flush_step<C, 0, G2, ER>(ae, tmp, lut, rowA, rowB, tb.g, tb.g2, tb.len, dec, T, t);
+	p16_flush_step<C, 1, G2, ER>(tmp, ae, lut, rowA, rowB, tb.g, tb.g2, tb.len + 1, dec, T, t);
+	p16_flush_step<C, 2, G2, ER>(ae, tmp, lut, rowA, rowB, tb.g, tb.g2, tb.len + 2, dec, T, t);
+	p16_flush_step<C, 3, G2, ER>(tmp, ae, lut, rowA, rowB, tb.g, tb.g2, tb.len + 3, dec, T, t);
+
+	if (a.conv) {
+		a.conv[unitA] = (int32_t)((ae[0] & 0xffffu) + offA);
+		if (okB)
+			a.conv[unitB] = (int32_t)((ae[0] >> 16) + offB);
+	}
+
+	// traceback of both codewords in one walk (two independent chains of load -> shift -> state)
+	uint8_t *outA = (uint8_t *)rowA, *outB = (uint8_t *)rowB;
+	{
+		unsigned sa = 0, sb = 0;
+		auto back = [&](int i) {
+			const uint32_t d = dec[(size_t)i * T + t];
+			const unsigned ba = (d >> sa) & 1u, bb = (d >> (16 + sb)) & 1u;
+			sa = (sa >> 1) | (ba << (C::K - 2));
+			sb = (sb >> 1) | (bb << (C::K - 2));
+		};
+		for (int i = tb.n_steps - 1; i >= tb.len; i--)
+			back(i);
+		int i = tb.len - 1;
+		unsigned acca = 0, accb = 0;
+		for (; (i & 7) != 7; i--) {          // ragged top byte (len not a multiple of 8)
+			acca |= (sa & 1u) << (i & 7);
+			accb |= (sb & 1u) << (i & 7);
+			back(i);
+		}
+		if ((tb.len & 7) != 0) {
+			outA[tb.len >> 3] = (uint8_t)acca;
+			outB[tb.len >> 3] = (uint8_t)accb;
+		}
+		// whole bytes: the decision word of a step does not depend on the state (one word per step for 16 states), so
+		// the eight words of the NEXT byte are fetched while the dependent shift chain of this one runs
+		uint32_t cur[8], nxt[8];
+		if (i >= 7) {
+#pragma unroll
+			for (int b = 0; b < 8; b++)
+				cur[b] = dec[(size_t)(i - 7 + b) * T + t];
+		}
+		for (; i >= 7; i -= 8) {
+			if (i >= 15) {
+#pragma unroll
+				for (int b = 0; b < 8; b++)
+					nxt[b] = dec[(size_t)(i - 15 + b) * T + t];
+			}
+			acca = accb = 0;
+#pragma unroll
+			for (int b = 7; b >= 0; b--) {
+				acca |= (sa & 1u) << b;
+				accb |= (sb & 1u) << b;
+				const uint32_t d = cur[b];
+				const unsigned ba = (d >> sa) & 1u, bb = (d >> (16 + sb)) & 1u;
+				sa = (sa >> 1) | (ba << (C::K - 2));
+				sb = (sb >> 1) | (bb << (C::K - 2));
+			}
+			outA[i >> 3] = (uint8_t)acca;
+			outB[i >> 3] = (uint8_t)accb;
+#pragma unroll
+			for (int b = 0; b < 8; b++)
+				cur[b] = nxt[b];
+		}
+	}
+	k5_outputs<CH>(a, unitA, outA);
+	if (okB)
+		k5_outputs<CH>(a, unitB, outB);
 }
 
 // ---- per-unit decode, TCH3 (two tail-biting K7 frames + class-2 bits) --------------------------
@@ -300,6 +417,92 @@ GMR1_HD void decode_unit_tch3(const TabRef &tb, const DecodeArgs &a, int unit,
 		fr[0] = (uint8_t)(w0 >> 24); fr[1] = (uint8_t)(w0 >> 16); fr[2] = (uint8_t)(w0 >> 8); fr[3] = (uint8_t)w0;
 		fr[4] = (uint8_t)(w1 >> 24); fr[5] = (uint8_t)(w1 >> 16); fr[6] = (uint8_t)(w1 >> 8); fr[7] = (uint8_t)w1;
 		fr[8] = (uint8_t)(w2 >> 24); fr[9] = (uint8_t)(w2 >> 16);
+	}
+}
+
+// ---- TWO units per thread, TCH3 (viterbi_p16.cuh; 64 packed path metrics per thread) -------------------------------
+// The one-unit form is bound by registers (143 per thread: 12 resident warps per SM); two units in the same registers
+// double the work of every resident warp.  dec: [48][4][T] 32-bit words (word w of a step: states 16 w .. 16 w + 15).
+GMR1_HD void decode_pair_tch3(const TabRef &tb, const DecodeArgs &a, const P16Lut *lut, int unitA, int unitB, bool okB,
+                              const int8_t *rowA, const int8_t *rowB, uint32_t *dec, int T, int t)
+{
+	using C = CodeK7_12;
+	if (a.bits_s)
+		for (int i = 0; i < 4; i++) {       // tch3.c:134-135
+			a.bits_s[(size_t)unitA * 4 + i] = a.ebits[(size_t)unitA * 212 + 52 + i] < 0;
+			if (okB)
+				a.bits_s[(size_t)unitB * 4 + i] = a.ebits[(size_t)unitB * 212 + 52 + i] < 0;
+		}
+
+	for (int f = 0; f < 2; f++) {
+		const uint16_t *g = tb.g + (2 * (a.tch3_m ? 1 : 0) + f) * 128;
+		uint32_t ae[C::NS];
+#pragma unroll
+		for (int s = 0; s < C::NS; s++)
+			ae[s] = s ? P16_UNREACHABLE : 0u;
+		uint32_t offA = 0, offB = 0;
+		// seeding pass, no history kept; 48 steps add at most 12 192 to the sentinel: no renormalisation inside a pass
+		p16_forward<C, false, false, true, false>(ae, lut, rowA, rowB, g, nullptr, 0, 48, dec, T, t, offA, offB);
+		p16_renorm<C>(ae, offA, offB);          // osmo_conv_decode_rewind: the minimum comes off (its value is not reported)
+		p16_forward<C, true, false, true, false>(ae, lut, rowA, rowB, g, nullptr, 0, 48, dec, T, t, offA, offB);
+		// end state: FIRST state with the minimal metric, per codeword
+		uint32_t mn = ae[0];
+#pragma unroll
+		for (int s = 1; s < C::NS; s++)
+			mn = p16_minu(mn, ae[s]);
+		const uint32_t bestA = mn & 0xffffu, bestB = mn >> 16;
+		unsigned sa = 0, sb = 0;
+#pragma unroll
+		for (int s = C::NS - 1; s >= 0; s--) {
+			// halves equal to the minimum: x = ae ^ mn has a zero half there
+			const uint32_t x = ae[s] ^ mn;
+			if ((x & 0xffffu) == 0)
+				sa = (unsigned)s;
+			if ((x >> 16) == 0)
+				sb = (unsigned)s;
+		}
+		int32_t *cv = f ? a.conv1 : a.conv;
+		if (cv) {
+			cv[unitA] = (int32_t)bestA;
+			if (okB)
+				cv[unitB] = (int32_t)bestB;
+		}
+
+		// frame bits 0..47 from the decoder, 48..79 = sign of c[72..103]; MSB-first packing
+		uint32_t wa0 = 0, wa1 = 0, wa2 = 0, wb0 = 0, wb1 = 0, wb2 = 0;
+		for (int i = 47; i >= 0; i--) {
+			const uint32_t da = dec[(size_t)(i * 4 + (int)(sa >> 4)) * T + t], db = dec[(size_t)(i * 4 + (int)(sb >> 4)) * T + t];
+			if (i < 32) {
+				wa0 |= (sa & 1u) << (31 - i);
+				wb0 |= (sb & 1u) << (31 - i);
+			} else {
+				wa1 |= (sa & 1u) << (63 - i);
+				wb1 |= (sb & 1u) << (63 - i);
+			}
+			const unsigned ba = (da >> (sa & 15u)) & 1u, bb = (db >> (16u + (sb & 15u))) & 1u;
+			sa = (sa >> 1) | (ba << (C::K - 2));
+			sb = (sb >> 1) | (bb << (C::K - 2));
+		}
+		for (int j = 48; j < 80; j++) {
+			const uint16_t w = g[96 + (j - 48)];
+			const unsigned bitA = gather_sbit(rowA, w) < 0 ? 1u : 0u, bitB = gather_sbit(rowB, w) < 0 ? 1u : 0u;
+			if (j < 64) {
+				wa1 |= bitA << (63 - j);
+				wb1 |= bitB << (63 - j);
+			} else {
+				wa2 |= bitA << (95 - j);
+				wb2 |= bitB << (95 - j);
+			}
+		}
+		auto put = [&](int unit, uint32_t w0, uint32_t w1, uint32_t w2) {
+			uint8_t *fr = (f ? a.l2b : a.l2) + (size_t)unit * 10;
+			fr[0] = (uint8_t)(w0 >> 24); fr[1] = (uint8_t)(w0 >> 16); fr[2] = (uint8_t)(w0 >> 8); fr[3] = (uint8_t)w0;
+			fr[4] = (uint8_t)(w1 >> 24); fr[5] = (uint8_t)(w1 >> 16); fr[6] = (uint8_t)(w1 >> 8); fr[7] = (uint8_t)w1;
+			fr[8] = (uint8_t)(w2 >> 24); fr[9] = (uint8_t)(w2 >> 16);
+		};
+		put(unitA, wa0, wa1, wa2);
+		if (okB)
+			put(unitB, wb0, wb1, wb2);
 	}
 }
 

@@ -29,6 +29,49 @@ static void run(const DecodeArgs &a)
 	}
 }
 
+// two units per "thread" (viterbi_p16.cuh): units (u, u + 1), a ragged last unit runs with an all-zero partner row
+template <int CH>
+static void run_p16(const DecodeArgs &a)
+{
+	const ChanTab &t = chan_tab(CH);
+	TabRef tb;
+	tb.g = t.g; tb.g2 = (CH == CH_RACH) ? t.g2 : nullptr; tb.cmap = t.cmap; tb.t9_src = t.t9_src;
+	tb.n_in = t.n_in; tb.n_row = t.n_row; tb.n_ciph = t.n_ciph; tb.n_steps = t.n_steps; tb.len = t.len;
+	std::vector<int8_t> rowA(t.n_row + 16), rowB(t.n_row + 16);
+	std::vector<uint32_t> dec(2 * 1024);
+	static P16Lut lut;
+	for (int i = 0; i < 512; i++)
+		(&lut.plain[0])[i] = p16_lut_word(i);
+	for (int u = 0; u < a.n; u += 2) {
+		const bool okB = u + 1 < a.n;
+		for (int r = 0; r < t.n_row; r++) {
+			rowA[r] = stage_elem<CH>(tb, a, u, r);
+			rowB[r] = okB ? stage_elem<CH>(tb, a, u + 1, r) : (int8_t)0;
+		}
+		if constexpr (CH == CH_TCH3)
+			decode_pair_tch3(tb, a, &lut, u, u + 1, okB, rowA.data(), rowB.data(), dec.data(), 1, 0);
+		else
+			decode_pair_k5<CH>(tb, a, &lut, u, u + 1, okB, rowA.data(), rowB.data(), dec.data(), 1, 0);
+	}
+}
+
+extern "C" int gmr1_emu_decode_p16(int ch, const DecodeArgs *a)
+{
+	switch (ch) {
+	case CH_BCCH:     run_p16<CH_BCCH>(*a); break;
+	case CH_CCCH:     run_p16<CH_CCCH>(*a); break;
+	case CH_FACCH3:   run_p16<CH_FACCH3>(*a); break;
+	case CH_FACCH9:   run_p16<CH_FACCH9>(*a); break;
+	case CH_TCH9_2K4: run_p16<CH_TCH9_2K4>(*a); break;
+	case CH_TCH9_4K8: run_p16<CH_TCH9_4K8>(*a); break;
+	case CH_TCH9_9K6: run_p16<CH_TCH9_9K6>(*a); break;
+	case CH_RACH:     run_p16<CH_RACH>(*a); break;
+	case CH_TCH3:     run_p16<CH_TCH3>(*a); break;
+	default: return -1;
+	}
+	return 0;
+}
+
 extern "C" int gmr1_emu_decode(int ch, const DecodeArgs *a)
 {
 	switch (ch) {
