@@ -47,6 +47,31 @@ struct HostArena {
 extern thread_local int g_host_hint;
 HostArena &host_arena();          // this thread's arena for the current device (allocated / grown between calls)
 
+// true when this thread can dereference p (plain or pinned host memory); device and managed pointers: false
+inline bool host_pointer(const void *p)
+{
+	if (g_host_hint)
+		return true;
+	cudaPointerAttributes at;
+	if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+		cudaGetLastError();
+		return true;
+	}
+	return at.type == cudaMemoryTypeUnregistered || at.type == cudaMemoryTypeHost;
+}
+
+// recordings [rec_ofs[i], rec_ofs[i] + rec_len[i]) must lie inside iq_len samples: checked when the host can read the
+// descriptors (device-resident descriptors are the caller's responsibility; the kernels bound every window by rec_len)
+inline bool recordings_in_range(const int64_t *rec_ofs, const int32_t *rec_len, int n, int64_t iq_len)
+{
+	if (!host_pointer(rec_ofs) || !host_pointer(rec_len))
+		return true;
+	for (int i = 0; i < n; i++)
+		if (rec_ofs[i] < 0 || rec_len[i] < 0 || rec_ofs[i] + rec_len[i] > iq_len)
+			return false;
+	return true;
+}
+
 // Stage: resolves each pointer argument of a batched call to a device pointer.
 //   in(p, bytes)   host  -> device scratch + H2D copy on the stream;   device -> p itself
 //   out(p, bytes)  host  -> device scratch, D2H copy queued for finish(); device -> p itself

@@ -51,8 +51,19 @@ static int run_demod(const int *types, int n_types, int mode, DemodArgs a, int64
 				ok = t.s_len[s][c] >= 1 && t.s_len[s][c] <= MAX_SYNC_SYMS && t.s_pos[s][c] >= 0 &&
 				     t.s_pos[s][c] + t.s_len[s][c] <= t.len;
 		}
-		for (int c = 0; ok && c < t.n_data; c++)
+		for (int s = 0; ok && s < t.n_sync; s++)
+			for (int c = 0; ok && c < t.n_chunk[s]; c++)
+				for (int k = 0; ok && k < t.s_len[s][c]; k++)
+					ok = t.s_sym[s][c][k] < 4;
+		int n_dsym = 0;
+		for (int c = 0; ok && c < t.n_data; c++) {
 			ok = t.d_pos[c] >= 0 && t.d_len[c] >= 0 && t.d_pos[c] + t.d_len[c] <= t.len;
+			for (int c2 = 0; ok && c2 < c; c2++)          // data chunks must not overlap (each symbol sliced once)
+				ok = t.d_pos[c] >= t.d_pos[c2] + t.d_len[c2] || t.d_pos[c2] >= t.d_pos[c] + t.d_len[c];
+			n_dsym += t.d_len[c];
+		}
+		// the kernel writes nbits soft bits per data symbol whatever `ebits` says: they have to agree
+		ok = ok && t.ebits == n_dsym * t.nbits;
 		if (!ok)
 			return set_err(-EINVAL, "pi4cxpsk batch: malformed burst descriptor");
 	}
@@ -67,6 +78,10 @@ static int run_demod(const int *types, int n_types, int mode, DemodArgs a, int64
 		return 0;
 	if (!a.ofs && (a.stride < 0 || (int64_t)(a.n - 1) * a.stride + a.win_len > iq_len))
 		return set_err(-EINVAL, "pi4cxpsk batch: windows exceed iq_len");
+	if (a.ofs && host_pointer(a.ofs))                     // offsets the host can read are range-checked here
+		for (int i = 0; i < a.n; i++)
+			if (a.ofs[i] < 0 || a.ofs[i] + a.win_len > iq_len)
+				return set_err(-EINVAL, "pi4cxpsk batch: a window offset is outside iq_len");
 
 	const BurstTab *d_all = nullptr;
 	cudaError_t e = device_bursts(&d_all);

@@ -97,6 +97,188 @@ struct GridPlan {
 	int32_t out_p[8], out_m[8];            // output slot of the shift +f / -f of a pass, -1 = not wanted
 };
 
+struct BarCta {                            // all threads of the CTA
+	static __device__ __forceinline__ void sync() { __syncthreads(); }
+};
+struct BarCompute {                        // the FG_T compute threads of the pipelined kernel (named barrier 1)
+	static __device__ __forceinline__ void sync() { asm volatile("bar.sync 1, %0;" ::"n"(FG_T) : "memory"); }
+};
+
+// The search over one normalised, decimated window `w` (swizzled, zero tail behind sample l) by FG_T threads:
+// every pass of the plan, results to toa_out / peak_out [slot][n_total].  Bar synchronises those FG_T threads.
+template <bool PAIR, class Bar>
+__device__ __forceinline__ void search_window(const FcchArgs &a, const GridPlan &gp, int32_t *toa_out, float *peak_out,
+                                              const float *w, float *refc, float *refs, float *red, float *tail,
+                                              int tid, int b, int n_total, int l, int len, int ng, float fbase)
+{
+	const int lane = tid & 31, warp = tid >> 5;
+	const int nc = l - len + 1;
+	const int lenp = (len + 7) & ~7;
+	const int rounds = (nc + FG_T * FG_TILE - 1) / (FG_T * FG_TILE);
+#pragma unroll 1
+	for (int pass = 0; pass < gp.n_pass; pass++) {
+		const float f = gp.n_pass == 1 && gp.f[0] < 0.0f ? fabsf(fbase) : gp.f[pass];
+		Bar::sync();                   // normalised samples ready / previous pass done with the taps
+		{	// dual-chirp reference at 1 sample/symbol (fcch.c:167-193) times e^{j f n}
+			const float phase_base = a.freq * 2.0f * PI_F / (float)len, halfpos = (float)len / 2.0f;
+			for (int i = tid; i < FG_MAXLEN; i += FG_T) {
+				const float pos = (float)i - halfpos;
+				const float r = i < len ? sqrtf(2.0f) * cosf(phase_base * (pos * pos)) : 0.0f;
+				float sn, cs;
+				sincosf(f * (float)i, &sn, &cs);
+				refc[i] = r * cs;
+				refs[i] = r * sn;
+			}
+			if (tid < 8)                   // carry slots: nothing in front of output 0
+				tail[(tid >> 2) * (FG_T + 1) * 4 + (tid & 3)] = 0.0f;
+		}
+		Bar::sync();
+		Best bp, bm;
+		best_init(bp);
+		best_init(bm);
+#pragma unroll 1
+		for (int rd = 0; rd < rounds; rd++) {
+			const int m0 = (rd * FG_T + tid) * FG_TILE;
+			float2 c[FG_TILE], d[FG_TILE], win[FG_TILE], alt[FG_TILE];
+			const float4 *w4 = reinterpret_cast<const float4 *>(w);
+			int g = m0 >> 3;                                   // m0 < ng * 8 always (zero tail)
+			const bool act = g < ng - (lenp >> 3);             // a whole tap span fits behind this group
+			if (!act)
+				g = 0;
+			auto load = [&](float2 (&dst)[FG_TILE], int gg) {
+				const int sw = (gg >> 1) & 3;
+#pragma unroll
+				for (int q = 0; q < 4; q++) {
+					const float4 v = w4[gg * 4 + (q ^ sw)];
+					dst[2 * q] = make_float2(v.x, v.y);
+					dst[2 * q + 1] = make_float2(v.z, v.w);
+				}
+			};
+			load(win, g);
+#pragma unroll
+			for (int t = 0; t < FG_TILE; t++)
+				c[t] = d[t] = make_float2(0.0f, 0.0f);
+			// one group of 8 taps: `cur` holds samples m0 + 8k .. + 7, `nxt` the following 8; output t of tap u
+			// reads sample u + t of the 16.  Two groups per iteration with the roles of the two register windows
+			// swapped, so no register is ever copied.
+			auto group = [&](int k, const float2 (&cur)[FG_TILE], float2 (&nxt)[FG_TILE]) {
+				load(nxt, g + k + 1);
+				const float4 c0 = reinterpret_cast<const float4 *>(refc)[2 * k], c1 = reinterpret_cast<const float4 *>(refc)[2 * k + 1];
+				const float rc[FG_TILE] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+				for (int u = 0; u < FG_TILE; u++)
+#pragma unroll
+					for (int t = 0; t < FG_TILE; t++)
+						fma2(c[t], rc[u], u + t < FG_TILE ? cur[u + t] : nxt[u + t - FG_TILE]);
+				if (PAIR) {
+					const float4 s0 = reinterpret_cast<const float4 *>(refs)[2 * k], s1 = reinterpret_cast<const float4 *>(refs)[2 * k + 1];
+					const float rs[FG_TILE] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+					for (int u = 0; u < FG_TILE; u++)
+#pragma unroll
+						for (int t = 0; t < FG_TILE; t++)
+							fma2(d[t], rs[u], u + t < FG_TILE ? cur[u + t] : nxt[u + t - FG_TILE]);
+				}
+			};
+			const int G = lenp >> 3;
+			int k = 0;
+#pragma unroll 1
+			for (; k + 1 < G; k += 2) {
+				group(k, win, alt);
+				group(k + 1, alt, win);
+			}
+			if (k < G)
+				group(k, win, alt);
+			// energies of the two shifts of this pass, window sums with the left neighbour's last four
+			float xp[12], xm[12];
+#pragma unroll
+			for (int t = 0; t < FG_TILE; t++) {
+				const bool ok = act && m0 + t < nc;
+				if (PAIR) {
+					const float pr = c[t].x - d[t].y, pi = c[t].y + d[t].x;      // A + jB
+					const float mr = c[t].x + d[t].y, mi = c[t].y - d[t].x;      // A - jB
+					xp[4 + t] = ok ? pr * pr + pi * pi : 0.0f;
+					xm[4 + t] = ok ? mr * mr + mi * mi : 0.0f;
+				} else {
+					xp[4 + t] = ok ? c[t].x * c[t].x + c[t].y * c[t].y : 0.0f;
+					xm[4 + t] = 0.0f;
+				}
+			}
+			float *tp = tail, *tm = tail + (FG_T + 1) * 4;
+			*reinterpret_cast<float4 *>(&tp[(tid + 1) * 4]) = make_float4(xp[8], xp[9], xp[10], xp[11]);
+			if (PAIR)
+				*reinterpret_cast<float4 *>(&tm[(tid + 1) * 4]) = make_float4(xm[8], xm[9], xm[10], xm[11]);
+			Bar::sync();
+			{
+				const float4 v = *reinterpret_cast<const float4 *>(&tp[tid * 4]);
+				xp[0] = v.x; xp[1] = v.y; xp[2] = v.z; xp[3] = v.w;
+				if (PAIR) {
+					const float4 u = *reinterpret_cast<const float4 *>(&tm[tid * 4]);
+					xm[0] = u.x; xm[1] = u.y; xm[2] = u.z; xm[3] = u.w;
+				}
+			}
+			Bar::sync();
+			if (tid == FG_T - 1) {         // carry into the next round
+				*reinterpret_cast<float4 *>(&tp[0]) = make_float4(xp[8], xp[9], xp[10], xp[11]);
+				if (PAIR)
+					*reinterpret_cast<float4 *>(&tm[0]) = make_float4(xm[8], xm[9], xm[10], xm[11]);
+			}
+			best_scan(bp, xp, m0, nc);
+			if (PAIR)
+				best_scan(bm, xm, m0, nc);
+		}
+		// block argmax (largest value, lowest index on ties) per shift; the winner writes TOA and peak
+#pragma unroll
+		for (int sgn = 0; sgn < (PAIR ? 2 : 1); sgn++) {
+			const Best &bb = sgn ? bm : bp;
+			const bool single = gp.n_pass == 1 && gp.f[0] < 0.0f;
+			int slot = sgn ? gp.out_m[pass] : gp.out_p[pass];
+			if (single)                    // single-shift use: the sign of the window's own shift picks the branch
+				slot = (fbase < 0.0f) == (sgn == 1) ? 0 : -1;
+			float bv = bb.val;
+			int bi = bb.idx;
+#pragma unroll
+			for (int o = 16; o; o >>= 1) {
+				const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+				const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+				if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+			}
+			Bar::sync();
+			int *redi = (int *)(red + 32);
+			if (lane == 0) { red[warp] = bv; redi[warp] = bi; }
+			Bar::sync();
+			bv = lane < FG_T / 32 ? red[lane] : 0.0f;
+			bi = lane < FG_T / 32 ? redi[lane] : 0x7fffffff;
+#pragma unroll
+			for (int o = 16; o; o >>= 1) {
+				const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+				const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+				if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+			}
+			if (slot < 0)
+				continue;
+			const size_t o = (size_t)slot * n_total + b;
+			if (bv <= 0.0f) {              // nothing correlated: position 0 (max_idx = 0, empty centroid)
+				if (tid == 0) {
+					toa_out[o] = 0;
+					if (peak_out) peak_out[o] = bv;
+				}
+			} else if (bb.idx == bi && bb.val == bv) {         // exactly one thread owns the winning window
+				const int max_idx = bi - 4 < 0 ? 0 : bi - 4;
+				float mw = 0.0f, sw = 0.0f;
+#pragma unroll
+				for (int k2 = 0; k2 < 5; k2++) {
+					sw += bb.e[k2];
+					mw += bb.e[k2] * (float)(max_idx + k2);
+				}
+				const float pos = sw > 0.0f ? mw / sw : (float)max_idx;
+				toa_out[o] = (int)round((double)(pos * 4.0f));
+				if (peak_out) peak_out[o] = bv;
+			}
+		}
+	}
+}
+
 // PAIR = false: every pass has f = 0 (real taps only).  One CTA per window.
 template <bool PAIR>
 __global__ void __launch_bounds__(FG_T, PAIR ? 2 : 3)
@@ -193,169 +375,7 @@ fcch_grid_kernel(const FcchArgs a, const GridPlan gp, int32_t *toa_out, float *p
 	}
 
 	const float fbase = a.freq_shift ? a.freq_shift[b] : a.freq_shift0;     // single-shift use: the pass is |fbase|
-	const int rounds = (nc + FG_T * FG_TILE - 1) / (FG_T * FG_TILE);
-#pragma unroll 1
-	for (int pass = 0; pass < gp.n_pass; pass++) {
-		const float f = gp.n_pass == 1 && gp.f[0] < 0.0f ? fabsf(fbase) : gp.f[pass];
-		__syncthreads();                   // normalised samples ready / previous pass done with the taps
-		{	// dual-chirp reference at 1 sample/symbol (fcch.c:167-193) times e^{j f n}
-			const float phase_base = a.freq * 2.0f * PI_F / (float)len, halfpos = (float)len / 2.0f;
-			for (int i = tid; i < FG_MAXLEN; i += FG_T) {
-				const float pos = (float)i - halfpos;
-				const float r = i < len ? sqrtf(2.0f) * cosf(phase_base * (pos * pos)) : 0.0f;
-				float sn, cs;
-				sincosf(f * (float)i, &sn, &cs);
-				refc[i] = r * cs;
-				refs[i] = r * sn;
-			}
-			if (tid < 8)                   // carry slots: nothing in front of output 0
-				tail[(tid >> 2) * (FG_T + 1) * 4 + (tid & 3)] = 0.0f;
-		}
-		__syncthreads();
-		Best bp, bm;
-		best_init(bp);
-		best_init(bm);
-#pragma unroll 1
-		for (int rd = 0; rd < rounds; rd++) {
-			const int m0 = (rd * FG_T + tid) * FG_TILE;
-			float2 c[FG_TILE], d[FG_TILE], win[FG_TILE], alt[FG_TILE];
-			const float4 *w4 = reinterpret_cast<const float4 *>(w);
-			int g = m0 >> 3;                                   // m0 < ng * 8 always (zero tail)
-			const bool act = g < ng - (lenp >> 3);             // a whole tap span fits behind this group
-			if (!act)
-				g = 0;
-			auto load = [&](float2 (&dst)[FG_TILE], int gg) {
-				const int sw = (gg >> 1) & 3;
-#pragma unroll
-				for (int q = 0; q < 4; q++) {
-					const float4 v = w4[gg * 4 + (q ^ sw)];
-					dst[2 * q] = make_float2(v.x, v.y);
-					dst[2 * q + 1] = make_float2(v.z, v.w);
-				}
-			};
-			load(win, g);
-#pragma unroll
-			for (int t = 0; t < FG_TILE; t++)
-				c[t] = d[t] = make_float2(0.0f, 0.0f);
-			// one group of 8 taps: `cur` holds samples m0 + 8k .. + 7, `nxt` the following 8; output t of tap u
-			// reads sample u + t of the 16.  Two groups per iteration with the roles of the two register windows
-			// swapped, so no register is ever copied.
-			auto group = [&](int k, const float2 (&cur)[FG_TILE], float2 (&nxt)[FG_TILE]) {
-				load(nxt, g + k + 1);
-				const float4 c0 = reinterpret_cast<const float4 *>(refc)[2 * k], c1 = reinterpret_cast<const float4 *>(refc)[2 * k + 1];
-				const float rc[FG_TILE] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-#pragma unroll
-				for (int u = 0; u < FG_TILE; u++)
-#pragma unroll
-					for (int t = 0; t < FG_TILE; t++)
-						fma2(c[t], rc[u], u + t < FG_TILE ? cur[u + t] : nxt[u + t - FG_TILE]);
-				if (PAIR) {
-					const float4 s0 = reinterpret_cast<const float4 *>(refs)[2 * k], s1 = reinterpret_cast<const float4 *>(refs)[2 * k + 1];
-					const float rs[FG_TILE] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-#pragma unroll
-					for (int u = 0; u < FG_TILE; u++)
-#pragma unroll
-						for (int t = 0; t < FG_TILE; t++)
-							fma2(d[t], rs[u], u + t < FG_TILE ? cur[u + t] : nxt[u + t - FG_TILE]);
-				}
-			};
-			const int G = lenp >> 3;
-			int k = 0;
-#pragma unroll 1
-			for (; k + 1 < G; k += 2) {
-				group(k, win, alt);
-				group(k + 1, alt, win);
-			}
-			if (k < G)
-				group(k, win, alt);
-			// energies of the two shifts of this pass, window sums with the left neighbour's last four
-			float xp[12], xm[12];
-#pragma unroll
-			for (int t = 0; t < FG_TILE; t++) {
-				const bool ok = act && m0 + t < nc;
-				if (PAIR) {
-					const float pr = c[t].x - d[t].y, pi = c[t].y + d[t].x;      // A + jB
-					const float mr = c[t].x + d[t].y, mi = c[t].y - d[t].x;      // A - jB
-					xp[4 + t] = ok ? pr * pr + pi * pi : 0.0f;
-					xm[4 + t] = ok ? mr * mr + mi * mi : 0.0f;
-				} else {
-					xp[4 + t] = ok ? c[t].x * c[t].x + c[t].y * c[t].y : 0.0f;
-					xm[4 + t] = 0.0f;
-				}
-			}
-			float *tp = tail, *tm = tail + (FG_T + 1) * 4;
-			*reinterpret_cast<float4 *>(&tp[(tid + 1) * 4]) = make_float4(xp[8], xp[9], xp[10], xp[11]);
-			if (PAIR)
-				*reinterpret_cast<float4 *>(&tm[(tid + 1) * 4]) = make_float4(xm[8], xm[9], xm[10], xm[11]);
-			__syncthreads();
-			{
-				const float4 v = *reinterpret_cast<const float4 *>(&tp[tid * 4]);
-				xp[0] = v.x; xp[1] = v.y; xp[2] = v.z; xp[3] = v.w;
-				if (PAIR) {
-					const float4 u = *reinterpret_cast<const float4 *>(&tm[tid * 4]);
-					xm[0] = u.x; xm[1] = u.y; xm[2] = u.z; xm[3] = u.w;
-				}
-			}
-			__syncthreads();
-			if (tid == FG_T - 1) {         // carry into the next round
-				*reinterpret_cast<float4 *>(&tp[0]) = make_float4(xp[8], xp[9], xp[10], xp[11]);
-				if (PAIR)
-					*reinterpret_cast<float4 *>(&tm[0]) = make_float4(xm[8], xm[9], xm[10], xm[11]);
-			}
-			best_scan(bp, xp, m0, nc);
-			if (PAIR)
-				best_scan(bm, xm, m0, nc);
-		}
-		// block argmax (largest value, lowest index on ties) per shift; the winner writes TOA and peak
-#pragma unroll
-		for (int sgn = 0; sgn < (PAIR ? 2 : 1); sgn++) {
-			const Best &bb = sgn ? bm : bp;
-			const bool single = gp.n_pass == 1 && gp.f[0] < 0.0f;
-			int slot = sgn ? gp.out_m[pass] : gp.out_p[pass];
-			if (single)                    // single-shift use: the sign of the window's own shift picks the branch
-				slot = (fbase < 0.0f) == (sgn == 1) ? 0 : -1;
-			float bv = bb.val;
-			int bi = bb.idx;
-#pragma unroll
-			for (int o = 16; o; o >>= 1) {
-				const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-				const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-				if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-			}
-			__syncthreads();
-			int *redi = (int *)(red + 32);
-			if (lane == 0) { red[warp] = bv; redi[warp] = bi; }
-			__syncthreads();
-			bv = lane < FG_T / 32 ? red[lane] : 0.0f;
-			bi = lane < FG_T / 32 ? redi[lane] : 0x7fffffff;
-#pragma unroll
-			for (int o = 16; o; o >>= 1) {
-				const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-				const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-				if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-			}
-			if (slot < 0)
-				continue;
-			const size_t o = (size_t)slot * gridDim.x + b;
-			if (bv <= 0.0f) {              // nothing correlated: position 0 (max_idx = 0, empty centroid)
-				if (tid == 0) {
-					toa_out[o] = 0;
-					if (peak_out) peak_out[o] = bv;
-				}
-			} else if (bb.idx == bi && bb.val == bv) {         // exactly one thread owns the winning window
-				const int max_idx = bi - 4 < 0 ? 0 : bi - 4;
-				float mw = 0.0f, sw = 0.0f;
-#pragma unroll
-				for (int k2 = 0; k2 < 5; k2++) {
-					sw += bb.e[k2];
-					mw += bb.e[k2] * (float)(max_idx + k2);
-				}
-				const float pos = sw > 0.0f ? mw / sw : (float)max_idx;
-				toa_out[o] = (int)round((double)(pos * 4.0f));
-				if (peak_out) peak_out[o] = bv;
-			}
-		}
-	}
+	search_window<PAIR, BarCta>(a, gp, toa_out, peak_out, w, refc, refs, red, tail, tid, b, (int)gridDim.x, l, len, ng, fbase);
 }
 
 }  // namespace

@@ -358,6 +358,8 @@ extern "C" int gmr1b200_rx_call_batch(const float *iq, int64_t iq_len, const int
 		return set_err(-EINVAL, "rx_call_batch: bad argument");
 	if (n == 0)
 		return 0;
+	if (!recordings_in_range(rec_ofs, rec_len, n, iq_len))
+		return set_err(-EINVAL, "rx_call_batch: a recording lies outside iq_len");
 	WalkStream ws(stream);
 	cudaStream_t cs = ws.get();
 	const BurstTab *d_all = nullptr;

@@ -30,6 +30,8 @@ static int rx_bcch_walk(const float *iq, int64_t iq_len, const int64_t *rec_ofs,
 		return set_err(-EINVAL, "rx_bcch_batch: bad argument");
 	if (n == 0)
 		return 0;
+	if (!recordings_in_range(rec_ofs, rec_len, n, iq_len))
+		return set_err(-EINVAL, "rx_bcch_batch: a recording lies outside iq_len");
 	WalkStream ws(stream);
 	cudaStream_t cs = ws.get();
 	const BurstTab *d_all = nullptr;
@@ -70,8 +72,6 @@ static int rx_bcch_walk(const float *iq, int64_t iq_len, const int64_t *rec_ofs,
 	if (s.failed())
 		return s.finish(cudaSuccess, "rx_bcch_batch: staging");
 
-	// every recording must lie inside iq (checked on the host copy of the descriptors when they are host memory
-	// is not possible in general: the kernels bound every window by rec_len, the caller vouches for rec_ofs)
 	const int tb = 128, grid = (n + tb - 1) / tb;
 	rx_init_kernel<<<grid, tb, 0, cs>>>(st, d_align0, d_ferr0, out.n_frames, out.tch3, out.tch3_energy, n);
 	cudaMemsetAsync(out.kind, 0, NF * sizeof(int32_t), cs);
@@ -358,6 +358,8 @@ static int rx_bcch_walk_paced(const float *iq, int64_t iq_len, const int64_t *re
 		return set_err(-EINVAL, "rx_bcch_batch: bad argument");
 	if (n == 0)
 		return 0;
+	if (!recordings_in_range(rec_ofs, rec_len, n, iq_len))
+		return set_err(-EINVAL, "rx_bcch_batch: a recording lies outside iq_len");
 	cudaStream_t cs = (cudaStream_t)stream;
 	const BurstTab *d_all = nullptr;
 	cudaError_t e = device_bursts(&d_all);

@@ -85,10 +85,11 @@ def test_batched_entry_points_reject_malformed_batches(gpu_lib):
     rejected("gmr1b200_fcch_multi_batch", 3, iq, n * wl, *multi, SPS, n, 4, i32(n), i32(n, 4), None, None, None)                      # FCCH type
     rejected("gmr1b200_fcch_multi_batch", 0, iq, n * wl, *multi, SPS, n, 4, None, i32(n, 4), None, None, None)                        # no count output
     assert L.kernel_launches() == before                                             # nothing was launched
-    # recordings shorter than the 650 ms window are flagged one by one, without a launch (gmr1_rx.c:661-665)
+    # recordings shorter than the 650 ms window are flagged one by one (gmr1_rx.c:661-665)
     cnt = np.full(n, 5, np.int32)
     assert L.call("gmr1b200_fcch_multi_batch", 0, iq, n * wl, *multi, SPS, n, 4, cnt, i32(n, 4), None, None, None) == 0
-    assert (cnt == -errno.EINVAL).all() and L.kernel_launches() == before
+    assert (cnt == -errno.EINVAL).all()              # decided on the device: the rows are rejected by the prep kernel
+    before = L.kernel_launches()
     assert L.call("gmr1b200_fcch_multi_batch", 0, iq, n * wl, *multi, SPS, 0, 4, cnt, i32(n, 4), None, None, None) == 0
     # empty batches are fine and do nothing
     assert L.call("gmr1b200_bcch_decode_batch", l2, eb, None, None, 0, None) == 0
