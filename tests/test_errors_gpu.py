@@ -95,3 +95,48 @@ def test_batched_entry_points_reject_malformed_batches(gpu_lib):
     assert L.call("gmr1b200_bcch_decode_batch", l2, eb, None, None, 0, None) == 0
     assert L.call("gmr1b200_pi4cxpsk_demod_batch", 0, iq, n * wl, None, wl, wl, SPS, None, 0.0, eb, 424, None, None, None, None, 0, None) == 0
     assert L.kernel_launches() == before
+
+
+def test_caller_descriptors_must_be_consistent(gpu_lib):
+    """gmr1b200_pi4cxpsk_demod_desc_batch: a descriptor whose ebits disagrees with its data symbols, whose data chunks
+    overlap or whose sync symbols are not phase indices is rejected before anything is launched; host-readable window
+    offsets are range-checked (the reference has no such path: its descriptors are compiled in, sdr/nb.c)."""
+    import ctypes
+    L = gpu_lib
+
+    class Desc(ctypes.Structure):            # include/gmr1_b200.h: struct gmr1b200_burst_desc
+        _fields_ = [("rotation", ctypes.c_float), ("nbits", ctypes.c_int32), ("len", ctypes.c_int32),
+                    ("ebits", ctypes.c_int32), ("n_sync", ctypes.c_int32), ("n_chunk", ctypes.c_int32 * 4),
+                    ("s_pos", ctypes.c_int16 * 6 * 4), ("s_len", ctypes.c_int16 * 6 * 4),
+                    ("s_sym", ctypes.c_uint8 * 32 * 6 * 4), ("n_data", ctypes.c_int32),
+                    ("d_pos", ctypes.c_int16 * 6), ("d_len", ctypes.c_int16 * 6)]
+
+    L.c.gmr1b200_burst_desc_get.argtypes = [ctypes.c_int, ctypes.c_void_p]
+    good = Desc()
+    assert L.c.gmr1b200_burst_desc_get(0, ctypes.addressof(good)) == 0 and good.ebits == 424
+    n, wl = 2, 234 * SPS + 80
+    iq = np.zeros((n, wl, 2), np.float32)
+    eb = np.zeros((n, 424), np.int8)
+
+    def run(d, ofs=None):
+        return L.c.gmr1b200_pi4cxpsk_demod_desc_batch(ctypes.addressof(d), iq.ctypes.data, n * wl,
+                                                      None if ofs is None else ofs.ctypes.data, wl, wl, SPS, None, 0.0,
+                                                      eb.ctypes.data, 424, None, None, None, None, n, None)
+
+    def variant(f):
+        d = Desc.from_buffer_copy(bytes(good))
+        f(d)
+        return d
+
+    assert run(good) == 0
+    before = L.kernel_launches()
+    bad = [variant(lambda d: setattr(d, "ebits", 400)),                     # fewer soft bits than data symbols
+           variant(lambda d: d.d_len.__setitem__(0, d.d_len[0] - 1)),       # data symbols no longer add up to ebits
+           variant(lambda d: d.s_sym[0][0].__setitem__(0, 7)),              # not a phase index
+           variant(lambda d: d.d_pos.__setitem__(1, d.d_pos[0]))]           # second data chunk on top of the first
+    for d in bad:
+        assert run(d) == -errno.EINVAL and b"descriptor" in L.c.gmr1b200_last_error()
+    assert run(good, np.array([0, wl + 1], np.int64)) == -errno.EINVAL      # second window runs past iq_len
+    assert run(good, np.array([-1, wl], np.int64)) == -errno.EINVAL
+    assert L.kernel_launches() == before
+    assert run(good, np.array([wl, 0], np.int64)) == 0

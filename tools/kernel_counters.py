@@ -34,13 +34,14 @@ for r in rows[1:]:
     per.setdefault((d["ID"], d["Kernel Name"]), {})[d["Metric Name"]] = float(d["Metric Value"].replace(",", ""))
 import osmo_gmr_b200
 build = osmo_gmr_b200.Lib().version().split("build ")[-1]
-units = {"demod_fast_kernel<0, 81, 0>": ("demod_bcch", 131072), "demod_fast_kernel<2, 41, 0>": ("demod_dc6", 131072),
-         "decode_tpc_kernel<0>": ("decode_bcch", 131072), "decode_tpc_kernel<1>": ("decode_ccch", 131072),
-         "fcch_rough_kernel": ("fcch_rough", 1024), "fcch_fine_kernel": ("fcch_fine", 1024)}
+units = {"demod_fast_kernel<0,81,0>": ("demod_bcch", 131072), "demod_fast_kernel<2,41,0>": ("demod_dc6", 131072),
+         "decode_tpc_kernel<0,": ("decode_bcch", 131072), "decode_tpc_kernel<1,": ("decode_ccch", 131072),
+         "fcch_grid_kernel<0>": ("fcch_rough", 1024), "fcch_rough_kernel": ("fcch_rough", 1024),
+         "fcch_fine_kernel": ("fcch_fine", 1024)}
 out = {}
 for (kid, name), m in per.items():
     for pat, (key, n) in units.items():
-        if pat.replace(" ", "") in name.replace(" ", "").replace("(int)", "").replace("(bool)", "").replace("gmr1::", ""):
+        if pat in name.replace(" ", "").replace("(int)", "").replace("(bool)", "").replace("gmr1::", ""):
             out[key] = {"kernel": name, "units": n, "warp_inst": m["smsp__inst_executed.sum"],
                         "warp_inst_per_unit": m["smsp__inst_executed.sum"] / n,
                         "dram_bytes": m["dram__bytes_read.sum"] + m["dram__bytes_write.sum"],
