@@ -462,6 +462,14 @@ int gmr1b200_synth_bursts(int burst_type, const gmr1b200_ubit_t *ebits, int ebit
                           const float *amp, float amp0, uint64_t seed,
                           float *iq, int64_t iq_len, const int64_t *win_ofs, int64_t win_stride,
                           int n, void *stream);
+/* the same with the TRANSMIT pulse only (RRC 0.35, unit energy per symbol) and no noise when esn0_db >= 100: the
+ * waveform in front of the receiver's matched filter, i.e. what the wideband channeliser below has to be fed */
+int gmr1b200_synth_bursts_tx(int burst_type, const gmr1b200_ubit_t *ebits, int ebits_stride, const int32_t *sync_id,
+                             int sps, int win_len, const float *toa, float toa0, const float *cfo, float cfo0,
+                             const float *phase, float phase0, const float *esn0_db, float esn0_db0,
+                             const float *amp, float amp0, uint64_t seed,
+                             float *iq, int64_t iq_len, const int64_t *win_ofs, int64_t win_stride,
+                             int n, void *stream);
 
 /* ---- several GPUs of one box from one process: the device pool -------------------------------------
  * The reference handles its channels one after the other in one thread (process loop over chan_desc,
@@ -490,6 +498,48 @@ int gmr1b200_pool_rx_xcch(struct gmr1b200_pool *pool, int chan, const float *hos
  * host_iq [n_arfcn][win_len]; align / freq_error [n_arfcn], rough [n_arfcn] or NULL. */
 int gmr1b200_pool_fcch_acquire(struct gmr1b200_pool *pool, int fcch_type, const float *host_iq, int n_arfcn,
                                int win_len, int sps, int32_t *rough, int32_t *align, float *freq_error);
+
+/* ---- wideband channeliser -----------------------------------------------------------------------------
+ * Replaces the "PFB Channelizer mode" of utils/gmr1_rx_sdr.py (:391-604): one wideband recording in, one stream of
+ * sps x 23.4 kS/s per ARFCN out - the per-ARFCN cfile contents gmr1_rx reads (gmr1_rx.c:924-988), here left in device
+ * memory (or copied to the host) in exactly the layout the rx_* / *_batch entry points take as `iq` + offsets.
+ * The reference wires GNU Radio blocks; the plan restates what PFBBase / PFBOutputParameters compute:
+ *   bank       pfb.channelizer_ccf(n_chans, firdes.low_pass(1, samp_rate, 15 625, 7 812.5), oversample 2)   (:433-470)
+ *   per ARFCN  pfb.arb_resampler_ccf(sps 23 400 / 62 500, firdes.root_raised_cosine(32, 32 x 62 500, 23 400, 0.35,
+ *              11 symbols), flt_size 32)                                                               (:520-529, :591-596)
+ * The recording's rate must sit on the carrier grid: samp_rate = n_chans x 31.25 kHz, n_chans even (the script's
+ * pre-rotator / pre-resampler, :398-401 / :455-462, bring a capture there and are not part of this entry).
+ * Bank channel k is centred k x 31.25 kHz above the recording's centre, k >= n_chans / 2 meaning k - n_chans
+ * (PFBBase.freq2index, :489-496).  GNU Radio is not in the reference tree: outputs are checked against the CPU
+ * restatement in oracle/chan_port.py (float tolerance) and by decoding them with the reference's C receive path. */
+struct gmr1b200_chan_info {
+	int32_t n_chans, sps;
+	int32_t n_taps, taps_per_branch;      /* bank prototype filter */
+	int32_t n_taps_resamp, fft_stages;
+	double  samp_rate, mid_rate, resamp;  /* wideband rate, bank output rate per channel (62.5 kS/s), 1.4976 at sps 4 */
+	double  delay_out;                    /* group delay of bank + RRC, in output samples */
+};
+int gmr1b200_chan_create(int n_chans, int sps, void **plan);
+void gmr1b200_chan_destroy(void *plan);
+int gmr1b200_chan_info(void *plan, struct gmr1b200_chan_info *info);
+/* the two filter designs (host memory): taps [>= n_taps], taps_resamp [>= n_taps_resamp]; either may be NULL */
+int gmr1b200_chan_taps(void *plan, float *taps, int max_taps, float *taps_resamp, int max_resamp);
+/* output samples per channel for a recording of n_wide samples */
+int64_t gmr1b200_chan_out_len(void *plan, int64_t n_wide);
+/* wide: n_wide complex samples from the start of the recording (zeros are assumed in front of it), iq_format 0 =
+ * complex float32, 1 = interleaved int16 I/Q scaled by 1 / 32768 (what SDR front ends deliver; half the bytes);
+ * chan_idx [n_wanted] bank channels wanted, NULL = channels 0 .. n_wanted-1;
+ * out [n_wanted][out_stride] complex float (interleaved), out_stride >= gmr1b200_chan_out_len(n_wide) samples.
+ * Host or device pointers. */
+int gmr1b200_channelize(void *plan, const void *wide, int iq_format, int64_t n_wide, const int32_t *chan_idx, int n_wanted,
+                        float *out, int64_t out_stride, void *stream);
+/* workload construction (tests, bench): the inverse direction.  streams [n_streams][stream_stride] complex float at
+ * sps x 23.4 kS/s (e.g. from gmr1b200_synth_bursts_tx) are interpolated to the wideband rate, mixed to their
+ * channels and summed; white noise for a per-channel Es/N0 of esn0_db (unit-power streams; >= 100: none); the sum is
+ * scaled by gain and written as iq_format. */
+int gmr1b200_synth_wideband(void *plan, const float *streams, int64_t stream_stride, int64_t stream_len,
+                            const int32_t *chan_idx, int n_streams, float esn0_db, float gain, uint64_t seed,
+                            void *wide, int iq_format, int64_t n_wide, void *stream);
 
 #ifdef __cplusplus
 }

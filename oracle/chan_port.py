@@ -116,8 +116,10 @@ class Plan:
         self.taps_resamp = firdes_root_raised_cosine(32.0, 32.0 * self.mid_rate, SYM_RATE, 0.35,
                                                      int(11.0 * 32 * self.mid_rate / SYM_RATE))
         # group delay of the chain in output samples (gmr1_rx_sdr.py min_delay(), :546-549, is the same idea)
+        # (the resampler starts its walk at phase (ntaps / 2) % 32, i.e. that fraction of a bank step EARLY)
         self.delay_out = (((len(self.taps) - 1) / 2.0) / self.samp_rate
-                          + ((len(self.taps_resamp) - 1) / 2.0) / (FLT_SIZE * self.mid_rate)) * SYM_RATE * sps
+                          + ((len(self.taps_resamp) - 1) / 2.0 - (len(self.taps_resamp) // 2) % FLT_SIZE)
+                          / (FLT_SIZE * self.mid_rate)) * SYM_RATE * sps
 
 
 # ---- pfb.channelizer_ccf(n_chans, taps, oversample_rate = 2) ------------------------------------------------------------

@@ -1,0 +1,239 @@
+// api_chan.cu - C ABI of the wideband channeliser (include/gmr1_b200.h, "wideband channeliser")
+#include "../../include/gmr1_b200.h"
+#include "api_common.h"
+#include "chan.h"
+
+#include <math.h>
+#include <mutex>
+#include <new>
+
+using namespace gmr1;
+
+namespace {
+
+struct Plan {
+	ChanPlan p;
+	std::mutex mu;                         // the phase walk and the device copies grow under it
+};
+
+// device copies of the plan's tables on the current device; the phase walk covers n_out outputs
+cudaError_t plan_device(Plan &pl, size_t n_out, ChanPlan::Dev **out)
+{
+	int dev = 0;
+	cudaError_t e = cudaGetDevice(&dev);
+	if (e != cudaSuccess)
+		return e;
+	if (dev < 0 || dev >= 64)
+		return cudaErrorInvalidDevice;
+	ChanPlan &p = pl.p;
+	ChanPlan::Dev &d = p.dev[dev];
+	auto up = [&](auto **dst, const auto &v) -> cudaError_t {
+		if (*dst)
+			return cudaSuccess;
+		cudaError_t e2 = cudaMalloc((void **)dst, v.size() * sizeof(v[0]));
+		if (e2 != cudaSuccess)
+			return e2;
+		return cudaMemcpy(*dst, v.data(), v.size() * sizeof(v[0]), cudaMemcpyHostToDevice);
+	};
+	if (!d.taps) {
+		std::vector<float> padded((size_t)p.taps_per_branch * p.n_chans, 0.0f);
+		std::copy(p.taps.begin(), p.taps.end(), padded.begin());
+		if ((e = up(&d.taps, padded)) != cudaSuccess)
+			return e;
+	}
+	if ((e = up(&d.filt, p.filt)) != cudaSuccess || (e = up(&d.dfilt, p.dfilt)) != cudaSuccess ||
+	    (e = up(&d.twiddle, p.twiddle)) != cudaSuccess)
+		return e;
+	if (d.sched_n < n_out) {               // (re)upload the walk, with headroom so that a stream of equal calls uploads once
+		const size_t n = p.sched_i.size();
+		cudaFree(d.sched_i);
+		cudaFree(d.sched_j);
+		cudaFree(d.sched_acc);
+		d.sched_i = nullptr; d.sched_j = nullptr; d.sched_acc = nullptr; d.sched_n = 0;
+		if ((e = up(&d.sched_i, p.sched_i)) != cudaSuccess || (e = up(&d.sched_j, p.sched_j)) != cudaSuccess ||
+		    (e = up(&d.sched_acc, p.sched_acc)) != cudaSuccess)
+			return e;
+		d.sched_n = n;
+	}
+	*out = &d;
+	return cudaSuccess;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gmr1b200_chan_create(int n_chans, int sps, void **plan)
+{
+	if (!plan)
+		return set_err(-EINVAL, "chan_create: plan NULL");
+	Plan *pl = new (std::nothrow) Plan;
+	if (!pl)
+		return set_err(-ENOMEM, "chan_create: out of memory");
+	if (chan_plan_init(pl->p, n_chans, sps)) {
+		delete pl;
+		return set_err(-EINVAL, "chan_create: n_chans must be even, 2..4096, with prime factors <= 31; sps 1..16");
+	}
+	*plan = pl;
+	return 0;
+}
+
+void gmr1b200_chan_destroy(void *plan)
+{
+	Plan *pl = (Plan *)plan;
+	if (!pl)
+		return;
+	int cur = 0;
+	cudaGetDevice(&cur);
+	for (int dev = 0; dev < 64; dev++) {
+		ChanPlan::Dev &d = pl->p.dev[dev];
+		if (!d.taps && !d.filt && !d.sched_i)
+			continue;
+		cudaSetDevice(dev);
+		cudaFree(d.taps); cudaFree(d.filt); cudaFree(d.dfilt); cudaFree(d.twiddle);
+		cudaFree(d.sched_i); cudaFree(d.sched_j); cudaFree(d.sched_acc);
+	}
+	cudaSetDevice(cur);
+	delete pl;
+}
+
+int gmr1b200_chan_info(void *plan, struct gmr1b200_chan_info *info)
+{
+	Plan *pl = (Plan *)plan;
+	if (!pl || !info)
+		return set_err(-EINVAL, "chan_info: NULL argument");
+	const ChanPlan &p = pl->p;
+	info->n_chans = p.n_chans; info->sps = p.sps; info->n_taps = (int)p.taps.size(); info->taps_per_branch = p.taps_per_branch;
+	info->n_taps_resamp = (int)p.taps_resamp.size(); info->fft_stages = (int)p.radix.size();
+	info->samp_rate = p.samp_rate; info->mid_rate = p.mid_rate; info->resamp = p.resamp; info->delay_out = p.delay_out;
+	return 0;
+}
+
+int gmr1b200_chan_taps(void *plan, float *taps, int max_taps, float *taps_resamp, int max_resamp)
+{
+	Plan *pl = (Plan *)plan;
+	if (!pl)
+		return set_err(-EINVAL, "chan_taps: plan NULL");
+	const ChanPlan &p = pl->p;
+	if ((taps && max_taps < (int)p.taps.size()) || (taps_resamp && max_resamp < (int)p.taps_resamp.size()))
+		return set_err(-EINVAL, "chan_taps: buffer too small");
+	if (taps)
+		memcpy(taps, p.taps.data(), p.taps.size() * sizeof(float));
+	if (taps_resamp)
+		memcpy(taps_resamp, p.taps_resamp.data(), p.taps_resamp.size() * sizeof(float));
+	return 0;
+}
+
+int64_t gmr1b200_chan_out_len(void *plan, int64_t n_wide)
+{
+	Plan *pl = (Plan *)plan;
+	if (!pl || n_wide < 0)
+		return set_err(-EINVAL, "chan_out_len: bad argument");
+	std::lock_guard<std::mutex> lk(pl->mu);
+	return chan_plan_out_len(pl->p, n_wide);
+}
+
+int gmr1b200_channelize(void *plan, const void *wide, int iq_format, int64_t n_wide, const int32_t *chan_idx, int n_wanted,
+                        float *out, int64_t out_stride, void *stream)
+{
+	Plan *pl = (Plan *)plan;
+	if (!pl || !wide || !out || n_wide < 0 || n_wanted < 0 || iq_format < 0 || iq_format > 1)
+		return set_err(-EINVAL, "channelize: bad argument");
+	ChanPlan &p = pl->p;
+	if (n_wanted == 0 || n_wide == 0)
+		return 0;
+	if (chan_idx && host_pointer(chan_idx))
+		for (int i = 0; i < n_wanted; i++)
+			if (chan_idx[i] < 0 || chan_idx[i] >= p.n_chans)
+				return set_err(-EINVAL, "channelize: channel index outside the bank");
+	if (!chan_idx && n_wanted > p.n_chans)
+		return set_err(-EINVAL, "channelize: more streams than channels");
+	int64_t n_out, n_steps;
+	ChanPlan::Dev *d = nullptr;
+	int rows_max = 0;
+	{
+		std::lock_guard<std::mutex> lk(pl->mu);
+		n_out = chan_plan_out_len(p, n_wide);
+		n_steps = n_wide / (p.n_chans / 2);
+		if (n_out > out_stride)
+			return set_err(-EINVAL, "channelize: out_stride smaller than gmr1b200_chan_out_len(n_wide)");
+		if (n_out == 0)
+			return 0;
+		cudaError_t e = plan_device(*pl, (size_t)n_out, &d);
+		if (e != cudaSuccess)
+			return cuda_rc(e, "channelize: table upload");
+		const int to = resamp_tile_outputs();
+		for (int64_t n0 = 0; n0 < n_out; n0 += to) {
+			const int64_t n1 = (n0 + to < n_out ? n0 + to : n_out) - 1;
+			const int rows = p.sched_i[n1] - p.sched_i[n0] + p.tpf;
+			rows_max = rows > rows_max ? rows : rows_max;
+		}
+	}
+	Stage s(stream);
+	const void *d_wide = iq_format == 0 ? (const void *)s.in((const float *)wide, (size_t)n_wide * 2)
+	                                    : (const void *)s.in((const int16_t *)wide, (size_t)n_wide * 2);
+	const int32_t *d_idx = s.in(chan_idx, (size_t)n_wanted);
+	float2 *d_out = (float2 *)s.out(out, (size_t)n_wanted * (size_t)out_stride * 2);
+	float2 *mid = s.tmp<float2>((size_t)n_steps * p.n_chans);
+	if (s.failed())
+		return s.finish(cudaSuccess, "channelize: staging");
+	if ((void *)d_out != (void *)out && out_stride > n_out)      // staged host output: the row tails travel back too
+		cudaMemsetAsync(d_out, 0, (size_t)n_wanted * (size_t)out_stride * sizeof(float2), (cudaStream_t)stream);
+	PfbArgs pa = {};
+	pa.wide = d_wide; pa.n_wide = n_wide; pa.n_chans = p.n_chans; pa.taps_per_branch = p.taps_per_branch;
+	pa.taps = d->taps; pa.twiddle = d->twiddle; pa.n_stage = (int)p.radix.size();
+	for (int i = 0; i < pa.n_stage; i++)
+		pa.radix[i] = p.radix[i];
+	pa.mid = mid; pa.n_steps = n_steps;
+	cudaError_t e = launch_pfb(pa, iq_format, (cudaStream_t)stream);
+	if (e == cudaSuccess) {
+		g_launches.fetch_add(1);
+		ResampArgs ra = {};
+		ra.mid = mid; ra.n_steps = n_steps; ra.n_chans = p.n_chans; ra.chan_idx = d_idx; ra.n_wanted = n_wanted;
+		ra.sched_i = d->sched_i; ra.sched_j = d->sched_j; ra.sched_acc = d->sched_acc; ra.filt = d->filt; ra.dfilt = d->dfilt;
+		ra.tpf = p.tpf; ra.rows_max = rows_max; ra.out = d_out; ra.out_stride = out_stride; ra.n_out = n_out;
+		e = launch_resamp(ra, (cudaStream_t)stream);
+		if (e == cudaSuccess)
+			g_launches.fetch_add(1);
+	}
+	return s.finish(e, "channelize kernels");
+}
+
+int gmr1b200_synth_wideband(void *plan, const float *streams, int64_t stream_stride, int64_t stream_len,
+                            const int32_t *chan_idx, int n_streams, float esn0_db, float gain, uint64_t seed,
+                            void *wide, int iq_format, int64_t n_wide, void *stream)
+{
+	Plan *pl = (Plan *)plan;
+	if (!pl || !streams || !wide || n_streams < 1 || stream_len < 4 || stream_stride < stream_len || n_wide < 0 ||
+	    iq_format < 0 || iq_format > 1)
+		return set_err(-EINVAL, "synth_wideband: bad argument");
+	ChanPlan &p = pl->p;
+	ChanPlan::Dev *d = nullptr;
+	{
+		std::lock_guard<std::mutex> lk(pl->mu);
+		cudaError_t e = plan_device(*pl, 0, &d);
+		if (e != cudaSuccess)
+			return cuda_rc(e, "synth_wideband: table upload");
+	}
+	Stage s(stream);
+	WideSynthArgs a = {};
+	a.streams = (const float2 *)s.in(streams, (size_t)n_streams * (size_t)stream_stride * 2);
+	a.stream_stride = stream_stride; a.stream_len = stream_len;
+	a.chan_idx = s.in(chan_idx, (size_t)n_streams);
+	a.n_streams = n_streams; a.n_chans = p.n_chans;
+	a.num = 468 * (int64_t)p.sps;          // stream samples per wideband sample: (23 400 sps) / (31 250 N) = 468 sps / (625 N)
+	a.den = 625 * (int64_t)p.n_chans;
+	a.twiddle = d->twiddle;
+	a.sigma = esn0_db >= 100.0f ? 0.0f : sqrtf(exp10f(-esn0_db / 10.0f) * (float)(p.samp_rate / 23400.0) * 0.5f);
+	a.gain = gain; a.seed = seed;
+	a.wide = iq_format == 0 ? (void *)s.out((float *)wide, (size_t)n_wide * 2) : (void *)s.out((int16_t *)wide, (size_t)n_wide * 2);
+	a.n_wide = n_wide;
+	if (s.failed())
+		return s.finish(cudaSuccess, "synth_wideband: staging");
+	cudaError_t e = launch_wide_synth(a, iq_format, (cudaStream_t)stream);
+	if (e == cudaSuccess)
+		g_launches.fetch_add(1);
+	return s.finish(e, "synth_wideband kernel");
+}
+
+}  // extern "C"

@@ -184,6 +184,20 @@ int gmr1b200_synth_bursts(int burst_type, const uint8_t *ebits, int ebits_stride
 	return run_synth(burst_type, a, iq_len, stream);
 }
 
+int gmr1b200_synth_bursts_tx(int burst_type, const uint8_t *ebits, int ebits_stride, const int32_t *sync_id,
+                             int sps, int win_len, const float *toa, float toa0, const float *cfo, float cfo0,
+                             const float *phase, float phase0, const float *esn0_db, float esn0_db0,
+                             const float *amp, float amp0, uint64_t seed,
+                             float *iq, int64_t iq_len, const int64_t *win_ofs, int64_t win_stride, int n, void *stream)
+{
+	SynthArgs a = {};
+	a.ebits = ebits; a.ebits_stride = ebits_stride; a.sync_id = sync_id; a.n = n; a.sps = sps; a.win_len = win_len;
+	a.toa = toa; a.toa0 = toa0; a.cfo = cfo; a.cfo0 = cfo0; a.phase = phase; a.phase0 = phase0;
+	a.esn0_db = esn0_db; a.esn0_db0 = esn0_db0; a.amp = amp; a.amp0 = amp0; a.seed = seed;
+	a.iq = (float2 *)iq; a.ofs = win_ofs; a.stride = win_stride; a.tx_pulse = 1;
+	return run_synth(burst_type, a, iq_len, stream);
+}
+
 int gmr1b200_set_sync_accumulator_reset(int on)
 {
 	return gmr1::g_sync_reset.exchange(on ? 1 : 0);

@@ -1,0 +1,393 @@
+// chan_kernels.cu - wideband channeliser: one wideband recording -> one sps-oversampled stream per
+// ARFCN, the step in front of the receive path.  Replaces the "PFB Channelizer mode" of utils/gmr1_rx_sdr.py
+// (:391-604), which wires GNU Radio blocks: pfb.channelizer_ccf(n_chans, low-pass taps, oversample 2) (:465-470) and,
+// per ARFCN, pfb.arb_resampler_ccf(93.6 / 62.5, RRC 0.35 taps, 32 phases) (:591-596).
+//
+//   pfb_kernel      2x oversampled polyphase analysis bank.  Output step m, channel k:
+//                     y_k[m] = (-1)^(k m) * sum_p e^{+j 2 pi k p / N} * u_p[m],   u_p[m] = sum_q h[p + q N] x[m N/2 - p - q N]
+//                   One CTA makes T = 8 G steps: the branch sums u from a sliding register window over the samples
+//                   (each sample is loaded once per thread although 2 P (step, tap) pairs use it), then T reverse FFTs
+//                   of size N in shared memory (Stockham, mixed radix 4 / 2 / odd primes), written time-major [m][k].
+//                   HBM: reads the recording once (neighbouring CTAs share the P N-sample history through L2), writes
+//                   8 N bytes per step.
+//   resamp_kernel   32-phase arbitrary resampler with the RRC matched filter: out[n] = sum_t (f_j[t] + acc df_j[t]) x[i - t]
+//                   with (i, j, acc) from the phase walk, which is the same for all channels (table built once per
+//                   plan on the host).  One CTA: 64 channels x 64 outputs; input rows staged in shared memory
+//                   (coalesced 512-byte rows of the time-major bank output), two channels per lane, results transposed
+//                   through shared memory into channel-major streams - the layout the receive path reads.
+//   wide_synth_kernel  the inverse direction for tests and the benchmark: per-ARFCN streams -> one wideband recording
+//                   (cubic interpolation to the wideband rate, mixed to +k 31.25 kHz, summed, AWGN).  Workload
+//                   construction, not the hot path.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "chan.h"
+
+namespace gmr1 {
+
+namespace {
+
+constexpr int PFB_TM = 8;                  // steps per work item (register window)
+constexpr int PFB_THREADS = 256;
+
+template <int FMT> __device__ __forceinline__ float2 load_wide(const void *x, int64_t i, int64_t n)
+{
+	if (i < 0 || i >= n)
+		return make_float2(0.0f, 0.0f);
+	if (FMT == 0)
+		return __ldg(reinterpret_cast<const float2 *>(x) + i);
+	const short2 v = __ldg(reinterpret_cast<const short2 *>(x) + i);
+	return make_float2((float)v.x * (1.0f / 32768.0f), (float)v.y * (1.0f / 32768.0f));
+}
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b)
+{
+	return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(PFB_THREADS) pfb_kernel(const PfbArgs a)
+{
+	extern __shared__ __align__(16) float2 sm[];
+	const int N = a.n_chans, D = N >> 1, P = a.taps_per_branch, G = a.groups, T = G * PFB_TM;
+	const int tid = threadIdx.x;
+	float2 *buf0 = sm, *buf1 = sm + (size_t)T * N;
+	const int64_t m_cta = (int64_t)blockIdx.x * T;
+
+	// ---- branch sums u_p[m] for the CTA's T steps
+	for (int item = tid; item < N * G; item += PFB_THREADS) {
+		const int p = item % N, g = item / N;
+		const int64_t m0 = m_cta + g * PFB_TM;
+		float2 xw[PFB_TM], acc[PFB_TM];
+#pragma unroll
+		for (int i = 0; i < PFB_TM; i++) {
+			xw[i] = load_wide<FMT>(a.wide, (m0 + i) * D - p, a.n_wide);
+			acc[i] = make_float2(0.0f, 0.0f);
+		}
+#pragma unroll 1
+		for (int q = 0; q < P; q++) {
+			const float h = __ldg(&a.taps[p + q * N]);
+#pragma unroll
+			for (int i = 0; i < PFB_TM; i++) {
+				acc[i].x = fmaf(h, xw[i].x, acc[i].x);
+				acc[i].y = fmaf(h, xw[i].y, acc[i].y);
+			}
+			if (q + 1 < P) {               // window of step offsets i - 2 (q + 1): shift by two, two new samples
+#pragma unroll
+				for (int i = PFB_TM - 1; i >= 2; i--)
+					xw[i] = xw[i - 2];
+				xw[0] = load_wide<FMT>(a.wide, (m0 - 2 * (q + 1)) * D - p, a.n_wide);
+				xw[1] = load_wide<FMT>(a.wide, (m0 + 1 - 2 * (q + 1)) * D - p, a.n_wide);
+			}
+		}
+#pragma unroll
+		for (int i = 0; i < PFB_TM; i++)
+			buf0[(size_t)(g * PFB_TM + i) * N + p] = acc[i];
+	}
+	__syncthreads();
+
+	// ---- T reverse FFTs of size N (Stockham autosort; stage radix r, Ns = product of the radices before it)
+	float2 *src = buf0, *dst = buf1;
+	int Ns = 1;
+	for (int st = 0; st < a.n_stage; st++) {
+		const int r = a.radix[st], nb = N / r, tw_step = N / (Ns * r);
+		for (int item = tid; item < T * nb; item += PFB_THREADS) {
+			const int f = item / nb, j = item - f * nb;
+			const int k = j % Ns, j0 = (j / Ns) * Ns * r + k;
+			const float2 *s = src + (size_t)f * N;
+			float2 *d = dst + (size_t)f * N;
+			if (r == 4) {
+				float2 v0 = s[j], v1 = s[j + nb], v2 = s[j + 2 * nb], v3 = s[j + 3 * nb];
+				if (k) {
+					v1 = cmul(v1, __ldg(&a.twiddle[k * tw_step]));
+					v2 = cmul(v2, __ldg(&a.twiddle[2 * k * tw_step]));
+					v3 = cmul(v3, __ldg(&a.twiddle[3 * k * tw_step]));
+				}
+				const float2 s02 = make_float2(v0.x + v2.x, v0.y + v2.y), d02 = make_float2(v0.x - v2.x, v0.y - v2.y);
+				const float2 s13 = make_float2(v1.x + v3.x, v1.y + v3.y), d13 = make_float2(v1.x - v3.x, v1.y - v3.y);
+				d[j0] = make_float2(s02.x + s13.x, s02.y + s13.y);
+				d[j0 + Ns] = make_float2(d02.x - d13.y, d02.y + d13.x);          // + j d13 (reverse transform)
+				d[j0 + 2 * Ns] = make_float2(s02.x - s13.x, s02.y - s13.y);
+				d[j0 + 3 * Ns] = make_float2(d02.x + d13.y, d02.y - d13.x);      // - j d13
+			} else if (r == 2) {
+				float2 v0 = s[j], v1 = s[j + nb];
+				if (k)
+					v1 = cmul(v1, __ldg(&a.twiddle[k * tw_step]));
+				d[j0] = make_float2(v0.x + v1.x, v0.y + v1.y);
+				d[j0 + Ns] = make_float2(v0.x - v1.x, v0.y - v1.y);
+			} else {                       // odd prime radix (<= CHAN_MAX_RADIX): direct r-point transform
+				float2 v[CHAN_MAX_RADIX];
+				for (int q = 0; q < r; q++) {
+					v[q] = s[j + q * nb];
+					if (k && q)
+						v[q] = cmul(v[q], __ldg(&a.twiddle[q * k * tw_step]));
+				}
+				for (int q2 = 0; q2 < r; q2++) {
+					float2 o = v[0];
+					for (int q = 1; q < r; q++) {
+						const float2 w = __ldg(&a.twiddle[((q * q2) % r) * nb]);
+						o.x += v[q].x * w.x - v[q].y * w.y;
+						o.y += v[q].x * w.y + v[q].y * w.x;
+					}
+					d[j0 + q2 * Ns] = o;
+				}
+			}
+		}
+		__syncthreads();
+		float2 *t = src;
+		src = dst;
+		dst = t;
+		Ns *= r;
+	}
+
+	// ---- time-major output, odd channels of odd steps negated
+	for (int item = tid; item < T * N; item += PFB_THREADS) {
+		const int f = item / N, k = item - f * N;
+		const int64_t m = m_cta + f;
+		if (m >= a.n_steps)
+			break;
+		float2 v = src[item];
+		if ((m & 1) && (k & 1))
+			v = make_float2(-v.x, -v.y);
+		a.mid[m * N + k] = v;
+	}
+}
+
+// ---- arbitrary resampler -------------------------------------------------------------------------------------------
+constexpr int RS_T = 256, RS_CH = 64, RS_TO = 64;
+
+__global__ void __launch_bounds__(RS_T) resamp_kernel(const ResampArgs a)
+{
+	extern __shared__ __align__(16) float2 sm[];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int tpf = a.tpf;
+	float2 *in_tile = sm;                                   // [rows_max][RS_CH]
+	float2 *out_tile = in_tile + (size_t)a.rows_max * RS_CH; // [RS_CH][RS_TO + 1]
+	float *filt = (float *)(out_tile + RS_CH * (RS_TO + 1)); // [32][tpf], then dfilt [32][tpf]
+	float *dfilt = filt + 32 * tpf;
+	float *comb = dfilt + 32 * tpf;                         // [warps][tpf] taps of the output a warp is working on
+	__shared__ int ch_idx[RS_CH];
+
+	const int64_t n0 = (int64_t)blockIdx.x * RS_TO;
+	const int c0 = blockIdx.y * RS_CH;
+	const int n_here = (int)min((int64_t)RS_TO, a.n_out - n0);
+	for (int i = tid; i < 32 * tpf; i += RS_T) {
+		filt[i] = __ldg(&a.filt[i]);
+		dfilt[i] = __ldg(&a.dfilt[i]);
+	}
+	if (tid < RS_CH)
+		ch_idx[tid] = c0 + tid < a.n_wanted ? (a.chan_idx ? __ldg(&a.chan_idx[c0 + tid]) : c0 + tid) : -1;
+	const int64_t row_hi = __ldg(&a.sched_i[n0 + n_here - 1]);
+	const int64_t row_lo = (int64_t)__ldg(&a.sched_i[n0]) - (tpf - 1);
+	const int rows = (int)(row_hi - row_lo + 1);
+	__syncthreads();
+	for (int item = tid; item < rows * RS_CH; item += RS_T) {
+		const int rr = item / RS_CH, c = item - rr * RS_CH;
+		const int64_t row = row_lo + rr;
+		const int k = ch_idx[c];
+		in_tile[item] = (row >= 0 && row < a.n_steps && k >= 0) ? __ldg(&a.mid[row * a.n_chans + k]) : make_float2(0.0f, 0.0f);
+	}
+	__syncthreads();
+
+	float *cw = comb + warp * tpf;
+	for (int o = warp; o < n_here; o += RS_T / 32) {
+		const int64_t n = n0 + o;
+		const int j = a.sched_j[n];
+		const float acc = a.sched_acc[n];
+		const int base = (int)(a.sched_i[n] - row_lo);      // row of x[i]; taps walk downwards
+		__syncwarp();
+		for (int t = lane; t < tpf; t += 32)
+			cw[t] = fmaf(acc, dfilt[j * tpf + t], filt[j * tpf + t]);
+		__syncwarp();
+		float4 s = make_float4(0.0f, 0.0f, 0.0f, 0.0f);     // channels 2 lane, 2 lane + 1
+		const float4 *rowp = reinterpret_cast<const float4 *>(in_tile) + lane;
+#pragma unroll 6
+		for (int t = 0; t < tpf; t++) {
+			const float4 x = rowp[(size_t)(base - t) * (RS_CH / 2)];
+			const float c = cw[t];
+			s.x = fmaf(c, x.x, s.x);
+			s.y = fmaf(c, x.y, s.y);
+			s.z = fmaf(c, x.z, s.z);
+			s.w = fmaf(c, x.w, s.w);
+		}
+		out_tile[(2 * lane) * (RS_TO + 1) + o] = make_float2(s.x, s.y);
+		out_tile[(2 * lane + 1) * (RS_TO + 1) + o] = make_float2(s.z, s.w);
+	}
+	__syncthreads();
+	for (int item = tid; item < RS_CH * RS_TO; item += RS_T) {
+		const int c = item / RS_TO, o = item - c * RS_TO;
+		if (o < n_here && c0 + c < a.n_wanted)
+			a.out[(int64_t)(c0 + c) * a.out_stride + n0 + o] = out_tile[c * (RS_TO + 1) + o];
+	}
+}
+
+// ---- wideband test-signal generator ------------------------------------------------------------------------------
+__device__ __forceinline__ void philox2(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1, uint32_t (&out)[4])
+{
+	uint32_t c2 = 0x243f6a88u, c3 = 0x85a308d3u;
+#pragma unroll
+	for (int r = 0; r < 10; r++) {
+		const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+		const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+		c0 = hi1 ^ c1 ^ k0;
+		c1 = lo1;
+		c2 = hi0 ^ c3 ^ k1;
+		c3 = lo0;
+		k0 += 0x9E3779B9u;
+		k1 += 0xBB67AE85u;
+	}
+	out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(256) wide_synth_kernel(const WideSynthArgs a)
+{
+	extern __shared__ __align__(16) float2 tw[];            // e^{+j 2 pi t / N}
+	const int N = a.n_chans;
+	for (int i = threadIdx.x; i < N; i += blockDim.x)
+		tw[i] = __ldg(&a.twiddle[i]);
+	__syncthreads();
+	for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < a.n_wide; t += (int64_t)gridDim.x * blockDim.x) {
+		const int64_t pos = t * a.num;
+		const int64_t i = pos / a.den;
+		const float f = (float)((double)(pos - i * a.den) / (double)a.den);
+		const float w0 = -f * (f - 1.0f) * (f - 2.0f) / 6.0f, w1 = (f + 1.0f) * (f - 1.0f) * (f - 2.0f) / 2.0f;
+		const float w2 = -(f + 1.0f) * f * (f - 2.0f) / 2.0f, w3 = (f + 1.0f) * f * (f - 1.0f) / 6.0f;
+		const int tm = (int)(t % N);
+		float xr = 0.0f, xi = 0.0f;
+		for (int c = 0; c < a.n_streams; c++) {
+			const float2 *s = a.streams + (int64_t)c * a.stream_stride;
+			const int k = a.chan_idx ? __ldg(&a.chan_idx[c]) : c;
+			float2 v = make_float2(0.0f, 0.0f);
+			if (i >= 1 && i + 2 < a.stream_len) {
+				const float2 s0 = __ldg(&s[i - 1]), s1 = __ldg(&s[i]), s2 = __ldg(&s[i + 1]), s3 = __ldg(&s[i + 2]);
+				v.x = w0 * s0.x + w1 * s1.x + w2 * s2.x + w3 * s3.x;
+				v.y = w0 * s0.y + w1 * s1.y + w2 * s2.y + w3 * s3.y;
+			} else {
+				for (int d = -1; d <= 2; d++) {
+					const int64_t ii = i + d;
+					if (ii >= 0 && ii < a.stream_len) {
+						const float w = d == -1 ? w0 : d == 0 ? w1 : d == 1 ? w2 : w3;
+						v.x += w * s[ii].x;
+						v.y += w * s[ii].y;
+					}
+				}
+			}
+			const float2 ph = tw[(k * tm) % N];
+			xr += v.x * ph.x - v.y * ph.y;
+			xi += v.x * ph.y + v.y * ph.x;
+		}
+		if (a.sigma > 0.0f) {
+			uint32_t rnd[4];
+			philox2((uint32_t)t, (uint32_t)(t >> 32), (uint32_t)a.seed, (uint32_t)(a.seed >> 32), rnd);
+			const float u1 = ((float)rnd[0] + 0.5f) * 2.3283064365386963e-10f;
+			const float u2 = ((float)rnd[1] + 0.5f) * 2.3283064365386963e-10f;
+			const float rad = sqrtf(-2.0f * logf(fmaxf(u1, 1e-30f)));
+			float ns, nc;
+			sincospif(2.0f * u2, &ns, &nc);
+			xr += a.sigma * rad * nc;
+			xi += a.sigma * rad * ns;
+		}
+		xr *= a.gain;
+		xi *= a.gain;
+		if (FMT == 0) {
+			reinterpret_cast<float2 *>(a.wide)[t] = make_float2(xr, xi);
+		} else {
+			const float sr = fminf(fmaxf(rintf(xr * 32768.0f), -32768.0f), 32767.0f);
+			const float si = fminf(fmaxf(rintf(xi * 32768.0f), -32768.0f), 32767.0f);
+			reinterpret_cast<short2 *>(a.wide)[t] = make_short2((short)sr, (short)si);
+		}
+	}
+}
+
+}  // namespace
+
+int pfb_groups(int n_chans)
+{
+	// T = 8 G steps per CTA; two [T][N] complex buffers in shared memory: aim at <= 64 KB so three CTAs fit an SM
+	int g = 4096 / (PFB_TM * n_chans);
+	if (g < 1)
+		g = 1;
+	if (g > 16)
+		g = 16;
+	return g;
+}
+
+cudaError_t launch_pfb(const PfbArgs &a0, int fmt, cudaStream_t st)
+{
+	PfbArgs a = a0;
+	if (a.n_steps <= 0)
+		return cudaSuccess;
+	a.groups = pfb_groups(a.n_chans);
+	const int T = a.groups * PFB_TM;
+	const size_t smem = 2 * (size_t)T * a.n_chans * sizeof(float2);
+	if (smem > 200 * 1024)
+		return cudaErrorNotSupported;
+	static std::atomic<size_t> attr_max[64][2];
+	int dev = 0;
+	cudaGetDevice(&dev);
+	auto *fn = fmt == 0 ? pfb_kernel<0> : pfb_kernel<1>;
+	{
+		GMR1_INIT_LOCK();
+		if (dev < 64 && attr_max[dev][fmt].load() < smem) {
+			cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+			if (e != cudaSuccess)
+				return e;
+			attr_max[dev][fmt].store(smem);
+		}
+	}
+	const int64_t grid = (a.n_steps + T - 1) / T;
+	fn<<<(unsigned)grid, PFB_THREADS, smem, st>>>(a);
+	return cudaGetLastError();
+}
+
+size_t resamp_smem(int rows_max, int tpf)
+{
+	return ((size_t)rows_max * RS_CH + (size_t)RS_CH * (RS_TO + 1)) * sizeof(float2) +
+	       ((size_t)64 * tpf + (size_t)(RS_T / 32) * tpf) * sizeof(float);
+}
+
+int resamp_tile_outputs() { return RS_TO; }
+
+cudaError_t launch_resamp(const ResampArgs &a, cudaStream_t st)
+{
+	if (a.n_out <= 0 || a.n_wanted <= 0)
+		return cudaSuccess;
+	const size_t smem = resamp_smem(a.rows_max, a.tpf);
+	if (smem > 200 * 1024)
+		return cudaErrorNotSupported;
+	static std::atomic<size_t> attr_max[64];
+	int dev = 0;
+	cudaGetDevice(&dev);
+	{
+		GMR1_INIT_LOCK();
+		if (dev < 64 && attr_max[dev].load() < smem) {
+			cudaError_t e = cudaFuncSetAttribute(resamp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+			if (e != cudaSuccess)
+				return e;
+			attr_max[dev].store(smem);
+		}
+	}
+	dim3 grid((unsigned)((a.n_out + RS_TO - 1) / RS_TO), (unsigned)((a.n_wanted + RS_CH - 1) / RS_CH));
+	resamp_kernel<<<grid, RS_T, smem, st>>>(a);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_wide_synth(const WideSynthArgs &a, int fmt, cudaStream_t st)
+{
+	if (a.n_wide <= 0)
+		return cudaSuccess;
+	int dev = 0, sms = 148;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	const size_t smem = (size_t)a.n_chans * sizeof(float2);
+	const int64_t want = (a.n_wide + 255) / 256;
+	const unsigned grid = (unsigned)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
+	if (fmt == 0)
+		wide_synth_kernel<0><<<grid, 256, smem, st>>>(a);
+	else
+		wide_synth_kernel<1><<<grid, 256, smem, st>>>(a);
+	return cudaGetLastError();
+}
+
+}  // namespace gmr1

@@ -135,6 +135,7 @@ struct SynthArgs {
 	float2        *iq;
 	const int64_t *ofs;
 	int64_t        stride;
+	int32_t        tx_pulse;    // 0: raised cosine (after the matched filter), 1: root raised cosine (transmit side)
 };
 cudaError_t launch_synth(const SynthArgs &a, const BurstTab *d_bt, cudaStream_t st);
 // device copy of the standard burst descriptors (api_demod.cu)

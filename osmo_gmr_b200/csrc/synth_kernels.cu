@@ -49,6 +49,18 @@ __device__ __forceinline__ double raised_cosine(double t)
 	return snc * cos(pi * alpha * t) / den;
 }
 
+// root raised cosine, unit energy per symbol (t in symbols): the transmit half of the pulse above
+__device__ __forceinline__ double root_raised_cosine(double t)
+{
+	const double alpha = 0.35, pi = 3.14159265358979323846;
+	if (fabs(t) < 1e-9)
+		return 1.0 - alpha + 4.0 * alpha / pi;
+	const double q = 4.0 * alpha * t;
+	if (fabs(fabs(q) - 1.0) < 1e-9)
+		return alpha / sqrt(2.0) * ((1.0 + 2.0 / pi) * sin(pi / (4.0 * alpha)) + (1.0 - 2.0 / pi) * cos(pi / (4.0 * alpha)));
+	return (sin(pi * t * (1.0 - alpha)) + q * cos(pi * t * (1.0 + alpha))) / (pi * t * (1.0 - q * q));
+}
+
 __global__ void __launch_bounds__(SY_T) synth_kernel(const SynthArgs a, const BurstTab *__restrict__ btp)
 {
 	__shared__ float2 sym[480];
@@ -102,12 +114,13 @@ __global__ void __launch_bounds__(SY_T) synth_kernel(const SynthArgs a, const Bu
 	const double tf = (double)toa - (double)ti;
 	for (int i = tid; i < sps * RC_TAPS; i += SY_T) {
 		const int r = i / RC_TAPS, j = i % RC_TAPS - 6;
-		rcw[r][j + 6] = (float)raised_cosine(((double)r - tf) / sps - (double)j);
+		const double tt = ((double)r - tf) / sps - (double)j;
+		rcw[r][j + 6] = (float)(a.tx_pulse ? root_raised_cosine(tt) : raised_cosine(tt));
 	}
 	__syncthreads();
 
 	// 3. samples
-	const float sigma = amp * exp10f(-esn0 / 20.0f) * 0.70710678118654752f;
+	const float sigma = esn0 >= 100.0f ? 0.0f : amp * exp10f(-esn0 / 20.0f) * 0.70710678118654752f;
 	float2 *out = a.iq + (a.ofs ? a.ofs[b] : (int64_t)b * a.stride);
 	for (int nn = tid; nn < L; nn += SY_T) {
 		const int dnn = nn - ti;

@@ -80,6 +80,13 @@ class Lib:
         "gmr1b200_pi4cxpsk_mod_order_batch": [_P, _L, _P, _L, _I, _I, _P, _F, _P, _I, _P],
         "gmr1b200_synth_bursts": [_I, _P, _I, _P, _I, _I, _P, _F, _P, _F, _P, _F, _P, _F, _P, _F, ctypes.c_uint64,
                                   _P, _L, _P, _L, _I, _P],
+        "gmr1b200_synth_bursts_tx": [_I, _P, _I, _P, _I, _I, _P, _F, _P, _F, _P, _F, _P, _F, _P, _F, ctypes.c_uint64,
+                                     _P, _L, _P, _L, _I, _P],
+        "gmr1b200_chan_create": [_I, _I, _P],
+        "gmr1b200_chan_info": [_P, _P],
+        "gmr1b200_chan_taps": [_P, _P, _I, _P, _I],
+        "gmr1b200_channelize": [_P, _P, _I, _L, _P, _I, _P, _L, _P],
+        "gmr1b200_synth_wideband": [_P, _P, _L, _L, _P, _I, _F, _F, ctypes.c_uint64, _P, _I, _L, _P],
         "gmr1b200_set_sync_accumulator_reset": [_I],
         "gmr1b200_set_demod_generic": [_I],
         "gmr1b200_set_rx_lockstep": [_I],
@@ -117,6 +124,10 @@ class Lib:
         self.c.gmr1b200_host_alloc.restype = _P
         self.c.gmr1b200_host_free.argtypes = [_P]
         self.c.gmr1b200_host_free.restype = None
+        self.c.gmr1b200_chan_destroy.argtypes = [_P]
+        self.c.gmr1b200_chan_destroy.restype = None
+        self.c.gmr1b200_chan_out_len.argtypes = [_P, _L]
+        self.c.gmr1b200_chan_out_len.restype = _L
 
     # -- helpers
     def _chk(self, rc, what):
