@@ -16,6 +16,8 @@ window + fine), then demod BCCH, decode BCCH, demod DC6, decode CCCH (6 kernel l
                    (oracle/harness.c), on the head of the same IQ; also the L2 / CRC parity check
   configs          BASELINE configs 3 and 4 at full size (N = 1 only): bursts/s, per-kernel times, their own demod
                    roofline, and a 4 096-burst-per-type comparison with the CPU reference
+  wideband         the headline receive work fed from one wideband int16 recording of all ARFCNs through the GPU
+                   channeliser, end to end from pinned host memory and device-resident (N = 1 only)
   sweep            BASELINE config 5: ARFCN count 1k .. 64k in total, sharded over the ranks, 1 s recording slice per
                    ARFCN (FCCH search + 25 bursts), device-resident and streamed from pinned host memory
 Multi-GPU: ARFCNs are independent, each rank owns its own ARFCNs (weak scaling), no data-path collective;
@@ -348,6 +350,172 @@ def run_configs(L, torch, dev, peak_gbs, cores, scale, reps, n_check):
 # ------------------------------------------------------------------------------------------------
 # the end-to-end step of several GPUs from ONE process (library device pool, csrc/api_multi.cu)
 # ------------------------------------------------------------------------------------------------
+def run_wideband(L, torch, dev, n_arfcn, per_arfcn, steps, seed=4242):
+    """SURVEY 8f N3 in front of the headline workload: the SAME receive work (one FCCH acquisition per ARFCN + per_arfcn
+    BCCH / DC6 bursts per ARFCN, demod + decode), but the input is ONE wideband recording of all ARFCNs (int16 I/Q at
+    n_arfcn x 31.25 kS/s, what an SDR front end delivers) instead of one 4x-oversampled complex-float stream per ARFCN:
+    pinned host recording -> H2D -> gmr1b200_channelize (filter bank + RRC resampler, streams stay in HBM) -> FCCH
+    acquire, demod, decode on window offsets into the streams -> host L2 / CRC.  The recording is made once on the device
+    (transmit-pulse bursts of every ARFCN interpolated, mixed to their carriers, summed, AWGN, int16)."""
+    import ctypes
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    n_b = {"bcch": per_arfcn // 2, "dc6": per_arfcn - per_arfcn // 2}
+    lead = 64
+    slot = wlen("bcch") + wlen("dc6")
+    slen = lead + FCCH_WIN + (per_arfcn // 2) * slot + 64
+    h = ctypes.c_void_p()
+    assert L.c.gmr1b200_chan_create(n_arfcn, SPS, ctypes.byref(h)) == 0
+
+    class Info(ctypes.Structure):
+        _fields_ = [("n_chans", ctypes.c_int32), ("sps", ctypes.c_int32), ("n_taps", ctypes.c_int32),
+                    ("taps_per_branch", ctypes.c_int32), ("n_taps_resamp", ctypes.c_int32), ("fft_stages", ctypes.c_int32),
+                    ("samp_rate", ctypes.c_double), ("mid_rate", ctypes.c_double), ("resamp", ctypes.c_double),
+                    ("delay_out", ctypes.c_double)]
+    info = Info()
+    L.c.gmr1b200_chan_info(h, ctypes.byref(info))
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    streams = torch.zeros((n_arfcn, slen, 2), dtype=torch.float32, device=dev)
+    # FCCH chirp of every ARFCN inside its 330 ms head (clean: the noise is added to the wideband sum)
+    rng = np.random.default_rng(seed)
+    fpos = rng.integers(600, FCCH_WIN - 1200, n_arfcn)
+    fcfo = rng.uniform(-0.27, 0.27, n_arfcn)
+    k = torch.arange(117 * SPS, device=dev, dtype=torch.float32)
+    t = k / SPS - 58.5
+    chirp = (2.0 ** 0.5) * torch.cos(0.32 * 2 * np.pi / 117 * t * t)
+    ang = d(fcfo.astype(np.float32))[:, None] * (k[None, :] / SPS)
+    idx = d(fpos + lead)[:, None] + torch.arange(117 * SPS, device=dev)[None, :]
+    rows = torch.arange(n_arfcn, device=dev)[:, None].expand_as(idx)
+    streams[rows, idx, 0] = chirp[None, :] * torch.cos(ang)
+    streams[rows, idx, 1] = chirp[None, :] * torch.sin(ang)
+    par, ofs = {}, {}
+    for kind, first in (("bcch", 0), ("dc6", wlen("bcch"))):
+        n = n_arfcn * n_b[kind]
+        pr = burst_params(n, kind, seed + BT[kind])
+        hard = np.zeros((n, EBITS[kind]), np.uint8)
+        L.call("gmr1b200_xcch_encode_batch", CHAN[kind], hard, pr["l2"], n)
+        o = (np.arange(n_arfcn, dtype=np.int64)[:, None] * slen + lead + FCCH_WIN + first +
+             np.arange(n_b[kind], dtype=np.int64)[None, :] * slot).reshape(-1)
+        L.call("gmr1b200_synth_bursts_tx", BT[kind], d(hard), EBITS[kind], None, SPS, wlen(kind), d(pr["toa"]), 0.0,
+               d(pr["cfo"]), 0.0, d(pr["phase"]), 0.0, None, 200.0, None, 1.0, seed, streams, n_arfcn * slen, d(o), 0, n, None)
+        par[kind], ofs[kind] = pr, o
+    n_wide = ((slen - 3) * 625 * n_arfcn) // (468 * SPS)
+    wide = torch.empty((n_wide, 2), dtype=torch.int16, device=dev)
+    esn0, gain = 15.0, 0.5 / (4.0 * np.sqrt(n_arfcn))
+    torch.cuda.synchronize()
+    g0 = time.perf_counter()
+    L.call("gmr1b200_synth_wideband", h.value, streams, slen, slen, None, n_arfcn, esn0, gain, seed, wide, 1, n_wide, None)
+    torch.cuda.synchronize()
+    gen_s = time.perf_counter() - g0
+    del streams
+    peak_i16 = int(wide.abs().max())
+    host_wide = torch.empty((n_wide, 2), dtype=torch.int16).pin_memory()
+    host_wide.copy_(wide)
+    n_out = int(L.c.gmr1b200_chan_out_len(h, n_wide))
+    out = torch.empty((n_arfcn, n_out, 2), dtype=torch.float32, device=dev)
+    dly = int(round(info.delay_out))
+    # window offsets inside the channelised streams: row stride n_out, everything delay_out later
+    res = {}
+    for kind in ("bcch", "dc6"):
+        n = n_arfcn * n_b[kind]
+        a, j = np.divmod(np.arange(n, dtype=np.int64), n_b[kind])
+        o = ofs[kind] - a * slen + a * n_out + dly
+        res[kind] = dict(ofs=d(o), eb=torch.empty((n, EBITS[kind]), dtype=torch.int8, device=dev),
+                         l2=torch.empty((n, 24), dtype=torch.uint8, device=dev), crc=torch.empty(n, dtype=torch.int32, device=dev),
+                         h_l2=torch.empty((n, 24), dtype=torch.uint8).pin_memory(), h_crc=torch.empty(n, dtype=torch.int32).pin_memory())
+    f_ofs = d(np.arange(n_arfcn, dtype=np.int64) * n_out + lead + dly)
+    f_toa = torch.empty(n_arfcn, dtype=torch.int32, device=dev)
+    f_align = torch.empty(n_arfcn, dtype=torch.int32, device=dev)
+    f_ferr = torch.empty(n_arfcn, dtype=torch.float32, device=dev)
+    h_f = torch.empty((2, n_arfcn), dtype=torch.float32).pin_memory()
+    st = torch.cuda.Stream(device=dev)
+    sh = st.cuda_stream
+
+    def receive(timers=None):
+        marks = []
+        mark = lambda name: (marks.append((name, ev())), marks[-1][1].record(st)) if timers is not None else None
+        mark("start")
+        L.call("gmr1b200_channelize", h.value, wide, 1, n_wide, None, n_arfcn, out, n_out, sh)
+        mark("channelize")
+        L.call("gmr1b200_fcch_acquire_batch", 0, out, n_arfcn * n_out, f_ofs, 0, FCCH_WIN, SPS, f_toa, f_align, f_ferr, n_arfcn, sh)
+        mark("fcch")
+        for kind in ("bcch", "dc6"):
+            r = res[kind]
+            n = r["crc"].numel()
+            L.call("gmr1b200_pi4cxpsk_demod_batch", BT[kind], out, n_arfcn * n_out, r["ofs"], 0, wlen(kind), SPS, None, 0.0,
+                   r["eb"], EBITS[kind], None, None, None, None, n, sh)
+            L.call("gmr1b200_bcch_decode_batch" if kind == "bcch" else "gmr1b200_ccch_decode_batch", r["l2"], r["eb"], None,
+                   r["crc"], n, sh)
+        mark("demod_decode")
+        if timers is not None:
+            timers.append(marks)
+
+    def e2e():
+        with torch.cuda.stream(st):
+            wide.copy_(host_wide, non_blocking=True)
+        receive()
+        with torch.cuda.stream(st):
+            for kind in ("bcch", "dc6"):
+                res[kind]["h_l2"].copy_(res[kind]["l2"], non_blocking=True)
+                res[kind]["h_crc"].copy_(res[kind]["crc"], non_blocking=True)
+            h_f[0].copy_(f_align.to(torch.float32), non_blocking=True)
+            h_f[1].copy_(f_ferr, non_blocking=True)
+        st.synchronize()
+
+    for _ in range(3):
+        receive()
+    torch.cuda.synchronize()
+    launches0 = L.kernel_launches()
+    timers = []
+    a, b = ev(), ev()
+    a.record(st)
+    for _ in range(steps):
+        receive(timers)
+    b.record(st)
+    torch.cuda.synchronize()
+    launches = (L.kernel_launches() - launches0) / steps
+    dev_ms = a.elapsed_time(b) / steps
+    part = {}
+    for marks in timers:
+        for (_, e0), (name, e1) in zip(marks[:-1], marks[1:]):
+            part[name] = part.get(name, 0.0) + e0.elapsed_time(e1) / steps
+    e2e()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        e2e()
+    torch.cuda.synchronize()
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / steps
+    # what came out: payloads against what was sent, FCCH positions against where the chirps were put
+    nb = sum(n_arfcn * n_b[kk] for kk in n_b)
+    ok = sum(int((res[kk]["h_crc"] == 0).sum()) for kk in n_b)
+    good = sum(int(((res[kk]["h_l2"].numpy() == par[kk]["l2"]).all(axis=1) & (res[kk]["h_crc"].numpy() == 0)).sum()) for kk in n_b)
+    wrong = sum(int(((res[kk]["h_l2"].numpy() != par[kk]["l2"]).any(axis=1) & (res[kk]["h_crc"].numpy() == 0)).sum()) for kk in n_b)
+    toa_err = h_f[0].numpy() - (fpos + info.delay_out - dly)
+    n_steps = n_wide // (n_arfcn // 2)
+    bank_bytes = n_wide * 4 + n_steps * n_arfcn * 8
+    rs_bytes = n_steps * n_arfcn * 8 + n_arfcn * n_out * 8
+    L.c.gmr1b200_chan_destroy(h)
+    return {
+        "what": "the headline receive work fed from ONE wideband int16 recording of all ARFCNs through the GPU channeliser "
+                "(replaces the PFB mode of utils/gmr1_rx_sdr.py) instead of one complex-float stream per ARFCN",
+        "arfcns": n_arfcn, "bursts": nb, "fcch_acquisitions": n_arfcn, "recording_seconds": n_wide / info.samp_rate,
+        "wideband_rate_msps": info.samp_rate / 1e6, "bank_taps": info.n_taps, "rrc_taps": info.n_taps_resamp,
+        "e2e": {"value": nb / (e2e_ms * 1e-3), "unit": "bursts/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(n_wide * 4), "d2h_bytes_per_step": int(nb * 28 + n_arfcn * 8),
+                "per_arfcn_cf32_bytes_equivalent": int(n_arfcn * n_out * 8),
+                "how": "pinned host int16 recording -> one H2D copy -> channelize -> fcch_acquire + demod + decode on "
+                       "offsets into the device-resident streams -> host L2 / CRC / alignments"},
+        "device_resident": {"bursts_per_s": nb / (dev_ms * 1e-3), "ms_per_step": dev_ms, "ms": {k_: round(v, 4) for k_, v in part.items()},
+                            "channelizer_input_msps": n_wide / (part["channelize"] * 1e-3) / 1e6,
+                            "channelizer_algorithmic_gbs": (bank_bytes + rs_bytes) / (part["channelize"] * 1e-3) / 1e9,
+                            "realtime_factor": (n_wide / info.samp_rate) / (dev_ms * 1e-3), "launches_per_step": launches},
+        "crc_ok_frac": ok / nb, "payload_correct_frac": good / nb, "crc_ok_but_payload_wrong": wrong,
+        "fcch_found_frac": float((np.abs(toa_err) <= 2).mean()),
+        "esn0_db": esn0, "int16_peak": peak_i16, "generation_s": gen_s,
+    }
+
+
+
 def run_pool_e2e(L, torch, W, host_iq, host_fcch, n_gpus, steps):
     """host IQ of n_gpus x (this GPU's ARFCNs) in pinned memory -> gmr1b200_pool_fcch_acquire + gmr1b200_pool_rx_xcch
     (BCCH, DC6): ARFCN a is processed on device a mod n_gpus, host-side gather of L2 / CRC.  The content of ARFCN a
@@ -863,6 +1031,12 @@ def run_gpu_arm(args):
                "single_core_bursts_per_s": 2 * m1 / wall1,
                "l2_crc_identical_to_gpu": same}
 
+    # ---------------- the same work from one wideband recording through the channeliser (N = 1)
+    wideband = None
+    if world == 1 and not args.no_wideband:
+        torch.cuda.empty_cache()
+        wideband = run_wideband(L, torch, dev, args.arfcns, args.bursts_per_arfcn, min(args.steps, 5))
+
     # ---------------- BASELINE configs 3 and 4 at full size (N = 1)
     if world == 1 and not args.no_configs:
         configs = run_configs(L, torch, dev, peak, 0 if args.no_cpu_baseline else cores, args.config_scale, 5, 4096)
@@ -903,6 +1077,7 @@ def run_gpu_arm(args):
         "fcch": fcch,
         "cpu_baseline": cpu,
         "configs": configs,
+        "wideband": wideband,
         "sweep": sweep,
         "build": L.version(),
         "clocks": sampler.summary(),
@@ -926,6 +1101,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip BASELINE configs 3 and 4")
     ap.add_argument("--no-sweep", action="store_true", help="skip the config-5 ARFCN sweep")
+    ap.add_argument("--no-wideband", action="store_true", help="skip the wideband-recording (channeliser) leg")
     ap.add_argument("--config-scale", type=float, default=1.0, help="fraction of the ARFCN counts of configs 3 / 4")
     ap.add_argument("--sweep-max", type=int, default=0, help="largest total ARFCN count of the sweep (0: 65536)")
     ap.add_argument("--sweep-chunk", type=int, default=1024, help="ARFCN slices per streamed chunk")
