@@ -430,11 +430,11 @@ def run_wideband(L, torch, dev, n_arfcn, per_arfcn, steps, seed=4242):
     st = torch.cuda.Stream(device=dev)
     sh = st.cuda_stream
 
-    def receive(timers=None):
+    def receive(timers=None, src=None):
         marks = []
         mark = lambda name: (marks.append((name, ev())), marks[-1][1].record(st)) if timers is not None else None
         mark("start")
-        L.call("gmr1b200_channelize", h.value, wide, 1, n_wide, None, n_arfcn, out, n_out, sh)
+        L.call("gmr1b200_channelize", h.value, wide if src is None else src, 1, n_wide, None, n_arfcn, out, n_out, sh)
         mark("channelize")
         L.call("gmr1b200_fcch_acquire_batch", 0, out, n_arfcn * n_out, f_ofs, 0, FCCH_WIN, SPS, f_toa, f_align, f_ferr, n_arfcn, sh)
         mark("fcch")
@@ -450,9 +450,9 @@ def run_wideband(L, torch, dev, n_arfcn, per_arfcn, steps, seed=4242):
             timers.append(marks)
 
     def e2e():
-        with torch.cuda.stream(st):
-            wide.copy_(host_wide, non_blocking=True)
-        receive()
+        # the pinned HOST recording goes straight into the C entry point: it copies it in pieces on its own copy stream
+        # while the bank and the resampler of the pieces before run (csrc/api_chan.cu)
+        receive(src=host_wide)
         with torch.cuda.stream(st):
             for kind in ("bcch", "dc6"):
                 res[kind]["h_l2"].copy_(res[kind]["l2"], non_blocking=True)
@@ -503,8 +503,10 @@ def run_wideband(L, torch, dev, n_arfcn, per_arfcn, steps, seed=4242):
         "e2e": {"value": nb / (e2e_ms * 1e-3), "unit": "bursts/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(n_wide * 4), "d2h_bytes_per_step": int(nb * 28 + n_arfcn * 8),
                 "per_arfcn_cf32_bytes_equivalent": int(n_arfcn * n_out * 8),
-                "how": "pinned host int16 recording -> one H2D copy -> channelize -> fcch_acquire + demod + decode on "
-                       "offsets into the device-resident streams -> host L2 / CRC / alignments"},
+                "h2d_gbs": n_wide * 4 / (e2e_ms * 1e-3) / 1e9,
+                "how": "pinned host int16 recording -> gmr1b200_channelize (H2D in pieces under the bank + resampler "
+                       "kernels) -> fcch_acquire + demod + decode on offsets into the device-resident streams -> host "
+                       "L2 / CRC / alignments"},
         "device_resident": {"bursts_per_s": nb / (dev_ms * 1e-3), "ms_per_step": dev_ms, "ms": {k_: round(v, 4) for k_, v in part.items()},
                             "channelizer_input_msps": n_wide / (part["channelize"] * 1e-3) / 1e6,
                             "channelizer_algorithmic_gbs": (bank_bytes + rs_bytes) / (part["channelize"] * 1e-3) / 1e9,

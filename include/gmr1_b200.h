@@ -530,9 +530,16 @@ int64_t gmr1b200_chan_out_len(void *plan, int64_t n_wide);
  * complex float32, 1 = interleaved int16 I/Q scaled by 1 / 32768 (what SDR front ends deliver; half the bytes);
  * chan_idx [n_wanted] bank channels wanted, NULL = channels 0 .. n_wanted-1;
  * out [n_wanted][out_stride] complex float (interleaved), out_stride >= gmr1b200_chan_out_len(n_wide) samples.
- * Host or device pointers. */
+ * Host or device pointers.  A HOST recording travels in up to 16 pieces on a copy stream of the plan while the bank
+ * and the resampler of the pieces before run on `stream` (page-locked memory - gmr1b200_host_alloc - makes the copies
+ * asynchronous); the results are the same as for one piece. */
 int gmr1b200_channelize(void *plan, const void *wide, int iq_format, int64_t n_wide, const int32_t *chan_idx, int n_wanted,
                         float *out, int64_t out_stride, void *stream);
+/* Kernel selection switch (testing / A-B measurements): banks of 64 .. 2048 channels, a power of two, run on a kernel
+ * with register radix-16 butterflies and compile-time geometry; every other channel count (mixed radix, odd primes up
+ * to 31) on the generic shared-memory Stockham kernel.  1 forces the generic kernel for every bank; both compute the
+ * same function.  Process-wide; returns the previous setting. */
+int gmr1b200_set_chan_generic(int on);
 /* workload construction (tests, bench): the inverse direction.  streams [n_streams][stream_stride] complex float at
  * sps x 23.4 kS/s (e.g. from gmr1b200_synth_bursts_tx) are interpolated to the wideband rate, mixed to their
  * channels and summed; white noise for a per-channel Es/N0 of esn0_db (unit-power streams; >= 100: none); the sum is

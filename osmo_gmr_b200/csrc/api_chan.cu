@@ -11,10 +11,38 @@ using namespace gmr1;
 
 namespace {
 
+constexpr int N_EV = 32;
+
 struct Plan {
 	ChanPlan p;
 	std::mutex mu;                         // the phase walk and the device copies grow under it
+	// host recordings travel in chunks on a copy stream of the plan while the kernels of the previous chunks run
+	struct Feed {
+		cudaStream_t st = nullptr;
+		cudaEvent_t  ev[N_EV] = {};
+		int          next = 0;
+	} feed[64];
 };
+
+cudaError_t plan_feed(Plan &pl, Plan::Feed **out)
+{
+	int dev = 0;
+	cudaError_t e = cudaGetDevice(&dev);
+	if (e != cudaSuccess)
+		return e;
+	if (dev < 0 || dev >= 64)
+		return cudaErrorInvalidDevice;
+	Plan::Feed &f = pl.feed[dev];
+	if (!f.st) {
+		if ((e = cudaStreamCreateWithFlags(&f.st, cudaStreamNonBlocking)) != cudaSuccess)
+			return e;
+		for (int i = 0; i < N_EV; i++)
+			if ((e = cudaEventCreateWithFlags(&f.ev[i], cudaEventDisableTiming)) != cudaSuccess)
+				return e;
+	}
+	*out = &f;
+	return cudaSuccess;
+}
 
 // device copies of the plan's tables on the current device; the phase walk covers n_out outputs
 cudaError_t plan_device(Plan &pl, size_t n_out, ChanPlan::Dev **out)
@@ -87,9 +115,15 @@ void gmr1b200_chan_destroy(void *plan)
 	cudaGetDevice(&cur);
 	for (int dev = 0; dev < 64; dev++) {
 		ChanPlan::Dev &d = pl->p.dev[dev];
-		if (!d.taps && !d.filt && !d.sched_i)
+		if (!d.taps && !d.filt && !d.sched_i && !pl->feed[dev].st)
 			continue;
 		cudaSetDevice(dev);
+		if (pl->feed[dev].st) {
+			cudaStreamSynchronize(pl->feed[dev].st);
+			for (int i = 0; i < N_EV; i++)
+				cudaEventDestroy(pl->feed[dev].ev[i]);
+			cudaStreamDestroy(pl->feed[dev].st);
+		}
 		cudaFree(d.taps); cudaFree(d.filt); cudaFree(d.dfilt); cudaFree(d.twiddle);
 		cudaFree(d.sched_i); cudaFree(d.sched_j); cudaFree(d.sched_acc);
 	}
@@ -150,7 +184,13 @@ int gmr1b200_channelize(void *plan, const void *wide, int iq_format, int64_t n_w
 		return set_err(-EINVAL, "channelize: more streams than channels");
 	int64_t n_out, n_steps;
 	ChanPlan::Dev *d = nullptr;
-	int rows_max = 0;
+	Plan::Feed *feed = nullptr;
+	int rows_max = 0, span_max = 0;
+	const bool wide_on_host = host_pointer(wide);
+	const size_t samp_bytes = iq_format == 0 ? sizeof(float2) : 2 * sizeof(int16_t);
+	// chunks: a host recording travels in up to 16 pieces (>= 2 MB each) so that the bank and the resampler of piece c
+	// run under the copy of piece c + 1; a device-resident recording is one piece
+	std::vector<int64_t> cut_m, cut_n;     // piece c makes steps [cut_m[c], cut_m[c+1]) and outputs [cut_n[c], cut_n[c+1])
 	{
 		std::lock_guard<std::mutex> lk(pl->mu);
 		n_out = chan_plan_out_len(p, n_wide);
@@ -160,43 +200,118 @@ int gmr1b200_channelize(void *plan, const void *wide, int iq_format, int64_t n_w
 		if (n_out == 0)
 			return 0;
 		cudaError_t e = plan_device(*pl, (size_t)n_out, &d);
+		if (e == cudaSuccess && wide_on_host)
+			e = plan_feed(*pl, &feed);
 		if (e != cudaSuccess)
 			return cuda_rc(e, "channelize: table upload");
-		const int to = resamp_tile_outputs();
+		const int to = resamp_tile_outputs(), go = resamp_group_outputs();
 		for (int64_t n0 = 0; n0 < n_out; n0 += to) {
 			const int64_t n1 = (n0 + to < n_out ? n0 + to : n_out) - 1;
 			const int rows = p.sched_i[n1] - p.sched_i[n0] + p.tpf;
 			rows_max = rows > rows_max ? rows : rows_max;
 		}
+		for (int64_t n0 = 0; n0 < n_out; n0 += go) {
+			const int64_t n1 = (n0 + go < n_out ? n0 + go : n_out) - 1;
+			const int span = p.sched_i[n1] - p.sched_i[n0] + p.tpf;
+			span_max = span > span_max ? span : span_max;
+		}
+		int pieces = 1;
+		if (wide_on_host) {
+			pieces = (int)((size_t)n_wide * samp_bytes / (2u << 20));
+			pieces = pieces < 1 ? 1 : pieces > 16 ? 16 : pieces;
+		}
+		cut_m.push_back(0);
+		cut_n.push_back(0);
+		for (int c = 1; c <= pieces; c++) {
+			int64_t m1 = c == pieces ? n_steps : (n_steps * c / pieces) & ~(int64_t)63;
+			if (m1 <= cut_m.back() && c < pieces)
+				continue;
+			// outputs whose newest input step is below m1, down to a whole tile (the rest waits for the next piece)
+			int64_t lo = cut_n.back(), hi = n_out;
+			while (lo < hi) {
+				const int64_t mid = (lo + hi) / 2;
+				if (p.sched_i[mid] < m1)
+					lo = mid + 1;
+				else
+					hi = mid;
+			}
+			const int64_t n1 = c == pieces ? n_out : lo - lo % to;
+			cut_m.push_back(m1);
+			cut_n.push_back(n1 < cut_n.back() ? cut_n.back() : n1);
+		}
 	}
+	cudaStream_t st = (cudaStream_t)stream;
 	Stage s(stream);
-	const void *d_wide = iq_format == 0 ? (const void *)s.in((const float *)wide, (size_t)n_wide * 2)
-	                                    : (const void *)s.in((const int16_t *)wide, (size_t)n_wide * 2);
+	const void *d_wide;
+	if (wide_on_host)
+		d_wide = s.tmp<char>((size_t)n_wide * samp_bytes);
+	else
+		d_wide = wide;
 	const int32_t *d_idx = s.in(chan_idx, (size_t)n_wanted);
 	float2 *d_out = (float2 *)s.out(out, (size_t)n_wanted * (size_t)out_stride * 2);
 	float2 *mid = s.tmp<float2>((size_t)n_steps * p.n_chans);
 	if (s.failed())
 		return s.finish(cudaSuccess, "channelize: staging");
 	if ((void *)d_out != (void *)out && out_stride > n_out)      // staged host output: the row tails travel back too
-		cudaMemsetAsync(d_out, 0, (size_t)n_wanted * (size_t)out_stride * sizeof(float2), (cudaStream_t)stream);
+		cudaMemsetAsync(d_out, 0, (size_t)n_wanted * (size_t)out_stride * sizeof(float2), st);
 	PfbArgs pa = {};
 	pa.wide = d_wide; pa.n_wide = n_wide; pa.n_chans = p.n_chans; pa.taps_per_branch = p.taps_per_branch;
 	pa.taps = d->taps; pa.twiddle = d->twiddle; pa.n_stage = (int)p.radix.size();
 	for (int i = 0; i < pa.n_stage; i++)
 		pa.radix[i] = p.radix[i];
 	pa.mid = mid; pa.n_steps = n_steps;
-	cudaError_t e = launch_pfb(pa, iq_format, (cudaStream_t)stream);
-	if (e == cudaSuccess) {
-		g_launches.fetch_add(1);
-		ResampArgs ra = {};
-		ra.mid = mid; ra.n_steps = n_steps; ra.n_chans = p.n_chans; ra.chan_idx = d_idx; ra.n_wanted = n_wanted;
-		ra.sched_i = d->sched_i; ra.sched_j = d->sched_j; ra.sched_acc = d->sched_acc; ra.filt = d->filt; ra.dfilt = d->dfilt;
-		ra.tpf = p.tpf; ra.rows_max = rows_max; ra.out = d_out; ra.out_stride = out_stride; ra.n_out = n_out;
-		e = launch_resamp(ra, (cudaStream_t)stream);
-		if (e == cudaSuccess)
+	ResampArgs ra = {};
+	ra.mid = mid; ra.n_steps = n_steps; ra.n_chans = p.n_chans; ra.chan_idx = d_idx; ra.n_wanted = n_wanted;
+	ra.sched_i = d->sched_i; ra.sched_j = d->sched_j; ra.sched_acc = d->sched_acc; ra.filt = d->filt; ra.dfilt = d->dfilt;
+	ra.tpf = p.tpf; ra.rows_max = rows_max; ra.span_max = span_max; ra.out = d_out; ra.out_stride = out_stride; ra.n_out = n_out;
+	cudaError_t e = cudaSuccess;
+	if (wide_on_host) {                    // the copy stream starts behind the allocation of its target
+		cudaEvent_t ev = feed->ev[feed->next++ % N_EV];
+		if ((e = cudaEventRecord(ev, st)) == cudaSuccess)
+			e = cudaStreamWaitEvent(feed->st, ev, 0);
+	}
+	int64_t copied = 0;                    // wideband samples on the device so far
+	for (size_t c = 0; c + 1 < cut_m.size() && e == cudaSuccess; c++) {
+		const bool last = c + 2 == cut_m.size();
+		if (wide_on_host) {
+			// steps below cut_m[c+1] read samples up to (cut_m[c+1] - 1) n_chans / 2; the last piece takes the rest
+			int64_t upto = last ? n_wide : (cut_m[c + 1] - 1) * (p.n_chans / 2) + 1;
+			upto = upto > n_wide ? n_wide : upto;
+			if (upto > copied) {
+				e = cudaMemcpyAsync((char *)d_wide + (size_t)copied * samp_bytes, (const char *)wide + (size_t)copied * samp_bytes,
+				                    (size_t)(upto - copied) * samp_bytes, cudaMemcpyHostToDevice, feed->st);
+				copied = upto;
+				cudaEvent_t ev = feed->ev[feed->next++ % N_EV];
+				if (e == cudaSuccess)
+					e = cudaEventRecord(ev, feed->st);
+				if (e == cudaSuccess)
+					e = cudaStreamWaitEvent(st, ev, 0);
+				if (e != cudaSuccess)
+					break;
+			}
+		}
+		pa.m_begin = cut_m[c]; pa.m_end = cut_m[c + 1];
+		if (pa.m_end > pa.m_begin) {
+			if ((e = launch_pfb(pa, iq_format, st)) != cudaSuccess)
+				break;
 			g_launches.fetch_add(1);
+		}
+		ra.n_begin = cut_n[c]; ra.n_end = cut_n[c + 1];
+		if (ra.n_end > ra.n_begin) {
+			if ((e = launch_resamp(ra, st)) != cudaSuccess)
+				break;
+			g_launches.fetch_add(1);
+		}
 	}
 	return s.finish(e, "channelize kernels");
+}
+
+int gmr1b200_set_chan_generic(int on)
+{
+	static std::atomic<int> cur{0};
+	const int prev = cur.exchange(on ? 1 : 0);
+	pfb_force_generic(on ? 1 : 0);
+	return prev;
 }
 
 int gmr1b200_synth_wideband(void *plan, const float *streams, int64_t stream_stride, int64_t stream_len,

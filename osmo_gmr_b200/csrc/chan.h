@@ -20,6 +20,8 @@ struct PfbArgs {
 	int32_t       n_stage, radix[CHAN_MAX_STAGE];
 	float2       *mid;                     // [n_steps][n_chans] bank output, 2 x 31.25 kS/s per channel
 	int64_t       n_steps;
+	int64_t       m_begin, m_end;          // the steps this launch makes (a chunk of the recording); samples up to
+	                                       // (m_end - 1) n_chans / 2 are read
 };
 
 struct ResampArgs {
@@ -32,9 +34,10 @@ struct ResampArgs {
 	const uint8_t *sched_j;                // [n_out] filter phase
 	const float   *sched_acc;              // [n_out] weight of the derivative filter
 	const float   *filt, *dfilt;           // [32][tpf]
-	int32_t        tpf, rows_max;
+	int32_t        tpf, rows_max, span_max; // taps per phase; input rows of a 64-output tile / of a 4-output group, at most
 	float2        *out;                    // [n_wanted][out_stride]
 	int64_t        out_stride, n_out;
+	int64_t        n_begin, n_end;         // the outputs this launch makes (n_begin a multiple of the tile, 64)
 };
 
 struct WideSynthArgs {
@@ -52,8 +55,11 @@ struct WideSynthArgs {
 
 int pfb_groups(int n_chans);
 cudaError_t launch_pfb(const PfbArgs &a, int fmt, cudaStream_t st);
-size_t resamp_smem(int rows_max, int tpf);
+size_t resamp_smem(int rows_max, int span_max, int tpf);
 int resamp_tile_outputs();
+int resamp_group_outputs();
+int pfb_is_fast(int n_chans, int taps_per_branch);
+void pfb_force_generic(int on);          // tests: run the generic kernel where the fast one would
 cudaError_t launch_resamp(const ResampArgs &a, cudaStream_t st);
 cudaError_t launch_wide_synth(const WideSynthArgs &a, int fmt, cudaStream_t st);
 

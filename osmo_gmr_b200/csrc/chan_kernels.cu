@@ -22,6 +22,7 @@
 #include <stdint.h>
 
 #include "chan.h"
+#include "chan_fft.cuh"
 
 namespace gmr1 {
 
@@ -52,7 +53,7 @@ __global__ void __launch_bounds__(PFB_THREADS) pfb_kernel(const PfbArgs a)
 	const int N = a.n_chans, D = N >> 1, P = a.taps_per_branch, G = a.groups, T = G * PFB_TM;
 	const int tid = threadIdx.x;
 	float2 *buf0 = sm, *buf1 = sm + (size_t)T * N;
-	const int64_t m_cta = (int64_t)blockIdx.x * T;
+	const int64_t m_cta = a.m_begin + (int64_t)blockIdx.x * T;
 
 	// ---- branch sums u_p[m] for the CTA's T steps
 	for (int item = tid; item < N * G; item += PFB_THREADS) {
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(PFB_THREADS) pfb_kernel(const PfbArgs a)
 	for (int item = tid; item < T * N; item += PFB_THREADS) {
 		const int f = item / N, k = item - f * N;
 		const int64_t m = m_cta + f;
-		if (m >= a.n_steps)
+		if (m >= a.m_end)
 			break;
 		float2 v = src[item];
 		if ((m & 1) && (k & 1))
@@ -153,8 +154,183 @@ __global__ void __launch_bounds__(PFB_THREADS) pfb_kernel(const PfbArgs a)
 	}
 }
 
+// ---- the bank for power-of-two channel counts (64 .. 2048) and 10 taps per branch -----------------------------------
+// Same arithmetic as pfb_kernel, a fifth of its instructions (10.8 k -> ~2 k warp-instructions per step at N = 1024):
+//   * branch sums: P = 10 is a compile-time constant (firdes.low_pass gives 9.64 N taps for every N), so the
+//     26-sample register window of 8 consecutive steps is loaded once and the 80 complex x real MACs are 80 packed
+//     FFMA2 with no register moves; the int16 scale rides on the taps; bounds are tested once per CTA;
+//   * FFT: register radix-16 butterflies (chan_fft.cuh), N / 16 threads per transform, in place in ONE padded
+//     shared-memory buffer (barrier between the loads and the stores of a round of rows), compile-time index
+//     arithmetic, the closing stage stores straight to HBM.  [T][N + N / 16] complex floats: 68 KB at N = 1024, three
+//     CTAs per SM (the two-buffer generic kernel: one).
+constexpr int PFB_P = 10;
+
+__device__ __forceinline__ void fma2p(float2 &c, float h, const float2 x)
+{
+	unsigned long long cc = *reinterpret_cast<unsigned long long *>(&c);
+	const float2 hh = make_float2(h, h);
+	asm("fma.rn.f32x2 %0, %1, %2, %0;"
+	    : "+l"(cc)
+	    : "l"(*reinterpret_cast<const unsigned long long *>(&hh)), "l"(*reinterpret_cast<const unsigned long long *>(&x)));
+	c = *reinterpret_cast<float2 *>(&cc);
+}
+
+template <int FMT> __device__ __forceinline__ float2 load_wide_raw(const void *x, int64_t i)
+{
+	if (FMT == 0)
+		return __ldg(reinterpret_cast<const float2 *>(x) + i);
+	const short2 v = __ldg(reinterpret_cast<const short2 *>(x) + i);
+	return make_float2((float)v.x, (float)v.y);          // 1 / 32768 is on the taps
+}
+
+template <int LOG2N> struct PfbFast {
+	typedef cfft::Plan<LOG2N> FP;
+	static constexpr int N = FP::N, D = N / 2;
+	static constexpr int T = 4096 / N > PFB_TM ? 4096 / N : PFB_TM;   // steps per CTA
+	static constexpr int G = T / PFB_TM;
+	static constexpr int RS = cfft::RowStride<N>::value;
+	static constexpr int RPR = PFB_THREADS / FP::TPR;   // rows of one round (PFB_THREADS / TPR threads-per-row)
+	static constexpr int ROUNDS = T / RPR;
+	static constexpr size_t SMEM = (size_t)T * RS * sizeof(float2);
+	static_assert(T % RPR == 0 && ROUNDS >= 1, "rows per round");
+};
+
+struct TwLdg {                             // e^{+j 2 pi t / N} from the plan's table (L1-resident)
+	const float2 *t;
+	__device__ __forceinline__ float2 operator()(int i) const { return __ldg(&t[i]); }
+};
+
+// one radix-16 stage S (NS = 16^S) over all T rows of the CTA, in place
+template <int LOG2N, int S> __device__ __forceinline__ void pfb_stage16(float2 *buf, const TwLdg tw, int tid)
+{
+	typedef PfbFast<LOG2N> K;
+	typedef cfft::Stage<K::N, cfft::Plan<LOG2N>::pow16(S), 16> St;
+	const int t = tid % K::FP::TPR, r0 = tid / K::FP::TPR;
+#pragma unroll 1
+	for (int rd = 0; rd < K::ROUNDS; rd++) {
+		float2 *row = buf + (size_t)(rd * K::RPR + r0) * K::RS;
+		float2 v[16];
+		St::read(row, t, tw, v);
+		__syncthreads();                   // every load of this round (and every store of the previous one) is done
+		St::write(row, t, v);
+	}
+	__syncthreads();
+}
+
+// closing stage: radix RL (16 / RL butterflies per thread), or the last radix-16 stage; stores to HBM, time-major,
+// odd channels of odd steps negated
+template <int LOG2N, int R, int NS> __device__ __forceinline__ void pfb_stage_out(const float2 *buf, const TwLdg tw, int tid,
+                                                                               const PfbArgs &a, int64_t m_cta)
+{
+	typedef PfbFast<LOG2N> K;
+	typedef cfft::Stage<K::N, NS, R> St;
+	const int t = tid % K::FP::TPR, r0 = tid / K::FP::TPR;
+#pragma unroll 1
+	for (int rd = 0; rd < K::ROUNDS; rd++) {
+		const int f = rd * K::RPR + r0;
+		const int64_t m = m_cta + f;
+		const float2 *row = buf + (size_t)f * K::RS;
+		if (m >= a.m_end)
+			continue;
+		float2 *dst = a.mid + m * K::N;
+		const bool odd = m & 1;
+#pragma unroll
+		for (int i = 0; i < 16 / R; i++) {
+			const int j = t + i * K::FP::TPR;
+			float2 v[R];
+			St::read(row, j, tw, v);
+#pragma unroll
+			for (int q2 = 0; q2 < R; q2++) {
+				const int k = St::out_index(j, q2);
+				dst[k] = (odd && (k & 1)) ? make_float2(-v[q2].x, -v[q2].y) : v[q2];
+			}
+		}
+	}
+}
+
+template <int LOG2N, int FMT>
+__global__ void __launch_bounds__(PFB_THREADS) pfb_fast_kernel(const PfbArgs a)
+{
+	typedef PfbFast<LOG2N> K;
+	constexpr int N = K::N, D = K::D, T = K::T;
+	constexpr int W = PFB_TM + 2 * (PFB_P - 1);           // samples of one branch that 8 steps touch
+	extern __shared__ __align__(16) float2 buf[];
+	const int tid = threadIdx.x;
+	const int64_t m_cta = a.m_begin + (int64_t)blockIdx.x * T;
+	const bool interior = (m_cta - 2 * (PFB_P - 1)) * D - (N - 1) >= 0 && (m_cta + T - 1) * D < a.n_wide;
+	const float scale = FMT == 0 ? 1.0f : 1.0f / 32768.0f;
+
+	// ---- branch sums: item = (branch p, group of 8 steps)
+#pragma unroll 1
+	for (int item = tid; item < N * K::G; item += PFB_THREADS) {
+		const int p = item & (N - 1), g = item >> LOG2N;
+		const int64_t m0 = m_cta + g * PFB_TM;
+		const int64_t base = (m0 - 2 * (PFB_P - 1)) * D - p;   // sample of window slot 0; slot r is r D further
+		float2 xs[W];
+		if (interior) {
+#pragma unroll
+			for (int r = 0; r < W; r++)
+				xs[r] = load_wide_raw<FMT>(a.wide, base + (int64_t)r * D);
+		} else {
+#pragma unroll
+			for (int r = 0; r < W; r++) {
+				const int64_t i = base + (int64_t)r * D;
+				xs[r] = (i >= 0 && i < a.n_wide) ? load_wide_raw<FMT>(a.wide, i) : make_float2(0.0f, 0.0f);
+			}
+		}
+		float2 acc[PFB_TM];
+#pragma unroll
+		for (int i = 0; i < PFB_TM; i++)
+			acc[i] = make_float2(0.0f, 0.0f);
+#pragma unroll
+		for (int q = 0; q < PFB_P; q++) {
+			const float h = __ldg(&a.taps[p + q * N]) * scale;
+#pragma unroll
+			for (int i = 0; i < PFB_TM; i++)
+				fma2p(acc[i], h, xs[i - 2 * q + 2 * (PFB_P - 1)]);
+		}
+#pragma unroll
+		for (int i = 0; i < PFB_TM; i++)
+			buf[(size_t)(g * PFB_TM + i) * K::RS + cfft::pad(p)] = acc[i];
+	}
+	__syncthreads();
+
+	// ---- T reverse FFTs
+	const TwLdg tw = {a.twiddle};
+	constexpr int N16 = K::FP::N16, RL = K::FP::RLAST;
+	if constexpr (RL > 1) {
+		if constexpr (N16 >= 1) pfb_stage16<LOG2N, 0>(buf, tw, tid);
+		if constexpr (N16 >= 2) pfb_stage16<LOG2N, 1>(buf, tw, tid);
+		constexpr int NS = cfft::Plan<LOG2N>::pow16(N16);
+		pfb_stage_out<LOG2N, RL, NS>(buf, tw, tid, a, m_cta);
+	} else {
+		if constexpr (N16 >= 2) pfb_stage16<LOG2N, 0>(buf, tw, tid);
+		if constexpr (N16 >= 3) pfb_stage16<LOG2N, 1>(buf, tw, tid);
+		constexpr int NS = cfft::Plan<LOG2N>::pow16(N16 - 1);
+		pfb_stage_out<LOG2N, 16, NS>(buf, tw, tid, a, m_cta);
+	}
+}
+
 // ---- arbitrary resampler -------------------------------------------------------------------------------------------
-constexpr int RS_T = 256, RS_CH = 64, RS_TO = 64;
+// Tile: 64 channels x 64 outputs per CTA.  A warp takes FOUR consecutive outputs at a time for two channels per lane:
+// the outputs' input spans overlap almost completely (1.5 outputs per input step at sps 4), so one 16-byte load of an
+// input row serves eight complex x real MACs.  The four outputs' taps - filter phase j, derivative weight acc, each
+// shifted by the output's own newest input step - are merged per group into one table [row][output] in shared memory,
+// each value stored twice so that a 16-byte load is two ready-made FFMA2 operands: 3 loads + 8 FFMA2 per row instead
+// of 8 loads + 16 FMA.
+constexpr int RS_T = 256, RS_CH = 64, RS_TO = 64, RS_K = 4;
+
+__device__ __forceinline__ void fma2u(unsigned long long &c, unsigned long long k, unsigned long long x)
+{
+	asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(k), "l"(x));
+}
+
+__device__ __forceinline__ float2 unpack2(unsigned long long v)
+{
+	float2 r;
+	asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+	return r;
+}
 
 __global__ void __launch_bounds__(RS_T) resamp_kernel(const ResampArgs a)
 {
@@ -165,12 +341,12 @@ __global__ void __launch_bounds__(RS_T) resamp_kernel(const ResampArgs a)
 	float2 *out_tile = in_tile + (size_t)a.rows_max * RS_CH; // [RS_CH][RS_TO + 1]
 	float *filt = (float *)(out_tile + RS_CH * (RS_TO + 1)); // [32][tpf], then dfilt [32][tpf]
 	float *dfilt = filt + 32 * tpf;
-	float *comb = dfilt + 32 * tpf;                         // [warps][tpf] taps of the output a warp is working on
+	float2 *comb = (float2 *)(dfilt + 32 * tpf) + (size_t)warp * a.span_max * RS_K;   // [warps][span_max][RS_K] (k, k)
 	__shared__ int ch_idx[RS_CH];
 
-	const int64_t n0 = (int64_t)blockIdx.x * RS_TO;
+	const int64_t n0 = a.n_begin + (int64_t)blockIdx.x * RS_TO;
 	const int c0 = blockIdx.y * RS_CH;
-	const int n_here = (int)min((int64_t)RS_TO, a.n_out - n0);
+	const int n_here = (int)min((int64_t)RS_TO, a.n_end - n0);
 	for (int i = tid; i < 32 * tpf; i += RS_T) {
 		filt[i] = __ldg(&a.filt[i]);
 		dfilt[i] = __ldg(&a.dfilt[i]);
@@ -181,37 +357,69 @@ __global__ void __launch_bounds__(RS_T) resamp_kernel(const ResampArgs a)
 	const int64_t row_lo = (int64_t)__ldg(&a.sched_i[n0]) - (tpf - 1);
 	const int rows = (int)(row_hi - row_lo + 1);
 	__syncthreads();
-	for (int item = tid; item < rows * RS_CH; item += RS_T) {
-		const int rr = item / RS_CH, c = item - rr * RS_CH;
-		const int64_t row = row_lo + rr;
-		const int k = ch_idx[c];
-		in_tile[item] = (row >= 0 && row < a.n_steps && k >= 0) ? __ldg(&a.mid[row * a.n_chans + k]) : make_float2(0.0f, 0.0f);
+	if (a.chan_idx == nullptr && c0 + RS_CH <= a.n_wanted && row_lo >= 0 && row_hi < a.n_steps) {
+		// whole rows of 64 consecutive channels: 16-byte loads
+		const float4 *src = reinterpret_cast<const float4 *>(a.mid + row_lo * a.n_chans + c0);
+		float4 *dst = reinterpret_cast<float4 *>(in_tile);
+		const int stride4 = a.n_chans >> 1;
+		for (int item = tid; item < rows * (RS_CH / 2); item += RS_T) {
+			const int rr = item / (RS_CH / 2), c = item - rr * (RS_CH / 2);
+			dst[item] = __ldg(&src[(size_t)rr * stride4 + c]);
+		}
+	} else {
+		for (int item = tid; item < rows * RS_CH; item += RS_T) {
+			const int rr = item / RS_CH, c = item - rr * RS_CH;
+			const int64_t row = row_lo + rr;
+			const int k = ch_idx[c];
+			in_tile[item] = (row >= 0 && row < a.n_steps && k >= 0) ? __ldg(&a.mid[row * a.n_chans + k]) : make_float2(0.0f, 0.0f);
+		}
 	}
 	__syncthreads();
 
-	float *cw = comb + warp * tpf;
-	for (int o = warp; o < n_here; o += RS_T / 32) {
-		const int64_t n = n0 + o;
-		const int j = a.sched_j[n];
-		const float acc = a.sched_acc[n];
-		const int base = (int)(a.sched_i[n] - row_lo);      // row of x[i]; taps walk downwards
-		__syncwarp();
-		for (int t = lane; t < tpf; t += 32)
-			cw[t] = fmaf(acc, dfilt[j * tpf + t], filt[j * tpf + t]);
-		__syncwarp();
-		float4 s = make_float4(0.0f, 0.0f, 0.0f, 0.0f);     // channels 2 lane, 2 lane + 1
-		const float4 *rowp = reinterpret_cast<const float4 *>(in_tile) + lane;
-#pragma unroll 6
-		for (int t = 0; t < tpf; t++) {
-			const float4 x = rowp[(size_t)(base - t) * (RS_CH / 2)];
-			const float c = cw[t];
-			s.x = fmaf(c, x.x, s.x);
-			s.y = fmaf(c, x.y, s.y);
-			s.z = fmaf(c, x.z, s.z);
-			s.w = fmaf(c, x.w, s.w);
+	const int oo = lane & (RS_K - 1);                       // the output of the group whose taps this lane merges
+	for (int o0 = warp * RS_K; o0 < n_here; o0 += (RS_T / 32) * RS_K) {
+		const int64_t n = n0 + o0;
+		const int cnt = min(RS_K, n_here - o0);
+		const int b_last = (int)(__ldg(&a.sched_i[n + cnt - 1]) - row_lo);   // newest row any of the outputs reads
+		const int span = b_last - (int)(__ldg(&a.sched_i[n]) - row_lo) + tpf; // rows b_last, b_last - 1, ... the group touches
+		{
+			const bool have = oo < cnt;
+			const int j = have ? a.sched_j[n + oo] : 0;
+			const float acc = have ? a.sched_acc[n + oo] : 0.0f;
+			const int shift = have ? b_last - (int)(__ldg(&a.sched_i[n + oo]) - row_lo) : 0;
+			__syncwarp();
+			for (int e = lane; e < span * RS_K; e += 32) {      // e & 3 == oo
+				const int t = (e >> 2) - shift;                 // tap of output oo that meets row b_last - (e >> 2)
+				const float k = (have && t >= 0 && t < tpf) ? fmaf(acc, dfilt[j * tpf + t], filt[j * tpf + t]) : 0.0f;
+				comb[e] = make_float2(k, k);
+			}
+			__syncwarp();
 		}
-		out_tile[(2 * lane) * (RS_TO + 1) + o] = make_float2(s.x, s.y);
-		out_tile[(2 * lane + 1) * (RS_TO + 1) + o] = make_float2(s.z, s.w);
+		unsigned long long s[RS_K][2];                           // [output][channel 2 lane, 2 lane + 1]
+#pragma unroll
+		for (int o = 0; o < RS_K; o++)
+			s[o][0] = s[o][1] = 0ull;
+		const ulonglong2 *rowp = reinterpret_cast<const ulonglong2 *>(in_tile) + (size_t)b_last * (RS_CH / 2) + lane;
+		const ulonglong2 *cp = reinterpret_cast<const ulonglong2 *>(comb);
+#pragma unroll 4
+		for (int r = 0; r < span; r++) {
+			const ulonglong2 x = *(rowp - (size_t)r * (RS_CH / 2));
+			const ulonglong2 k01 = cp[2 * r], k23 = cp[2 * r + 1];
+			fma2u(s[0][0], k01.x, x.x);
+			fma2u(s[0][1], k01.x, x.y);
+			fma2u(s[1][0], k01.y, x.x);
+			fma2u(s[1][1], k01.y, x.y);
+			fma2u(s[2][0], k23.x, x.x);
+			fma2u(s[2][1], k23.x, x.y);
+			fma2u(s[3][0], k23.y, x.x);
+			fma2u(s[3][1], k23.y, x.y);
+		}
+#pragma unroll
+		for (int o = 0; o < RS_K; o++)
+			if (o < cnt) {
+				out_tile[(2 * lane) * (RS_TO + 1) + o0 + o] = unpack2(s[o][0]);
+				out_tile[(2 * lane + 1) * (RS_TO + 1) + o0 + o] = unpack2(s[o][1]);
+			}
 	}
 	__syncthreads();
 	for (int item = tid; item < RS_CH * RS_TO; item += RS_T) {
@@ -313,19 +521,60 @@ int pfb_groups(int n_chans)
 	return g;
 }
 
+template <int LOG2N> cudaError_t launch_pfb_fast(const PfbArgs &a, int fmt, cudaStream_t st, int dev)
+{
+	typedef PfbFast<LOG2N> K;
+	static std::atomic<int> attr_done[64][2];
+	auto *fn = fmt == 0 ? pfb_fast_kernel<LOG2N, 0> : pfb_fast_kernel<LOG2N, 1>;
+	{
+		GMR1_INIT_LOCK();
+		if (dev >= 64 || !attr_done[dev][fmt].load()) {
+			cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM);
+			if (e != cudaSuccess)
+				return e;
+			if (dev < 64)
+				attr_done[dev][fmt].store(1);
+		}
+	}
+	const int64_t grid = (a.m_end - a.m_begin + K::T - 1) / K::T;
+	fn<<<(unsigned)grid, PFB_THREADS, K::SMEM, st>>>(a);
+	return cudaGetLastError();
+}
+
+// which kernel a plan gets: 1 = pfb_fast_kernel (power-of-two bank, 64 .. 2048 channels, 10 taps per branch)
+int pfb_is_fast(int n_chans, int taps_per_branch)
+{
+	return taps_per_branch == PFB_P && n_chans >= 64 && n_chans <= 2048 && (n_chans & (n_chans - 1)) == 0;
+}
+
+static std::atomic<int> g_pfb_force_generic{0};
+void pfb_force_generic(int on) { g_pfb_force_generic.store(on); }
+
 cudaError_t launch_pfb(const PfbArgs &a0, int fmt, cudaStream_t st)
 {
 	PfbArgs a = a0;
-	if (a.n_steps <= 0)
+	if (a.m_end > a.n_steps)
+		a.m_end = a.n_steps;
+	if (a.m_end <= a.m_begin)
 		return cudaSuccess;
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (pfb_is_fast(a.n_chans, a.taps_per_branch) && !g_pfb_force_generic.load()) {
+		switch (a.n_chans) {
+		case 64:   return launch_pfb_fast<6>(a, fmt, st, dev);
+		case 128:  return launch_pfb_fast<7>(a, fmt, st, dev);
+		case 256:  return launch_pfb_fast<8>(a, fmt, st, dev);
+		case 512:  return launch_pfb_fast<9>(a, fmt, st, dev);
+		case 1024: return launch_pfb_fast<10>(a, fmt, st, dev);
+		default:   return launch_pfb_fast<11>(a, fmt, st, dev);
+		}
+	}
 	a.groups = pfb_groups(a.n_chans);
 	const int T = a.groups * PFB_TM;
 	const size_t smem = 2 * (size_t)T * a.n_chans * sizeof(float2);
 	if (smem > 200 * 1024)
 		return cudaErrorNotSupported;
 	static std::atomic<size_t> attr_max[64][2];
-	int dev = 0;
-	cudaGetDevice(&dev);
 	auto *fn = fmt == 0 ? pfb_kernel<0> : pfb_kernel<1>;
 	{
 		GMR1_INIT_LOCK();
@@ -336,24 +585,30 @@ cudaError_t launch_pfb(const PfbArgs &a0, int fmt, cudaStream_t st)
 			attr_max[dev][fmt].store(smem);
 		}
 	}
-	const int64_t grid = (a.n_steps + T - 1) / T;
+	const int64_t grid = (a.m_end - a.m_begin + T - 1) / T;
 	fn<<<(unsigned)grid, PFB_THREADS, smem, st>>>(a);
 	return cudaGetLastError();
 }
 
-size_t resamp_smem(int rows_max, int tpf)
+size_t resamp_smem(int rows_max, int span_max, int tpf)
 {
-	return ((size_t)rows_max * RS_CH + (size_t)RS_CH * (RS_TO + 1)) * sizeof(float2) +
-	       ((size_t)64 * tpf + (size_t)(RS_T / 32) * tpf) * sizeof(float);
+	return ((size_t)rows_max * RS_CH + (size_t)RS_CH * (RS_TO + 1)) * sizeof(float2) + (size_t)64 * tpf * sizeof(float) +
+	       (size_t)(RS_T / 32) * span_max * RS_K * sizeof(float2);
 }
 
 int resamp_tile_outputs() { return RS_TO; }
+int resamp_group_outputs() { return RS_K; }
 
-cudaError_t launch_resamp(const ResampArgs &a, cudaStream_t st)
+cudaError_t launch_resamp(const ResampArgs &a0, cudaStream_t st)
 {
-	if (a.n_out <= 0 || a.n_wanted <= 0)
+	ResampArgs a = a0;
+	if (a.n_end > a.n_out)
+		a.n_end = a.n_out;
+	if (a.n_end <= a.n_begin || a.n_wanted <= 0)
 		return cudaSuccess;
-	const size_t smem = resamp_smem(a.rows_max, a.tpf);
+	if (a.n_begin % RS_TO)
+		return cudaErrorInvalidValue;
+	const size_t smem = resamp_smem(a.rows_max, a.span_max, a.tpf);
 	if (smem > 200 * 1024)
 		return cudaErrorNotSupported;
 	static std::atomic<size_t> attr_max[64];
@@ -368,7 +623,7 @@ cudaError_t launch_resamp(const ResampArgs &a, cudaStream_t st)
 			attr_max[dev].store(smem);
 		}
 	}
-	dim3 grid((unsigned)((a.n_out + RS_TO - 1) / RS_TO), (unsigned)((a.n_wanted + RS_CH - 1) / RS_CH));
+	dim3 grid((unsigned)((a.n_end - a.n_begin + RS_TO - 1) / RS_TO), (unsigned)((a.n_wanted + RS_CH - 1) / RS_CH));
 	resamp_kernel<<<grid, RS_T, smem, st>>>(a);
 	return cudaGetLastError();
 }

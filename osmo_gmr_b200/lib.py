@@ -89,6 +89,7 @@ class Lib:
         "gmr1b200_synth_wideband": [_P, _P, _L, _L, _P, _I, _F, _F, ctypes.c_uint64, _P, _I, _L, _P],
         "gmr1b200_set_sync_accumulator_reset": [_I],
         "gmr1b200_set_demod_generic": [_I],
+        "gmr1b200_set_chan_generic": [_I],
         "gmr1b200_set_rx_lockstep": [_I],
         "gmr1b200_rx_call_batch": [_P, _L, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
         "gmr1b200_pool_create": [_P, _I, _I, _L, _P],

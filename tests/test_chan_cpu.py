@@ -120,3 +120,27 @@ def test_product_plan_matches_the_oracle():
     for bad in ((15, 4), (0, 4), (2 * 37, 4), (8192, 4), (16, 0)):
         rc, h = plan_of(L, *bad)
         assert rc < 0 and b"chan_create" in L.c.gmr1b200_last_error()
+
+
+def test_register_butterfly_fft_on_the_cpu():
+    """chan_fft.cuh (the radix-16 register butterflies and Stockham index arithmetic of pfb_fast_kernel and of the
+    FCCH search) compiled for the host by tests/emu/chan_emu.cpp and run with the kernels' barrier structure: equals
+    numpy's reverse FFT for every size the kernels use (stage plans 16, 16x2 ... 16x16x16x2)."""
+    import ctypes
+    import subprocess
+    emu_dir = os.path.join(ROOT, "tests", "emu")
+    so, src = os.path.join(emu_dir, "libchan_emu.so"), os.path.join(emu_dir, "chan_emu.cpp")
+    hdr = os.path.join(ROOT, "osmo_gmr_b200", "csrc", "chan_fft.cuh")
+    if not os.path.exists(so) or max(os.path.getmtime(src), os.path.getmtime(hdr)) > os.path.getmtime(so):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-Wno-unknown-pragmas",
+                               "-I" + os.path.dirname(hdr), "-o", so, src])
+    emu = ctypes.CDLL(so)
+    rng = np.random.default_rng(3)
+    for log2n in range(4, 14):
+        n = 1 << log2n
+        x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+        y = np.zeros(n, np.complex64)
+        assert emu.chan_emu_fft(log2n, x.ctypes.data_as(ctypes.c_void_p), y.ctypes.data_as(ctypes.c_void_p)) == 0
+        want = np.fft.ifft(x.astype(np.complex128)) * n
+        assert np.abs(y - want).max() < 5e-7 * np.abs(want).max()
+    assert emu.chan_emu_fft(3, None, None) == -1

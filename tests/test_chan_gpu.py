@@ -60,6 +60,64 @@ def test_bank_and_resampler_match_the_oracle(gpu_lib, n_chans):
     L.c.gmr1b200_chan_destroy(h)
 
 
+@pytest.mark.parametrize("n_chans", [64, 128, 256, 512, 1024, 2048])
+def test_power_of_two_banks_fast_kernel(gpu_lib, n_chans):
+    """Banks of 64 .. 2048 channels run on pfb_fast_kernel (register radix-16 butterflies, chan_fft.cuh; stage plans
+    16x4, 16x8, 16x16, 16x16x2, 16x16x4, 16x16x8): against the oracle and against the generic kernel on the same input,
+    complex-float and int16 recordings, a length that is not a multiple of the kernel's step tile, all channels."""
+    L = gpu_lib
+    rng = np.random.default_rng(n_chans)
+    n_wide = n_chans * 150 + n_chans // 2 + 3
+    x = (rng.standard_normal(n_wide) + 1j * rng.standard_normal(n_wide)).astype(np.complex64)
+    pl = cp.Plan(n_chans)
+    h = make_plan(L, n_chans)
+    chans = sorted(set([0, 1, 5, n_chans // 2 - 1, n_chans // 2, n_chans - 2, n_chans - 1]))
+    got = channelize(L, h, x, 0, chans)
+    want = cp.channelize(x, pl, chans)
+    assert got.shape == want.shape and got.shape[1] > 400
+    scale = np.abs(want).max()
+    assert np.abs(got - want).max() < 3e-5 * scale
+    every = channelize(L, h, x, 0, list(range(n_chans)))
+    assert L.c.gmr1b200_set_chan_generic(1) == 0
+    try:
+        generic = channelize(L, h, x, 0, list(range(n_chans)))
+    finally:
+        assert L.c.gmr1b200_set_chan_generic(0) == 1
+    assert np.abs(every - generic).max() < 1e-5 * scale and np.array_equal(every[chans], got)
+    xi = rng.integers(-30000, 30000, (n_wide, 2), dtype=np.int16)
+    xf = (xi.astype(np.float32) / 32768.0).view(np.complex64)[:, 0]
+    a = channelize(L, h, xi, 1, chans)
+    b = channelize(L, h, xf, 0, chans)
+    assert np.abs(a - b).max() < 1e-6 * np.abs(b).max()     # the int16 scale rides on the taps: same up to rounding
+    L.c.gmr1b200_chan_destroy(h)
+
+
+def test_host_recording_travels_in_pieces(gpu_lib):
+    """A host recording of 12 MB is copied in 6 pieces under the kernels of the pieces before; the streams are bit for
+    bit those of the same recording processed in one piece from device memory.  Pinned and pageable host memory."""
+    import torch
+    L = gpu_lib
+    n_chans, n_wide = 256, 3_000_000 + 77
+    rng = np.random.default_rng(12)
+    xi = rng.integers(-20000, 20000, (n_wide, 2), dtype=np.int16)
+    h = make_plan(L, n_chans)
+    chans = [0, 3, 127, 128, 255]
+    n_out = L.c.gmr1b200_chan_out_len(h, n_wide)
+    didx = torch.tensor(chans, dtype=torch.int32, device="cuda")
+    one = torch.zeros((len(chans), n_out, 2), dtype=torch.float32, device="cuda")
+    L.call("gmr1b200_channelize", h.value, torch.from_numpy(xi).cuda(), 1, n_wide, didx, len(chans), one, n_out, None)
+    torch.cuda.synchronize()
+    pinned = torch.from_numpy(xi).pin_memory()
+    st = torch.cuda.Stream()
+    for src in (pinned, xi):
+        pieces = torch.zeros_like(one)
+        L.call("gmr1b200_channelize", h.value, src, 1, n_wide, didx, len(chans), pieces, n_out, st.cuda_stream)
+        st.synchronize()
+        assert torch.equal(pieces, one)
+    assert float(one.abs().max()) > 0.01
+    L.c.gmr1b200_chan_destroy(h)
+
+
 def test_int16_recordings_and_device_pointers(gpu_lib):
     import torch
     L = gpu_lib
