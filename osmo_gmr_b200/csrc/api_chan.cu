@@ -185,7 +185,7 @@ int gmr1b200_channelize(void *plan, const void *wide, int iq_format, int64_t n_w
 	int64_t n_out, n_steps;
 	ChanPlan::Dev *d = nullptr;
 	Plan::Feed *feed = nullptr;
-	int rows_max = 0, span_max = 0;
+	int rows_max = 0, span_max = 0, to = 64;
 	const bool wide_on_host = host_pointer(wide);
 	const size_t samp_bytes = iq_format == 0 ? sizeof(float2) : 2 * sizeof(int16_t);
 	// chunks: a host recording travels in up to 16 pieces (>= 2 MB each) so that the bank and the resampler of piece c
@@ -204,17 +204,19 @@ int gmr1b200_channelize(void *plan, const void *wide, int iq_format, int64_t n_w
 			e = plan_feed(*pl, &feed);
 		if (e != cudaSuccess)
 			return cuda_rc(e, "channelize: table upload");
-		const int to = resamp_tile_outputs(), go = resamp_group_outputs();
-		for (int64_t n0 = 0; n0 < n_out; n0 += to) {
-			const int64_t n1 = (n0 + to < n_out ? n0 + to : n_out) - 1;
-			const int rows = p.sched_i[n1] - p.sched_i[n0] + p.tpf;
-			rows_max = rows > rows_max ? rows : rows_max;
-		}
-		for (int64_t n0 = 0; n0 < n_out; n0 += go) {
-			const int64_t n1 = (n0 + go < n_out ? n0 + go : n_out) - 1;
-			const int span = p.sched_i[n1] - p.sched_i[n0] + p.tpf;
-			span_max = span > span_max ? span : span_max;
-		}
+		const int go = resamp_group_outputs();
+		auto span_of = [&](int step) {
+			int m = 0;
+			for (int64_t n0 = 0; n0 < n_out; n0 += step) {
+				const int64_t n1 = (n0 + step < n_out ? n0 + step : n_out) - 1;
+				const int rows = p.sched_i[n1] - p.sched_i[n0] + p.tpf;
+				m = rows > m ? rows : m;
+			}
+			return m;
+		};
+		span_max = span_of(go);
+		to = resamp_tile_outputs(span_of(64), span_max, p.tpf);
+		rows_max = span_of(to);
 		int pieces = 1;
 		if (wide_on_host) {
 			pieces = (int)((size_t)n_wide * samp_bytes / (2u << 20));
@@ -263,7 +265,7 @@ int gmr1b200_channelize(void *plan, const void *wide, int iq_format, int64_t n_w
 	ResampArgs ra = {};
 	ra.mid = mid; ra.n_steps = n_steps; ra.n_chans = p.n_chans; ra.chan_idx = d_idx; ra.n_wanted = n_wanted;
 	ra.sched_i = d->sched_i; ra.sched_j = d->sched_j; ra.sched_acc = d->sched_acc; ra.filt = d->filt; ra.dfilt = d->dfilt;
-	ra.tpf = p.tpf; ra.rows_max = rows_max; ra.span_max = span_max; ra.out = d_out; ra.out_stride = out_stride; ra.n_out = n_out;
+	ra.tpf = p.tpf; ra.rows_max = rows_max; ra.span_max = span_max; ra.tile_out = to; ra.out = d_out; ra.out_stride = out_stride; ra.n_out = n_out;
 	cudaError_t e = cudaSuccess;
 	if (wide_on_host) {                    // the copy stream starts behind the allocation of its target
 		cudaEvent_t ev = feed->ev[feed->next++ % N_EV];

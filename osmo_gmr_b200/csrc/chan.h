@@ -34,10 +34,11 @@ struct ResampArgs {
 	const uint8_t *sched_j;                // [n_out] filter phase
 	const float   *sched_acc;              // [n_out] weight of the derivative filter
 	const float   *filt, *dfilt;           // [32][tpf]
-	int32_t        tpf, rows_max, span_max; // taps per phase; input rows of a 64-output tile / of a 4-output group, at most
+	int32_t        tpf, rows_max, span_max; // taps per phase; input rows of a tile / of an 8-output group, at most
+	int32_t        tile_out;               // outputs per tile: resamp_tile_outputs()
 	float2        *out;                    // [n_wanted][out_stride]
 	int64_t        out_stride, n_out;
-	int64_t        n_begin, n_end;         // the outputs this launch makes (n_begin a multiple of the tile, 64)
+	int64_t        n_begin, n_end;         // the outputs this launch makes (n_begin a multiple of tile_out)
 };
 
 struct WideSynthArgs {
@@ -55,8 +56,8 @@ struct WideSynthArgs {
 
 int pfb_groups(int n_chans);
 cudaError_t launch_pfb(const PfbArgs &a, int fmt, cudaStream_t st);
-size_t resamp_smem(int rows_max, int span_max, int tpf);
-int resamp_tile_outputs();
+// outputs per resampler tile (64, or 32 when 64 outputs span too many input rows for two CTAs per SM)
+int resamp_tile_outputs(int rows64, int span_max, int tpf);
 int resamp_group_outputs();
 int pfb_is_fast(int n_chans, int taps_per_branch);
 void pfb_force_generic(int on);          // tests: run the generic kernel where the fast one would

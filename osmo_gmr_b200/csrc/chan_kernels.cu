@@ -312,13 +312,15 @@ __global__ void __launch_bounds__(PFB_THREADS) pfb_fast_kernel(const PfbArgs a)
 }
 
 // ---- arbitrary resampler -------------------------------------------------------------------------------------------
-// Tile: 64 channels x 64 outputs per CTA.  A warp takes FOUR consecutive outputs at a time for two channels per lane:
-// the outputs' input spans overlap almost completely (1.5 outputs per input step at sps 4), so one 16-byte load of an
-// input row serves eight complex x real MACs.  The four outputs' taps - filter phase j, derivative weight acc, each
+// Tile: 128 channels x 64 outputs per CTA.  A warp takes EIGHT consecutive outputs at a time for four channels per lane:
+// the outputs' input spans overlap almost completely (1.5 outputs per input step at sps 4), so two 16-byte loads of an
+// input row serve 32 complex x real MACs.  The eight outputs' taps - filter phase j, derivative weight acc, each
 // shifted by the output's own newest input step - are merged per group into one table [row][output] in shared memory,
-// each value stored twice so that a 16-byte load is two ready-made FFMA2 operands: 3 loads + 8 FFMA2 per row instead
-// of 8 loads + 16 FMA.
-constexpr int RS_T = 256, RS_CH = 64, RS_TO = 64, RS_K = 4;
+// each value stored twice so that a 16-byte load is two ready-made FFMA2 operands: 6 loads (12 shared-memory
+// wavefronts) + 32 FFMA2 per row.  (The first version - one output at a time, two channels per lane - needed 64
+// wavefronts for the same MACs and was bound by shared-memory bandwidth; four outputs x two channels: 24.)
+// The output tile is transposed through the memory of the input tile.
+constexpr int RS_CH = 128, RS_TO = 64, RS_K = 8;   // RS_TO: outputs of the standard tile; plans with long input spans use 32
 
 __device__ __forceinline__ void fma2u(unsigned long long &c, unsigned long long k, unsigned long long x)
 {
@@ -332,14 +334,17 @@ __device__ __forceinline__ float2 unpack2(unsigned long long v)
 	return r;
 }
 
-__global__ void __launch_bounds__(RS_T) resamp_kernel(const ResampArgs a)
+template <int TO>
+__global__ void __launch_bounds__(TO / RS_K * 32, 2) resamp_kernel(const ResampArgs a)
 {
+	constexpr int RS_T = TO / RS_K * 32, RS_TO = TO;       // one warp per group of RS_K outputs
 	extern __shared__ __align__(16) float2 sm[];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int tpf = a.tpf;
-	float2 *in_tile = sm;                                   // [rows_max][RS_CH]
-	float2 *out_tile = in_tile + (size_t)a.rows_max * RS_CH; // [RS_CH][RS_TO + 1]
-	float *filt = (float *)(out_tile + RS_CH * (RS_TO + 1)); // [32][tpf], then dfilt [32][tpf]
+	float2 *in_tile = sm;                                   // [rows_max][RS_CH]; later the output tile [RS_CH][RS_TO + 1]
+	float2 *out_tile = sm;
+	const size_t tile_elems = max((size_t)a.rows_max * RS_CH, (size_t)RS_CH * (RS_TO + 1));
+	float *filt = (float *)(sm + ((tile_elems + 1) & ~(size_t)1)); // [32][tpf], then dfilt [32][tpf]
 	float *dfilt = filt + 32 * tpf;
 	float2 *comb = (float2 *)(dfilt + 32 * tpf) + (size_t)warp * a.span_max * RS_K;   // [warps][span_max][RS_K] (k, k)
 	__shared__ int ch_idx[RS_CH];
@@ -358,7 +363,7 @@ __global__ void __launch_bounds__(RS_T) resamp_kernel(const ResampArgs a)
 	const int rows = (int)(row_hi - row_lo + 1);
 	__syncthreads();
 	if (a.chan_idx == nullptr && c0 + RS_CH <= a.n_wanted && row_lo >= 0 && row_hi < a.n_steps) {
-		// whole rows of 64 consecutive channels: 16-byte loads
+		// whole rows of 128 consecutive channels: 16-byte loads
 		const float4 *src = reinterpret_cast<const float4 *>(a.mid + row_lo * a.n_chans + c0);
 		float4 *dst = reinterpret_cast<float4 *>(in_tile);
 		const int stride4 = a.n_chans >> 1;
@@ -376,10 +381,16 @@ __global__ void __launch_bounds__(RS_T) resamp_kernel(const ResampArgs a)
 	}
 	__syncthreads();
 
+	// one group of RS_K outputs per warp (RS_TO / RS_K == warps): channels 2 lane, 2 lane + 1, 64 + 2 lane, 65 + 2 lane
+	const int o0 = warp * RS_K;
 	const int oo = lane & (RS_K - 1);                       // the output of the group whose taps this lane merges
-	for (int o0 = warp * RS_K; o0 < n_here; o0 += (RS_T / 32) * RS_K) {
+	unsigned long long s[RS_K][4];
+#pragma unroll
+	for (int o = 0; o < RS_K; o++)
+		s[o][0] = s[o][1] = s[o][2] = s[o][3] = 0ull;
+	const int cnt = min(RS_K, n_here - o0);
+	if (cnt > 0) {
 		const int64_t n = n0 + o0;
-		const int cnt = min(RS_K, n_here - o0);
 		const int b_last = (int)(__ldg(&a.sched_i[n + cnt - 1]) - row_lo);   // newest row any of the outputs reads
 		const int span = b_last - (int)(__ldg(&a.sched_i[n]) - row_lo) + tpf; // rows b_last, b_last - 1, ... the group touches
 		{
@@ -387,40 +398,44 @@ __global__ void __launch_bounds__(RS_T) resamp_kernel(const ResampArgs a)
 			const int j = have ? a.sched_j[n + oo] : 0;
 			const float acc = have ? a.sched_acc[n + oo] : 0.0f;
 			const int shift = have ? b_last - (int)(__ldg(&a.sched_i[n + oo]) - row_lo) : 0;
-			__syncwarp();
-			for (int e = lane; e < span * RS_K; e += 32) {      // e & 3 == oo
-				const int t = (e >> 2) - shift;                 // tap of output oo that meets row b_last - (e >> 2)
-				const float k = (have && t >= 0 && t < tpf) ? fmaf(acc, dfilt[j * tpf + t], filt[j * tpf + t]) : 0.0f;
+			const float *fj = filt + j * tpf, *dj = dfilt + j * tpf;
+			for (int e = lane; e < span * RS_K; e += 32) {      // e % RS_K == oo
+				const int t = e / RS_K - shift;                 // tap of output oo that meets row b_last - e / RS_K
+				const float k = (have && t >= 0 && t < tpf) ? fmaf(acc, dj[t], fj[t]) : 0.0f;
 				comb[e] = make_float2(k, k);
 			}
 			__syncwarp();
 		}
-		unsigned long long s[RS_K][2];                           // [output][channel 2 lane, 2 lane + 1]
-#pragma unroll
-		for (int o = 0; o < RS_K; o++)
-			s[o][0] = s[o][1] = 0ull;
-		const ulonglong2 *rowp = reinterpret_cast<const ulonglong2 *>(in_tile) + (size_t)b_last * (RS_CH / 2) + lane;
+		const ulonglong2 *xp = reinterpret_cast<const ulonglong2 *>(in_tile) + (size_t)b_last * (RS_CH / 2) + lane;
 		const ulonglong2 *cp = reinterpret_cast<const ulonglong2 *>(comb);
-#pragma unroll 4
+#pragma unroll 2
 		for (int r = 0; r < span; r++) {
-			const ulonglong2 x = *(rowp - (size_t)r * (RS_CH / 2));
-			const ulonglong2 k01 = cp[2 * r], k23 = cp[2 * r + 1];
-			fma2u(s[0][0], k01.x, x.x);
-			fma2u(s[0][1], k01.x, x.y);
-			fma2u(s[1][0], k01.y, x.x);
-			fma2u(s[1][1], k01.y, x.y);
-			fma2u(s[2][0], k23.x, x.x);
-			fma2u(s[2][1], k23.x, x.y);
-			fma2u(s[3][0], k23.y, x.x);
-			fma2u(s[3][1], k23.y, x.y);
-		}
+			const ulonglong2 xa = xp[0], xb = xp[32];
+			xp -= RS_CH / 2;
 #pragma unroll
-		for (int o = 0; o < RS_K; o++)
-			if (o < cnt) {
-				out_tile[(2 * lane) * (RS_TO + 1) + o0 + o] = unpack2(s[o][0]);
-				out_tile[(2 * lane + 1) * (RS_TO + 1) + o0 + o] = unpack2(s[o][1]);
+			for (int h = 0; h < RS_K / 2; h++) {
+				const ulonglong2 k = cp[h];
+				fma2u(s[2 * h][0], k.x, xa.x);
+				fma2u(s[2 * h][1], k.x, xa.y);
+				fma2u(s[2 * h][2], k.x, xb.x);
+				fma2u(s[2 * h][3], k.x, xb.y);
+				fma2u(s[2 * h + 1][0], k.y, xa.x);
+				fma2u(s[2 * h + 1][1], k.y, xa.y);
+				fma2u(s[2 * h + 1][2], k.y, xb.x);
+				fma2u(s[2 * h + 1][3], k.y, xb.y);
 			}
+			cp += RS_K / 2;
+		}
 	}
+	__syncthreads();                                            // every warp is done with the input tile
+#pragma unroll
+	for (int o = 0; o < RS_K; o++)
+		if (o < cnt) {
+			out_tile[(2 * lane) * (RS_TO + 1) + o0 + o] = unpack2(s[o][0]);
+			out_tile[(2 * lane + 1) * (RS_TO + 1) + o0 + o] = unpack2(s[o][1]);
+			out_tile[(64 + 2 * lane) * (RS_TO + 1) + o0 + o] = unpack2(s[o][2]);
+			out_tile[(65 + 2 * lane) * (RS_TO + 1) + o0 + o] = unpack2(s[o][3]);
+		}
 	__syncthreads();
 	for (int item = tid; item < RS_CH * RS_TO; item += RS_T) {
 		const int c = item / RS_TO, o = item - c * RS_TO;
@@ -590,13 +605,20 @@ cudaError_t launch_pfb(const PfbArgs &a0, int fmt, cudaStream_t st)
 	return cudaGetLastError();
 }
 
-size_t resamp_smem(int rows_max, int span_max, int tpf)
+static size_t resamp_smem_to(int to, int rows_max, int span_max, int tpf)
 {
-	return ((size_t)rows_max * RS_CH + (size_t)RS_CH * (RS_TO + 1)) * sizeof(float2) + (size_t)64 * tpf * sizeof(float) +
-	       (size_t)(RS_T / 32) * span_max * RS_K * sizeof(float2);
+	size_t tile = (size_t)rows_max * RS_CH > (size_t)RS_CH * (to + 1) ? (size_t)rows_max * RS_CH : (size_t)RS_CH * (to + 1);
+	tile = (tile + 1) & ~(size_t)1;
+	return tile * sizeof(float2) + (size_t)64 * tpf * sizeof(float) + (size_t)(to / RS_K) * span_max * RS_K * sizeof(float2);
 }
 
-int resamp_tile_outputs() { return RS_TO; }
+constexpr size_t RS_SMEM_MAX = 110 * 1024;                  // two CTAs per SM
+
+// outputs per tile for a plan whose 64-output tiles span rows64 input rows
+int resamp_tile_outputs(int rows64, int span_max, int tpf)
+{
+	return resamp_smem_to(RS_TO, rows64, span_max, tpf) <= RS_SMEM_MAX ? RS_TO : RS_TO / 2;
+}
 int resamp_group_outputs() { return RS_K; }
 
 cudaError_t launch_resamp(const ResampArgs &a0, cudaStream_t st)
@@ -606,25 +628,28 @@ cudaError_t launch_resamp(const ResampArgs &a0, cudaStream_t st)
 		a.n_end = a.n_out;
 	if (a.n_end <= a.n_begin || a.n_wanted <= 0)
 		return cudaSuccess;
-	if (a.n_begin % RS_TO)
+	const int to = a.tile_out;
+	if ((to != RS_TO && to != RS_TO / 2) || a.n_begin % to)
 		return cudaErrorInvalidValue;
-	const size_t smem = resamp_smem(a.rows_max, a.span_max, a.tpf);
-	if (smem > 200 * 1024)
+	const size_t smem = resamp_smem_to(to, a.rows_max, a.span_max, a.tpf);
+	if (smem > 220 * 1024)
 		return cudaErrorNotSupported;
-	static std::atomic<size_t> attr_max[64];
+	static std::atomic<size_t> attr_max[64][2];
 	int dev = 0;
 	cudaGetDevice(&dev);
+	auto *fn = to == RS_TO ? resamp_kernel<RS_TO> : resamp_kernel<RS_TO / 2>;
 	{
 		GMR1_INIT_LOCK();
-		if (dev < 64 && attr_max[dev].load() < smem) {
-			cudaError_t e = cudaFuncSetAttribute(resamp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (dev >= 64 || attr_max[dev][to == RS_TO].load() < smem) {
+			cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 			if (e != cudaSuccess)
 				return e;
-			attr_max[dev].store(smem);
+			if (dev < 64)
+				attr_max[dev][to == RS_TO].store(smem);
 		}
 	}
-	dim3 grid((unsigned)((a.n_end - a.n_begin + RS_TO - 1) / RS_TO), (unsigned)((a.n_wanted + RS_CH - 1) / RS_CH));
-	resamp_kernel<<<grid, RS_T, smem, st>>>(a);
+	dim3 grid((unsigned)((a.n_end - a.n_begin + to - 1) / to), (unsigned)((a.n_wanted + RS_CH - 1) / RS_CH));
+	fn<<<grid, to / RS_K * 32, smem, st>>>(a);
 	return cudaGetLastError();
 }
 
