@@ -350,7 +350,7 @@ def run_configs(L, torch, dev, peak_gbs, cores, scale, reps, n_check):
 # ------------------------------------------------------------------------------------------------
 # the end-to-end step of several GPUs from ONE process (library device pool, csrc/api_multi.cu)
 # ------------------------------------------------------------------------------------------------
-def run_wideband(L, torch, dev, n_arfcn, per_arfcn, steps, seed=4242):
+def run_wideband(L, torch, dev, n_arfcn, per_arfcn, steps, seed=4242, world=1, dist=None):
     """SURVEY 8f N3 in front of the headline workload: the SAME receive work (one FCCH acquisition per ARFCN + per_arfcn
     BCCH / DC6 bursts per ARFCN, demod + decode), but the input is ONE wideband recording of all ARFCNs (int16 I/Q at
     n_arfcn x 31.25 kS/s, what an SDR front end delivers) instead of one 4x-oversampled complex-float stream per ARFCN:
@@ -461,9 +461,21 @@ def run_wideband(L, torch, dev, n_arfcn, per_arfcn, steps, seed=4242):
             h_f[1].copy_(f_ferr, non_blocking=True)
         st.synchronize()
 
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def rank_max(v):                       # a time of the whole job = the slowest rank's
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
     for _ in range(3):
         receive()
-    torch.cuda.synchronize()
+    barrier()
     launches0 = L.kernel_launches()
     timers = []
     a, b = ev(), ev()
@@ -471,20 +483,20 @@ def run_wideband(L, torch, dev, n_arfcn, per_arfcn, steps, seed=4242):
     for _ in range(steps):
         receive(timers)
     b.record(st)
-    torch.cuda.synchronize()
+    barrier()
     launches = (L.kernel_launches() - launches0) / steps
-    dev_ms = a.elapsed_time(b) / steps
+    dev_ms = rank_max(a.elapsed_time(b) / steps)
     part = {}
     for marks in timers:
         for (_, e0), (name, e1) in zip(marks[:-1], marks[1:]):
             part[name] = part.get(name, 0.0) + e0.elapsed_time(e1) / steps
     e2e()
-    torch.cuda.synchronize()
+    barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
         e2e()
-    torch.cuda.synchronize()
-    e2e_ms = 1e3 * (time.perf_counter() - t0) / steps
+    barrier()
+    e2e_ms = rank_max(1e3 * (time.perf_counter() - t0) / steps)
     # what came out: payloads against what was sent, FCCH positions against where the chirps were put
     nb = sum(n_arfcn * n_b[kk] for kk in n_b)
     ok = sum(int((res[kk]["h_crc"] == 0).sum()) for kk in n_b)
@@ -498,16 +510,18 @@ def run_wideband(L, torch, dev, n_arfcn, per_arfcn, steps, seed=4242):
     return {
         "what": "the headline receive work fed from ONE wideband int16 recording of all ARFCNs through the GPU channeliser "
                 "(replaces the PFB mode of utils/gmr1_rx_sdr.py) instead of one complex-float stream per ARFCN",
+        "n_gpus": world, "per_gpu": "every rank has its own wideband recording of n_arfcn ARFCNs (weak scaling; value = all "
+                                    "ranks' bursts / slowest rank's time; the check fields are rank 0's)",
         "arfcns": n_arfcn, "bursts": nb, "fcch_acquisitions": n_arfcn, "recording_seconds": n_wide / info.samp_rate,
         "wideband_rate_msps": info.samp_rate / 1e6, "bank_taps": info.n_taps, "rrc_taps": info.n_taps_resamp,
-        "e2e": {"value": nb / (e2e_ms * 1e-3), "unit": "bursts/s", "ms_per_step": e2e_ms,
+        "e2e": {"value": world * nb / (e2e_ms * 1e-3), "unit": "bursts/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(n_wide * 4), "d2h_bytes_per_step": int(nb * 28 + n_arfcn * 8),
                 "per_arfcn_cf32_bytes_equivalent": int(n_arfcn * n_out * 8),
-                "h2d_gbs": n_wide * 4 / (e2e_ms * 1e-3) / 1e9,
+                "h2d_gbs_per_gpu": n_wide * 4 / (e2e_ms * 1e-3) / 1e9,
                 "how": "pinned host int16 recording -> gmr1b200_channelize (H2D in pieces under the bank + resampler "
                        "kernels) -> fcch_acquire + demod + decode on offsets into the device-resident streams -> host "
                        "L2 / CRC / alignments"},
-        "device_resident": {"bursts_per_s": nb / (dev_ms * 1e-3), "ms_per_step": dev_ms, "ms": {k_: round(v, 4) for k_, v in part.items()},
+        "device_resident": {"bursts_per_s": world * nb / (dev_ms * 1e-3), "ms_per_step": dev_ms, "ms": {k_: round(v, 4) for k_, v in part.items()},
                             "channelizer_input_msps": n_wide / (part["channelize"] * 1e-3) / 1e6,
                             "channelizer_algorithmic_gbs": (bank_bytes + rs_bytes) / (part["channelize"] * 1e-3) / 1e9,
                             "realtime_factor": (n_wide / info.samp_rate) / (dev_ms * 1e-3), "launches_per_step": launches},
@@ -1033,11 +1047,12 @@ def run_gpu_arm(args):
                "single_core_bursts_per_s": 2 * m1 / wall1,
                "l2_crc_identical_to_gpu": same}
 
-    # ---------------- the same work from one wideband recording through the channeliser (N = 1)
+    # ---------------- the same work from one wideband recording per GPU through the channeliser
     wideband = None
-    if world == 1 and not args.no_wideband:
+    if not args.no_wideband:
         torch.cuda.empty_cache()
-        wideband = run_wideband(L, torch, dev, args.arfcns, args.bursts_per_arfcn, min(args.steps, 5))
+        wideband = run_wideband(L, torch, dev, args.arfcns, args.bursts_per_arfcn, min(args.steps, 5), seed=4242 + rank,
+                                world=world, dist=dist if world > 1 else None)
 
     # ---------------- BASELINE configs 3 and 4 at full size (N = 1)
     if world == 1 and not args.no_configs:

@@ -261,10 +261,12 @@ int gmr1b200_pi4cxpsk_detect_desc_batch(const struct gmr1b200_burst_desc *descs,
 int gmr1b200_fcch_rough_multi(int fcch_type, const float *iq, int64_t win_len, int sps, float freq_shift,
                               int32_t *toa, int N, void *stream);
 
-/* ---- burst window -> L2 in one call (the fused entry of SURVEY 8b) ----------------------------------
+/* ---- burst window -> L2 in one call ----------------------------------------------------------------
  * gmr1_pi4cxpsk_demod + gmr1_{bcch,ccch,xch_dc12}_decode (rx_bcch / rx_ccch, src/gmr1_rx.c:747-851) for n
  * windows: chan 0 = BCCH burst + BCCH decode, 1 = DC6 burst + CCCH decode, 2 = DC12 burst + DC12 decode.
- * The soft bits stay in device memory.  l2 [n][24]; crc / conv / toa / freq_err [n], each may be NULL.
+ * One call, TWO kernel launches (demod, then decode): the soft bits stay in a device buffer between them (L2-resident
+ * for batches up to ~250 k bursts) and never reach the host.  A single fused kernel was weighed and not
+ * built: DESIGN.md 4.9 has the measurements.  l2 [n][24]; crc / conv / toa / freq_err [n], each may be NULL.
  * Results are identical to calling gmr1b200_pi4cxpsk_demod_batch and the *_decode_batch one after the other. */
 int gmr1b200_rx_xcch_batch(int chan, const float *iq, int64_t iq_len, const int64_t *win_ofs, int64_t win_stride,
                            int win_len, int sps, const float *freq_shift, float freq_shift0,
@@ -343,6 +345,24 @@ int gmr1b200_rx_call_batch(const float *iq, int64_t iq_len, const int64_t *rec_o
                            const int32_t *align0, const float *freq_err0, int sps, int n, int max_frames,
                            int32_t *kind, int32_t *fn, int32_t *crc, int32_t *conv, uint8_t *l2, int32_t *n_frames,
                            int32_t *tch_rec, uint8_t *tch_data, int32_t *csd_rec, uint8_t *csd_data, void *stream);
+
+/* ---- TCH3 speech frames -> vocoder input (the AMBE hand-off) ---------------------------------------
+ * The reference hands speech to its vocoder as a stream of 10-byte frames, one per 20 ms, two per TCH3 burst:
+ * gmr1_tch3_decode returns frame0 / frame1 (src/l1/tch3.c:116-184), src/gmr1_ambe_decode.c:127-150 reads such a stream
+ * 10 bytes at a time into gmr1_codec_decode_frame(codec, audio, 160, frame, bad) (codec/codec.h:40-45) and
+ * gmr1_codec_decode_dtx covers a slot without a frame.  The vocoder is out of scope; this builds what it is fed,
+ * per channel and with the timing kept, from the per-frame records of gmr1b200_rx_call_batch (tch_rec, tch_data, fn,
+ * n_frames as that call wrote them).  Slot 0 is the first 20 ms of the first frame with traffic-channel activity, the
+ * last slot the second half of the release frame (or of the last frame walked); every TDMA frame is two slots.
+ *   voice [n][2 max_frames][10]  the frames, zeros where flag != 0
+ *   flag  [n][2 max_frames]      0 = speech frame (decode_frame, bad = 0); 1 = no speech in this slot - FACCH3-stolen,
+ *                                DKAB / silence, missed burst (decode_dtx); 2 = behind the end of the stream
+ *   n_voice [n]                  slots of the stream (0: the channel never had a traffic channel)
+ *   first_fn [n] or NULL         frame number of slot 0, -1 without a stream
+ * Concatenating the flag-0 frames of a channel gives the file gmr1_ambe_decode takes.  Host or device pointers. */
+int gmr1b200_tch3_voice_stream_batch(const int32_t *tch_rec, const uint8_t *tch_data, const int32_t *fn,
+                                     const int32_t *n_frames, int n, int max_frames, uint8_t *voice, uint8_t *flag,
+                                     int32_t *n_voice, int32_t *first_fn, void *stream);
 
 /* ---- A5 cipher stream (host; input to the ciphered decoders) ------------------------------------
  * replaces gmr1_a5 / gmr1_a5_1, src/l1/a5.c:57,226 (l1/a5.h:37-41): n = 0 (all zero) or 1 (A5/1-GMR);

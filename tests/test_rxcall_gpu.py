@@ -79,6 +79,28 @@ def _run_batch(L, oracle, calls, F=80):
     L.call("gmr1b200_rx_call_batch", iq, len(iq) // 2, np.array(rec_ofs, np.int64), np.array(rec_len, np.int32),
            np.array(tch_ofs, np.int64), np.array(csd_ofs, np.int64), kcs, np.array(align0, np.int32),
            np.array(ferr0, np.float32), SPS, n, F, kind, fn, crc, conv, l2, nfr, trec, tdat, crec, cdat, None)
+    # SURVEY 8f N4, the AMBE hand-off: the speech frames of every call as the vocoder's input stream, built on the device
+    # from the records above; checked here against those records, by the callers against the reference's log
+    voice, flag = np.zeros((n, 2 * F, 10), np.uint8), np.zeros((n, 2 * F), np.uint8)
+    n_voice, first_fn = i32(n), i32(n)
+    L.call("gmr1b200_tch3_voice_stream_batch", trec, tdat, fn, nfr, n, F, voice, flag, n_voice, first_fn, None)
+    _run_batch.voice = []
+    for i in range(n):
+        act = [f for f in range(nfr[i]) if trec[i, f, 0] != 0 or trec[i, f, 1]]
+        if not act:
+            assert n_voice[i] == 0 and first_fn[i] == -1 and (flag[i] == 2).all() and not voice[i].any()
+            _run_batch.voice.append(b"")
+            continue
+        f0, f1 = act[0], act[-1]
+        assert n_voice[i] == 2 * (f1 - f0 + 1) and first_fn[i] == fn[i, f0]
+        for f in range(f0, f1 + 1):
+            sp = trec[i, f, 0] == 4
+            for h in (0, 1):
+                k = 2 * (f - f0) + h
+                assert flag[i, k] == (0 if sp else 1)
+                assert bytes(voice[i, k]) == (bytes(tdat[i, f, 10 * h:10 * h + 10]) if sp else bytes(10))
+        assert (flag[i, n_voice[i]:] == 2).all() and not voice[i, n_voice[i]:].any()
+        _run_batch.voice.append(b"".join(bytes(voice[i, k]) for k in range(n_voice[i]) if flag[i, k] == 0))
     out = []
     for i in range(n):
         frames = []
@@ -169,6 +191,13 @@ def test_calls_follow_the_reference_application(gpu_lib, oracle, tmp_path):
     got = _run_batch(L, oracle, calls)
     for g, e, tag in zip(got, refs, tags):
         _compare(g, e, tag)
+    # the vocoder streams (what gmr1_ambe_decode would read): the reference's speech frames in order; the protected
+    # 6 bytes of every frame exactly (the class-2 bits carry the float stage's +-1 LSB, see _compare)
+    for stream, e in zip(_run_batch.voice, refs):
+        want = [fr for rec in e if rec["tch"] == "tch3" for fr in (rec["frame0"], rec["frame1"])]
+        assert len(stream) == 10 * len(want) and len(want) > 0
+        for k, fr in enumerate(want):
+            assert stream[10 * k:10 * k + 6] == fr[:6]
     ref0 = refs[0]
     assert sum(e["tch"] == "tch3" for e in ref0) == PLAN.count("s") and any(e["end"] for e in ref0)
     assert sum(len(e["flush"]) for r in refs for e in r) >= 12
