@@ -944,6 +944,13 @@ def run_gpu_arm(args):
             totals = [t for t in totals if t <= args.sweep_max]
         sweep = run_sweep(L, torch, dist if world > 1 else None, dev, world, rank, barrier, totals, args.sweep_chunk)
 
+    # ---------------- the same work from one wideband recording per GPU through the channeliser (every rank)
+    wideband = None
+    if not args.no_wideband:
+        torch.cuda.empty_cache()
+        wideband = run_wideband(L, torch, dev, args.arfcns, args.bursts_per_arfcn, min(args.steps, 5), seed=4242 + rank,
+                                world=world, dist=dist if world > 1 else None)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -1046,13 +1053,6 @@ def run_gpu_arm(args):
                          f"per core, compiled loops (oracle/harness.c), {wall:.2f} s wall",
                "single_core_bursts_per_s": 2 * m1 / wall1,
                "l2_crc_identical_to_gpu": same}
-
-    # ---------------- the same work from one wideband recording per GPU through the channeliser
-    wideband = None
-    if not args.no_wideband:
-        torch.cuda.empty_cache()
-        wideband = run_wideband(L, torch, dev, args.arfcns, args.bursts_per_arfcn, min(args.steps, 5), seed=4242 + rank,
-                                world=world, dist=dist if world > 1 else None)
 
     # ---------------- BASELINE configs 3 and 4 at full size (N = 1)
     if world == 1 and not args.no_configs:

@@ -85,8 +85,16 @@ static void bind_thread(const std::vector<int> &cpus)
 	pthread_setaffinity_np(pthread_self(), sizeof(set), &set);      // best effort
 }
 
+// pool_create / pool_free visit every device from the CALLER's thread: its current device is put back on the way out
+struct DeviceGuard {
+	int dev = -1;
+	DeviceGuard() { if (cudaGetDevice(&dev) != cudaSuccess) { dev = -1; cudaGetLastError(); } }
+	~DeviceGuard() { if (dev >= 0) cudaSetDevice(dev); }
+};
+
 static void pool_free(gmr1b200_pool *p)
 {
+	DeviceGuard keep;
 	for (Dev &d : p->devs) {
 		cudaSetDevice(d.id);
 		for (Slot &s : d.slots) {
@@ -161,6 +169,7 @@ int gmr1b200_pool_create(const int *devices, int n_dev, int streams_per_dev, int
 	cudaError_t e = cudaGetDeviceCount(&have);
 	if (e != cudaSuccess)
 		return cuda_rc(e, "pool_create: cudaGetDeviceCount");
+	DeviceGuard keep;
 	gmr1b200_pool *p = new gmr1b200_pool;
 	p->chunk_bytes = chunk_bytes;
 	p->chunk_units = chunk_bytes / 1024;             // >= one result row per KB of IQ (the shortest window is 3.8 KB)

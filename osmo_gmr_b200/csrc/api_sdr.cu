@@ -480,6 +480,14 @@ static int fine_or_snr(int mode, int fcch_type, const float *iq, int64_t iq_len,
 	return s.finish(e, "fcch_fine kernel");
 }
 
+int gmr1b200_set_fcch_fft(int on)
+{
+	static std::atomic<int> cur{1};
+	const int prev = cur.exchange(on ? 1 : 0);
+	fcch_fft_enable(on ? 1 : 0);
+	return prev;
+}
+
 int gmr1b200_fcch_rough_grid_batch(int fcch_type, const float *iq, int64_t iq_len, const int64_t *win_ofs,
                                    int64_t win_stride, int win_len, int sps, const float *shifts, int n_shifts,
                                    int32_t *toa, float *peak, int n, void *stream)
@@ -501,7 +509,11 @@ int gmr1b200_fcch_rough_grid_batch(int fcch_type, const float *iq, int64_t iq_le
 	float *d_peak = s.out(peak, N * n_shifts);
 	cudaError_t e = cudaSuccess;
 	if (!s.failed()) {
-		e = launch_fcch_grid(a, shifts, n_shifts, d_toa, d_peak, (cudaStream_t)stream);
+		e = launch_fcch_fft(a, shifts, n_shifts, d_toa, d_peak, (cudaStream_t)stream);
+		if (e == cudaErrorNotSupported) {
+			cudaGetLastError();
+			e = launch_fcch_grid(a, shifts, n_shifts, d_toa, d_peak, (cudaStream_t)stream);
+		}
 		if (e == cudaSuccess) {
 			g_launches.fetch_add(1);
 		} else if (e == cudaErrorNotSupported) {       // geometry outside the grid kernel: one search per shift

@@ -119,9 +119,14 @@ template <int N, int NS, int R> struct Stage {
 	static constexpr int NB = N / R;
 	template <class TW> CF_HD static void read(const cfl *row, int j, TW tw, cfl (&v)[R])
 	{
+		read_ld([row](int i) { return row[pad(i)]; }, j, tw, v);
+	}
+	// the same with the points fetched by ld(point index) - a stage fused with whatever produces its input
+	template <class LD, class TW> CF_HD static void read_ld(LD ld, int j, TW tw, cfl (&v)[R])
+	{
 #pragma unroll
 		for (int q = 0; q < R; q++)
-			v[q] = row[pad(j + q * NB)];
+			v[q] = ld(j + q * NB);
 		if (NS > 1) {
 			const int k = j & (NS - 1);
 			constexpr int STEP = N / (NS * R);

@@ -1,0 +1,429 @@
+// fcch_fft.cu - stage 1, third generation of the coarse FCCH search: gmr1_fcch_rough (src/sdr/fcch.c:211-250) for one
+// frequency shift or a grid of shifts per window, with the 117-tap correlation done in the frequency domain.
+//
+// The direct kernels (fcch_kernels.cu, fcch_grid.cu) are bound by arithmetic: 7 606 outputs x 117 taps x 2 FMAs per
+// window and shift, 3.6 MFLOP for 247 KB of samples, 37 % of the fp32 rate at best.  The correlation
+//     corr_s[m] = sum_n c_s[n] y[m + n],   c_s[n] = r[n] e^{j f_s n}   (r = the real dual chirp, fcch.c:167-193)
+// over the normalised, decimated window y (l = 7 722 samples for a 330 ms window) is a circular one of length
+// N = 8192 >= l, because every wanted output m < l - 116 ends inside the window:
+//     corr_s = IDFT( Y . T_s ),   Y = DFT(y),   T_s[k] = (1 / N) sum_n c_s[n] e^{+2 pi i k n / N}
+// T_s depends on the FCCH format and the shift only: built on the host in double, cached on the device.  Per window:
+// ONE forward transform, then per shift a product and a reverse transform - 2 transforms instead of 117 taps for a
+// single shift (1.1 vs 3.6 MFLOP), 6 instead of 5 x 117 for config 4's grid (3.2 vs 18 MFLOP).
+//
+// One CTA of 512 threads per window.  The transforms are the register radix-16 butterflies of chan_fft.cuh (Stockham,
+// 16 x 16 x 16 x 2, one radix-16 butterfly per thread and stage, in place in a padded shared-memory row with a barrier
+// between the loads and the stores of a stage).  Only reverse transforms are needed: DFT(y) = conj(reverse(conj y)),
+// the conjugations ride on the store of the decimated samples and on the product.  The product is fused into the
+// loads of the first reverse stage, |corr|^2 into the stores of the last one; the 5-sample energy-window argmax and
+// its centroid (osmo_cxvec_peak_energy_find, PEAK_WEIGH_WIN) then run over the energies in shared memory exactly as
+// in fcch_grid.cu (oldest-first sums, strict maximum, lowest index on ties).
+// Float contract as for the direct kernels: integer TOA equal to the C path except at rounding ties (the transform's
+// rounding error is ~1e-6 of the correlation peak, the direct sum's ~1e-6 as well, in a different order).
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include <mutex>
+#include <vector>
+
+#include "chan_fft.cuh"
+#include "launch.h"
+
+namespace gmr1 {
+
+namespace {
+
+constexpr int FF_LOG2N = 13, FF_N = 1 << FF_LOG2N;
+constexpr int FF_T = FF_N / 16;                    // 512 threads: one radix-16 butterfly each
+constexpr int FF_RS = cfft::RowStride<FF_N>::value;
+constexpr int FF_PER = FF_N / FF_T;                // 16 consecutive outputs per thread in the peak search
+constexpr int FF_MAXLEN = 128;
+
+struct TwLdg {
+	const float2 *t;
+	__device__ __forceinline__ float2 operator()(int i) const { return __ldg(&t[i]); }
+};
+
+__device__ __forceinline__ float wsum(float v)
+{
+#pragma unroll
+	for (int o = 16; o; o >>= 1)
+		v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+
+// stage S (radix 16, NS = 16^S) of the reverse transform, in place
+template <int S> __device__ __forceinline__ void stage16(float2 *row, const TwLdg tw, int tid)
+{
+	typedef cfft::Stage<FF_N, cfft::Plan<FF_LOG2N>::pow16(S), 16> St;
+	float2 v[16];
+	St::read(row, tid, tw, v);
+	__syncthreads();
+	St::write(row, tid, v);
+	__syncthreads();
+}
+
+// closing radix-2 stage (NS = 4096): 8 butterflies per thread; f(point index, value) takes the outputs
+template <class F> __device__ __forceinline__ void stage2_out(const float2 *row, const TwLdg tw, int tid, F f)
+{
+	typedef cfft::Stage<FF_N, FF_N / 2, 2> St;
+	float2 v[8][2];
+#pragma unroll
+	for (int i = 0; i < 8; i++)
+		St::read(row, tid + i * FF_T, tw, v[i]);
+	__syncthreads();                       // the outputs may land in the memory the inputs came from
+#pragma unroll
+	for (int i = 0; i < 8; i++) {
+		f(St::out_index(tid + i * FF_T, 0), v[i][0]);
+		f(St::out_index(tid + i * FF_T, 1), v[i][1]);
+	}
+	__syncthreads();
+}
+
+struct FftPlan {
+	int32_t n_shifts;
+	const float2 *T;                       // [n_shifts][FF_N] tap spectra / N
+	const float2 *tw;                      // [FF_N] e^{+2 pi i t / N}
+};
+
+// MULTI: the spectrum stays in buffer A, every shift works in buffer B.  Single shift: everything in place in A.
+template <bool MULTI>
+__global__ void __launch_bounds__(FF_T, 1)
+fcch_fft_kernel(const FcchArgs a, const FftPlan fp, int32_t *toa_out, float *peak_out)
+{
+	extern __shared__ __align__(16) uint8_t smem[];
+	const int tid = threadIdx.x, b = blockIdx.x, lane = tid & 31, warp = tid >> 5;
+	if (a.skip && a.skip[b])
+		return;
+	float2 *A = (float2 *)smem;
+	float2 *B = MULTI ? A + FF_RS : A;
+	float *red = (float *)(A + (MULTI ? 2 : 1) * FF_RS);    // [96] reduction scratch
+	const int L = a.win_len, len = a.len;
+	const int l = L >> 2;                  // decimated length (sps 4), <= FF_N
+	const int nc = l - len + 1;
+	const TwLdg tw = {fp.tw};
+
+	const float2 *x = a.iq + (a.ofs ? a.ofs[b] : (int64_t)b * a.stride);
+	const bool al16 = (((uintptr_t)x) & 15) == 0;
+	if (al16) {                            // the whole window -> L2 up front
+		const int chunk = 16384, bytes = (L * 8) & ~15;
+		for (int o = tid * chunk; o < bytes; o += FF_T * chunk)
+			asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((const char *)x + o), "r"(min(chunk, bytes - o))
+			             : "memory");
+	}
+	// ---- statistics over ALL samples (sig_normalize averages before decimating); every 4th sample is kept
+	float sr = 0.0f, si = 0.0f, sq = 0.0f;
+	{
+		float2 s2 = make_float2(0.0f, 0.0f), q2 = make_float2(0.0f, 0.0f);
+		if (al16) {
+			const float4 *x4 = reinterpret_cast<const float4 *>(x);
+#pragma unroll 4
+			for (int i = tid; i < l; i += FF_T) {
+				const float4 v0 = __ldg(&x4[2 * i]), v1 = __ldg(&x4[2 * i + 1]);
+				const float2 p0 = make_float2(v0.x, v0.y), p1 = make_float2(v0.z, v0.w), p2 = make_float2(v1.x, v1.y),
+				             p3 = make_float2(v1.z, v1.w);
+				s2 = __fadd2_rn(s2, __fadd2_rn(__fadd2_rn(p0, p1), __fadd2_rn(p2, p3)));
+				q2 = __ffma2_rn(p0, p0, q2);
+				q2 = __ffma2_rn(p1, p1, q2);
+				q2 = __ffma2_rn(p2, p2, q2);
+				q2 = __ffma2_rn(p3, p3, q2);
+				A[cfft::pad(i)] = p0;
+			}
+		} else {
+#pragma unroll 1
+			for (int i = tid; i < l; i += FF_T)
+#pragma unroll
+				for (int k = 0; k < 4; k++) {
+					const float2 v = __ldg(&x[4 * i + k]);
+					s2 = __fadd2_rn(s2, v);
+					q2 = __ffma2_rn(v, v, q2);
+					if (k == 0)
+						A[cfft::pad(i)] = v;
+				}
+		}
+		sr = s2.x;
+		si = s2.y;
+		sq = q2.x + q2.y;
+		for (int i = 4 * l + tid; i < L; i += FF_T) {           // L % 4 trailing samples (none is kept)
+			const float2 v = __ldg(&x[i]);
+			sr += v.x;
+			si += v.y;
+			sq = fmaf(v.x, v.x, sq);
+			sq = fmaf(v.y, v.y, sq);
+		}
+	}
+	sr = wsum(sr);
+	si = wsum(si);
+	sq = wsum(sq);
+	if (lane == 0) {
+		red[warp] = sr;
+		red[16 + warp] = si;
+		red[32 + warp] = sq;
+	}
+	__syncthreads();
+	sr = wsum(lane < FF_T / 32 ? red[lane] : 0.0f);
+	si = wsum(lane < FF_T / 32 ? red[16 + lane] : 0.0f);
+	sq = wsum(lane < FF_T / 32 ? red[32 + lane] : 0.0f);
+	const float ar = sr / (float)L, ai = si / (float)L;
+	const float var = sq / (float)L - (ar * ar + ai * ai);
+	float sd = var > 0.0f ? sqrtf(var) : 0.0f;
+	if (sd == 0.0f)
+		sd = 1.0f;
+	const float inv_sd = 1.0f / sd;
+	// normalised samples, conjugated (the forward transform is run as conj . reverse . conj), zeros behind the window
+	for (int i = tid; i < FF_N; i += FF_T) {
+		float2 *p = &A[cfft::pad(i)];
+		*p = i < l ? make_float2((p->x - ar) * inv_sd, -((p->y - ai) * inv_sd)) : make_float2(0.0f, 0.0f);
+	}
+	__syncthreads();
+
+	// ---- R = reverse(conj y) = conj(DFT(y)), in place in A
+	{
+		typedef cfft::Stage<FF_N, 1, 16> St0;
+		float2 v[16];
+		St0::read(A, tid, tw, v);
+		__syncthreads();
+		St0::write(A, tid, v);
+		__syncthreads();
+	}
+	stage16<1>(A, tw, tid);
+	stage16<2>(A, tw, tid);
+	stage2_out(A, tw, tid, [A](int k, float2 v) { A[cfft::pad(k)] = v; });
+
+	// ---- per shift: corr = reverse(conj(R) . T_s), energies, peak
+	float *en = (float *)B;                // [4 zeros][FF_N] energies, over the first half of B
+#pragma unroll 1
+	for (int s = 0; s < fp.n_shifts; s++) {
+		const float2 *T = fp.T + (size_t)s * FF_N;
+		{
+			typedef cfft::Stage<FF_N, 1, 16> St0;
+			float2 v[16];
+			St0::read_ld([A, T](int i) {
+				const float2 r = A[cfft::pad(i)], t = __ldg(&T[i]);
+				return make_float2(r.x * t.x + r.y * t.y, r.x * t.y - r.y * t.x);      // conj(r) t
+			}, tid, tw, v);
+			if (!MULTI)
+				__syncthreads();
+			St0::write(B, tid, v);
+			__syncthreads();
+		}
+		stage16<1>(B, tw, tid);
+		stage16<2>(B, tw, tid);
+		stage2_out(B, tw, tid, [en, nc](int k, float2 v) { en[4 + k] = k < nc ? v.x * v.x + v.y * v.y : 0.0f; });
+		if (tid < 4)
+			en[tid] = 0.0f;
+		__syncthreads();
+
+		// 5-sample energy windows ending at m = 16 tid .. 16 tid + 15: oldest first, as the reference sums
+		float xw[FF_PER + 4];
+		{
+			const float4 *e4 = reinterpret_cast<const float4 *>(en + FF_PER * tid);
+#pragma unroll
+			for (int q = 0; q < (FF_PER + 4) / 4; q++) {
+				const float4 v = e4[q];
+				xw[4 * q] = v.x; xw[4 * q + 1] = v.y; xw[4 * q + 2] = v.z; xw[4 * q + 3] = v.w;
+			}
+		}
+		float bv = 0.0f;
+		int bi = 0x7fffffff;
+		const int m0 = FF_PER * tid;
+#pragma unroll
+		for (int j = 0; j < FF_PER; j++) {
+			const float val = ((((0.0f + xw[j]) + xw[j + 1]) + xw[j + 2]) + xw[j + 3]) + xw[j + 4];
+			if (val > bv && m0 + j < nc) {
+				bv = val;
+				bi = m0 + j;
+			}
+		}
+		const float my_v = bv;
+		const int my_i = bi;
+#pragma unroll
+		for (int o = 16; o; o >>= 1) {
+			const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+			const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+			if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+		}
+		int *redi = (int *)(red + 48);
+		if (lane == 0) { red[warp] = bv; redi[warp] = bi; }
+		__syncthreads();
+		bv = lane < FF_T / 32 ? red[lane] : 0.0f;
+		bi = lane < FF_T / 32 ? redi[lane] : 0x7fffffff;
+#pragma unroll
+		for (int o = 16; o; o >>= 1) {
+			const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+			const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+			if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+		}
+		const size_t o = (size_t)s * gridDim.x + b;
+		if (bv <= 0.0f) {                  // nothing correlated: position 0 (max_idx = 0, empty centroid)
+			if (tid == 0) {
+				toa_out[o] = 0;
+				if (peak_out) peak_out[o] = bv;
+			}
+		} else if (my_i == bi && my_v == bv) {                 // exactly one thread owns the winning window
+			// centroid window: [idx-4, idx], or [0, 5) when that would start in front of the vector
+			const int max_idx = bi - 4 < 0 ? 0 : bi - 4;
+			float mw = 0.0f, sw = 0.0f;
+#pragma unroll
+			for (int k2 = 0; k2 < 5; k2++) {
+				const float e = en[4 + max_idx + k2];
+				sw += e;
+				mw += e * (float)(max_idx + k2);
+			}
+			const float pos = sw > 0.0f ? mw / sw : (float)max_idx;
+			toa_out[o] = (int)round((double)(pos * 4.0f));
+			if (peak_out) peak_out[o] = bv;
+		}
+		__syncthreads();                   // the energies are read before the next shift overwrites B
+	}
+}
+
+// ---- tap spectra, cached per device -------------------------------------------------------------------------------
+struct SpecKey {
+	int dev, len, n_shifts;
+	float freq;
+	float shifts[16];
+	bool operator==(const SpecKey &o) const
+	{
+		if (dev != o.dev || len != o.len || n_shifts != o.n_shifts || freq != o.freq)
+			return false;
+		for (int i = 0; i < n_shifts; i++)
+			if (shifts[i] != o.shifts[i])
+				return false;
+		return true;
+	}
+};
+struct SpecEntry {
+	SpecKey key;
+	float2 *T;
+};
+std::vector<SpecEntry> g_spec;             // under GMR1_INIT_LOCK
+float2 *g_tw[64];
+
+cudaError_t spectra(const SpecKey &key, const float2 **T, const float2 **tw)
+{
+	GMR1_INIT_LOCK();
+	if (key.dev < 0 || key.dev >= 64)
+		return cudaErrorInvalidDevice;
+	if (!g_tw[key.dev]) {
+		std::vector<float2> h(FF_N);
+		for (int t = 0; t < FF_N; t++)
+			h[t] = make_float2((float)cos(2.0 * M_PI * t / FF_N), (float)sin(2.0 * M_PI * t / FF_N));
+		cudaError_t e = cudaMalloc((void **)&g_tw[key.dev], FF_N * sizeof(float2));
+		if (e != cudaSuccess)
+			return e;
+		if ((e = cudaMemcpy(g_tw[key.dev], h.data(), FF_N * sizeof(float2), cudaMemcpyHostToDevice)) != cudaSuccess)
+			return e;
+	}
+	*tw = g_tw[key.dev];
+	for (const SpecEntry &e : g_spec)
+		if (e.key == key) {
+			*T = e.T;
+			return cudaSuccess;
+		}
+	// dual-chirp reference at 1 sample/symbol as the reference computes it in float (fcch.c:182-190), times e^{j f n},
+	// transformed in double
+	std::vector<double> wr(FF_N), wi(FF_N);
+	for (int t = 0; t < FF_N; t++) {
+		wr[t] = cos(2.0 * M_PI * t / FF_N);
+		wi[t] = sin(2.0 * M_PI * t / FF_N);
+	}
+	std::vector<float2> h((size_t)key.n_shifts * FF_N);
+	const float phase_base = key.freq * 2.0f * 3.14159265358979323846264338327f / (float)key.len;
+	const float halfpos = (float)key.len / 2.0f;
+	for (int s = 0; s < key.n_shifts; s++) {
+		std::vector<double> cr(key.len), ci(key.len);
+		for (int n = 0; n < key.len; n++) {
+			const float pos = (float)n - halfpos;
+			const float r = sqrtf(2.0f) * cosf(phase_base * (pos * pos));
+			const float ang = key.shifts[s] * (float)n;         // float product, as the sample rotation forms it
+			cr[n] = (double)r * cos((double)ang);
+			ci[n] = (double)r * sin((double)ang);
+		}
+		for (int k = 0; k < FF_N; k++) {
+			double tr = 0.0, ti = 0.0;
+			for (int n = 0; n < key.len; n++) {
+				const int idx = (int)(((int64_t)k * n) & (FF_N - 1));
+				tr += cr[n] * wr[idx] - ci[n] * wi[idx];
+				ti += cr[n] * wi[idx] + ci[n] * wr[idx];
+			}
+			h[(size_t)s * FF_N + k] = make_float2((float)(tr / FF_N), (float)(ti / FF_N));
+		}
+	}
+	float2 *d = nullptr;
+	cudaError_t e = cudaMalloc((void **)&d, h.size() * sizeof(float2));
+	if (e != cudaSuccess)
+		return e;
+	if ((e = cudaMemcpy(d, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice)) != cudaSuccess) {
+		cudaFree(d);
+		return e;
+	}
+	if (g_spec.size() >= 32) {             // a caller sweeping shifts: drop the oldest table
+		cudaFree(g_spec.front().T);
+		g_spec.erase(g_spec.begin());
+	}
+	g_spec.push_back({key, d});
+	*T = d;
+	return cudaSuccess;
+}
+
+std::atomic<int> g_fft_off{0};
+
+}  // namespace
+
+void fcch_fft_enable(int on) { g_fft_off.store(on ? 0 : 1); }
+
+// shifts == NULL: one search per window with the uniform shift a.freq_shift0, results to a.toa / a.peak.  Else n_shifts
+// searches per window, results to toa / peak [n_shifts][n].  cudaErrorNotSupported: geometry or arguments outside what
+// this kernel covers (per-window shifts, sps != 4, windows beyond 8192 symbols) - the caller falls back to the
+// direct kernels.
+cudaError_t launch_fcch_fft(const FcchArgs &a, const float *shifts, int n_shifts, int32_t *toa, float *peak, cudaStream_t st)
+{
+	if (a.n <= 0)
+		return cudaSuccess;
+	const int l = a.win_len / 4, nc = l - a.len + 1;
+	if (g_fft_off.load() || a.sps != 4 || l > FF_N || a.len > FF_MAXLEN || nc < 8 || a.en_out || a.freq_shift)
+		return cudaErrorNotSupported;
+	SpecKey key = {};
+	cudaError_t e = cudaGetDevice(&key.dev);
+	if (e != cudaSuccess)
+		return e;
+	key.len = a.len;
+	key.freq = a.freq;
+	if (!shifts) {
+		key.n_shifts = 1;
+		key.shifts[0] = a.freq_shift0;
+		toa = a.toa;
+		peak = a.peak;
+	} else {
+		if (n_shifts < 1 || n_shifts > 16 || a.freq_shift0 != 0.0f)
+			return cudaErrorNotSupported;
+		key.n_shifts = n_shifts;
+		for (int k = 0; k < n_shifts; k++)
+			key.shifts[k] = shifts[k];
+	}
+	FftPlan fp = {};
+	fp.n_shifts = key.n_shifts;
+	if ((e = spectra(key, &fp.T, &fp.tw)) != cudaSuccess)
+		return e;
+	const bool multi = key.n_shifts > 1;
+	const size_t smem = (size_t)(multi ? 2 : 1) * FF_RS * sizeof(float2) + 96 * sizeof(float);
+	{
+		GMR1_INIT_LOCK();
+		static bool attr_set[64][2];
+		const void *fn = multi ? (const void *)fcch_fft_kernel<true> : (const void *)fcch_fft_kernel<false>;
+		if (key.dev >= 64 || !attr_set[key.dev][multi]) {
+			if ((e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+				return e;
+			if (key.dev < 64)
+				attr_set[key.dev][multi] = true;
+		}
+	}
+	if (multi)
+		fcch_fft_kernel<true><<<a.n, FF_T, smem, st>>>(a, fp, toa, peak);
+	else
+		fcch_fft_kernel<false><<<a.n, FF_T, smem, st>>>(a, fp, toa, peak);
+	return cudaGetLastError();
+}
+
+}  // namespace gmr1

@@ -518,7 +518,11 @@ cudaError_t launch_fcch_rough(const FcchArgs &a, cudaStream_t st)
 	if (a.n <= 0)
 		return cudaSuccess;
 	static const bool old_only = [] { const char *e = getenv("GMR1B200_FCCH_OLD"); return e && atoi(e) != 0; }();
-	if (!a.en_out && !old_only) {          // the search itself: second-generation kernel where it applies
+	if (!a.en_out && !old_only) {          // the search itself: frequency-domain kernel, else the direct grid kernel
+		const cudaError_t fe = launch_fcch_fft(a, nullptr, 0, nullptr, nullptr, st);
+		if (fe != cudaErrorNotSupported)
+			return fe;
+		cudaGetLastError();
 		const cudaError_t ge = launch_fcch_grid(a, nullptr, 0, nullptr, nullptr, st);
 		if (ge != cudaErrorNotSupported)
 			return ge;

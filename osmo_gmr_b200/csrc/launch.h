@@ -77,6 +77,10 @@ cudaError_t launch_fcch_rough(const FcchArgs &a, cudaStream_t st);
 // else n_shifts searches per window sharing one pass over the samples, toa / peak [n_shifts][n].
 // cudaErrorNotSupported: geometry outside the kernel's range, use launch_fcch_rough
 cudaError_t launch_fcch_grid(const FcchArgs &a, const float *shifts, int n_shifts, int32_t *toa, float *peak, cudaStream_t st);
+// third generation (fcch_fft.cu): the same searches with the correlation in the frequency domain; same arguments and
+// results as launch_fcch_grid; cudaErrorNotSupported: per-window shifts, sps != 4, windows beyond 8192 symbols, switched off
+cudaError_t launch_fcch_fft(const FcchArgs &a, const float *shifts, int n_shifts, int32_t *toa, float *peak, cudaStream_t st);
+void fcch_fft_enable(int on);
 cudaError_t launch_fcch_fine(const FcchArgs &a, int mode, cudaStream_t st);
 
 // ---- DKAB / modulation order

@@ -39,7 +39,9 @@ def test_pool_rx_xcch_and_fcch(gpu_lib, oracle, members):
     else:
         devs = [i % torch.cuda.device_count() for i in range(members)]
     # chunk_bytes so small that every member needs several chunks (2 ARFCNs per chunk)
+    cur = torch.cuda.current_device()
     pool = L.pool_create(devs, streams_per_dev=2, chunk_bytes=max(1 << 20, 2 * per * wl * 8 + 64))
+    assert torch.cuda.current_device() == cur        # the pool visits every device but leaves the caller's current one
     try:
         assert L.call("gmr1b200_pool_size", pool) == len(devs)
         pin = torch.from_numpy(iq).pin_memory()
@@ -66,6 +68,7 @@ def test_pool_rx_xcch_and_fcch(gpu_lib, oracle, members):
         assert np.abs(a1 - (4000 + 913 * np.arange(7))).max() <= 2
     finally:
         L.pool_destroy(pool)
+    assert torch.cuda.current_device() == cur
 
 
 def test_pool_errors(gpu_lib):

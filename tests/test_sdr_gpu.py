@@ -32,11 +32,20 @@ def test_fcch_rough(gpu_lib, oracle):
     assert same >= n - 1
 
 
+@pytest.fixture(params=["fft", "direct"])
+def fcch_kernel(request, gpu_lib):
+    """the coarse search through the frequency-domain kernel (csrc/fcch_fft.cu, the default) and through the
+    direct-correlation kernel (csrc/fcch_grid.cu)"""
+    prev = gpu_lib.c.gmr1b200_set_fcch_fft(1 if request.param == "fft" else 0)
+    yield request.param
+    gpu_lib.c.gmr1b200_set_fcch_fft(prev)
+
+
 @pytest.mark.parametrize("grid", [[0.0, 0.27, -0.27, 0.54, -0.54], [0.1], [-0.2, 0.0], [0.05, 0.1, 0.15, -0.15]])
-def test_fcch_rough_grid(gpu_lib, oracle, grid):
+def test_fcch_rough_grid(gpu_lib, oracle, grid, fcch_kernel):
     """gmr1b200_fcch_rough_grid_batch: every shift of the grid answers what gmr1_fcch_rough (src/sdr/fcch.c:211)
     answers for that freq_shift on the same window - paired (+-f), unpaired and zero shifts, ragged window
-    lengths (the last round of outputs partly empty), host and strided windows."""
+    lengths (the last round of outputs partly empty), host and strided windows; both kernels."""
     rng = np.random.default_rng(131 + len(grid))
     n, L = 10, 30888 - 4 * 37
     stride = L + 24
@@ -64,6 +73,16 @@ def test_fcch_rough_grid(gpu_lib, oracle, grid):
     gpu_lib.call("gmr1b200_fcch_rough_batch", 0, _iq(buf), n * stride, None, stride, L, SPS, None, float(g[0]), t1, p1, n,
                  None)
     assert (t1 == toa[0]).all() and np.allclose(p1, peak[0], rtol=1e-4)
+    # the other kernel on the same windows: same positions (rounding ties aside), same window energies
+    other = gpu_lib.c.gmr1b200_set_fcch_fft(0 if fcch_kernel == "fft" else 1)
+    try:
+        toa2 = np.full((len(grid), n), -1, np.int32)
+        peak2 = np.zeros((len(grid), n), np.float32)
+        gpu_lib.call("gmr1b200_fcch_rough_grid_batch", 0, _iq(buf), n * stride, None, stride, L, SPS, g, len(grid), toa2,
+                     peak2, n, None)
+    finally:
+        gpu_lib.c.gmr1b200_set_fcch_fft(other)
+    assert np.abs(toa2 - toa).max() <= 1 and (toa2 == toa).mean() > 0.95 and np.allclose(peak2, peak, rtol=2e-4)
 
 
 def test_fcch_fine_and_snr(gpu_lib, oracle):
