@@ -27,6 +27,7 @@ CF_HD cfl cf(float x, float y) { cfl r; r.x = x; r.y = y; return r; }
 CF_HD cfl cadd(cfl a, cfl b) { return cf(a.x + b.x, a.y + b.y); }
 CF_HD cfl csub(cfl a, cfl b) { return cf(a.x - b.x, a.y - b.y); }
 CF_HD cfl cmul(cfl a, cfl b) { return cf(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+CF_HD cfl csqr(cfl a) { return cf(a.x * a.x - a.y * a.y, 2.0f * a.x * a.y); }
 
 // shared-memory index of point i of a row: one pad slot per 16 points, so that the stride-16 stores of the first
 // stage (thread j writes points 16 j + q) fall on 17 j + q - all banks, no conflict
@@ -128,11 +129,19 @@ template <int N, int NS, int R> struct Stage {
 		for (int q = 0; q < R; q++)
 			v[q] = ld(j + q * NB);
 		if (NS > 1) {
+			// stage twiddles w^q, w = e^{+j 2 pi k / (NS R)}: ONE table load per butterfly, the powers by squaring and
+			// multiplying (depth <= 4: ~3e-7 relative).  Fifteen loads of tw(q k STEP) would be fifteen gathers over up
+			// to 32 cache lines each - measured: that, not arithmetic, bound the first version of these kernels.
 			const int k = j & (NS - 1);
 			constexpr int STEP = N / (NS * R);
+			cfl w[R];
+			w[1] = tw(k * STEP);
+#pragma unroll
+			for (int q = 2; q < R; q++)
+				w[q] = (q & 1) ? cmul(w[q - 1], w[1]) : csqr(w[q >> 1]);
 #pragma unroll
 			for (int q = 1; q < R; q++)
-				v[q] = cmul(v[q], tw(q * k * STEP));
+				v[q] = cmul(v[q], w[q]);
 		}
 		Dft<R>::run(v);
 	}

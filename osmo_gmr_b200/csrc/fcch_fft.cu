@@ -22,6 +22,7 @@
 // rounding error is ~1e-6 of the correlation peak, the direct sum's ~1e-6 as well, in a different order).
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include <mutex>
 #include <vector>
@@ -88,7 +89,7 @@ struct FftPlan {
 
 // MULTI: the spectrum stays in buffer A, every shift works in buffer B.  Single shift: everything in place in A.
 template <bool MULTI>
-__global__ void __launch_bounds__(FF_T, 1)
+__global__ void __launch_bounds__(FF_T, MULTI ? 1 : 2)
 fcch_fft_kernel(const FcchArgs a, const FftPlan fp, int32_t *toa_out, float *peak_out)
 {
 	extern __shared__ __align__(16) uint8_t smem[];
@@ -382,7 +383,8 @@ cudaError_t launch_fcch_fft(const FcchArgs &a, const float *shifts, int n_shifts
 	if (a.n <= 0)
 		return cudaSuccess;
 	const int l = a.win_len / 4, nc = l - a.len + 1;
-	if (g_fft_off.load() || a.sps != 4 || l > FF_N || a.len > FF_MAXLEN || nc < 8 || a.en_out || a.freq_shift)
+	static const bool env_off = [] { const char *e = getenv("GMR1B200_FCCH_FFT"); return e && atoi(e) == 0; }();   // A/B knob
+	if (env_off || g_fft_off.load() || a.sps != 4 || l > FF_N || a.len > FF_MAXLEN || nc < 8 || a.en_out || a.freq_shift)
 		return cudaErrorNotSupported;
 	SpecKey key = {};
 	cudaError_t e = cudaGetDevice(&key.dev);
