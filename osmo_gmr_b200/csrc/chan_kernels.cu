@@ -352,26 +352,31 @@ __global__ void __launch_bounds__(TO / RS_K * 32, 2) resamp_kernel(const ResampA
 	const int64_t n0 = a.n_begin + (int64_t)blockIdx.x * RS_TO;
 	const int c0 = blockIdx.y * RS_CH;
 	const int n_here = (int)min((int64_t)RS_TO, a.n_end - n0);
+	const int64_t row_hi = __ldg(&a.sched_i[n0 + n_here - 1]);
+	const int64_t row_lo = (int64_t)__ldg(&a.sched_i[n0]) - (tpf - 1);
+	const int rows = (int)(row_hi - row_lo + 1);
+	const bool whole = a.chan_idx == nullptr && c0 + RS_CH <= a.n_wanted && row_lo >= 0 && row_hi < a.n_steps;
+	if (whole) {
+		// whole rows of 128 consecutive channels: asynchronous 16-byte copies straight into shared memory (LDGSTS), in
+		// flight while the filters are fetched and the tap tables merged; collected in front of the MAC loop
+		const float4 *src = reinterpret_cast<const float4 *>(a.mid + row_lo * a.n_chans + c0);
+		const unsigned dst = (unsigned)__cvta_generic_to_shared(in_tile);
+		const int stride4 = a.n_chans >> 1;
+		for (int item = tid; item < rows * (RS_CH / 2); item += RS_T) {
+			const int rr = item / (RS_CH / 2), c = item - rr * (RS_CH / 2);
+			asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * item), "l"(src + (size_t)rr * stride4 + c)
+			             : "memory");
+		}
+		asm volatile("cp.async.commit_group;" ::: "memory");
+	}
 	for (int i = tid; i < 32 * tpf; i += RS_T) {
 		filt[i] = __ldg(&a.filt[i]);
 		dfilt[i] = __ldg(&a.dfilt[i]);
 	}
 	if (tid < RS_CH)
 		ch_idx[tid] = c0 + tid < a.n_wanted ? (a.chan_idx ? __ldg(&a.chan_idx[c0 + tid]) : c0 + tid) : -1;
-	const int64_t row_hi = __ldg(&a.sched_i[n0 + n_here - 1]);
-	const int64_t row_lo = (int64_t)__ldg(&a.sched_i[n0]) - (tpf - 1);
-	const int rows = (int)(row_hi - row_lo + 1);
 	__syncthreads();
-	if (a.chan_idx == nullptr && c0 + RS_CH <= a.n_wanted && row_lo >= 0 && row_hi < a.n_steps) {
-		// whole rows of 128 consecutive channels: 16-byte loads
-		const float4 *src = reinterpret_cast<const float4 *>(a.mid + row_lo * a.n_chans + c0);
-		float4 *dst = reinterpret_cast<float4 *>(in_tile);
-		const int stride4 = a.n_chans >> 1;
-		for (int item = tid; item < rows * (RS_CH / 2); item += RS_T) {
-			const int rr = item / (RS_CH / 2), c = item - rr * (RS_CH / 2);
-			dst[item] = __ldg(&src[(size_t)rr * stride4 + c]);
-		}
-	} else {
+	if (!whole) {
 		for (int item = tid; item < rows * RS_CH; item += RS_T) {
 			const int rr = item / RS_CH, c = item - rr * RS_CH;
 			const int64_t row = row_lo + rr;
@@ -379,7 +384,6 @@ __global__ void __launch_bounds__(TO / RS_K * 32, 2) resamp_kernel(const ResampA
 			in_tile[item] = (row >= 0 && row < a.n_steps && k >= 0) ? __ldg(&a.mid[row * a.n_chans + k]) : make_float2(0.0f, 0.0f);
 		}
 	}
-	__syncthreads();
 
 	// one group of RS_K outputs per warp (RS_TO / RS_K == warps): channels 2 lane, 2 lane + 1, 64 + 2 lane, 65 + 2 lane
 	const int o0 = warp * RS_K;
@@ -406,6 +410,13 @@ __global__ void __launch_bounds__(TO / RS_K * 32, 2) resamp_kernel(const ResampA
 			}
 			__syncwarp();
 		}
+	}
+	asm volatile("cp.async.wait_all;" ::: "memory");
+	__syncthreads();                                            // the input tile is complete
+	if (cnt > 0) {
+		const int64_t n = n0 + o0;
+		const int b_last = (int)(__ldg(&a.sched_i[n + cnt - 1]) - row_lo);
+		const int span = b_last - (int)(__ldg(&a.sched_i[n]) - row_lo) + tpf;
 		const ulonglong2 *xp = reinterpret_cast<const ulonglong2 *>(in_tile) + (size_t)b_last * (RS_CH / 2) + lane;
 		const ulonglong2 *cp = reinterpret_cast<const ulonglong2 *>(comb);
 #pragma unroll 2

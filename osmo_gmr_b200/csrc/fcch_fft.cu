@@ -11,9 +11,9 @@
 // ONE forward transform, then per shift a product and a reverse transform - 2 transforms instead of 117 taps for a
 // single shift (1.1 vs 3.6 MFLOP), 6 instead of 5 x 117 for config 4's grid (3.2 vs 18 MFLOP).
 //
-// One CTA of 512 threads per window.  The transforms are the register radix-16 butterflies of chan_fft.cuh (Stockham,
+// One CTA of 512 threads per window (persistent CTAs, two per SM).  The transforms are the register radix-16 butterflies of chan_fft.cuh (Stockham,
 // 16 x 16 x 16 x 2, one radix-16 butterfly per thread and stage, in place in a padded shared-memory row with a barrier
-// between the loads and the stores of a stage).  Only reverse transforms are needed: DFT(y) = conj(reverse(conj y)),
+// between the loads and the stores of a stage; the stage twiddles are powers of one table value).  Only reverse transforms are needed: DFT(y) = conj(reverse(conj y)),
 // the conjugations ride on the store of the decimated samples and on the product.  The product is fused into the
 // loads of the first reverse stage, |corr|^2 into the stores of the last one; the 5-sample energy-window argmax and
 // its centroid (osmo_cxvec_peak_energy_find, PEAK_WEIGH_WIN) then run over the energies in shared memory exactly as
@@ -85,25 +85,33 @@ struct FftPlan {
 	int32_t n_shifts;
 	const float2 *T;                       // [n_shifts][FF_N] tap spectra / N
 	const float2 *tw;                      // [FF_N] e^{+2 pi i t / N}
+	float2 *spec;                          // MULTI: [gridDim.x][FF_N] the window's spectrum between the shifts
 };
 
-// MULTI: the spectrum stays in buffer A, every shift works in buffer B.  Single shift: everything in place in A.
+// Persistent CTAs, two per SM: CTA c takes windows c, c + gridDim.x, ...  One padded shared-memory row A for everything.
+// MULTI (several shifts per window): the spectrum is parked in the CTA's own 64 KB of global scratch (written once,
+// read once per shift with coalesced loads, L2-resident: 296 CTAs x 64 KB) - a second shared-memory row would halve
+// the CTAs per SM.  Single shift: the product is taken in place.
 template <bool MULTI>
-__global__ void __launch_bounds__(FF_T, MULTI ? 1 : 2)
+__global__ void __launch_bounds__(FF_T, 2)
 fcch_fft_kernel(const FcchArgs a, const FftPlan fp, int32_t *toa_out, float *peak_out)
 {
 	extern __shared__ __align__(16) uint8_t smem[];
-	const int tid = threadIdx.x, b = blockIdx.x, lane = tid & 31, warp = tid >> 5;
-	if (a.skip && a.skip[b])
-		return;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	float2 *A = (float2 *)smem;
-	float2 *B = MULTI ? A + FF_RS : A;
-	float *red = (float *)(A + (MULTI ? 2 : 1) * FF_RS);    // [96] reduction scratch
+	float2 *B = A;
+	float *red = (float *)(A + FF_RS);     // [96] reduction scratch
+	float2 *spec = MULTI ? fp.spec + (size_t)blockIdx.x * FF_N : nullptr;
 	const int L = a.win_len, len = a.len;
 	const int l = L >> 2;                  // decimated length (sps 4), <= FF_N
 	const int nc = l - len + 1;
 	const TwLdg tw = {fp.tw};
 
+#pragma unroll 1
+	for (int b = blockIdx.x; b < a.n; b += gridDim.x) {
+	if (a.skip && a.skip[b])
+		continue;
+	__syncthreads();                       // the previous window's energies and reduction scratch are done with
 	const float2 *x = a.iq + (a.ofs ? a.ofs[b] : (int64_t)b * a.stride);
 	const bool al16 = (((uintptr_t)x) & 15) == 0;
 	if (al16) {                            // the whole window -> L2 up front
@@ -189,7 +197,10 @@ fcch_fft_kernel(const FcchArgs a, const FftPlan fp, int32_t *toa_out, float *pea
 	}
 	stage16<1>(A, tw, tid);
 	stage16<2>(A, tw, tid);
-	stage2_out(A, tw, tid, [A](int k, float2 v) { A[cfft::pad(k)] = v; });
+	if (MULTI)
+		stage2_out(A, tw, tid, [spec](int k, float2 v) { spec[k] = v; });
+	else
+		stage2_out(A, tw, tid, [A](int k, float2 v) { A[cfft::pad(k)] = v; });
 
 	// ---- per shift: corr = reverse(conj(R) . T_s), energies, peak
 	float *en = (float *)B;                // [4 zeros][FF_N] energies, over the first half of B
@@ -199,8 +210,8 @@ fcch_fft_kernel(const FcchArgs a, const FftPlan fp, int32_t *toa_out, float *pea
 		{
 			typedef cfft::Stage<FF_N, 1, 16> St0;
 			float2 v[16];
-			St0::read_ld([A, T](int i) {
-				const float2 r = A[cfft::pad(i)], t = __ldg(&T[i]);
+			St0::read_ld([A, T, spec](int i) {
+				const float2 r = MULTI ? spec[i] : A[cfft::pad(i)], t = __ldg(&T[i]);
 				return make_float2(r.x * t.x + r.y * t.y, r.x * t.y - r.y * t.x);      // conj(r) t
 			}, tid, tw, v);
 			if (!MULTI)
@@ -255,7 +266,7 @@ fcch_fft_kernel(const FcchArgs a, const FftPlan fp, int32_t *toa_out, float *pea
 			const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
 			if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
 		}
-		const size_t o = (size_t)s * gridDim.x + b;
+		const size_t o = (size_t)s * a.n + b;
 		if (bv <= 0.0f) {                  // nothing correlated: position 0 (max_idx = 0, empty centroid)
 			if (tid == 0) {
 				toa_out[o] = 0;
@@ -276,6 +287,7 @@ fcch_fft_kernel(const FcchArgs a, const FftPlan fp, int32_t *toa_out, float *pea
 			if (peak_out) peak_out[o] = bv;
 		}
 		__syncthreads();                   // the energies are read before the next shift overwrites B
+	}
 	}
 }
 
@@ -300,6 +312,7 @@ struct SpecEntry {
 };
 std::vector<SpecEntry> g_spec;             // under GMR1_INIT_LOCK
 float2 *g_tw[64];
+int     g_ctas[64];                        // persistent CTAs per launch: 2 x SMs
 
 cudaError_t spectra(const SpecKey &key, const float2 **T, const float2 **tw)
 {
@@ -409,9 +422,16 @@ cudaError_t launch_fcch_fft(const FcchArgs &a, const float *shifts, int n_shifts
 	if ((e = spectra(key, &fp.T, &fp.tw)) != cudaSuccess)
 		return e;
 	const bool multi = key.n_shifts > 1;
-	const size_t smem = (size_t)(multi ? 2 : 1) * FF_RS * sizeof(float2) + 96 * sizeof(float);
+	const size_t smem = (size_t)FF_RS * sizeof(float2) + 96 * sizeof(float);
+	int ctas = 0;
 	{
 		GMR1_INIT_LOCK();
+		if (!g_ctas[key.dev]) {
+			int sms = 148;
+			cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, key.dev);
+			g_ctas[key.dev] = 2 * sms;
+		}
+		ctas = g_ctas[key.dev];
 		static bool attr_set[64][2];
 		const void *fn = multi ? (const void *)fcch_fft_kernel<true> : (const void *)fcch_fft_kernel<false>;
 		if (key.dev >= 64 || !attr_set[key.dev][multi]) {
@@ -421,10 +441,18 @@ cudaError_t launch_fcch_fft(const FcchArgs &a, const float *shifts, int n_shifts
 				attr_set[key.dev][multi] = true;
 		}
 	}
-	if (multi)
-		fcch_fft_kernel<true><<<a.n, FF_T, smem, st>>>(a, fp, toa, peak);
-	else
-		fcch_fft_kernel<false><<<a.n, FF_T, smem, st>>>(a, fp, toa, peak);
+	// several shifts per window: persistent CTAs (the spectrum parking is per CTA); one shift: a CTA per window, the
+	// hardware balances the tail (1024 windows over 296 persistent CTAs would run at 3.46 / 4)
+	const int grid = (multi && a.n > ctas) ? ctas : a.n;
+	if (multi) {                           // spectrum parking of this launch: stream-ordered, back to the pool right behind it
+		if ((e = cudaMallocAsync((void **)&fp.spec, (size_t)grid * FF_N * sizeof(float2), st)) != cudaSuccess)
+			return e;
+		fcch_fft_kernel<true><<<grid, FF_T, smem, st>>>(a, fp, toa, peak);
+		e = cudaGetLastError();
+		cudaFreeAsync(fp.spec, st);
+		return e;
+	}
+	fcch_fft_kernel<false><<<grid, FF_T, smem, st>>>(a, fp, toa, peak);
 	return cudaGetLastError();
 }
 
