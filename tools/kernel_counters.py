@@ -24,7 +24,7 @@ metrics = "smsp__inst_executed.sum,dram__bytes_read.sum,dram__bytes_write.sum,gp
           "smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active"
 cmd = ["ncu", "--metrics", metrics, "--clock-control", "none", "-k", "regex:demod_|decode_tpc|fcch_", "-s", "18", "-c", "6",
        "--csv", "--log-file", args.csv, sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "3",
-       "--no-cpu-baseline", "--no-configs", "--no-sweep", "--min-seconds", "0", "--streams", "1"]
+       "--no-cpu-baseline", "--no-configs", "--no-sweep", "--no-wideband", "--min-seconds", "0", "--streams", "1"]
 subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 rows = [r for r in csv.reader(open(args.csv)) if len(r) > 10]
 h = rows[0]
@@ -36,7 +36,8 @@ import osmo_gmr_b200
 build = osmo_gmr_b200.Lib().version().split("build ")[-1]
 units = {"demod_fast_kernel<0,81,0>": ("demod_bcch", 131072), "demod_fast_kernel<2,41,0>": ("demod_dc6", 131072),
          "decode_tpc_kernel<0,": ("decode_bcch", 131072), "decode_tpc_kernel<1,": ("decode_ccch", 131072),
-         "fcch_grid_kernel<0>": ("fcch_rough", 1024), "fcch_rough_kernel": ("fcch_rough", 1024),
+         "fcch_fft_kernel<0>": ("fcch_rough", 1024), "fcch_grid_kernel<0>": ("fcch_rough", 1024),
+         "fcch_rough_kernel": ("fcch_rough", 1024),
          "fcch_fine_kernel": ("fcch_fine", 1024)}
 out = {}
 for (kid, name), m in per.items():

@@ -15,9 +15,14 @@ python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/${TAG}_bench_
 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/${TAG}_launches.csv \
 	python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-configs --no-sweep --min-seconds 0 > /dev/null 2>&1
 ncu --set full --import-source on --clock-control none -k regex:"demod_|decode_tpc|fcch_" -s 18 -c 6 -f -o gpurun_out/${TAG}_full \
-	python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-configs --no-sweep --min-seconds 0 --streams 1 > /dev/null 2>&1
-python tools/ncu_summary.py gpurun_out/${TAG}_full.ncu-rep > gpurun_out/${TAG}_ncu_full_summary.csv
-rm -f gpurun_out/${TAG}_full.ncu-rep
+	python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-configs --no-sweep --no-wideband --min-seconds 0 --streams 1 > /dev/null 2>&1
+ncu --set full --import-source on --clock-control none -k regex:"pfb_|resamp_kernel" -s 4 -c 2 -f -o gpurun_out/${TAG}_full_chan \
+	python tools/bench_chan.py --reps 2 > /dev/null 2>&1
+ncu --set full --import-source on --clock-control none --kernel-name-base demangled -k regex:"fcch_fft_kernel<\(bool\)1>|fcch_fft_kernel<true>" -c 1 -f -o gpurun_out/${TAG}_full_grid \
+	python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-sweep --no-wideband --min-seconds 0 > /dev/null 2>&1
+python tools/ncu_summary.py gpurun_out/${TAG}_full.ncu-rep gpurun_out/${TAG}_full_chan.ncu-rep gpurun_out/${TAG}_full_grid.ncu-rep > gpurun_out/${TAG}_ncu_full_summary.csv
+rm -f gpurun_out/${TAG}_full.ncu-rep gpurun_out/${TAG}_full_chan.ncu-rep gpurun_out/${TAG}_full_grid.ncu-rep
+python tools/bench_chan.py > gpurun_out/${TAG}_chan.jsonl; python tools/bench_chan.py --chans 256 >> gpurun_out/${TAG}_chan.jsonl
 for n in 1024 4096 16384; do python tools/bench_rxloop.py --channels $n; done > gpurun_out/${TAG}_rxloop.jsonl 2> gpurun_out/${TAG}_rxloop.err
 python tools/bench_config1.py > gpurun_out/${TAG}_config1.json 2> gpurun_out/${TAG}_config1.err
 ls -la gpurun_out/${TAG}_*
