@@ -350,13 +350,18 @@ def run_configs(L, torch, dev, peak_gbs, cores, scale, reps, n_check):
 # ------------------------------------------------------------------------------------------------
 # the end-to-end step of several GPUs from ONE process (library device pool, csrc/api_multi.cu)
 # ------------------------------------------------------------------------------------------------
-def run_wideband(L, torch, dev, n_arfcn, per_arfcn, steps, seed=4242, world=1, dist=None):
+def run_wideband(L, torch, dev, n_arfcn, per_arfcn, steps, seed=4242, world=1, dist=None, shared=False, rank=0):
     """SURVEY 8f N3 in front of the headline workload: the SAME receive work (one FCCH acquisition per ARFCN + per_arfcn
     BCCH / DC6 bursts per ARFCN, demod + decode), but the input is ONE wideband recording of all ARFCNs (int16 I/Q at
     n_arfcn x 31.25 kS/s, what an SDR front end delivers) instead of one 4x-oversampled complex-float stream per ARFCN:
     pinned host recording -> H2D -> gmr1b200_channelize (filter bank + RRC resampler, streams stay in HBM) -> FCCH
     acquire, demod, decode on window offsets into the streams -> host L2 / CRC.  The recording is made once on the device
-    (transmit-pulse bursts of every ARFCN interpolated, mixed to their carriers, summed, AWGN, int16)."""
+    (transmit-pulse bursts of every ARFCN interpolated, mixed to their carriers, summed, AWGN, int16).
+    shared (world > 1): ONE recording for the whole job (every rank makes the same one from the same seed and keeps a
+    1 / world time slice of it in pinned host memory): per step every rank copies its slice to its GPU, an NCCL
+    all-gather over NVLink gives every GPU the whole recording - the one real exchange step of this system, SURVEY 8f
+    N3 - every GPU runs the bank and resamples / acquires / demodulates / decodes ITS ARFCNs (a mod world == rank):
+    strong scaling of one capture."""
     import ctypes
     ev = lambda: torch.cuda.Event(enable_timing=True)
     n_b = {"bcch": per_arfcn // 2, "dc6": per_arfcn - per_arfcn // 2}
@@ -408,25 +413,41 @@ def run_wideband(L, torch, dev, n_arfcn, per_arfcn, steps, seed=4242, world=1, d
     gen_s = time.perf_counter() - g0
     del streams
     peak_i16 = int(wide.abs().max())
-    host_wide = torch.empty((n_wide, 2), dtype=torch.int16).pin_memory()
-    host_wide.copy_(wide)
+    shared = shared and world > 1
+    own = np.arange(rank, n_arfcn, world) if shared else np.arange(n_arfcn)      # the ARFCNs this rank receives
+    n_own = len(own)
+    own_idx = d(own.astype(np.int32)) if shared else None
+    if shared:
+        n_slice = -(-n_wide // world)
+        wide_full = torch.zeros((world * n_slice, 2), dtype=torch.int16, device=dev)
+        my_slice = torch.empty((n_slice, 2), dtype=torch.int16, device=dev)
+        host_wide = torch.zeros((n_slice, 2), dtype=torch.int16).pin_memory()
+        lo_s, hi_s = rank * n_slice, min(n_wide, (rank + 1) * n_slice)
+        host_wide[:hi_s - lo_s].copy_(wide[lo_s:hi_s])
+        wide_full[:n_wide].copy_(wide)
+        wide = wide_full[:n_wide]
+    else:
+        host_wide = torch.empty((n_wide, 2), dtype=torch.int16).pin_memory()
+        host_wide.copy_(wide)
     n_out = int(L.c.gmr1b200_chan_out_len(h, n_wide))
-    out = torch.empty((n_arfcn, n_out, 2), dtype=torch.float32, device=dev)
+    out = torch.empty((n_own, n_out, 2), dtype=torch.float32, device=dev)
     dly = int(round(info.delay_out))
     # window offsets inside the channelised streams: row stride n_out, everything delay_out later
-    res = {}
+    res, sel = {}, {}
     for kind in ("bcch", "dc6"):
-        n = n_arfcn * n_b[kind]
-        a, j = np.divmod(np.arange(n, dtype=np.int64), n_b[kind])
-        o = ofs[kind] - a * slen + a * n_out + dly
+        sel[kind] = (own[:, None] * n_b[kind] + np.arange(n_b[kind])[None, :]).reshape(-1)      # this rank's bursts
+        n = len(sel[kind])
+        a = np.repeat(own, n_b[kind]).astype(np.int64)
+        i_loc = np.repeat(np.arange(n_own, dtype=np.int64), n_b[kind])
+        o = ofs[kind][sel[kind]] - a * slen + i_loc * n_out + dly
         res[kind] = dict(ofs=d(o), eb=torch.empty((n, EBITS[kind]), dtype=torch.int8, device=dev),
                          l2=torch.empty((n, 24), dtype=torch.uint8, device=dev), crc=torch.empty(n, dtype=torch.int32, device=dev),
                          h_l2=torch.empty((n, 24), dtype=torch.uint8).pin_memory(), h_crc=torch.empty(n, dtype=torch.int32).pin_memory())
-    f_ofs = d(np.arange(n_arfcn, dtype=np.int64) * n_out + lead + dly)
-    f_toa = torch.empty(n_arfcn, dtype=torch.int32, device=dev)
-    f_align = torch.empty(n_arfcn, dtype=torch.int32, device=dev)
-    f_ferr = torch.empty(n_arfcn, dtype=torch.float32, device=dev)
-    h_f = torch.empty((2, n_arfcn), dtype=torch.float32).pin_memory()
+    f_ofs = d(np.arange(n_own, dtype=np.int64) * n_out + lead + dly)
+    f_toa = torch.empty(n_own, dtype=torch.int32, device=dev)
+    f_align = torch.empty(n_own, dtype=torch.int32, device=dev)
+    f_ferr = torch.empty(n_own, dtype=torch.float32, device=dev)
+    h_f = torch.empty((2, n_own), dtype=torch.float32).pin_memory()
     st = torch.cuda.Stream(device=dev)
     sh = st.cuda_stream
 
@@ -434,14 +455,14 @@ def run_wideband(L, torch, dev, n_arfcn, per_arfcn, steps, seed=4242, world=1, d
         marks = []
         mark = lambda name: (marks.append((name, ev())), marks[-1][1].record(st)) if timers is not None else None
         mark("start")
-        L.call("gmr1b200_channelize", h.value, wide if src is None else src, 1, n_wide, None, n_arfcn, out, n_out, sh)
+        L.call("gmr1b200_channelize", h.value, wide if src is None else src, 1, n_wide, own_idx, n_own, out, n_out, sh)
         mark("channelize")
-        L.call("gmr1b200_fcch_acquire_batch", 0, out, n_arfcn * n_out, f_ofs, 0, FCCH_WIN, SPS, f_toa, f_align, f_ferr, n_arfcn, sh)
+        L.call("gmr1b200_fcch_acquire_batch", 0, out, n_own * n_out, f_ofs, 0, FCCH_WIN, SPS, f_toa, f_align, f_ferr, n_own, sh)
         mark("fcch")
         for kind in ("bcch", "dc6"):
             r = res[kind]
             n = r["crc"].numel()
-            L.call("gmr1b200_pi4cxpsk_demod_batch", BT[kind], out, n_arfcn * n_out, r["ofs"], 0, wlen(kind), SPS, None, 0.0,
+            L.call("gmr1b200_pi4cxpsk_demod_batch", BT[kind], out, n_own * n_out, r["ofs"], 0, wlen(kind), SPS, None, 0.0,
                    r["eb"], EBITS[kind], None, None, None, None, n, sh)
             L.call("gmr1b200_bcch_decode_batch" if kind == "bcch" else "gmr1b200_ccch_decode_batch", r["l2"], r["eb"], None,
                    r["crc"], n, sh)
@@ -452,7 +473,13 @@ def run_wideband(L, torch, dev, n_arfcn, per_arfcn, steps, seed=4242, world=1, d
     def e2e():
         # the pinned HOST recording goes straight into the C entry point: it copies it in pieces on its own copy stream
         # while the bank and the resampler of the pieces before run (csrc/api_chan.cu)
-        receive(src=host_wide)
+        if shared:                         # this rank's time slice up, all-gather over NVLink, then the device-resident call
+            with torch.cuda.stream(st):
+                my_slice.copy_(host_wide, non_blocking=True)
+                dist.all_gather_into_tensor(wide_full.view(torch.int32), my_slice.view(torch.int32))    # one I/Q pair = one int32
+            receive()
+        else:
+            receive(src=host_wide)
         with torch.cuda.stream(st):
             for kind in ("bcch", "dc6"):
                 res[kind]["h_l2"].copy_(res[kind]["l2"], non_blocking=True)
@@ -498,34 +525,41 @@ def run_wideband(L, torch, dev, n_arfcn, per_arfcn, steps, seed=4242, world=1, d
     barrier()
     e2e_ms = rank_max(1e3 * (time.perf_counter() - t0) / steps)
     # what came out: payloads against what was sent, FCCH positions against where the chirps were put
-    nb = sum(n_arfcn * n_b[kk] for kk in n_b)
+    nb = sum(n_arfcn * n_b[kk] for kk in n_b)                  # bursts of the whole recording
+    nb_own = sum(len(sel[kk]) for kk in n_b)
     ok = sum(int((res[kk]["h_crc"] == 0).sum()) for kk in n_b)
-    good = sum(int(((res[kk]["h_l2"].numpy() == par[kk]["l2"]).all(axis=1) & (res[kk]["h_crc"].numpy() == 0)).sum()) for kk in n_b)
-    wrong = sum(int(((res[kk]["h_l2"].numpy() != par[kk]["l2"]).any(axis=1) & (res[kk]["h_crc"].numpy() == 0)).sum()) for kk in n_b)
-    toa_err = h_f[0].numpy() - (fpos + info.delay_out - dly)
+    good = sum(int(((res[kk]["h_l2"].numpy() == par[kk]["l2"][sel[kk]]).all(axis=1) & (res[kk]["h_crc"].numpy() == 0)).sum()) for kk in n_b)
+    wrong = sum(int(((res[kk]["h_l2"].numpy() != par[kk]["l2"][sel[kk]]).any(axis=1) & (res[kk]["h_crc"].numpy() == 0)).sum()) for kk in n_b)
+    toa_err = h_f[0].numpy() - (fpos[own] + info.delay_out - dly)
+    jobs = 1 if shared else world          # recordings processed per step by the whole job
     n_steps = n_wide // (n_arfcn // 2)
     bank_bytes = n_wide * 4 + n_steps * n_arfcn * 8
-    rs_bytes = n_steps * n_arfcn * 8 + n_arfcn * n_out * 8
+    rs_bytes = n_steps * n_own * 8 + n_own * n_out * 8
     L.c.gmr1b200_chan_destroy(h)
     return {
         "what": "the headline receive work fed from ONE wideband int16 recording of all ARFCNs through the GPU channeliser "
                 "(replaces the PFB mode of utils/gmr1_rx_sdr.py) instead of one complex-float stream per ARFCN",
-        "n_gpus": world, "per_gpu": "every rank has its own wideband recording of n_arfcn ARFCNs (weak scaling; value = all "
-                                    "ranks' bursts / slowest rank's time; the check fields are rank 0's)",
+        "n_gpus": world, "scaling": "strong" if shared else "weak",
+        "per_gpu": ("ONE recording for the whole job: every rank copies a 1 / n_gpus time slice from pinned host memory, NCCL "
+                    "all-gather over NVLink, every GPU runs the bank and receives the ARFCNs a mod n_gpus == rank; value = "
+                    "the recording's bursts / slowest rank's time; the check fields are rank 0's share") if shared else
+                   ("every rank has its own wideband recording of n_arfcn ARFCNs (weak scaling; value = all ranks' bursts / "
+                    "slowest rank's time; the check fields are rank 0's)"),
         "arfcns": n_arfcn, "bursts": nb, "fcch_acquisitions": n_arfcn, "recording_seconds": n_wide / info.samp_rate,
         "wideband_rate_msps": info.samp_rate / 1e6, "bank_taps": info.n_taps, "rrc_taps": info.n_taps_resamp,
-        "e2e": {"value": world * nb / (e2e_ms * 1e-3), "unit": "bursts/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": int(n_wide * 4), "d2h_bytes_per_step": int(nb * 28 + n_arfcn * 8),
+        "e2e": {"value": jobs * nb / (e2e_ms * 1e-3), "unit": "bursts/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(host_wide.numel() * 2), "d2h_bytes_per_step": int(nb_own * 28 + n_own * 8),
+                "nvlink_allgather_bytes_per_gpu": int(wide_full.numel() * 2) if shared else 0,
                 "per_arfcn_cf32_bytes_equivalent": int(n_arfcn * n_out * 8),
                 "h2d_gbs_per_gpu": n_wide * 4 / (e2e_ms * 1e-3) / 1e9,
                 "how": "pinned host int16 recording -> gmr1b200_channelize (H2D in pieces under the bank + resampler "
                        "kernels) -> fcch_acquire + demod + decode on offsets into the device-resident streams -> host "
                        "L2 / CRC / alignments"},
-        "device_resident": {"bursts_per_s": world * nb / (dev_ms * 1e-3), "ms_per_step": dev_ms, "ms": {k_: round(v, 4) for k_, v in part.items()},
+        "device_resident": {"bursts_per_s": jobs * nb / (dev_ms * 1e-3), "ms_per_step": dev_ms, "ms": {k_: round(v, 4) for k_, v in part.items()},
                             "channelizer_input_msps": n_wide / (part["channelize"] * 1e-3) / 1e6,
                             "channelizer_algorithmic_gbs": (bank_bytes + rs_bytes) / (part["channelize"] * 1e-3) / 1e9,
                             "realtime_factor": (n_wide / info.samp_rate) / (dev_ms * 1e-3), "launches_per_step": launches},
-        "crc_ok_frac": ok / nb, "payload_correct_frac": good / nb, "crc_ok_but_payload_wrong": wrong,
+        "crc_ok_frac": ok / nb_own, "payload_correct_frac": good / nb_own, "crc_ok_but_payload_wrong": wrong,
         "fcch_found_frac": float((np.abs(toa_err) <= 2).mean()),
         "esn0_db": esn0, "int16_peak": peak_i16, "generation_s": gen_s,
     }
@@ -950,6 +984,10 @@ def run_gpu_arm(args):
         torch.cuda.empty_cache()
         wideband = run_wideband(L, torch, dev, args.arfcns, args.bursts_per_arfcn, min(args.steps, 5), seed=4242 + rank,
                                 world=world, dist=dist if world > 1 else None)
+        if world > 1:                      # and ONE recording shared by all GPUs (all-gather over NVLink): strong scaling
+            torch.cuda.empty_cache()
+            wideband["shared_capture"] = run_wideband(L, torch, dev, args.arfcns, args.bursts_per_arfcn, min(args.steps, 5),
+                                                      seed=4242, world=world, dist=dist, shared=True, rank=rank)
 
     if rank != 0:
         if world > 1:

@@ -267,6 +267,11 @@ int gmr1b200_channelize(void *plan, const void *wide, int iq_format, int64_t n_w
 	ra.sched_i = d->sched_i; ra.sched_j = d->sched_j; ra.sched_acc = d->sched_acc; ra.filt = d->filt; ra.dfilt = d->dfilt;
 	ra.tpf = p.tpf; ra.rows_max = rows_max; ra.span_max = span_max; ra.tile_out = to; ra.out = d_out; ra.out_stride = out_stride; ra.n_out = n_out;
 	cudaError_t e = cudaSuccess;
+	// the plan's copy stream and event ring serve one call at a time: host-fed calls on one plan queue up here (they
+	// only enqueue; device-resident calls do not take the lock)
+	std::unique_lock<std::mutex> feed_lock(pl->mu, std::defer_lock);
+	if (wide_on_host)
+		feed_lock.lock();
 	if (wide_on_host) {                    // the copy stream starts behind the allocation of its target
 		cudaEvent_t ev = feed->ev[feed->next++ % N_EV];
 		if ((e = cudaEventRecord(ev, st)) == cudaSuccess)
