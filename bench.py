@@ -350,6 +350,19 @@ def run_configs(L, torch, dev, peak_gbs, cores, scale, reps, n_check):
 # ------------------------------------------------------------------------------------------------
 # the end-to-end step of several GPUs from ONE process (library device pool, csrc/api_multi.cu)
 # ------------------------------------------------------------------------------------------------
+def capture_shares(n_wide, n_arfcn, world, rank):
+    """one wideband recording shared by `world` ranks: rank r feeds the time slice [lo, hi) of its n_wide samples (slices
+    of n_slice samples, the last one ragged) and receives the ARFCNs a with a mod world == r"""
+    n_slice = -(-n_wide // world)
+    lo = min(n_wide, rank * n_slice)
+    return {"n_slice": n_slice, "lo": lo, "hi": min(n_wide, lo + n_slice), "own": np.arange(rank, n_arfcn, world)}
+
+
+def burst_rows(own, per):
+    """rows of a [n_arfcn * per] burst table (ARFCN-major) that belong to the ARFCNs `own`"""
+    return (np.asarray(own)[:, None] * per + np.arange(per)[None, :]).reshape(-1)
+
+
 def run_wideband(L, torch, dev, n_arfcn, per_arfcn, steps, seed=4242, world=1, dist=None, shared=False, rank=0):
     """SURVEY 8f N3 in front of the headline workload: the SAME receive work (one FCCH acquisition per ARFCN + per_arfcn
     BCCH / DC6 bursts per ARFCN, demod + decode), but the input is ONE wideband recording of all ARFCNs (int16 I/Q at
@@ -414,15 +427,15 @@ def run_wideband(L, torch, dev, n_arfcn, per_arfcn, steps, seed=4242, world=1, d
     del streams
     peak_i16 = int(wide.abs().max())
     shared = shared and world > 1
-    own = np.arange(rank, n_arfcn, world) if shared else np.arange(n_arfcn)      # the ARFCNs this rank receives
+    share = capture_shares(n_wide, n_arfcn, world if shared else 1, rank if shared else 0)
+    own = share["own"]                     # the ARFCNs this rank receives
     n_own = len(own)
     own_idx = d(own.astype(np.int32)) if shared else None
     if shared:
-        n_slice = -(-n_wide // world)
+        n_slice, lo_s, hi_s = share["n_slice"], share["lo"], share["hi"]
         wide_full = torch.zeros((world * n_slice, 2), dtype=torch.int16, device=dev)
         my_slice = torch.empty((n_slice, 2), dtype=torch.int16, device=dev)
         host_wide = torch.zeros((n_slice, 2), dtype=torch.int16).pin_memory()
-        lo_s, hi_s = rank * n_slice, min(n_wide, (rank + 1) * n_slice)
         host_wide[:hi_s - lo_s].copy_(wide[lo_s:hi_s])
         wide_full[:n_wide].copy_(wide)
         wide = wide_full[:n_wide]
@@ -435,7 +448,7 @@ def run_wideband(L, torch, dev, n_arfcn, per_arfcn, steps, seed=4242, world=1, d
     # window offsets inside the channelised streams: row stride n_out, everything delay_out later
     res, sel = {}, {}
     for kind in ("bcch", "dc6"):
-        sel[kind] = (own[:, None] * n_b[kind] + np.arange(n_b[kind])[None, :]).reshape(-1)      # this rank's bursts
+        sel[kind] = burst_rows(own, n_b[kind])             # this rank's bursts
         n = len(sel[kind])
         a = np.repeat(own, n_b[kind]).astype(np.int64)
         i_loc = np.repeat(np.arange(n_own, dtype=np.int64), n_b[kind])
