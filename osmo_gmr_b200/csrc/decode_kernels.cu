@@ -168,7 +168,9 @@ __global__ void __launch_bounds__(tpc_threads(PAIR)) decode_tpc_kernel(const Dec
 				const int tt = idx / NROW, r = idx - tt * NROW;
 				const uint16_t w = s_src[r];
 				const int age = (w >> 10) & 3, sidx = w & G_IDX;
-				const int u = age == 0 ? base + tt : s_prev[age - 1][tt];
+				// units behind the tile's last one read unit 0 (a valid address; the value is dropped): base + tt may lie
+				// behind the batch (found by compute-sanitizer on a 6-burst TCH9 batch)
+				const int u = tt >= cnt ? -1 : age == 0 ? base + tt : s_prev[age - 1][tt];
 				ok[e] = tt < cnt && u >= 0;
 				flip[e] = (w & G_FLIP) != 0;
 				const size_t uu = (size_t)max(u, 0);
