@@ -140,3 +140,58 @@ def test_caller_descriptors_must_be_consistent(gpu_lib):
     assert run(good, np.array([-1, wl], np.int64)) == -errno.EINVAL
     assert L.kernel_launches() == before
     assert run(good, np.array([wl, 0], np.int64)) == 0
+
+
+def test_round2_entry_points_reject_malformed_calls(gpu_lib):
+    """the entry points added around the path (channeliser, vocoder stream, FCCH grid, kernel switches): -EINVAL with
+    a message for malformed calls, empty batches are no-ops, switches report the previous setting"""
+    import ctypes
+    L = gpu_lib
+    h = ctypes.c_void_p()
+    for n_chans, sps in ((15, 4), (0, 4), (4098, 4), (2 * 37, 4), (16, 0), (16, 17)):      # odd, empty, too many, prime > 31, sps
+        assert L.c.gmr1b200_chan_create(n_chans, sps, ctypes.byref(h)) == -errno.EINVAL
+        assert b"chan_create" in L.c.gmr1b200_last_error()
+    assert L.c.gmr1b200_chan_create(16, 4, None) == -errno.EINVAL
+    assert L.c.gmr1b200_chan_create(16, 4, ctypes.byref(h)) == 0
+    assert L.c.gmr1b200_chan_out_len(h, -1) == -errno.EINVAL and L.c.gmr1b200_chan_out_len(h, 7) == 0
+    x = np.zeros((100, 2), np.int16)
+    out = np.zeros((1, 64, 2), np.float32)
+    L.call("gmr1b200_channelize", h.value, x, 1, 7, None, 1, out, 64, None)          # shorter than one bank step: no output
+    L.call("gmr1b200_channelize", h.value, x, 1, 100, None, 0, out, 64, None)        # no stream wanted
+    assert not out.any()
+    for args in ((None, x, 1, 100, None, 1, out, 64, None), (h.value, None, 1, 100, None, 1, out, 64, None),
+                 (h.value, x, 1, 100, None, 17, out, 64, None), (h.value, x, 1, -1, None, 1, out, 64, None)):
+        with pytest.raises(Gmr1Error) as e:
+            L.call("gmr1b200_channelize", *args)
+        assert f"rc={-errno.EINVAL}" in str(e.value)
+    L.c.gmr1b200_chan_destroy(h)
+    L.c.gmr1b200_chan_destroy(None)
+    # vocoder stream
+    F = 4
+    rec, dat = np.zeros((2, F, 12), np.int32), np.zeros((2, F, 20), np.uint8)
+    fn, nfr = np.zeros((2, F), np.int32), np.zeros(2, np.int32)
+    voice, flag, nv = np.zeros((2, 2 * F, 10), np.uint8), np.zeros((2, 2 * F), np.uint8), np.full(2, -1, np.int32)
+    L.call("gmr1b200_tch3_voice_stream_batch", rec, dat, fn, nfr, 0, F, voice, flag, nv, None, None)       # n = 0
+    assert (nv == -1).all()
+    L.call("gmr1b200_tch3_voice_stream_batch", rec, dat, fn, nfr, 2, F, voice, flag, nv, None, None)       # no call at all
+    assert (nv == 0).all() and (flag == 2).all()
+    for args in ((None, dat, fn, nfr, 2, F, voice, flag, nv, None, None), (rec, dat, fn, nfr, 2, 0, voice, flag, nv, None, None),
+                 (rec, dat, fn, nfr, -1, F, voice, flag, nv, None, None), (rec, dat, fn, nfr, 2, F, voice, None, nv, None, None)):
+        with pytest.raises(Gmr1Error) as e:
+            L.call("gmr1b200_tch3_voice_stream_batch", *args)
+        assert f"rc={-errno.EINVAL}" in str(e.value)
+    # FCCH grid: shift count, missing outputs, window shorter than the burst
+    W = 117 * SPS + 40
+    iq = np.zeros((1, W, 2), np.float32)
+    toa = np.zeros((17, 1), np.int32)
+    g = np.zeros(17, np.float32)
+    for args in ((0, iq, W, None, W, W, SPS, g, 17, toa, None, 1, None), (0, iq, W, None, W, W, SPS, g, 0, toa, None, 1, None),
+                 (0, iq, W, None, W, W, SPS, None, 2, toa, None, 1, None), (0, iq, W, None, W, W, SPS, g, 2, None, None, 1, None),
+                 (0, iq, W, None, W, 100, SPS, g, 2, toa, None, 1, None)):
+        with pytest.raises(Gmr1Error) as e:
+            L.call("gmr1b200_fcch_rough_grid_batch", *args)
+        assert f"rc={-errno.EINVAL}" in str(e.value)
+    # switches: return the previous setting
+    for name, default in (("gmr1b200_set_fcch_fft", 1), ("gmr1b200_set_chan_generic", 0), ("gmr1b200_set_demod_generic", 0)):
+        fn_ = getattr(L.c, name)
+        assert fn_(1 - default) == default and fn_(default) == 1 - default and fn_(default) == default
