@@ -561,6 +561,22 @@ int64_t gmr1b200_chan_out_len(void *plan, int64_t n_wide);
  * asynchronous); the results are the same as for one piece. */
 int gmr1b200_channelize(void *plan, const void *wide, int iq_format, int64_t n_wide, const int32_t *chan_idx, int n_wanted,
                         float *out, int64_t out_stride, void *stream);
+/* Streaming form: consecutive blocks of ONE endless recording (what the reference's flowgraph does with its SDR source).
+ * The state keeps what the filters still need of the past - the last 18 bank steps of samples, the last rows of the
+ * bank's output the 30-tap resampler phases reach back to, the resampler's phase walk - on the device, so the blocks
+ * may have any length (a fraction of a bank step up to seconds) and the concatenated outputs are, bit for bit, what
+ * gmr1b200_channelize makes of the whole recording at once.  One state per recording and device; calls on one state
+ * must not overlap and should use one CUDA stream.
+ *   create   chan_idx [n_wanted] bank channels (host or device memory, copied), NULL = channels 0 .. n_wanted-1
+ *   push     wide: n_wide NEW samples (host or device memory; iq_format as above, fixed for the life of the state);
+ *            out [n_wanted][out_stride] complex float receives this block's outputs from column 0, *n_out (host) their
+ *            number per channel - 0 while less than a bank step has arrived; out_stride >= chan_stream_max_out(n_wide)
+ *   max_out  upper bound of the outputs one push of n_wide samples can produce */
+int gmr1b200_chan_stream_create(void *plan, const int32_t *chan_idx, int n_wanted, void **state);
+void gmr1b200_chan_stream_destroy(void *state);
+int64_t gmr1b200_chan_stream_max_out(void *state, int64_t n_wide);
+int gmr1b200_chan_stream_push(void *state, const void *wide, int iq_format, int64_t n_wide, float *out, int64_t out_stride,
+                              int64_t *n_out, void *stream);
 /* Kernel selection switch (testing / A-B measurements): banks of 64 .. 2048 channels, a power of two, run on a kernel
  * with register radix-16 butterflies and compile-time geometry; every other channel count (mixed radix, odd primes up
  * to 31) on the generic shared-memory Stockham kernel.  1 forces the generic kernel for every bank; both compute the

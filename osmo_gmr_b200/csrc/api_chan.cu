@@ -313,6 +313,275 @@ int gmr1b200_channelize(void *plan, const void *wide, int iq_format, int64_t n_w
 	return s.finish(e, "channelize kernels");
 }
 
+// ---- streaming: consecutive blocks of one endless recording ------------------------------------------------------------
+namespace {
+
+struct ChanStream {
+	Plan *pl = nullptr;
+	int dev = 0, n_wanted = 0, fmt = -1;
+	int32_t *d_idx = nullptr;              // [n_wanted] or NULL (identity)
+	ChanWalk walk;
+	int64_t s_total = 0, s_base = 0;       // samples received / first sample kept in `wide`
+	int64_t m_done = 0, r_base = 0;        // bank steps made / first bank row kept in `mid`
+	int64_t n_done = 0;                    // outputs delivered per channel
+	char *wide[2] = {nullptr, nullptr};    // [cap_wide] bytes, ping-pong: history + the new block
+	float2 *mid[2] = {nullptr, nullptr};   // [cap_rows][n_chans]
+	size_t cap_wide = 0, cap_rows = 0;
+	int cur_w = 0, cur_m = 0;
+	int32_t *d_si = nullptr; uint8_t *d_sj = nullptr; float *d_sa = nullptr; size_t cap_sched = 0;
+	int32_t *h_si = nullptr; uint8_t *h_sj = nullptr; float *h_sa = nullptr; size_t cap_hsched = 0;   // page-locked
+	cudaEvent_t h_free = nullptr;          // the page-locked walk of the previous block has been read
+	std::vector<int32_t> vi; std::vector<uint8_t> vj; std::vector<float> va;
+};
+
+void stream_free(ChanStream *cs)
+{
+	if (!cs)
+		return;
+	int cur = 0;
+	cudaGetDevice(&cur);
+	cudaSetDevice(cs->dev);
+	cudaDeviceSynchronize();
+	for (int k = 0; k < 2; k++) {
+		cudaFree(cs->wide[k]);
+		cudaFree(cs->mid[k]);
+	}
+	cudaFree(cs->d_idx); cudaFree(cs->d_si); cudaFree(cs->d_sj); cudaFree(cs->d_sa);
+	cudaFreeHost(cs->h_si); cudaFreeHost(cs->h_sj); cudaFreeHost(cs->h_sa);
+	if (cs->h_free)
+		cudaEventDestroy(cs->h_free);
+	cudaSetDevice(cur);
+	delete cs;
+}
+
+}  // namespace
+
+int gmr1b200_chan_stream_create(void *plan, const int32_t *chan_idx, int n_wanted, void **state)
+{
+	Plan *pl = (Plan *)plan;
+	if (!pl || !state || n_wanted < 1 || (!chan_idx && n_wanted > pl->p.n_chans))
+		return set_err(-EINVAL, "chan_stream_create: bad argument");
+	std::vector<int32_t> idx;
+	if (chan_idx) {
+		idx.resize(n_wanted);
+		cudaError_t e = cudaMemcpy(idx.data(), chan_idx, sizeof(int32_t) * n_wanted, cudaMemcpyDefault);   // host or device list
+		if (e != cudaSuccess)
+			return cuda_rc(e, "chan_stream_create: channel list");
+		for (int i = 0; i < n_wanted; i++)
+			if (idx[i] < 0 || idx[i] >= pl->p.n_chans)
+				return set_err(-EINVAL, "chan_stream_create: channel index outside the bank");
+	}
+	ChanStream *cs = new (std::nothrow) ChanStream;
+	if (!cs)
+		return set_err(-ENOMEM, "chan_stream_create: out of memory");
+	cs->pl = pl;
+	cs->n_wanted = n_wanted;
+	cs->walk = chan_walk_start(pl->p);
+	cudaError_t e = cudaGetDevice(&cs->dev);
+	if (e == cudaSuccess)
+		e = cudaEventCreateWithFlags(&cs->h_free, cudaEventDisableTiming);
+	if (e == cudaSuccess && chan_idx) {
+		e = cudaMalloc((void **)&cs->d_idx, sizeof(int32_t) * n_wanted);
+		if (e == cudaSuccess)
+			e = cudaMemcpy(cs->d_idx, idx.data(), sizeof(int32_t) * n_wanted, cudaMemcpyHostToDevice);
+	}
+	if (e != cudaSuccess) {
+		stream_free(cs);
+		return cuda_rc(e, "chan_stream_create");
+	}
+	*state = cs;
+	return 0;
+}
+
+void gmr1b200_chan_stream_destroy(void *state) { stream_free((ChanStream *)state); }
+
+int64_t gmr1b200_chan_stream_max_out(void *state, int64_t n_wide)
+{
+	ChanStream *cs = (ChanStream *)state;
+	if (!cs || n_wide < 0)
+		return set_err(-EINVAL, "chan_stream_max_out: bad argument");
+	const ChanPlan &p = cs->pl->p;
+	const int64_t steps = n_wide / (p.n_chans / 2) + 2;     // the new block plus what was left over from the blocks before
+	return (int64_t)ceil((double)steps * p.resamp) + 2;
+}
+
+int gmr1b200_chan_stream_push(void *state, const void *wide, int iq_format, int64_t n_wide, float *out, int64_t out_stride,
+                              int64_t *n_out, void *stream)
+{
+	ChanStream *cs = (ChanStream *)state;
+	if (!cs || !n_out || n_wide < 0 || (n_wide && !wide) || iq_format < 0 || iq_format > 1)
+		return set_err(-EINVAL, "chan_stream_push: bad argument");
+	if (cs->fmt >= 0 && cs->fmt != iq_format)
+		return set_err(-EINVAL, "chan_stream_push: the sample format of a stream cannot change");
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (dev != cs->dev)
+		return set_err(-EINVAL, "chan_stream_push: the stream lives on another device");
+	*n_out = 0;
+	if (n_wide == 0)
+		return 0;
+	cs->fmt = iq_format;
+	ChanPlan &p = cs->pl->p;
+	const int N = p.n_chans, D = N / 2, P = p.taps_per_branch;
+	const size_t sb = iq_format == 0 ? sizeof(float2) : 2 * sizeof(int16_t);
+	cudaStream_t st = (cudaStream_t)stream;
+	ChanPlan::Dev *d = nullptr;
+	{
+		std::lock_guard<std::mutex> lk(cs->pl->mu);
+		cudaError_t e = plan_device(*cs->pl, 0, &d);
+		if (e != cudaSuccess)
+			return cuda_rc(e, "chan_stream_push: table upload");
+	}
+	// what the next bank step (m_done) and the next output (the walk's input position) still need of the past
+	const int64_t s_keep0 = (cs->m_done - 2 * (int64_t)(P - 1)) * D - (N - 1);
+	const int64_t s_keep = s_keep0 < cs->s_base ? cs->s_base : s_keep0;
+	const int64_t r_keep0 = cs->walk.i_in - (p.tpf - 1);
+	const int64_t r_keep = r_keep0 < cs->r_base ? cs->r_base : r_keep0;
+	const int64_t s_new = cs->s_total + n_wide;
+	const int64_t m_avail = s_new / D;
+	// the outputs of this block must fit: checked before anything changes (the walk has not passed step m_done)
+	if (m_avail > cs->m_done) {
+		const int64_t bound = (int64_t)ceil((double)(m_avail - cs->m_done + 1) * p.resamp) + 2;
+		if (!out || out_stride < bound)
+			return set_err(-EINVAL, "chan_stream_push: out NULL or out_stride smaller than gmr1b200_chan_stream_max_out(n_wide)");
+	}
+	cudaError_t e = cudaSuccess;
+	// ---- samples: history + new block into the other buffer
+	{
+		const size_t need = (size_t)(s_new - s_keep) * sb;
+		const int nxt = cs->cur_w ^ 1;
+		if (need > cs->cap_wide) {                              // grow both (the old one is still read below)
+			const size_t cap = need + need / 2 + 4096;
+			char *nw[2] = {nullptr, nullptr};
+			if ((e = cudaMalloc((void **)&nw[0], cap)) != cudaSuccess || (e = cudaMalloc((void **)&nw[1], cap)) != cudaSuccess) {
+				cudaFree(nw[0]);
+				return cuda_rc(e, "chan_stream_push: sample buffer");
+			}
+			if (cs->s_total > s_keep)
+				e = cudaMemcpyAsync(nw[nxt], cs->wide[cs->cur_w] + (size_t)(s_keep - cs->s_base) * sb,
+				                    (size_t)(cs->s_total - s_keep) * sb, cudaMemcpyDeviceToDevice, st);
+			cudaStreamSynchronize(st);
+			cudaFree(cs->wide[0]);
+			cudaFree(cs->wide[1]);
+			cs->wide[0] = nw[0]; cs->wide[1] = nw[1]; cs->cap_wide = cap;
+		} else if (cs->s_total > s_keep) {
+			e = cudaMemcpyAsync(cs->wide[nxt], cs->wide[cs->cur_w] + (size_t)(s_keep - cs->s_base) * sb,
+			                    (size_t)(cs->s_total - s_keep) * sb, cudaMemcpyDeviceToDevice, st);
+		}
+		if (e == cudaSuccess)
+			e = cudaMemcpyAsync(cs->wide[nxt] + (size_t)(cs->s_total - s_keep) * sb, wide, (size_t)n_wide * sb, cudaMemcpyDefault, st);
+		if (e != cudaSuccess)
+			return cuda_rc(e, "chan_stream_push: sample copy");
+		cs->cur_w = nxt;
+		cs->s_base = s_keep;
+		cs->s_total = s_new;
+	}
+	if (m_avail <= cs->m_done)
+		return 0;                                               // not a whole bank step yet
+	// ---- bank rows: history + new rows into the other buffer
+	{
+		const size_t need = (size_t)(m_avail - r_keep);
+		const int nxt = cs->cur_m ^ 1;
+		const size_t row_b = (size_t)N * sizeof(float2);
+		if (need > cs->cap_rows) {
+			const size_t cap = need + need / 2 + 64;
+			float2 *nm[2] = {nullptr, nullptr};
+			if ((e = cudaMalloc((void **)&nm[0], cap * row_b)) != cudaSuccess || (e = cudaMalloc((void **)&nm[1], cap * row_b)) != cudaSuccess) {
+				cudaFree(nm[0]);
+				return cuda_rc(e, "chan_stream_push: bank buffer");
+			}
+			if (cs->m_done > r_keep)
+				e = cudaMemcpyAsync(nm[nxt], cs->mid[cs->cur_m] + (size_t)(r_keep - cs->r_base) * N, (size_t)(cs->m_done - r_keep) * row_b,
+				                    cudaMemcpyDeviceToDevice, st);
+			cudaStreamSynchronize(st);
+			cudaFree(cs->mid[0]);
+			cudaFree(cs->mid[1]);
+			cs->mid[0] = nm[0]; cs->mid[1] = nm[1]; cs->cap_rows = cap;
+		} else if (cs->m_done > r_keep) {
+			e = cudaMemcpyAsync(cs->mid[nxt], cs->mid[cs->cur_m] + (size_t)(r_keep - cs->r_base) * N, (size_t)(cs->m_done - r_keep) * row_b,
+			                    cudaMemcpyDeviceToDevice, st);
+		}
+		if (e != cudaSuccess)
+			return cuda_rc(e, "chan_stream_push: bank history");
+		cs->cur_m = nxt;
+		cs->r_base = r_keep;
+	}
+	PfbArgs pa = {};
+	pa.wide = cs->wide[cs->cur_w] - (ptrdiff_t)(cs->s_base * (int64_t)sb);      // absolute sample index -> buffer
+	pa.n_wide = cs->s_total; pa.n_chans = N; pa.taps_per_branch = P;
+	pa.taps = d->taps; pa.twiddle = d->twiddle; pa.n_stage = (int)p.radix.size();
+	for (int i = 0; i < pa.n_stage; i++)
+		pa.radix[i] = p.radix[i];
+	pa.mid = cs->mid[cs->cur_m] - (ptrdiff_t)(cs->r_base * N);                  // absolute step -> buffer row
+	pa.n_steps = m_avail; pa.m_begin = cs->m_done; pa.m_end = m_avail;
+	if ((e = launch_pfb(pa, iq_format, st)) != cudaSuccess)
+		return cuda_rc(e, "chan_stream_push: bank kernel");
+	g_launches.fetch_add(1);
+	cs->m_done = m_avail;
+	// ---- outputs whose newest input step exists now
+	cs->vi.clear(); cs->vj.clear(); cs->va.clear();
+	chan_walk(p, cs->walk, m_avail, cs->vi, cs->vj, cs->va, cs->r_base);
+	const size_t nn = cs->vi.size();
+	if (nn == 0)
+		return 0;
+	if (nn > cs->cap_sched) {
+		cudaStreamSynchronize(st);
+		cudaFree(cs->d_si); cudaFree(cs->d_sj); cudaFree(cs->d_sa);
+		cs->d_si = nullptr; cs->d_sj = nullptr; cs->d_sa = nullptr;
+		const size_t cap = nn + nn / 2 + 256;
+		if ((e = cudaMalloc((void **)&cs->d_si, cap * 4)) != cudaSuccess || (e = cudaMalloc((void **)&cs->d_sj, cap)) != cudaSuccess ||
+		    (e = cudaMalloc((void **)&cs->d_sa, cap * 4)) != cudaSuccess)
+			return cuda_rc(e, "chan_stream_push: walk buffers");
+		cs->cap_sched = cap;
+	}
+	cudaEventSynchronize(cs->h_free);                           // the previous block's walk has left the page-locked arrays
+	if (nn > cs->cap_hsched) {
+		cudaFreeHost(cs->h_si); cudaFreeHost(cs->h_sj); cudaFreeHost(cs->h_sa);
+		cs->h_si = nullptr; cs->h_sj = nullptr; cs->h_sa = nullptr;
+		const size_t cap = nn + nn / 2 + 256;
+		if ((e = cudaMallocHost((void **)&cs->h_si, cap * 4)) != cudaSuccess || (e = cudaMallocHost((void **)&cs->h_sj, cap)) != cudaSuccess ||
+		    (e = cudaMallocHost((void **)&cs->h_sa, cap * 4)) != cudaSuccess)
+			return cuda_rc(e, "chan_stream_push: walk staging");
+		cs->cap_hsched = cap;
+	}
+	memcpy(cs->h_si, cs->vi.data(), nn * 4);
+	memcpy(cs->h_sj, cs->vj.data(), nn);
+	memcpy(cs->h_sa, cs->va.data(), nn * 4);
+	cudaMemcpyAsync(cs->d_si, cs->h_si, nn * 4, cudaMemcpyHostToDevice, st);
+	cudaMemcpyAsync(cs->d_sj, cs->h_sj, nn, cudaMemcpyHostToDevice, st);
+	cudaMemcpyAsync(cs->d_sa, cs->h_sa, nn * 4, cudaMemcpyHostToDevice, st);
+	cudaEventRecord(cs->h_free, st);
+	const int go = resamp_group_outputs();
+	auto span_of = [&](int step) {
+		int m = 0;
+		for (size_t n0 = 0; n0 < nn; n0 += step) {
+			const size_t n1 = (n0 + step < nn ? n0 + step : nn) - 1;
+			const int rows = cs->vi[n1] - cs->vi[n0] + p.tpf;
+			m = rows > m ? rows : m;
+		}
+		return m;
+	};
+	Stage s(stream);
+	ResampArgs ra = {};
+	ra.mid = cs->mid[cs->cur_m]; ra.n_steps = m_avail - cs->r_base; ra.n_chans = N; ra.chan_idx = cs->d_idx; ra.n_wanted = cs->n_wanted;
+	ra.sched_i = cs->d_si; ra.sched_j = cs->d_sj; ra.sched_acc = cs->d_sa; ra.filt = d->filt; ra.dfilt = d->dfilt;
+	ra.tpf = p.tpf; ra.span_max = span_of(go);
+	ra.tile_out = resamp_tile_outputs(span_of(64), ra.span_max, p.tpf);
+	ra.rows_max = span_of(ra.tile_out);
+	ra.out = (float2 *)s.out(out, (size_t)cs->n_wanted * (size_t)out_stride * 2);
+	ra.out_stride = out_stride; ra.n_out = (int64_t)nn; ra.n_begin = 0; ra.n_end = (int64_t)nn;
+	if (s.failed())
+		return s.finish(cudaSuccess, "chan_stream_push: staging");
+	if ((void *)ra.out != (void *)out)                          // staged host output: the row tails travel back too
+		cudaMemsetAsync(ra.out, 0, (size_t)cs->n_wanted * (size_t)out_stride * sizeof(float2), st);
+	e = launch_resamp(ra, st);
+	if (e == cudaSuccess)
+		g_launches.fetch_add(1);
+	cs->n_done += (int64_t)nn;
+	*n_out = (int64_t)nn;
+	return s.finish(e, "chan_stream_push kernels");
+}
+
 int gmr1b200_set_chan_generic(int on)
 {
 	static std::atomic<int> cur{0};

@@ -91,6 +91,12 @@ struct ChanPlan {
 	} dev[64];
 };
 
+struct ChanWalk { int64_t i_in; int j; float acc; };            // the resampler's phase walk between two outputs
+ChanWalk chan_walk_start(const ChanPlan &p);
+// outputs whose newest input step lies below n_steps, appended to the three vectors (input steps relative to i_base)
+void chan_walk(const ChanPlan &p, ChanWalk &w, int64_t n_steps, std::vector<int32_t> &out_i, std::vector<uint8_t> &out_j,
+               std::vector<float> &out_acc, int64_t i_base);
+
 int  chan_plan_init(ChanPlan &p, int n_chans, int sps);         // 0 / -EINVAL
 void chan_plan_walk(ChanPlan &p, int64_t n_steps);              // extend the phase walk to cover n_steps input steps
 int64_t chan_plan_out_len(ChanPlan &p, int64_t n_wide);         // outputs per channel for n_wide wideband samples

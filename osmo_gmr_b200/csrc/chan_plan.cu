@@ -122,18 +122,21 @@ int chan_plan_init(ChanPlan &p, int n_chans, int sps)
 
 // pfb_arb_resampler::filter's walk: every output takes filter j at input i with weight acc; then
 // acc += flt_rate, j += dec_rate + floor(acc), acc = fmodf(acc, 1), and whole multiples of 32 in j move the input on.
-void chan_plan_walk(ChanPlan &p, int64_t n_steps)
+// The walk is resumable: `w` carries (input position, filter, weight) from one call to the next, so a streaming caller
+// gets exactly the outputs a one-shot caller gets.
+void chan_walk(const ChanPlan &p, ChanWalk &w, int64_t n_steps, std::vector<int32_t> &out_i, std::vector<uint8_t> &out_j,
+               std::vector<float> &out_acc, int64_t i_base)
 {
 	const int dec_rate = (int)floor(FLT / p.resamp);
 	const float flt_rate = (float)(FLT / p.resamp - dec_rate);
-	int64_t i_in = p.sched_in;
-	int j = p.walk_j;
-	float acc = p.walk_acc;
+	int64_t i_in = w.i_in;
+	int j = w.j;
+	float acc = w.acc;
 	while (i_in < n_steps) {
 		while (j < FLT) {
-			p.sched_i.push_back((int32_t)i_in);
-			p.sched_j.push_back((uint8_t)j);
-			p.sched_acc.push_back(acc);
+			out_i.push_back((int32_t)(i_in - i_base));
+			out_j.push_back((uint8_t)j);
+			out_acc.push_back(acc);
 			acc += flt_rate;
 			j += dec_rate + (int)floorf(acc);
 			acc = fmodf(acc, 1.0f);
@@ -141,9 +144,26 @@ void chan_plan_walk(ChanPlan &p, int64_t n_steps)
 		i_in += j / FLT;
 		j = j % FLT;
 	}
-	p.sched_in = i_in;
-	p.walk_j = j;
-	p.walk_acc = acc;
+	w.i_in = i_in;
+	w.j = j;
+	w.acc = acc;
+}
+
+ChanWalk chan_walk_start(const ChanPlan &p)
+{
+	ChanWalk w;
+	w.i_in = 0;
+	w.j = ((int)p.taps_resamp.size() / 2) % FLT;           // pfb_arb_resampler: d_last_filter = (ntaps / 2) % nfilts
+	w.acc = 0.0f;
+	return w;
+}
+
+void chan_plan_walk(ChanPlan &p, int64_t n_steps)
+{
+	ChanWalk w;
+	w.i_in = p.sched_in; w.j = p.walk_j; w.acc = p.walk_acc;
+	chan_walk(p, w, n_steps, p.sched_i, p.sched_j, p.sched_acc, 0);
+	p.sched_in = w.i_in; p.walk_j = w.j; p.walk_acc = w.acc;
 }
 
 int64_t chan_plan_out_len(ChanPlan &p, int64_t n_wide)

@@ -86,6 +86,8 @@ class Lib:
         "gmr1b200_chan_info": [_P, _P],
         "gmr1b200_chan_taps": [_P, _P, _I, _P, _I],
         "gmr1b200_channelize": [_P, _P, _I, _L, _P, _I, _P, _L, _P],
+        "gmr1b200_chan_stream_create": [_P, _P, _I, _P],
+        "gmr1b200_chan_stream_push": [_P, _P, _I, _L, _P, _L, _P, _P],
         "gmr1b200_synth_wideband": [_P, _P, _L, _L, _P, _I, _F, _F, ctypes.c_uint64, _P, _I, _L, _P],
         "gmr1b200_set_sync_accumulator_reset": [_I],
         "gmr1b200_set_demod_generic": [_I],
@@ -131,6 +133,10 @@ class Lib:
         self.c.gmr1b200_chan_destroy.restype = None
         self.c.gmr1b200_chan_out_len.argtypes = [_P, _L]
         self.c.gmr1b200_chan_out_len.restype = _L
+        self.c.gmr1b200_chan_stream_destroy.argtypes = [_P]
+        self.c.gmr1b200_chan_stream_destroy.restype = None
+        self.c.gmr1b200_chan_stream_max_out.argtypes = [_P, _L]
+        self.c.gmr1b200_chan_stream_max_out.restype = _L
 
     # -- helpers
     def _chk(self, rc, what):

@@ -138,6 +138,62 @@ def test_host_recording_travels_in_pieces(gpu_lib):
     L.c.gmr1b200_chan_destroy(h)
 
 
+@pytest.mark.parametrize("n_chans,fmt", [(64, 1), (12, 0), (256, 1)])
+def test_streaming_blocks_equal_the_whole_recording(gpu_lib, n_chans, fmt):
+    """gmr1b200_chan_stream_push over ragged blocks (single samples, fractions of a bank step, odd sizes, long blocks,
+    an empty push) delivers, concatenated, bit for bit what gmr1b200_channelize makes of the whole recording: fast and
+    generic bank kernel, int16 and complex-float samples, host and device blocks, a channel list."""
+    import torch
+    L = gpu_lib
+    rng = np.random.default_rng(100 + n_chans)
+    n_wide = n_chans * 700 + 13
+    if fmt == 1:
+        x = rng.integers(-20000, 20000, (n_wide, 2), dtype=np.int16)
+    else:
+        x = (rng.standard_normal(n_wide) + 1j * rng.standard_normal(n_wide)).astype(np.complex64)
+    h = make_plan(L, n_chans)
+    chans = sorted(set([0, 3, n_chans // 2, n_chans - 1]))
+    whole = channelize(L, h, x, fmt, chans)
+    st = ctypes.c_void_p()
+    assert L.c.gmr1b200_chan_stream_create(h, np.asarray(chans, np.int32).ctypes.data_as(ctypes.c_void_p), len(chans),
+                                           ctypes.byref(st)) == 0
+    sizes = [1, 1, n_chans // 2 - 2, 1, 0, 7, n_chans * 3 + 5, n_chans // 2, 5 * n_chans, 123, n_chans * 200 + 1]
+    pos, parts, k = 0, [], 0
+    while pos < n_wide:
+        nb = min(sizes[k % len(sizes)], n_wide - pos)
+        k += 1
+        cap = int(L.c.gmr1b200_chan_stream_max_out(st, nb))
+        blk = x[pos:pos + nb]
+        buf = blk.view(np.float32) if fmt == 0 else blk
+        n_out = ctypes.c_int64(-1)
+        if k % 3 == 0 and nb:                        # a device-resident block and device output
+            dblk = torch.from_numpy(np.ascontiguousarray(buf)).cuda()
+            dout = torch.zeros((len(chans), max(cap, 1), 2), dtype=torch.float32, device="cuda")
+            L.call("gmr1b200_chan_stream_push", st.value, dblk, fmt, nb, dout, max(cap, 1), ctypes.addressof(n_out), None)
+            torch.cuda.synchronize()
+            o = dout.cpu().numpy().view(np.complex64)[..., 0]
+        else:
+            o = np.zeros((len(chans), max(cap, 1)), np.complex64)
+            L.call("gmr1b200_chan_stream_push", st.value, buf if nb else None, fmt, nb, o.view(np.float32), max(cap, 1),
+                   ctypes.addressof(n_out), None)
+        assert 0 <= n_out.value <= cap and not o[:, n_out.value:].any()
+        parts.append(o[:, :n_out.value].copy())
+        pos += nb
+    got = np.concatenate(parts, axis=1)
+    # the whole-recording call stops at n_wide // (n_chans / 2) bank steps, as the stream does
+    assert got.shape == whole.shape and got.shape[1] > 900
+    assert np.array_equal(got, whole)
+    # too small an output row is refused before anything changes
+    n_out = ctypes.c_int64(0)
+    o = np.zeros((len(chans), 2), np.complex64)
+    with pytest.raises(Exception) as e:
+        L.call("gmr1b200_chan_stream_push", st.value, x[:n_chans * 4], fmt, n_chans * 4, o.view(np.float32), 2,
+               ctypes.addressof(n_out), None)
+    assert f"rc={-errno.EINVAL}" in str(e.value)
+    L.c.gmr1b200_chan_stream_destroy(st)
+    L.c.gmr1b200_chan_destroy(h)
+
+
 def test_int16_recordings_and_device_pointers(gpu_lib):
     import torch
     L = gpu_lib
