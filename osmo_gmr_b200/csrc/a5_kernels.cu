@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "a5_bitslice.cuh"
 #include "launch.h"
 
 namespace gmr1 {
@@ -116,11 +117,120 @@ __global__ void __launch_bounds__(128) a5_kernel(const A5Args a)
 		emit(s, ul, a.nbits, word_ok);
 }
 
+// ---- 32 streams per thread (a5_bitslice.cuh): the form for large batches -----------------------------------------------
+// A warp takes 1024 consecutive units: bit l of lane t's words is unit base + 32 l + t.  The key bits are transposed
+// into that layout with warp votes (lane l holds the folded key of unit base + 32 l + tt, the vote over bit q is lane
+// tt's word of set-up step q), 32 set-up steps at a time so that the key words and the 81 state words fit the register
+// file.  The keystream leaves 32 clocks at a time: a 32 x 32 bit transpose turns "one word per clock" into "32 bits per
+// unit", which are spread to ubit bytes four at a time (one multiply) and stored as 32-bit words.
+constexpr int A5S_THREADS = 64;
+
+__global__ void __launch_bounds__(A5S_THREADS) a5_slice_kernel(const A5Args a)
+{
+	using namespace a5s;
+	const int lane = threadIdx.x & 31;
+	const int64_t base = ((int64_t)blockIdx.x * (A5S_THREADS / 32) + (threadIdx.x >> 5)) * 1024;
+	const int n_eff = a.n_dev ? min(a.n, *a.n_dev * (a.n_dev_mul ? a.n_dev_mul : 1)) : a.n;
+	if (base >= n_eff)
+		return;
+	const bool word_ok = ((a.stride & 3) == 0) && ((((uintptr_t)a.dl) | ((uintptr_t)a.ul)) & 3) == 0;
+	__shared__ uint32_t sw[32 * A5S_THREADS];
+	State s;
+	init(s);
+#pragma unroll 1
+	for (int half = 0; half < 2; half++) {
+		uint32_t kb[32];
+#pragma unroll
+		for (int q = 0; q < 32; q++)
+			kb[q] = 0;
+#pragma unroll 1
+		for (int tt = 0; tt < 32; tt++) {
+			const int64_t u = base + 32 * lane + tt;
+			uint64_t fk = 0;
+			if (u < n_eff && (a.alg ? a.alg[u] : a.alg0) == 1)
+				fk = folded_key(a.key + (size_t)u * 8, a.fn[u]);
+			const uint32_t part = (uint32_t)(fk >> (32 * half));
+#pragma unroll
+			for (int q = 0; q < 32; q++) {
+				const uint32_t w = __ballot_sync(0xffffffffu, (part >> q) & 1u);
+				kb[q] = lane == tt ? w : kb[q];
+			}
+		}
+#pragma unroll
+		for (int q = 0; q < 32; q++)
+			key_step(s, kb[q]);
+	}
+	force_bit0(s);
+#pragma unroll 1
+	for (int i = 0; i < 250; i++)
+		clock(s);
+#pragma unroll 1
+	for (int dir = 0; dir < 2; dir++) {
+		uint8_t *dst = dir ? a.ul : a.dl;
+		if (dir && !a.ul)
+			break;
+#pragma unroll 1
+		for (int b0 = 0; b0 < a.nbits; b0 += 32) {
+			uint32_t w[32];
+#pragma unroll
+			for (int c = 0; c < 32; c++) {
+				w[c] = 0;
+				if (b0 + c < a.nbits) {
+					clock(s);
+					w[c] = output(s);
+				}
+			}
+			if (!dst)
+				continue;
+			transpose32(w);
+			// the 32 words go through shared memory so that the store loop can run over the units at run time (unrolled
+			// 32 times it made the compiler hoist and spill 32 row addresses)
+			__syncwarp();
+#pragma unroll
+			for (int l = 0; l < 32; l++)
+				sw[l * A5S_THREADS + threadIdx.x] = w[l];
+			__syncwarp();
+#pragma unroll 1
+			for (int l = 0; l < 32; l++) {
+				const int64_t u = base + 32 * l + lane;
+				if (u >= n_eff)
+					break;
+				const int alg = a.alg ? a.alg[u] : a.alg0;
+				if (alg != 0 && alg != 1)          // A5/2..7 do not exist for GMR-1 (a5.c:73-76): rows left alone
+					continue;
+				const uint32_t bits = alg == 1 ? sw[l * A5S_THREADS + threadIdx.x] : 0u;
+				uint8_t *row = dst + (size_t)u * a.stride + b0;
+#pragma unroll
+				for (int b = 0; b < 32; b += 4) {
+					const uint32_t v = spread4(bits, b);
+					if (word_ok && b0 + b + 4 <= a.nbits)
+						*reinterpret_cast<uint32_t *>(row + b) = v;
+					else
+						for (int k = 0; k < 4 && b0 + b + k < a.nbits; k++)
+							row[b + k] = (uint8_t)(v >> (8 * k));
+				}
+			}
+		}
+	}
+}
+
+static std::atomic<int> g_a5_mode{-1};             // -1 by batch size, 0 one unit per thread, 1 bitsliced
+void a5_force_mode(int mode) { g_a5_mode.store(mode); }
+
 cudaError_t launch_a5(const A5Args &a, cudaStream_t st)
 {
 	if (a.n <= 0)
 		return cudaSuccess;
-	a5_kernel<<<(a.n + 127) / 128, 128, 0, st>>>(a);
+	// the bitsliced form needs whole warps of 1024 units to pay: below ~16 k units the one-unit-per-thread kernel
+	// fills the machine better (a call of a few channels runs on a single lane's worth of work either way)
+	const int mode = g_a5_mode.load();
+	const bool slice = mode < 0 ? a.n >= 16384 : mode == 1;
+	if (slice) {
+		const int warps = (a.n + 1023) / 1024, per = A5S_THREADS / 32;
+		a5_slice_kernel<<<(warps + per - 1) / per, A5S_THREADS, 0, st>>>(a);
+	} else {
+		a5_kernel<<<(a.n + 127) / 128, 128, 0, st>>>(a);
+	}
 	return cudaGetLastError();
 }
 

@@ -655,6 +655,15 @@ int gmr1b200_pi4cxpsk_mod_order_batch(const float *iq, int64_t iq_len, const int
 
 }  // extern "C"
 
+extern "C" int gmr1b200_set_a5_bitslice(int mode)
+{
+	static std::atomic<int> cur{-1};
+	const int m = mode < 0 ? -1 : (mode ? 1 : 0);
+	const int prev = cur.exchange(m);
+	a5_force_mode(m);
+	return prev;
+}
+
 extern "C" int gmr1b200_a5_batch(const int32_t *alg, int alg0, const uint8_t *key, const uint32_t *fn, int nbits,
                                  int stride, uint8_t *dl, uint8_t *ul, int n, void *stream)
 {

@@ -113,6 +113,7 @@ struct A5Args {
 	int32_t        n_dev_mul;    // ... times this factor (0 = 1): e.g. four A5 streams per FACCH3 codeword
 };
 cudaError_t launch_a5(const A5Args &a, cudaStream_t st);
+void a5_force_mode(int mode);           // tests / A-B: -1 by batch size, 0 one unit per thread, 1 bitsliced (32 units per thread)
 
 // ---- GSMTAP records of decoded units
 struct GsmtapArgs {

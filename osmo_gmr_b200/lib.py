@@ -93,6 +93,7 @@ class Lib:
         "gmr1b200_set_demod_generic": [_I],
         "gmr1b200_set_chan_generic": [_I],
         "gmr1b200_set_fcch_fft": [_I],
+        "gmr1b200_set_a5_bitslice": [_I],
         "gmr1b200_set_rx_lockstep": [_I],
         "gmr1b200_rx_call_batch": [_P, _L, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
         "gmr1b200_tch3_voice_stream_batch": [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P],

@@ -94,3 +94,51 @@ extern "C" int chan_emu_fft(int log2n, const float *in, float *out)
 	}
 	return -1;
 }
+
+// ---- A5/1, 32 streams per "thread" (osmo_gmr_b200/csrc/a5_bitslice.cuh) on the CPU -----------------------------------
+#include <stdint.h>
+#include <string.h>
+#include "a5_bitslice.cuh"
+
+// keys [32][8], fn [32] -> dl / ul [32][nbits] ubits (ul may be NULL), exactly as a5_slice_kernel produces them
+extern "C" void a5_emu_slice(const uint8_t *keys, const uint32_t *fn, int nbits, uint8_t *dl, uint8_t *ul)
+{
+	using namespace gmr1::a5s;
+	State s;
+	init(s);
+	uint64_t fk[32];
+	for (int l = 0; l < 32; l++)
+		fk[l] = folded_key(keys + 8 * l, fn[l]);
+	for (int q = 0; q < 64; q++) {
+		uint32_t kb = 0;
+		for (int l = 0; l < 32; l++)
+			kb |= (uint32_t)((fk[l] >> q) & 1u) << l;
+		key_step(s, kb);
+	}
+	force_bit0(s);
+	for (int i = 0; i < 250; i++)
+		clock(s);
+	for (int dir = 0; dir < 2; dir++) {
+		uint8_t *dst = dir ? ul : dl;
+		for (int b0 = 0; b0 < nbits; b0 += 32) {
+			uint32_t w[32];
+			for (int c = 0; c < 32; c++) {
+				if (b0 + c < nbits) {
+					clock(s);
+					w[c] = output(s);
+				} else
+					w[c] = 0;
+			}
+			transpose32(w);
+			if (dst)
+				for (int l = 0; l < 32; l++)
+					for (int b = 0; b < 32 && b0 + b < nbits; b += 4) {
+						const uint32_t v = spread4(w[l], b);
+						for (int k = 0; k < 4 && b0 + b + k < nbits; k++)
+							dst[(size_t)l * nbits + b0 + b + k] = (uint8_t)(v >> (8 * k));
+					}
+		}
+		if (!ul)
+			break;
+	}
+}

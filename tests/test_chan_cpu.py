@@ -131,7 +131,8 @@ def test_register_butterfly_fft_on_the_cpu():
     emu_dir = os.path.join(ROOT, "tests", "emu")
     so, src = os.path.join(emu_dir, "libchan_emu.so"), os.path.join(emu_dir, "chan_emu.cpp")
     hdr = os.path.join(ROOT, "osmo_gmr_b200", "csrc", "chan_fft.cuh")
-    if not os.path.exists(so) or max(os.path.getmtime(src), os.path.getmtime(hdr)) > os.path.getmtime(so):
+    hdr2 = os.path.join(ROOT, "osmo_gmr_b200", "csrc", "a5_bitslice.cuh")
+    if not os.path.exists(so) or max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(hdr2)) > os.path.getmtime(so):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-Wno-unknown-pragmas",
                                "-I" + os.path.dirname(hdr), "-o", so, src])
     emu = ctypes.CDLL(so)

@@ -62,12 +62,21 @@ def test_empty_and_single(gpu_lib, oracle):
     dp.check_simple(be, oracle, "bcch", CH["BCCH"], 424, 9, 29)               # < one tile
 
 
+@pytest.fixture(params=["thread", "bitsliced"])
+def a5_kernel(request, gpu_lib):
+    """the cipher streams from the one-unit-per-thread kernel and from the bitsliced one (32 units per thread,
+    csrc/a5_bitslice.cuh; the default from 16 384 units up)"""
+    prev = gpu_lib.c.gmr1b200_set_a5_bitslice(1 if request.param == "bitsliced" else 0)
+    yield request.param
+    gpu_lib.c.gmr1b200_set_a5_bitslice(prev)
+
+
 @pytest.mark.parametrize("nbits,stride", [(208, 208), (658, 658), (658, 660), (96, 100), (5, 7)])
-def test_a5_batch(gpu_lib, oracle, nbits, stride):
+def test_a5_batch(gpu_lib, oracle, nbits, stride, a5_kernel):
     """gmr1b200_a5_batch vs gmr1_a5 (src/l1/a5.c:57): downlink and uplink streams, A5/0 and A5/1 units mixed,
-    word-aligned and odd row strides, host and device pointers"""
+    word-aligned and odd row strides, host and device pointers; batch sizes that end inside a warp's 1024 units"""
     rng = np.random.default_rng(nbits * 7 + stride)
-    n = 300
+    n = 300 if nbits != 208 else 1024 + 37
     keys = rng.integers(0, 256, (n, 8), dtype=np.uint8)
     keys[0] = 0
     keys[1] = 255
@@ -90,3 +99,27 @@ def test_a5_batch(gpu_lib, oracle, nbits, stride):
     got = ddl.cpu().numpy()
     for i in range(0, n, 17):
         assert (got[i, :nbits] == oracle.a5(1, keys[i], int(fn[i]), nbits)).all(), i
+
+
+def test_a5_large_batch_both_kernels_agree(gpu_lib, oracle):
+    """40 000 units (the size from which the bitsliced kernel is the default): both kernels give the same streams,
+    spot-checked against gmr1_a5"""
+    import torch
+    rng = np.random.default_rng(77)
+    n, nbits = 40000, 208
+    keys = torch.from_numpy(rng.integers(0, 256, (n, 8), dtype=np.uint8)).cuda()
+    fn = torch.from_numpy(rng.integers(0, 1 << 19, n).astype(np.int32)).cuda()
+    out = []
+    for mode in (0, 1, -1):
+        prev = gpu_lib.c.gmr1b200_set_a5_bitslice(mode)
+        dl = torch.full((n, nbits), 7, dtype=torch.uint8, device="cuda")
+        ul = torch.full((n, nbits), 7, dtype=torch.uint8, device="cuda")
+        gpu_lib.call("gmr1b200_a5_batch", None, 1, keys, fn, nbits, nbits, dl, ul, n, None)
+        torch.cuda.synchronize()
+        gpu_lib.c.gmr1b200_set_a5_bitslice(prev)
+        out.append((dl.cpu().numpy(), ul.cpu().numpy()))
+    assert all((out[0][0] == o[0]).all() and (out[0][1] == o[1]).all() for o in out[1:])
+    k, f = keys.cpu().numpy(), fn.cpu().numpy()
+    for i in (0, 1, 1023, 1024, 33333, n - 1):
+        d, u = oracle.a5(1, k[i], int(f[i]), nbits, both=True)
+        assert (out[1][0][i] == d).all() and (out[1][1][i] == u).all(), i
