@@ -376,7 +376,7 @@ void gmr1b200_a5(int n, const uint8_t *key, uint32_t fn, int nbits, gmr1b200_ubi
  * every pointer host or device memory. */
 int gmr1b200_a5_batch(const int32_t *alg, int alg0, const uint8_t *key, const uint32_t *fn, int nbits, int stride,
                       gmr1b200_ubit_t *dl, gmr1b200_ubit_t *ul, int n, void *stream);
-/* Kernel selection switch (testing / A-B measurements): batches of 16 384 units and more run bitsliced - 32 keystreams
+/* Kernel selection switch (testing / A-B measurements): batches of 163 840 units and more run bitsliced - 32 keystreams
  * per thread, bit l of every register word belongs to unit l (csrc/a5_bitslice.cuh) - smaller ones one unit per
  * thread.  -1: by batch size (default), 0: one unit per thread always, 1: bitsliced always.  Same streams, bit for
  * bit.  Process-wide; returns the previous setting. */

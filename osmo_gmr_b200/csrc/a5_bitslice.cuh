@@ -9,6 +9,9 @@
 // (tests/test_a5_bitslice_cpu.py).
 #pragma once
 #include <stdint.h>
+#if !defined(__CUDACC__)
+struct uint2 { unsigned int x, y; };
+#endif
 #if defined(__CUDACC__)
 #define A5_HD __host__ __device__ __forceinline__
 #else
@@ -93,39 +96,52 @@ A5_HD uint32_t output(const State &s)
 }
 
 // the 64 key bits in the order the set-up consumes them: bytes swapped in pairs, the frame number folded in
-// (a5.c:232-247), byte j from its bit 7 down
+// (a5.c:232-247), byte j from its bit 7 down; bit q of the result = key bit of set-up step q
+A5_HD uint32_t rev_bits_in_bytes(uint32_t x)
+{
+	x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+	x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+	return ((x >> 4) & 0x0f0f0f0fu) | ((x & 0x0f0f0f0fu) << 4);
+}
+
 A5_HD uint64_t folded_key(const uint8_t *key, uint32_t fn)
 {
-	uint8_t k[8];
-#pragma unroll
-	for (int i = 0; i < 8; i++)
-		k[i] = key[i ^ 1];
-	k[6] ^= (uint8_t)((fn & 0x0000fu) << 4);
-	k[3] ^= (uint8_t)((fn & 0x00030u) << 2);
-	k[1] ^= (uint8_t)((fn & 0x007c0u) >> 3);
-	k[0] ^= (uint8_t)((fn & 0x0f800u) >> 11);
-	k[0] ^= (uint8_t)((fn & 0x70000u) >> 11);
-	uint64_t v = 0;                        // bit q of v = key bit of set-up step q
-#pragma unroll
-	for (int q = 0; q < 64; q++)
-		v |= (uint64_t)((k[q >> 3] >> (7 - (q & 7))) & 1u) << q;
-	return v;
+	uint32_t lo, hi;                        // bytes k[0..3], k[4..7] with k[i] = key[i ^ 1]
+	if ((((uintptr_t)key) & 7) == 0) {
+		const uint2 raw = *reinterpret_cast<const uint2 *>(key);
+		lo = ((raw.x >> 8) & 0x00ff00ffu) | ((raw.x & 0x00ff00ffu) << 8);
+		hi = ((raw.y >> 8) & 0x00ff00ffu) | ((raw.y & 0x00ff00ffu) << 8);
+	} else {
+		lo = (uint32_t)key[1] | ((uint32_t)key[0] << 8) | ((uint32_t)key[3] << 16) | ((uint32_t)key[2] << 24);
+		hi = (uint32_t)key[5] | ((uint32_t)key[4] << 8) | ((uint32_t)key[7] << 16) | ((uint32_t)key[6] << 24);
+	}
+	hi ^= (((fn & 0x0000fu) << 4) & 0xffu) << 16;                       // k[6]
+	lo ^= (((fn & 0x00030u) << 2) & 0xffu) << 24;                       // k[3]
+	lo ^= (((fn & 0x007c0u) >> 3) & 0xffu) << 8;                        // k[1]
+	lo ^= (((fn & 0x0f800u) >> 11) ^ ((fn & 0x70000u) >> 11)) & 0xffu;  // k[0]
+	return (uint64_t)rev_bits_in_bytes(lo) | ((uint64_t)rev_bits_in_bytes(hi) << 32);
 }
 
 // 32 x 32 bit-matrix transpose in place: afterwards bit c of a[l] is what bit l of a[c] was
+template <int J> A5_HD void transpose_stage(uint32_t (&a)[32])
+{
+	constexpr uint32_t M = J == 16 ? 0x0000ffffu : J == 8 ? 0x00ff00ffu : J == 4 ? 0x0f0f0f0fu : J == 2 ? 0x33333333u : 0x55555555u;
+#pragma unroll
+	for (int k = 0; k < 32; k++)
+		if ((k & J) == 0) {
+			const uint32_t t = ((a[k] >> J) ^ a[k + J]) & M;
+			a[k] ^= t << J;
+			a[k + J] ^= t;
+		}
+}
+
 A5_HD void transpose32(uint32_t (&a)[32])
 {
-#pragma unroll
-	for (int j = 16; j != 0; j >>= 1) {
-		const uint32_t m = j == 16 ? 0x0000ffffu : j == 8 ? 0x00ff00ffu : j == 4 ? 0x0f0f0f0fu : j == 2 ? 0x33333333u : 0x55555555u;
-#pragma unroll
-		for (int k = 0; k < 32; k++)
-			if ((k & j) == 0) {
-				const uint32_t t = ((a[k] >> j) ^ a[k + j]) & m;
-				a[k] ^= t << j;
-				a[k + j] ^= t;
-			}
-	}
+	transpose_stage<16>(a);
+	transpose_stage<8>(a);
+	transpose_stage<4>(a);
+	transpose_stage<2>(a);
+	transpose_stage<1>(a);
 }
 
 // four keystream bits (bits b .. b+3 of v) as four ubit bytes

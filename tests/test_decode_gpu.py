@@ -65,7 +65,7 @@ def test_empty_and_single(gpu_lib, oracle):
 @pytest.fixture(params=["thread", "bitsliced"])
 def a5_kernel(request, gpu_lib):
     """the cipher streams from the one-unit-per-thread kernel and from the bitsliced one (32 units per thread,
-    csrc/a5_bitslice.cuh; the default from 16 384 units up)"""
+    csrc/a5_bitslice.cuh; the default from 163 840 units up)"""
     prev = gpu_lib.c.gmr1b200_set_a5_bitslice(1 if request.param == "bitsliced" else 0)
     yield request.param
     gpu_lib.c.gmr1b200_set_a5_bitslice(prev)
@@ -102,8 +102,7 @@ def test_a5_batch(gpu_lib, oracle, nbits, stride, a5_kernel):
 
 
 def test_a5_large_batch_both_kernels_agree(gpu_lib, oracle):
-    """40 000 units (the size from which the bitsliced kernel is the default): both kernels give the same streams,
-    spot-checked against gmr1_a5"""
+    """40 000 units: both kernels (and the size-based default) give the same streams, spot-checked against gmr1_a5"""
     import torch
     rng = np.random.default_rng(77)
     n, nbits = 40000, 208
