@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <type_traits>
 
 #include "decode_unit.cuh"
 #include "tma.cuh"
@@ -157,7 +158,12 @@ __global__ void __launch_bounds__(tpc_threads(PAIR)) decode_tpc_kernel(const Dec
 		__syncthreads();
 		// eight elements per thread and pass: source addresses first (shared-memory lookups only), then the eight
 		// byte loads back to back (clamped, so that they are unconditional), then the stores
+		// A ragged last tile takes a second copy of the loop whose unit index is checked against the tile's count
+		// (base + tt may lie behind the batch: found by compute-sanitizer on a 6-burst TCH9 batch).  The check is kept
+		// out of the full-tile copy: one more select in front of the index lookups cost 0.85 -> 1.18 ms per 157 284
+		// bursts (A/B on one box, tools/gpu_r2_t9ab.sh)
 		constexpr int E = 8;
+		auto gather = [&](auto FULL) {
 		for (int idx0 = tid; idx0 < TPC_T * NROW; idx0 += NT * E) {
 			const int8_t *src[E];
 			const uint8_t *csrc[E];
@@ -168,9 +174,11 @@ __global__ void __launch_bounds__(tpc_threads(PAIR)) decode_tpc_kernel(const Dec
 				const int tt = idx / NROW, r = idx - tt * NROW;
 				const uint16_t w = s_src[r];
 				const int age = (w >> 10) & 3, sidx = w & G_IDX;
-				// units behind the tile's last one read unit 0 (a valid address; the value is dropped): base + tt may lie
-				// behind the batch (found by compute-sanitizer on a 6-burst TCH9 batch)
-				const int u = tt >= cnt ? -1 : age == 0 ? base + tt : s_prev[age - 1][tt];
+				int u;
+				if constexpr (decltype(FULL)::value)
+					u = age == 0 ? base + tt : s_prev[age - 1][tt];
+				else
+					u = tt >= cnt ? -1 : age == 0 ? base + tt : s_prev[age - 1][tt];
 				ok[e] = tt < cnt && u >= 0;
 				flip[e] = (w & G_FLIP) != 0;
 				const size_t uu = (size_t)max(u, 0);
@@ -195,6 +203,11 @@ __global__ void __launch_bounds__(tpc_threads(PAIR)) decode_tpc_kernel(const Dec
 					rows[idx0 + e * NT] = ok[e] ? (int8_t)x : (int8_t)0;
 			}
 		}
+		};
+		if (cnt == TPC_T)
+			gather(std::true_type{});
+		else
+			gather(std::false_type{});
 		__syncthreads();
 	} else {
 #pragma unroll 4

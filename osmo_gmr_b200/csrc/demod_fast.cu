@@ -134,12 +134,20 @@ constexpr int fg_dmax(int bt)
 	return m;
 }
 // the per-format kernels require: every sync sequence has the chunk layout of sequence 0, at most 32 training
-// symbols, regions disjoint, in ascending order and inside the window, every symbol pick inside the window
+// symbols (or one sequence of chunks of at most 32 symbols and at most 8 search offsets: RACH), regions disjoint, in
+// ascending order and inside the window, every symbol pick inside the window
 constexpr bool fg_ok(int bt, int w)
 {
 	const int nch = fg_nch(bt);
-	if (w < 1 || w > 96 || (fg_L(bt, w) & 1) || fg_cstart(bt, nch) > 32 || fg_cstart(bt, nch) < 1)
+	if (w < 1 || w > 96 || (fg_L(bt, w) & 1) || fg_cstart(bt, nch) < 1)
 		return false;
+	if (fg_cstart(bt, nch) > 32) {          // RACH: one row of lanes per chunk, quarter-chunks per lane in the search
+		if (bf_n_sync(bt) != 1 || w > 8)
+			return false;
+		for (int c = 0; c < nch; c++)
+			if (fg_clen(bt, c) > 32)
+				return false;
+	}
 	for (int s = 1; s < bf_n_sync(bt); s++) {
 		if (bf_n_chunk(bt, s) != nch)
 			return false;
@@ -164,6 +172,10 @@ struct Geo {
 	static constexpr int L = fg_L(BT, W_);
 	static constexpr int ROWS = (W_ + 31) / 32;
 	static constexpr int NSYNC = bf_n_sync(BT), NCH = fg_nch(BT), NTR = fg_cstart(BT, fg_nch(BT));
+	// more than 32 training symbols (RACH, 99 in five chunks): the training-symbol phase takes one row of lanes per
+	// chunk, and the search splits every chunk over the four lanes of a quad (8 quads <-> up to 8 search offsets)
+	static constexpr bool TROWS = fg_cstart(BT, fg_nch(BT)) > 32;
+	static constexpr int TR = TROWS ? fg_nch(BT) : 1;
 	static constexpr int REG_TOTAL = fg_roff(BT, W_, fg_nch(BT));
 	// the never-stored search offsets W .. 32*ROWS-1 read this far past the end of a region
 	static constexpr int REG_ALLOC = (REG_TOTAL + 32 * ROWS - W_ + 2 + 1) & ~1;
@@ -345,7 +357,7 @@ demod_fast_kernel(const DemodArgs a)
 	extern __shared__ __align__(16) uint8_t smem[];
 	__shared__ uint16_t soft_lut[LUT_CELLS << NB];
 	__shared__ uint2 dtab[G::DROWS * 32];          // data symbol -> (byte offset of its sample for TOA 0, position as float)
-	__shared__ uint4 lane_tab[32];
+	__shared__ uint4 lane_tab[G::TR * 32];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const FastSmem sm = fast_carve<G>(smem + (size_t)warp * G::WARP_BYTES);
 
@@ -375,7 +387,22 @@ demod_fast_kernel(const DemodArgs a)
 	//   .z  [7:0] end of the symbol's chunk (segmented sum)  [15:8] / [23:16] lane c >= 1: first symbol of chunk c / c-1
 	//       [24 + 2s +: 2] reference symbol of sequence s
 	//   .w  lane c >= 1: distance between the centres of chunks c and c-1 (float)
-	if (warp == 0) {
+	if constexpr (G::TROWS) {
+		// one row of lanes per chunk: entry [c][lane] = symbol `lane` of chunk c (.x, .y as above, .z its reference symbol)
+		for (int t = threadIdx.x; t < G::TR * 32; t += blockDim.x) {
+			const int cc = t >> 5, l = t & 31;
+			uint4 ent = make_uint4(0u, 0u, 0u, 0u);
+			static_for<NCH>([&](auto C) {
+				constexpr int c = decltype(C)::value, cl = fg_clen(BT, c);
+				unsigned long long w64 = 0;
+				static_for<cl>([&](auto K) { w64 |= (unsigned long long)bf_s_sym(BT, 0, c, decltype(K)::value) << (2 * decltype(K)::value); });
+				if (cc == c && l < cl)
+					ent = make_uint4((unsigned)((fg_roff(BT, W, c) + 2 + l * FG_SPS) * 8), __float_as_uint((float)(fg_cpos(BT, c) + l)),
+					                 (unsigned)((w64 >> (2 * l)) & 3), 0u);
+			});
+			lane_tab[t] = ent;
+		}
+	} else if (warp == 0) {
 		int t_roff = 0, t_end = 0, c_src = 0, c_srcp = 0, syms = 0;
 		float t_posf = 0.0f, c_dist = 1.0f;
 		static_for<NCH>([&](auto C) {
@@ -495,6 +522,33 @@ demod_fast_kernel(const DemodArgs a)
 					const float2 Rs = sm.tsum[s * NCH + c];
 					// corr = sum t_n x - avg * sum t_n: the accumulators start at -avg * sum t_n
 					const float2 init = make_float2(-(nm.ar * Rs.x - nm.ai * Rs.y), -(nm.ar * Rs.y + nm.ai * Rs.x));
+					if constexpr (G::TROWS) {
+						// quad m <-> search offset m, lane q of the quad takes taps q, q + 4, ...: a quarter of the
+						// multiply-adds of the lane-per-offset form, whose lanes >= W idle (99 taps at 7 offsets)
+						const int q = lane & 3;
+						float2 P = q == 0 ? init : make_float2(0.0f, 0.0f), Q = make_float2(0.0f, 0.0f);
+						const float2 *g = sm.reg + fg_roff(BT, W, c) + 2 + (lane >> 2) + FG_SPS * q;
+						const float2 *tq = tapb + fg_toff(BT, c) + q;
+						static_for<(cl + 3) / 4>([&](auto K) {
+							constexpr int k = decltype(K)::value;
+							float2 t = tq[4 * k];
+							if constexpr (4 * k + 3 >= cl) {
+								if (q >= cl - 4 * k)
+									t = make_float2(0.0f, 0.0f);
+							}
+							const float2 v = g[4 * FG_SPS * k];
+							fma2s(P, t.x, v);
+							fma2s(Q, t.y, v);
+						});
+						float xr = P.x - Q.y, xi = P.y + Q.x;
+						xr += __shfl_xor_sync(0xffffffffu, xr, 1);
+						xi += __shfl_xor_sync(0xffffffffu, xi, 1);
+						xr += __shfl_xor_sync(0xffffffffu, xr, 2);
+						xi += __shfl_xor_sync(0xffffffffu, xi, 2);
+						float mag;
+						asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(mag) : "f"(fmaf(xr, xr, xi * xi)));
+						acc[0] += mag;
+					} else {
 					float2 P[ROWS], Q[ROWS];
 #pragma unroll
 					for (int r = 0; r < ROWS; r++) {
@@ -556,11 +610,17 @@ demod_fast_kernel(const DemodArgs a)
 						asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(mag) : "f"(fmaf(xr, xr, xi * xi)));
 						acc[r] += mag;      // unscaled: 1/stddev changes no decision, it only scales the reported power
 					}
+					}
 				});
 				__syncwarp();
+				if constexpr (G::TROWS) {
+					const float av = __shfl_sync(0xffffffffu, acc[0], (4 * lane) & 31);     // offset `lane` sits in quad `lane`
+					sm.accv[lane] = lane < W ? av : 0.0f;
+				} else {
 #pragma unroll
 				for (int r = 0; r < ROWS; r++)
 					sm.accv[lane + 32 * r] = (32 * r + 31 < W || lane + 32 * r < W) ? acc[r] : 0.0f;
+				}
 				__syncwarp();
 				float peak;
 				TapLane tpl;
@@ -605,6 +665,62 @@ demod_fast_kernel(const DemodArgs a)
 		const float df = roundf(toa);
 		const int d = (int)df;
 
+		float ferr, phi0;
+		if constexpr (G::TROWS) {
+			// ---- 4. (more than 32 training symbols) one row of lanes per chunk: symbol `lane` of chunk c, chunk sums by
+			// one folded shuffle tree each, the angle between chunks c and c-1 in lane c, phase reference from the
+			// per-lane sums of the rotated symbols
+			const unsigned lt_s = (unsigned)__cvta_generic_to_shared(&lane_tab[lane]);
+			float2 zc[NCH];
+			float posc[NCH];
+			float2 S[NCH];
+			static_for<NCH>([&](auto C) {
+				constexpr int c = decltype(C)::value, cl = fg_clen(BT, c);
+				uint4 lt;
+				asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lt.x), "=r"(lt.y), "=r"(lt.z), "=r"(lt.w) : "r"(lt_s + c * 512));
+				posc[c] = __uint_as_float(lt.y);
+				zc[c] = make_float2(0.0f, 0.0f);
+				if (lane < cl) {
+					float2 v;
+					asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(reg_s + lt.x + (unsigned)(d * 8)));
+					const float2 e = sincos_red(fs * fmaf(posc[c], (float)FG_SPS, df));
+					const float yr = v.x - nm.ar, yi = v.y - nm.ai;
+					zc[c] = mul_conj_sym((int)lt.z, make_float2(yr * e.x - yi * e.y, yr * e.y + yi * e.x));
+				}
+				if constexpr (cl == 1)
+					S[c] = make_float2(__shfl_sync(0xffffffffu, zc[c].x, 0), __shfl_sync(0xffffffffu, zc[c].y, 0));
+				else
+					S[c] = warp_sum2(zc[c].x, zc[c].y, lane);
+			});
+			float2 sa = S[0], sb = S[0];
+			float dist = 1.0f;
+			static_for<NCH - 1>([&](auto C) {
+				constexpr int c = decltype(C)::value + 1;
+				constexpr float pc = (float)fg_cpos(BT, c) + (float)fg_clen(BT, c) / 2.0f;
+				constexpr float pp = (float)fg_cpos(BT, c - 1) + (float)fg_clen(BT, c - 1) / 2.0f;
+				if (lane == c) {
+					sa = S[c];
+					sb = S[c - 1];
+					dist = pc - pp;
+				}
+			});
+			const float part = fast_atan2f_inl(sa.y * sb.x - sa.x * sb.y, sa.x * sb.x + sa.y * sb.y) / dist;
+			float f = 0.0f;
+#pragma unroll
+			for (int k = 1; k < NCH; k++)
+				f += __shfl_sync(0xffffffffu, part, k);
+			ferr = f / (float)(NCH - 1);
+			if (lane == 0 && a.freq_err) a.freq_err[b] = ferr;
+			float2 acc2 = make_float2(0.0f, 0.0f);
+			static_for<NCH>([&](auto C) {
+				constexpr int c = decltype(C)::value;
+				const float2 e = sincos_red((-ferr) * posc[c]);
+				acc2.x += zc[c].x * e.x - zc[c].y * e.y;       // lanes past the chunk hold z = 0
+				acc2.y += zc[c].x * e.y + zc[c].y * e.x;
+			});
+			const float2 sum = warp_sum2(acc2.x, acc2.y, lane);
+			phi0 = fast_atan2f_inl(sum.y, sum.x);
+		} else {
 		// ---- 4. training symbols, one per lane, derotated as the reference derotates every sample:
 		//      z = (x - avg) * e^{j*fl32(fs*idx)}, times conj(reference symbol)
 		uint4 lt;
@@ -620,7 +736,7 @@ demod_fast_kernel(const DemodArgs a)
 			const float yr = v.x - nm.ar, yi = v.y - nm.ai;      // (the scale 1/sd does not change an angle)
 			z = mul_conj_sym(sym, make_float2(yr * e.x - yi * e.y, yr * e.y + yi * e.x));
 		}
-		float ferr = 0.0f;
+		ferr = 0.0f;
 		if constexpr (NCH > 1) {
 			// all chunk sums at once: segmented shuffle reduction (a lane adds the value `o` lanes up while that lane
 			// is still inside its chunk); the sum of a chunk ends in the chunk's first lane
@@ -647,7 +763,6 @@ demod_fast_kernel(const DemodArgs a)
 		if (lane == 0 && a.freq_err) a.freq_err[b] = ferr;
 
 		// ---- phase reference: all training symbols after the -ferr rotation (:415-433, :574)
-		float phi0;
 		{
 			float2 zr = z;
 			if constexpr (NCH > 1) {
@@ -656,6 +771,8 @@ demod_fast_kernel(const DemodArgs a)
 			}
 			const float2 sum = warp_sum2(zr.x, zr.y, lane);
 			phi0 = fast_atan2f_inl(sum.y, sum.x);
+		}
+
 		}
 
 		// ---- 5. data symbols in the angle domain: arg(x - avg) + fl32(fs*idx) + fl32(-ferr*i) - arg(phasor), the
@@ -740,7 +857,7 @@ FastEntry make_entry()
 {
 	using G = Geo<BT, W>;
 	return {BT, W, {(const void *)demod_fast_kernel<BT, W, false>, (const void *)demod_fast_kernel<BT, W, true>},
-	        (size_t)G::WARP_BYTES, (size_t)(2 * (LUT_CELLS << G::NB) + 8 * G::DROWS * 32)};
+	        (size_t)G::WARP_BYTES, (size_t)(2 * (LUT_CELLS << G::NB) + 8 * G::DROWS * 32 + 512 * G::TR)};
 }
 
 // the standard search widths: what gmr1_rx cuts (BCCH 20*sps, DC6 10*sps, NT3 / NT9 sps + sps/2, gmr1_rx.c:290,549,
@@ -750,7 +867,7 @@ const FastEntry *fast_entries(int *n)
 	static const FastEntry tab[] = {
 		make_entry<BT_BCCH, 81>(), make_entry<BT_DC6, 41>(), make_entry<BT_NT3_SPEECH, 7>(), make_entry<BT_NT3_FACCH, 7>(),
 		make_entry<BT_NT9, 7>(),   make_entry<BT_NT6, 7>(),  make_entry<BT_SDCCH, 41>(),     make_entry<BT_DC2, 25>(),
-		make_entry<BT_DC12, 41>(),
+		make_entry<BT_DC12, 41>(), make_entry<BT_RACH, 7>(),
 	};
 	*n = (int)(sizeof(tab) / sizeof(tab[0]));
 	return tab;
