@@ -20,6 +20,9 @@
 #include "decode_unit.cuh"
 #include "tma.cuh"
 #include "launch.h"
+#ifndef TPC_LUT
+#define TPC_LUT 1       // one codeword per thread: branch metrics through the shared-memory table (0: arithmetic)
+#endif
 
 namespace gmr1 {
 
@@ -126,6 +129,9 @@ __global__ void __launch_bounds__(tpc_threads(PAIR)) decode_tpc_kernel(const Dec
 	if constexpr (PAIR) {
 		for (int i = tid; i < 512; i += NT)
 			(&lut->plain[0])[i] = p16_lut_word(i);                    // visible after the barrier that ends phase 1
+	} else if constexpr (TPC_LUT) {
+		for (int i = tid; i < 512; i += NT)
+			rel_lut_fill((RelLut *)lut, i);
 	}
 
 	// ---- phase 1: stage the tile
@@ -232,9 +238,9 @@ __global__ void __launch_bounds__(tpc_threads(PAIR)) decode_tpc_kernel(const Dec
 	} else if (tid < cnt) {
 		const int T = gdec ? (int)gridDim.x * TPC_T : TPC_T, t = gdec ? base + tid : tid;
 		if constexpr (CH == CH_TCH3)
-			decode_unit_tch3(tb, a, base + tid, rows + tid * NROW, (uint32_t *)dec, T, t);
+			decode_unit_tch3<TPC_LUT != 0>(tb, a, base + tid, rows + tid * NROW, (uint32_t *)dec, T, t, (const RelLut *)lut);
 		else
-			decode_unit_k5<CH>(tb, a, base + tid, rows + tid * NROW, (uint16_t *)dec, T, t);
+			decode_unit_k5<CH, TPC_LUT != 0>(tb, a, base + tid, rows + tid * NROW, (uint16_t *)dec, T, t, (const RelLut *)lut);
 	}
 }
 
@@ -270,7 +276,8 @@ static cudaError_t launch_tpc(const DecodeArgs &a, cudaStream_t st)
 			attr_done[dev] = true;
 	}
 	const int grid = (a.n + TPC_T - 1) / TPC_T;
-	const int smem_used = (a.dec_scratch ? tpc_rows_bytes(CH) + 16 : smem - (int)sizeof(P16Lut)) + (PAIR ? (int)sizeof(P16Lut) : 0);
+	const int smem_used = (a.dec_scratch ? tpc_rows_bytes(CH) + 16 : smem - (int)sizeof(P16Lut)) +
+	                      (PAIR ? (int)sizeof(P16Lut) : TPC_LUT ? (int)sizeof(RelLut) : 0);
 	decode_tpc_kernel<CH, PAIR><<<grid, tpc_threads(PAIR), smem_used, st>>>(a);
 	return cudaGetLastError();
 }

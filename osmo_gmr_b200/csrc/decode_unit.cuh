@@ -152,9 +152,10 @@ GMR1_HD void k5_side_outputs(const DecodeArgs &a, int unit)
 template <int CH>
 GMR1_HD void k5_outputs(const DecodeArgs &a, int unit, uint8_t *out);
 
-template <int CH>
+// lut != nullptr: branch metrics through the byte tables (RelLut) instead of the arithmetic - same numbers
+template <int CH, bool LUT = false>
 GMR1_HD void decode_unit_k5(const TabRef &tb, const DecodeArgs &a, int unit,
-                            int8_t *row, uint16_t *dec, int T, int t)
+                            int8_t *row, uint16_t *dec, int T, int t, const RelLut *lut = nullptr)
 {
 	using C = typename ChanCode<CH>::type;
 	k5_side_outputs<CH>(a, unit);
@@ -167,8 +168,8 @@ GMR1_HD void decode_unit_k5(const TabRef &tb, const DecodeArgs &a, int unit,
 	// path metrics relative to the all-zero branch of every step (acs_step REL): `off` is what they lack
 	uint32_t off = 0;
 	constexpr bool ER = chan_has_erasures(CH);
-	forward<C, false, true, CH == CH_RACH, true, ER>(ae, row, tb.g, tb.g2, 0, tb.len, dec, T, t, off);
-	forward<C, true,  true, CH == CH_RACH, true, ER>(ae, row, tb.g, tb.g2, tb.len, C::K - 1, dec, T, t, off);
+	forward<C, false, true, CH == CH_RACH, true, ER, LUT>(ae, row, tb.g, tb.g2, 0, tb.len, dec, T, t, off, lut);
+	forward<C, true,  true, CH == CH_RACH, true, ER, LUT>(ae, row, tb.g, tb.g2, tb.len, C::K - 1, dec, T, t, off, lut);
 
 	if (a.conv)
 		a.conv[unit] = (int32_t)(ae[0] + off);
@@ -356,8 +357,9 @@ GMR1_HD void decode_pair_k5(const TabRef &tb, const DecodeArgs &a, const P16Lut 
 }
 
 // ---- per-unit decode, TCH3 (two tail-biting K7 frames + class-2 bits) --------------------------
+template <bool LUT = false>
 GMR1_HD void decode_unit_tch3(const TabRef &tb, const DecodeArgs &a, int unit,
-                              const int8_t *row, uint32_t *dec, int T, int t)
+                              const int8_t *row, uint32_t *dec, int T, int t, const RelLut *lut = nullptr)
 {
 	using C = CodeK7_12;
 	if (a.bits_s)
@@ -376,7 +378,7 @@ GMR1_HD void decode_unit_tch3(const TabRef &tb, const DecodeArgs &a, int unit,
 		// the reported metric.  (After the normalisation the smallest metric is 0 < MAX_AE, so an end state always
 		// exists: the reference's "no state" return cannot occur here.)
 		uint32_t off = 0;
-		forward<C, false, false, false, true>(ae, row, g, nullptr, 0, 48, dec, T, t, off);
+		forward<C, false, false, false, true, true, LUT>(ae, row, g, nullptr, 0, 48, dec, T, t, off, lut);
 		int32_t mn = (int32_t)ae[0];
 #pragma unroll
 		for (int s = 1; s < C::NS; s++)
@@ -385,7 +387,7 @@ GMR1_HD void decode_unit_tch3(const TabRef &tb, const DecodeArgs &a, int unit,
 		for (int s = 0; s < C::NS; s++)
 			ae[s] -= (uint32_t)mn;
 		off = 0;
-		forward<C, false, true, false, true>(ae, row, g, nullptr, 0, 48, dec, T, t, off);
+		forward<C, false, true, false, true, true, LUT>(ae, row, g, nullptr, 0, 48, dec, T, t, off, lut);
 		// end state: first state with the minimal metric
 		int32_t best = (int32_t)ae[0];
 		unsigned end = 0;

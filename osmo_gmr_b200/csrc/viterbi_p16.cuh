@@ -63,9 +63,7 @@ GMR1_HD constexpr bool p16_needs_renorm(int n, int k, int n_steps) { return 0x40
 // (both 0 for an erased soft bit, soft_metrics).  `flipped` is the same table for the negated soft bit (the gather program's
 // descrambling flips), so a flip costs nothing: the table base is picked by a uniform select.  The kernel keeps the
 // two tables in shared memory (2 KB per CTA); lanes that hold the same value read the same word (broadcast).
-struct P16Lut {
-	uint32_t plain[256], flipped[256];
-};
+using P16Lut = MetricLut;      // viterbi_tpc.cuh
 GMR1_HD uint32_t p16_lut_entry(int is)
 {
 	uint32_t m0, m1;

@@ -105,6 +105,54 @@ GMR1_HD void soft_metrics_rel(int is, uint32_t &m0, uint32_t &d)
 	m0 = is ? (uint32_t)r0 : 0u;
 }
 
+// ---- branch metrics through a table ----------------------------------------------------------------------------
+// One entry per soft-bit byte value, `flipped` the same for the negated soft bit (the gather program's descrambling
+// flips cost nothing: the table base is picked by a uniform select).  Lanes that hold the same value read the same
+// word (broadcast).  The kernel keeps the tables in shared memory.
+//   two codewords per thread (viterbi_p16.cuh, p16_lut_word): MetricLut, 32-bit words, low half m0, high half m1;
+//   one codeword per thread: RelLut, BYTE tables of m0 and d = m1 - m0 (soft_metrics_rel; both fit a byte:
+//       m0 <= 127, -127 <= d <= 126), read with sign- / zero-extending byte loads at [table + value]: no index
+//       scaling, no field extraction.  The arithmetic form costs ~13 integer-ALU instructions per soft bit (compare,
+//       selects, shifts) on the pipe that bounds the kernel; a first table of packed 32-bit words moved the
+//       extraction onto the same pipe (LEA.HI.SX32) and won nothing there.
+struct MetricLut {
+	uint32_t plain[256], flipped[256];
+};
+struct RelLut {
+	int8_t  d[2][256];       // [flipped][value]
+	uint8_t m0[2][256];
+};
+static_assert(sizeof(RelLut) <= sizeof(MetricLut), "the kernels reserve sizeof(MetricLut) for either table");
+// entry i (0..511: 256 + value = flipped) of the two byte tables
+GMR1_HD void rel_lut_fill(RelLut *lut, int i)
+{
+	const int v = (int)(int8_t)(i & 0xff);
+	uint32_t m0, d;
+	soft_metrics_rel(i < 256 ? v : sbit_neg(v), m0, d);
+	lut->d[i >> 8][i & 0xff] = (int8_t)(int32_t)d;
+	lut->m0[i >> 8][i & 0xff] = (uint8_t)m0;
+}
+GMR1_HD int lut_ld_s8(const int8_t *base, unsigned idx)
+{
+#ifdef __CUDA_ARCH__
+	int v;
+	asm("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(base) + idx));
+	return v;
+#else
+	return base[idx];
+#endif
+}
+GMR1_HD unsigned row_ld_u8(const int8_t *row, unsigned idx)
+{
+#ifdef __CUDA_ARCH__
+	unsigned v;
+	asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(row) + idx));
+	return v;
+#else
+	return (uint8_t)row[idx];
+#endif
+}
+
 // (hi << 1) | (lo >> 31): shifts the sign of lo into hi
 GMR1_HD uint32_t funnel_l1(uint32_t lo, uint32_t hi)
 {
@@ -124,19 +172,31 @@ GMR1_HD uint32_t funnel_l1(uint32_t lo, uint32_t hi)
 // off, handed back to the caller for conv_rv and the MAX_AE sentinel of the flush steps).  bm[0] becomes the
 // constant 0: the 2^(K-1-... ) transitions with an all-zero output need no add, and the branch sums need N - 1 adds
 // less.  Relative metrics can be negative: comparisons are signed (|values| < 2^25).
+template <class C, bool FLUSH_STEP, bool REL>
+GMR1_HD void acs_core(const uint32_t (&ae)[C::NS], uint32_t (&nae)[C::NS], const uint32_t (&m0)[C::N], const uint32_t (&m1)[C::N],
+                      uint32_t (&dec)[(C::NS + 31) / 32], uint32_t &off);
+
 template <class C, bool FLUSH_STEP, bool REL = false>
 GMR1_HD void acs_step(const uint32_t (&ae)[C::NS], uint32_t (&nae)[C::NS], const int (&v)[C::N],
                       uint32_t (&dec)[(C::NS + 31) / 32], uint32_t &off)
 {
-	constexpr int N = C::N, NS = C::NS, H = NS / 2;
-	uint32_t m0[N], m1[N];                       // REL: m1 holds m1 - m0
+	uint32_t m0[C::N], m1[C::N];                 // REL: m1 holds m1 - m0
 #pragma unroll
-	for (int j = 0; j < N; j++) {
+	for (int j = 0; j < C::N; j++) {
 		if (REL)
 			soft_metrics_rel(v[j], m0[j], m1[j]);
 		else
 			soft_metrics(v[j], m0[j], m1[j]);
 	}
+	acs_core<C, FLUSH_STEP, REL>(ae, nae, m0, m1, dec, off);
+}
+
+// the step proper, from the per-bit metrics (REL: m1 holds m1 - m0)
+template <class C, bool FLUSH_STEP, bool REL>
+GMR1_HD void acs_core(const uint32_t (&ae)[C::NS], uint32_t (&nae)[C::NS], const uint32_t (&m0)[C::N], const uint32_t (&m1)[C::N],
+                      uint32_t (&dec)[(C::NS + 31) / 32], uint32_t &off)
+{
+	constexpr int N = C::N, NS = C::NS, H = NS / 2;
 	// all 2^N branch sums, built by doubling (entries that no transition uses are dead code)
 	uint32_t bm[1 << N];
 	bm[0] = 0;
@@ -226,6 +286,33 @@ GMR1_HD void fetch_inputs(int (&v)[C::N], const int8_t *row, const uint16_t *g, 
 	}
 }
 
+// relative metrics (m0, d = m1 - m0) of the N soft bits of step i through the byte tables (RelLut)
+template <class C, bool HAS_G2, bool ERASE = true>
+GMR1_HD void fetch_metrics_rel(uint32_t (&m0)[C::N], uint32_t (&d)[C::N], const RelLut *lut, const int8_t *row,
+                               const uint16_t *g, const uint16_t *g2, int i)
+{
+#pragma unroll
+	for (int j = 0; j < C::N; j++) {
+		const uint16_t w = g[i * C::N + j];
+		if (HAS_G2) {                             // RACH: two sources averaged (rach.c:159-160), then the table
+			int s = gather_sbit<ERASE>(row, w);
+			const uint16_t w2 = g2[i * C::N + j];
+			if (w2 != G_ERASED)
+				s = (s + gather_sbit(row, w2)) >> 1;
+			m0[j] = row_ld_u8((const int8_t *)lut->m0[0], (unsigned)s & 0xffu);
+			d[j] = (uint32_t)lut_ld_s8(lut->d[0], (unsigned)s & 0xffu);
+		} else if (ERASE && (w & 0x8000u)) {      // punctured position: no metric
+			m0[j] = 0;
+			d[j] = 0;
+		} else {
+			const int f = (w & G_FLIP) ? 1 : 0;
+			const unsigned val = row_ld_u8(row, w & G_IDX);
+			m0[j] = row_ld_u8((const int8_t *)lut->m0[f], val);
+			d[j] = (uint32_t)lut_ld_s8(lut->d[f], val);
+		}
+	}
+}
+
 template <class C, bool STORE>
 GMR1_HD void store_dec(const uint32_t (&dec)[(C::NS + 31) / 32], typename DecWord<C::NS>::type *dec_base, int T, int t, int i)
 {
@@ -237,14 +324,40 @@ GMR1_HD void store_dec(const uint32_t (&dec)[(C::NS + 31) / 32], typename DecWor
 	}
 }
 
-template <class C, bool FLUSH_STEP, bool STORE, bool HAS_G2, bool REL = false, bool ERASE = true>
+// LUT (REL only): the per-bit metrics come from the table `lut` instead of the arithmetic of soft_metrics_rel
+template <class C, bool FLUSH_STEP, bool STORE, bool HAS_G2, bool REL = false, bool ERASE = true, bool LUT = false>
 GMR1_HD void forward(uint32_t (&ae)[C::NS], const int8_t *row, const uint16_t *g, const uint16_t *g2,
-                     int step0, int nsteps, typename DecWord<C::NS>::type *dec_base, int T, int t, uint32_t &off)
+                     int step0, int nsteps, typename DecWord<C::NS>::type *dec_base, int T, int t, uint32_t &off,
+                     const RelLut *lut = nullptr)
 {
 	constexpr int DW = (C::NS + 31) / 32;
 	uint32_t tmp[C::NS];
 	int i = step0;
 	const int end = step0 + nsteps;
+	if constexpr (LUT) {
+		static_assert(REL, "the metric table holds relative metrics");
+		for (; i + 1 < end; i += 2) {
+			uint32_t m0[C::N], d[C::N];
+			uint32_t dec[DW];
+			fetch_metrics_rel<C, HAS_G2, ERASE>(m0, d, lut, row, g, g2, i);
+			acs_core<C, FLUSH_STEP, true>(ae, tmp, m0, d, dec, off);
+			store_dec<C, STORE>(dec, dec_base, T, t, i);
+			fetch_metrics_rel<C, HAS_G2, ERASE>(m0, d, lut, row, g, g2, i + 1);
+			acs_core<C, FLUSH_STEP, true>(tmp, ae, m0, d, dec, off);
+			store_dec<C, STORE>(dec, dec_base, T, t, i + 1);
+		}
+		if (i < end) {
+			uint32_t m0[C::N], d[C::N];
+			uint32_t dec[DW];
+			fetch_metrics_rel<C, HAS_G2, ERASE>(m0, d, lut, row, g, g2, i);
+			acs_core<C, FLUSH_STEP, true>(ae, tmp, m0, d, dec, off);
+			store_dec<C, STORE>(dec, dec_base, T, t, i);
+#pragma unroll
+			for (int s = 0; s < C::NS; s++)
+				ae[s] = tmp[s];
+		}
+		return;
+	}
 	for (; i + 1 < end; i += 2) {           // two steps per iteration: ae -> tmp -> ae
 		int v[C::N];
 		uint32_t dec[DW];

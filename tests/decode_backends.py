@@ -47,11 +47,13 @@ def _outs(ch, n):
 class EmuBackend:
     name = "emu"
 
-    def __init__(self, emu, p16=False):
-        """p16: two codewords per "thread" with packed 16-bit metrics (viterbi_p16.cuh)"""
+    def __init__(self, emu, p16=False, lut=False):
+        """p16: two codewords per "thread" with packed 16-bit metrics (viterbi_p16.cuh); lut: one codeword per "thread"
+        with the branch metrics through the table (viterbi_tpc.cuh, RelLut) - what the kernels run"""
         self.emu = emu
         self.p16 = p16
-        self.name = "emu-p16" if p16 else "emu"
+        self.lut = lut
+        self.name = "emu-p16" if p16 else "emu-lut" if lut else "emu"
         assert ctypes.sizeof(Args) == emu.gmr1_emu_sizeof_args()
 
     def decode(self, ch, e, ciph=None, prev1=None, prev2=None, sb_mask=None, m=0):
@@ -61,7 +63,7 @@ class EmuBackend:
                  conv1=_p(o.get("conv1")), crc=_p(o.get("crc")), crc2=_p(o.get("crc2")), bits_s=_p(o.get("bits_s")),
                  sacch=_p(o.get("sacch")), status=_p(o.get("status")), prev1=_p(prev1), prev2=_p(prev2),
                  sb_mask=_p(sb_mask), sb_mask0=0, tch3_m=m)
-        fn = self.emu.gmr1_emu_decode_p16 if self.p16 else self.emu.gmr1_emu_decode
+        fn = self.emu.gmr1_emu_decode_p16 if self.p16 else self.emu.gmr1_emu_decode_lut if self.lut else self.emu.gmr1_emu_decode
         assert fn(ch, ctypes.byref(a)) == 0
         return o
 

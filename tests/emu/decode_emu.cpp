@@ -10,9 +10,13 @@
 
 using namespace gmr1;
 
-template <int CH>
+// lut: one codeword per "thread" with the branch metrics through the byte tables (RelLut), as the kernels run it
+template <int CH, bool LUT = false>
 static void run(const DecodeArgs &a)
 {
+	static RelLut lut;
+	for (int i = 0; i < 512; i++)
+		rel_lut_fill(&lut, i);
 	const ChanTab &t = chan_tab(CH);
 	TabRef tb;
 	tb.g = t.g; tb.g2 = (CH == CH_RACH) ? t.g2 : nullptr; tb.cmap = t.cmap; tb.t9_src = t.t9_src;
@@ -23,9 +27,9 @@ static void run(const DecodeArgs &a)
 		for (int r = 0; r < t.n_row; r++)
 			row[r] = stage_elem<CH>(tb, a, u, r);
 		if constexpr (CH == CH_TCH3)
-			decode_unit_tch3(tb, a, u, row.data(), dec.data(), 1, 0);
+			decode_unit_tch3<LUT>(tb, a, u, row.data(), dec.data(), 1, 0, &lut);
 		else
-			decode_unit_k5<CH>(tb, a, u, row.data(), (uint16_t *)dec.data(), 1, 0);
+			decode_unit_k5<CH, LUT>(tb, a, u, row.data(), (uint16_t *)dec.data(), 1, 0, &lut);
 	}
 }
 
@@ -67,6 +71,23 @@ extern "C" int gmr1_emu_decode_p16(int ch, const DecodeArgs *a)
 	case CH_TCH9_9K6: run_p16<CH_TCH9_9K6>(*a); break;
 	case CH_RACH:     run_p16<CH_RACH>(*a); break;
 	case CH_TCH3:     run_p16<CH_TCH3>(*a); break;
+	default: return -1;
+	}
+	return 0;
+}
+
+extern "C" int gmr1_emu_decode_lut(int ch, const DecodeArgs *a)
+{
+	switch (ch) {
+	case CH_BCCH:     run<CH_BCCH, true>(*a); break;
+	case CH_CCCH:     run<CH_CCCH, true>(*a); break;
+	case CH_FACCH3:   run<CH_FACCH3, true>(*a); break;
+	case CH_FACCH9:   run<CH_FACCH9, true>(*a); break;
+	case CH_TCH9_2K4: run<CH_TCH9_2K4, true>(*a); break;
+	case CH_TCH9_4K8: run<CH_TCH9_4K8, true>(*a); break;
+	case CH_TCH9_9K6: run<CH_TCH9_9K6, true>(*a); break;
+	case CH_RACH:     run<CH_RACH, true>(*a); break;
+	case CH_TCH3:     run<CH_TCH3, true>(*a); break;
 	default: return -1;
 	}
 	return 0;

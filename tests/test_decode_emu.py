@@ -5,9 +5,9 @@ import decode_parity as dp
 from decode_backends import CH, EmuBackend
 
 
-@pytest.fixture(scope="module", params=["one-per-thread", "two-per-thread-16-bit"])
+@pytest.fixture(scope="module", params=["one-per-thread", "one-per-thread-metric-table", "two-per-thread-16-bit"])
 def be(emu, request):
-    return EmuBackend(emu, p16=request.param != "one-per-thread")
+    return EmuBackend(emu, p16=request.param == "two-per-thread-16-bit", lut=request.param == "one-per-thread-metric-table")
 
 
 def test_bcch(be, oracle):
@@ -62,5 +62,7 @@ def test_p16_equals_one_per_thread_on_hostile_input(emu, ch, n_in, kind):
         e = rng.integers(-2, 3, (n, n_in)).astype(np.int8)
     a = EmuBackend(emu).decode(CH[ch], e)
     b = EmuBackend(emu, p16=True).decode(CH[ch], e)
+    c = EmuBackend(emu, lut=True).decode(CH[ch], e)
     for k in a:
         assert (a[k] == b[k]).all(), (ch, kind, k)
+        assert (a[k] == c[k]).all(), (ch, kind, k, "metric table")
