@@ -135,8 +135,11 @@ __global__ void __launch_bounds__(tpc_threads(PAIR)) decode_tpc_kernel(const Dec
 	}
 
 	// ---- phase 1: stage the tile
-	const bool plain = !chan_is_t9(CH) && (chan_n_ciph(CH) == 0 || a.ciph == nullptr);
-	const bool bulk = plain && cnt == TPC_T && ((((uintptr_t)a.ebits) & 15) == 0);
+	// ciphered FACCH3 / TCH3 / FACCH9: the rows come in like plain ones, the cipher signs are applied in shared memory
+	// by a second pass (below)
+	constexpr bool CAN_CIPH = !chan_is_t9(CH) && chan_n_ciph(CH) > 0;
+	const bool ciphered = CAN_CIPH && a.ciph != nullptr;
+	const bool bulk = !chan_is_t9(CH) && cnt == TPC_T && ((((uintptr_t)a.ebits) & 15) == 0);
 	if (bulk) {
 		// the tile is one contiguous, 16-byte aligned span of TPC_T*NIN bytes: a single TMA
 		// bulk copy brings it in while no LSU instruction is spent on it
@@ -215,13 +218,52 @@ __global__ void __launch_bounds__(tpc_threads(PAIR)) decode_tpc_kernel(const Dec
 		else
 			gather(std::false_type{});
 		__syncthreads();
-	} else {
+	} else if (chan_is_t9(CH)) {
 #pragma unroll 4
 		for (int idx = tid; idx < TPC_T * NROW; idx += NT) {
 			const int tt = idx / NROW, r = idx - tt * NROW;
 			rows[idx] = (tt < cnt) ? stage_elem<CH>(tb, a, base + tt, r) : (int8_t)0;
 		}
 		__syncthreads();
+	} else {
+		// ragged last tile or unaligned batch: plain coalesced copy (NROW == NIN: the tile is one span of bytes)
+#pragma unroll 4
+		for (int idx = tid; idx < TPC_T * NROW; idx += NT)
+			rows[idx] = idx < cnt * NROW ? a.ebits[(size_t)base * NIN + idx] : (int8_t)0;
+		__syncthreads();
+	}
+	if constexpr (CAN_CIPH) {
+		// Cipher signs (tch3.c:137-139, facch3.c:145-153, facch9.c:121-128: a set cipher bit negates the soft bit),
+		// applied to the staged rows: cipher position of every soft bit from a shared-memory copy of the map, eight
+		// cipher bytes per thread requested together (unconditional, clamped index), then the negations.  The first
+		// form did this inside the staging loop, one element at a time with the map read from global memory: two
+		// dependent global loads per soft bit, 55 % of the TCH3 kernel's stall samples (ncu, config 3).
+		if (ciphered) {
+			__shared__ int16_t s_cmap[NIN];
+			for (int r = tid; r < NIN; r += NT)
+				s_cmap[r] = tb.cmap[r];
+			__syncthreads();
+			constexpr int E = 8;
+			const int total = cnt * NROW;
+			for (int idx0 = tid; idx0 < total; idx0 += NT * E) {
+				int c[E];
+				unsigned cb[E];
+#pragma unroll
+				for (int e = 0; e < E; e++) {
+					const int idx = min(idx0 + e * NT, total - 1);
+					const int tt = idx / NROW, r = idx - tt * NROW;
+					c[e] = s_cmap[r];
+					cb[e] = a.ciph[(size_t)(base + tt) * chan_n_ciph(CH) + max(c[e], 0)];
+				}
+#pragma unroll
+				for (int e = 0; e < E; e++) {
+					const int idx = idx0 + e * NT;
+					if (idx < total && c[e] >= 0 && cb[e])
+						rows[idx] = (int8_t)sbit_neg(rows[idx]);
+				}
+			}
+			__syncthreads();
+		}
 	}
 
 	// ---- phase 2: one codeword (PAIR: two) per thread

@@ -179,9 +179,16 @@ GMR1_HD void decode_unit_k5(const TabRef &tb, const DecodeArgs &a, int unit,
 	uint8_t *out = (uint8_t *)row;
 	{
 		unsigned st = 0;
-		for (int i = tb.n_steps - 1; i >= tb.len; i--) {
-			const unsigned bit = (dec[(size_t)i * T + t] >> st) & 1u;
-			st = (st >> 1) | (bit << (C::K - 2));
+		{
+			uint16_t fw[C::K - 1];               // the K - 1 flush steps (n_steps = len + K - 1), requested together
+#pragma unroll
+			for (int j = 0; j < C::K - 1; j++)
+				fw[j] = dec[(size_t)(tb.len + j) * T + t];
+#pragma unroll
+			for (int j = C::K - 2; j >= 0; j--) {
+				const unsigned bit = ((unsigned)fw[j] >> st) & 1u;
+				st = (st >> 1) | (bit << (C::K - 2));
+			}
 		}
 		int i = tb.len - 1;
 		unsigned acc = 0;
@@ -192,6 +199,26 @@ GMR1_HD void decode_unit_k5(const TabRef &tb, const DecodeArgs &a, int unit,
 		}
 		if ((tb.len & 7) != 0)
 			out[tb.len >> 3] = (uint8_t)acc;
+		// The decision words live in global memory (L2) and their addresses do not depend on the state: 32 steps'
+		// words are requested together, then walked (four output bytes).  With 8 per batch the walk waited for L2
+		// 26 times per codeword on a kernel with four resident warps per scheduler: 19 % of its stall samples.
+		for (; i >= 31; i -= 32) {
+			uint16_t dw[32];
+#pragma unroll
+			for (int b = 0; b < 32; b++)
+				dw[b] = dec[(size_t)(i - 31 + b) * T + t];
+#pragma unroll
+			for (int q = 3; q >= 0; q--) {
+				acc = 0;
+#pragma unroll
+				for (int b = 7; b >= 0; b--) {
+					acc |= (st & 1u) << b;
+					const unsigned bit = ((unsigned)dw[8 * q + b] >> st) & 1u;
+					st = (st >> 1) | (bit << (C::K - 2));
+				}
+				out[(i >> 3) - 3 + q] = (uint8_t)acc;
+			}
+		}
 		for (; i >= 7; i -= 8) {
 			acc = 0;
 #pragma unroll
@@ -472,18 +499,33 @@ GMR1_HD void decode_pair_tch3(const TabRef &tb, const DecodeArgs &a, const P16Lu
 
 		// frame bits 0..47 from the decoder, 48..79 = sign of c[72..103]; MSB-first packing
 		uint32_t wa0 = 0, wa1 = 0, wa2 = 0, wb0 = 0, wb1 = 0, wb2 = 0;
-		for (int i = 47; i >= 0; i--) {
-			const uint32_t da = dec[(size_t)(i * 4 + (int)(sa >> 4)) * T + t], db = dec[(size_t)(i * 4 + (int)(sb >> 4)) * T + t];
-			if (i < 32) {
-				wa0 |= (sa & 1u) << (31 - i);
-				wb0 |= (sb & 1u) << (31 - i);
-			} else {
-				wa1 |= (sa & 1u) << (63 - i);
-				wb1 |= (sb & 1u) << (63 - i);
+		// Which of a step's four decision words a codeword needs depends on its state, so a load per step would be a
+		// chain of 48 dependent global loads: all four words of eight steps are requested together instead (32 loads
+		// in flight, six waits per frame) and the word is picked by selects.
+		for (int i0 = 40; i0 >= 0; i0 -= 8) {
+			uint32_t dw[8][4];
+#pragma unroll
+			for (int b = 0; b < 8; b++)
+#pragma unroll
+				for (int w = 0; w < 4; w++)
+					dw[b][w] = dec[(size_t)((i0 + b) * 4 + w) * T + t];
+#pragma unroll
+			for (int b = 7; b >= 0; b--) {
+				const int i = i0 + b;
+				const unsigned qa = sa >> 4, qb = sb >> 4;
+				const uint32_t da = (qa & 2u) ? ((qa & 1u) ? dw[b][3] : dw[b][2]) : ((qa & 1u) ? dw[b][1] : dw[b][0]);
+				const uint32_t db = (qb & 2u) ? ((qb & 1u) ? dw[b][3] : dw[b][2]) : ((qb & 1u) ? dw[b][1] : dw[b][0]);
+				if (i < 32) {
+					wa0 |= (sa & 1u) << (31 - i);
+					wb0 |= (sb & 1u) << (31 - i);
+				} else {
+					wa1 |= (sa & 1u) << (63 - i);
+					wb1 |= (sb & 1u) << (63 - i);
+				}
+				const unsigned ba = (da >> (sa & 15u)) & 1u, bb = (db >> (16u + (sb & 15u))) & 1u;
+				sa = (sa >> 1) | (ba << (C::K - 2));
+				sb = (sb >> 1) | (bb << (C::K - 2));
 			}
-			const unsigned ba = (da >> (sa & 15u)) & 1u, bb = (db >> (16u + (sb & 15u))) & 1u;
-			sa = (sa >> 1) | (ba << (C::K - 2));
-			sb = (sb >> 1) | (bb << (C::K - 2));
 		}
 		for (int j = 48; j < 80; j++) {
 			const uint16_t w = g[96 + (j - 48)];
