@@ -20,6 +20,9 @@
 #include "decode_unit.cuh"
 #include "tma.cuh"
 #include "launch.h"
+#ifndef T9_E
+#define T9_E 16        // TCH9 gather: elements per thread whose loads are issued together (8: 0.79, 16: 0.75 ms per 157 284 bursts)
+#endif
 #ifndef TPC_LUT
 #define TPC_LUT 1       // one codeword per thread: branch metrics through the shared-memory table (0: arithmetic)
 #endif
@@ -165,13 +168,13 @@ __global__ void __launch_bounds__(tpc_threads(PAIR)) decode_tpc_kernel(const Dec
 		for (int r = tid; r < 648; r += NT)
 			s_src[r] = tb.t9_src[r];
 		__syncthreads();
-		// eight elements per thread and pass: source addresses first (shared-memory lookups only), then the eight
+		// T9_E elements per thread and pass: source addresses first (shared-memory lookups only), then the eight
 		// byte loads back to back (clamped, so that they are unconditional), then the stores
 		// A ragged last tile takes a second copy of the loop whose unit index is checked against the tile's count
 		// (base + tt may lie behind the batch: found by compute-sanitizer on a 6-burst TCH9 batch).  The check is kept
 		// out of the full-tile copy: one more select in front of the index lookups cost 0.85 -> 1.18 ms per 157 284
 		// bursts (A/B on one box, tools/gpu_r2_t9ab.sh)
-		constexpr int E = 8;
+		constexpr int E = T9_E;
 		auto gather = [&](auto FULL) {
 		for (int idx0 = tid; idx0 < TPC_T * NROW; idx0 += NT * E) {
 			const int8_t *src[E];
@@ -243,23 +246,49 @@ __global__ void __launch_bounds__(tpc_threads(PAIR)) decode_tpc_kernel(const Dec
 			for (int r = tid; r < NIN; r += NT)
 				s_cmap[r] = tb.cmap[r];
 			__syncthreads();
-			constexpr int E = 8;
-			const int total = cnt * NROW;
-			for (int idx0 = tid; idx0 < total; idx0 += NT * E) {
-				int c[E];
-				unsigned cb[E];
+			// four soft bits (one word of the staged tile) per step: when their cipher bytes are four consecutive,
+			// word-aligned bytes - all of TCH3's but the word of the four unciphered status bits - they come with one
+			// 32-bit load, eight of those in flight per thread; other words take byte loads.  rows is 16-byte aligned.
+			constexpr int E = 8, NC = chan_n_ciph(CH);
+			const int nwords = (cnt * NROW + 3) / 4, total = cnt * NROW;
+			const uint8_t *ctile = a.ciph + (size_t)base * NC;
+			const uint8_t *safe = (const uint8_t *)(((uintptr_t)ctile + 3) & ~(uintptr_t)3);    // a valid aligned word
+			uint32_t *rows4 = (uint32_t *)rows;
+			for (int w0 = tid; w0 < nwords; w0 += NT * E) {
+				uint32_t cw[E];
+				int adr[E][4];
+				bool fast[E];
 #pragma unroll
 				for (int e = 0; e < E; e++) {
-					const int idx = min(idx0 + e * NT, total - 1);
-					const int tt = idx / NROW, r = idx - tt * NROW;
-					c[e] = s_cmap[r];
-					cb[e] = a.ciph[(size_t)(base + tt) * chan_n_ciph(CH) + max(c[e], 0)];
+					const int w = min(w0 + e * NT, nwords - 1);
+#pragma unroll
+					for (int k = 0; k < 4; k++) {
+						const int idx = 4 * w + k;
+						const int tt = idx / NROW, r = idx - tt * NROW;
+						const int c = idx < total ? (int)s_cmap[r] : -1;
+						adr[e][k] = c >= 0 ? tt * NC + c : -1;
+					}
+					fast[e] = adr[e][0] >= 0 && adr[e][1] == adr[e][0] + 1 && adr[e][2] == adr[e][0] + 2 &&
+					          adr[e][3] == adr[e][0] + 3 && ((((uintptr_t)ctile + (unsigned)adr[e][0]) & 3) == 0);
+					cw[e] = *(const uint32_t *)(fast[e] ? ctile + adr[e][0] : safe);
 				}
 #pragma unroll
 				for (int e = 0; e < E; e++) {
-					const int idx = idx0 + e * NT;
-					if (idx < total && c[e] >= 0 && cb[e])
-						rows[idx] = (int8_t)sbit_neg(rows[idx]);
+					const int w = w0 + e * NT;
+					if (w >= nwords)
+						continue;
+					uint32_t m = cw[e];
+					if (!fast[e]) {
+						m = 0;
+#pragma unroll
+						for (int k = 0; k < 4; k++)
+							if (adr[e][k] >= 0)
+								m |= (uint32_t)ctile[adr[e][k]] << (8 * k);
+					}
+					if (m) {
+						const uint32_t v = rows4[w], sel = __vcmpne4(m, 0u);      // 0xff where the cipher byte is set
+						rows4[w] = (__vneg4(v) & sel) | (v & ~sel);              // bytewise negate, -128 stays -128
+					}
 				}
 			}
 			__syncthreads();

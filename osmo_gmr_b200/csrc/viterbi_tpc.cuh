@@ -356,8 +356,7 @@ GMR1_HD void forward(uint32_t (&ae)[C::NS], const int8_t *row, const uint16_t *g
 			for (int s = 0; s < C::NS; s++)
 				ae[s] = tmp[s];
 		}
-		return;
-	}
+	} else {
 	for (; i + 1 < end; i += 2) {           // two steps per iteration: ae -> tmp -> ae
 		int v[C::N];
 		uint32_t dec[DW];
@@ -377,6 +376,7 @@ GMR1_HD void forward(uint32_t (&ae)[C::NS], const int8_t *row, const uint16_t *g
 #pragma unroll
 		for (int s = 0; s < C::NS; s++)
 			ae[s] = tmp[s];
+	}
 	}
 }
 
