@@ -29,10 +29,20 @@
 
 namespace gmr1 {
 
-static constexpr int TPC_T = 128;    // codewords per CTA
+static constexpr int TPC_T = 128;    // codewords per CTA (upper bound; tpc_tile(ch) is the tile of a channel)
+#ifndef TPC_T_XCCH
+#define TPC_T_XCCH 128
+#endif
+#ifndef TPC_T_RACH
+#define TPC_T_RACH 128
+#endif
+#ifndef TPC_T_BIG
+#define TPC_T_BIG 32                 // tile of the channels with 648 / 662-byte rows
+#endif
 // threads per CTA: one per codeword, or - PAIR - one per two codewords (viterbi_p16.cuh: thread i takes codewords
 // i and i + 64 of the tile)
-__host__ __device__ constexpr int tpc_threads(bool pair) { return pair ? TPC_T / 2 : TPC_T; }
+__host__ __device__ constexpr int tpc_tile(int ch);
+__host__ __device__ constexpr int tpc_threads(bool pair, int ch) { return pair ? tpc_tile(ch) / 2 : tpc_tile(ch); }
 
 // ---- device tables --------------------------------------------------------------------------
 __constant__ uint16_t c_g[CH_COUNT][MAX_CODED];     // gather programs (uniform access)
@@ -93,26 +103,35 @@ __host__ __device__ constexpr int chan_dec_bytes(int ch)
 {
 	return ch == CH_TCH3 ? 48 * 8 : chan_n_steps(ch) * 2;
 }
-__host__ __device__ constexpr int tpc_rows_bytes(int ch) { return (TPC_T * chan_n_row(ch) + 15) & ~15; }
+// Codewords per CTA.  FACCH9 / TCH9 rows are 662 / 648 bytes: 128 of them (83 KB) leave two CTAs = 8 warps per SM,
+// tiles of 32 (21 KB) ten CTAs = 10 warps and a finer interleave of the staging and the trellis phases of
+// neighbouring CTAs: FACCH9 0.352 -> 0.293 (64) -> 0.255 ms (32), TCH9-9k6 0.751 -> 0.647 -> 0.634 ms per 157 284
+// bursts.  The 424 / 432-byte BCCH / CCCH rows and RACH (494) are best at 128 (A/B on one box: 64 and 32 lose 1-5 %).
+__host__ __device__ constexpr int tpc_tile(int ch)
+{
+	return (ch == CH_FACCH9 || chan_is_t9(ch)) ? TPC_T_BIG : ch == CH_RACH ? TPC_T_RACH :
+	       (ch == CH_BCCH || ch == CH_CCCH) ? TPC_T_XCCH : TPC_T;
+}
+__host__ __device__ constexpr int tpc_rows_bytes(int ch) { return (tpc_tile(ch) * chan_n_row(ch) + 15) & ~15; }
 __host__ __device__ constexpr int tpc_smem_bytes(int ch)
 {
-	return tpc_rows_bytes(ch) + TPC_T * chan_dec_bytes(ch) + 16 + (int)sizeof(P16Lut);
+	return tpc_rows_bytes(ch) + tpc_tile(ch) * chan_dec_bytes(ch) + 16 + (int)sizeof(P16Lut);
 }
 
 // ---- thread-per-codeword kernel ------------------------------------------------------------------
 template <int CH, bool PAIR>
-__global__ void __launch_bounds__(tpc_threads(PAIR)) decode_tpc_kernel(const DecodeArgs a)
+__global__ void __launch_bounds__(tpc_threads(PAIR, CH)) decode_tpc_kernel(const DecodeArgs a)
 {
 	extern __shared__ __align__(16) uint8_t smem[];
-	constexpr int NIN = chan_n_in(CH), NROW = chan_n_row(CH), NT = tpc_threads(PAIR);
+	constexpr int NIN = chan_n_in(CH), NROW = chan_n_row(CH), NT = tpc_threads(PAIR, CH), TT = tpc_tile(CH);
 
-	int8_t *rows = (int8_t *)smem;                                    // [TPC_T][NROW], unpadded
+	int8_t *rows = (int8_t *)smem;                                    // [TT][NROW], unpadded
 	// survivor decisions [steps][words][slots]: in the caller's scratch (slot = unit, all units of the launch
 	// side by side: coalesced 64-byte stores per warp and step) or, without scratch, behind the rows in
 	// shared memory (slot = thread)
 	const bool gdec = a.dec_scratch != nullptr;
 	uint8_t *dec = gdec ? a.dec_scratch : smem + tpc_rows_bytes(CH);
-	uint64_t *bar = (uint64_t *)(smem + tpc_rows_bytes(CH) + (gdec ? 0 : TPC_T * chan_dec_bytes(CH)));
+	uint64_t *bar = (uint64_t *)(smem + tpc_rows_bytes(CH) + (gdec ? 0 : TT * chan_dec_bytes(CH)));
 	P16Lut *lut = (P16Lut *)(bar + 2);                                // PAIR: soft bit -> packed metrics
 
 	TabRef tb;
@@ -124,11 +143,11 @@ __global__ void __launch_bounds__(tpc_threads(PAIR)) decode_tpc_kernel(const Dec
 	tb.n_steps = chan_n_steps(CH); tb.len = chan_len(CH);
 
 	const int tid = threadIdx.x;
-	const int base = blockIdx.x * TPC_T;
+	const int base = blockIdx.x * TT;
 	const int n_eff = a.n_dev ? min(a.n, *a.n_dev) : a.n;
 	if (base >= n_eff)
 		return;                  // whole CTA, before any barrier
-	const int cnt = min(TPC_T, n_eff - base);
+	const int cnt = min(TT, n_eff - base);
 	if constexpr (PAIR) {
 		for (int i = tid; i < 512; i += NT)
 			(&lut->plain[0])[i] = p16_lut_word(i);                    // visible after the barrier that ends phase 1
@@ -142,15 +161,15 @@ __global__ void __launch_bounds__(tpc_threads(PAIR)) decode_tpc_kernel(const Dec
 	// by a second pass (below)
 	constexpr bool CAN_CIPH = !chan_is_t9(CH) && chan_n_ciph(CH) > 0;
 	const bool ciphered = CAN_CIPH && a.ciph != nullptr;
-	const bool bulk = !chan_is_t9(CH) && cnt == TPC_T && ((((uintptr_t)a.ebits) & 15) == 0);
+	const bool bulk = !chan_is_t9(CH) && cnt == TT && ((((uintptr_t)a.ebits) & 15) == 0);
 	if (bulk) {
-		// the tile is one contiguous, 16-byte aligned span of TPC_T*NIN bytes: a single TMA
+		// the tile is one contiguous, 16-byte aligned span of TT*NIN bytes: a single TMA
 		// bulk copy brings it in while no LSU instruction is spent on it
 		if (tid == 0) {
 			mbar_init(bar, 1);
 			mbar_fence_init();
-			mbar_arrive_expect_tx(bar, (uint32_t)(TPC_T * NIN));
-			tma_load_1d(rows, a.ebits + (size_t)base * NIN, (uint32_t)(TPC_T * NIN), bar);
+			mbar_arrive_expect_tx(bar, (uint32_t)(TT * NIN));
+			tma_load_1d(rows, a.ebits + (size_t)base * NIN, (uint32_t)(TT * NIN), bar);
 		}
 		__syncthreads();
 		mbar_wait(bar, 0);
@@ -159,9 +178,9 @@ __global__ void __launch_bounds__(tpc_threads(PAIR)) decode_tpc_kernel(const Dec
 		// go to shared memory first, so that an element costs one dependent global load instead of two, and
 		// four elements per thread are in flight (this staging, not the Viterbi, bounded the kernel: 8 resident
 		// warps per SM and a chain of three dependent loads per byte)
-		__shared__ int s_prev[2][TPC_T];
+		__shared__ int s_prev[2][TT];
 		__shared__ uint16_t s_src[648];
-		for (int u = tid; u < TPC_T; u += NT) {
+		for (int u = tid; u < TT; u += NT) {
 			s_prev[0][u] = (u < cnt && a.prev1) ? a.prev1[base + u] : -1;
 			s_prev[1][u] = (u < cnt && a.prev2) ? a.prev2[base + u] : -1;
 		}
@@ -176,13 +195,13 @@ __global__ void __launch_bounds__(tpc_threads(PAIR)) decode_tpc_kernel(const Dec
 		// bursts (A/B on one box, tools/gpu_r2_t9ab.sh)
 		constexpr int E = T9_E;
 		auto gather = [&](auto FULL) {
-		for (int idx0 = tid; idx0 < TPC_T * NROW; idx0 += NT * E) {
+		for (int idx0 = tid; idx0 < TT * NROW; idx0 += NT * E) {
 			const int8_t *src[E];
 			const uint8_t *csrc[E];
 			bool ok[E], flip[E];
 #pragma unroll
 			for (int e = 0; e < E; e++) {
-				const int idx = min(idx0 + e * NT, TPC_T * NROW - 1);
+				const int idx = min(idx0 + e * NT, TT * NROW - 1);
 				const int tt = idx / NROW, r = idx - tt * NROW;
 				const uint16_t w = s_src[r];
 				const int age = (w >> 10) & 3, sidx = w & G_IDX;
@@ -211,19 +230,19 @@ __global__ void __launch_bounds__(tpc_threads(PAIR)) decode_tpc_kernel(const Dec
 					x = sbit_neg(x);
 				if (flip[e])
 					x = sbit_neg(x);
-				if (idx0 + e * NT < TPC_T * NROW)
+				if (idx0 + e * NT < TT * NROW)
 					rows[idx0 + e * NT] = ok[e] ? (int8_t)x : (int8_t)0;
 			}
 		}
 		};
-		if (cnt == TPC_T)
+		if (cnt == TT)
 			gather(std::true_type{});
 		else
 			gather(std::false_type{});
 		__syncthreads();
 	} else if (chan_is_t9(CH)) {
 #pragma unroll 4
-		for (int idx = tid; idx < TPC_T * NROW; idx += NT) {
+		for (int idx = tid; idx < TT * NROW; idx += NT) {
 			const int tt = idx / NROW, r = idx - tt * NROW;
 			rows[idx] = (tt < cnt) ? stage_elem<CH>(tb, a, base + tt, r) : (int8_t)0;
 		}
@@ -231,7 +250,7 @@ __global__ void __launch_bounds__(tpc_threads(PAIR)) decode_tpc_kernel(const Dec
 	} else {
 		// ragged last tile or unaligned batch: plain coalesced copy (NROW == NIN: the tile is one span of bytes)
 #pragma unroll 4
-		for (int idx = tid; idx < TPC_T * NROW; idx += NT)
+		for (int idx = tid; idx < TT * NROW; idx += NT)
 			rows[idx] = idx < cnt * NROW ? a.ebits[(size_t)base * NIN + idx] : (int8_t)0;
 		__syncthreads();
 	}
@@ -307,7 +326,7 @@ __global__ void __launch_bounds__(tpc_threads(PAIR)) decode_tpc_kernel(const Dec
 				                   rows + (tid + NT) * NROW, (uint32_t *)dec, T, t);
 		}
 	} else if (tid < cnt) {
-		const int T = gdec ? (int)gridDim.x * TPC_T : TPC_T, t = gdec ? base + tid : tid;
+		const int T = gdec ? (int)gridDim.x * TT : TT, t = gdec ? base + tid : tid;
 		if constexpr (CH == CH_TCH3)
 			decode_unit_tch3<TPC_LUT != 0>(tb, a, base + tid, rows + tid * NROW, (uint32_t *)dec, T, t, (const RelLut *)lut);
 		else
@@ -346,10 +365,10 @@ static cudaError_t launch_tpc(const DecodeArgs &a, cudaStream_t st)
 		if (dev < 64)
 			attr_done[dev] = true;
 	}
-	const int grid = (a.n + TPC_T - 1) / TPC_T;
+	const int grid = (a.n + tpc_tile(CH) - 1) / tpc_tile(CH);
 	const int smem_used = (a.dec_scratch ? tpc_rows_bytes(CH) + 16 : smem - (int)sizeof(P16Lut)) +
 	                      (PAIR ? (int)sizeof(P16Lut) : TPC_LUT ? (int)sizeof(RelLut) : 0);
-	decode_tpc_kernel<CH, PAIR><<<grid, tpc_threads(PAIR), smem_used, st>>>(a);
+	decode_tpc_kernel<CH, PAIR><<<grid, tpc_threads(PAIR, CH), smem_used, st>>>(a);
 	return cudaGetLastError();
 }
 
