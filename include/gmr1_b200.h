@@ -147,8 +147,8 @@ int gmr1b200_set_sync_accumulator_reset(int on);
 
 /* Kernel selection switch (testing / A-B measurements).  The ten standard burst formats at sps 4 and their standard
  * search widths (what gmr1_rx cuts: BCCH 20*sps, DC6 10*sps, NT3 / NT9 sps + sps/2, src/gmr1_rx.c:290,549,759,809) run
- * on kernels specialised per format at compile time; everything else (other sps / widths, custom descriptors, RACH,
- * detect) runs on the generic kernel.  1 forces the generic kernel for everything; both compute the same function
+ * on kernels specialised per format at compile time (RACH with sps + sps/2 included); everything else (other sps /
+ * widths, custom descriptors, detect) runs on the generic kernel.  1 forces the generic kernel for everything; both compute the same function
  * and are held to the same parity tests.  Process-wide; returns the previous setting. */
 int gmr1b200_set_demod_generic(int on);
 
