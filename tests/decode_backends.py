@@ -69,9 +69,12 @@ class EmuBackend:
 
 
 class GpuBackend:
-    def __init__(self, lib, device=False):
+    def __init__(self, lib, device=False, misalign=0):
+        """misalign (device only): soft bits and cipher bytes start `misalign` bytes behind a 16-byte boundary (no bulk
+        copy of the tile, no word loads of the cipher bytes)"""
         self.lib = lib
         self.device = device
+        self.misalign = misalign
         self.name = "gpu-dev" if device else "gpu-host"
 
     def decode(self, ch, e, ciph=None, prev1=None, prev2=None, sb_mask=None, m=0):
@@ -80,7 +83,17 @@ class GpuBackend:
         if self.device:
             import torch
             dev = lambda a: None if a is None else torch.from_numpy(a).cuda()
-            ins = [dev(x) for x in (e, ciph, prev1, prev2, sb_mask)]
+
+            def dev_off(a):
+                if a is None or not self.misalign:
+                    return dev(a)
+                flat = torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1))
+                buf = torch.zeros(flat.numel() + 32, dtype=torch.uint8, device="cuda")
+                sl = buf[self.misalign:self.misalign + flat.numel()]
+                sl.copy_(flat)
+                assert sl.data_ptr() % 16 == self.misalign % 16
+                return sl.view(torch.int8 if a.dtype == np.int8 else torch.uint8).view(a.shape)
+            ins = [dev_off(e), dev_off(ciph)] + [dev(x) for x in (prev1, prev2, sb_mask)]
             e_, ciph_, prev1_, prev2_, sb_ = ins
             d = {k: dev(v) for k, v in o.items()}
         else:

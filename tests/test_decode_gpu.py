@@ -49,6 +49,17 @@ def test_tch3(be, oracle, use_ciph, m):
     dp.check_tch3(be, oracle, 200, 27, use_ciph, m)
 
 
+@pytest.mark.parametrize("off", [1, 2, 8])
+def test_ciphered_channels_unaligned_inputs(gpu_lib, oracle, off):
+    """soft bits and cipher bytes that do not start on a 16-byte boundary: the tile comes in by the plain copy instead
+    of the bulk copy, the cipher pass takes byte loads where its words are not aligned; full tiles + a ragged one"""
+    be = GpuBackend(gpu_lib, device=True, misalign=off)
+    dp.check_tch3(be, oracle, 128 * 2 + 37, 31, True, 0)
+    dp.check_facch3(be, oracle, 128 + 5, 32, True)
+    dp.check_facch9(be, oracle, 32 * 3 + 7, 33, True)
+    dp.check_simple(be, oracle, "bcch", CH["BCCH"], 424, 128 + 9, 34)
+
+
 def test_dc12(be, oracle):
     dp.check_dc12(be, oracle, 70, 28)
 

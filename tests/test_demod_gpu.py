@@ -118,32 +118,37 @@ def test_sync_power_fast_vs_generic(gpu_lib):
         assert d.max() <= 1 and (d == 0).mean() > 0.995
 
 
-def test_demod_device_pointers_and_freq_shift(gpu_lib, oracle):
+@pytest.mark.parametrize("name,win", [("bcch", 80), ("rach", 6)])
+def test_demod_device_pointers_and_freq_shift(gpu_lib, oracle, name, win):
+    """a frequency shift per window (the per-format kernels rebuild their rotated taps when it changes; RACH has its
+    own tap layout: one row of lanes per chunk)"""
     rng = np.random.default_rng(7)
-    x, _, _ = gen("bcch", 40, 80, rng)
+    x, _, _ = gen(name, 40, win, rng)
     fsh = rng.uniform(-0.01, 0.01, 40).astype(np.float32)
-    got = gpu_demod(gpu_lib, "bcch", x, freq_shift=fsh, device=True)
-    compare("bcch", oracle, x, got, freq_shift=fsh)
+    got = gpu_demod(gpu_lib, name, x, freq_shift=fsh, device=True)
+    compare(name, oracle, x, got, freq_shift=fsh)
 
 
+@pytest.mark.parametrize("name,win", [("bcch", 80), ("rach", 6)])
 @pytest.mark.parametrize("generic", [0, 1])
-def test_demod_hot_path_layouts(gpu_lib, oracle, generic):
+def test_demod_hot_path_layouts(gpu_lib, oracle, generic, name, win):
     prev = gpu_lib.call("gmr1b200_set_demod_generic", generic)
     try:
-        _hot_path_layouts(gpu_lib, oracle)
+        _hot_path_layouts(gpu_lib, oracle, name, win)
     finally:
         gpu_lib.call("gmr1b200_set_demod_generic", prev)
 
 
-def _hot_path_layouts(gpu_lib, oracle):
+def _hot_path_layouts(gpu_lib, oracle, name="bcch", win=80):
     """The same bursts through the kernel's usual path (no sync power requested, 16-byte aligned windows, even
     soft-bit rows) and through its out-of-line variants (odd soft-bit row stride -> byte stores, windows at an odd
     sample offset -> unaligned statistics loop + separate region copy, sync power requested) give the same soft bits."""
     rng = np.random.default_rng(77)
     n = 48
-    x, _, _ = gen("bcch", n, 80, rng)
-    ref = gpu_demod(gpu_lib, "bcch", x)                      # sync power requested (cold statistics variant)
-    compare("bcch", oracle, x, ref)
+    x, _, _ = gen(name, n, win, rng)
+    neb = sigen.burst_ebits(name)
+    ref = gpu_demod(gpu_lib, name, x)                      # sync power requested (cold statistics variant)
+    compare(name, oracle, x, ref)
     wl = x.shape[1]
     iq = np.ascontiguousarray(x).view(np.float32)
 
@@ -152,19 +157,19 @@ def _hot_path_layouts(gpu_lib, oracle):
         sid = np.full(n, -9, np.int32)
         toa = np.zeros(n, np.float32)
         fe = np.zeros(n, np.float32)
-        gpu_lib.call("gmr1b200_pi4cxpsk_demod_batch", sigen.BT_ID["bcch"], iq_buf, iq_len, ofs, stride, wl, 4, None, 0.0,
+        gpu_lib.call("gmr1b200_pi4cxpsk_demod_batch", sigen.BT_ID[name], iq_buf, iq_len, ofs, stride, wl, 4, None, 0.0,
                      eb, eb_stride, sid, toa, fe, None, n, None)
         return eb, sid, toa, fe
 
-    for eb_stride in (424, 425, 431):
+    for eb_stride in (neb, neb + 1, neb + 7):
         eb, sid, toa, fe = run(iq, n * wl, None, wl, eb_stride)
-        assert (eb[:, :424] == ref[0]).all() and (sid == ref[1]).all()
+        assert (eb[:, :neb] == ref[0]).all() and (sid == ref[1]).all()
         assert np.abs(toa - ref[2]).max() < 1e-6 and np.abs(fe - ref[3]).max() < 1e-7
     # windows at odd sample offsets (8-byte but not 16-byte aligned)
     pad = np.zeros((n, 2 * (wl + 1)), np.float32)
     pad[:, 2:] = iq.reshape(n, 2 * wl)
     ofs = (np.arange(n, dtype=np.int64) * (wl + 1) + 1)
-    eb, sid, toa, fe = run(pad, n * (wl + 1), ofs, 0, 424)
+    eb, sid, toa, fe = run(pad, n * (wl + 1), ofs, 0, neb)
     d = np.abs(eb.astype(int) - ref[0].astype(int))
     assert (sid == ref[1]).all() and np.abs(toa - ref[2]).max() <= 0.004 and d.max() <= 1 and (d == 0).mean() > 0.999
 
