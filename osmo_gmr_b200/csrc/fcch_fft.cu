@@ -39,6 +39,12 @@ constexpr int FF_T = FF_N / 16;                    // 512 threads: one radix-16 
 constexpr int FF_RS = cfft::RowStride<FF_N>::value;
 constexpr int FF_PER = FF_N / FF_T;                // 16 consecutive outputs per thread in the peak search
 constexpr int FF_MAXLEN = 128;
+// Two-block form (overlap-save): the window as two 4096-point blocks, block 1 starting FF_HOP samples into the window,
+// each half of the CTA transforming one of them.  4096 = 16^3: three radix-16 stages per transform and no closing
+// radix-2 stage - three shared-memory passes instead of four - and 8 % fewer butterflies than one 8192-point transform.
+// Block b delivers the correlation outputs [b FF_HOP, b FF_HOP + 4096 - len]; two rows of 4096 + 256 points take
+// exactly the shared memory of one row of 8192 + 512.
+constexpr int FF_N2 = 4096, FF_HOP = 3712;
 
 struct TwLdg {
 	const float2 *t;
@@ -53,14 +59,27 @@ __device__ __forceinline__ float wsum(float v)
 	return v;
 }
 
-// stage S (radix 16, NS = 16^S) of the reverse transform, in place
-template <int S> __device__ __forceinline__ void stage16(float2 *row, const TwLdg tw, int tid)
+// stage S (radix 16, NS = 16^S) of the reverse transform of TN points, in place; u = butterfly of this thread
+template <int TN, int S> __device__ __forceinline__ void stage16(float2 *row, const TwLdg tw, int u)
 {
-	typedef cfft::Stage<FF_N, cfft::Plan<FF_LOG2N>::pow16(S), 16> St;
+	typedef cfft::Stage<TN, cfft::Plan<13>::pow16(S), 16> St;
 	float2 v[16];
-	St::read(row, tid, tw, v);
+	St::read(row, u, tw, v);
 	__syncthreads();
-	St::write(row, tid, v);
+	St::write(row, u, v);
+	__syncthreads();
+}
+
+// the same with the outputs handed to f(point index, value) instead of stored to the row
+template <int TN, int S, class F> __device__ __forceinline__ void stage16_out(const float2 *row, const TwLdg tw, int u, F f)
+{
+	typedef cfft::Stage<TN, cfft::Plan<13>::pow16(S), 16> St;
+	float2 v[16];
+	St::read(row, u, tw, v);
+	__syncthreads();                       // the outputs may land in the memory the inputs came from
+#pragma unroll
+	for (int q = 0; q < 16; q++)
+		f(St::out_index(u, q), v[q]);
 	__syncthreads();
 }
 
@@ -83,8 +102,8 @@ template <class F> __device__ __forceinline__ void stage2_out(const float2 *row,
 
 struct FftPlan {
 	int32_t n_shifts;
-	const float2 *T;                       // [n_shifts][FF_N] tap spectra / N
-	const float2 *tw;                      // [FF_N] e^{+2 pi i t / N}
+	const float2 *T;                       // [n_shifts][N] tap spectra / N (N = 8192, two-block form: 4096)
+	const float2 *tw;                      // [N] e^{+2 pi i t / N}
 	float2 *spec;                          // MULTI: [gridDim.x][FF_N] the window's spectrum between the shifts
 };
 
@@ -92,7 +111,7 @@ struct FftPlan {
 // MULTI (several shifts per window): the spectrum is parked in the CTA's own 64 KB of global scratch (written once,
 // read once per shift with coalesced loads, L2-resident: 296 CTAs x 64 KB) - a second shared-memory row would halve
 // the CTAs per SM.  Single shift: the product is taken in place.
-template <bool MULTI>
+template <bool MULTI, bool SPLIT>
 __global__ void __launch_bounds__(FF_T, 2)
 fcch_fft_kernel(const FcchArgs a, const FftPlan fp, int32_t *toa_out, float *peak_out)
 {
@@ -100,6 +119,10 @@ fcch_fft_kernel(const FcchArgs a, const FftPlan fp, int32_t *toa_out, float *pea
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	float2 *A = (float2 *)smem;
 	float2 *B = A;
+	// SPLIT: block h of the window in row Ah, butterfly u of its transform
+	constexpr int TN = SPLIT ? FF_N2 : FF_N, RSH = cfft::RowStride<FF_N2>::value;
+	const int h = SPLIT ? tid >> 8 : 0, u = SPLIT ? tid & 255 : tid;
+	float2 *Ah = A + h * RSH;
 	float *red = (float *)(A + FF_RS);     // [96] reduction scratch
 	float2 *spec = MULTI ? fp.spec + (size_t)blockIdx.x * FF_N : nullptr;
 	const int L = a.win_len, len = a.len;
@@ -136,7 +159,9 @@ fcch_fft_kernel(const FcchArgs a, const FftPlan fp, int32_t *toa_out, float *pea
 				q2 = __ffma2_rn(p1, p1, q2);
 				q2 = __ffma2_rn(p2, p2, q2);
 				q2 = __ffma2_rn(p3, p3, q2);
-				A[cfft::pad(i)] = p0;
+				// SPLIT: one store per sample as well (a second, predicated one for the overlap kept the compiler from
+				// issuing the loads of the unrolled iterations together); the overlap is copied below
+				A[SPLIT && i >= FF_N2 ? RSH + cfft::pad(i - FF_HOP) : cfft::pad(i)] = p0;
 			}
 		} else {
 #pragma unroll 1
@@ -147,7 +172,7 @@ fcch_fft_kernel(const FcchArgs a, const FftPlan fp, int32_t *toa_out, float *pea
 					s2 = __fadd2_rn(s2, v);
 					q2 = __ffma2_rn(v, v, q2);
 					if (k == 0)
-						A[cfft::pad(i)] = v;
+						A[SPLIT && i >= FF_N2 ? RSH + cfft::pad(i - FF_HOP) : cfft::pad(i)] = v;
 				}
 		}
 		sr = s2.x;
@@ -170,6 +195,11 @@ fcch_fft_kernel(const FcchArgs a, const FftPlan fp, int32_t *toa_out, float *pea
 		red[32 + warp] = sq;
 	}
 	__syncthreads();
+	if (SPLIT) {                           // samples FF_HOP .. 4095 belong to both blocks
+		for (int j = tid; j < FF_N2 - FF_HOP; j += FF_T)
+			A[RSH + cfft::pad(j)] = A[cfft::pad(FF_HOP + j)];
+		__syncthreads();
+	}
 	sr = wsum(lane < FF_T / 32 ? red[lane] : 0.0f);
 	si = wsum(lane < FF_T / 32 ? red[16 + lane] : 0.0f);
 	sq = wsum(lane < FF_T / 32 ? red[32 + lane] : 0.0f);
@@ -181,47 +211,69 @@ fcch_fft_kernel(const FcchArgs a, const FftPlan fp, int32_t *toa_out, float *pea
 	const float inv_sd = 1.0f / sd;
 	// normalised samples, conjugated (the forward transform is run as conj . reverse . conj), zeros behind the window
 	for (int i = tid; i < FF_N; i += FF_T) {
-		float2 *p = &A[cfft::pad(i)];
-		*p = i < l ? make_float2((p->x - ar) * inv_sd, -((p->y - ai) * inv_sd)) : make_float2(0.0f, 0.0f);
+		// SPLIT: point i & 4095 of block i >> 12 is sample (i >> 12) FF_HOP + (i & 4095) of the window
+		float2 *p = SPLIT ? &A[(i >> 12) * RSH + cfft::pad(i & (FF_N2 - 1))] : &A[cfft::pad(i)];
+		const int g = SPLIT ? (i >> 12) * FF_HOP + (i & (FF_N2 - 1)) : i;
+		*p = g < l ? make_float2((p->x - ar) * inv_sd, -((p->y - ai) * inv_sd)) : make_float2(0.0f, 0.0f);
 	}
 	__syncthreads();
 
-	// ---- R = reverse(conj y) = conj(DFT(y)), in place in A
+	// ---- R = reverse(conj y) = conj(DFT(y)), in place in A (SPLIT: of each block, in its row)
 	{
-		typedef cfft::Stage<FF_N, 1, 16> St0;
+		typedef cfft::Stage<TN, 1, 16> St0;
 		float2 v[16];
-		St0::read(A, tid, tw, v);
+		St0::read(Ah, u, tw, v);
 		__syncthreads();
-		St0::write(A, tid, v);
+		St0::write(Ah, u, v);
 		__syncthreads();
 	}
-	stage16<1>(A, tw, tid);
-	stage16<2>(A, tw, tid);
-	if (MULTI)
-		stage2_out(A, tw, tid, [spec](int k, float2 v) { spec[k] = v; });
-	else
-		stage2_out(A, tw, tid, [A](int k, float2 v) { A[cfft::pad(k)] = v; });
+	stage16<TN, 1>(Ah, tw, u);
+	if (SPLIT) {
+		if (MULTI)
+			stage16_out<TN, 2>(Ah, tw, u, [spec, h](int k, float2 v) { spec[h * FF_N2 + k] = v; });
+		else
+			stage16_out<TN, 2>(Ah, tw, u, [Ah](int k, float2 v) { Ah[cfft::pad(k)] = v; });
+	} else {
+		stage16<TN, 2>(Ah, tw, u);
+		if (MULTI)
+			stage2_out(A, tw, tid, [spec](int k, float2 v) { spec[k] = v; });
+		else
+			stage2_out(A, tw, tid, [A](int k, float2 v) { A[cfft::pad(k)] = v; });
+	}
 
 	// ---- per shift: corr = reverse(conj(R) . T_s), energies, peak
 	float *en = (float *)B;                // [4 zeros][FF_N] energies, over the first half of B
 #pragma unroll 1
 	for (int s = 0; s < fp.n_shifts; s++) {
-		const float2 *T = fp.T + (size_t)s * FF_N;
+		const float2 *T = fp.T + (size_t)s * TN;
+		float2 *Bh = B + h * RSH;
 		{
-			typedef cfft::Stage<FF_N, 1, 16> St0;
+			typedef cfft::Stage<TN, 1, 16> St0;
 			float2 v[16];
-			St0::read_ld([A, T, spec](int i) {
-				const float2 r = MULTI ? spec[i] : A[cfft::pad(i)], t = __ldg(&T[i]);
+			St0::read_ld([Ah, T, spec, h](int i) {
+				const float2 r = MULTI ? spec[h * FF_N2 + i] : Ah[cfft::pad(i)], t = __ldg(&T[i]);
 				return make_float2(r.x * t.x + r.y * t.y, r.x * t.y - r.y * t.x);      // conj(r) t
-			}, tid, tw, v);
+			}, u, tw, v);
 			if (!MULTI)
 				__syncthreads();
-			St0::write(B, tid, v);
+			St0::write(Bh, u, v);
 			__syncthreads();
 		}
-		stage16<1>(B, tw, tid);
-		stage16<2>(B, tw, tid);
-		stage2_out(B, tw, tid, [en, nc](int k, float2 v) { en[4 + k] = k < nc ? v.x * v.x + v.y * v.y : 0.0f; });
+		stage16<TN, 1>(Bh, tw, u);
+		if (SPLIT) {
+			// block 0 delivers the outputs [0, FF_HOP), block 1 the rest; everything from nc on is 0 for the peak search
+			const int len1 = FF_N2 - len + 1;              // valid (non-wrapped) outputs of a block
+			stage16_out<TN, 2>(Bh, tw, u, [en, nc, h, len1](int k, float2 v) {
+				const int m = h * FF_HOP + k;
+				if (h ? true : k < FF_HOP)
+					en[4 + m] = (m < nc && k < len1) ? v.x * v.x + v.y * v.y : 0.0f;
+			});
+			for (int m = FF_HOP + FF_N2 + tid; m < FF_N; m += FF_T)
+				en[4 + m] = 0.0f;
+		} else {
+			stage16<TN, 2>(Bh, tw, u);
+			stage2_out(B, tw, tid, [en, nc](int k, float2 v) { en[4 + k] = k < nc ? v.x * v.x + v.y * v.y : 0.0f; });
+		}
 		if (tid < 4)
 			en[tid] = 0.0f;
 		__syncthreads();
@@ -293,12 +345,12 @@ fcch_fft_kernel(const FcchArgs a, const FftPlan fp, int32_t *toa_out, float *pea
 
 // ---- tap spectra, cached per device -------------------------------------------------------------------------------
 struct SpecKey {
-	int dev, len, n_shifts;
+	int dev, len, n_shifts, tn;             // tn: transform size (8192, two-block form 4096)
 	float freq;
 	float shifts[16];
 	bool operator==(const SpecKey &o) const
 	{
-		if (dev != o.dev || len != o.len || n_shifts != o.n_shifts || freq != o.freq)
+		if (dev != o.dev || len != o.len || n_shifts != o.n_shifts || tn != o.tn || freq != o.freq)
 			return false;
 		for (int i = 0; i < n_shifts; i++)
 			if (shifts[i] != o.shifts[i])
@@ -311,7 +363,7 @@ struct SpecEntry {
 	float2 *T;
 };
 std::vector<SpecEntry> g_spec;             // under GMR1_INIT_LOCK
-float2 *g_tw[64];
+float2 *g_tw[2][64];                      // [two-block form][device]
 int     g_ctas[64];                        // persistent CTAs per launch: 2 x SMs
 
 cudaError_t spectra(const SpecKey &key, const float2 **T, const float2 **tw)
@@ -319,17 +371,18 @@ cudaError_t spectra(const SpecKey &key, const float2 **T, const float2 **tw)
 	GMR1_INIT_LOCK();
 	if (key.dev < 0 || key.dev >= 64)
 		return cudaErrorInvalidDevice;
-	if (!g_tw[key.dev]) {
-		std::vector<float2> h(FF_N);
-		for (int t = 0; t < FF_N; t++)
-			h[t] = make_float2((float)cos(2.0 * M_PI * t / FF_N), (float)sin(2.0 * M_PI * t / FF_N));
-		cudaError_t e = cudaMalloc((void **)&g_tw[key.dev], FF_N * sizeof(float2));
+	const int TN = key.tn, w = TN == FF_N ? 0 : 1;
+	if (!g_tw[w][key.dev]) {
+		std::vector<float2> h(TN);
+		for (int t = 0; t < TN; t++)
+			h[t] = make_float2((float)cos(2.0 * M_PI * t / TN), (float)sin(2.0 * M_PI * t / TN));
+		cudaError_t e = cudaMalloc((void **)&g_tw[w][key.dev], TN * sizeof(float2));
 		if (e != cudaSuccess)
 			return e;
-		if ((e = cudaMemcpy(g_tw[key.dev], h.data(), FF_N * sizeof(float2), cudaMemcpyHostToDevice)) != cudaSuccess)
+		if ((e = cudaMemcpy(g_tw[w][key.dev], h.data(), TN * sizeof(float2), cudaMemcpyHostToDevice)) != cudaSuccess)
 			return e;
 	}
-	*tw = g_tw[key.dev];
+	*tw = g_tw[w][key.dev];
 	for (const SpecEntry &e : g_spec)
 		if (e.key == key) {
 			*T = e.T;
@@ -337,12 +390,12 @@ cudaError_t spectra(const SpecKey &key, const float2 **T, const float2 **tw)
 		}
 	// dual-chirp reference at 1 sample/symbol as the reference computes it in float (fcch.c:182-190), times e^{j f n},
 	// transformed in double
-	std::vector<double> wr(FF_N), wi(FF_N);
-	for (int t = 0; t < FF_N; t++) {
-		wr[t] = cos(2.0 * M_PI * t / FF_N);
-		wi[t] = sin(2.0 * M_PI * t / FF_N);
+	std::vector<double> wr(TN), wi(TN);
+	for (int t = 0; t < TN; t++) {
+		wr[t] = cos(2.0 * M_PI * t / TN);
+		wi[t] = sin(2.0 * M_PI * t / TN);
 	}
-	std::vector<float2> h((size_t)key.n_shifts * FF_N);
+	std::vector<float2> h((size_t)key.n_shifts * TN);
 	const float phase_base = key.freq * 2.0f * 3.14159265358979323846264338327f / (float)key.len;
 	const float halfpos = (float)key.len / 2.0f;
 	for (int s = 0; s < key.n_shifts; s++) {
@@ -354,14 +407,14 @@ cudaError_t spectra(const SpecKey &key, const float2 **T, const float2 **tw)
 			cr[n] = (double)r * cos((double)ang);
 			ci[n] = (double)r * sin((double)ang);
 		}
-		for (int k = 0; k < FF_N; k++) {
+		for (int k = 0; k < TN; k++) {
 			double tr = 0.0, ti = 0.0;
 			for (int n = 0; n < key.len; n++) {
-				const int idx = (int)(((int64_t)k * n) & (FF_N - 1));
+				const int idx = (int)(((int64_t)k * n) & (TN - 1));
 				tr += cr[n] * wr[idx] - ci[n] * wi[idx];
 				ti += cr[n] * wi[idx] + ci[n] * wr[idx];
 			}
-			h[(size_t)s * FF_N + k] = make_float2((float)(tr / FF_N), (float)(ti / FF_N));
+			h[(size_t)s * TN + k] = make_float2((float)(tr / TN), (float)(ti / TN));
 		}
 	}
 	float2 *d = nullptr;
@@ -403,6 +456,10 @@ cudaError_t launch_fcch_fft(const FcchArgs &a, const float *shifts, int n_shifts
 	cudaError_t e = cudaGetDevice(&key.dev);
 	if (e != cudaSuccess)
 		return e;
+	// two-block form when the window fits two overlapping 4096-point blocks (the standard 330 ms window does)
+	static const bool env_one = [] { const char *e = getenv("GMR1B200_FCCH_FFT_SPLIT"); return e && atoi(e) == 0; }();   // A/B knob
+	const bool split = !env_one && l <= FF_HOP + FF_N2 && l > FF_N2 && nc <= FF_HOP + (FF_N2 - a.len + 1);
+	key.tn = split ? FF_N2 : FF_N;
 	key.len = a.len;
 	key.freq = a.freq;
 	if (!shifts) {
@@ -432,13 +489,15 @@ cudaError_t launch_fcch_fft(const FcchArgs &a, const float *shifts, int n_shifts
 			g_ctas[key.dev] = 2 * sms;
 		}
 		ctas = g_ctas[key.dev];
-		static bool attr_set[64][2];
-		const void *fn = multi ? (const void *)fcch_fft_kernel<true> : (const void *)fcch_fft_kernel<false>;
-		if (key.dev >= 64 || !attr_set[key.dev][multi]) {
-			if ((e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+		static bool attr_set[64][4];
+		const void *fns[4] = {(const void *)fcch_fft_kernel<false, false>, (const void *)fcch_fft_kernel<true, false>,
+		                      (const void *)fcch_fft_kernel<false, true>, (const void *)fcch_fft_kernel<true, true>};
+		const int fi = (multi ? 1 : 0) + (split ? 2 : 0);
+		if (key.dev >= 64 || !attr_set[key.dev][fi]) {
+			if ((e = cudaFuncSetAttribute(fns[fi], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
 				return e;
 			if (key.dev < 64)
-				attr_set[key.dev][multi] = true;
+				attr_set[key.dev][fi] = true;
 		}
 	}
 	// several shifts per window: persistent CTAs (the spectrum parking is per CTA); one shift: a CTA per window, the
@@ -447,12 +506,18 @@ cudaError_t launch_fcch_fft(const FcchArgs &a, const float *shifts, int n_shifts
 	if (multi) {                           // spectrum parking of this launch: stream-ordered, back to the pool right behind it
 		if ((e = cudaMallocAsync((void **)&fp.spec, (size_t)grid * FF_N * sizeof(float2), st)) != cudaSuccess)
 			return e;
-		fcch_fft_kernel<true><<<grid, FF_T, smem, st>>>(a, fp, toa, peak);
+		if (split)
+			fcch_fft_kernel<true, true><<<grid, FF_T, smem, st>>>(a, fp, toa, peak);
+		else
+			fcch_fft_kernel<true, false><<<grid, FF_T, smem, st>>>(a, fp, toa, peak);
 		e = cudaGetLastError();
 		cudaFreeAsync(fp.spec, st);
 		return e;
 	}
-	fcch_fft_kernel<false><<<grid, FF_T, smem, st>>>(a, fp, toa, peak);
+	if (split)
+		fcch_fft_kernel<false, true><<<grid, FF_T, smem, st>>>(a, fp, toa, peak);
+	else
+		fcch_fft_kernel<false, false><<<grid, FF_T, smem, st>>>(a, fp, toa, peak);
 	return cudaGetLastError();
 }
 
