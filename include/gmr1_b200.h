@@ -409,9 +409,11 @@ int gmr1b200_fcch_rough_batch(int fcch_type, const float *iq, int64_t iq_len,
 
 /* Kernel selection switch (testing / A-B measurements): the coarse FCCH searches (gmr1b200_fcch_rough_batch with one
  * shift for all windows, _rough_grid_batch, _acquire_batch; sps 4, windows up to 8192 symbols) correlate in the
- * frequency domain - one 8192-point transform of the decimated window, one product + reverse transform per shift
- * (csrc/fcch_fft.cu).  0 sends them to the direct-correlation kernels (csrc/fcch_grid.cu), which also serve every
- * other geometry.  Same results up to float rounding.  Process-wide; returns the previous setting (default 1). */
+ * frequency domain - one forward transform of the decimated window, one product + reverse transform per shift
+ * (csrc/fcch_fft.cu); windows of 4097 .. 7808 symbols (the standard 330 ms window has 7722) as two overlapping
+ * 4096-point blocks, others as one 8192-point block.  0 sends them to the direct-correlation kernels
+ * (csrc/fcch_grid.cu), which also serve every other geometry; 2 = frequency domain, always one 8192-point block.
+ * Same results up to float rounding.  Process-wide; returns the previous setting (default 1). */
 int gmr1b200_set_fcch_fft(int on);
 /* gmr1_fcch_rough for a GRID of frequency shifts per window (the "+-frequency-offset FCCH search" of a receiver that
  * does not know its carrier offset yet: n_shifts calls of gmr1_fcch_rough, src/sdr/fcch.c:211, with freq_shift =

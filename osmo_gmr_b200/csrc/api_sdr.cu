@@ -483,8 +483,9 @@ static int fine_or_snr(int mode, int fcch_type, const float *iq, int64_t iq_len,
 int gmr1b200_set_fcch_fft(int on)
 {
 	static std::atomic<int> cur{1};
-	const int prev = cur.exchange(on ? 1 : 0);
-	fcch_fft_enable(on ? 1 : 0);
+	const int mode = on == 2 ? 2 : (on ? 1 : 0);
+	const int prev = cur.exchange(mode);
+	fcch_fft_enable(mode);
 	return prev;
 }
 

@@ -434,11 +434,16 @@ cudaError_t spectra(const SpecKey &key, const float2 **T, const float2 **tw)
 	return cudaSuccess;
 }
 
-std::atomic<int> g_fft_off{0};
+std::atomic<int> g_fft_off{0}, g_fft_one_block{0};
 
 }  // namespace
 
-void fcch_fft_enable(int on) { g_fft_off.store(on ? 0 : 1); }
+// 0: off (direct kernels), 1: on, 2: on, always one 8192-point block
+void fcch_fft_enable(int on)
+{
+	g_fft_off.store(on ? 0 : 1);
+	g_fft_one_block.store(on == 2 ? 1 : 0);
+}
 
 // shifts == NULL: one search per window with the uniform shift a.freq_shift0, results to a.toa / a.peak.  Else n_shifts
 // searches per window, results to toa / peak [n_shifts][n].  cudaErrorNotSupported: geometry or arguments outside what
@@ -458,7 +463,7 @@ cudaError_t launch_fcch_fft(const FcchArgs &a, const float *shifts, int n_shifts
 		return e;
 	// two-block form when the window fits two overlapping 4096-point blocks (the standard 330 ms window does)
 	static const bool env_one = [] { const char *e = getenv("GMR1B200_FCCH_FFT_SPLIT"); return e && atoi(e) == 0; }();   // A/B knob
-	const bool split = !env_one && l <= FF_HOP + FF_N2 && l > FF_N2 && nc <= FF_HOP + (FF_N2 - a.len + 1);
+	const bool split = !env_one && !g_fft_one_block.load() && l <= FF_HOP + FF_N2 && l > FF_N2 && nc <= FF_HOP + (FF_N2 - a.len + 1);
 	key.tn = split ? FF_N2 : FF_N;
 	key.len = a.len;
 	key.freq = a.freq;

@@ -32,22 +32,29 @@ def test_fcch_rough(gpu_lib, oracle):
     assert same >= n - 1
 
 
-@pytest.fixture(params=["fft", "direct"])
+@pytest.fixture(params=["fft", "fft-one-block", "direct"])
 def fcch_kernel(request, gpu_lib):
-    """the coarse search through the frequency-domain kernel (csrc/fcch_fft.cu, the default) and through the
-    direct-correlation kernel (csrc/fcch_grid.cu)"""
-    prev = gpu_lib.c.gmr1b200_set_fcch_fft(1 if request.param == "fft" else 0)
+    """the coarse search through the frequency-domain kernel (csrc/fcch_fft.cu, the default: two 4096-point blocks for
+    the standard window), through its one-block form (8192 points) and through the direct-correlation kernel
+    (csrc/fcch_grid.cu)"""
+    prev = gpu_lib.c.gmr1b200_set_fcch_fft({"fft": 1, "fft-one-block": 2, "direct": 0}[request.param])
     yield request.param
     gpu_lib.c.gmr1b200_set_fcch_fft(prev)
 
 
-@pytest.mark.parametrize("grid", [[0.0, 0.27, -0.27, 0.54, -0.54], [0.1], [-0.2, 0.0], [0.05, 0.1, 0.15, -0.15]])
-def test_fcch_rough_grid(gpu_lib, oracle, grid, fcch_kernel):
+@pytest.mark.parametrize("grid,L", [([0.0, 0.27, -0.27, 0.54, -0.54], 30888 - 4 * 37), ([0.1], 30888 - 4 * 37),
+                                    ([-0.2, 0.0], 30888 - 4 * 37), ([0.05, 0.1, 0.15, -0.15], 30888 - 4 * 37),
+                                    # window lengths either side of the two-block form of the frequency-domain kernel
+                                    # (4097 .. 7808 decimated samples): 7808 (its last), 7809 and 8190 (one block of 8192),
+                                    # 4098 (its first, block 1 almost empty), 4000 (one block)
+                                    ([0.0, 0.2], 4 * 7808), ([0.0, -0.2], 4 * 7809 + 3), ([0.1], 4 * 8190),
+                                    ([0.0, 0.27, -0.27], 4 * 4098 + 1), ([0.27], 4 * 4000)])
+def test_fcch_rough_grid(gpu_lib, oracle, grid, L, fcch_kernel):
     """gmr1b200_fcch_rough_grid_batch: every shift of the grid answers what gmr1_fcch_rough (src/sdr/fcch.c:211)
     answers for that freq_shift on the same window - paired (+-f), unpaired and zero shifts, ragged window
-    lengths (the last round of outputs partly empty), host and strided windows; both kernels."""
+    lengths (the last round of outputs partly empty), host and strided windows; all kernels."""
     rng = np.random.default_rng(131 + len(grid))
-    n, L = 10, 30888 - 4 * 37
+    n = 10
     stride = L + 24
     pos = rng.integers(600, L - 1200, n)
     cfo = rng.choice(np.array(grid, np.float64), n) * -1.0 + rng.uniform(-0.05, 0.05, n)
@@ -74,7 +81,7 @@ def test_fcch_rough_grid(gpu_lib, oracle, grid, fcch_kernel):
                  None)
     assert (t1 == toa[0]).all() and np.allclose(p1, peak[0], rtol=1e-4)
     # the other kernel on the same windows: same positions (rounding ties aside), same window energies
-    other = gpu_lib.c.gmr1b200_set_fcch_fft(0 if fcch_kernel == "fft" else 1)
+    other = gpu_lib.c.gmr1b200_set_fcch_fft(0 if fcch_kernel.startswith("fft") else 1)
     try:
         toa2 = np.full((len(grid), n), -1, np.int32)
         peak2 = np.zeros((len(grid), n), np.float32)
