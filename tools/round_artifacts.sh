@@ -18,7 +18,7 @@ ncu --set full --import-source on --clock-control none -k regex:"demod_|decode_t
 	python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-configs --no-sweep --no-wideband --min-seconds 0 --streams 1 > /dev/null 2>&1
 ncu --set full --import-source on --clock-control none -k regex:"pfb_|resamp_kernel" -s 4 -c 2 -f -o gpurun_out/${TAG}_full_chan \
 	python tools/bench_chan.py --reps 2 > /dev/null 2>&1
-ncu --set full --import-source on --clock-control none --kernel-name-base demangled -k regex:"fcch_fft_kernel<\(bool\)1>|fcch_fft_kernel<true>" -c 1 -f -o gpurun_out/${TAG}_full_grid \
+ncu --set full --import-source on --clock-control none --kernel-name-base demangled -k regex:"fcch_fft_kernel<\(bool\)1|fcch_fft_kernel<true" -c 1 -f -o gpurun_out/${TAG}_full_grid \
 	python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-sweep --no-wideband --min-seconds 0 > /dev/null 2>&1
 python tools/ncu_summary.py gpurun_out/${TAG}_full.ncu-rep gpurun_out/${TAG}_full_chan.ncu-rep gpurun_out/${TAG}_full_grid.ncu-rep > gpurun_out/${TAG}_ncu_full_summary.csv
 rm -f gpurun_out/${TAG}_full.ncu-rep gpurun_out/${TAG}_full_chan.ncu-rep gpurun_out/${TAG}_full_grid.ncu-rep
