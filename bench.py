@@ -363,7 +363,7 @@ def burst_rows(own, per):
     return (np.asarray(own)[:, None] * per + np.arange(per)[None, :]).reshape(-1)
 
 
-def run_wideband(L, torch, dev, n_arfcn, per_arfcn, steps, seed=4242, world=1, dist=None, shared=False, rank=0):
+def run_wideband(L, torch, dev, n_arfcn, per_arfcn, steps, seed=4242, world=1, dist=None, shared=False, rank=0, fmt=1):
     """SURVEY 8f N3 in front of the headline workload: the SAME receive work (one FCCH acquisition per ARFCN + per_arfcn
     BCCH / DC6 bursts per ARFCN, demod + decode), but the input is ONE wideband recording of all ARFCNs (int16 I/Q at
     n_arfcn x 31.25 kS/s, what an SDR front end delivers) instead of one 4x-oversampled complex-float stream per ARFCN:
@@ -374,8 +374,11 @@ def run_wideband(L, torch, dev, n_arfcn, per_arfcn, steps, seed=4242, world=1, d
     1 / world time slice of it in pinned host memory): per step every rank copies its slice to its GPU, an NCCL
     all-gather over NVLink gives every GPU the whole recording - the one real exchange step of this system, SURVEY 8f
     N3 - every GPU runs the bank and resamples / acquires / demodulates / decodes ITS ARFCNs (a mod world == rank):
-    strong scaling of one capture."""
+    strong scaling of one capture.
+    fmt: 1 = int16 I/Q (the default), 2 = int8 I/Q (8-bit front ends: a quarter of the complex-float bytes per sample)."""
     import ctypes
+    assert fmt in (1, 2) and not (shared and fmt != 1)
+    wdt, sbytes = (torch.int16, 4) if fmt == 1 else (torch.int8, 2)
     ev = lambda: torch.cuda.Event(enable_timing=True)
     n_b = {"bcch": per_arfcn // 2, "dc6": per_arfcn - per_arfcn // 2}
     lead = 64
@@ -417,15 +420,15 @@ def run_wideband(L, torch, dev, n_arfcn, per_arfcn, steps, seed=4242, world=1, d
                d(pr["cfo"]), 0.0, d(pr["phase"]), 0.0, None, 200.0, None, 1.0, seed, streams, n_arfcn * slen, d(o), 0, n, None)
         par[kind], ofs[kind] = pr, o
     n_wide = ((slen - 3) * 625 * n_arfcn) // (468 * SPS)
-    wide = torch.empty((n_wide, 2), dtype=torch.int16, device=dev)
+    wide = torch.empty((n_wide, 2), dtype=wdt, device=dev)
     esn0, gain = 15.0, 0.5 / (4.0 * np.sqrt(n_arfcn))
     torch.cuda.synchronize()
     g0 = time.perf_counter()
-    L.call("gmr1b200_synth_wideband", h.value, streams, slen, slen, None, n_arfcn, esn0, gain, seed, wide, 1, n_wide, None)
+    L.call("gmr1b200_synth_wideband", h.value, streams, slen, slen, None, n_arfcn, esn0, gain, seed, wide, fmt, n_wide, None)
     torch.cuda.synchronize()
     gen_s = time.perf_counter() - g0
     del streams
-    peak_i16 = int(wide.abs().max())
+    peak_i16 = int(wide.to(torch.int32).abs().max())
     shared = shared and world > 1
     share = capture_shares(n_wide, n_arfcn, world if shared else 1, rank if shared else 0)
     own = share["own"]                     # the ARFCNs this rank receives
@@ -440,7 +443,7 @@ def run_wideband(L, torch, dev, n_arfcn, per_arfcn, steps, seed=4242, world=1, d
         wide_full[:n_wide].copy_(wide)
         wide = wide_full[:n_wide]
     else:
-        host_wide = torch.empty((n_wide, 2), dtype=torch.int16).pin_memory()
+        host_wide = torch.empty((n_wide, 2), dtype=wdt).pin_memory()
         host_wide.copy_(wide)
     n_out = int(L.c.gmr1b200_chan_out_len(h, n_wide))
     out = torch.empty((n_own, n_out, 2), dtype=torch.float32, device=dev)
@@ -468,7 +471,7 @@ def run_wideband(L, torch, dev, n_arfcn, per_arfcn, steps, seed=4242, world=1, d
         marks = []
         mark = lambda name: (marks.append((name, ev())), marks[-1][1].record(st)) if timers is not None else None
         mark("start")
-        L.call("gmr1b200_channelize", h.value, wide if src is None else src, 1, n_wide, own_idx, n_own, out, n_out, sh)
+        L.call("gmr1b200_channelize", h.value, wide if src is None else src, fmt, n_wide, own_idx, n_own, out, n_out, sh)
         mark("channelize")
         L.call("gmr1b200_fcch_acquire_batch", 0, out, n_own * n_out, f_ofs, 0, FCCH_WIN, SPS, f_toa, f_align, f_ferr, n_own, sh)
         mark("fcch")
@@ -551,7 +554,7 @@ def run_wideband(L, torch, dev, n_arfcn, per_arfcn, steps, seed=4242, world=1, d
 
         def issue(S):
             q = S["st"].cuda_stream
-            L.call("gmr1b200_channelize", h.value, host_wide, 1, n_wide, own_idx, n_own, S["out"], n_out, q)
+            L.call("gmr1b200_channelize", h.value, host_wide, fmt, n_wide, own_idx, n_own, S["out"], n_out, q)
             L.call("gmr1b200_fcch_acquire_batch", 0, S["out"], n_own * n_out, f_ofs, 0, FCCH_WIN, SPS, S["f_toa"], S["f_align"],
                    S["f_ferr"], n_own, q)
             for kind in ("bcch", "dc6"):
@@ -583,7 +586,7 @@ def run_wideband(L, torch, dev, n_arfcn, per_arfcn, steps, seed=4242, world=1, d
         same = all(bool((slots[1]["res"][k]["h_l2"] == res[k]["h_l2"]).all()) and bool((slots[1]["res"][k]["h_crc"] == res[k]["h_crc"]).all())
                    for k in res)
         pipe = {"value": world * sum(n_arfcn * n_b[kk] for kk in n_b) / (pipe_ms * 1e-3), "unit": "bursts/s", "ms_per_recording": pipe_ms,
-                "recordings_in_flight": 2, "h2d_gbs_per_gpu": n_wide * 4 / (pipe_ms * 1e-3) / 1e9, "same_results_in_both_slots": same,
+                "recordings_in_flight": 2, "h2d_gbs_per_gpu": n_wide * sbytes / (pipe_ms * 1e-3) / 1e9, "same_results_in_both_slots": same,
                 "how": "the e2e step issued for recording i + 1 before recording i is waited for (own stream and buffers each)"}
         del slots
     # what came out: payloads against what was sent, FCCH positions against where the chirps were put
@@ -595,11 +598,12 @@ def run_wideband(L, torch, dev, n_arfcn, per_arfcn, steps, seed=4242, world=1, d
     toa_err = h_f[0].numpy() - (fpos[own] + info.delay_out - dly)
     jobs = 1 if shared else world          # recordings processed per step by the whole job
     n_steps = n_wide // (n_arfcn // 2)
-    bank_bytes = n_wide * 4 + n_steps * n_arfcn * 8
+    bank_bytes = n_wide * sbytes + n_steps * n_arfcn * 8
     rs_bytes = n_steps * n_own * 8 + n_own * n_out * 8
     L.c.gmr1b200_chan_destroy(h)
     return {
-        "what": "the headline receive work fed from ONE wideband int16 recording of all ARFCNs through the GPU channeliser "
+        "iq_format": "int16" if fmt == 1 else "int8",
+        "what": "the headline receive work fed from ONE wideband int16 / int8 recording of all ARFCNs through the GPU channeliser "
                 "(replaces the PFB mode of utils/gmr1_rx_sdr.py) instead of one complex-float stream per ARFCN",
         "n_gpus": world, "scaling": "strong" if shared else "weak",
         "per_gpu": ("ONE recording for the whole job: every rank copies a 1 / n_gpus time slice from pinned host memory, NCCL "
@@ -610,10 +614,10 @@ def run_wideband(L, torch, dev, n_arfcn, per_arfcn, steps, seed=4242, world=1, d
         "arfcns": n_arfcn, "bursts": nb, "fcch_acquisitions": n_arfcn, "recording_seconds": n_wide / info.samp_rate,
         "wideband_rate_msps": info.samp_rate / 1e6, "bank_taps": info.n_taps, "rrc_taps": info.n_taps_resamp,
         "e2e": {"value": jobs * nb / (e2e_ms * 1e-3), "unit": "bursts/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": int(host_wide.numel() * 2), "d2h_bytes_per_step": int(nb_own * 28 + n_own * 8),
+                "h2d_bytes_per_step": int(host_wide.numel() * sbytes // 2), "d2h_bytes_per_step": int(nb_own * 28 + n_own * 8),
                 "nvlink_allgather_bytes_per_gpu": int(wide_full.numel() * 2) if shared else 0,
                 "per_arfcn_cf32_bytes_equivalent": int(n_arfcn * n_out * 8),
-                "h2d_gbs_per_gpu": n_wide * 4 / (e2e_ms * 1e-3) / 1e9,
+                "h2d_gbs_per_gpu": n_wide * sbytes / (e2e_ms * 1e-3) / 1e9,
                 "how": "pinned host int16 recording -> gmr1b200_channelize (H2D in pieces under the bank + resampler "
                        "kernels) -> fcch_acquire + demod + decode on offsets into the device-resident streams -> host "
                        "L2 / CRC / alignments"},
@@ -624,7 +628,7 @@ def run_wideband(L, torch, dev, n_arfcn, per_arfcn, steps, seed=4242, world=1, d
                             "realtime_factor": (n_wide / info.samp_rate) / (dev_ms * 1e-3), "launches_per_step": launches},
         "crc_ok_frac": ok / nb_own, "payload_correct_frac": good / nb_own, "crc_ok_but_payload_wrong": wrong,
         "fcch_found_frac": float((np.abs(toa_err) <= 2).mean()),
-        "esn0_db": esn0, "int16_peak": peak_i16, "generation_s": gen_s,
+        "esn0_db": esn0, "int16_peak" if fmt == 1 else "int8_peak": peak_i16, "generation_s": gen_s,
     }
 
 
@@ -1047,6 +1051,12 @@ def run_gpu_arm(args):
         torch.cuda.empty_cache()
         wideband = run_wideband(L, torch, dev, args.arfcns, args.bursts_per_arfcn, min(args.steps, 5), seed=4242 + rank,
                                 world=world, dist=dist if world > 1 else None)
+        if world == 1:                     # the same recording as int8 I/Q (8-bit front ends): half the bytes again
+            torch.cuda.empty_cache()
+            w8 = run_wideband(L, torch, dev, args.arfcns, args.bursts_per_arfcn, min(args.steps, 5), seed=4242 + rank, fmt=2)
+            wideband["int8_recording"] = {k: w8[k] for k in ("iq_format", "e2e", "e2e_pipelined", "device_resident", "crc_ok_frac",
+                                                             "payload_correct_frac", "crc_ok_but_payload_wrong",
+                                                             "fcch_found_frac", "int8_peak")}
         if world > 1:                      # and ONE recording shared by all GPUs (all-gather over NVLink): strong scaling
             torch.cuda.empty_cache()
             wideband["shared_capture"] = run_wideband(L, torch, dev, args.arfcns, args.bursts_per_arfcn, min(args.steps, 5),

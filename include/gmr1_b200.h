@@ -560,7 +560,8 @@ int gmr1b200_chan_taps(void *plan, float *taps, int max_taps, float *taps_resamp
 /* output samples per channel for a recording of n_wide samples */
 int64_t gmr1b200_chan_out_len(void *plan, int64_t n_wide);
 /* wide: n_wide complex samples from the start of the recording (zeros are assumed in front of it), iq_format 0 =
- * complex float32, 1 = interleaved int16 I/Q scaled by 1 / 32768 (what SDR front ends deliver; half the bytes);
+ * complex float32, 1 = interleaved int16 I/Q scaled by 1 / 32768 (what SDR front ends deliver; half the bytes), 2 =
+ * interleaved int8 I/Q scaled by 1 / 128 (8-bit front ends; a quarter of the bytes);
  * chan_idx [n_wanted] bank channels wanted, NULL = channels 0 .. n_wanted-1;
  * out [n_wanted][out_stride] complex float (interleaved), out_stride >= gmr1b200_chan_out_len(n_wide) samples.
  * Host or device pointers.  A HOST recording travels in up to 16 pieces on a copy stream of the plan while the bank

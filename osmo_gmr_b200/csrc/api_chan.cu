@@ -171,7 +171,7 @@ int gmr1b200_channelize(void *plan, const void *wide, int iq_format, int64_t n_w
                         float *out, int64_t out_stride, void *stream)
 {
 	Plan *pl = (Plan *)plan;
-	if (!pl || !wide || !out || n_wide < 0 || n_wanted < 0 || iq_format < 0 || iq_format > 1)
+	if (!pl || !wide || !out || n_wide < 0 || n_wanted < 0 || iq_format < 0 || iq_format > 2)
 		return set_err(-EINVAL, "channelize: bad argument");
 	ChanPlan &p = pl->p;
 	if (n_wanted == 0 || n_wide == 0)
@@ -187,7 +187,7 @@ int gmr1b200_channelize(void *plan, const void *wide, int iq_format, int64_t n_w
 	Plan::Feed *feed = nullptr;
 	int rows_max = 0, span_max = 0, to = 64;
 	const bool wide_on_host = host_pointer(wide);
-	const size_t samp_bytes = iq_format == 0 ? sizeof(float2) : 2 * sizeof(int16_t);
+	const size_t samp_bytes = iq_format == 0 ? sizeof(float2) : iq_format == 2 ? 2 * sizeof(int8_t) : 2 * sizeof(int16_t);
 	// chunks: a host recording travels in up to 16 pieces (>= 2 MB each) so that the bank and the resampler of piece c
 	// run under the copy of piece c + 1; a device-resident recording is one piece
 	std::vector<int64_t> cut_m, cut_n;     // piece c makes steps [cut_m[c], cut_m[c+1]) and outputs [cut_n[c], cut_n[c+1])
@@ -409,7 +409,7 @@ int gmr1b200_chan_stream_push(void *state, const void *wide, int iq_format, int6
                               int64_t *n_out, void *stream)
 {
 	ChanStream *cs = (ChanStream *)state;
-	if (!cs || !n_out || n_wide < 0 || (n_wide && !wide) || iq_format < 0 || iq_format > 1)
+	if (!cs || !n_out || n_wide < 0 || (n_wide && !wide) || iq_format < 0 || iq_format > 2)
 		return set_err(-EINVAL, "chan_stream_push: bad argument");
 	if (cs->fmt >= 0 && cs->fmt != iq_format)
 		return set_err(-EINVAL, "chan_stream_push: the sample format of a stream cannot change");
@@ -423,7 +423,7 @@ int gmr1b200_chan_stream_push(void *state, const void *wide, int iq_format, int6
 	cs->fmt = iq_format;
 	ChanPlan &p = cs->pl->p;
 	const int N = p.n_chans, D = N / 2, P = p.taps_per_branch;
-	const size_t sb = iq_format == 0 ? sizeof(float2) : 2 * sizeof(int16_t);
+	const size_t sb = iq_format == 0 ? sizeof(float2) : iq_format == 2 ? 2 * sizeof(int8_t) : 2 * sizeof(int16_t);
 	cudaStream_t st = (cudaStream_t)stream;
 	ChanPlan::Dev *d = nullptr;
 	{
@@ -596,7 +596,7 @@ int gmr1b200_synth_wideband(void *plan, const float *streams, int64_t stream_str
 {
 	Plan *pl = (Plan *)plan;
 	if (!pl || !streams || !wide || n_streams < 1 || stream_len < 4 || stream_stride < stream_len || n_wide < 0 ||
-	    iq_format < 0 || iq_format > 1)
+	    iq_format < 0 || iq_format > 2)
 		return set_err(-EINVAL, "synth_wideband: bad argument");
 	ChanPlan &p = pl->p;
 	ChanPlan::Dev *d = nullptr;
@@ -617,7 +617,8 @@ int gmr1b200_synth_wideband(void *plan, const float *streams, int64_t stream_str
 	a.twiddle = d->twiddle;
 	a.sigma = esn0_db >= 100.0f ? 0.0f : sqrtf(exp10f(-esn0_db / 10.0f) * (float)(p.samp_rate / 23400.0) * 0.5f);
 	a.gain = gain; a.seed = seed;
-	a.wide = iq_format == 0 ? (void *)s.out((float *)wide, (size_t)n_wide * 2) : (void *)s.out((int16_t *)wide, (size_t)n_wide * 2);
+	a.wide = iq_format == 0 ? (void *)s.out((float *)wide, (size_t)n_wide * 2) :
+	         iq_format == 2 ? (void *)s.out((int8_t *)wide, (size_t)n_wide * 2) : (void *)s.out((int16_t *)wide, (size_t)n_wide * 2);
 	a.n_wide = n_wide;
 	if (s.failed())
 		return s.finish(cudaSuccess, "synth_wideband: staging");

@@ -37,6 +37,10 @@ template <int FMT> __device__ __forceinline__ float2 load_wide(const void *x, in
 		return make_float2(0.0f, 0.0f);
 	if (FMT == 0)
 		return __ldg(reinterpret_cast<const float2 *>(x) + i);
+	if (FMT == 2) {
+		const char2 v = __ldg(reinterpret_cast<const char2 *>(x) + i);
+		return make_float2((float)v.x * (1.0f / 128.0f), (float)v.y * (1.0f / 128.0f));
+	}
 	const short2 v = __ldg(reinterpret_cast<const short2 *>(x) + i);
 	return make_float2((float)v.x * (1.0f / 32768.0f), (float)v.y * (1.0f / 32768.0f));
 }
@@ -179,6 +183,10 @@ template <int FMT> __device__ __forceinline__ float2 load_wide_raw(const void *x
 {
 	if (FMT == 0)
 		return __ldg(reinterpret_cast<const float2 *>(x) + i);
+	if (FMT == 2) {
+		const char2 v = __ldg(reinterpret_cast<const char2 *>(x) + i);
+		return make_float2((float)v.x, (float)v.y);      // 1 / 128 is on the taps
+	}
 	const short2 v = __ldg(reinterpret_cast<const short2 *>(x) + i);
 	return make_float2((float)v.x, (float)v.y);          // 1 / 32768 is on the taps
 }
@@ -258,7 +266,7 @@ __global__ void __launch_bounds__(PFB_THREADS) pfb_fast_kernel(const PfbArgs a)
 	const int tid = threadIdx.x;
 	const int64_t m_cta = a.m_begin + (int64_t)blockIdx.x * T;
 	const bool interior = (m_cta - 2 * (PFB_P - 1)) * D - (N - 1) >= 0 && (m_cta + T - 1) * D < a.n_wide;
-	const float scale = FMT == 0 ? 1.0f : 1.0f / 32768.0f;
+	const float scale = FMT == 0 ? 1.0f : FMT == 2 ? 1.0f / 128.0f : 1.0f / 32768.0f;
 
 	// ---- branch sums: item = (branch p, group of 8 steps)
 #pragma unroll 1
@@ -526,6 +534,10 @@ __global__ void __launch_bounds__(256) wide_synth_kernel(const WideSynthArgs a)
 		xi *= a.gain;
 		if (FMT == 0) {
 			reinterpret_cast<float2 *>(a.wide)[t] = make_float2(xr, xi);
+		} else if (FMT == 2) {
+			const float sr = fminf(fmaxf(rintf(xr * 128.0f), -128.0f), 127.0f);
+			const float si = fminf(fmaxf(rintf(xi * 128.0f), -128.0f), 127.0f);
+			reinterpret_cast<char2 *>(a.wide)[t] = make_char2((signed char)sr, (signed char)si);
 		} else {
 			const float sr = fminf(fmaxf(rintf(xr * 32768.0f), -32768.0f), 32767.0f);
 			const float si = fminf(fmaxf(rintf(xi * 32768.0f), -32768.0f), 32767.0f);
@@ -550,8 +562,8 @@ int pfb_groups(int n_chans)
 template <int LOG2N> cudaError_t launch_pfb_fast(const PfbArgs &a, int fmt, cudaStream_t st, int dev)
 {
 	typedef PfbFast<LOG2N> K;
-	static std::atomic<int> attr_done[64][2];
-	auto *fn = fmt == 0 ? pfb_fast_kernel<LOG2N, 0> : pfb_fast_kernel<LOG2N, 1>;
+	static std::atomic<int> attr_done[64][3];
+	auto *fn = fmt == 0 ? pfb_fast_kernel<LOG2N, 0> : fmt == 2 ? pfb_fast_kernel<LOG2N, 2> : pfb_fast_kernel<LOG2N, 1>;
 	{
 		GMR1_INIT_LOCK();
 		if (dev >= 64 || !attr_done[dev][fmt].load()) {
@@ -600,8 +612,8 @@ cudaError_t launch_pfb(const PfbArgs &a0, int fmt, cudaStream_t st)
 	const size_t smem = 2 * (size_t)T * a.n_chans * sizeof(float2);
 	if (smem > 200 * 1024)
 		return cudaErrorNotSupported;
-	static std::atomic<size_t> attr_max[64][2];
-	auto *fn = fmt == 0 ? pfb_kernel<0> : pfb_kernel<1>;
+	static std::atomic<size_t> attr_max[64][3];
+	auto *fn = fmt == 0 ? pfb_kernel<0> : fmt == 2 ? pfb_kernel<2> : pfb_kernel<1>;
 	{
 		GMR1_INIT_LOCK();
 		if (dev < 64 && attr_max[dev][fmt].load() < smem) {
@@ -676,6 +688,8 @@ cudaError_t launch_wide_synth(const WideSynthArgs &a, int fmt, cudaStream_t st)
 	const unsigned grid = (unsigned)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
 	if (fmt == 0)
 		wide_synth_kernel<0><<<grid, 256, smem, st>>>(a);
+	else if (fmt == 2)
+		wide_synth_kernel<2><<<grid, 256, smem, st>>>(a);
 	else
 		wide_synth_kernel<1><<<grid, 256, smem, st>>>(a);
 	return cudaGetLastError();

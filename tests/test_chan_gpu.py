@@ -138,7 +138,7 @@ def test_host_recording_travels_in_pieces(gpu_lib):
     L.c.gmr1b200_chan_destroy(h)
 
 
-@pytest.mark.parametrize("n_chans,fmt", [(64, 1), (12, 0), (256, 1)])
+@pytest.mark.parametrize("n_chans,fmt", [(64, 1), (12, 0), (256, 1), (128, 2), (12, 2)])
 def test_streaming_blocks_equal_the_whole_recording(gpu_lib, n_chans, fmt):
     """gmr1b200_chan_stream_push over ragged blocks (single samples, fractions of a bank step, odd sizes, long blocks,
     an empty push) delivers, concatenated, bit for bit what gmr1b200_channelize makes of the whole recording: fast and
@@ -149,6 +149,8 @@ def test_streaming_blocks_equal_the_whole_recording(gpu_lib, n_chans, fmt):
     n_wide = n_chans * 700 + 13
     if fmt == 1:
         x = rng.integers(-20000, 20000, (n_wide, 2), dtype=np.int16)
+    elif fmt == 2:
+        x = rng.integers(-128, 128, (n_wide, 2), dtype=np.int8)
     else:
         x = (rng.standard_normal(n_wide) + 1j * rng.standard_normal(n_wide)).astype(np.complex64)
     h = make_plan(L, n_chans)
@@ -194,6 +196,33 @@ def test_streaming_blocks_equal_the_whole_recording(gpu_lib, n_chans, fmt):
     L.c.gmr1b200_chan_destroy(h)
 
 
+@pytest.mark.parametrize("n_chans", [32, 1024, 12])
+def test_int8_recordings(gpu_lib, n_chans):
+    """iq_format 2 (interleaved int8 I/Q scaled by 1 / 128): the same samples as floats, through the fast and the generic
+    bank, host and device memory (streamed blocks: test_streaming_blocks_equal_the_whole_recording)"""
+    import torch
+    L = gpu_lib
+    rng = np.random.default_rng(19 + n_chans)
+    n_wide = n_chans * (400 if n_chans < 1024 else 150) + 7
+    xi = rng.integers(-128, 128, (n_wide, 2), dtype=np.int8)
+    xf = (xi.astype(np.float32) / 128.0).view(np.complex64)[:, 0]
+    h = make_plan(L, n_chans)
+    chans = [n_chans - 1, 0, 7, n_chans // 2]
+    a = channelize(L, h, xi, 2, chans)
+    b = channelize(L, h, xf, 0, chans)
+    assert np.abs(a - b).max() <= 1e-6 * np.abs(b).max()     # the int8 scale rides on the taps of the fast bank: same up to rounding
+    if n_chans == 12:
+        assert np.array_equal(a, b)                          # generic bank: bit for bit
+    dx = torch.from_numpy(xi).cuda()
+    n_out = L.c.gmr1b200_chan_out_len(h, n_wide)
+    dout = torch.zeros((len(chans), n_out, 2), dtype=torch.float32, device="cuda")
+    didx = torch.tensor(chans, dtype=torch.int32, device="cuda")
+    L.call("gmr1b200_channelize", h.value, dx, 2, n_wide, didx, len(chans), dout, n_out, None)
+    torch.cuda.synchronize()
+    assert np.array_equal(dout.cpu().numpy().view(np.complex64)[..., 0], a)
+    L.c.gmr1b200_chan_destroy(h)
+
+
 def test_int16_recordings_and_device_pointers(gpu_lib):
     import torch
     L = gpu_lib
@@ -219,7 +248,7 @@ def test_int16_recordings_and_device_pointers(gpu_lib):
     out = np.zeros((1, n_out, 2), np.float32)
     for args in ((h.value, xi, 1, n_wide, np.array([32], np.int32), 1, out, n_out, None),
                  (h.value, xi, 1, n_wide, np.array([3], np.int32), 1, out, n_out - 1, None),
-                 (h.value, xi, 2, n_wide, np.array([3], np.int32), 1, out, n_out, None)):
+                 (h.value, xi, 3, n_wide, np.array([3], np.int32), 1, out, n_out, None)):
         with pytest.raises(Exception) as e:
             L.call("gmr1b200_channelize", *args)
         assert f"rc={-errno.EINVAL}" in str(e.value)
