@@ -1,6 +1,7 @@
 // api_common.h - plumbing shared by the C-ABI translation units: error reporting, lazy device
 // init, and the Stage helper that lets every entry point take host OR device pointers.
 #pragma once
+#include <stdlib.h>
 #include <cuda_runtime.h>
 #include <errno.h>
 #include <stdint.h>
@@ -238,6 +239,13 @@ private:
 			if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
 				uint64_t thr = UINT64_MAX;
 				cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+				// no reuse of a block whose free is still pending on ANOTHER stream: the runtime would make the
+				// allocating stream wait for that stream's work, which serialises callers that keep several
+				// streams busy (two wideband recordings in flight ran at half speed that way); the pool grows by
+				// a block per busy stream instead.  GMR1B200_POOL_INTERNAL_DEPS=1 restores the default.
+				const char *ev = getenv("GMR1B200_POOL_INTERNAL_DEPS");
+				int dep = ev && atoi(ev) != 0 ? 1 : 0;
+				cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowInternalDependencies, &dep);
 			}
 		}
 		void *d = nullptr;
